@@ -1,0 +1,43 @@
+"""Loader for the fixtures written by tests/golden/make_golden.py."""
+import ast
+import glob
+import os
+
+import numpy as np
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def names():
+    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+
+
+def load(name):
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    meta = ast.literal_eval(str(z["meta"]))
+    nc = int(z["n_cores"])
+    if bool(z["x_is_list"]):
+        x = [z[f"x_{i}"] for i in range(sum(1 for k in z.files if k.startswith("x_") and k != "x_is_list"))]
+    else:
+        x = z["x"]
+    ups = []
+    for ui in range(int(z["n_updates"])):
+        NS, k, eps, loss = z[f"u{ui}_scal"]
+        u = {"NS": int(NS), "k": int(k), "eps": float(eps), "loss": float(loss),
+             "A": z[f"u{ui}_A"], "b": z[f"u{ui}_b"], "step": z[f"u{ui}_step"],
+             "before": [z[f"u{ui}_before_{i}"] for i in range(nc)],
+             "after": [z[f"u{ui}_after_{i}"] for i in range(nc)]}
+        for key in ("L", "R"):
+            if f"u{ui}_{key}" in z.files:
+                u[key] = z[f"u{ui}_{key}"]
+        ups.append(u)
+    return {"meta": meta, "x": x, "y": z["y"], "cores0": [z[f"cores0_{i}"] for i in range(nc)],
+            "updates": ups, "pred": z["pred"], "ok": bool(z["ok"])}
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    d = np.linalg.norm((a - b).ravel())
+    n = np.linalg.norm(b.ravel())
+    return d / n if n > 0 else d
