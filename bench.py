@@ -1,0 +1,427 @@
+#!/usr/bin/env python
+"""Benchmark of the per-site Gauss-Newton / ALS sweep (BASELINE.json metric: GN site-updates/s).
+
+    python bench.py --gpus N --steps K --warmup W [--workload cfg5a] [--n ROWS_PER_GPU] [--gram-mode tf32x3]
+    python bench.py --impl reference ...        # the reference's algorithm on the host cores (oracle port)
+
+A step is one full sweep (left-to-right + right-to-left half) of ``accumulating_swipe`` over the
+rank's shard of synthetic rows (U(-1,1) features, smooth teacher target, seeds fixed).  Weak scaling:
+rows per GPU are fixed, ranks shard the samples and all-reduce the per-site Gram.
+Rank 0 prints ONE JSON line.  See DESIGN.md §Measurement for how every field is produced.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+torch.set_default_dtype(torch.float64)
+
+# name -> model / data shape (BASELINE.json configs; SURVEY.md §8 "Config sizes")
+WORKLOADS = {
+    "cfg1": dict(kind="tt", sites=3, r=6, features=8, bias=True, basis=None, C=1, n=4177, constrict=True, perturb=True,
+                 batch_size=512, desc="TT poly-mode abalone-shaped N=4177 F=8(+1) r=6 3 cores"),
+    "cfg2": dict(kind="cpd", sites=5, r=100, features=8, bias=True, basis=None, C=1, n=20640, batch_size=-1,
+                 desc="CPD rank 100 california_housing-shaped N=20640 F=8(+1) 5 factors"),
+    "cfg3": dict(kind="tt", sites=90, r=24, features=90, bias=False, basis="sin-cos", C=1, n=515345, constrict=True,
+                 perturb=False, batch_size=512, orthonormalize=True, desc="TNML sin-cos year-shaped N=515345 F=90 r=24 90 sites"),
+    "cfg5a": dict(kind="tt", sites=5, r=38, features=28, bias=True, basis=None, C=1, n=1250000, constrict=False,
+                  perturb=False, batch_size=-1, desc="TT poly-mode higgs-shaped F=28(+1) r=38 5 cores (degree 5), P=41876"),
+    "cfg5b": dict(kind="tt", sites=28, r=38, features=28, bias=False, basis="polynomial", degree=5, C=1, n=1250000,
+                  constrict=True, perturb=False, batch_size=-1, orthonormalize=True,
+                  desc="TNML polynomial degree 5 higgs-shaped F=28 r=38 28 sites, P<=8664"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="cfg5a", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=None, help="rows per GPU (default: the workload's)")
+    ap.add_argument("--gram-mode", default="fp64", choices=["fp64", "tf32", "tf32x3"])
+    ap.add_argument("--eps", type=float, default=1.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--ref-rows", type=int, default=None)
+    return ap.parse_args()
+
+
+def make_data(wl, n, seed, device):
+    """Synthetic rows of the workload's shape: X ~ U(-1,1), y = smooth teacher + noise."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    F = wl["features"]
+    X = torch.rand((n, F), generator=g, dtype=torch.float64) * 2 - 1
+    w1 = torch.randn((F, 1), generator=g, dtype=torch.float64) / F ** 0.5
+    w2 = torch.randn((F, 1), generator=g, dtype=torch.float64) / F ** 0.5
+    y = torch.tanh(X @ w1) + 0.5 * (X @ w2) ** 2 + 0.1 * torch.randn((n, 1), generator=g, dtype=torch.float64)
+    if wl["bias"]:
+        X = torch.cat([X, torch.ones((n, 1), dtype=torch.float64)], dim=1)
+    return X.to(device), y.to(device)
+
+
+def build_model(wl, device, gram_mode):
+    import tensornetworksfork_b200 as tnb
+    f = wl["features"] + 1 if wl["bias"] else (2 if wl["basis"] == "sin-cos" else wl.get("degree", 3) + 1)
+    if wl["kind"] == "cpd":
+        layer = tnb.CPDLayer(wl["sites"], wl["r"], f, output_shape=(wl["C"],), seed=42)
+    else:
+        layer = tnb.TensorTrainLayer(wl["sites"], wl["r"], f, output_shape=wl["C"], constrict_bond=wl["constrict"],
+                                     perturb=wl["perturb"], seed=42)
+    layer.to(device)
+    layer.tensor_network.gram_mode = gram_mode
+    return layer, f
+
+
+def wrap_input(wl, X):
+    import tensornetworksfork_b200 as tnb
+    if wl["basis"] is None:
+        return X
+    return tnb.MappedInput(X, kind=wl["basis"], degree=wl.get("degree", 3))
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            p = [t.strip() for t in ln.split(",")]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1]))
+                mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, p[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+class KernelTimer:
+    """CUDA-event timing of individual ops.* calls on torch's current stream (the launching stream)."""
+
+    def __init__(self, ops, names):
+        self.ops = ops
+        self.names = names
+        self.orig = {}
+        self.events = {n: [] for n in names}
+        self.extra = {n: [] for n in names}
+        self.enabled = False
+
+    def install(self):
+        for n in self.names:
+            self.orig[n] = getattr(self.ops, n)
+            setattr(self.ops, n, self._wrap(n))
+
+    def _wrap(self, n):
+        fn = self.orig[n]
+
+        def inner(*a, **k):
+            if not self.enabled:
+                return fn(*a, **k)
+            e0 = torch.cuda.Event(enable_timing=True)
+            e1 = torch.cuda.Event(enable_timing=True)
+            e0.record()
+            out = fn(*a, **k)
+            e1.record()
+            self.events[n].append((e0, e1))
+            self.extra[n].append((a, k))
+            return out
+
+        return inner
+
+    def totals(self):
+        return {n: [e0.elapsed_time(e1) for e0, e1 in ev] for n, ev in self.events.items()}
+
+
+def gram_flops(call):
+    """Issued multiply-adds x2 of one ops.gram call: rows * n_a*n_b*n_c pairs (the Kronecker-symmetric GEMM)."""
+    a, k = call
+    fa, fb, fc, rows = a[1], a[2], a[3], a[5]
+    npair = lambda m: m * (m + 1) // 2
+    P = fa.m * fb.m * fc.m
+    return 2.0 * rows * npair(fa.m) * npair(fb.m) * npair(fc.m), float(rows) * P * (P + 1)
+
+
+def run_sweeps(layer, x, y, wl, args, steps, counter):
+    import tensornetworksfork_b200 as tnb
+    tn = layer.tensor_network
+    loss_fn = tnb.SquareBregFunction()
+
+    def cb(NS, node):
+        counter[0] += 1
+
+    ok = tn.accumulating_swipe(x, y, loss_fn, batch_size=wl["batch_size"], num_swipes=steps, lr=1.0, method="ridge_cholesky",
+                               eps=args.eps, orthonormalize=wl.get("orthonormalize", False), block_callback=cb,
+                               model_device=layer.tensor_network.main_nodes[0].tensor.device)
+    if not ok:
+        raise RuntimeError("sweep reported a singular system")
+
+
+def bench_b200(args):
+    import torch.distributed as dist
+    import tensornetworksfork_b200 as tnb
+    from tensornetworksfork_b200 import ops
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    wl = WORKLOADS[args.workload]
+    n = args.n if args.n is not None else wl["n"]
+    layer, f = build_model(wl, dev, args.gram_mode)
+    tn = layer.tensor_network
+    X, y = make_data(wl, n, seed=1000 + rank, device=dev)
+    if world > 1:
+        tn.process_group = dist.group.WORLD
+        tn.shard_offset = rank * n
+        tn.shard_total = world * n
+    x = wrap_input(wl, X)
+    if wl.get("orthonormalize"):
+        tn.orthonormalize_left()
+
+    timer = KernelTimer(ops, ["gram", "rhs", "env_update", "predict", "cholesky_solve", "gram_expand"])
+    timer.install()
+    counter = [0]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    run_sweeps(layer, x, y, wl, args, args.warmup, counter)
+    barrier()
+    # ---- device-resident timed region
+    counter[0] = 0
+    timer.enabled = True
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    run_sweeps(layer, x, y, wl, args, args.steps, counter)
+    e1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    timer.enabled = False
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    updates = counter[0]
+    value = updates / (ms / 1e3)
+
+    # ---- end to end: host (pinned) buffers in, loss scalar out, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        Xh, yh = X.cpu().pin_memory(), y.cpu().pin_memory()
+        got = []
+        counter2 = [0]
+
+        def one_e2e():
+            xin = wrap_input(wl, Xh)
+            tn.accumulating_swipe(xin, yh, tnb.SquareBregFunction(), batch_size=wl["batch_size"], num_swipes=1, lr=1.0,
+                                  method="ridge_cholesky", eps=args.eps, orthonormalize=wl.get("orthonormalize", False),
+                                  block_callback=lambda NS, node: counter2.__setitem__(0, counter2[0] + 1),
+                                  data_device=torch.device("cpu"), model_device=dev)
+            pred = tn.forward_batch(wrap_input(wl, X[:1024]), -1)
+            got.append(float(((pred - y[:1024]) ** 2).mean().item()))      # device -> host read of the result
+
+        one_e2e()
+        barrier()
+        counter2[0] = 0
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            one_e2e()
+        barrier()
+        dt = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        e2e = {"value": counter2[0] / float(dt.item()), "unit": "site-updates/s",
+               "h2d_bytes_per_step": int(Xh.numel() * 8 + yh.numel() * 8), "d2h_bytes_per_step": 8}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tot = timer.totals()
+    gram_ms = tot["gram"]
+    launches = sum(len(v) for v in tot.values())
+    issued = algo = 0.0
+    for c in timer.extra["gram"]:
+        i_, a_ = gram_flops(c)
+        issued += i_
+        algo += a_
+    gsum = sum(gram_ms) / 1e3
+    if args.gram_mode == "fp64":
+        peak, peak_src = 40.0, "nominal B200 fp64 40 TFLOP/s (no measured fp64 peak in MEASURED_PEAKS.json)"
+    else:
+        bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak, peak_src = bf16 / 2.0, "half of the measured sustained bf16 dense peak (TF32 rate = bf16/2); " + ("measured" if peaks else "fallback")
+    mult = 3.0 if args.gram_mode == "tf32x3" else 1.0
+    achieved = issued * mult / gsum / 1e12 if gsum > 0 else 0.0
+    roofline = {"kernel": f"gram_kr3[{args.gram_mode}]", "bound": "tensor" if args.gram_mode != "fp64" else "fp64", "achieved": achieved,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                "peak_source": peak_src, "issued_flops_per_step": issued * mult / args.steps,
+                "survey_algorithmic_flops_per_step": algo / args.steps,
+                "survey_equiv_tflops": algo / gsum / 1e12 if gsum > 0 else 0.0,
+                "share_of_step": gsum / (ms / 1e3), "launches": len(gram_ms)}
+    shares = {k: sum(v) / ms for k, v in tot.items()}
+    out = {"metric": "gn_site_updates_per_s", "value": value, "unit": "site-updates/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f64" if args.gram_mode == "fp64" else f"f64+{args.gram_mode}", "data": "synthetic",
+           "config": {"workload": f"{args.workload}: {wl['desc']}", "rows_per_gpu": n, "rows_total": n * world,
+                      "site_updates_per_step": updates // max(args.steps, 1), "gram_mode": args.gram_mode, "eps": args.eps,
+                      "l2": "inputs larger than L2 (per-site streams of rows*(r_l+f+r_r)*8 B)", "parallelism": f"sample-shard x{world}"},
+           "samples_per_s": value * n * world, "roofline": roofline, "kernel_time_share": shares, "gpu_launches": launches,
+           "clocks": clk, "e2e": e2e}
+    if not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(args, wl, n * world)
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ------------------------------------------------------------------------------------------ CPU side
+def cpu_site_time(wl, rows, reps=1):
+    """Seconds the oracle port needs for the Gram+rhs+forward of every distinct site shape on `rows` rows
+    (one minibatch), and the dense solve per site, on all host threads."""
+    from oracle import tn_oracle as orc
+    import tensornetworksfork_b200 as tnb
+    f = wl["features"] + 1 if wl["bias"] else (2 if wl["basis"] == "sin-cos" else wl.get("degree", 3) + 1)
+    if wl["kind"] == "cpd":
+        layer = tnb.CPDLayer(wl["sites"], wl["r"], f, output_shape=(wl["C"],), seed=42)
+    else:
+        layer = tnb.TensorTrainLayer(wl["sites"], wl["r"], f, output_shape=wl["C"], constrict_bond=wl["constrict"], perturb=wl["perturb"], seed=42)
+    cores = [n.tensor.numpy().copy() for n in layer.tensor_network.train_nodes]
+    rng = np.random.default_rng(0)
+    X = rng.uniform(-1, 1, size=(rows, wl["features"]))
+    if wl["bias"]:
+        X = np.concatenate([X, np.ones((rows, 1))], 1)
+    y = rng.normal(size=(rows, 1))
+    xin = X if wl["basis"] is None else (orc.fbasis(X) if wl["basis"] == "sin-cos" else orc.polynomial_basis(X, wl.get("degree", 3)))
+    n = len(cores)
+    shapes = {}
+    for k in range(n):
+        shapes.setdefault(cores[k].shape, []).append(k)
+    t_batch = 0.0
+    t_solve = 0.0
+    for shp, ks in shapes.items():
+        k = ks[0]
+        t0 = time.perf_counter()
+        if wl["kind"] == "cpd":
+            pred = orc.cpd_forward(cores, xin)
+            lo, g, H = orc.loss_square(pred, y)
+            J = orc.cpd_jacobian(cores, xin, k)
+        else:
+            phis = orc.site_inputs(xin, n)
+            Ls, Rs = orc.left_envs(cores, phis), orc.right_envs(cores, phis)
+            pred = Ls[-1][:, :, 0]
+            lo, g, H = orc.loss_square(pred, y)
+            J = orc.jacobian(cores, phis, k, Ls[k - 1] if k > 0 else np.ones((rows, 1, 1)), Rs[k + 1] if k < n - 1 else np.ones((rows, 1, 1)))
+        A, b = orc.gram(J, g, H)
+        t_batch += (time.perf_counter() - t0) * len(ks)
+        P = b.size
+        if P <= 4096:
+            t0 = time.perf_counter()
+            orc.solve_system(A, b, cores[k].ravel(), "ridge_cholesky", 1.0)
+            t_solve += (time.perf_counter() - t0) * len(ks)
+        else:
+            t_solve += 0.0  # not timed on the bounded sample: favours the CPU number
+    return t_batch, t_solve, n
+
+
+def cpu_baseline(args, wl, rows_total):
+    rows = args.ref_rows or (256 if args.workload == "cfg5a" else 2048)
+    t_batch, t_solve, n = cpu_site_time(wl, rows)
+    per_sweep_sites = max(2 * n - 2, 1)
+    t_all_sites = t_batch * (rows_total / rows) + t_solve     # every site once
+    value = n / t_all_sites
+    return {"value": value, "unit": "site-updates/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"oracle port (numpy/BLAS, all host threads): env + Jacobian + Gram + rhs of every site on one {rows}-row "
+                      f"minibatch ({t_batch:.2f} s) plus the dense solves with P<=4096 ({t_solve:.2f} s; larger P not timed, "
+                      f"which favours the CPU); per-row cost extrapolated linearly to {rows_total} rows"}
+
+
+def bench_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    n = (args.n if args.n is not None else wl["n"]) * world
+    rows = args.ref_rows or (256 if args.workload == "cfg5a" else 2048)
+    for _ in range(args.warmup):
+        cpu_site_time(wl, min(rows, 64))
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(args.steps):
+        t_batch, t_solve, ns = cpu_site_time(wl, rows)
+        vals.append(ns / (t_batch * (n / rows) + t_solve))
+    wall = time.perf_counter() - t0
+    value = float(np.median(vals))
+    sample = (f"oracle port of tensor/network.py (numpy/BLAS, {os.cpu_count()} host threads): per step, env+Jacobian+Gram+rhs of every "
+              f"site on one {rows}-row minibatch and the dense solves with P<=4096, extrapolated linearly to {n} rows")
+    out = {"impl": "reference", "metric": "gn_site_updates_per_s", "value": value, "unit": "site-updates/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"{args.workload}: {wl['desc']}", "rows_total": n},
+           "cpu_baseline": {"value": value, "unit": "site-updates/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "site-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        bench_reference(a)
+    else:
+        bench_b200(a)

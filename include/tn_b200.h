@@ -1,0 +1,126 @@
+/* tn_b200.h -- C ABI of the B200-native Gauss-Newton / ALS sweep kernels.
+ *
+ * The reference (niccogc/TensorNetworksFork) has no FFI/plugin boundary: its hot
+ * path is Python on torch.einsum / torch.linalg.  These entry
+ * points are what a binding for that path replaces, one per reference function.
+ * Every pointer is a DEVICE pointer to fp64 data unless stated; sizes are in
+ * elements; `stream` is a cudaStream_t passed as void*.  Every function enqueues
+ * on `stream`, returns 0 on success or a negative TN_E* code, and never throws;
+ * tn_last_error() gives the message for the calling thread.
+ *
+ * Shared vocabulary
+ *   S           samples in the shard / batch
+ *   rows        S * V "virtual rows": a sample whose output Hessian H_s is written as
+ *               sum_t lam_t u_t u_t^T contributes V rows (V = 1 when C = 1)
+ *   factor      a per-row vector F[row / div, 0..m) read with row stride ld; the local
+ *               Jacobian of a core is the Kronecker product of three factors
+ *               (left environment, site input, right environment): network.py:101-113
+ *   map_kind    feature map applied to the site input while it is read:
+ *               TN_MAP_IDENTITY  phi[p] = x[p]                    (poly-mode, models/tensor_train.py:223)
+ *               TN_MAP_SINCOS    phi = [cos(pi x/2), sin(pi x/2)] (models/tnml.py:11-16)
+ *               TN_MAP_POLY      phi[p] = x^p, p = 0..m-1         (models/tnml.py:18-23)
+ */
+#ifndef TN_B200_H
+#define TN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TN_OK 0
+#define TN_EINVAL (-1)   /* bad argument                                   */
+#define TN_ECUDA (-2)    /* CUDA runtime error (see tn_last_error)         */
+#define TN_ENOTSPD (-3)  /* reserved: factorisation status is in *info     */
+#define TN_EUNSUPPORTED (-4)
+
+#define TN_MAP_IDENTITY 0
+#define TN_MAP_SINCOS 1
+#define TN_MAP_POLY 2
+
+/* One Kronecker factor of the local Jacobian. */
+typedef struct tn_factor {
+    const double *ptr; /* row r lives at ptr + (r / div) * ld                         */
+    int64_t ld;        /* row stride in elements                                      */
+    int32_t m;         /* entries per row AFTER the feature map                       */
+    int32_t div;       /* row divisor: 1, or V when the factor is shared by V rows    */
+    int32_t map_kind;  /* TN_MAP_*; for SINCOS / POLY one raw value is read per row   */
+    int32_t _pad;
+} tn_factor;
+
+int tn_version(void);
+const char *tn_last_error(void);
+/* Number of SMs of the current device (grid sizing on the host side). */
+int tn_sm_count(void);
+
+/* ---- environments: TensorNetwork.compute_stacks / left|right_update_stacks / forward
+ *      (tensor/network.py:55-71, 152-172, 115-137).
+ * out[row, b] = sum_{a,p} env_in[row / env_div, a] * phi[row / cdiv, p] * core[a, p, b]
+ * env_in == NULL means r_in == 1 and env_in == 1 (chain end).  `core` is [r_in, f, r_out]
+ * contiguous, already oriented for the sweep direction by the caller.
+ * If dot != NULL nothing is stored to `out`; instead
+ *   yhat[row] = sum_b out[row, b] * dot[(row / dot_div) * dot_ld + b]   (the prediction).       */
+int tn_env_update(const double *env_in, int64_t env_ld, int env_div, const double *x, int64_t x_ld, int map_kind, int f,
+                  int cdiv, const double *core, double *out, int64_t out_ld, const double *dot, int64_t dot_ld,
+                  int dot_div, double *yhat, int64_t rows, int r_in, int r_out, void *stream);
+
+/* ---- class-leg rows: fold the output Hessian into the left factor
+ *      (what the 3-operand einsum of network.py:207-212 does implicitly).
+ * F[(s,t), a] = sum_c U[s,t,c] * env[s,c,a]        t < V
+ * G[s, a]     = sum_c g[s,c]   * env[s,c,a]        (right-hand-side factor), either may be NULL  */
+int tn_class_rows(const double *env, const double *U, const double *g, double *F, double *G, int64_t S, int C,
+                  int V, int r, void *stream);
+
+/* ---- Gram build: TensorNetwork.get_A_b (tensor/network.py:174-217), never materialising J.
+ * With pair(F)[(i<=j)] = F[i]*F[j]:
+ *   M[qa, qb, qc] (+)= sum_rows w[row] * pair(fa)[qa] * pair(fb)[qb] * pair(fc)[qc]
+ * M has na*nb*nc entries, n = m(m+1)/2: the unique entries of A = J^T H J under the
+ * Kronecker symmetry.  `w` may be NULL (all ones).  `work` holds ksplit partial copies of M
+ * (ksplit >= 1 chosen by tn_gram_ksplit); the result is reduced into M deterministically.
+ * mode: 0 = fp64 (CUDA-core FMA), 1 = TF32 tcgen05, 2 = 3xTF32 tcgen05 (fp64 flush every
+ * `flush_rows` rows).  accumulate != 0 adds to M instead of overwriting.                        */
+int tn_gram_ksplit(int64_t rows, int ma, int mb, int mc, int mode);
+int tn_gram_kr3(int mode, const tn_factor *fa, const tn_factor *fb, const tn_factor *fc, const double *w,
+                int64_t rows, double *M, double *work, int ksplit, int accumulate, void *stream);
+
+/* b[ia, ib, ic] (+)= sum_rows w[row] * fa[ia] * fb[ib] * fc[ic]    (network.py:215)            */
+int tn_rhs_ksplit(int64_t rows, int ma, int mb, int mc);
+int tn_rhs_kr3(const tn_factor *fa, const tn_factor *fb, const tn_factor *fc, const double *w, int64_t rows,
+               double *b, double *work, int ksplit, int accumulate, void *stream);
+
+/* ---- local solve: TensorNetwork.solve_system (tensor/network.py:293-327).
+ * sigma_out[0] = mean_i |A_ii| computed from M (1 if 0).  role_of_pos[t] says which role
+ * (0=a,1=b,2=c) parameter position t = 0,1,2 plays; m_pos[t] is its size.                       */
+int tn_gram_sigma(const double *M, const int *m_pos, const int *role_of_pos, double *sigma_out, void *stream);
+/* A[i, j] = M[pair...] / sigma + (i == j) * ridge      (P x P, row stride lda)                  */
+int tn_gram_expand(const double *M, const int *m_pos, const int *role_of_pos, const double *sigma, double ridge,
+                   double *A, int64_t lda, void *stream);
+/* rhs[i] = -( b[i] / sigma + ridge * theta[i] )                                                 */
+int tn_rhs_prepare(const double *b, const double *theta, const double *sigma, double ridge, double *rhs, int64_t P,
+                   void *stream);
+/* In-place blocked Cholesky of the lower triangle of A, then the two triangular solves on rhs.
+ * work: tn_cholesky_work_elems(P) doubles.  info[0] = 0, or k>0 if the leading minor of order
+ * k is not positive definite (caller raises LinAlgError as torch.linalg.cholesky does).         */
+int64_t tn_cholesky_work_elems(int64_t P);
+int tn_cholesky_solve(double *A, int64_t lda, int64_t P, double *rhs, double *work, int *info, void *stream);
+
+/* theta <- theta + lr * step with the optional adaptive shrink / max-norm projection
+ * (TensorNode.update_node, tensor/node.py:178-203).  max_norm <= 0 disables the projection.     */
+int tn_update_node(double *theta, const double *step, int64_t P, double lr, int adaptive_step, double max_norm,
+                   double *scratch, void *stream);
+
+/* ---- QR re-gauge: node_orthonormalize_left/right (tensor/network.py:625-707).
+ * a (m x n, row-major, m >= n) <- Q (reduced, LAPACK sign convention); r (n x n) <- R.          */
+int tn_qr(double *a, int m, int n, double *r, void *stream);
+
+/* ---- matrix-free local operator: the matvec of lanczos_swipe / scipy_swipe
+ *      (tensor/network.py:770-790, 896-918):  out = J^T diag(w) J v  on virtual rows.           */
+int64_t tn_matvec_work_elems(int64_t rows, int ma, int mb, int mc);
+int tn_matvec_kr3(const tn_factor *fa, const tn_factor *fb, const tn_factor *fc, const double *w, int64_t rows,
+                  const double *v, double *out, double *work, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TN_B200_H */

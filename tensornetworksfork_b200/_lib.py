@@ -1,0 +1,77 @@
+"""ctypes binding of the C ABI declared in include/tn_b200.h.
+
+The shared library is built in-tree by ``make`` (or ``__graft_entry__.build()``).  There is no
+CPU fallback: if the library is missing, or a CUDA tensor is required and absent, the caller gets
+an exception.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtn_b200.so")
+
+c_double_p = ctypes.c_void_p
+c_int_p = ctypes.c_void_p
+i64 = ctypes.c_int64
+i32 = ctypes.c_int
+f64 = ctypes.c_double
+vp = ctypes.c_void_p
+
+
+class tn_factor(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("ld", ctypes.c_int64), ("m", ctypes.c_int32), ("div", ctypes.c_int32),
+                ("map_kind", ctypes.c_int32), ("_pad", ctypes.c_int32)]
+
+
+FP = ctypes.POINTER(tn_factor)
+IP = ctypes.POINTER(ctypes.c_int)
+
+# name -> (restype, argtypes); mirrors include/tn_b200.h one to one
+PROTOTYPES = {
+    "tn_version": (i32, []),
+    "tn_last_error": (ctypes.c_char_p, []),
+    "tn_sm_count": (i32, []),
+    "tn_env_update": (i32, [vp, i64, i32, vp, i64, i32, i32, i32, vp, vp, i64, vp, i64, i32, vp, i64, i32, i32, vp]),
+    "tn_class_rows": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
+    "tn_gram_ksplit": (i32, [i64, i32, i32, i32, i32]),
+    "tn_gram_kr3": (i32, [i32, FP, FP, FP, vp, i64, vp, vp, i32, i32, vp]),
+    "tn_rhs_ksplit": (i32, [i64, i32, i32, i32]),
+    "tn_rhs_kr3": (i32, [FP, FP, FP, vp, i64, vp, vp, i32, i32, vp]),
+    "tn_gram_sigma": (i32, [vp, IP, IP, vp, vp]),
+    "tn_gram_expand": (i32, [vp, IP, IP, vp, f64, vp, i64, vp]),
+    "tn_rhs_prepare": (i32, [vp, vp, vp, f64, vp, i64, vp]),
+    "tn_cholesky_work_elems": (i64, [i64]),
+    "tn_cholesky_solve": (i32, [vp, i64, i64, vp, vp, vp, vp]),
+    "tn_update_node": (i32, [vp, vp, i64, f64, i32, f64, vp, vp]),
+    "tn_qr": (i32, [vp, i32, i32, vp, vp]),
+    "tn_matvec_work_elems": (i64, [i64, i32, i32, i32]),
+    "tn_matvec_kr3": (i32, [FP, FP, FP, vp, i64, vp, vp, vp, vp]),
+}
+
+_lib = None
+
+
+class TnError(RuntimeError):
+    pass
+
+
+def load():
+    """Load libtn_b200.so; raise if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise TnError(f"{LIB_PATH} is missing: run `make` (or __graft_entry__.build()) first; there is no CPU fallback")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc, what):
+    if rc != 0:
+        msg = load().tn_last_error().decode("utf-8", "replace")
+        raise TnError(f"{what} failed (rc={rc}): {msg}")

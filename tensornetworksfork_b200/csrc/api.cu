@@ -1,0 +1,27 @@
+// Error plumbing and device queries of the C ABI.
+#include <stdarg.h>
+#include <string.h>
+#include "common.cuh"
+
+namespace tn {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+int sm_count() {
+    static int cached = 0;
+    if (cached) return cached;
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
+    cached = n;
+    return n;
+}
+}  // namespace tn
+
+extern "C" int tn_version(void) { return 100; }
+extern "C" const char* tn_last_error(void) { return tn::g_err; }
+extern "C" int tn_sm_count(void) { return tn::sm_count(); }

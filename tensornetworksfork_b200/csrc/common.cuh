@@ -1,0 +1,63 @@
+// Shared helpers for the tn_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "../../include/tn_b200.h"
+
+namespace tn {
+
+void set_error(const char* fmt, ...);
+
+#define TN_CHECK_ARG(cond, ...)            \
+    do {                                   \
+        if (!(cond)) {                     \
+            tn::set_error(__VA_ARGS__);    \
+            return TN_EINVAL;              \
+        }                                  \
+    } while (0)
+
+#define TN_CUDA(call)                                                                   \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            tn::set_error("%s:%d %s: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            return TN_ECUDA;                                                            \
+        }                                                                               \
+    } while (0)
+
+#define TN_LAUNCH_CHECK() TN_CUDA(cudaGetLastError())
+
+static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
+
+__host__ __device__ __forceinline__ int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ __forceinline__ int npairs(int m) { return m * (m + 1) / 2; }
+// index of the unordered pair (i <= j) among m, row-major over the upper triangle
+__host__ __device__ __forceinline__ int pair_index(int i, int j, int m) { return i * m - (i * (i - 1)) / 2 + (j - i); }
+// inverse of pair_index
+__host__ __device__ inline void pair_decode(int q, int m, int& i, int& j) {
+    int ii = 0, rem = q;
+    while (rem >= m - ii) {
+        rem -= m - ii;
+        ++ii;
+    }
+    i = ii;
+    j = ii + rem;
+}
+
+// Evaluate one site-input entry under a feature map.  raw = x[row*ld] for SINCOS/POLY.
+__device__ __forceinline__ double map_eval(int map_kind, const double* __restrict__ xrow, int p) {
+    if (map_kind == TN_MAP_IDENTITY) return xrow[p];
+    const double t = xrow[0];
+    if (map_kind == TN_MAP_SINCOS) {
+        const double a = (0.5 * 3.14159265358979323846) * t;  // same operation order as models/tnml.py:14
+        return p == 0 ? cos(a) : sin(a);
+    }
+    double v = 1.0;  // TN_MAP_POLY
+    for (int d = 0; d < p; ++d) v *= t;
+    return v;
+}
+
+int sm_count();
+
+}  // namespace tn

@@ -1,0 +1,427 @@
+// Gram build without the Jacobian: fp64 CUDA-core path, right-hand side, sigma, expansion.
+//
+// Replaces TensorNetwork.get_A_b (reference tensor/network.py:174-217).  The local Jacobian
+// of a core is a row-wise Kronecker product J[row, (ia,ib,ic)] = fa[ia] fb[ib] fc[ic], so
+//   A[(i),(j)] = sum_rows w * fa[ia]fa[ja] * fb[ib]fb[jb] * fc[ic]fc[jc]
+// is invariant under ia<->ja, ib<->jb, ic<->jc separately.  Only the unique entries
+//   M[qa,qb,qc] = sum_rows w * pair(fa)[qa] * pair(fb)[qb] * pair(fc)[qc]
+// are accumulated (about P^2/8 of them instead of P^2/2 for a plain SYRK) as one GEMM
+//   M = U^T V,  U[row,(qa,qb)] = w*pair(fa)*pair(fb),  V[row,qc] = pair(fc)
+// whose operand tiles are synthesised in shared memory from the raw factors; nothing of
+// size rows x P ever exists.  tn_gram_expand scatters M to the dense scaled system.
+#include "common.cuh"
+
+namespace tn {
+
+constexpr int GR_TU = 128;      // U columns per CTA
+constexpr int GR_TV = 64;       // V columns per CTA
+constexpr int GR_KC = 16;       // rows per staged chunk
+constexpr int GR_THREADS = 256;
+
+struct FactorDev {
+    const double* ptr;
+    int64_t ld;
+    int m;
+    int div;
+    int map_kind;
+};
+
+static inline FactorDev to_dev(const tn_factor* f) { return FactorDev{f->ptr, f->ld, f->m, f->div < 1 ? 1 : f->div, f->map_kind}; }
+
+__device__ __forceinline__ void stage_factor(const FactorDev& f, double* dst, int st, int64_t kb, int64_t k_end, int tid) {
+    for (int idx = tid; idx < GR_KC * f.m; idx += GR_THREADS) {
+        const int k = idx / f.m, i = idx - k * f.m;
+        const int64_t row = kb + k;
+        double v = 0.0;
+        if (row < k_end) v = map_eval(f.map_kind, f.ptr + (row / f.div) * f.ld, i);
+        dst[k * st + i] = v;
+    }
+}
+
+// PAIR = true : Gram (pairs of each factor).  PAIR = false : right-hand side (plain products).
+template <bool PAIR>
+__global__ void __launch_bounds__(GR_THREADS)
+kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restrict__ w, int64_t rows,
+               double* __restrict__ out, int nA, int nB, int nC, int64_t rows_per_split) {
+    extern __shared__ double sm[];
+    const int stA = fa.m | 1, stB = fb.m | 1, stC = fc.m | 1;
+    double* sFA = sm;
+    double* sFB = sFA + GR_KC * stA;
+    double* sFC = sFB + GR_KC * stB;
+    double* sW = sFC + GR_KC * stC;
+    double* sU = sW + GR_KC;              // [GR_KC][GR_TU]
+    double* sV = sU + GR_KC * GR_TU;      // [GR_KC][GR_TV]
+    short* tIA = reinterpret_cast<short*>(sV + GR_KC * GR_TV);
+    short* tJA = tIA + GR_TU;
+    short* tIB = tJA + GR_TU;
+    short* tJB = tIB + GR_TU;
+    short* tIC = tJB + GR_TU;
+    short* tJC = tIC + GR_TV;
+
+    const int tid = threadIdx.x;
+    const int64_t nU = (int64_t)nA * nB;
+    const int64_t u0 = (int64_t)blockIdx.x * GR_TU;
+    const int v0 = blockIdx.y * GR_TV;
+    const int64_t k_begin = (int64_t)blockIdx.z * rows_per_split;
+    const int64_t k_end = min(rows, k_begin + rows_per_split);
+
+    if (tid < GR_TU) {
+        const int64_t gu = u0 + tid;
+        int ia = -1, ja = 0, ib = 0, jb = 0;
+        if (gu < nU) {
+            const int qa = (int)(gu / nB), qb = (int)(gu - (int64_t)qa * nB);
+            if (PAIR) {
+                pair_decode(qa, fa.m, ia, ja);
+                pair_decode(qb, fb.m, ib, jb);
+            } else {
+                ia = ja = qa;
+                ib = jb = qb;
+            }
+        }
+        tIA[tid] = (short)ia; tJA[tid] = (short)ja; tIB[tid] = (short)ib; tJB[tid] = (short)jb;
+    } else if (tid < GR_TU + GR_TV) {
+        const int t = tid - GR_TU;
+        const int gv = v0 + t;
+        int ic = -1, jc = 0;
+        if (gv < nC) {
+            if (PAIR) pair_decode(gv, fc.m, ic, jc);
+            else ic = jc = gv;
+        }
+        tIC[t] = (short)ic; tJC[t] = (short)jc;
+    }
+
+    const int tx = tid & 15, ty = tid >> 4;
+    double acc[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+
+    for (int64_t kb = k_begin; kb < k_end; kb += GR_KC) {
+        __syncthreads();  // previous chunk's sU/sV fully consumed; tables visible on first pass
+        stage_factor(fa, sFA, stA, kb, k_end, tid);
+        stage_factor(fb, sFB, stB, kb, k_end, tid);
+        stage_factor(fc, sFC, stC, kb, k_end, tid);
+        if (tid < GR_KC) {
+            const int64_t row = kb + tid;
+            sW[tid] = (row < k_end) ? (w ? w[row] : 1.0) : 0.0;
+        }
+        __syncthreads();
+        for (int idx = tid; idx < GR_KC * GR_TU; idx += GR_THREADS) {
+            const int k = idx >> 7, u = idx & (GR_TU - 1);
+            const int ia = tIA[u];
+            double v = 0.0;
+            if (ia >= 0) {
+                const double* a = sFA + k * stA;
+                const double* b = sFB + k * stB;
+                v = PAIR ? sW[k] * a[ia] * a[tJA[u]] * b[tIB[u]] * b[tJB[u]] : sW[k] * a[ia] * b[tIB[u]];
+            }
+            sU[idx] = v;
+        }
+        for (int idx = tid; idx < GR_KC * GR_TV; idx += GR_THREADS) {
+            const int k = idx >> 6, t = idx & (GR_TV - 1);
+            const int ic = tIC[t];
+            double v = 0.0;
+            if (ic >= 0) {
+                const double* c = sFC + k * stC;
+                v = PAIR ? c[ic] * c[tJC[t]] : c[ic];
+            }
+            sV[idx] = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < GR_KC; ++k) {
+            double a[8], b[4];
+            const double2* up = reinterpret_cast<const double2*>(sU + k * GR_TU + ty * 8);
+            const double2 a0 = up[0], a1 = up[1], a2 = up[2], a3 = up[3];
+            a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y; a[6] = a3.x; a[7] = a3.y;
+            const double2 b0 = *reinterpret_cast<const double2*>(sV + k * GR_TV + 2 * tx);
+            const double2 b1 = *reinterpret_cast<const double2*>(sV + k * GR_TV + 32 + 2 * tx);
+            b[0] = b0.x; b[1] = b0.y; b[2] = b1.x; b[3] = b1.y;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        }
+    }
+
+    double* o = out + (int64_t)blockIdx.z * nU * nC;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int64_t gu = u0 + ty * 8 + i;
+        if (gu >= nU) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gv = v0 + ((j < 2) ? (2 * tx + j) : (32 + 2 * tx + (j - 2)));
+            if (gv < nC) o[gu * nC + gv] = acc[i][j];
+        }
+    }
+}
+
+__global__ void reduce_splits_kernel(const double* __restrict__ work, double* __restrict__ dst, int64_t n, int ksplit,
+                                     int accumulate) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double s = accumulate ? dst[i] : 0.0;
+        for (int k = 0; k < ksplit; ++k) s += work[(int64_t)k * n + i];
+        dst[i] = s;
+    }
+}
+
+static int choose_ksplit(int64_t rows, int64_t nU, int64_t nV) {
+    const int64_t tiles = ceil_div64(nU, GR_TU) * ceil_div64(nV, GR_TV);
+    const int64_t want = 4LL * sm_count();
+    int64_t ks = ceil_div64(want, tiles);
+    const int64_t max_by_rows = ceil_div64(rows, 8 * GR_KC);
+    if (ks > max_by_rows) ks = max_by_rows;
+    const int64_t max_by_mem = (int64_t)(64LL << 20) / (nU * nV > 0 ? nU * nV : 1);  // <= 512 MB of partials
+    if (ks > max_by_mem) ks = max_by_mem;
+    if (ks < 1) ks = 1;
+    if (ks > 1024) ks = 1024;
+    return (int)ks;
+}
+
+template <bool PAIR>
+static int launch_kr3(const tn_factor* fa, const tn_factor* fb, const tn_factor* fc, const double* w, int64_t rows,
+                      double* dst, double* work, int ksplit, int accumulate, cudaStream_t st) {
+    const FactorDev a = to_dev(fa), b = to_dev(fb), c = to_dev(fc);
+    const int nA = PAIR ? npairs(a.m) : a.m, nB = PAIR ? npairs(b.m) : b.m, nC = PAIR ? npairs(c.m) : c.m;
+    const int64_t nU = (int64_t)nA * nB;
+    const int64_t n = nU * nC;
+    if (ksplit < 1) ksplit = 1;
+    int64_t rps = ceil_div64(ceil_div64(rows, ksplit), GR_KC) * GR_KC;
+    if (rps < GR_KC) rps = GR_KC;
+    const bool direct = (ksplit == 1 && !accumulate);
+    TN_CHECK_ARG(direct || work != nullptr, "kr3: ksplit=%d / accumulate need a work buffer", ksplit);
+    const size_t smem = (size_t)(GR_KC * ((a.m | 1) + (b.m | 1) + (c.m | 1)) + GR_KC + GR_KC * GR_TU + GR_KC * GR_TV) * sizeof(double) +
+                        (size_t)(4 * GR_TU + 2 * GR_TV) * sizeof(short);
+    TN_CHECK_ARG(smem <= 227 * 1024, "kr3: factor sizes %d,%d,%d need %zu B of shared memory", a.m, b.m, c.m, smem);
+    TN_CHECK_ARG(a.m < 32768 && b.m < 32768 && c.m < 32768, "kr3: factor too large");
+    static size_t configured[2] = {0, 0};
+    if (smem > configured[PAIR]) {
+        TN_CUDA(cudaFuncSetAttribute(kr3_f64_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[PAIR] = smem;
+    }
+    const int64_t gx = ceil_div64(nU, GR_TU), gy = ceil_div64(nC, GR_TV);
+    TN_CHECK_ARG(gy <= 65535 && ksplit <= 65535 && gx <= 0x7fffffff, "kr3: grid too large");
+    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)ksplit);
+    kr3_f64_kernel<PAIR><<<grid, GR_THREADS, smem, st>>>(a, b, c, w, rows, direct ? dst : work, nA, nB, nC, rps);
+    TN_LAUNCH_CHECK();
+    if (!direct) {
+        int64_t blocks = ceil_div64(n, 256);
+        const int64_t cap = (int64_t)sm_count() * 8;
+        if (blocks > cap) blocks = cap;
+        reduce_splits_kernel<<<(unsigned)blocks, 256, 0, st>>>(work, dst, n, ksplit, accumulate);
+        TN_LAUNCH_CHECK();
+    }
+    return TN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// sigma, expansion, right-hand side preparation, node update
+
+struct PosInfo {
+    int m[3];     // size of parameter position t
+    int role[3];  // role (0=a,1=b,2=c) of position t
+    int n_role[3];  // pair counts per role
+};
+
+__device__ __forceinline__ int64_t m_index(const PosInfo& pi, const int* ii, const int* jj) {
+    int q[3];
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int lo = min(ii[t], jj[t]), hi = max(ii[t], jj[t]);
+        q[pi.role[t]] = pair_index(lo, hi, pi.m[t]);
+    }
+    return ((int64_t)q[0] * pi.n_role[1] + q[1]) * pi.n_role[2] + q[2];
+}
+
+__global__ void sigma_kernel(const double* __restrict__ M, PosInfo pi, double* __restrict__ sigma) {
+    __shared__ double red[32];
+    const int64_t P = (int64_t)pi.m[0] * pi.m[1] * pi.m[2];
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < P; i += blockDim.x) {
+        int ii[3];
+        ii[2] = (int)(i % pi.m[2]);
+        const int64_t r = i / pi.m[2];
+        ii[1] = (int)(r % pi.m[1]);
+        ii[0] = (int)(r / pi.m[1]);
+        s += fabs(M[m_index(pi, ii, ii)]);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double v = (threadIdx.x < (blockDim.x >> 5)) ? red[threadIdx.x] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (threadIdx.x == 0) {
+            double sc = v / (double)P;  // diag.abs().mean(), network.py:298
+            if (sc == 0.0) sc = 1.0;    // network.py:299-300
+            sigma[0] = sc;
+        }
+    }
+}
+
+__global__ void expand_kernel(const double* __restrict__ M, PosInfo pi, const double* __restrict__ sigma, double ridge,
+                              double* __restrict__ A, int64_t lda) {
+    const int64_t P = (int64_t)pi.m[0] * pi.m[1] * pi.m[2];
+    const double sc = sigma[0];
+    for (int64_t i = blockIdx.x; i < P; i += gridDim.x) {
+        int ii[3];
+        ii[2] = (int)(i % pi.m[2]);
+        const int64_t r = i / pi.m[2];
+        ii[1] = (int)(r % pi.m[1]);
+        ii[0] = (int)(r / pi.m[1]);
+        double* Ai = A + i * lda;
+        for (int64_t j = threadIdx.x; j < P; j += blockDim.x) {
+            int jj[3];
+            jj[2] = (int)(j % pi.m[2]);
+            const int64_t rj = j / pi.m[2];
+            jj[1] = (int)(rj % pi.m[1]);
+            jj[0] = (int)(rj / pi.m[1]);
+            double v = M[m_index(pi, ii, jj)] / sc;  // A_f / scale, network.py:301
+            if (i == j) v += ridge;                   // + 2 eps I, network.py:308,312
+            Ai[j] = v;
+        }
+    }
+}
+
+__global__ void rhs_prepare_kernel(const double* __restrict__ b, const double* __restrict__ theta,
+                                   const double* __restrict__ sigma, double ridge, double* __restrict__ rhs, int64_t P) {
+    const double sc = sigma[0];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = b[i] / sc;                       // network.py:302
+        if (ridge != 0.0) v += ridge * theta[i];    // network.py:309,313
+        rhs[i] = -v;                                // solve(A, -b), network.py:305,315
+    }
+}
+
+__device__ double block_sum(double v, double* red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int k = 0; k < (int)(blockDim.x >> 5); ++k) t += red[k];
+    return t;
+}
+
+// One CTA: norms and the axpy of TensorNode.update_node (node.py:178-203).
+__global__ void update_node_kernel(double* __restrict__ theta, const double* __restrict__ step, int64_t P, double lr,
+                                   int adaptive, double max_norm) {
+    __shared__ double red[32];
+    double scale = 1.0;
+    if (adaptive) {
+        double s2 = 0.0, p2 = 0.0;
+        for (int64_t i = threadIdx.x; i < P; i += blockDim.x) {
+            s2 += step[i] * step[i];
+            p2 += theta[i] * theta[i];
+        }
+        const double sn = sqrt(block_sum(s2, red)), pn = sqrt(block_sum(p2, red));
+        if (sn > pn) scale = pn / sn;
+    }
+    double n2 = 0.0;
+    for (int64_t i = threadIdx.x; i < P; i += blockDim.x) {
+        const double v = theta[i] + lr * (step[i] * scale);
+        theta[i] = v;
+        n2 += v * v;
+    }
+    if (max_norm > 0.0) {
+        const double cn = sqrt(block_sum(n2, red));
+        if (cn > max_norm) {
+            const double f = max_norm / cn;
+            for (int64_t i = threadIdx.x; i < P; i += blockDim.x) theta[i] *= f;
+        }
+    }
+}
+
+static int make_pos(const int* m_pos, const int* role_of_pos, PosInfo& pi) {
+    bool seen[3] = {false, false, false};
+    for (int t = 0; t < 3; ++t) {
+        if (m_pos[t] < 1 || role_of_pos[t] < 0 || role_of_pos[t] > 2 || seen[role_of_pos[t]]) return -1;
+        seen[role_of_pos[t]] = true;
+        pi.m[t] = m_pos[t];
+        pi.role[t] = role_of_pos[t];
+        pi.n_role[role_of_pos[t]] = npairs(m_pos[t]);
+    }
+    return 0;
+}
+
+}  // namespace tn
+
+extern "C" int tn_gram_ksplit(int64_t rows, int ma, int mb, int mc, int mode) {
+    using namespace tn;
+    if (mode != 0) return 1;
+    return choose_ksplit(rows, (int64_t)npairs(ma) * npairs(mb), npairs(mc));
+}
+
+extern "C" int tn_rhs_ksplit(int64_t rows, int ma, int mb, int mc) {
+    return tn::choose_ksplit(rows, (int64_t)ma * mb, mc);
+}
+
+int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_factor* fc, const double* w,
+                   int64_t rows, double* M, int accumulate, void* stream);
+
+extern "C" int tn_gram_kr3(int mode, const tn_factor* fa, const tn_factor* fb, const tn_factor* fc, const double* w,
+                           int64_t rows, double* M, double* work, int ksplit, int accumulate, void* stream) {
+    using namespace tn;
+    TN_CHECK_ARG(fa && fb && fc && M, "tn_gram_kr3: null argument");
+    TN_CHECK_ARG(rows >= 0, "tn_gram_kr3: negative rows");
+    TN_CHECK_ARG(fa->m >= 1 && fb->m >= 1 && fc->m >= 1, "tn_gram_kr3: empty factor");
+    if (mode == 0) return launch_kr3<true>(fa, fb, fc, w, rows, M, work, ksplit, accumulate, as_stream(stream));
+    if (mode == 1 || mode == 2) return tn_gram_kr3_tc(mode, fa, fb, fc, w, rows, M, accumulate, stream);
+    set_error("tn_gram_kr3: unknown mode %d", mode);
+    return TN_EINVAL;
+}
+
+extern "C" int tn_rhs_kr3(const tn_factor* fa, const tn_factor* fb, const tn_factor* fc, const double* w, int64_t rows,
+                          double* b, double* work, int ksplit, int accumulate, void* stream) {
+    using namespace tn;
+    TN_CHECK_ARG(fa && fb && fc && b, "tn_rhs_kr3: null argument");
+    TN_CHECK_ARG(rows >= 0, "tn_rhs_kr3: negative rows");
+    return launch_kr3<false>(fa, fb, fc, w, rows, b, work, ksplit, accumulate, as_stream(stream));
+}
+
+extern "C" int tn_gram_sigma(const double* M, const int* m_pos, const int* role_of_pos, double* sigma_out, void* stream) {
+    using namespace tn;
+    PosInfo pi;
+    TN_CHECK_ARG(M && sigma_out && m_pos && role_of_pos && make_pos(m_pos, role_of_pos, pi) == 0, "tn_gram_sigma: bad arguments");
+    sigma_kernel<<<1, 1024, 0, as_stream(stream)>>>(M, pi, sigma_out);
+    TN_LAUNCH_CHECK();
+    return TN_OK;
+}
+
+extern "C" int tn_gram_expand(const double* M, const int* m_pos, const int* role_of_pos, const double* sigma, double ridge,
+                              double* A, int64_t lda, void* stream) {
+    using namespace tn;
+    PosInfo pi;
+    TN_CHECK_ARG(M && A && sigma && m_pos && role_of_pos && make_pos(m_pos, role_of_pos, pi) == 0, "tn_gram_expand: bad arguments");
+    const int64_t P = (int64_t)pi.m[0] * pi.m[1] * pi.m[2];
+    TN_CHECK_ARG(lda >= P, "tn_gram_expand: lda < P");
+    int64_t blocks = P;
+    const int64_t cap = (int64_t)sm_count() * 32;
+    if (blocks > cap) blocks = cap;
+    expand_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(M, pi, sigma, ridge, A, lda);
+    TN_LAUNCH_CHECK();
+    return TN_OK;
+}
+
+extern "C" int tn_rhs_prepare(const double* b, const double* theta, const double* sigma, double ridge, double* rhs,
+                              int64_t P, void* stream) {
+    using namespace tn;
+    TN_CHECK_ARG(b && sigma && rhs && P >= 1 && (ridge == 0.0 || theta), "tn_rhs_prepare: bad arguments");
+    int64_t blocks = ceil_div64(P, 256);
+    if (blocks > 1024) blocks = 1024;
+    rhs_prepare_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(b, theta, sigma, ridge, rhs, P);
+    TN_LAUNCH_CHECK();
+    return TN_OK;
+}
+
+extern "C" int tn_update_node(double* theta, const double* step, int64_t P, double lr, int adaptive_step, double max_norm,
+                              double* scratch, void* stream) {
+    using namespace tn;
+    (void)scratch;
+    TN_CHECK_ARG(theta && step && P >= 1, "tn_update_node: bad arguments");
+    update_node_kernel<<<1, 1024, 0, as_stream(stream)>>>(theta, step, P, lr, adaptive_step, max_norm);
+    TN_LAUNCH_CHECK();
+    return TN_OK;
+}

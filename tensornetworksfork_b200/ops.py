@@ -1,0 +1,230 @@
+"""Torch-tensor front end of the C ABI: borrows device pointers for the duration of a call.
+
+PyTorch is used here for device memory and streams only; every function below enqueues the
+hand-written kernels of libtn_b200.so on torch's current CUDA stream.  No function has a CPU
+implementation: a non-CUDA tensor raises.
+"""
+import ctypes
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib
+from ._lib import tn_factor
+
+MAP_IDENTITY, MAP_SINCOS, MAP_POLY = 0, 1, 2
+GRAM_FP64, GRAM_TF32, GRAM_TF32X3 = 0, 1, 2
+
+
+@dataclass
+class Factor:
+    """One Kronecker factor of the local Jacobian: rows of ``tensor`` (2-D, last dim contiguous)."""
+    tensor: torch.Tensor
+    m: int
+    div: int = 1
+    map_kind: int = MAP_IDENTITY
+    col: int = 0  # first column read (raw feature index for SINCOS / POLY)
+
+    @property
+    def ld(self):
+        return self.tensor.stride(0) if self.tensor.dim() == 2 else 1
+
+    def ptr(self):
+        return self.tensor.data_ptr() + 8 * self.col
+
+    def c(self):
+        return tn_factor(self.ptr(), self.ld, self.m, self.div, self.map_kind, 0)
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise _lib.TnError("tensornetworksfork_b200 kernels need CUDA tensors; there is no CPU path")
+        if t.dtype != torch.float64:
+            raise _lib.TnError(f"fp64 tensors expected, got {t.dtype}")
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return ctypes.c_void_p(0 if t is None else t.data_ptr())
+
+
+def ones_factor(like):
+    return Factor(torch.ones(1, 1, dtype=torch.float64, device=like.device), m=1, div=1 << 30)
+
+
+def env_update(env_in, x: Factor, core3, rows, cdiv=1, env_div=1, out=None):
+    """out[row,b] = sum_{a,p} env_in[row/env_div,a] phi[row/cdiv,p] core3[a,p,b]."""
+    lib = _lib.load()
+    r_in, f, r_out = core3.shape
+    core3 = core3.contiguous()
+    _need_cuda(env_in, x.tensor, core3)
+    if out is None:
+        out = torch.empty((rows, r_out), dtype=torch.float64, device=core3.device)
+    env_ld = env_in.stride(0) if env_in is not None else 0
+    rc = lib.tn_env_update(_p(env_in), env_ld, env_div, ctypes.c_void_p(x.ptr()), x.ld, x.map_kind, f, cdiv, _p(core3),
+                           _p(out), out.stride(0), None, 0, 1, None, rows, r_in, r_out, _stream())
+    _lib.check(rc, "tn_env_update")
+    return out
+
+
+def predict(env_in, x: Factor, core3, dot, rows, cdiv=1, env_div=1, dot_div=1, out=None):
+    """yhat[row] = sum_{a,p,b} env_in[row/env_div,a] phi[row/cdiv,p] core3[a,p,b] dot[row/dot_div,b]."""
+    lib = _lib.load()
+    r_in, f, r_out = core3.shape
+    core3 = core3.contiguous()
+    _need_cuda(env_in, x.tensor, core3, dot)
+    if out is None:
+        out = torch.empty((rows,), dtype=torch.float64, device=core3.device)
+    env_ld = env_in.stride(0) if env_in is not None else 0
+    rc = lib.tn_env_update(_p(env_in), env_ld, env_div, ctypes.c_void_p(x.ptr()), x.ld, x.map_kind, f, cdiv, _p(core3),
+                           None, 0, _p(dot), dot.stride(0), dot_div, _p(out), rows, r_in, r_out, _stream())
+    _lib.check(rc, "tn_env_update(predict)")
+    return out
+
+
+def class_rows(env, U, g):
+    """F[(s,t),a] = sum_c U[s,t,c] env[s,c,a];  G[s,a] = sum_c g[s,c] env[s,c,a]."""
+    lib = _lib.load()
+    S, C, r = env.shape
+    env = env.contiguous()
+    _need_cuda(env, U, g)
+    F = G = None
+    V = 1
+    if U is not None:
+        U = U.contiguous()
+        V = U.shape[1]
+        F = torch.empty((S * V, r), dtype=torch.float64, device=env.device)
+    if g is not None:
+        g = g.contiguous()
+        G = torch.empty((S, r), dtype=torch.float64, device=env.device)
+    rc = lib.tn_class_rows(_p(env), _p(U), _p(g), _p(F), _p(G), S, C, V, r, _stream())
+    _lib.check(rc, "tn_class_rows")
+    return F, G
+
+
+def npairs(m):
+    return m * (m + 1) // 2
+
+
+def gram(mode, fa: Factor, fb: Factor, fc: Factor, w, rows, M=None, accumulate=False):
+    """M[qa,qb,qc] (+)= sum_rows w * pair(fa)[qa] * pair(fb)[qb] * pair(fc)[qc]."""
+    lib = _lib.load()
+    _need_cuda(fa.tensor, fb.tensor, fc.tensor, w)
+    n = npairs(fa.m) * npairs(fb.m) * npairs(fc.m)
+    dev = fa.tensor.device
+    if M is None:
+        M = torch.empty((n,), dtype=torch.float64, device=dev)
+        accumulate = False
+    ks = lib.tn_gram_ksplit(rows, fa.m, fb.m, fc.m, mode)
+    work = None
+    if mode == GRAM_FP64 and (ks > 1 or accumulate):
+        work = torch.empty((ks * n,), dtype=torch.float64, device=dev)
+    a, b, c = fa.c(), fb.c(), fc.c()
+    rc = lib.tn_gram_kr3(mode, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), _p(w), rows, _p(M), _p(work), ks,
+                         1 if accumulate else 0, _stream())
+    _lib.check(rc, "tn_gram_kr3")
+    return M
+
+
+def rhs(fa: Factor, fb: Factor, fc: Factor, w, rows, b=None, accumulate=False):
+    """b[ia,ib,ic] (+)= sum_rows w * fa[ia] fb[ib] fc[ic]."""
+    lib = _lib.load()
+    _need_cuda(fa.tensor, fb.tensor, fc.tensor, w)
+    n = fa.m * fb.m * fc.m
+    dev = fa.tensor.device
+    if b is None:
+        b = torch.empty((n,), dtype=torch.float64, device=dev)
+        accumulate = False
+    ks = lib.tn_rhs_ksplit(rows, fa.m, fb.m, fc.m)
+    work = torch.empty((ks * n,), dtype=torch.float64, device=dev) if (ks > 1 or accumulate) else None
+    a, bb, c = fa.c(), fb.c(), fc.c()
+    rc = lib.tn_rhs_kr3(ctypes.byref(a), ctypes.byref(bb), ctypes.byref(c), _p(w), rows, _p(b), _p(work), ks,
+                        1 if accumulate else 0, _stream())
+    _lib.check(rc, "tn_rhs_kr3")
+    return b
+
+
+def _int3(v):
+    return (ctypes.c_int * 3)(*v)
+
+
+def gram_sigma(M, m_pos, role_of_pos):
+    lib = _lib.load()
+    sigma = torch.empty((1,), dtype=torch.float64, device=M.device)
+    _lib.check(lib.tn_gram_sigma(_p(M), _int3(m_pos), _int3(role_of_pos), _p(sigma), _stream()), "tn_gram_sigma")
+    return sigma
+
+
+def gram_expand(M, m_pos, role_of_pos, sigma, ridge, A=None):
+    """Dense scaled system A = expand(M)/sigma + ridge*I, row stride padded to a multiple of 8."""
+    lib = _lib.load()
+    P = m_pos[0] * m_pos[1] * m_pos[2]
+    lda = (P + 7) // 8 * 8
+    if A is None:
+        A = torch.empty((P, lda), dtype=torch.float64, device=M.device)
+    _lib.check(lib.tn_gram_expand(_p(M), _int3(m_pos), _int3(role_of_pos), _p(sigma), float(ridge), _p(A), A.stride(0),
+                                  _stream()), "tn_gram_expand")
+    return A
+
+
+def rhs_prepare(b, theta, sigma, ridge):
+    lib = _lib.load()
+    P = b.numel()
+    out = torch.empty((P,), dtype=torch.float64, device=b.device)
+    theta = theta.contiguous() if theta is not None else None
+    _lib.check(lib.tn_rhs_prepare(_p(b), _p(theta), _p(sigma), float(ridge), _p(out), P, _stream()), "tn_rhs_prepare")
+    return out
+
+
+def cholesky_solve(A, rhs_vec):
+    """In place: A (P x lda) <- its Cholesky factor (lower), rhs_vec <- solution.  Returns info tensor."""
+    lib = _lib.load()
+    P = A.shape[0]
+    _need_cuda(A, rhs_vec)
+    work = torch.empty((lib.tn_cholesky_work_elems(P),), dtype=torch.float64, device=A.device)
+    info = torch.zeros((1,), dtype=torch.int32, device=A.device)
+    _lib.check(lib.tn_cholesky_solve(_p(A), A.stride(0), P, _p(rhs_vec), _p(work), ctypes.c_void_p(info.data_ptr()),
+                                     _stream()), "tn_cholesky_solve")
+    return info
+
+
+def update_node(theta, step, lr=1.0, adaptive_step=False, max_norm=None):
+    """theta (contiguous) <- theta + lr*step, in place."""
+    lib = _lib.load()
+    _need_cuda(theta, step)
+    assert theta.is_contiguous() and step.is_contiguous()
+    _lib.check(lib.tn_update_node(_p(theta), _p(step), theta.numel(), float(lr), 1 if adaptive_step else 0,
+                                  float(max_norm) if max_norm is not None else -1.0, None, _stream()), "tn_update_node")
+    return theta
+
+
+def qr(a):
+    """a (m x n contiguous, m >= n) <- Q in place; returns R (n x n)."""
+    lib = _lib.load()
+    _need_cuda(a)
+    assert a.is_contiguous() and a.dim() == 2
+    m, n = a.shape
+    r = torch.empty((n, n), dtype=torch.float64, device=a.device)
+    _lib.check(lib.tn_qr(_p(a), m, n, _p(r), _stream()), "tn_qr")
+    return r
+
+
+def matvec(fa: Factor, fb: Factor, fc: Factor, w, rows, v, out=None):
+    """out = J^T diag(w) J v with J[row,(ia,ib,ic)] = fa fb fc."""
+    lib = _lib.load()
+    _need_cuda(fa.tensor, fb.tensor, fc.tensor, w, v)
+    n = fa.m * fb.m * fc.m
+    if out is None:
+        out = torch.empty((n,), dtype=torch.float64, device=v.device)
+    work = torch.empty((lib.tn_matvec_work_elems(rows, fa.m, fb.m, fc.m),), dtype=torch.float64, device=v.device)
+    a, b, c = fa.c(), fb.c(), fc.c()
+    v = v.contiguous()
+    _lib.check(lib.tn_matvec_kr3(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), _p(w), rows, _p(v), _p(out), _p(work),
+                                 _stream()), "tn_matvec_kr3")
+    return out

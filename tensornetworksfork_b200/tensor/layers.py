@@ -1,0 +1,224 @@
+"""Layer constructors: topology and initial state of the models the sweep fits.
+
+They mirror the reference's constructors (tensor/layers.py:9-97 MainNodeLayer, :114-192
+TensorNetworkLayer, :194-221 TensorTrainLayer, :1549-1625 CPDLayer) in name, arguments, label
+scheme and -- because parity needs identical initial cores -- in the *order and shape of the random
+draws* for a given seed.  The graphs they build are handed to the B200 sweep engine
+(``network.TensorNetwork`` / ``cpd.CPDNetwork``) instead of the reference's einsum engine.
+"""
+import torch
+from torch import nn
+
+from .network import TensorNetwork
+from .node import TensorNode
+
+
+def chain_bond_dims(n_sites, r, f, constrict_bond=True, perturb=False):
+    """Bond dimensions d[0..n] of a chain (d[0] = d[n] = 1).
+
+    Random-init chains grow bonds from both ends towards the middle, ``min(r, d*f)`` per step when
+    ``constrict_bond`` (reference layers.py:20-30,58-73: left side gets the extra core for odd
+    remainders).  Identity-init ('perturb') chains grow from the left only and keep the last bond at
+    ``r`` (layers.py:40-57).
+    """
+    if n_sites == 1:
+        return [1, 1]
+    grow = (lambda d: min(r, d * f)) if constrict_bond else (lambda d: r)
+    d = [None] * (n_sites + 1)
+    d[0] = d[n_sites] = 1
+    if perturb:
+        d[n_sites - 1] = r
+        for j in range(n_sites - 2):
+            d[j + 1] = grow(d[j])
+        if n_sites == 2:
+            d[1] = grow(1)
+        return d
+    n_left = 1 + max(0, (n_sites - 2) // 2)
+    n_right = 1 + max(0, (n_sites - 3) // 2)
+    for j in range(n_left):
+        d[j + 1] = grow(d[j])
+    for j in range(n_right):
+        d[n_sites - 1 - j] = grow(d[n_sites - j])
+    return d
+
+
+def _identity_core(rl, f, rr, dtype=None):
+    """Core that passes the bond through on the LAST feature (the bias column) and is zero elsewhere
+    (reference layers.py:32-38): ones if either bond is 1, else a rectangular identity."""
+    blk = torch.ones(rl, rr, dtype=dtype) if (rl == 1 or rr == 1) else torch.eye(rl, rr, dtype=dtype)
+    core = torch.zeros(rl, 1, f, rr, dtype=blk.dtype)
+    core[:, 0, f - 1, :] = blk
+    return core
+
+
+class MainNodeLayer(nn.Module):
+    """The train cores A1..AN with labels r{i} -[c{i}|c, p{i}]- r{i+1} (reference layers.py:9-97)."""
+
+    def __init__(self, N, r, f, output_shape=tuple(), down_label="p", horizontal_label="r{0}", constrict_bond=True,
+                 perturb=False, dtype=None):
+        super().__init__()
+        output_shape = output_shape if isinstance(output_shape, tuple) else (output_shape,)
+        if N == 1:
+            r = 1
+        dims = chain_bond_dims(N, r, f, constrict_bond, perturb)
+        blocks = None
+        if perturb:
+            # draw order matters for seed parity: first core's noise, then last core's (layers.py:41-44)
+            first = _identity_core(1, f, dims[1], dtype)
+            first = first * (1 + 0.02 * torch.randn_like(first))
+            last = _identity_core(dims[N - 1] if N > 1 else r, f, 1, dtype)
+            last = last * (1 + 0.02 * torch.randn_like(last))
+            blocks = [first] + [_identity_core(dims[i], f, dims[i + 1], dtype) for i in range(1, N - 1)] + ([last] if N > 1 else [])
+        self.labels = ["s"]
+        self.nodes = []
+        for i in range(1, N + 1):
+            if i - 1 < len(output_shape):
+                up, up_label = output_shape[i - 1], f"c{i}"
+                self.labels.append(up_label)
+            else:
+                up, up_label = 1, "c"
+            left_label, right_label = horizontal_label.format(i), horizontal_label.format(i + 1)
+            init = blocks[i - 1] if perturb else (dims[i - 1], up, f, dims[i])
+            self.nodes.append(TensorNode(init, [left_label, up_label, down_label.format(i), right_label], l=left_label,
+                                         r=right_label, name=f"A{i}", dtype=dtype))
+
+
+class InputNodeLayer(nn.Module):
+    """Placeholder input nodes X1..XN with labels (s, p{i}) (reference layers.py:99-112)."""
+
+    def __init__(self, N, f, label="p", dtype=None):
+        super().__init__()
+        self.nodes = [TensorNode((1, f), ["s", label.format(i)], name=f"X{i}", dtype=dtype) for i in range(1, N + 1)]
+
+
+class TensorNetworkLayer(nn.Module):
+    """Owner of a tensor network; state = the tensors of its train nodes (reference layers.py:114-192)."""
+
+    def __init__(self, tensor_network=None):
+        super().__init__()
+        self.set_tensor_network(tensor_network)
+
+    def set_tensor_network(self, tensor_network=None):
+        self.tensor_network = tensor_network
+        self.labels = tensor_network.output_labels if tensor_network is not None else None
+        self.parametrized = False
+        self.nodes = tensor_network.train_nodes if tensor_network is not None else []
+
+    def node_states(self, detach=True):
+        return {f"tensor_param_{i}": (n.tensor.detach().clone() if detach else n.tensor)
+                for i, n in enumerate(self.tensor_network.train_nodes)}
+
+    def load_node_states(self, tensor_params, set_value=False):
+        for i, n in enumerate(self.tensor_network.train_nodes):
+            key = f"tensor_param_{i}"
+            if key not in tensor_params:
+                raise ValueError(f"Missing parameter: {key}")
+            if set_value:
+                n.tensor = tensor_params[key]
+            else:
+                n.tensor.data.copy_(tensor_params[key].detach().clone())
+        self.tensor_network.reset_stacks()
+
+    def cuda(self, *a, **k):
+        self.tensor_network.cuda()
+        return super().cuda(*a, **k)
+
+    def to(self, *a, **k):
+        self.tensor_network.to(*a, **k)
+        return super().to(*a, **k)
+
+    def cpu(self, *a, **k):
+        self.tensor_network.to("cpu")
+        return super().cpu(*a, **k)
+
+    def forward(self, x, to_tensor=True):
+        out = self.tensor_network.forward(x)
+        if self.labels is not None:
+            out.permute_first(*self.labels)
+        return out.tensor if to_tensor else out
+
+    def num_parameters(self):
+        return sum(n.tensor.numel() for n in self.tensor_network.train_nodes)
+
+    @staticmethod
+    def zip_connect(nodes1, nodes2, label="p", priority=-1):
+        if len(nodes1) != len(nodes2):
+            raise ValueError("The number of nodes in both lists must be the same.")
+        for i, (a, b) in enumerate(zip(nodes1, nodes2), 1):
+            a.connect(b, label.format(i), priority=priority)
+
+    @staticmethod
+    def horizontal_connect(nodes):
+        for a, b in zip(nodes[:-1], nodes[1:]):
+            if a.right_labels and b.left_labels and a.right_labels[0] != b.left_labels[0]:
+                raise ValueError(f"Right label of the first node does not match left label of the second node. "
+                                 f"Nodes: {a.name}, {b.name}")
+            a.connect(b, a.right_labels[0], priority=1)
+
+
+class TensorTrainLayer(TensorNetworkLayer):
+    """Tensor train with one input per core (reference layers.py:194-221)."""
+
+    def __init__(self, num_carriages, bond_dim, input_features, output_shape=tuple(), squeeze=True, constrict_bond=True,
+                 perturb=False, dtype=None, seed=None):
+        super().__init__()
+        self.num_carriages = num_carriages
+        self.bond_dim = bond_dim
+        self.input_features = input_features
+        self.output_shape = output_shape if isinstance(output_shape, tuple) else (output_shape,)
+        if seed is not None:
+            torch.manual_seed(seed)
+            if torch.cuda.is_available():
+                torch.cuda.manual_seed(seed)
+        self.main_node_layer = MainNodeLayer(num_carriages, bond_dim, input_features, output_shape=output_shape,
+                                             down_label="p{0}", constrict_bond=constrict_bond, perturb=perturb, dtype=dtype)
+        self.horizontal_connect(self.main_node_layer.nodes)
+        self.input_node_layer = InputNodeLayer(num_carriages, input_features, label="p{0}", dtype=dtype)
+        self.zip_connect(self.input_node_layer.nodes, self.main_node_layer.nodes, label="p{0}")
+        if squeeze:
+            for n in self.main_node_layer.nodes:
+                n.squeeze(self.main_node_layer.labels)
+        self.set_tensor_network(TensorNetwork(self.input_node_layer.nodes, self.main_node_layer.nodes,
+                                              output_labels=self.main_node_layer.labels))
+
+
+class CPDLayer(TensorNetworkLayer):
+    """Rank-R canonical polyadic model: factor i is (b, p[, o]) (reference layers.py:1549-1625)."""
+
+    def __init__(self, num_factors, rank, input_features, output_shape=tuple(), perturb=False, seed=None):
+        from .cpd import CPDNetwork
+        self.num_factors = num_factors
+        self.rank = rank
+        self.input_features = input_features
+        self.output_shape = output_shape if isinstance(output_shape, tuple) else (output_shape,)
+        if seed is not None:
+            torch.manual_seed(seed)
+            if torch.cuda.is_available():
+                torch.cuda.manual_seed(seed)
+        # inputs are created first: their (unused) random draws advance the generator (layers.py:1569-1576)
+        x_nodes = [TensorNode((1, input_features), ["s", "p"], name=f"X{i}") for i in range(1, num_factors + 1)]
+        factors = []
+        labels = ["s"]
+        for i in range(1, num_factors + 1):
+            out_dim = self.output_shape[i - 1] if i - 1 < len(self.output_shape) else 1
+            if i == 1:
+                if num_factors == 1:
+                    node = TensorNode((input_features, out_dim), ["p", "o"], name="A1")
+                else:
+                    node = TensorNode((rank, input_features, out_dim), ["b", "p", "o"], name="A1")
+                labels.append("o")
+            else:
+                init = (rank, input_features)
+                if perturb:
+                    bias = torch.ones(rank, 1)
+                    if i == num_factors:
+                        bias = bias + 0.02 * torch.randn(rank, 1)
+                    init = torch.cat((torch.zeros(rank, input_features - 1), bias), dim=1)
+                node = TensorNode(init, ["b", "p"], name=f"A{i}")
+            factors.append(node)
+        for xn, an in zip(x_nodes, factors):
+            xn.connect(an, "p")
+        self.x_nodes = x_nodes
+        super().__init__(CPDNetwork(x_nodes, factors, output_labels=tuple(labels), sample_dim="s"))
+        self.nodes = factors
+        self.labels = tuple(labels)

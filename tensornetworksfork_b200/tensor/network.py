@@ -1,0 +1,886 @@
+"""Sweep engine: per-site Gauss-Newton / ALS on B200.
+
+Same public surface as the reference's ``TensorNetwork`` (tensor/network.py:13-932): a layer
+hands over its node graph and callers drive ``accumulating_swipe`` / ``lanczos_swipe`` /
+``scipy_swipe`` / ``forward`` / ``forward_batch`` / ``orthonormalize_*`` with the reference's
+keywords and return conventions.  Underneath nothing is shared with
+it: the graph is *recognised* once as a chain of sites, environments are cached per site
+(O(sites) work per sweep instead of the reference's O(sites^2)), and all arithmetic runs in the
+hand-written CUDA kernels of libtn_b200.so through ``ops``.  There is no CPU path.
+
+Parameters stay ordinary ``torch.Tensor`` objects on ``node.tensor`` (a new tensor per update),
+so ``node_states()/load_node_states()`` snapshots and EarlyStopping keep working; any outside
+change of a core is noticed through tensor identity/version and drops the cached environments,
+the way ``set_input``/``reset_stacks`` do in the reference (network.py:78-81, 329-345).
+"""
+import math
+import time
+
+import torch
+
+from .. import ops
+from ..ops import Factor
+from .bregman import hessian_terms
+from .node import TensorNode
+
+_GRAM_MODES = {"fp64": ops.GRAM_FP64, "tf32": ops.GRAM_TF32, "tf32x3": ops.GRAM_TF32X3, "3xtf32": ops.GRAM_TF32X3}
+
+
+class MappedInput:
+    """Raw samples ``X (N, F)`` plus a per-feature map evaluated inside the kernels.
+
+    Stands in for the list of pre-mapped ``(N, f)`` tensors the reference builds with ``fbasis`` /
+    ``polynomial_basis`` (models/tnml.py:11-23): site k reads column k of X and maps it on the fly,
+    so the n*f*N*8 bytes of mapped copies never exist.
+    """
+
+    def __init__(self, X, kind="sin-cos", degree=3):
+        if kind not in ("sin-cos", "polynomial"):
+            raise ValueError(f"unknown feature map {kind!r}")
+        self.X = X
+        self.kind = kind
+        self.f = 2 if kind == "sin-cos" else degree + 1
+        self.map_kind = ops.MAP_SINCOS if kind == "sin-cos" else ops.MAP_POLY
+
+    def __len__(self):
+        return self.X.shape[0]
+
+    @property
+    def device(self):
+        return self.X.device
+
+    def __getitem__(self, sl):
+        out = MappedInput.__new__(MappedInput)
+        out.X, out.kind, out.f, out.map_kind = self.X[sl], self.kind, self.f, self.map_kind
+        return out
+
+    def to(self, *a, **k):
+        out = MappedInput.__new__(MappedInput)
+        out.X, out.kind, out.f, out.map_kind = self.X.to(*a, **k), self.kind, self.f, self.map_kind
+        return out
+
+
+class _Site:
+    __slots__ = ("node", "left", "right", "phys", "cls", "input_index")
+
+
+def sweep_schedule(first_cols, second_cols, num_swipes, eps, eps_decay=None, skip_second=False, direction="l2r",
+                   eps_per_node=False):
+    """Order, half-sweep counter NS and epsilon of every update ``accumulating_swipe`` performs.
+
+    Pure function of the reference's control flow (network.py:409-433, 506-535, 604).
+    ``first_cols`` / ``second_cols`` are the column ids (``node_indices``) of the nodes of the first and
+    second half-sweep in visiting order.  Returns ``(NS, half, index_in_half, eps)`` tuples.  The
+    turn-around skip compares columns: a node is skipped when the previous half ended on its column.
+    """
+    out = []
+    NS = 0
+    last_first = None
+    last_second = None
+
+    def eps_at(ns):
+        e = eps[ns] if isinstance(eps, list) else eps
+        if eps_decay is not None:
+            e = e * eps_decay ** ns
+        return e
+
+    for _ in range(num_swipes):
+        e = eps_at(NS)
+        for i, col in enumerate(first_cols):
+            if eps_per_node:
+                e = eps[i if direction == "l2r" else len(first_cols) - 1 - i] if isinstance(eps, list) else eps
+            last_first = col
+            if last_second is not None and col == last_second:
+                continue
+            out.append((NS, 0, i, e))
+        NS += 1
+        if skip_second:
+            continue
+        e = eps_at(NS)
+        for i, col in enumerate(second_cols):
+            if eps_per_node:
+                e = eps[i if direction == "r2l" else len(second_cols) - 1 - i] if isinstance(eps, list) else eps
+            last_second = col
+            if last_first is not None and col == last_first:
+                continue
+            out.append((NS, 1, i, e))
+        NS += 1
+    return out
+
+
+def batch_mean_of_means(loss_rows, batch_size, row_offset=0, n_total=None, group=None):
+    """mean over minibatches of the per-minibatch mean loss (reference network.py:472-474): the last,
+    short batch weighs as much as a full one.  ``loss_rows`` is (S_local, ...) for global rows
+    [row_offset, row_offset+S_local); with ``group`` the per-batch sums are all-reduced."""
+    S = loss_rows.shape[0]
+    per = loss_rows.reshape(S, -1).mean(dim=1) if loss_rows.dim() > 1 else loss_rows
+    N = n_total if n_total is not None else S
+    bs = N if batch_size <= 0 or batch_size > N else batch_size
+    nb = (N + bs - 1) // bs
+    if nb == 1 and group is None:
+        return per.mean()
+    idx = (torch.arange(S, device=per.device) + row_offset) // bs
+    sums = torch.zeros(nb, dtype=per.dtype, device=per.device).index_add_(0, idx, per)
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(sums, group=group)
+    counts = torch.full((nb,), float(bs), dtype=per.dtype, device=per.device)
+    counts[-1] = float(N - (nb - 1) * bs)
+    return (sums / counts).mean()
+
+
+class TensorNetwork:
+    def __init__(self, input_nodes, main_nodes, train_nodes=None, output_labels=("s",), sample_dim="s"):
+        self.input_nodes = input_nodes
+        self.main_nodes = main_nodes
+        self.train_nodes = main_nodes if train_nodes is None else train_nodes
+        self.output_labels = output_labels
+        self.sample_dim = sample_dim
+        self.left_stacks = None   # kept for API compatibility; the engine uses its own caches
+        self.right_stacks = None
+        self.nodes, self.node_indices = self._discover_nodes()
+        self.gram_mode = "fp64"
+        self.process_group = None       # torch.distributed group: x, y are then this rank's row shard
+        self.shard_offset = 0           # global index of this rank's first row
+        self.shard_total = None         # global number of rows
+        self.lean_envs = False
+        self._sites = None
+        self._left = {}
+        self._right = {}
+        self._stamps = None
+        self._data_key = None
+        self._data = None
+        self.last_site_seconds = None
+
+    # ------------------------------------------------------------------ graph / plan
+    def _discover_nodes(self):
+        idx = {n: i for i, n in enumerate(self.main_nodes)}
+        seen = list(self.main_nodes)
+        queue = list(self.main_nodes)
+        while queue:
+            cur = queue.pop(0)
+            for lab, other in cur.connections.items():
+                if other not in idx and not cur.is_horizontal_bond(lab):
+                    idx[other] = idx[cur]
+                    seen.append(other)
+                    queue.append(other)
+        return sorted(seen, key=lambda n: n.name), idx
+
+    def cuda(self):
+        for n in self.nodes:
+            n.cuda()
+        return self
+
+    def to(self, device=None, dtype=None):
+        for n in self.nodes:
+            n.to(device=device, dtype=dtype)
+        return self
+
+    def _plan(self):
+        if self._sites is not None:
+            return self._sites
+        out_labels = [l for l in self.output_labels if l != self.sample_dim]
+        sites = []
+        for node in self.main_nodes:
+            s = _Site()
+            s.node = node
+            s.left = node.left_labels[0] if node.left_labels else None
+            s.right = node.right_labels[0] if node.right_labels else None
+            if len(node.left_labels) > 1 or len(node.right_labels) > 1:
+                raise NotImplementedError(f"{node.name}: more than one bond per side is not a plain chain")
+            cls = [l for l in node.dim_labels if l in out_labels]
+            if len(cls) > 1:
+                raise NotImplementedError(f"{node.name}: more than one output leg")
+            s.cls = cls[0] if cls else None
+            phys = [(lab, other) for lab, other in node.connections.items() if other in self.input_nodes]
+            if len(phys) != 1:
+                raise NotImplementedError(f"{node.name}: expected exactly one input node, found {len(phys)} "
+                                          "(this engine covers plain tensor-train chains; see DESIGN.md)")
+            s.phys = phys[0][0]
+            s.input_index = self.input_nodes.index(phys[0][1])
+            known = {s.left, s.right, s.cls, s.phys} - {None}
+            extra = [l for l in node.dim_labels if l not in known]
+            if extra:
+                raise NotImplementedError(f"{node.name}: unsupported legs {extra}")
+            sites.append(s)
+        for a, b in zip(sites[:-1], sites[1:]):
+            if a.right is None or a.right != b.left:
+                raise NotImplementedError(f"{a.node.name}-{b.node.name}: bond labels do not chain")
+        if len([s for s in sites if s.cls is not None]) > 1:
+            raise NotImplementedError("more than one site carries an output leg")
+        self._sites = sites
+        return sites
+
+    def _owner(self):
+        for k, s in enumerate(self._plan()):
+            if s.cls is not None and s.node.dim_size(s.cls) > 1:
+                return k
+        return None
+
+    def _canon(self, k):
+        """Core k as a (r_l, c, f, r_r) tensor (a view when the label order already is canonical)."""
+        s = self._plan()[k]
+        node = s.node
+        order = [l for l in (s.left, s.cls, s.phys, s.right) if l is not None and l in node.dim_labels]
+        t = node.tensor.permute(*[node.dim_labels.index(l) for l in order])
+        rl = node.dim_size(s.left) if s.left in node.dim_labels else 1
+        c = node.dim_size(s.cls) if s.cls in node.dim_labels else 1
+        f = node.dim_size(s.phys)
+        rr = node.dim_size(s.right) if s.right in node.dim_labels else 1
+        return t.reshape(rl, c, f, rr)
+
+    def _from_canon(self, k, t4):
+        """(r_l, c, f, r_r) tensor -> tensor in the node's own label order and shape."""
+        s = self._plan()[k]
+        node = s.node
+        order = [l for l in (s.left, s.cls, s.phys, s.right) if l is not None and l in node.dim_labels]
+        t = t4.reshape([node.dim_size(l) for l in order])
+        return t.permute(*[order.index(l) for l in node.dim_labels]).contiguous()
+
+    # ------------------------------------------------------------------ data binding / caches
+    def _bind(self, x):
+        """Per-site Factor descriptors for a data object (tensor shared by all sites, list, MappedInput)."""
+        sites = self._plan()
+        facs = []
+        if isinstance(x, MappedInput):
+            X = x.X
+            for k, s in enumerate(sites):
+                if s.node.dim_size(s.phys) != x.f:
+                    raise ValueError(f"site {k}: core has f={s.node.dim_size(s.phys)}, feature map gives {x.f}")
+                facs.append(Factor(X, m=x.f, map_kind=x.map_kind, col=s.input_index))
+            return facs, X.shape[0], X.device
+        if isinstance(x, (list, tuple)):
+            for k, s in enumerate(sites):
+                t = x[s.input_index]
+                if t.dim() != 2 or t.stride(1) != 1:
+                    t = t.reshape(t.shape[0], -1).contiguous()
+                if t.shape[1] != s.node.dim_size(s.phys):
+                    raise ValueError(f"site {k}: input has {t.shape[1]} features, core expects {s.node.dim_size(s.phys)}")
+                facs.append(Factor(t, m=t.shape[1]))
+            return facs, x[0].shape[0], x[0].device
+        t = x
+        if t.dim() != 2 or t.stride(1) != 1:
+            t = t.reshape(t.shape[0], -1).contiguous()
+        for k, s in enumerate(sites):
+            if t.shape[1] != s.node.dim_size(s.phys):
+                raise ValueError(f"site {k}: input has {t.shape[1]} features, core expects {s.node.dim_size(s.phys)}")
+            facs.append(Factor(t, m=t.shape[1]))
+        return facs, t.shape[0], t.device
+
+    @staticmethod
+    def _key_of(x):
+        if isinstance(x, MappedInput):
+            return ("map", id(x.X), x.kind, x.f)
+        if isinstance(x, (list, tuple)):
+            return ("list",) + tuple(id(t) for t in x)
+        return ("tensor", id(x))
+
+    def set_input(self, x):
+        """Bind training data; a different object drops the cached environments (network.py:329-345)."""
+        key = self._key_of(x)
+        if key == self._data_key:
+            return False
+        self._data_key = key
+        self._data = (x,) + self._bind(x)   # keep x alive so ids stay unique
+        self._left.clear()
+        self._right.clear()
+        return True
+
+    def reset_stacks(self, node=None):
+        self._left.clear()
+        self._right.clear()
+        self.left_stacks = None
+        self.right_stacks = None
+
+    def _stamp(self):
+        return [(id(s.node.tensor), s.node.tensor._version) for s in self._plan()]
+
+    def _check_external(self):
+        st = self._stamp()
+        if self._stamps != st:
+            self._left.clear()
+            self._right.clear()
+            self._stamps = st
+
+    def _core_changed(self, k):
+        for j in [j for j in self._left if j >= k]:
+            del self._left[j]
+        for j in [j for j in self._right if j <= k]:
+            del self._right[j]
+        self._stamps = self._stamp()
+
+    # ------------------------------------------------------------------ environments
+    def _step(self, env, fac, k, left, rows_S):
+        """One environment step through site k.  env: (S, c, r) or None; returns (S, c', r')."""
+        G = self._canon(k)
+        rl, c, f, rr = G.shape
+        S = rows_S
+        if left:
+            r_in, r_out = rl, rr
+            core = G if c == 1 else G.permute(0, 2, 1, 3)          # (rl, f, c, rr)
+        else:
+            r_in, r_out = rr, rl
+            core = G.permute(3, 2, 1, 0)                           # (rr, f, c, rl)
+        cin = 1 if env is None else env.shape[1]
+        if c == 1:
+            core3 = (core.reshape(rl, f, rr) if left else core.reshape(rr, f, rl))
+            rows = S * cin
+            e2 = None if env is None else env.reshape(rows, r_in)
+            out = ops.env_update(e2, fac, core3, rows, cdiv=cin)
+            return out.view(S, cin, r_out)
+        if cin != 1:
+            raise NotImplementedError("two class legs meet")
+        core3 = core.reshape(r_in, f, c * r_out)
+        e2 = None if env is None else env.reshape(S, r_in)
+        out = ops.env_update(e2, fac, core3, S, cdiv=1)
+        return out.view(S, c, r_out)
+
+    def _get_left(self, k):
+        """Environment of sites 0..k (None for k < 0)."""
+        if k < 0:
+            return None
+        _, facs, S, _ = self._data
+        j = k
+        while j >= 0 and j not in self._left:
+            j -= 1
+        env = self._left[j] if j >= 0 else None
+        for i in range(j + 1, k + 1):
+            env = self._step(env, facs[i], i, True, S)
+            self._left[i] = env
+        return env
+
+    def _get_right(self, k):
+        """Environment of sites k..n-1 (None for k >= n)."""
+        n = len(self._plan())
+        if k >= n:
+            return None
+        _, facs, S, _ = self._data
+        j = k
+        while j < n and j not in self._right:
+            j += 1
+        env = self._right[j] if j < n else None
+        for i in range(j - 1, k - 1, -1):
+            env = self._step(env, facs[i], i, False, S)
+            self._right[i] = env
+        return env
+
+    # ------------------------------------------------------------------ forward
+    def _chain_forward(self, x):
+        """Prediction (S, C) for arbitrary data, without touching the training caches."""
+        facs, S, dev = self._bind(x)
+        self._require_cuda(dev)
+        env = None
+        for k in range(len(self._plan())):
+            env = self._step(env, facs[k], k, True, S)
+        return env[:, :, 0]
+
+    def _require_cuda(self, dev):
+        if dev.type != "cuda":
+            raise RuntimeError("tensornetworksfork_b200 runs on CUDA devices only (no CPU fallback); move data and "
+                               "model with .to('cuda')")
+        for n in self.main_nodes:
+            if n.tensor.device != dev:
+                raise RuntimeError(f"core {n.name} lives on {n.tensor.device}, data on {dev}")
+
+    def forward(self, x, to_tensor=False):
+        """Prediction.  Returns a TensorNode labelled by ``output_labels`` (reference network.py:115-137)
+        or the bare tensor."""
+        y = self._chain_forward(x)
+        C = self._num_outputs()
+        out_labels = [l for l in self.output_labels if l != self.sample_dim]
+        if not out_labels:
+            y = y[:, 0]
+        if to_tensor:
+            return y
+        return TensorNode(y, [self.sample_dim] + out_labels, name="O")
+
+    def forward_batch(self, x, batch_size):
+        """Reference network.py:139-150.  Batching only bounds temporary memory here."""
+        n = len(x) if not isinstance(x, (list, tuple)) else x[0].shape[0]
+        if batch_size <= 0 or batch_size >= n:
+            return self.forward(x, to_tensor=True)
+        chunk = max(batch_size, 1 << 16)  # same numbers, fewer launches: rows are independent
+        outs = []
+        for lo in range(0, n, chunk):
+            xb = x[lo:lo + chunk] if not isinstance(x, (list, tuple)) else [t[lo:lo + chunk] for t in x]
+            outs.append(self.forward(xb, to_tensor=True))
+        return torch.cat(outs, dim=0)
+
+    def _num_outputs(self):
+        k = self._owner()
+        if k is None:
+            return 1
+        s = self._plan()[k]
+        return s.node.dim_size(s.cls)
+
+    # ------------------------------------------------------------------ local system of one site
+    def _site_problem(self, k, y, loss_fn):
+        """Prediction, loss terms and the three Kronecker factors of site k's Jacobian.
+
+        Returns dict with: yhat (S,C), loss (S[,C]), gram factors + weights + rows, rhs factors + weights,
+        m_pos (sizes of the three parameter positions in canonical (a,c,p,b) order, merged to three).
+        """
+        _, facs, S, dev = self._data
+        G = self._canon(k)
+        rl, ck, f, rr = G.shape
+        L = self._get_left(k - 1)
+        R = self._get_right(k + 1)
+        owner = self._owner()
+        C = self._num_outputs()
+        xk = facs[k]
+        one = ops.ones_factor(G)
+
+        def fac_of(env, r, div):
+            if env is None:
+                return one
+            return Factor(env.reshape(-1, r), m=r, div=div)
+
+        # ---- prediction
+        if C == 1:
+            Lf = None if L is None else L.reshape(S, rl)
+            Rf = R.reshape(S, rr) if R is not None else torch.ones((1, 1), dtype=torch.float64, device=dev)
+            yhat = ops.predict(Lf, xk, G.reshape(rl, f, rr), Rf, S, dot_div=1 if R is not None else (1 << 30)).view(S, 1)
+        elif owner < k:
+            Rf = R.reshape(S, rr) if R is not None else torch.ones((1, 1), dtype=torch.float64, device=dev)
+            yhat = ops.predict(L.reshape(S * C, rl), xk, G.reshape(rl, f, rr), Rf, S * C, cdiv=C,
+                               dot_div=C if R is not None else (1 << 30)).view(S, C)
+        elif owner > k:
+            Lf = None if L is None else L.reshape(S, rl)
+            yhat = ops.predict(Lf, xk, G.reshape(rl, f, rr), R.reshape(S * C, rr), S * C, cdiv=C, env_div=C).view(S, C)
+        else:
+            Lf = None if L is None else L.reshape(S, rl)
+            Rf = R.reshape(S, rr) if R is not None else torch.ones((1, 1), dtype=torch.float64, device=dev)
+            yT = torch.empty((C, S), dtype=torch.float64, device=dev)
+            for c in range(C):
+                ops.predict(Lf, xk, G[:, c].contiguous(), Rf, S, dot_div=1 if R is not None else (1 << 30), out=yT[c])
+            yhat = yT.t().contiguous()
+
+        out_labels = [l for l in self.output_labels if l != self.sample_dim]
+        y_in = yhat if out_labels else yhat[:, 0]
+        loss, g, U, lam = hessian_terms(loss_fn, y_in, y)
+        g = g.reshape(S, C).contiguous()
+        V = lam.shape[1]
+
+        # ---- factors
+        if C == 1:
+            w = (lam.reshape(S, V) * U.reshape(S, V) ** 2).sum(dim=1).contiguous()
+            fa, fb, fc = fac_of(L, rl, 1), xk, fac_of(R, rr, 1)
+            prob = dict(gram=(fa, fb, fc), gw=w, grows=S, rhs=(fa, fb, fc), rw=g.reshape(S).contiguous(), rrows=S,
+                        m_pos=(rl, f, rr))
+        else:
+            U = U.contiguous()
+            lamf = lam.reshape(S * V).contiguous()
+            xv = Factor(xk.tensor, m=xk.m, div=V, map_kind=xk.map_kind, col=xk.col)
+            if owner < k:
+                F, Gr = ops.class_rows(L, U, g)
+                prob = dict(gram=(Factor(F, m=rl), xv, fac_of(R, rr, V)), gw=lamf, grows=S * V,
+                            rhs=(Factor(Gr, m=rl), xk, fac_of(R, rr, 1)), rw=None, rrows=S, m_pos=(rl, f, rr))
+            elif owner > k:
+                F, Gr = ops.class_rows(R, U, g)
+                prob = dict(gram=(fac_of(L, rl, V), xv, Factor(F, m=rr)), gw=lamf, grows=S * V,
+                            rhs=(fac_of(L, rl, 1), xk, Factor(Gr, m=rr)), rw=None, rrows=S, m_pos=(rl, f, rr))
+            else:
+                if rl == 1:
+                    Fu = U.reshape(S * V, C)
+                    Fg = g
+                else:  # class leg on an interior site: merge (a, c) into one factor
+                    Lf = L.reshape(S, rl)
+                    Fu = (Lf[:, None, :, None] * U[:, :, None, :]).reshape(S * V, rl * C).contiguous()
+                    Fg = (Lf[:, :, None] * g[:, None, :]).reshape(S, rl * C).contiguous()
+                prob = dict(gram=(Factor(Fu, m=rl * C), xv, fac_of(R, rr, V)), gw=lamf, grows=S * V,
+                            rhs=(Factor(Fg, m=rl * C), xk, fac_of(R, rr, 1)), rw=None, rrows=S, m_pos=(rl * C, f, rr))
+        prob["yhat"] = yhat
+        prob["loss"] = loss
+        prob["keep"] = (L, R, U, lam, g)  # keep operands alive until the kernels have been enqueued
+        return prob
+
+    @staticmethod
+    def _roles(m_pos):
+        """Which parameter position becomes the N dimension of the Gram GEMM (least padded work)."""
+        n = [ops.npairs(m) for m in m_pos]
+        best = None
+        for c in range(3):
+            others = [t for t in range(3) if t != c]
+            nu = n[others[0]] * n[others[1]]
+            cost = (-(-nu // 128) * 128) * (-(-n[c] // 64) * 64)
+            if best is None or cost < best[0]:
+                best = (cost, c, others)
+        _, c, others = best
+        role_of_pos = [0, 0, 0]
+        role_of_pos[others[0]] = 0
+        role_of_pos[others[1]] = 1
+        role_of_pos[c] = 2
+        return role_of_pos, (others[0], others[1], c)
+
+    def _accumulate(self, prob):
+        """Local Gram (unique entries M), right-hand side b and the bookkeeping needed to expand them."""
+        mode = _GRAM_MODES[self.gram_mode]
+        m_pos = prob["m_pos"]
+        role_of_pos, order = self._roles(m_pos)
+        gf = prob["gram"]
+        nM = ops.npairs(m_pos[0]) * ops.npairs(m_pos[1]) * ops.npairs(m_pos[2])
+        P = m_pos[0] * m_pos[1] * m_pos[2]
+        dev = prob["yhat"].device
+        buf = torch.empty((nM + P,), dtype=torch.float64, device=dev)
+        M, b = buf[:nM], buf[nM:]
+        ops.gram(mode, gf[order[0]], gf[order[1]], gf[order[2]], prob["gw"], prob["grows"], M=M)
+        rf = prob["rhs"]
+        ops.rhs(rf[0], rf[1], rf[2], prob["rw"], prob["rrows"], b=b)
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(buf, group=self.process_group)
+        return M, b, role_of_pos
+
+    def _solve(self, k, M, b, m_pos, role_of_pos, method, eps):
+        """sigma-scaling, ridge and Cholesky solve (reference network.py:293-327) -> step in node layout."""
+        m = method.lower()
+        if m == "gradient":
+            return self._from_canon(k, (-b).reshape(self._canon(k).shape))
+        if m not in ("exact", "ridge_exact", "cholesky") and not m.startswith("ridge_cholesky"):
+            raise ValueError(f"Unknown method: {method}")
+        ridge = 0.0 if m in ("exact", "cholesky") else 2.0 * float(eps)
+        theta = self._canon(k).contiguous().view(-1)
+        sigma = ops.gram_sigma(M, m_pos, role_of_pos)
+        A = ops.gram_expand(M, m_pos, role_of_pos, sigma, ridge)
+        rhs = ops.rhs_prepare(b, theta, sigma, ridge)
+        info = ops.cholesky_solve(A, rhs)
+        bad = int(info.item())
+        if bad != 0:
+            raise torch.linalg.LinAlgError(
+                f"linalg.cholesky: The factorization could not be completed because the input is not positive-definite "
+                f"(the leading minor of order {bad} is not positive-definite).")
+        return self._from_canon(k, rhs.reshape(self._canon(k).shape))
+
+    def get_A_b(self, node, grad=None, hessian=None, method=None, y=None, loss_fn=None):
+        """Dense (A, b) of one node in the reference's layout (network.py:174-217), built from the
+        currently bound data.  Provided for inspection/tests; the sweep never forms the dense A."""
+        k = self.main_nodes.index(node)
+        if loss_fn is None:
+            loss_fn = _FixedTerms(grad, hessian)
+        prob = self._site_problem(k, y, loss_fn)
+        M, b, role_of_pos = self._accumulate(prob)
+        one = torch.ones((1,), dtype=torch.float64, device=M.device)
+        A = ops.gram_expand(M, prob["m_pos"], role_of_pos, one, 0.0)
+        P = A.shape[0]
+        dims, perm = self._layout(k)
+        A = A[:, :P].reshape(dims + dims)
+        A = A.permute(*(perm + [len(dims) + p for p in perm])).contiguous()
+        return A, self._from_canon(k, b.reshape(tuple(self._canon(k).shape)))
+
+    def _layout(self, k):
+        """(sizes of the node's legs in canonical order, permutation canonical -> node label order)."""
+        s = self._plan()[k]
+        node = s.node
+        order = [l for l in (s.left, s.cls, s.phys, s.right) if l is not None and l in node.dim_labels]
+        return [node.dim_size(l) for l in order], [order.index(l) for l in node.dim_labels]
+
+    def solve_system(self, node, A, b, method="exact", eps=0.0):
+        """Dense-input variant of the local solve for API compatibility (network.py:293-327)."""
+        P = b.numel()
+        A_f = A.reshape(P, P)
+        scale = A_f.diagonal().abs().mean()
+        scale = torch.where(scale == 0, torch.ones_like(scale), scale)
+        m = method.lower()
+        if m == "gradient":
+            return -b
+        if m not in ("exact", "ridge_exact", "cholesky") and not m.startswith("ridge_cholesky"):
+            raise ValueError(f"Unknown method: {method}")
+        ridge = 0.0 if m in ("exact", "cholesky") else 2.0 * float(eps)
+        lda = (P + 7) // 8 * 8
+        Ap = torch.zeros((P, lda), dtype=torch.float64, device=A.device)
+        Ap[:, :P] = A_f / scale
+        Ap.diagonal().add_(ridge)
+        rhs = -(b.reshape(P) / scale + ridge * node.tensor.reshape(P))
+        info = ops.cholesky_solve(Ap, rhs)
+        if int(info.item()) != 0:
+            raise torch.linalg.LinAlgError("linalg.cholesky: The factorization could not be completed because the "
+                                           "input is not positive-definite")
+        return rhs.reshape(b.shape)
+
+    # ------------------------------------------------------------------ QR re-gauge
+    def orthonormalize_left(self):
+        for n in self.main_nodes:
+            self.node_orthonormalize_left(n)
+
+    def orthonormalize_right(self):
+        for n in self.main_nodes:
+            self.node_orthonormalize_right(n)
+
+    def node_orthonormalize_left(self, node):
+        """core_k <- Q, core_{k+1} <- R core_{k+1} (reference network.py:625-660)."""
+        k = self.main_nodes.index(node)
+        if k >= len(self.main_nodes) - 1:
+            return
+        self._require_cuda(node.tensor.device)
+        G = self._canon(k)
+        rl, c, f, rr = G.shape
+        a = G.reshape(rl * c * f, rr).contiguous().clone()
+        if a.shape[0] < a.shape[1]:
+            raise NotImplementedError("QR re-gauge of a core with fewer rows than columns")
+        Rm = ops.qr(a)
+        node.tensor = self._from_canon(k, a.reshape(rl, c, f, rr))
+        Gn = self._canon(k + 1)
+        nl, nc, nf, nr = Gn.shape
+        newn = ops.env_update(None, Factor(Rm, m=rr), Gn.reshape(1, nl, nc * nf * nr), rr)
+        self.main_nodes[k + 1].tensor = self._from_canon(k + 1, newn.reshape(nl, nc, nf, nr))
+        self._core_changed(k)
+        self._core_changed(k + 1)
+
+    def node_orthonormalize_right(self, node):
+        """RQ via the doubly flipped QR; factor pushed into core_{k-1} (reference network.py:662-707)."""
+        k = self.main_nodes.index(node)
+        if k <= 0:
+            return
+        self._require_cuda(node.tensor.device)
+        G = self._canon(k)
+        rl, c, f, rr = G.shape
+        a = G.permute(1, 2, 3, 0).reshape(c * f * rr, rl)
+        if a.shape[0] < a.shape[1]:
+            raise NotImplementedError("QR re-gauge of a core with fewer rows than columns")
+        a = torch.flip(a, dims=[0, 1]).contiguous()
+        Rrev = ops.qr(a)
+        Q = torch.flip(a, dims=[0, 1]).reshape(c, f, rr, rl).permute(3, 0, 1, 2)
+        Rm = torch.flip(Rrev.t(), dims=[0, 1]).contiguous()          # (rl_old, rl_new)
+        node.tensor = self._from_canon(k, Q.reshape(rl, c, f, rr))
+        Gp = self._canon(k - 1)
+        pl, pc, pf, pr = Gp.shape
+        rows = pl * pc * pf
+        newp = ops.env_update(None, Factor(Gp.reshape(rows, pr).contiguous(), m=pr), Rm.reshape(1, pr, rl), rows)
+        self.main_nodes[k - 1].tensor = self._from_canon(k - 1, newp.reshape(pl, pc, pf, rl))
+        self._core_changed(k)
+        self._core_changed(k - 1)
+
+    # ------------------------------------------------------------------ the sweep
+    def _prepare_data(self, x, y_true, data_device, model_device):
+        """Bind (and if needed move) the training data.  Host-resident data is copied once per call,
+        not once per minibatch per site as the reference does (network.py:397-403,453-454)."""
+        target = model_device if model_device is not None else self.main_nodes[0].tensor.device
+        target = torch.device(target)
+
+        def mv(t):
+            if isinstance(t, MappedInput):
+                return t if t.device == target else t.to(target, non_blocking=True)
+            if isinstance(t, (list, tuple)):
+                moved = [mv(u) for u in t]
+                return t if all(a is b for a, b in zip(moved, t)) else moved
+            return t if t.device == target else t.to(target, non_blocking=True)
+
+        xm = mv(x)
+        ym = mv(y_true)
+        self._require_cuda(target)
+        self.set_input(xm)
+        if ym.dtype != torch.float64:
+            ym = ym.to(torch.float64)
+        return xm, ym
+
+    def _one_update(self, k, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss):
+        self._check_external()
+        prob = self._site_problem(k, y, loss_fn)
+        M, b, role_of_pos = self._accumulate(prob)
+        step = self._solve(k, M, b, prob["m_pos"], role_of_pos, method, eps)
+        node = self._plan()[k].node
+        new = node.tensor.detach().clone().contiguous()
+        ops.update_node(new.view(-1), step.view(-1), lr=lr, adaptive_step=adaptive_step, max_norm=max_norm)
+        node.tensor = new
+        self._core_changed(k)
+        if not need_loss:
+            return None
+        S = prob["yhat"].shape[0]
+        return batch_mean_of_means(prob["loss"], batch_size, row_offset=self.shard_offset,
+                                   n_total=self.shard_total if self.process_group is not None else S,
+                                   group=self.process_group)
+
+    def accumulating_swipe(self, x, y_true, loss_fn, node_order=None, batch_size=-1, num_swipes=1, lr=1.0, method="exact",
+                           eps=1e-12, eps_decay=None, convergence_criterion=None, orthonormalize=False, verbose=False,
+                           skip_second=False, blocks_input=False, timeout=None, data_device=None, model_device=None,
+                           disable_tqdm=None, block_callback=None, loss_callback=None, direction="l2r",
+                           update_or_reset_stack="reset", adaptive_step=False, min_norm=None, max_norm=None,
+                           eps_per_node=False):
+        """Reference tensor/network.py:379-608, same keywords and return value.
+
+        Differences that do not change results: A and b of a node are built from the whole data set in
+        one pass (they are sums over minibatches at fixed cores); ``batch_size`` only shapes the
+        reported mean-of-batch-means loss.  ``update_or_reset_stack`` is accepted; environments are
+        always kept incrementally.  ``method='gradient'`` (per-batch ascent quirk, network.py:469-470)
+        is not provided.
+        """
+        if blocks_input:
+            raise NotImplementedError("blocks_input (compressed-data experiment) is outside the sweep path")
+        if method == "gradient":
+            raise NotImplementedError("method='gradient' is not part of the B200 path")
+        x, y = self._prepare_data(x, y_true, data_device, model_device)
+        # node lists of the two half-sweeps, exactly as network.py:418-425,520-527 derive them
+        if node_order is None:
+            first, second = list(self.train_nodes), list(self.train_nodes)
+        elif isinstance(node_order, tuple):
+            first, second = list(node_order[0]), list(node_order[1])
+        else:
+            first, second = list(node_order), list(reversed(list(node_order)))
+        first = first if direction == "l2r" else list(reversed(first))
+        second = second if direction == "r2l" else list(reversed(second))
+        halves = (first, second)
+        col = lambda nd, i: self.node_indices[nd] if nd in self.node_indices else ("x", id(nd))
+        sched = sweep_schedule([col(nd, i) for i, nd in enumerate(first)], [col(nd, i) for i, nd in enumerate(second)],
+                               num_swipes, eps, eps_decay, skip_second, direction, eps_per_node)
+        start = time.time() if timeout is not None else None
+        need_loss = loss_callback is not None or (verbose and verbose > 1)
+        for NS, half, pos, eps_ in sched:
+            node = halves[half][pos]
+            if timeout is not None and (time.time() - start) > timeout:
+                print(f"Timeout reached ({timeout} seconds). Stopping accumulating_swipe.")
+                return False
+            k = self.main_nodes.index(node)
+            _method = "exact" if (eps_ == 0 and method == "ridge_exact") else method
+            try:
+                loss = self._one_update(k, y, loss_fn, _method, eps_, lr, batch_size, adaptive_step, max_norm, need_loss)
+            except torch.linalg.LinAlgError:
+                if verbose and verbose > 0:
+                    print(f"Singular system for node {node.name}")
+                return False
+            going_right = half == 0     # the first half re-gauges to the left, the second to the right (network.py:487-488,585-586)
+            if orthonormalize:
+                if going_right:
+                    self.node_orthonormalize_left(node)
+                else:
+                    self.node_orthonormalize_right(node)
+            if self.lean_envs:
+                drop = self._right if going_right else self._left
+                for j in [j for j in drop if (j <= k + 1 if going_right else j >= k - 1)]:
+                    del drop[j]
+            if need_loss:
+                lv = float(loss.item())
+                if verbose and verbose > 1:
+                    print(f"NS: {NS}, {'Left' if half == 0 else 'Right'} loss ({node.name}):", lv, f" (eps: {eps_})")
+                if loss_callback is not None:
+                    loss_callback(NS, node, lv)
+            if convergence_criterion is not None and convergence_criterion():
+                if verbose and verbose > 0:
+                    print("Converged (left pass)" if half == 0 else "Converged (right pass)")
+                if block_callback is not None:
+                    block_callback(NS, node)
+                return True
+            if block_callback is not None:
+                block_callback(NS, node)
+        return True
+
+    # ------------------------------------------------------------------ matrix-free sweeps
+    def _krylov_setup(self, k, y, loss_fn):
+        prob = self._site_problem(k, y, loss_fn)
+        gf, rf = prob["gram"], prob["rhs"]
+        b = ops.rhs(rf[0], rf[1], rf[2], prob["rw"], prob["rrows"])
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(b, group=self.process_group)
+
+        def matvec(v):
+            out = ops.matvec(gf[0], gf[1], gf[2], prob["gw"], prob["grows"], v.contiguous().view(-1))
+            if self.process_group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(out, group=self.process_group)
+            return out
+
+        return prob, b, matvec
+
+    def _krylov_swipe(self, x, y_true, loss_fn, solve, batch_size, num_swipes, lr, timeout, data_device, model_device,
+                      block_callback, loss_callback, what):
+        x, y = self._prepare_data(x, y_true, data_device, model_device)
+        start = time.time() if timeout is not None else None
+        for NS in range(num_swipes):
+            order = list(self.train_nodes) if NS % 2 == 0 else list(reversed(self.train_nodes))
+            for node in order:
+                if timeout is not None and (time.time() - start) > timeout:
+                    print(f"Timeout reached ({timeout} seconds). Stopping {what}.")
+                    return False
+                self._check_external()
+                k = self.main_nodes.index(node)
+                prob, b, matvec = self._krylov_setup(k, y, loss_fn)
+                if loss_callback is not None:
+                    S = prob["yhat"].shape[0]
+                    lv = batch_mean_of_means(prob["loss"], batch_size, row_offset=self.shard_offset,
+                                             n_total=self.shard_total if self.process_group is not None else S,
+                                             group=self.process_group)
+                    loss_callback(float(lv.item()))
+                step_c = solve(node, matvec, b)                       # canonical order, flat
+                step = self._from_canon(k, step_c.reshape(self._canon(k).shape))
+                new = node.tensor.detach().clone().contiguous()
+                ops.update_node(new.view(-1), step.view(-1), lr=lr)
+                node.tensor = new
+                self._core_changed(k)
+                if block_callback is not None:
+                    block_callback(NS, node)
+        return True
+
+    def lanczos_swipe(self, x, y_true, loss_fn, batch_size=1, num_swipes=1, lr=1.0, max_iter=50, tol=1e-6, verbose=False,
+                      timeout=None, data_device=None, model_device=None, disable_tqdm=None, block_callback=None,
+                      loss_callback=None, x0_fn=None):
+        """Reference tensor/network.py:709-832: Lanczos-Galerkin solve of A step = -b per node, matrix-free.
+        The start vector is random there (``randn_like``, :793); ``x0_fn(node, b)`` lets a caller inject one."""
+
+        def solve(node, matvec, b):
+            rhs = -b
+            x0 = x0_fn(node, b) if x0_fn is not None else torch.randn_like(rhs)
+            x0 = x0.reshape(-1)
+            vs = [torch.zeros_like(x0)]
+            alphas = []
+            betas = [None]
+            r0 = rhs - matvec(x0)
+            beta1 = torch.norm(r0)
+            betas.append(beta1)
+            vs.append(r0 / beta1)
+            j = 0
+            for j in range(1, max_iter + 1):
+                wv = matvec(vs[j]) - betas[j] * vs[j - 1] if j > 1 else matvec(vs[j])
+                a_j = (wv * vs[j]).sum()
+                alphas.append(a_j)
+                wv = wv - a_j * vs[j]
+                b_j = torch.norm(wv)
+                betas.append(b_j)
+                vs.append(wv / b_j)
+                if float(b_j.item()) < tol:
+                    break
+            Vm = torch.stack(vs[1:j + 1], dim=-1)
+            Tm = torch.diag(torch.stack(alphas))
+            if len(alphas) > 1:
+                off = torch.stack(betas[2:j + 1])
+                Tm = Tm + torch.diag(off, 1) + torch.diag(off, -1)
+            e1 = torch.zeros(len(alphas), dtype=x0.dtype, device=x0.device)
+            e1[0] = beta1
+            yv = torch.linalg.solve(Tm, e1)                          # j x j tridiagonal, j <= max_iter
+            return x0 + Vm @ yv
+
+        return self._krylov_swipe(x, y_true, loss_fn, solve, batch_size, num_swipes, lr, timeout, data_device, model_device,
+                                  block_callback, loss_callback, "lanczos_swipe")
+
+    def scipy_swipe(self, x, y_true, loss_fn, solver, batch_size=1, num_swipes=1, lr=1.0, max_iter=50, tol=1e-6, verbose=False,
+                    timeout=None, data_device=None, model_device=None, disable_tqdm=None, block_callback=None,
+                    loss_callback=None):
+        """Reference tensor/network.py:834-932.  ``solver`` is ``scipy.sparse.linalg.cg``/``minres``-like or one of
+        the strings 'cg' / 'minres', which select the on-device float64 solvers of this package
+        (the reference runs the SciPy recurrences in float32 on the host, :918,921)."""
+        sols = getattr(self, "_node_sols", None)
+        if sols is None:
+            sols = self._node_sols = {}
+
+        def solve(node, matvec, b):
+            from ..krylov import cg, minres, scipy_bridge
+            prev = sols.get(node)
+            if isinstance(solver, str):
+                fn = {"cg": cg, "minres": minres}[solver]
+                xs = fn(matvec, -b, x0=prev, maxiter=max_iter, rtol=tol)
+            else:
+                xs = scipy_bridge(solver, matvec, -b, x0=prev, maxiter=max_iter, rtol=tol)
+            sols[node] = xs
+            return xs if isinstance(xs, torch.Tensor) else torch.as_tensor(xs, dtype=b.dtype, device=b.device)
+
+        return self._krylov_swipe(x, y_true, loss_fn, solve, batch_size, num_swipes, lr, timeout, data_device, model_device,
+                                  block_callback, loss_callback, "scipy_swipe")
+
+
+class _FixedTerms:
+    """Adapter: a (grad, hessian) pair supplied by the caller, presented as a loss object."""
+
+    def __init__(self, g, H):
+        self.g, self.H = g, H
+
+    def forward(self, y_pred, y):
+        return torch.zeros(self.g.shape[0], dtype=self.g.dtype, device=self.g.device), self.g, self.H

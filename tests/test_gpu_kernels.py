@@ -1,0 +1,205 @@
+"""Kernel-level parity through the C ABI against the numpy oracle (needs a B200)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+from oracle import tn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+torch.set_default_dtype(torch.float64)
+
+from tensornetworksfork_b200 import ops  # noqa: E402
+from tensornetworksfork_b200.ops import Factor  # noqa: E402
+
+DEV = "cuda"
+
+
+def T(a):
+    return torch.tensor(np.ascontiguousarray(a), dtype=torch.float64, device=DEV)
+
+
+def pairs(F):
+    m = F.shape[1]
+    iu = [(i, j) for i in range(m) for j in range(i, m)]
+    return np.stack([F[:, i] * F[:, j] for i, j in iu], axis=1)
+
+
+@pytest.mark.parametrize("S,rin,f,rout", [(1, 1, 3, 2), (200, 4, 5, 6), (1000, 24, 2, 24), (333, 38, 29, 38), (130, 3, 7, 100),
+                                          (64, 100, 9, 70), (4177, 6, 9, 6)])
+def test_env_update_identity(S, rin, f, rout):
+    rng = np.random.default_rng(S + rin)
+    env = rng.normal(size=(S, rin))
+    x = rng.uniform(-1, 1, size=(S, f))
+    core = rng.normal(size=(rin, f, rout))
+    want = np.einsum("sa,sp,apb->sb", env, x, core)
+    got = ops.env_update(T(env), Factor(T(x), m=f), T(core), S).cpu().numpy()
+    assert gu.relerr(got, want) < 1e-13
+    dot = rng.normal(size=(S, rout))
+    yh = ops.predict(T(env), Factor(T(x), m=f), T(core), T(dot), S).cpu().numpy()
+    assert gu.relerr(yh, (want * dot).sum(1)) < 1e-13
+
+
+def test_env_update_chain_end_and_class_rows():
+    rng = np.random.default_rng(1)
+    S, C, f, r = 300, 3, 4, 5
+    x = rng.uniform(-1, 1, size=(S, f))
+    core = rng.normal(size=(1, f, r))
+    got = ops.env_update(None, Factor(T(x), m=f), T(core), S).cpu().numpy()
+    assert gu.relerr(got, x @ core[0]) < 1e-14
+    env = rng.normal(size=(S, C, r))
+    core2 = rng.normal(size=(r, f, 6))
+    got = ops.env_update(T(env).reshape(S * C, r), Factor(T(x), m=f), T(core2), S * C, cdiv=C).cpu().numpy()
+    want = np.einsum("sca,sp,apb->scb", env, x, core2).reshape(S * C, 6)
+    assert gu.relerr(got, want) < 1e-13
+    U = rng.normal(size=(S, 4, C))
+    g = rng.normal(size=(S, C))
+    F, G = ops.class_rows(T(env), T(U), T(g))
+    assert gu.relerr(F.cpu().numpy(), np.einsum("stc,sca->sta", U, env).reshape(S * 4, r)) < 1e-13
+    assert gu.relerr(G.cpu().numpy(), np.einsum("sc,sca->sa", g, env)) < 1e-13
+
+
+def test_env_update_feature_maps():
+    rng = np.random.default_rng(2)
+    S, F_, r = 500, 6, 7
+    X = rng.uniform(-1, 1, size=(S, F_))
+    env = rng.normal(size=(S, r))
+    for kind, f, mk, phi in (("sincos", 2, ops.MAP_SINCOS, orc.fbasis(X)), ("poly", 4, ops.MAP_POLY, orc.polynomial_basis(X, 3))):
+        core = rng.normal(size=(r, f, 5))
+        for col in (0, 3, F_ - 1):
+            want = np.einsum("sa,sp,apb->sb", env, phi[col], core)
+            got = ops.env_update(T(env), Factor(T(X), m=f, map_kind=mk, col=col), T(core), S).cpu().numpy()
+            assert gu.relerr(got, want) < 1e-13, (kind, col)
+
+
+@pytest.mark.parametrize("S,ma,mb,mc,V", [(50, 1, 3, 2, 1), (777, 4, 5, 4, 1), (1500, 6, 9, 6, 1), (400, 3, 4, 1, 1), (300, 5, 3, 4, 3),
+                                          (5000, 24, 2, 24, 1), (260, 12, 7, 12, 1)])
+def test_gram_and_rhs_fp64(S, ma, mb, mc, V):
+    rng = np.random.default_rng(S)
+    rows = S * V
+    Fa = rng.normal(size=(rows, ma))
+    Fb = rng.uniform(-1, 1, size=(S, mb))
+    Fc = rng.normal(size=(S, mc))
+    w = rng.normal(size=rows)
+    Fb_r, Fc_r = np.repeat(Fb, V, axis=0), np.repeat(Fc, V, axis=0)
+    J = np.einsum("ra,rp,rb->rapb", Fa, Fb_r, Fc_r).reshape(rows, -1)
+    A_want = (J * w[:, None]).T @ J
+    b_want = J.T @ w
+    fa, fb, fc = Factor(T(Fa), m=ma), Factor(T(Fb), m=mb, div=V), Factor(T(Fc), m=mc, div=V)
+    for role_of_pos, order in (([0, 1, 2], (0, 1, 2)), ([2, 0, 1], (1, 2, 0)), ([0, 2, 1], (0, 2, 1))):
+        facs = (fa, fb, fc)
+        M = ops.gram(ops.GRAM_FP64, facs[order[0]], facs[order[1]], facs[order[2]], T(w), rows)
+        one = torch.ones(1, device=DEV)
+        A = ops.gram_expand(M, (ma, mb, mc), role_of_pos, one, 0.0)
+        P = ma * mb * mc
+        assert gu.relerr(A[:, :P].cpu().numpy(), A_want) < 1e-12, role_of_pos
+        sig = ops.gram_sigma(M, (ma, mb, mc), role_of_pos)
+        assert abs(float(sig) - np.abs(np.diag(A_want)).mean()) < 1e-12 * max(1.0, np.abs(np.diag(A_want)).mean())
+    b = ops.rhs(fa, fb, fc, T(w), rows).cpu().numpy()
+    assert gu.relerr(b, b_want) < 1e-12
+    M2 = ops.gram(ops.GRAM_FP64, fa, fb, fc, T(w), rows)
+    M3 = ops.gram(ops.GRAM_FP64, fa, fb, fc, T(w), rows, M=M2.clone(), accumulate=True)
+    assert gu.relerr(M3.cpu().numpy(), 2 * M2.cpu().numpy()) < 1e-14
+    v = rng.normal(size=ma * mb * mc)
+    mv = ops.matvec(fa, fb, fc, T(w), rows, T(v)).cpu().numpy()
+    assert gu.relerr(mv, A_want @ v) < 1e-11
+
+
+@pytest.mark.parametrize("P", [1, 5, 64, 65, 100, 324, 900, 1200, 2888, 4500])
+def test_cholesky_solve(P):
+    rng = np.random.default_rng(P)
+    B = rng.normal(size=(P, P + 10))
+    A = B @ B.T / P + 0.5 * np.eye(P)
+    rhs = rng.normal(size=P)
+    lda = (P + 7) // 8 * 8
+    Ap = torch.zeros((P, lda), device=DEV)
+    Ap[:, :P] = T(A)
+    r = T(rhs)
+    info = ops.cholesky_solve(Ap, r)
+    assert int(info.item()) == 0
+    x = r.cpu().numpy()
+    res = np.linalg.norm(A @ x - rhs) / np.linalg.norm(rhs)
+    assert res < 1e-11, res
+    Lref = np.linalg.cholesky(A)
+    Lgot = np.tril(Ap[:, :P].cpu().numpy())
+    assert gu.relerr(Lgot, Lref) < 1e-11
+
+
+def test_cholesky_reports_non_spd():
+    P = 150
+    rng = np.random.default_rng(0)
+    B = rng.normal(size=(P, P))
+    A = B @ B.T
+    A[100, 100] = -1.0
+    Ap = torch.zeros((P, 152), device=DEV)
+    Ap[:, :P] = T(A)
+    r = T(rng.normal(size=P))
+    info = ops.cholesky_solve(Ap, r)
+    assert int(info.item()) == 101
+
+
+def test_solve_pipeline_matches_oracle():
+    rng = np.random.default_rng(3)
+    S, ma, mb, mc = 900, 4, 5, 4
+    Fa, Fb, Fc = rng.normal(size=(S, ma)), rng.uniform(-1, 1, size=(S, mb)), rng.normal(size=(S, mc))
+    w = np.full(S, 2.0)
+    g = rng.normal(size=S)
+    theta = rng.normal(size=ma * mb * mc)
+    J = np.einsum("ra,rp,rb->rapb", Fa, Fb, Fc).reshape(S, 1, -1)
+    A, b = orc.gram(J, g[:, None], w[:, None, None])
+    for eps in (1.0, 1e-3):
+        want = orc.solve_system(A, b, theta, "ridge_cholesky", eps)
+        fa, fb, fc = Factor(T(Fa), m=ma), Factor(T(Fb), m=mb), Factor(T(Fc), m=mc)
+        M = ops.gram(ops.GRAM_FP64, fa, fb, fc, T(w), S)
+        bb = ops.rhs(fa, fb, fc, T(g), S)
+        pos = (ma, mb, mc)
+        sig = ops.gram_sigma(M, pos, [0, 1, 2])
+        Ad = ops.gram_expand(M, pos, [0, 1, 2], sig, 2 * eps)
+        rv = ops.rhs_prepare(bb, T(theta), sig, 2 * eps)
+        info = ops.cholesky_solve(Ad, rv)
+        assert int(info.item()) == 0
+        assert gu.relerr(rv.cpu().numpy(), want) < 1e-10
+
+
+def test_update_node_variants():
+    rng = np.random.default_rng(4)
+    th, st = rng.normal(size=1000), 5 * rng.normal(size=1000)
+    for kw in (dict(lr=1.0), dict(lr=0.3), dict(lr=1.0, adaptive_step=True), dict(lr=1.0, max_norm=2.0),
+               dict(lr=0.5, adaptive_step=True, max_norm=1.0)):
+        want = orc.update_node(th, st, **kw)
+        t = T(th)
+        ops.update_node(t, T(st), **kw)
+        assert gu.relerr(t.cpu().numpy(), want) < 1e-14, kw
+
+
+@pytest.mark.parametrize("m,n", [(4, 2), (8, 4), (48, 24), (76, 38), (228, 38), (100, 100), (1102, 38), (9, 1)])
+def test_qr_matches_lapack_convention(m, n):
+    rng = np.random.default_rng(m * n)
+    A = rng.normal(size=(m, n))
+    Q, R = np.linalg.qr(A, mode="reduced")
+    a = T(A)
+    r = ops.qr(a)
+    assert gu.relerr(r.cpu().numpy(), R) < 1e-12
+    assert gu.relerr(a.cpu().numpy(), Q) < 1e-12
+
+
+def test_env_update_full_size_linearity():
+    """Config-3 size (N=515k, r=24, f=2): linearity in the environment and agreement of a strided
+    sample of rows with the oracle -- properties that do not need the oracle at full size."""
+    S, r, f = 515345, 24, 2
+    g = torch.Generator(device=DEV).manual_seed(0)
+    e1 = torch.randn((S, r), device=DEV, generator=g)
+    e2 = torch.randn((S, r), device=DEV, generator=g)
+    X = torch.rand((S, 90), device=DEV, generator=g) * 2 - 1
+    core = torch.randn((r, f, r), device=DEV, generator=g)
+    fx = Factor(X, m=2, map_kind=ops.MAP_SINCOS, col=17)
+    o1 = ops.env_update(e1, fx, core, S)
+    o2 = ops.env_update(e2, fx, core, S)
+    o12 = ops.env_update(e1 + 2 * e2, fx, core, S)
+    assert float((o12 - (o1 + 2 * o2)).abs().max()) < 1e-12 * float(o12.abs().max())
+    idx = torch.arange(0, S, 5003, device=DEV)
+    phi = orc.fbasis(X[idx].cpu().numpy())[17]
+    want = np.einsum("sa,sp,apb->sb", e1[idx].cpu().numpy(), phi, core.cpu().numpy())
+    assert gu.relerr(o1[idx].cpu().numpy(), want) < 1e-13

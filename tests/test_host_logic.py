@@ -1,0 +1,141 @@
+"""CPU-side checks: constructors reproduce the reference's initial state, the sweep schedule
+reproduces its control flow, the C-ABI library loads and exports what include/tn_b200.h declares,
+and the product path refuses to run without CUDA (no CPU fallback)."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+
+torch.set_default_dtype(torch.float64)
+
+import tensornetworksfork_b200 as tnb  # noqa: E402
+from tensornetworksfork_b200 import _lib  # noqa: E402
+from tensornetworksfork_b200.tensor.layers import chain_bond_dims  # noqa: E402
+from tensornetworksfork_b200.tensor.network import sweep_schedule, batch_mean_of_means  # noqa: E402
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+CONSTRUCT = {
+    "tt_poly_reg": lambda: tnb.TensorTrainLayer(3, 4, 5, output_shape=1, constrict_bond=True, perturb=True, seed=42),
+    "tt_poly5_full": lambda: tnb.TensorTrainLayer(5, 3, 4, output_shape=1, constrict_bond=False, perturb=False, seed=7),
+    "tnml_poly_xe": lambda: tnb.TensorTrainLayer(5, 3, 3, output_shape=3, constrict_bond=True, perturb=False, seed=5),
+    "tt_multi_square": lambda: tnb.TensorTrainLayer(3, 3, 4, output_shape=2, constrict_bond=False, perturb=False, seed=11),
+    "cpd_reg": lambda: tnb.CPDLayer(4, 6, 4, output_shape=(1,), seed=42),
+    "tt_exact_lr": lambda: tnb.TensorTrainLayer(2, 2, 3, output_shape=1, constrict_bond=False, perturb=False, seed=3),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CONSTRUCT))
+def test_constructors_reproduce_reference_init(name):
+    """Same seed -> same shapes, labels order and values as the reference's layers (cores0 of the fixtures)."""
+    fx = gu.load(name)
+    layer = CONSTRUCT[name]()
+    nodes = layer.tensor_network.train_nodes
+    assert len(nodes) == len(fx["cores0"])
+    for n, ref in zip(nodes, fx["cores0"]):
+        assert tuple(n.shape) == ref.shape
+        assert np.array_equal(n.tensor.numpy(), ref)
+
+
+def test_bond_dims_table():
+    assert chain_bond_dims(6, 8, 2) == [1, 2, 4, 8, 4, 2, 1]
+    assert chain_bond_dims(7, 8, 2) == [1, 2, 4, 8, 8, 4, 2, 1]
+    assert chain_bond_dims(5, 38, 29, constrict_bond=False) == [1, 38, 38, 38, 38, 1]
+    assert chain_bond_dims(3, 6, 9, True, True) == [1, 6, 6, 1]
+    assert chain_bond_dims(1, 8, 2) == [1, 1]
+    d = chain_bond_dims(90, 24, 2)
+    assert d[:7] == [1, 2, 4, 8, 16, 24, 24] and d[-6:] == [24, 16, 8, 4, 2, 1]
+
+
+@pytest.mark.parametrize("name", [n for n in gu.names()])
+def test_sweep_schedule_matches_reference_trace(name):
+    fx = gu.load(name)
+    meta = fx["meta"]
+    n = len(fx["cores0"])
+    cols = list(range(n)) if meta["kind"] == "tt" else list(range(n))
+    direction = meta.get("direction", "l2r")
+    first = cols if direction == "l2r" else cols[::-1]
+    second = cols[::-1] if direction == "l2r" else cols
+    sched = sweep_schedule(first, second, meta["num_swipes"], meta["eps"], meta.get("eps_decay"),
+                           meta.get("skip_second", False), direction)
+    got = [(NS, (first, second)[half][i], e) for NS, half, i, e in sched]
+    want = [(u["NS"], u["k"], u["eps"]) for u in fx["updates"]]
+    assert [(a, b) for a, b, _ in got] == [(a, b) for a, b, _ in want]
+    for (_, _, e1), (_, _, e2) in zip(got, want):
+        assert abs(e1 - e2) <= 1e-15 * max(1.0, abs(e2))
+
+
+def test_schedule_single_node_updates_once():
+    """With one train node the turn-around skip leaves a single update per call."""
+    assert len(sweep_schedule([0], [0], 5, 1.0)) == 1
+
+
+def test_schedule_eps_list_and_skip_second():
+    s = sweep_schedule([0, 1, 2], [2, 1, 0], 2, [4.0, 3.0, 2.0, 1.0])
+    assert [(ns, h, i) for ns, h, i, _ in s] == [(0, 0, 0), (0, 0, 1), (0, 0, 2), (1, 1, 1), (1, 1, 2), (2, 0, 1), (2, 0, 2),
+                                                 (3, 1, 1), (3, 1, 2)]
+    assert [e for *_, e in s] == [4.0, 4.0, 4.0, 3.0, 3.0, 2.0, 2.0, 1.0, 1.0]
+    s2 = sweep_schedule([0, 1], [1, 0], 2, [4.0, 3.0], skip_second=True)
+    assert [(ns, i) for ns, _, i, _ in s2] == [(0, 0), (0, 1), (1, 0), (1, 1)]
+
+
+def test_batch_mean_of_means_overweights_short_batch():
+    loss = torch.arange(10.0)
+    got = batch_mean_of_means(loss, 4)
+    want = (loss[:4].mean() + loss[4:8].mean() + loss[8:].mean()) / 3
+    assert abs(float(got) - float(want)) < 1e-15
+    assert abs(float(batch_mean_of_means(loss, -1)) - 4.5) < 1e-15
+
+
+def test_library_exports_every_declared_symbol():
+    """Every function include/tn_b200.h declares is exported and bound (no compute without a GPU)."""
+    hdr = open(os.path.join(ROOT, "include", "tn_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(tn_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations parsed"
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_lib.PROTOTYPES), (declared ^ set(_lib.PROTOTYPES))
+    assert lib.tn_version() >= 100
+
+
+def test_no_cpu_fallback():
+    """On a CPU tensor the product path raises instead of computing."""
+    layer = tnb.TensorTrainLayer(3, 2, 3, output_shape=1, seed=0)
+    x = torch.rand(8, 3)
+    with pytest.raises(RuntimeError):
+        layer.tensor_network.forward(x, to_tensor=True)
+    with pytest.raises(RuntimeError):
+        layer.tensor_network.accumulating_swipe(x, torch.rand(8, 1), tnb.SquareBregFunction(), eps=1.0, method="ridge_cholesky")
+
+
+def test_product_does_not_import_oracle():
+    import subprocess
+    import sys
+    code = "import sys; sys.path.insert(0, %r); import tensornetworksfork_b200, tensornetworksfork_b200.models; " \
+           "assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules)" % ROOT
+    subprocess.check_call([sys.executable, "-c", code])
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "tensornetworksfork_b200")):
+        for fn in files:
+            if fn.endswith(".py"):
+                src = open(os.path.join(dirpath, fn)).read()
+                assert "import oracle" not in src and "from oracle" not in src, fn
+
+
+def test_loss_closed_forms_match_rank1_terms():
+    from tensornetworksfork_b200.tensor.bregman import hessian_terms
+    torch.manual_seed(0)
+    x = torch.randn(7, 3)
+    y = torch.eye(4)[torch.randint(0, 4, (7,))]
+    for lf, yy in ((tnb.XEAutogradBregman(w=0.7), y), (tnb.AutogradLoss(), torch.randn(7, 3)), (tnb.SquareBregFunction(), torch.randn(7, 3))):
+        loss, g, H = lf.forward(x, yy)
+        l2, g2, U, lam = hessian_terms(lf, x, yy)
+        Hr = torch.einsum("st,stc,std->scd", lam, U, U)
+        Hf = H.expand(7, 3, 3) if H.shape[-1] == 1 else H
+        assert torch.allclose(Hr, Hf, atol=1e-14)
+        assert torch.allclose(g, g2) and torch.allclose(loss, l2)
