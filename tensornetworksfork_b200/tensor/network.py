@@ -678,7 +678,7 @@ class TensorNetwork:
         prob = self._site_problem(k, y, loss_fn)
         M, b, role_of_pos = self._accumulate(prob)
         step = self._solve(k, M, b, prob["m_pos"], role_of_pos, method, eps)
-        node = self._plan()[k].node
+        node = self.main_nodes[k]
         new = node.tensor.detach().clone().contiguous()
         ops.update_node(new.view(-1), step.view(-1), lr=lr, adaptive_step=adaptive_step, max_norm=max_norm)
         node.tensor = new
