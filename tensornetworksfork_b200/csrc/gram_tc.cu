@@ -1,9 +1,551 @@
-// tcgen05 (TF32 / 3xTF32) Gram kernel -- placeholder until the tensor-core path lands.
+// Gram build on the 5th-generation tensor cores: tcgen05.mma kind::tf32, accumulators in TMEM.
+//
+// Same contraction as the fp64 kernel in gram.cu -- M[(qa,qb),qc] = sum_rows U[row,(qa,qb)] V[row,qc]
+// with U = w*pair(fa)*pair(fb), V = pair(fc) -- but the operand tiles are synthesised by producer warps
+// straight into the UMMA canonical shared-memory layout (K-major, no swizzle: 8-row x 16-byte core
+// matrices, SBO = 128 B between 8-row groups, LBO = rows*16 B between the two 4-sample halves of an
+// MMA-K step) and multiplied by tcgen05.mma into fp32 TMEM accumulators.
+//
+//   mode 1 (TF32)   : one MMA per K step on the tf32-rounded operands.
+//   mode 2 (3xTF32) : operands split x = hi + lo (hi = tf32(x), lo = x - hi); three MMAs per K step
+//                     (hi*hi, hi*lo, lo*hi) recover ~fp32 products.
+// Every FLUSH_ROWS rows the accumulator is drained TMEM -> registers -> fp64 and added to M in
+// global memory, which bounds the fp32 accumulation length.
+//
+// Warp roles in a CTA of 288 threads: warp 0 allocates TMEM and issues the MMAs (one elected lane);
+// warps 1..8 stage the raw factors (global fp64 -> shared fp32, transposed, prefetched one chunk
+// ahead in registers), synthesise the tiles, and drain the accumulator at flush points.
+// Shared-memory stages are handed over with mbarriers: full[s] (producers -> MMA, after
+// fence.proxy.async) and empty[s] (tcgen05.commit -> producers).
+#include <stdlib.h>
+#include <type_traits>
 #include "common.cuh"
+
+namespace tn {
+
+constexpr int TC_M = 128;          // rows of one U tile = MMA M
+constexpr int TC_KC = 16;          // samples per pipeline stage (two MMA K steps of 8)
+constexpr int TC_KCP = TC_KC + 4;  // padded row of the transposed raw-factor staging (floats)
+constexpr int TC_PROD_WARPS = 8;
+constexpr int TC_PROD = TC_PROD_WARPS * 32;
+constexpr int TC_THREADS = 32 + TC_PROD;
+constexpr int TC_MAXLD = 8;        // raw values a producer thread prefetches per chunk
+constexpr int TC_FLUSH_ROWS_DEFAULT = 1024;
+
+struct TcFactor {
+    const double* ptr;
+    int64_t ld;
+    int m;
+    int div;
+    int map_kind;
+};
+
+struct TcParams {
+    TcFactor fa, fb, fc;
+    const double* w;
+    int64_t rows;
+    int64_t rows_per_split;
+    double* M;
+    int nA, nB, nC;   // pair counts
+    int BN;           // V tile width (multiple of 16, <= 256)
+    int T;            // U tiles per CTA (1 or 2)
+    int nstages;
+    int split;        // 1 = 3xTF32, 0 = TF32
+    int flush_rows;   // rows accumulated in fp32 before a drain to fp64 (multiple of TC_KC)
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __noinline__ void mbar_timeout() {
+    printf("tn_gram_tc: mbarrier wait timed out (block %d,%d,%d thread %d)\n", blockIdx.x, blockIdx.y, blockIdx.z, threadIdx.x);
+    __trap();
+}
+// Bounded wait: a protocol bug traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t it = 0; it < (1u << 26); ++it)
+        if (mbar_try_wait(bar, parity)) return;
+    mbar_timeout();
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor: K-major, SWIZZLE_NONE, version 1 (sm_100).
+// (cute/arch/mma_sm100_desc.hpp: start[0,14) LBO[16,30) SBO[32,46) version[46,48) layout[61,64))
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+// Instruction descriptor for kind::tf32, fp32 accumulate, both operands K-major.
+__device__ __forceinline__ uint32_t make_idesc(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// Round-to-nearest (ties away) to tf32 with two integer ops; inputs are finite products of finite factors.
+__device__ __forceinline__ float tf32_rn(float x) { return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xffffe000u); }
+
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, float4 v) {
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 mul4(float4 a, float4 b) { return make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w); }
+
+// hi/lo split of four samples of one operand row; lo = x - hi is exact in fp32 and the MMA truncates it to tf32.
+template <int SPLIT>
+__device__ __forceinline__ void store_split(float4 v, uint32_t hi_addr, uint32_t lo_addr) {
+    const float4 h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
+    sts128(hi_addr, h);
+    if (SPLIT) sts128(lo_addr, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
+}
+
+// TMEM accumulator -> registers -> fp64 atomic adds into M.  Warp w may touch TMEM lanes 32*(w%4)..+31;
+// the two producer warps that share a lane quarter split the columns.
+__device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_total, int BN, int warp, int lane, int64_t u0,
+                                               int64_t nU, int v0, int nC, double* __restrict__ M) {
+    const int q = warp & 3;
+    const int half = (warp - 1) >> 2;
+    const int cols_half = ((cols_total / 16 + 1) / 2) * 16;
+    const int col_lo = half * cols_half;
+    const int col_hi = min(cols_total, col_lo + cols_half);
+    const int row_in_tile = q * 32 + lane;
+    for (int col = col_lo; col < col_hi; col += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
+        const int t = col / BN;
+        const int cbase = col - t * BN;
+        const int64_t gu = u0 + (int64_t)t * TC_M + row_in_tile;
+        if (gu < nU) {
+            double* dst = M + gu * nC + v0 + cbase;
+#pragma unroll
+            for (int e = 0; e < 16; ++e)
+                if (v0 + cbase + e < nC) atomicAdd(dst + e, (double)__uint_as_float(r[e]));
+        }
+    }
+}
+
+template <int SPLIT, int T, int SLOW>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gram_tc_kernel(TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ float wbuf_s[2][TC_KC];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int BN = p.BN, NS = p.nstages;
+    const int mA = p.fa.m, mB = p.fb.m, mC = p.fc.m;
+    const int msum = mA + mB + mC;
+
+    // ---- shared memory carve-up: [NS stages][2 raw-factor buffers][mbarriers][tmem slot]
+    constexpr uint32_t a_tile_bytes = TC_M * TC_KC * 4;      // one U tile, hi or lo, one stage
+    const uint32_t b_tile_bytes = (uint32_t)BN * TC_KC * 4;  // V tile, hi or lo
+    const uint32_t stage_bytes = 2 * T * a_tile_bytes + 2 * b_tile_bytes;
+    const uint32_t raw_rows = (uint32_t)(2 * mA + mB + mC) + 2;   // + an all-zero row (padding rows of the tiles) + a scratch row
+    const uint32_t raw_floats = raw_rows * TC_KCP;
+    uint8_t* stage_base = smem_raw;
+    float* raw0 = reinterpret_cast<float*>(smem_raw + (size_t)NS * stage_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(raw0) + 2 * (size_t)raw_floats * 4);
+    uint64_t* full = bars;              // [NS]
+    uint64_t* empty = bars + NS;        // [NS]
+    uint64_t* acc_full = bars + 2 * NS;
+    uint64_t* acc_empty = bars + 2 * NS + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
+
+    const uint32_t tmem_cols_needed = (uint32_t)(T * BN);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], TC_PROD_WARPS);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, TC_PROD_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < 2 * TC_KCP; i += TC_THREADS)   // the zero row of both raw buffers
+        raw0[(size_t)(i / TC_KCP) * raw_floats + (raw_rows - 2) * TC_KCP + (i % TC_KCP)] = 0.f;
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t k_begin = (int64_t)blockIdx.z * p.rows_per_split;
+    const int64_t k_end = min(p.rows, k_begin + p.rows_per_split);
+    const int64_t nchunks = (k_end > k_begin) ? (k_end - k_begin + TC_KC - 1) / TC_KC : 0;
+    const int64_t chunks_per_flush = p.flush_rows / TC_KC;
+    const int64_t nU = (int64_t)p.nA * p.nB;
+    const int64_t u0 = (int64_t)blockIdx.x * (TC_M * T);
+    const int v0 = blockIdx.y * BN;
+
+    if (warp == 0) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0 && nchunks > 0) {
+            const uint32_t idesc = make_idesc(TC_M, BN);
+            const uint32_t lbo_a = TC_M * 16, lbo_b = (uint32_t)BN * 16, sbo = 128;
+            uint32_t acc_phase = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            int64_t in_window = 0;
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const bool first_of_window = in_window == 0;
+                if (first_of_window && c > 0) {
+                    mbar_wait(acc_empty, acc_phase);   // accumulator drained by the producers
+                    acc_phase ^= 1;
+                    tc_fence_after();
+                }
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(stage_base + (size_t)s * stage_bytes);
+                const uint32_t b_hi = sb + 2 * T * a_tile_bytes;
+                const uint32_t b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    const uint32_t a_hi = sb + (uint32_t)t * 2 * a_tile_bytes;
+                    const uint32_t a_lo = a_hi + a_tile_bytes;
+                    const uint32_t d = tmem_base + (uint32_t)(t * BN);
+#pragma unroll
+                    for (int j = 0; j < TC_KC / 8; ++j) {
+                        const uint32_t ao = (uint32_t)(2 * j) * lbo_a, bo = (uint32_t)(2 * j) * lbo_b;
+                        const uint32_t acc0 = (first_of_window && j == 0) ? 0u : 1u;
+                        umma_tf32(d, make_desc(a_hi + ao, lbo_a, sbo), make_desc(b_hi + bo, lbo_b, sbo), idesc, acc0);
+                        if (SPLIT) {
+                            umma_tf32(d, make_desc(a_hi + ao, lbo_a, sbo), make_desc(b_lo + bo, lbo_b, sbo), idesc, 1u);
+                            umma_tf32(d, make_desc(a_lo + ao, lbo_a, sbo), make_desc(b_hi + bo, lbo_b, sbo), idesc, 1u);
+                        }
+                    }
+                }
+                umma_commit(&empty[s]);                          // smem stage free once these MMAs have read it
+                const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+                if (last_of_window) {
+                    umma_commit(acc_full);                       // accumulator complete for this window
+                    in_window = 0;
+                }
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // =============================== producers / epilogue ===============================
+        const int pt = tid - 32;  // 0..255
+        const uint32_t raw_s = smem_u32(raw0);
+        const uint32_t zero_row = (raw_rows - 2) * TC_KCP * 4;        // byte offset of the zero row in a raw buffer
+        // -- rows of the operand tiles this thread synthesises (fixed for the kernel)
+        uint32_t usrc[4] = {zero_row, zero_row, zero_row, zero_row};   // byte offsets of Aw[ia], A[ja], B[ib], B[jb]
+        int u_tile = 0, u_row = pt & 127, u_c0 = 0;
+        constexpr int U_NC = (T == 2) ? TC_KC / 4 : TC_KC / 8;          // k-chunks of 4 samples per thread and stage
+        if (T == 2) u_tile = pt >> 7;
+        else u_c0 = (pt >> 7) * U_NC;
+        {
+            const int64_t gu = u0 + (int64_t)u_tile * TC_M + u_row;
+            if (gu < nU) {
+                const int qa = (int)(gu / p.nB), qb = (int)(gu - (int64_t)qa * p.nB);
+                int ia, ja, ib, jb;
+                pair_decode(qa, mA, ia, ja);
+                pair_decode(qb, mB, ib, jb);
+                usrc[0] = (uint32_t)(ia * TC_KCP * 4);
+                usrc[1] = (uint32_t)((mA + ja) * TC_KCP * 4);
+                usrc[2] = (uint32_t)((2 * mA + ib) * TC_KCP * 4);
+                usrc[3] = (uint32_t)((2 * mA + jb) * TC_KCP * 4);
+            }
+        }
+        uint32_t vsrc[2] = {zero_row, zero_row};
+        if (pt < BN && v0 + pt < p.nC) {
+            int ic, jc;
+            pair_decode(v0 + pt, mC, ic, jc);
+            vsrc[0] = (uint32_t)((2 * mA + mB + ic) * TC_KCP * 4);
+            vsrc[1] = (uint32_t)((2 * mA + mB + jc) * TC_KCP * 4);
+        }
+        const uint32_t udst = (uint32_t)u_tile * 2 * a_tile_bytes + (uint32_t)u_row * 16 + (uint32_t)u_c0 * (TC_M * 16);
+        const uint32_t vdst = 2 * T * a_tile_bytes + (uint32_t)pt * 16;
+        const uint32_t lbo_b = (uint32_t)BN * 16;
+        const uint32_t stage_s = smem_u32(stage_base);
+
+        // -- load plan: the raw values this thread fetches every chunk (fixed for the kernel).  Unused slots
+        //    read a harmless address and write into the scratch row, so the per-chunk code has no branches.
+        const int nvals = TC_KC * msum;
+        const int scratch_f = (int)(raw_rows - 1) * TC_KCP;   // float index of the scratch row (after the zero row)
+        const double* ld_ptr[TC_MAXLD];   // address of the value in the next chunk to prefetch
+        int ld_step[TC_MAXLD];            // elements to advance per chunk
+        int ld_meta[TC_MAXLD];            // dst | dst_weighted << 13 | k << 26        (float indices in a raw buffer)
+        int ld_gen[TC_MAXLD];             // SLOW kernels: fac | i_local << 2
+#pragma unroll
+        for (int q = 0; q < TC_MAXLD; ++q) {
+            const int idx = pt + q * TC_PROD;
+            ld_ptr[q] = p.fa.ptr;
+            ld_step[q] = 0;
+            ld_meta[q] = scratch_f | (scratch_f << 13);
+            ld_gen[q] = -1;
+            if (idx < nvals) {
+                const int k = idx / msum, i = idx - k * msum;
+                const int fac = (i < mA) ? 0 : ((i < mA + mB) ? 1 : 2);
+                const int il = (fac == 0) ? i : ((fac == 1) ? i - mA : i - mA - mB);
+                const TcFactor& f = (fac == 0) ? p.fa : ((fac == 1) ? p.fb : p.fc);
+                const int dst = (mA + i) * TC_KCP + k;
+                const int dstw = (fac == 0) ? dst - mA * TC_KCP : scratch_f;
+                ld_meta[q] = dst | (dstw << 13) | (k << 26);
+                const bool shared_row = f.div >= (1 << 29);          // the all-ones factor: one row for every sample
+                ld_ptr[q] = f.ptr + (shared_row ? 0 : (k_begin + k) * f.ld) + il;
+                ld_step[q] = shared_row ? 0 : (int)(TC_KC * f.ld);
+                ld_gen[q] = fac | (il << 2);
+            }
+        }
+
+        // Issue the global loads of the next chunk (chunks are prefetched in increasing order).
+        auto prefetch = [&](int64_t chunk, double (&pre)[TC_MAXLD], double& pre_w) {
+            const int64_t kb = k_begin + chunk * TC_KC;
+#pragma unroll
+            for (int q = 0; q < TC_MAXLD; ++q) {
+                if (!SLOW) {
+                    pre[q] = *ld_ptr[q];
+                    ld_ptr[q] += ld_step[q];
+                } else {
+                    double v = 0.0;
+                    const int gen = ld_gen[q];
+                    if (gen >= 0) {
+                        const int fac = gen & 3;
+                        const TcFactor& f = (fac == 0) ? p.fa : ((fac == 1) ? p.fb : p.fc);
+                        const int64_t row = kb + (ld_meta[q] >> 26);
+                        if (row < k_end) {                               // ragged last chunk: rows past the end are zero
+                            const int64_t ri = (f.div == 1) ? row : row / f.div;
+                            v = map_eval(f.map_kind, f.ptr + ri * f.ld, gen >> 2);
+                        }
+                    }
+                    pre[q] = v;
+                }
+            }
+            if (pt < TC_KC) pre_w = (kb + pt < k_end) ? (p.w ? p.w[kb + pt] : 1.0) : 0.0;
+        };
+        // registers -> transposed fp32 staging [factor row][sample]; A rows are stored twice (weighted copy first)
+        auto stash = [&](float* raw, float* wbuf, const double (&pre)[TC_MAXLD], double pre_w) {
+            if (pt < TC_KC) wbuf[pt] = (float)pre_w;
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");
+#pragma unroll
+            for (int q = 0; q < TC_MAXLD; ++q) {
+                const int meta = ld_meta[q];
+                const float v = (float)pre[q];
+                raw[meta & 0x1fff] = v;
+                raw[(meta >> 13) & 0x1fff] = v * wbuf[meta >> 26];
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");
+        };
+        double preE[TC_MAXLD], preO[TC_MAXLD];   // prefetched raw values of even / odd chunks
+        double wE = 0.0, wO = 0.0;
+        if (nchunks > 0) {
+            prefetch(0, preE, wE);
+            stash(raw0, wbuf_s[0], preE, wE);
+            if (nchunks > 1) prefetch(1, preO, wO);
+        }
+        uint32_t acc_phase = 0;
+        int s = 0;
+        uint32_t ph = 0;
+        int64_t in_window = 0;
+
+        // One pipeline stage: synthesise chunk c from raw buffer PAR, hand it to the MMA warp, then move the
+        // already-loaded chunk c+1 into the other raw buffer and start the loads of chunk c+2.
+        auto body = [&](int64_t c, auto par_tag) {
+            constexpr int PAR = decltype(par_tag)::value;
+            const uint32_t rb = raw_s + (uint32_t)PAR * raw_floats * 4;
+            if (c + 2 < nchunks) {
+                if (PAR) prefetch(c + 2, preO, wO);
+                else prefetch(c + 2, preE, wE);
+            }
+            if (lane == 0) mbar_wait(&empty[s], ph ^ 1);       // first pass over the ring returns immediately
+            __syncwarp();
+            const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
+            {   // ---- U rows: all loads, then the products, then the stores (no load waits behind a store)
+                float4 x0[U_NC], x1[U_NC], x2[U_NC], x3[U_NC];
+#pragma unroll
+                for (int cc = 0; cc < U_NC; ++cc) {
+                    const uint32_t o = (uint32_t)(u_c0 + cc) * 16;
+                    x0[cc] = lds128(rb + usrc[0] + o);
+                    x1[cc] = lds128(rb + usrc[1] + o);
+                    x2[cc] = lds128(rb + usrc[2] + o);
+                    x3[cc] = lds128(rb + usrc[3] + o);
+                }
+#pragma unroll
+                for (int cc = 0; cc < U_NC; ++cc) {
+                    const float4 v = mul4(mul4(x0[cc], x1[cc]), mul4(x2[cc], x3[cc]));
+                    const uint32_t d = sb + udst + (uint32_t)cc * (TC_M * 16);
+                    store_split<SPLIT>(v, d, d + a_tile_bytes);
+                }
+            }
+            if (pt < BN) {   // ---- V rows
+                float4 y0[TC_KC / 4], y1[TC_KC / 4];
+#pragma unroll
+                for (int cc = 0; cc < TC_KC / 4; ++cc) {
+                    y0[cc] = lds128(rb + vsrc[0] + cc * 16);
+                    y1[cc] = lds128(rb + vsrc[1] + cc * 16);
+                }
+#pragma unroll
+                for (int cc = 0; cc < TC_KC / 4; ++cc) {
+                    const uint32_t d = sb + vdst + (uint32_t)cc * lbo_b;
+                    store_split<SPLIT>(mul4(y0[cc], y1[cc]), d, d + b_tile_bytes);
+                }
+            }
+            fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+            if (c + 1 < nchunks) {        // chunk c+1 (opposite parity) goes into the other raw buffer
+                float* nraw = raw0 + (size_t)(1 - PAR) * raw_floats;
+                if (PAR) stash(nraw, wbuf_s[0], preE, wE);
+                else stash(nraw, wbuf_s[1], preO, wO);
+            }
+            if (++s == NS) { s = 0; ph ^= 1; }
+            // ---- flush: drain the accumulator into fp64 M
+            const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+            if (last_of_window) {
+                in_window = 0;
+                mbar_wait(acc_full, acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);
+            }
+        };
+        for (int64_t c = 0; c < nchunks; c += 2) {
+            body(c, std::integral_constant<int, 0>{});
+            if (c + 1 < nchunks) body(c + 1, std::integral_constant<int, 1>{});
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+static size_t tc_smem_bytes(int mA, int mB, int mC, int BN, int T, int NS) {
+    const size_t stage = 2 * (size_t)T * TC_M * TC_KC * 4 + 2 * (size_t)BN * TC_KC * 4;
+    const size_t raw = (size_t)(2 * mA + mB + mC + 2) * TC_KCP * 4;
+    return NS * stage + 2 * raw + (2 * NS + 2) * 8 + 16;
+}
+
+}  // namespace tn
 
 int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_factor* fc, const double* w, int64_t rows,
                    double* M, int accumulate, void* stream) {
-    (void)mode; (void)fa; (void)fb; (void)fc; (void)w; (void)rows; (void)M; (void)accumulate; (void)stream;
-    tn::set_error("tn_gram_kr3: tensor-core modes are not built yet");
-    return TN_EUNSUPPORTED;
+    using namespace tn;
+    cudaStream_t st = as_stream(stream);
+    TcParams p;
+    p.fa = TcFactor{fa->ptr, fa->ld, fa->m, fa->div < 1 ? 1 : fa->div, fa->map_kind};
+    p.fb = TcFactor{fb->ptr, fb->ld, fb->m, fb->div < 1 ? 1 : fb->div, fb->map_kind};
+    p.fc = TcFactor{fc->ptr, fc->ld, fc->m, fc->div < 1 ? 1 : fc->div, fc->map_kind};
+    p.w = w;
+    p.rows = rows;
+    p.M = M;
+    p.nA = npairs(fa->m);
+    p.nB = npairs(fb->m);
+    p.nC = npairs(fc->m);
+    p.split = (mode == 2) ? 1 : 0;
+    p.flush_rows = TC_FLUSH_ROWS_DEFAULT;
+    if (const char* e = getenv("TN_TC_FLUSH_ROWS")) {
+        const int v = atoi(e);
+        if (v >= TC_KC) p.flush_rows = (v / TC_KC) * TC_KC;
+    }
+    const int64_t nU = (int64_t)p.nA * p.nB;
+    const int64_t n = nU * p.nC;
+    TN_CHECK_ARG(TC_KC * (fa->m + fb->m + fc->m) <= TC_MAXLD * TC_PROD,
+                 "tn_gram_kr3 (tensor-core modes): factor sizes %d+%d+%d exceed the staging capacity of %d per row", fa->m, fb->m,
+                 fc->m, TC_MAXLD * TC_PROD / TC_KC);
+    p.BN = (p.nC >= 256) ? 256 : ((p.nC + 15) / 16) * 16;
+    p.T = (nU > TC_M && p.BN * 2 <= 512) ? 2 : 1;
+    int NS = 4;
+    while (NS >= 2 && tc_smem_bytes(fa->m, fb->m, fc->m, p.BN, p.T, NS) > 227 * 1024) --NS;
+    if (NS < 2 && p.T == 2) {
+        p.T = 1;
+        NS = 4;
+        while (NS >= 2 && tc_smem_bytes(fa->m, fb->m, fc->m, p.BN, p.T, NS) > 227 * 1024) --NS;
+    }
+    TN_CHECK_ARG(NS >= 2, "tn_gram_kr3 (tensor-core modes): factors too large for the shared-memory pipeline");
+    p.nstages = NS;
+    const size_t smem = tc_smem_bytes(fa->m, fb->m, fc->m, p.BN, p.T, NS);
+    if (!accumulate) TN_CUDA(cudaMemsetAsync(M, 0, (size_t)n * sizeof(double), st));
+    if (rows == 0) return TN_OK;
+    const int64_t gx = ceil_div64(nU, (int64_t)TC_M * p.T), gy = ceil_div64(p.nC, p.BN);
+    TN_CHECK_ARG(gy <= 65535 && gx <= 0x7fffffff, "tn_gram_kr3: grid too large");
+    using Kern = void (*)(TcParams);
+    static const Kern kerns[2][2][2] = {{{gram_tc_kernel<0, 1, 0>, gram_tc_kernel<0, 1, 1>}, {gram_tc_kernel<0, 2, 0>, gram_tc_kernel<0, 2, 1>}},
+                                        {{gram_tc_kernel<1, 1, 0>, gram_tc_kernel<1, 1, 1>}, {gram_tc_kernel<1, 2, 0>, gram_tc_kernel<1, 2, 1>}}};
+    static size_t configured[2][2][2] = {};
+    auto launch = [&](TcParams q, int slow) -> int {
+        if (q.rows <= 0) return TN_OK;
+        // split the rows when there are too few tiles to fill the machine (flushes are atomic adds, so splits compose)
+        int64_t ks = ceil_div64((int64_t)sm_count(), gx * gy);
+        const int64_t max_ks = ceil_div64(q.rows, 4 * TC_KC);
+        if (ks > max_ks) ks = max_ks;
+        if (ks < 1) ks = 1;
+        if (ks > 65535) ks = 65535;
+        q.rows_per_split = ceil_div64(ceil_div64(q.rows, ks), TC_KC) * TC_KC;
+        ks = ceil_div64(q.rows, q.rows_per_split);
+        Kern k = kerns[q.split][q.T - 1][slow];
+        if (smem > configured[q.split][q.T - 1][slow]) {
+            TN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured[q.split][q.T - 1][slow] = smem;
+        }
+        dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)ks);
+        k<<<grid, TC_THREADS, smem, st>>>(q);
+        TN_LAUNCH_CHECK();
+        return TN_OK;
+    };
+    auto simple = [](const TcFactor& f) { return (f.div == 1 || f.div >= (1 << 29)) && f.map_kind == TN_MAP_IDENTITY; };
+    if (!(simple(p.fa) && simple(p.fb) && simple(p.fc))) return launch(p, 1);   // class rows / fused feature maps
+    // fast kernel on the whole 16-row chunks, generic kernel on the ragged remainder
+    const int64_t main_rows = rows - rows % TC_KC;
+    TcParams q = p;
+    q.rows = main_rows;
+    int rc = launch(q, 0);
+    if (rc != TN_OK || main_rows == rows) return rc;
+    q = p;
+    q.rows = rows - main_rows;
+    auto shift = [&](TcFactor& f) { if (f.div == 1) f.ptr += main_rows * f.ld; };
+    shift(q.fa); shift(q.fb); shift(q.fc);
+    if (q.w) q.w += main_rows;
+    return launch(q, 1);
 }

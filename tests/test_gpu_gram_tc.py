@@ -1,0 +1,102 @@
+"""tcgen05 Gram kernel (TF32 / 3xTF32, TMEM accumulators) against the fp64 kernel and numpy (needs a B200).
+
+Stated tolerances (relative Frobenius error of the unique-entry tensor M against fp64):
+  3xTF32 : <= 3e-5   products are fp32-grade (~3e-7), but tcgen05 accumulates in fp32 with TRUNCATION (measured:
+                     error grows linearly with the rows accumulated between two fp64 flushes, ~7e-9 per row; 1024
+                     rows per flush by default -> ~1e-5).  The end-to-end bound that matters -- per-update loss of a
+                     free-running sweep within 1e-6 of the fp64 mode -- is asserted at the bottom of this file.
+  TF32   : <= 2e-3
+"""
+import numpy as np
+import pytest
+import torch
+
+import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+torch.set_default_dtype(torch.float64)
+
+from tensornetworksfork_b200 import ops  # noqa: E402
+from tensornetworksfork_b200.ops import Factor  # noqa: E402
+
+DEV = "cuda"
+TOL = {ops.GRAM_TF32X3: 3e-5, ops.GRAM_TF32: 2e-3}
+
+SHAPES = [
+    # rows, ma, mb, mc, V
+    (64, 2, 2, 2, 1),          # one tile, one chunk window
+    (1000, 4, 5, 4, 1),        # ragged rows
+    (5000, 6, 9, 6, 1),        # several U tiles, flush boundary (4096) crossed
+    (20000, 24, 2, 24, 1),     # config-3 middle site: BN=256, two V tiles, T=2
+    (3000, 38, 6, 38, 1),      # config-5b middle site: 3 V tiles
+    (2500, 1, 29, 38, 1),      # config-5a first site (trivial left factor)
+    (2500, 38, 29, 1, 1),      # config-5a last site
+    (9000, 100, 9, 1, 1),      # config-2 CPD factor: rank 100
+    (1200, 5, 3, 4, 3),        # class rows, signed weights
+]
+
+
+def make(rows, ma, mb, mc, V, seed):
+    g = torch.Generator(device=DEV).manual_seed(seed)
+    S = rows
+    Fa = torch.randn((S * V, ma), device=DEV, generator=g)
+    Fb = torch.rand((S, mb), device=DEV, generator=g) * 2 - 1
+    Fc = torch.randn((S, mc), device=DEV, generator=g)
+    w = torch.randn((S * V,), device=DEV, generator=g)
+    return Factor(Fa, m=ma), Factor(Fb, m=mb, div=V), Factor(Fc, m=mc, div=V), w, S * V
+
+
+@pytest.mark.parametrize("mode", [ops.GRAM_TF32X3, ops.GRAM_TF32])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_tc_gram_matches_fp64(shape, mode):
+    fa, fb, fc, w, rows = make(*shape, seed=sum(shape))
+    ref = ops.gram(ops.GRAM_FP64, fa, fb, fc, w, rows)
+    got = ops.gram(mode, fa, fb, fc, w, rows)
+    torch.cuda.synchronize()
+    err = gu.relerr(got.cpu().numpy(), ref.cpu().numpy())
+    assert err < TOL[mode], err
+
+
+def test_tc_gram_positive_weights_and_accumulate():
+    fa, fb, fc, w, rows = make(6000, 8, 4, 8, 1, seed=5)
+    w = w.abs()
+    ref = ops.gram(ops.GRAM_FP64, fa, fb, fc, w, rows)
+    got = ops.gram(ops.GRAM_TF32X3, fa, fb, fc, w, rows)
+    assert gu.relerr(got.cpu().numpy(), ref.cpu().numpy()) < 3e-5
+    twice = ops.gram(ops.GRAM_TF32X3, fa, fb, fc, w, rows, M=got.clone(), accumulate=True)
+    assert gu.relerr(twice.cpu().numpy(), 2 * ref.cpu().numpy()) < 3e-5
+
+
+def test_tc_gram_feature_map_factor():
+    g = torch.Generator(device=DEV).manual_seed(9)
+    S = 7000
+    X = torch.rand((S, 12), device=DEV, generator=g) * 2 - 1
+    L = torch.randn((S, 16), device=DEV, generator=g)
+    R = torch.randn((S, 16), device=DEV, generator=g)
+    w = torch.full((S,), 2.0, device=DEV)
+    fb = Factor(X, m=2, map_kind=ops.MAP_SINCOS, col=7)
+    ref = ops.gram(ops.GRAM_FP64, Factor(L, m=16), fb, Factor(R, m=16), w, S)
+    got = ops.gram(ops.GRAM_TF32X3, Factor(L, m=16), fb, Factor(R, m=16), w, S)
+    assert gu.relerr(got.cpu().numpy(), ref.cpu().numpy()) < 3e-5
+
+
+def test_sweep_in_3xtf32_tracks_fp64_sweep():
+    """Free-running sweep (well-conditioned, eps >= 0.25): per-update loss and predictions of the 3xTF32 Gram
+    mode against the fp64 mode, tolerance 1e-6 relative (BASELINE.json north_star)."""
+    import tensornetworksfork_b200 as tnb
+    g = torch.Generator(device=DEV).manual_seed(3)
+    N, F = 20000, 6
+    X = torch.cat([torch.rand((N, F), device=DEV, generator=g) * 2 - 1, torch.ones((N, 1), device=DEV)], 1)
+    y = torch.tanh(X[:, :1]) + 0.5 * X[:, 1:2] * X[:, 2:3] + 0.05 * torch.randn((N, 1), device=DEV, generator=g)
+    out = {}
+    for mode in ("fp64", "tf32x3"):
+        layer = tnb.TensorTrainLayer(4, 8, F + 1, output_shape=1, constrict_bond=False, seed=42).to(DEV)
+        layer.tensor_network.gram_mode = mode
+        losses = []
+        ok = layer.tensor_network.accumulating_swipe(X, y, tnb.SquareBregFunction(), num_swipes=2, method="ridge_cholesky", eps=1.0,
+                                                     eps_decay=0.5, loss_callback=lambda NS, n, l: losses.append(l))
+        assert ok
+        out[mode] = (losses, layer.tensor_network.forward(X, to_tensor=True))
+    for a, b in zip(out["tf32x3"][0], out["fp64"][0]):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (a, b)
+    assert gu.relerr(out["tf32x3"][1].cpu().numpy(), out["fp64"][1].cpu().numpy()) < 1e-5
