@@ -167,6 +167,103 @@ syrk_update_kernel(double* __restrict__ A, int64_t lda, int64_t P, int64_t c0, i
     }
 }
 
+// ---- large trailing update on the FP64 tensor pipe (DMMA m8n8k4), 128x128 tile, K streamed by cp.async.
+//      Same contract as syrk_update_kernel; requires kb % 16 == 0 and lda % 2 == 0, k0 % 2 == 0.
+constexpr int DS_BT = 128;   // tile
+constexpr int DS_KC = 16;    // k per stage
+constexpr int DS_LD = DS_KC + 2;   // padded smem row (doubles): 16-byte aligned rows, conflict-free fragment reads
+constexpr int DS_STAGES = 3;
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(256, 1)
+syrk_update_dmma_kernel(double* __restrict__ A, int64_t lda, int64_t P, int64_t c0, int64_t c1, int64_t k0, int kb,
+                        const int* __restrict__ info) {
+    extern __shared__ double dsm[];
+    if (*info != 0) return;
+    const int bi = blockIdx.y, bj = blockIdx.x;
+    if (bj > bi) return;
+    const int64_t r0 = c0 + (int64_t)bi * DS_BT, q0 = c0 + (int64_t)bj * DS_BT;
+    if (r0 >= P || q0 >= c1) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = warp >> 1, wn = warp & 1;          // 4 x 2 warps: warp tile 32 (rows) x 64 (cols)
+    double* sA = dsm;                                  // [stage][128][DS_LD]
+    double* sB = dsm + DS_STAGES * DS_BT * DS_LD;
+
+    double acc[4][8][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    // each thread copies 4 + 4 sixteen-byte pieces per stage: piece = (row, half-pair index 0..7)
+    auto issue = [&](int stage, int kk) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int piece = tid + u * 256;           // 0..1023
+            const int row = piece >> 3, part = piece & 7;
+            int64_t ra = r0 + row, rb = q0 + row;
+            if (ra >= P) ra = P - 1;                   // clamped rows are never stored
+            if (rb >= P) rb = P - 1;
+            cp_async16(sA + ((size_t)stage * DS_BT + row) * DS_LD + part * 2, A + ra * lda + k0 + kk + part * 2);
+            cp_async16(sB + ((size_t)stage * DS_BT + row) * DS_LD + part * 2, A + rb * lda + k0 + kk + part * 2);
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int nk = kb / DS_KC;
+    for (int s = 0; s < DS_STAGES - 1; ++s) {
+        if (s < nk) issue(s, s * DS_KC);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    const int fr = lane >> 2, fk = lane & 3;
+    for (int it = 0; it < nk; ++it) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(DS_STAGES - 2) : "memory");
+        __syncthreads();
+        const int nxt = it + DS_STAGES - 1;
+        if (nxt < nk) issue(nxt % DS_STAGES, nxt * DS_KC);
+        else asm volatile("cp.async.commit_group;" ::: "memory");
+        const double* a_s = sA + ((size_t)(it % DS_STAGES) * DS_BT + wm * 32 + fr) * DS_LD + fk;
+        const double* b_s = sB + ((size_t)(it % DS_STAGES) * DS_BT + wn * 64 + fr) * DS_LD + fk;
+#pragma unroll
+        for (int k4 = 0; k4 < DS_KC; k4 += 4) {
+            double af[4], bf[8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) af[i] = a_s[(size_t)i * 8 * DS_LD + k4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) bf[j] = b_s[(size_t)j * 8 * DS_LD + k4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int64_t row = r0 + wm * 32 + i * 8 + fr;
+        if (row >= P) continue;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int64_t col = q0 + wn * 64 + j * 8 + fk * 2;
+            double* cptr = A + row * lda + col;
+            if (col + 1 < c1 && col + 1 <= row) {
+                double2 v = *reinterpret_cast<double2*>(cptr);
+                v.x -= acc[i][j][0];
+                v.y -= acc[i][j][1];
+                *reinterpret_cast<double2*>(cptr) = v;
+            } else {
+                if (col < c1 && col <= row) cptr[0] -= acc[i][j][0];
+                if (col + 1 < c1 && col + 1 <= row) cptr[1] -= acc[i][j][1];
+            }
+        }
+    }
+}
+
 // ---- triangular solves -------------------------------------------------------------------------
 // y_j = Linv_j * rhs_j (forward) or Linv_j^T * rhs_j (backward), in place, one CTA of 64 threads.
 __global__ void trsv_diag_kernel(double* __restrict__ rhs, int64_t j, int nb, const double* __restrict__ Linv, int transpose,
@@ -232,8 +329,10 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
     TN_CHECK_ARG(A && work && info && P >= 1 && lda >= P, "tn_cholesky_solve: bad arguments");
     cudaStream_t st = as_stream(stream);
     constexpr size_t kBlkSmem = 2 * CH_NB * (CH_NB + 1) * sizeof(double);
+    constexpr size_t kDmmaSmem = (size_t)2 * DS_STAGES * DS_BT * DS_LD * sizeof(double);
     static bool configured = false;
     if (!configured) {
+        TN_CUDA(cudaFuncSetAttribute(syrk_update_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmem));
         TN_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkSmem));
         TN_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkSmem));
         configured = true;
@@ -258,9 +357,13 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
         }
         if (Jend < P) {
             const int64_t n = P - Jend;
-            if (n > 512) {
+            const int kbo = (int)(Jend - J);
+            if (n > 512 && kbo % DS_KC == 0 && lda % 2 == 0) {
+                dim3 grid((unsigned)ceil_div64(n, DS_BT), (unsigned)ceil_div64(n, DS_BT));
+                syrk_update_dmma_kernel<<<grid, 256, kDmmaSmem, st>>>(A, lda, P, Jend, P, J, kbo, info);
+            } else if (n > 512) {
                 dim3 grid((unsigned)ceil_div64(n, 128), (unsigned)ceil_div64(n, 128));
-                syrk_update_kernel<128><<<grid, 256, 0, st>>>(A, lda, P, Jend, P, J, (int)(Jend - J), info);
+                syrk_update_kernel<128><<<grid, 256, 0, st>>>(A, lda, P, Jend, P, J, kbo, info);
             } else {
                 dim3 grid((unsigned)ceil_div64(n, 64), (unsigned)ceil_div64(n, 64));
                 syrk_update_kernel<64><<<grid, 256, 0, st>>>(A, lda, P, Jend, P, J, (int)(Jend - J), info);

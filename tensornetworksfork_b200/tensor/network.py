@@ -428,6 +428,10 @@ class TensorNetwork:
         owner = self._owner()
         C = self._num_outputs()
         xk = facs[k]
+        if self.gram_mode != "fp64" and xk.map_kind != ops.MAP_IDENTITY:
+            # tensor-core Gram: evaluate the feature map once per site (S x f) so the kernel stays on its fast path
+            phi = ops.env_update(None, xk, torch.eye(f, dtype=torch.float64, device=dev).reshape(1, f, f), S)
+            xk = Factor(phi, m=f)
         one = ops.ones_factor(G)
 
         def fac_of(env, r, div):

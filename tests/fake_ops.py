@@ -1,0 +1,168 @@
+"""CPU stand-ins for tensornetworksfork_b200.ops, for exercising the HOST logic (sweep driver,
+caching, sharding, all-reduce bookkeeping) without a GPU.  TEST INFRASTRUCTURE ONLY: each function
+restates what the corresponding C-ABI kernel computes, with torch CPU ops, following the oracle."""
+import numpy as np
+import torch
+
+from tensornetworksfork_b200 import ops as real
+from tensornetworksfork_b200.ops import Factor, npairs  # noqa: F401
+
+
+def _rows(f: Factor, rows):
+    t = f.tensor
+    idx = torch.arange(rows) // max(f.div, 1)
+    idx = idx.clamp(max=t.shape[0] - 1)
+    if f.map_kind == real.MAP_IDENTITY:
+        return t[idx][:, f.col:f.col + f.m]
+    x = t[idx][:, f.col]
+    if f.map_kind == real.MAP_SINCOS:
+        return torch.stack([torch.cos(0.5 * np.pi * x), torch.sin(0.5 * np.pi * x)], dim=1)
+    return torch.stack([x ** d for d in range(f.m)], dim=1)
+
+
+def ones_factor(like):
+    return Factor(torch.ones(1, 1, dtype=torch.float64), m=1, div=1 << 30)
+
+
+def env_update(env_in, x, core3, rows, cdiv=1, env_div=1, out=None):
+    phi = _rows(Factor(x.tensor, m=x.m, div=cdiv, map_kind=x.map_kind, col=x.col), rows)
+    e = torch.ones(rows, 1, dtype=torch.float64) if env_in is None else env_in[torch.arange(rows) // env_div]
+    return torch.einsum("sa,sp,apb->sb", e, phi, core3)
+
+
+def predict(env_in, x, core3, dot, rows, cdiv=1, env_div=1, dot_div=1, out=None):
+    o = env_update(env_in, x, core3, rows, cdiv, env_div)
+    d = dot[(torch.arange(rows) // dot_div).clamp(max=dot.shape[0] - 1)]
+    y = (o * d).sum(1)
+    if out is not None:
+        out.copy_(y)
+        return out
+    return y
+
+
+def class_rows(env, U, g):
+    F = torch.einsum("stc,sca->sta", U, env).reshape(-1, env.shape[2]) if U is not None else None
+    G = torch.einsum("sc,sca->sa", g, env) if g is not None else None
+    return F, G
+
+
+def _pairs(F):
+    m = F.shape[1]
+    return torch.stack([F[:, i] * F[:, j] for i in range(m) for j in range(i, m)], dim=1)
+
+
+def gram(mode, fa, fb, fc, w, rows, M=None, accumulate=False):
+    A, B, C = _pairs(_rows(fa, rows)), _pairs(_rows(fb, rows)), _pairs(_rows(fc, rows))
+    ww = torch.ones(rows, dtype=torch.float64) if w is None else w
+    out = torch.einsum("s,sa,sb,sc->abc", ww, A, B, C).reshape(-1)
+    if M is None:
+        return out
+    if accumulate:
+        M += out
+    else:
+        M.copy_(out)
+    return M
+
+
+def rhs(fa, fb, fc, w, rows, b=None, accumulate=False):
+    ww = torch.ones(rows, dtype=torch.float64) if w is None else w
+    out = torch.einsum("s,sa,sb,sc->abc", ww, _rows(fa, rows), _rows(fb, rows), _rows(fc, rows)).reshape(-1)
+    if b is None:
+        return out
+    if accumulate:
+        b += out
+    else:
+        b.copy_(out)
+    return b
+
+
+def _dense(M, m_pos, role_of_pos):
+    n = [npairs(m) for m in m_pos]
+    n_role = [0, 0, 0]
+    for t in range(3):
+        n_role[role_of_pos[t]] = n[t]
+    Mt = M.reshape(n_role)
+    P = m_pos[0] * m_pos[1] * m_pos[2]
+    idx = torch.arange(P)
+    ii = [idx // (m_pos[1] * m_pos[2]), (idx // m_pos[2]) % m_pos[1], idx % m_pos[2]]
+    q = [None, None, None]
+    for t in range(3):
+        lo = torch.minimum(ii[t][:, None], ii[t][None, :])
+        hi = torch.maximum(ii[t][:, None], ii[t][None, :])
+        q[role_of_pos[t]] = lo * m_pos[t] - (lo * (lo - 1)) // 2 + (hi - lo)
+    return Mt[q[0], q[1], q[2]]
+
+
+def gram_sigma(M, m_pos, role_of_pos):
+    s = _dense(M, m_pos, role_of_pos).diagonal().abs().mean()
+    return torch.where(s == 0, torch.ones_like(s), s).reshape(1)
+
+
+def gram_expand(M, m_pos, role_of_pos, sigma, ridge, A=None):
+    D = _dense(M, m_pos, role_of_pos) / sigma
+    D = D + ridge * torch.eye(D.shape[0], dtype=torch.float64)
+    return D.contiguous()
+
+
+def rhs_prepare(b, theta, sigma, ridge):
+    v = b / sigma
+    if ridge != 0:
+        v = v + ridge * theta
+    return -v
+
+
+def cholesky_solve(A, rhs_vec):
+    P = A.shape[0]
+    info = torch.zeros(1, dtype=torch.int32)
+    try:
+        L = torch.linalg.cholesky(A[:, :P])
+    except torch.linalg.LinAlgError:
+        info[0] = 1
+        return info
+    rhs_vec.copy_(torch.cholesky_solve(rhs_vec.unsqueeze(-1), L).squeeze(-1))
+    return info
+
+
+def update_node(theta, step, lr=1.0, adaptive_step=False, max_norm=None):
+    if adaptive_step:
+        sn, pn = torch.norm(step), torch.norm(theta)
+        if sn > pn:
+            step = step * (pn / sn)
+    theta += lr * step
+    if max_norm is not None:
+        cn = torch.norm(theta)
+        if cn > max_norm:
+            theta *= max_norm / cn
+    return theta
+
+
+def qr(a):
+    Q, R = torch.linalg.qr(a, mode="reduced")
+    a.copy_(Q)
+    return R
+
+
+def matvec(fa, fb, fc, w, rows, v, out=None):
+    J = torch.einsum("sa,sb,sc->sabc", _rows(fa, rows), _rows(fb, rows), _rows(fc, rows)).reshape(rows, -1)
+    ww = torch.ones(rows, dtype=torch.float64) if w is None else w
+    return J.t() @ (ww * (J @ v))
+
+
+NAMES = ["ones_factor", "env_update", "predict", "class_rows", "gram", "rhs", "gram_sigma", "gram_expand", "rhs_prepare",
+         "cholesky_solve", "update_node", "qr", "matvec"]
+
+
+def install(monkeypatch=None):
+    """Swap the kernels for the stand-ins and lift the CUDA-only guard (tests only)."""
+    import sys
+    from tensornetworksfork_b200.tensor import network
+    me = sys.modules[__name__]
+    for n in NAMES:
+        if monkeypatch is not None:
+            monkeypatch.setattr(real, n, getattr(me, n))
+        else:
+            setattr(real, n, getattr(me, n))
+    if monkeypatch is not None:
+        monkeypatch.setattr(network.TensorNetwork, "_require_cuda", lambda self, dev: None)
+    else:
+        network.TensorNetwork._require_cuda = lambda self, dev: None

@@ -107,7 +107,7 @@ def test_gram_and_rhs_fp64(S, ma, mb, mc, V):
     assert gu.relerr(mv, A_want @ v) < 1e-11
 
 
-@pytest.mark.parametrize("P", [1, 5, 64, 65, 100, 324, 900, 1200, 2888, 4500])
+@pytest.mark.parametrize("P", [1, 5, 64, 65, 100, 324, 900, 1200, 2888, 4500, 6001])
 def test_cholesky_solve(P):
     rng = np.random.default_rng(P)
     B = rng.normal(size=(P, P + 10))

@@ -1,0 +1,119 @@
+"""Host-side sweep driver on CPU stand-in kernels: golden parity of the DRIVER logic (schedule, caching,
+QR re-gauge, loss bookkeeping) and the sample-sharded path over gloo with world_size 2."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import fake_ops
+import golden_util as gu
+
+torch.set_default_dtype(torch.float64)
+import tensornetworksfork_b200 as tnb  # noqa: E402
+
+
+def build(fx):
+    meta = fx["meta"]
+    if meta["kind"] == "cpd":
+        layer = tnb.CPDLayer(meta["n"], meta["r"], meta["f"], output_shape=(meta["C"],), seed=0)
+    else:
+        layer = tnb.TensorTrainLayer(meta["n"], meta["r"], meta["f"], output_shape=meta["C"], constrict_bond=False, seed=0)
+    for n, c in zip(layer.tensor_network.train_nodes, fx["cores0"]):
+        n.tensor = torch.tensor(c)
+    return layer
+
+
+def loss_of(meta):
+    return {"square": tnb.SquareBregFunction, "mse": tnb.AutogradLoss, "xe": lambda: tnb.XEAutogradBregman(w=meta.get("w", 1.0))}[meta["loss"]]()
+
+
+def run(fx, layer, x, y, **extra):
+    meta = fx["meta"]
+    trace = []
+    tn = layer.tensor_network
+    ok = tn.accumulating_swipe(x, y, loss_of(meta), batch_size=meta["batch_size"], num_swipes=meta["num_swipes"], lr=meta["lr"],
+                               method=meta["method"], eps=meta["eps"], eps_decay=meta.get("eps_decay"),
+                               orthonormalize=meta.get("orthonormalize", False), skip_second=meta.get("skip_second", False),
+                               loss_callback=lambda NS, node, l: trace.append((NS, tn.train_nodes.index(node), l)), **extra)
+    return ok, trace
+
+
+@pytest.mark.parametrize("name", [n for n in gu.names() if n != "tt_exact_lr"])
+def test_driver_reproduces_reference_on_standin_kernels(name, monkeypatch):
+    fake_ops.install(monkeypatch)
+    fx = gu.load(name)
+    layer = build(fx)
+    x = [torch.tensor(t) for t in fx["x"]] if isinstance(fx["x"], list) else torch.tensor(fx["x"])
+    y = torch.tensor(fx["y"])
+    ok, trace = run(fx, layer, x, y)
+    assert ok == fx["ok"]
+    assert [(a, b) for a, b, _ in trace] == [(u["NS"], u["k"]) for u in fx["updates"]]
+    for (_, _, l), u in zip(trace, fx["updates"]):
+        assert abs(l - u["loss"]) <= 1e-7 * max(1.0, abs(u["loss"]))
+    pred = layer.tensor_network.forward_batch(x, meta_bs(fx)).numpy()
+    assert gu.relerr(pred.reshape(fx["pred"].shape), fx["pred"]) < 1e-7
+
+
+def meta_bs(fx):
+    return fx["meta"]["batch_size"]
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _shard_worker(rank, world, port, name, out_dir):
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_default_dtype(torch.float64)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fake_ops as fo
+    fo.install()
+    fx = gu.load(name)
+    layer = build(fx)
+    tn = layer.tensor_network
+    N = fx["y"].shape[0]
+    cut = [0, N // 2 + 7, N][rank:rank + 2]          # uneven shards on purpose
+    sl = slice(cut[0], cut[1])
+    x = [torch.tensor(t[sl]) for t in fx["x"]] if isinstance(fx["x"], list) else torch.tensor(fx["x"][sl])
+    y = torch.tensor(fx["y"][sl])
+    tn.process_group = dist.group.WORLD
+    tn.shard_offset = cut[0]
+    tn.shard_total = N
+    ok, trace = run(fx, layer, x, y)
+    cores = [n.tensor.numpy() for n in tn.train_nodes]
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), ok=ok, losses=np.array([l for _, _, l in trace]),
+             **{f"core{i}": c for i, c in enumerate(cores)})
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["tt_poly_reg", "tnml_poly_xe"])
+def test_sample_sharded_sweep_world2_gloo(name, tmp_path):
+    """Two ranks, each with a row shard: one sum-all-reduce of [M | b] (and the per-batch loss sums) per site.
+    Result must equal the single-process sweep and the reference recording; cores bit-identical across ranks."""
+    port = _free_port()
+    mp.spawn(_shard_worker, args=(2, port, name, str(tmp_path)), nprocs=2, join=True)
+    fx = gu.load(name)
+    r0 = np.load(tmp_path / "rank0.npz")
+    r1 = np.load(tmp_path / "rank1.npz")
+    assert bool(r0["ok"]) and bool(r1["ok"])
+    nc = len(fx["cores0"])
+    for i in range(nc):
+        assert np.array_equal(r0[f"core{i}"], r1[f"core{i}"]), "ranks diverged"
+    for l0, l1, u in zip(r0["losses"], r1["losses"], fx["updates"]):
+        assert l0 == l1
+        assert abs(l0 - u["loss"]) <= 1e-7 * max(1.0, abs(u["loss"]))
+    last = fx["updates"][-1]["after"]
+    for i in range(nc):
+        assert gu.relerr(r0[f"core{i}"], last[i]) < 1e-6

@@ -51,3 +51,26 @@ if what in ("time", "all"):
                 ms = timeit(lambda: ops.gram(mode, fa, fb, fc, w, S, M=M), n=2)
                 print(json.dumps({"probe": "time", "site": name, "rows": S, "mode": nm, "flush_rows": fr, "ms": ms,
                                   "issued_tflops": flops * mult / ms / 1e9, "useful_tflops": flops / ms / 1e9}))
+if what in ("chol",):
+    for P in (2888, 8664, 20000, 41876):
+        lda = (P + 7) // 8 * 8
+        g = torch.Generator(device=DEV).manual_seed(P)
+        A = torch.empty((P, lda), device=DEV)
+        blk = 4096
+        for i in range(0, P, blk):      # symmetric, diagonally dominant: cheap to generate at 14 GB
+            A[i:i + blk, :P] = 0.5 / P ** 0.5 * torch.randn((min(blk, P - i), P), device=DEV, generator=g)
+        A[:, :P] = 0.5 * (A[:, :P] + A[:, :P].t())
+        A[:, :P].diagonal().add_(2.0)
+        rhs = torch.randn((P,), device=DEV, generator=g)
+        A0 = A.clone() if P <= 20000 else None
+        r = rhs.clone()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        info = ops.cholesky_solve(A, r)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        res = None
+        if A0 is not None:
+            res = float((A0[:, :P] @ r - rhs).norm() / rhs.norm())
+        print(json.dumps({"probe": "chol", "P": P, "ms": ms, "tflops": P ** 3 / 3 / ms / 1e9, "info": int(info.item()), "residual": res}))
