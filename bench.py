@@ -33,9 +33,9 @@ WORKLOADS = {
                  desc="CPD rank 100 california_housing-shaped N=20640 F=8(+1) 5 factors"),
     "cfg3": dict(kind="tt", sites=90, r=24, features=90, bias=False, basis="sin-cos", C=1, n=515345, constrict=True,
                  perturb=False, batch_size=512, orthonormalize=True, desc="TNML sin-cos year-shaped N=515345 F=90 r=24 90 sites"),
-    "cfg5a": dict(kind="tt", sites=5, r=38, features=28, bias=True, basis=None, C=1, n=1250000, constrict=False,
+    "cfg5a": dict(kind="tt", sites=5, r=38, features=28, bias=True, basis=None, C=1, n=1000000, constrict=False,
                   perturb=False, batch_size=-1, desc="TT poly-mode higgs-shaped F=28(+1) r=38 5 cores (degree 5), P=41876"),
-    "cfg5b": dict(kind="tt", sites=28, r=38, features=28, bias=False, basis="polynomial", degree=5, C=1, n=1250000,
+    "cfg5b": dict(kind="tt", sites=28, r=38, features=28, bias=False, basis="polynomial", degree=5, C=1, n=1000000,
                   constrict=True, perturb=False, batch_size=-1, orthonormalize=True,
                   desc="TNML polynomial degree 5 higgs-shaped F=28 r=38 28 sites, P<=8664"),
 }
@@ -49,7 +49,8 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg5a", choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=None, help="rows per GPU (default: the workload's)")
-    ap.add_argument("--gram-mode", default="fp64", choices=["fp64", "tf32", "tf32x3"])
+    ap.add_argument("--gram-mode", default="tf32x3", choices=["fp64", "tf32", "tf32x3"])
+    ap.add_argument("--no-peaks", action="store_true", help="skip the cuBLAS TF32/FP64 peak measurement")
     ap.add_argument("--eps", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -163,7 +164,11 @@ class KernelTimer:
             out = fn(*a, **k)
             e1.record()
             self.events[n].append((e0, e1))
-            self.extra[n].append((a, k))
+            # keep sizes only: holding the argument tensors would pin every 14 GB system matrix of the step
+            if n == "gram":
+                self.extra[n].append((a[1].m, a[2].m, a[3].m, a[5]))
+            elif n == "cholesky_solve":
+                self.extra[n].append(int(a[0].shape[0]))
             return out
 
         return inner
@@ -174,11 +179,10 @@ class KernelTimer:
 
 def gram_flops(call):
     """Issued multiply-adds x2 of one ops.gram call: rows * n_a*n_b*n_c pairs (the Kronecker-symmetric GEMM)."""
-    a, k = call
-    fa, fb, fc, rows = a[1], a[2], a[3], a[5]
+    ma, mb, mc, rows = call
     npair = lambda m: m * (m + 1) // 2
-    P = fa.m * fb.m * fc.m
-    return 2.0 * rows * npair(fa.m) * npair(fb.m) * npair(fc.m), float(rows) * P * (P + 1)
+    P = ma * mb * mc
+    return 2.0 * rows * npair(ma) * npair(mb) * npair(mc), float(rows) * P * (P + 1)
 
 
 def run_sweeps(layer, x, y, wl, args, steps, counter):
@@ -293,6 +297,11 @@ def bench_b200(args):
     except Exception:
         pass
     tot = timer.totals()
+    measured = None
+    if not args.no_peaks:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import peaks as _peaks
+        measured = _peaks.measure()
     gram_ms = tot["gram"]
     launches = sum(len(v) for v in tot.values())
     issued = algo = 0.0
@@ -302,10 +311,16 @@ def bench_b200(args):
         algo += a_
     gsum = sum(gram_ms) / 1e3
     if args.gram_mode == "fp64":
-        peak, peak_src = 40.0, "nominal B200 fp64 40 TFLOP/s (no measured fp64 peak in MEASURED_PEAKS.json)"
+        if measured:
+            peak, peak_src = measured["fp64_tflops_sustained"], "cuBLAS DGEMM 8192^3 measured in this run (sustained)"
+        else:
+            peak, peak_src = 35.5, "cuBLAS DGEMM measured on this pool earlier (profiles/r1_peaks_tf32_fp64.json)"
     else:
-        bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
-        peak, peak_src = bf16 / 2.0, "half of the measured sustained bf16 dense peak (TF32 rate = bf16/2); " + ("measured" if peaks else "fallback")
+        if measured:
+            peak, peak_src = measured["tf32_tflops_sustained"], "cuBLAS TF32 GEMM 8192^3 measured in this run (sustained; kernel is timed inside a long step)"
+        else:
+            bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
+            peak, peak_src = bf16 / 2.0, "half of the sustained bf16 dense peak of MEASURED_PEAKS.json (TF32 rate = bf16/2); " + ("of measured" if peaks else "of fallback")
     mult = 3.0 if args.gram_mode == "tf32x3" else 1.0
     achieved = issued * mult / gsum / 1e12 if gsum > 0 else 0.0
     roofline = {"kernel": f"gram_kr3[{args.gram_mode}]", "bound": "tensor" if args.gram_mode != "fp64" else "fp64", "achieved": achieved,
@@ -313,7 +328,12 @@ def bench_b200(args):
                 "peak_source": peak_src, "issued_flops_per_step": issued * mult / args.steps,
                 "survey_algorithmic_flops_per_step": algo / args.steps,
                 "survey_equiv_tflops": algo / gsum / 1e12 if gsum > 0 else 0.0,
-                "share_of_step": gsum / (ms / 1e3), "launches": len(gram_ms)}
+                "share_of_step": gsum / (ms / 1e3), "launches": len(gram_ms), "measured_peaks": measured,
+                "bf16_peaks_file": {k: peaks.get(k) for k in ("bf16_tflops", "bf16_tflops_sustained", "hbm_gbs")}}
+    chol_ms = tot["cholesky_solve"]
+    chol_flops = sum(P_ ** 3 / 3.0 for P_ in timer.extra["cholesky_solve"])
+    solve_info = {"kernel": "cholesky_solve[fp64]", "tflops": chol_flops / (sum(chol_ms) / 1e3) / 1e12 if chol_ms else None,
+                  "share_of_step": sum(chol_ms) / ms, "peak": measured["fp64_tflops_sustained"] if measured else 35.5}
     shares = {k: sum(v) / ms for k, v in tot.items()}
     out = {"metric": "gn_site_updates_per_s", "value": value, "unit": "site-updates/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -321,7 +341,8 @@ def bench_b200(args):
            "config": {"workload": f"{args.workload}: {wl['desc']}", "rows_per_gpu": n, "rows_total": n * world,
                       "site_updates_per_step": updates // max(args.steps, 1), "gram_mode": args.gram_mode, "eps": args.eps,
                       "l2": "inputs larger than L2 (per-site streams of rows*(r_l+f+r_r)*8 B)", "parallelism": f"sample-shard x{world}"},
-           "samples_per_s": value * n * world, "roofline": roofline, "kernel_time_share": shares, "gpu_launches": launches,
+           "samples_per_s": value * n * world, "roofline": roofline, "solve": solve_info, "kernel_time_share": shares,
+           "gpu_launches": launches,
            "clocks": clk, "e2e": e2e}
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, wl, n * world)

@@ -9,7 +9,22 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
 def names():
-    return sorted(os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+    return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
+                  if not n.startswith("krylov_"))
+
+
+def load_krylov(name):
+    """Fixtures of tests/golden/make_golden_krylov.py (lanczos_swipe / scipy_swipe recordings)."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"), allow_pickle=False)
+    nc = int(z["n_cores"])
+    ups = []
+    for ui in range(int(z["n_updates"])):
+        NS, k = z[f"u{ui}_scal"]
+        u = {"NS": int(NS), "k": int(k), "after": [z[f"u{ui}_after_{i}"] for i in range(nc)]}
+        if f"u{ui}_x0" in z.files:
+            u["x0"] = z[f"u{ui}_x0"]
+        ups.append(u)
+    return {"x": z["x"], "y": z["y"], "cores0": [z[f"cores0_{i}"] for i in range(nc)], "updates": ups, "losses": z["losses"]}
 
 
 def load(name):
