@@ -12,11 +12,12 @@
 // Every FLUSH_ROWS rows the accumulator is drained TMEM -> registers -> fp64 and added to M in
 // global memory, which bounds the fp32 accumulation length.
 //
-// Warp roles in a CTA of 288 threads: warp 0 allocates TMEM and issues the MMAs (one elected lane);
-// warps 1..8 stage the raw factors (global fp64 -> shared fp32, transposed, prefetched one chunk
-// ahead in registers), synthesise the tiles, and drain the accumulator at flush points.
-// Shared-memory stages are handed over with mbarriers: full[s] (producers -> MMA, after
-// fence.proxy.async) and empty[s] (tcgen05.commit -> producers).
+// A pre-pass (tc_stage_kernel) evaluates the feature maps / row divisors once and writes the raw factors
+// feature-major in fp32, Z[(w*fa | fa | fb | fc)][rows], so a 16-sample piece of a factor row is 64
+// contiguous bytes.  Warp roles in a CTA of 288 threads: warp 0 allocates TMEM and issues the MMAs (one
+// elected lane); warps 1..8 cp.async the next chunks of Z into a 3-slot shared ring, synthesise the operand
+// tiles, and drain the accumulator at flush points.  Operand stages are handed over with mbarriers:
+// full[s] (producers -> MMA, after fence.proxy.async) and empty[s] (tcgen05.commit -> producers).
 #include <stdlib.h>
 #include <type_traits>
 #include "common.cuh"
@@ -29,7 +30,7 @@ constexpr int TC_KCP = TC_KC + 4;  // padded row of the transposed raw-factor st
 constexpr int TC_PROD_WARPS = 8;
 constexpr int TC_PROD = TC_PROD_WARPS * 32;
 constexpr int TC_THREADS = 32 + TC_PROD;
-constexpr int TC_MAXLD = 8;        // raw values a producer thread prefetches per chunk
+constexpr int TC_RAW_SLOTS = 3;    // shared ring of raw-factor chunks filled by cp.async
 constexpr int TC_FLUSH_ROWS_DEFAULT = 1024;
 
 struct TcFactor {
@@ -41,8 +42,9 @@ struct TcFactor {
 };
 
 struct TcParams {
-    TcFactor fa, fb, fc;
-    const double* w;
+    const float* Z;      // staged factors, feature-major: rows [w*fa (mA) | fa (mA) | fb (mB) | fc (mC)], each zpitch floats
+    int64_t zpitch;      // floats per row of Z (rows rounded up to TC_KC, zero padded)
+    int mA, mB, mC;
     int64_t rows;
     int64_t rows_per_split;
     double* M;
@@ -142,6 +144,42 @@ __device__ __forceinline__ void store_split(float4 v, uint32_t hi_addr, uint32_t
     if (SPLIT) sts128(lo_addr, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
 }
 
+// ---- pre-pass: factors (fp64, sample-major, possibly mapped / shared by V rows) -> Z (fp32, feature-major)
+__global__ void __launch_bounds__(256)
+tc_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict__ w, int64_t rows, float* __restrict__ Z,
+                int64_t zpitch) {
+    __shared__ float tile[32][33];
+    const int mA = fa.m, mB = fb.m, mC = fc.m;
+    const int msum = mA + mB + mC;
+    const int64_t s0 = (int64_t)blockIdx.x * 32;
+    const int i0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+    // read: lane = feature (coalesced along a sample's row), 8 samples per pass
+    for (int r = ty; r < 32; r += 8) {
+        const int64_t s = s0 + r;
+        const int i = i0 + tx;
+        float v = 0.f;
+        if (s < rows && i < msum) {
+            const TcFactor& f = (i < mA) ? fa : ((i < mA + mB) ? fb : fc);
+            const int il = (i < mA) ? i : ((i < mA + mB) ? i - mA : i - mA - mB);
+            const int64_t ri = (f.div == 1) ? s : s / f.div;
+            v = (float)map_eval(f.map_kind, f.ptr + ri * f.ld, il);
+        }
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    // write: lane = sample (coalesced along Z rows); rows past `rows` are written as zeros up to zpitch
+    for (int c = ty; c < 32; c += 8) {
+        const int i = i0 + c;
+        const int64_t s = s0 + tx;
+        if (i < msum && s < zpitch) {
+            const float v = tile[tx][c];
+            Z[(int64_t)(mA + i) * zpitch + s] = v;
+            if (i < mA) Z[(int64_t)i * zpitch + s] = (s < rows) ? v * (float)(w ? w[s] : 1.0) : 0.f;
+        }
+    }
+}
+
 // TMEM accumulator -> registers -> fp64 atomic adds into M.  Warp w may touch TMEM lanes 32*(w%4)..+31;
 // the two producer warps that share a lane quarter split the columns.
 __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_total, int BN, int warp, int lane, int64_t u0,
@@ -167,26 +205,25 @@ __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_tota
     }
 }
 
-template <int SPLIT, int T, int SLOW>
+template <int SPLIT, int T>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gram_tc_kernel(TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    __shared__ float wbuf_s[2][TC_KC];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int BN = p.BN, NS = p.nstages;
-    const int mA = p.fa.m, mB = p.fb.m, mC = p.fc.m;
-    const int msum = mA + mB + mC;
+    const int mA = p.mA, mB = p.mB, mC = p.mC;
 
-    // ---- shared memory carve-up: [NS stages][2 raw-factor buffers][mbarriers][tmem slot]
+    // ---- shared memory carve-up: [NS operand stages][TC_RAW_SLOTS raw-factor slots][mbarriers][tmem slot]
     constexpr uint32_t a_tile_bytes = TC_M * TC_KC * 4;      // one U tile, hi or lo, one stage
     const uint32_t b_tile_bytes = (uint32_t)BN * TC_KC * 4;  // V tile, hi or lo
     const uint32_t stage_bytes = 2 * T * a_tile_bytes + 2 * b_tile_bytes;
-    const uint32_t raw_rows = (uint32_t)(2 * mA + mB + mC) + 2;   // + an all-zero row (padding rows of the tiles) + a scratch row
-    const uint32_t raw_floats = raw_rows * TC_KCP;
+    const uint32_t z_rows = (uint32_t)(2 * mA + mB + mC);
+    const uint32_t raw_rows = z_rows + 1;                      // + an all-zero row for the padding rows of the tiles
+    const uint32_t raw_bytes = raw_rows * TC_KCP * 4;
     uint8_t* stage_base = smem_raw;
-    float* raw0 = reinterpret_cast<float*>(smem_raw + (size_t)NS * stage_bytes);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(raw0) + 2 * (size_t)raw_floats * 4);
+    uint8_t* raw_base = smem_raw + (size_t)NS * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)TC_RAW_SLOTS * raw_bytes);
     uint64_t* full = bars;              // [NS]
     uint64_t* empty = bars + NS;        // [NS]
     uint64_t* acc_full = bars + 2 * NS;
@@ -206,17 +243,17 @@ gram_tc_kernel(TcParams p) {
         mbar_init(acc_empty, TC_PROD_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < 2 * TC_KCP; i += TC_THREADS)   // the zero row of both raw buffers
-        raw0[(size_t)(i / TC_KCP) * raw_floats + (raw_rows - 2) * TC_KCP + (i % TC_KCP)] = 0.f;
+    for (int i = tid; i < TC_RAW_SLOTS * TC_KCP; i += TC_THREADS)   // the zero row of every raw slot
+        reinterpret_cast<float*>(raw_base + (size_t)(i / TC_KCP) * raw_bytes)[z_rows * TC_KCP + (i % TC_KCP)] = 0.f;
     if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int64_t k_begin = (int64_t)blockIdx.z * p.rows_per_split;
-    const int64_t k_end = min(p.rows, k_begin + p.rows_per_split);
-    const int64_t nchunks = (k_end > k_begin) ? (k_end - k_begin + TC_KC - 1) / TC_KC : 0;
+    const int64_t k_begin = (int64_t)blockIdx.z * p.rows_per_split;          // multiples of TC_KC; Z is zero padded
+    const int64_t k_end = min(p.zpitch, k_begin + p.rows_per_split);
+    const int64_t nchunks = (k_end > k_begin) ? (k_end - k_begin) / TC_KC : 0;
     const int64_t chunks_per_flush = p.flush_rows / TC_KC;
     const int64_t nU = (int64_t)p.nA * p.nB;
     const int64_t u0 = (int64_t)blockIdx.x * (TC_M * T);
@@ -271,10 +308,10 @@ gram_tc_kernel(TcParams p) {
     } else {
         // =============================== producers / epilogue ===============================
         const int pt = tid - 32;  // 0..255
-        const uint32_t raw_s = smem_u32(raw0);
-        const uint32_t zero_row = (raw_rows - 2) * TC_KCP * 4;        // byte offset of the zero row in a raw buffer
+        const uint32_t raw_s = smem_u32(raw_base);
+        const uint32_t zero_row = z_rows * TC_KCP * 4;                 // byte offset of the zero row in a raw slot
         // -- rows of the operand tiles this thread synthesises (fixed for the kernel)
-        uint32_t usrc[4] = {zero_row, zero_row, zero_row, zero_row};   // byte offsets of Aw[ia], A[ja], B[ib], B[jb]
+        uint32_t usrc[4] = {zero_row, zero_row, zero_row, zero_row};   // byte offsets of w*fa[ia], fa[ja], fb[ib], fb[jb]
         int u_tile = 0, u_row = pt & 127, u_c0 = 0;
         constexpr int U_NC = (T == 2) ? TC_KC / 4 : TC_KC / 8;          // k-chunks of 4 samples per thread and stage
         if (T == 2) u_tile = pt >> 7;
@@ -304,97 +341,34 @@ gram_tc_kernel(TcParams p) {
         const uint32_t lbo_b = (uint32_t)BN * 16;
         const uint32_t stage_s = smem_u32(stage_base);
 
-        // -- load plan: the raw values this thread fetches every chunk (fixed for the kernel).  Unused slots
-        //    read a harmless address and write into the scratch row, so the per-chunk code has no branches.
-        const int nvals = TC_KC * msum;
-        const int scratch_f = (int)(raw_rows - 1) * TC_KCP;   // float index of the scratch row (after the zero row)
-        const double* ld_ptr[TC_MAXLD];   // address of the value in the next chunk to prefetch
-        int ld_step[TC_MAXLD];            // elements to advance per chunk
-        int ld_meta[TC_MAXLD];            // dst | dst_weighted << 13 | k << 26        (float indices in a raw buffer)
-        int ld_gen[TC_MAXLD];             // SLOW kernels: fac | i_local << 2
-#pragma unroll
-        for (int q = 0; q < TC_MAXLD; ++q) {
-            const int idx = pt + q * TC_PROD;
-            ld_ptr[q] = p.fa.ptr;
-            ld_step[q] = 0;
-            ld_meta[q] = scratch_f | (scratch_f << 13);
-            ld_gen[q] = -1;
-            if (idx < nvals) {
-                const int k = idx / msum, i = idx - k * msum;
-                const int fac = (i < mA) ? 0 : ((i < mA + mB) ? 1 : 2);
-                const int il = (fac == 0) ? i : ((fac == 1) ? i - mA : i - mA - mB);
-                const TcFactor& f = (fac == 0) ? p.fa : ((fac == 1) ? p.fb : p.fc);
-                const int dst = (mA + i) * TC_KCP + k;
-                const int dstw = (fac == 0) ? dst - mA * TC_KCP : scratch_f;
-                ld_meta[q] = dst | (dstw << 13) | (k << 26);
-                const bool shared_row = f.div >= (1 << 29);          // the all-ones factor: one row for every sample
-                ld_ptr[q] = f.ptr + (shared_row ? 0 : (k_begin + k) * f.ld) + il;
-                ld_step[q] = shared_row ? 0 : (int)(TC_KC * f.ld);
-                ld_gen[q] = fac | (il << 2);
-            }
-        }
-
-        // Issue the global loads of the next chunk (chunks are prefetched in increasing order).
-        auto prefetch = [&](int64_t chunk, double (&pre)[TC_MAXLD], double& pre_w) {
-            const int64_t kb = k_begin + chunk * TC_KC;
-#pragma unroll
-            for (int q = 0; q < TC_MAXLD; ++q) {
-                if (!SLOW) {
-                    pre[q] = *ld_ptr[q];
-                    ld_ptr[q] += ld_step[q];
-                } else {
-                    double v = 0.0;
-                    const int gen = ld_gen[q];
-                    if (gen >= 0) {
-                        const int fac = gen & 3;
-                        const TcFactor& f = (fac == 0) ? p.fa : ((fac == 1) ? p.fb : p.fc);
-                        const int64_t row = kb + (ld_meta[q] >> 26);
-                        if (row < k_end) {                               // ragged last chunk: rows past the end are zero
-                            const int64_t ri = (f.div == 1) ? row : row / f.div;
-                            v = map_eval(f.map_kind, f.ptr + ri * f.ld, gen >> 2);
-                        }
-                    }
-                    pre[q] = v;
+        // -- cp.async plan: 16-byte pieces (4 samples of one Z row) of a chunk, spread over the producer threads
+        const int npieces = (int)z_rows * (TC_KC / 4);
+        auto issue_chunk = [&](int64_t chunk) {
+            if (chunk < nchunks) {
+                const float* src0 = p.Z + k_begin + chunk * TC_KC;
+                const uint32_t dst0 = raw_s + (uint32_t)(chunk % TC_RAW_SLOTS) * raw_bytes;
+                for (int pc = pt; pc < npieces; pc += TC_PROD) {
+                    const int row = pc >> 2, part = pc & 3;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)row * (TC_KCP * 4) + part * 16),
+                                 "l"(src0 + (int64_t)row * p.zpitch + part * 4) : "memory");
                 }
             }
-            if (pt < TC_KC) pre_w = (kb + pt < k_end) ? (p.w ? p.w[kb + pt] : 1.0) : 0.0;
+            asm volatile("cp.async.commit_group;" ::: "memory");
         };
-        // registers -> transposed fp32 staging [factor row][sample]; A rows are stored twice (weighted copy first)
-        auto stash = [&](float* raw, float* wbuf, const double (&pre)[TC_MAXLD], double pre_w) {
-            if (pt < TC_KC) wbuf[pt] = (float)pre_w;
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");
-#pragma unroll
-            for (int q = 0; q < TC_MAXLD; ++q) {
-                const int meta = ld_meta[q];
-                const float v = (float)pre[q];
-                raw[meta & 0x1fff] = v;
-                raw[(meta >> 13) & 0x1fff] = v * wbuf[meta >> 26];
-            }
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");
-        };
-        double preE[TC_MAXLD], preO[TC_MAXLD];   // prefetched raw values of even / odd chunks
-        double wE = 0.0, wO = 0.0;
-        if (nchunks > 0) {
-            prefetch(0, preE, wE);
-            stash(raw0, wbuf_s[0], preE, wE);
-            if (nchunks > 1) prefetch(1, preO, wO);
-        }
+        issue_chunk(0);
+        issue_chunk(1);
+
         uint32_t acc_phase = 0;
-        int s = 0;
+        int s = 0, rs = 0;
         uint32_t ph = 0;
         int64_t in_window = 0;
-
-        // One pipeline stage: synthesise chunk c from raw buffer PAR, hand it to the MMA warp, then move the
-        // already-loaded chunk c+1 into the other raw buffer and start the loads of chunk c+2.
-        auto body = [&](int64_t c, auto par_tag) {
-            constexpr int PAR = decltype(par_tag)::value;
-            const uint32_t rb = raw_s + (uint32_t)PAR * raw_floats * 4;
-            if (c + 2 < nchunks) {
-                if (PAR) prefetch(c + 2, preO, wO);
-                else prefetch(c + 2, preE, wE);
-            }
-            if (lane == 0) mbar_wait(&empty[s], ph ^ 1);       // first pass over the ring returns immediately
+        for (int64_t c = 0; c < nchunks; ++c) {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");       // this thread's pieces of chunk c have landed
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");  // everyone's have; chunk c-1 is fully consumed
+            issue_chunk(c + 2);                                          // reuses the slot chunk c-1 occupied
+            if (lane == 0) mbar_wait(&empty[s], ph ^ 1);                 // first pass over the ring returns immediately
             __syncwarp();
+            const uint32_t rb = raw_s + (uint32_t)rs * raw_bytes;
             const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
             {   // ---- U rows: all loads, then the products, then the stores (no load waits behind a store)
                 float4 x0[U_NC], x1[U_NC], x2[U_NC], x3[U_NC];
@@ -429,12 +403,8 @@ gram_tc_kernel(TcParams p) {
             fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
-            if (c + 1 < nchunks) {        // chunk c+1 (opposite parity) goes into the other raw buffer
-                float* nraw = raw0 + (size_t)(1 - PAR) * raw_floats;
-                if (PAR) stash(nraw, wbuf_s[0], preE, wE);
-                else stash(nraw, wbuf_s[1], preO, wO);
-            }
             if (++s == NS) { s = 0; ph ^= 1; }
+            if (++rs == TC_RAW_SLOTS) rs = 0;
             // ---- flush: drain the accumulator into fp64 M
             const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
             if (last_of_window) {
@@ -447,11 +417,8 @@ gram_tc_kernel(TcParams p) {
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty);
             }
-        };
-        for (int64_t c = 0; c < nchunks; c += 2) {
-            body(c, std::integral_constant<int, 0>{});
-            if (c + 1 < nchunks) body(c + 1, std::integral_constant<int, 1>{});
         }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -463,8 +430,8 @@ gram_tc_kernel(TcParams p) {
 
 static size_t tc_smem_bytes(int mA, int mB, int mC, int BN, int T, int NS) {
     const size_t stage = 2 * (size_t)T * TC_M * TC_KC * 4 + 2 * (size_t)BN * TC_KC * 4;
-    const size_t raw = (size_t)(2 * mA + mB + mC + 2) * TC_KCP * 4;
-    return NS * stage + 2 * raw + (2 * NS + 2) * 8 + 16;
+    const size_t raw = (size_t)(2 * mA + mB + mC + 1) * TC_KCP * 4;
+    return NS * stage + TC_RAW_SLOTS * raw + (2 * NS + 2) * 8 + 16;
 }
 
 }  // namespace tn
@@ -473,16 +440,16 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
                    double* M, int accumulate, void* stream) {
     using namespace tn;
     cudaStream_t st = as_stream(stream);
+    const TcFactor A{fa->ptr, fa->ld, fa->m, fa->div < 1 ? 1 : fa->div, fa->map_kind};
+    const TcFactor B{fb->ptr, fb->ld, fb->m, fb->div < 1 ? 1 : fb->div, fb->map_kind};
+    const TcFactor C{fc->ptr, fc->ld, fc->m, fc->div < 1 ? 1 : fc->div, fc->map_kind};
     TcParams p;
-    p.fa = TcFactor{fa->ptr, fa->ld, fa->m, fa->div < 1 ? 1 : fa->div, fa->map_kind};
-    p.fb = TcFactor{fb->ptr, fb->ld, fb->m, fb->div < 1 ? 1 : fb->div, fb->map_kind};
-    p.fc = TcFactor{fc->ptr, fc->ld, fc->m, fc->div < 1 ? 1 : fc->div, fc->map_kind};
-    p.w = w;
+    p.mA = A.m; p.mB = B.m; p.mC = C.m;
     p.rows = rows;
     p.M = M;
-    p.nA = npairs(fa->m);
-    p.nB = npairs(fb->m);
-    p.nC = npairs(fc->m);
+    p.nA = npairs(A.m);
+    p.nB = npairs(B.m);
+    p.nC = npairs(C.m);
     p.split = (mode == 2) ? 1 : 0;
     p.flush_rows = TC_FLUSH_ROWS_DEFAULT;
     if (const char* e = getenv("TN_TC_FLUSH_ROWS")) {
@@ -491,61 +458,53 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     }
     const int64_t nU = (int64_t)p.nA * p.nB;
     const int64_t n = nU * p.nC;
-    TN_CHECK_ARG(TC_KC * (fa->m + fb->m + fc->m) <= TC_MAXLD * TC_PROD,
-                 "tn_gram_kr3 (tensor-core modes): factor sizes %d+%d+%d exceed the staging capacity of %d per row", fa->m, fb->m,
-                 fc->m, TC_MAXLD * TC_PROD / TC_KC);
     p.BN = (p.nC >= 256) ? 256 : ((p.nC + 15) / 16) * 16;
     p.T = (nU > TC_M && p.BN * 2 <= 512) ? 2 : 1;
     int NS = 4;
-    while (NS >= 2 && tc_smem_bytes(fa->m, fb->m, fc->m, p.BN, p.T, NS) > 227 * 1024) --NS;
+    while (NS >= 2 && tc_smem_bytes(A.m, B.m, C.m, p.BN, p.T, NS) > 226 * 1024) --NS;
     if (NS < 2 && p.T == 2) {
         p.T = 1;
         NS = 4;
-        while (NS >= 2 && tc_smem_bytes(fa->m, fb->m, fc->m, p.BN, p.T, NS) > 227 * 1024) --NS;
+        while (NS >= 2 && tc_smem_bytes(A.m, B.m, C.m, p.BN, p.T, NS) > 226 * 1024) --NS;
     }
-    TN_CHECK_ARG(NS >= 2, "tn_gram_kr3 (tensor-core modes): factors too large for the shared-memory pipeline");
+    TN_CHECK_ARG(NS >= 2, "tn_gram_kr3 (tensor-core modes): factor sizes %d+%d+%d do not fit the shared-memory pipeline", A.m, B.m, C.m);
     p.nstages = NS;
-    const size_t smem = tc_smem_bytes(fa->m, fb->m, fc->m, p.BN, p.T, NS);
+    const size_t smem = tc_smem_bytes(A.m, B.m, C.m, p.BN, p.T, NS);
     if (!accumulate) TN_CUDA(cudaMemsetAsync(M, 0, (size_t)n * sizeof(double), st));
     if (rows == 0) return TN_OK;
+
+    // ---- pre-pass: Z = [w*fa | fa | fb | fc] feature-major fp32, rows zero padded to a multiple of TC_KC
+    p.zpitch = ceil_div64(rows, TC_KC) * TC_KC;
+    const int z_rows = 2 * A.m + B.m + C.m;
+    float* Z = nullptr;
+    TN_CUDA(cudaMallocAsync(&Z, (size_t)z_rows * p.zpitch * sizeof(float), st));
+    p.Z = Z;
+    {
+        dim3 grid((unsigned)ceil_div64(p.zpitch, 32), (unsigned)ceil_div64(A.m + B.m + C.m, 32));
+        tc_stage_kernel<<<grid, 256, 0, st>>>(A, B, C, w, rows, Z, p.zpitch);
+        TN_LAUNCH_CHECK();
+    }
     const int64_t gx = ceil_div64(nU, (int64_t)TC_M * p.T), gy = ceil_div64(p.nC, p.BN);
     TN_CHECK_ARG(gy <= 65535 && gx <= 0x7fffffff, "tn_gram_kr3: grid too large");
+    // split the rows when there are too few tiles to fill the machine (flushes are atomic adds, so splits compose)
+    int64_t ks = ceil_div64((int64_t)sm_count(), gx * gy);
+    const int64_t max_ks = ceil_div64(p.zpitch, 4 * TC_KC);
+    if (ks > max_ks) ks = max_ks;
+    if (ks < 1) ks = 1;
+    if (ks > 65535) ks = 65535;
+    p.rows_per_split = ceil_div64(ceil_div64(p.zpitch, ks), TC_KC) * TC_KC;
+    ks = ceil_div64(p.zpitch, p.rows_per_split);
     using Kern = void (*)(TcParams);
-    static const Kern kerns[2][2][2] = {{{gram_tc_kernel<0, 1, 0>, gram_tc_kernel<0, 1, 1>}, {gram_tc_kernel<0, 2, 0>, gram_tc_kernel<0, 2, 1>}},
-                                        {{gram_tc_kernel<1, 1, 0>, gram_tc_kernel<1, 1, 1>}, {gram_tc_kernel<1, 2, 0>, gram_tc_kernel<1, 2, 1>}}};
-    static size_t configured[2][2][2] = {};
-    auto launch = [&](TcParams q, int slow) -> int {
-        if (q.rows <= 0) return TN_OK;
-        // split the rows when there are too few tiles to fill the machine (flushes are atomic adds, so splits compose)
-        int64_t ks = ceil_div64((int64_t)sm_count(), gx * gy);
-        const int64_t max_ks = ceil_div64(q.rows, 4 * TC_KC);
-        if (ks > max_ks) ks = max_ks;
-        if (ks < 1) ks = 1;
-        if (ks > 65535) ks = 65535;
-        q.rows_per_split = ceil_div64(ceil_div64(q.rows, ks), TC_KC) * TC_KC;
-        ks = ceil_div64(q.rows, q.rows_per_split);
-        Kern k = kerns[q.split][q.T - 1][slow];
-        if (smem > configured[q.split][q.T - 1][slow]) {
-            TN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured[q.split][q.T - 1][slow] = smem;
-        }
-        dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)ks);
-        k<<<grid, TC_THREADS, smem, st>>>(q);
-        TN_LAUNCH_CHECK();
-        return TN_OK;
-    };
-    auto simple = [](const TcFactor& f) { return (f.div == 1 || f.div >= (1 << 29)) && f.map_kind == TN_MAP_IDENTITY; };
-    if (!(simple(p.fa) && simple(p.fb) && simple(p.fc))) return launch(p, 1);   // class rows / fused feature maps
-    // fast kernel on the whole 16-row chunks, generic kernel on the ragged remainder
-    const int64_t main_rows = rows - rows % TC_KC;
-    TcParams q = p;
-    q.rows = main_rows;
-    int rc = launch(q, 0);
-    if (rc != TN_OK || main_rows == rows) return rc;
-    q = p;
-    q.rows = rows - main_rows;
-    auto shift = [&](TcFactor& f) { if (f.div == 1) f.ptr += main_rows * f.ld; };
-    shift(q.fa); shift(q.fb); shift(q.fc);
-    if (q.w) q.w += main_rows;
-    return launch(q, 1);
+    static const Kern kerns[2][2] = {{gram_tc_kernel<0, 1>, gram_tc_kernel<0, 2>}, {gram_tc_kernel<1, 1>, gram_tc_kernel<1, 2>}};
+    static size_t configured[2][2] = {};
+    Kern k = kerns[p.split][p.T - 1];
+    if (smem > configured[p.split][p.T - 1]) {
+        TN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[p.split][p.T - 1] = smem;
+    }
+    dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)ks);
+    k<<<grid, TC_THREADS, smem, st>>>(p);
+    TN_LAUNCH_CHECK();
+    TN_CUDA(cudaFreeAsync(Z, st));
+    return TN_OK;
 }
