@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the per-site Gauss-Newton / ALS sweep (BASELINE.json metric: GN site-updates/s).
 
-    python bench.py --gpus N --steps K --warmup W [--workload cfg5a] [--n ROWS_PER_GPU] [--gram-mode tf32x3]
+    python bench.py --gpus N --steps K --warmup W [--workload cfg5a] [--rows ROWS_PER_GPU] [--gram-mode tf32x3]
     python bench.py --impl reference ...        # the reference's algorithm on the host cores (oracle port)
 
 A step is one full sweep (left-to-right + right-to-left half) of ``accumulating_swipe`` over the
@@ -48,7 +48,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg5a", choices=sorted(WORKLOADS))
-    ap.add_argument("--n", type=int, default=None, help="rows per GPU (default: the workload's)")
+    ap.add_argument("--rows", dest="n", type=int, default=None, help="rows per GPU (default: the workload's)")
     ap.add_argument("--gram-mode", default="tf32x3", choices=["fp64", "tf32", "tf32x3"])
     ap.add_argument("--no-peaks", action="store_true", help="skip the cuBLAS TF32/FP64 peak measurement")
     ap.add_argument("--eps", type=float, default=1.0)

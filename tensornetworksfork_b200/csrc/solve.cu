@@ -13,51 +13,91 @@ namespace tn {
 constexpr int CH_NB = 64;
 
 // ---- diagonal block: factor (lower) and invert ------------------------------------------------
+// Latency work on one CTA.  Factorisation: warp 0 alone, left-looking, two rows per lane, __syncwarp only
+// (no block barriers in the 64-step dependency chain).  Inversion: all 8 warps, 4 lanes per column of
+// L^{-1}; lane l keeps the entries x[q], q = l (mod 4), of its column in registers, so a row step is a
+// 16-term dot product, two shuffles and a divide.
 __global__ void __launch_bounds__(256)
 potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t j, int nb, double* __restrict__ Linv, int* __restrict__ info) {
     extern __shared__ double dsm[];
     double (*a)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(dsm);
-    double (*li)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(dsm + CH_NB * (CH_NB + 1));
+    __shared__ int bad;
     if (*info != 0) return;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) bad = 0;
     for (int idx = tid; idx < CH_NB * CH_NB; idx += 256) {
         const int r = idx >> 6, c = idx & 63;
-        a[r][c] = (r < nb && c <= r) ? A[(j + r) * lda + j + c] : 0.0;
-        li[r][c] = 0.0;
+        a[r][c] = (r < nb && c <= r) ? A[(j + r) * lda + j + c] : ((r == c) ? 1.0 : 0.0);   // identity padding
     }
-    for (int c = 0; c < nb; ++c) {
-        __syncthreads();
-        const double d = a[c][c];
-        if (!(d > 0.0)) {  // also catches NaN
-            if (tid == 0) *info = (int)(j + c + 1);
-            return;
+    __syncthreads();
+    if (warp == 0) {
+        const int r0 = lane, r1 = lane + 32;
+        int fail = 0;
+        for (int c = 0; c < nb; ++c) {
+            // v[r] = a[r][c] - sum_{t<c} L[r][t] L[c][t]   for this lane's rows r >= c
+            double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
+            int t = 0;
+            for (; t + 1 < c; t += 2) {
+                const double l0 = a[c][t], l1 = a[c][t + 1];
+                s0 = fma(a[r0][t], l0, s0); t0 = fma(a[r0][t + 1], l1, t0);
+                s1 = fma(a[r1][t], l0, s1); t1 = fma(a[r1][t + 1], l1, t1);
+            }
+            if (t < c) {
+                const double l0 = a[c][t];
+                s0 = fma(a[r0][t], l0, s0);
+                s1 = fma(a[r1][t], l0, s1);
+            }
+            const double v0 = a[r0][c] - (s0 + t0), v1 = a[r1][c] - (s1 + t1);
+            const double d = __shfl_sync(0xffffffffu, (c < 32) ? v0 : v1, c & 31);
+            if (!(d > 0.0)) {   // also catches NaN; uniform across the warp
+                fail = c + 1;
+                break;
+            }
+            const double sd = sqrt(d);
+            __syncwarp();
+            if (r0 >= c) a[r0][c] = (r0 == c) ? sd : v0 / sd;
+            if (r1 >= c) a[r1][c] = (r1 == c) ? sd : v1 / sd;
+            __syncwarp();
         }
-        const double sd = sqrt(d);
-        __syncthreads();
-        for (int r = c + tid; r < nb; r += 256) a[r][c] = (r == c) ? sd : a[r][c] / sd;
-        __syncthreads();
-        const int rem = nb - c - 1;
-        for (int idx = tid; idx < rem * rem; idx += 256) {
-            const int rr = c + 1 + idx / rem, cc = c + 1 + idx % rem;
-            if (cc <= rr) a[rr][cc] = fma(-a[rr][c], a[cc][c], a[rr][cc]);
+        if (fail && lane == 0) {
+            bad = 1;
+            *info = (int)(j + fail);
         }
     }
     __syncthreads();
+    if (bad) return;
     for (int idx = tid; idx < nb * nb; idx += 256) {
         const int r = idx / nb, c = idx % nb;
         if (c <= r) A[(j + r) * lda + j + c] = a[r][c];
     }
-    if (tid < nb) {  // column tid of L^{-1} by forward substitution
-        const int t = tid;
-        li[t][t] = 1.0 / a[t][t];
-        for (int r = t + 1; r < nb; ++r) {
-            double s = 0.0;
-            for (int q = t; q < r; ++q) s = fma(a[r][q], li[q][t], s);
-            li[r][t] = -s / a[r][r];
+    // ---- inverse: column t of X = L^{-1}, 4 lanes per column
+    {
+        const int t = tid >> 2, l = tid & 3;
+        double x[16];          // x[m] = X[4m + l][t]
+#pragma unroll
+        for (int m = 0; m < 16; ++m) x[m] = 0.0;
+#pragma unroll
+        for (int m = 0; m < 16; ++m)
+            if (4 * m + l == t) x[m] = 1.0 / a[t][t];
+        for (int r = 1; r < CH_NB; ++r) {
+            double sdot = 0.0;
+#pragma unroll
+            for (int m = 0; m < 16; ++m) {
+                const int q = 4 * m + l;
+                if (q < r) sdot = fma(a[r][q], x[m], sdot);      // x[m] is zero for q < t
+            }
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+            if (r > t) {
+                const double xr = -sdot / a[r][r];
+#pragma unroll
+                for (int m = 0; m < 16; ++m)
+                    if (4 * m + l == r) x[m] = xr;
+            }
         }
+#pragma unroll
+        for (int m = 0; m < 16; ++m) Linv[(4 * m + l) * CH_NB + t] = x[m];
     }
-    __syncthreads();
-    for (int idx = tid; idx < CH_NB * CH_NB; idx += 256) Linv[idx] = li[idx >> 6][idx & 63];
 }
 
 // ---- panel: X = B * Linv^T for the rows below the diagonal block -------------------------------
@@ -318,6 +358,74 @@ trsv_bwd_update_kernel(const double* __restrict__ A, int64_t lda, int64_t j, int
     }
 }
 
+// Both substitutions in one launch for small systems (P <= TS_MAXP): one CTA, rhs in shared memory,
+// blocks of 64 processed in order; the 64x64 block solves use the inverted diagonal blocks.
+constexpr int TS_MAXP = 8192;
+__global__ void __launch_bounds__(1024)
+trsv_small_kernel(const double* __restrict__ A, int64_t lda, int P, double* __restrict__ rhs, const double* __restrict__ Linv_all,
+                  const int* __restrict__ info) {
+    extern __shared__ double x[];      // [P] right-hand side / solution, then [64] block result
+    double* yb = x + ((P + 63) / 64) * 64;
+    if (*info != 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nblk = (P + CH_NB - 1) / CH_NB;
+    for (int i = tid; i < nblk * CH_NB; i += 1024) x[i] = (i < P) ? rhs[i] : 0.0;
+    __syncthreads();
+    // forward: L y = rhs
+    for (int b = 0; b < nblk; ++b) {
+        const int j = b * CH_NB;
+        const int nb = min(CH_NB, P - j);
+        const double* Li = Linv_all + (size_t)b * CH_NB * CH_NB;
+        // y_b = Linv_b * x_b : 64 rows, 16 threads per row
+        {
+            const int r = tid >> 4, l = tid & 15;
+            double sdot = 0.0;
+            for (int q = l; q <= r; q += 16) sdot = fma(Li[r * CH_NB + q], x[j + q], sdot);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 8);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+            if (l == 0) yb[r] = sdot;
+        }
+        __syncthreads();
+        if (tid < CH_NB) x[j + tid] = (tid < nb) ? yb[tid] : 0.0;
+        // x[i] -= sum_t L[i][j+t] y[t], i > block : one warp per row
+        for (int i = j + CH_NB + warp; i < P; i += 32) {
+            const double* row = A + (int64_t)i * lda + j;
+            double sdot = row[lane] * yb[lane] + row[lane + 32] * yb[lane + 32];
+            for (int o = 16; o > 0; o >>= 1) sdot += __shfl_xor_sync(0xffffffffu, sdot, o);
+            if (lane == 0) x[i] -= sdot;
+        }
+        __syncthreads();
+    }
+    // backward: L^T z = y
+    for (int b = nblk - 1; b >= 0; --b) {
+        const int j = b * CH_NB;
+        const int nb = min(CH_NB, P - j);
+        const double* Li = Linv_all + (size_t)b * CH_NB * CH_NB;
+        {
+            const int r = tid >> 4, l = tid & 15;
+            double sdot = 0.0;
+            for (int q = r + l; q < CH_NB; q += 16) sdot = fma(Li[q * CH_NB + r], x[j + q], sdot);   // Linv^T
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 8);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+            if (l == 0) yb[r] = sdot;
+        }
+        __syncthreads();
+        if (tid < CH_NB) x[j + tid] = (tid < nb) ? yb[tid] : 0.0;
+        // x[c] -= sum_t L[j+t][c] z[t], c < j : one thread per column (coalesced rows)
+        for (int c = tid; c < j; c += 1024) {
+            double sdot = 0.0;
+            for (int t = 0; t < nb; ++t) sdot = fma(A[(int64_t)(j + t) * lda + c], yb[t], sdot);
+            x[c] -= sdot;
+        }
+        __syncthreads();
+    }
+    for (int i = tid; i < P; i += 1024) rhs[i] = x[i];
+}
+
 }  // namespace tn
 
 extern "C" int64_t tn_cholesky_work_elems(int64_t P) {
@@ -328,7 +436,7 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
     using namespace tn;
     TN_CHECK_ARG(A && work && info && P >= 1 && lda >= P, "tn_cholesky_solve: bad arguments");
     cudaStream_t st = as_stream(stream);
-    constexpr size_t kBlkSmem = 2 * CH_NB * (CH_NB + 1) * sizeof(double);
+    constexpr size_t kBlkSmem = 2 * CH_NB * (CH_NB + 1) * sizeof(double);   // trsm needs two blocks, potrf one
     constexpr size_t kDmmaSmem = (size_t)2 * DS_STAGES * DS_BT * DS_LD * sizeof(double);
     static bool configured = false;
     if (!configured) {
@@ -371,7 +479,16 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
         }
         TN_LAUNCH_CHECK();
     }
-    if (rhs) {
+    if (rhs && P <= TS_MAXP) {
+        const size_t smem = ((size_t)ceil_div64(P, 64) * 64 + 64) * sizeof(double);
+        static size_t ts_configured = 0;
+        if (smem > ts_configured) {
+            TN_CUDA(cudaFuncSetAttribute(trsv_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ts_configured = smem;
+        }
+        trsv_small_kernel<<<1, 1024, smem, st>>>(A, lda, (int)P, rhs, work, info);
+        TN_LAUNCH_CHECK();
+    } else if (rhs) {
         const int sms = sm_count();
         for (int64_t j = 0; j < P; j += CH_NB) {
             const int nb = (int)((P - j < CH_NB) ? P - j : CH_NB);
