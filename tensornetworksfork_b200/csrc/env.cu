@@ -6,94 +6,122 @@
 //
 // Layout: environments are sample-major [rows, r] fp64, so a tile of consecutive rows is one
 // contiguous byte range; the site input is read once per sample and mapped in registers.
-// One CTA owns ENV_TR rows; the core is streamed through shared memory in (a, p) slabs that
+// One CTA owns 64..128 rows; the core is streamed through shared memory in feature slabs that
 // every CTA re-reads from L2 (the core is at most a few hundred KB).
 #include "common.cuh"
 
 namespace tn {
 
-constexpr int ENV_TR = 64;       // rows per CTA
-constexpr int ENV_TC = 64;       // output columns per pass
-constexpr int ENV_THREADS = 256; // 16 (row groups of 4) x 16 (column lanes)
+constexpr int ENV_THREADS = 256;
+constexpr int ENV_RT = 4;        // rows per thread
 
+// TXN column lanes x (256/TXN) row groups; each thread owns ENV_RT rows x CN columns (tx + TXN*j).
+// The contraction is ordered  out = sum_p phi_p * (sum_a env_a * core[a,p,:])  so the inner loop is pure FMA.
+template <int TXN, int CN>
 __global__ void __launch_bounds__(ENV_THREADS)
 env_kernel(const double* __restrict__ env_in, int64_t env_ld, int env_div, const double* __restrict__ x, int64_t x_ld,
            int map_kind, int f, int cdiv, const double* __restrict__ core, double* __restrict__ out,
            int64_t out_ld, const double* __restrict__ dot, int64_t dot_ld, int dot_div,
-           double* __restrict__ yhat, int64_t rows, int r_in, int r_out, int a_chunk) {
+           double* __restrict__ yhat, int64_t rows, int r_in, int r_out, int p_chunk) {
+    constexpr int TR = (ENV_THREADS / TXN) * ENV_RT;   // rows per CTA
+    constexpr int TC = TXN * CN;                        // columns per pass
     extern __shared__ double sm[];
     const int in_st = r_in | 1;
     const int phi_st = f | 1;
     double* s_in = sm;
-    double* s_phi = s_in + ENV_TR * in_st;
-    double* s_g = s_phi + ENV_TR * phi_st;
+    double* s_phi = s_in + TR * in_st;
+    double* s_g = s_phi + TR * phi_st;                  // [p_chunk][r_in][TC]
 
     const int tid = threadIdx.x;
-    const int tx = tid & 15;
-    const int ty = tid >> 4;
-    const int64_t row0 = (int64_t)blockIdx.x * ENV_TR;
+    const int tx = tid % TXN;
+    const int ty = tid / TXN;
+    const int64_t row0 = (int64_t)blockIdx.x * TR;
 
-    for (int idx = tid; idx < ENV_TR * r_in; idx += ENV_THREADS) {
+    for (int idx = tid; idx < TR * r_in; idx += ENV_THREADS) {
         const int r = idx / r_in, a = idx - r * r_in;
         const int64_t row = row0 + r;
         double v = 0.0;
-        if (row < rows) v = env_in ? env_in[(row / env_div) * env_ld + a] : 1.0;
+        if (row < rows) v = env_in ? env_in[(env_div == 1 ? row : row / env_div) * env_ld + a] : 1.0;
         s_in[r * in_st + a] = v;
     }
-    for (int idx = tid; idx < ENV_TR * f; idx += ENV_THREADS) {
-        const int r = idx / f, p = idx - r * f;
-        const int64_t row = row0 + r;
-        double v = 0.0;
-        if (row < rows) v = map_eval(map_kind, x + (row / cdiv) * x_ld, p);
-        s_phi[r * phi_st + p] = v;
+    if (map_kind == TN_MAP_SINCOS) {
+        for (int r = tid; r < TR; r += ENV_THREADS) {
+            const int64_t row = row0 + r;
+            double c = 0.0, sn = 0.0;
+            if (row < rows) sincos((0.5 * 3.14159265358979323846) * x[(cdiv == 1 ? row : row / cdiv) * x_ld], &sn, &c);
+            s_phi[r * phi_st] = c;
+            s_phi[r * phi_st + 1] = sn;
+        }
+    } else {
+        for (int idx = tid; idx < TR * f; idx += ENV_THREADS) {
+            const int r = idx / f, p = idx - r * f;
+            const int64_t row = row0 + r;
+            double v = 0.0;
+            if (row < rows) v = map_eval(map_kind, x + (cdiv == 1 ? row : row / cdiv) * x_ld, p);
+            s_phi[r * phi_st + p] = v;
+        }
     }
 
-    double ydot[4] = {0.0, 0.0, 0.0, 0.0};
-    for (int c0 = 0; c0 < r_out; c0 += ENV_TC) {
-        double acc[4][4];
+    double ydot[ENV_RT];
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < ENV_RT; ++i) ydot[i] = 0.0;
+    for (int c0 = 0; c0 < r_out; c0 += TC) {
+        double acc[ENV_RT][CN];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        for (int i = 0; i < ENV_RT; ++i)
+#pragma unroll
+            for (int j = 0; j < CN; ++j) acc[i][j] = 0.0;
 
-        for (int a0 = 0; a0 < r_in; a0 += a_chunk) {
-            const int ac = min(a_chunk, r_in - a0);
+        for (int p0 = 0; p0 < f; p0 += p_chunk) {
+            const int pc = min(p_chunk, f - p0);
             __syncthreads();
-            for (int idx = tid; idx < ac * f * ENV_TC; idx += ENV_THREADS) {
-                const int col = idx & (ENV_TC - 1);
-                const int ap = idx >> 6;  // (a, p) flattened, ENV_TC == 64
+            // stage core[:, p0:p0+pc, c0:c0+TC] as [p][a][col]
+            for (int idx = tid; idx < pc * r_in * TC; idx += ENV_THREADS) {
+                const int col = idx % TC;
+                const int pa = idx / TC;
+                const int pp = pa / r_in, a = pa - pp * r_in;
                 const int b = c0 + col;
-                s_g[idx] = (b < r_out) ? core[((int64_t)a0 * f + ap) * r_out + b] : 0.0;
+                s_g[idx] = (b < r_out) ? core[((int64_t)a * f + p0 + pp) * r_out + b] : 0.0;
             }
             __syncthreads();
-            for (int a = 0; a < ac; ++a) {
-                double ein[4];
+            for (int pp = 0; pp < pc; ++pp) {
+                double t[ENV_RT][CN];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) ein[i] = s_in[(ty * 4 + i) * in_st + a0 + a];
-                const double* gp = s_g + (a * f) * ENV_TC + tx;
-                for (int p = 0; p < f; ++p) {
-                    double z[4], g[4];
+                for (int i = 0; i < ENV_RT; ++i)
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) z[i] = ein[i] * s_phi[(ty * 4 + i) * phi_st + p];
+                    for (int j = 0; j < CN; ++j) t[i][j] = 0.0;
+                const double* gp = s_g + (size_t)pp * r_in * TC + tx;
+                const double* ip = s_in + (ty * ENV_RT) * in_st;
+#pragma unroll 2
+                for (int a = 0; a < r_in; ++a) {
+                    double e[ENV_RT], g[CN];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) g[j] = gp[p * ENV_TC + 16 * j];
+                    for (int i = 0; i < ENV_RT; ++i) e[i] = ip[i * in_st + a];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
+                    for (int j = 0; j < CN; ++j) g[j] = gp[a * TC + TXN * j];
 #pragma unroll
-                        for (int j = 0; j < 4; ++j) acc[i][j] = fma(z[i], g[j], acc[i][j]);
+                    for (int i = 0; i < ENV_RT; ++i)
+#pragma unroll
+                        for (int j = 0; j < CN; ++j) t[i][j] = fma(e[i], g[j], t[i][j]);
+                }
+#pragma unroll
+                for (int i = 0; i < ENV_RT; ++i) {
+                    const double ph = s_phi[(ty * ENV_RT + i) * phi_st + p0 + pp];
+#pragma unroll
+                    for (int j = 0; j < CN; ++j) acc[i][j] = fma(ph, t[i][j], acc[i][j]);
                 }
             }
         }
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int64_t row = row0 + ty * 4 + i;
+        for (int i = 0; i < ENV_RT; ++i) {
+            const int64_t row = row0 + ty * ENV_RT + i;
             if (row >= rows) continue;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int b = c0 + tx + 16 * j;
+            for (int j = 0; j < CN; ++j) {
+                const int b = c0 + tx + TXN * j;
                 if (b >= r_out) continue;
                 if (dot)
-                    ydot[i] = fma(acc[i][j], dot[(row / dot_div) * dot_ld + b], ydot[i]);
+                    ydot[i] = fma(acc[i][j], dot[(dot_div == 1 ? row : row / dot_div) * dot_ld + b], ydot[i]);
                 else
                     out[row * out_ld + b] = acc[i][j];
             }
@@ -101,13 +129,11 @@ env_kernel(const double* __restrict__ env_in, int64_t env_ld, int env_div, const
     }
     if (dot) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
+        for (int i = 0; i < ENV_RT; ++i) {
             double v = ydot[i];
-            v += __shfl_xor_sync(0xffffffffu, v, 8);
-            v += __shfl_xor_sync(0xffffffffu, v, 4);
-            v += __shfl_xor_sync(0xffffffffu, v, 2);
-            v += __shfl_xor_sync(0xffffffffu, v, 1);
-            const int64_t row = row0 + ty * 4 + i;
+#pragma unroll
+            for (int o = TXN / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+            const int64_t row = row0 + ty * ENV_RT + i;
             if (tx == 0 && row < rows) yhat[row] = v;
         }
     }
@@ -155,21 +181,29 @@ extern "C" int tn_env_update(const double* env_in, int64_t env_ld, int env_div, 
     TN_CHECK_ARG(map_kind >= 0 && map_kind <= 2, "tn_env_update: unknown map_kind %d", map_kind);
     TN_CHECK_ARG(map_kind != TN_MAP_SINCOS || f == 2, "tn_env_update: sin-cos map has f == 2");
     if (rows == 0) return TN_OK;
-    int a_chunk = 8192 / (f * ENV_TC);
-    if (a_chunk < 1) a_chunk = 1;
-    if (a_chunk > r_in) a_chunk = r_in;
-    const size_t smem = ((size_t)ENV_TR * (r_in | 1) + (size_t)ENV_TR * (f | 1) + (size_t)a_chunk * f * ENV_TC) * sizeof(double);
+    // column tiling: 8 lanes x ceil(r_out/8) columns per thread for narrow outputs (no padded work), 16 x 4 for wide ones
+    int TXN = 8, CN = (r_out + 7) / 8;
+    if (CN > 5) { TXN = 16; CN = 4; }
+    const int TR = (ENV_THREADS / TXN) * ENV_RT, TC = TXN * CN;
+    int p_chunk = (int)(48 * 1024 / sizeof(double)) / (r_in * TC);     // <= 48 KB of core slab per stage
+    if (p_chunk < 1) p_chunk = 1;
+    if (p_chunk > f) p_chunk = f;
+    const size_t smem = ((size_t)TR * (r_in | 1) + (size_t)TR * (f | 1) + (size_t)p_chunk * r_in * TC) * sizeof(double);
     TN_CHECK_ARG(smem <= 227 * 1024, "tn_env_update: r_in=%d f=%d needs %zu B of shared memory", r_in, f, smem);
-    static size_t configured = 0;
-    if (smem > configured) {
-        TN_CUDA(cudaFuncSetAttribute(env_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
+    using Kern = void (*)(const double*, int64_t, int, const double*, int64_t, int, int, int, const double*, double*, int64_t,
+                          const double*, int64_t, int, double*, int64_t, int, int, int);
+    static const Kern kerns[6] = {env_kernel<8, 1>, env_kernel<8, 2>, env_kernel<8, 3>, env_kernel<8, 4>, env_kernel<8, 5>, env_kernel<16, 4>};
+    static size_t configured[6] = {0, 0, 0, 0, 0, 0};
+    const int ki = (TXN == 16) ? 5 : CN - 1;
+    if (smem > configured[ki]) {
+        TN_CUDA(cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[ki] = smem;
     }
-    const int64_t grid = ceil_div64(rows, ENV_TR);
+    const int64_t grid = ceil_div64(rows, TR);
     TN_CHECK_ARG(grid <= 0x7fffffff, "tn_env_update: too many rows");
-    env_kernel<<<(unsigned)grid, ENV_THREADS, smem, as_stream(stream)>>>(env_in, env_ld, env_div < 1 ? 1 : env_div, x, x_ld, map_kind, f, cdiv, core,
-                                                                         out, out_ld, dot, dot_ld, dot_div, yhat, rows,
-                                                                         r_in, r_out, a_chunk);
+    kerns[ki]<<<(unsigned)grid, ENV_THREADS, smem, as_stream(stream)>>>(env_in, env_ld, env_div < 1 ? 1 : env_div, x, x_ld, map_kind, f,
+                                                                       cdiv, core, out, out_ld, dot, dot_ld, dot_div, yhat, rows,
+                                                                       r_in, r_out, p_chunk);
     TN_LAUNCH_CHECK();
     return TN_OK;
 }

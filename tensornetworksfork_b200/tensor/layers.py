@@ -222,3 +222,108 @@ class CPDLayer(TensorNetworkLayer):
         super().__init__(CPDNetwork(x_nodes, factors, output_labels=tuple(labels), sample_dim="s"))
         self.nodes = factors
         self.labels = tuple(labels)
+
+
+class TensorTrainDMRGInfiLayer(TensorNetworkLayer):
+    """Two-site growth of a tensor train ("infinite DMRG" style; reference layers.py:480-680).
+
+    Starts as a 2-core chain AL1-AR1.  ``grow_middle`` inserts a trainable 2-site block
+    ``D[r_l, pL, pR, r_r]`` fed by two inputs between the two middle cores (only the block is trained by
+    the next sweep); ``split_node`` splits it back into two cores by a truncated SVD on the host.
+    """
+
+    def __init__(self, bond_dim, input_features, output_shape=tuple(), ring=False, squeeze=True, constrict_bond=True):
+        self.num_carriages = 2
+        self.bond_dim = bond_dim
+        self.input_features = input_features
+        self.output_shape = output_shape if isinstance(output_shape, tuple) else (output_shape,)
+        self.ring = ring
+        # draw order (inputs first, then the cores) follows the reference for seed parity
+        self.x_nodes = [TensorNode((1, input_features), ["s", "pL1"], name="XL1"),
+                        TensorNode((1, input_features), ["s", "pR1"], name="XR1")]
+        bond = min(bond_dim, input_features) if constrict_bond else bond_dim
+        self.ranks = [(1, bond), (bond, 1)]
+        self.labels = ["s", "c1"]
+        n1 = TensorNode((self.output_shape[0], input_features, bond), ["c1", "pL1", "r1"], r="r1", name="AL1")
+        n1.connect(self.x_nodes[0], "pL1", priority=2)
+        n2 = TensorNode((bond, input_features), ["r1", "pR1"], l="r1", name="AR1")
+        n2.connect(self.x_nodes[1], "pR1", priority=2)
+        n1.connect(n2, "r1", priority=0)
+        self.nodes = [n1, n2]
+        if squeeze:
+            for n in self.nodes:
+                n.squeeze(self.labels)
+        super().__init__(TensorNetwork(self.x_nodes, self.nodes, output_labels=self.labels))
+        self.nodes = [n1, n2]
+
+    def _rebuild(self, train_nodes, device):
+        self.tensor_network = TensorNetwork(self.x_nodes, self.nodes, train_nodes=train_nodes, output_labels=self.labels)
+        self.tensor_network.to(device)
+
+    def grow_middle(self):
+        """Insert the 2-site block between the two middle cores (reference layers.py:556-614)."""
+        n = self.num_carriages
+        pl, pr = f"pL{n}", f"pR{n}"
+        x1 = TensorNode((1, self.input_features), ["s", pl], name=f"XL{n}")
+        x2 = TensorNode((1, self.input_features), ["s", pr], name=f"XR{n}")
+        left, right = self.nodes[n // 2 - 1], self.nodes[n // 2]
+        old = left.right_labels[0]
+        left.connections.pop(old, None)
+        right.connections.pop(right.left_labels[0], None)
+        ll, rl = old + "L", right.left_labels[0] + "R"
+        left.right_labels = [ll]
+        left.dim_labels[-1] = ll
+        right.left_labels = [rl]
+        right.dim_labels[0] = rl
+        b1, b2 = left.dim_size(ll), right.dim_size(rl)
+        block = TensorNode((b1, 1, self.input_features, self.input_features, b2), [ll, f"c{n}", pl, pr, rl], l=ll, r=rl,
+                           name=f"D{n}")
+        x1.connect(block, pl)
+        x2.connect(block, pr)
+        self.x_nodes.insert(n // 2, x2)
+        self.x_nodes.insert(n // 2, x1)
+        block.connect(left, ll)
+        block.connect(right, rl)
+        block.squeeze()
+        self.nodes.insert(n // 2, block)
+        self.num_carriages += 1
+        self._rebuild([block], left.tensor.device)
+
+    def split_node(self, left_labels, right_labels, rank, err=None, is_last=False):
+        """Split the block by a truncated SVD into two cores (host-side, reference layers.py:616-680).
+        Returns the discarded tail of the singular values."""
+        import numpy as np
+        n = self.num_carriages
+        node = self.nodes[n // 2]
+        cur_l, cur_r = node.left_labels[0], node.right_labels[0]
+        node.permute_first(*left_labels)
+        node.permute_last(*right_labels)
+        ldims = [node.dim_size(l) for l in left_labels]
+        rdims = [node.dim_size(l) for l in right_labels]
+        u, sv, v = torch.linalg.svd(node.tensor.reshape(int(np.prod(ldims)), int(np.prod(rdims))), full_matrices=False)
+        if is_last:
+            v = sv.diag() @ v
+        tail = torch.flip(sv, dims=[0]).cumsum(0)
+        if err is not None:
+            rank = max(min(rank, int((tail > err).sum())), 1)
+        split_err = tail[-rank]
+        u = u[:, :rank].reshape(ldims + [rank])
+        v = v[:rank].reshape([rank] + rdims)
+        bond = f"r{n}"
+        a = TensorNode(u, list(left_labels) + [bond], r=bond, l=cur_l, name=f"AL{n}")
+        b = TensorNode(v, [bond] + list(right_labels), r=cur_r, l=bond, name=f"AR{n}")
+        if cur_l in node.connections:
+            node.connections[cur_l].connect(a, cur_l)
+        if cur_r in node.connections:
+            node.connections[cur_r].connect(b, cur_r)
+        a.connect(b, bond)
+        xa, xb = self.x_nodes[n // 2], self.x_nodes[n // 2 + 1]
+        xa.reset_connections()
+        xb.reset_connections()
+        xa.connect(a, xa.dim_labels[1])
+        xb.connect(b, xb.dim_labels[1])
+        pos = self.nodes.index(node)
+        self.nodes[pos:pos + 1] = [a, b]
+        self.num_carriages += 1
+        self._rebuild([], node.tensor.device)
+        return split_err

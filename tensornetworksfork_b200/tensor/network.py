@@ -192,13 +192,16 @@ class TensorNetwork:
             if len(cls) > 1:
                 raise NotImplementedError(f"{node.name}: more than one output leg")
             s.cls = cls[0] if cls else None
-            phys = [(lab, other) for lab, other in node.connections.items() if other in self.input_nodes]
-            if len(phys) != 1:
-                raise NotImplementedError(f"{node.name}: expected exactly one input node, found {len(phys)} "
-                                          "(this engine covers plain tensor-train chains; see DESIGN.md)")
-            s.phys = phys[0][0]
-            s.input_index = self.input_nodes.index(phys[0][1])
-            known = {s.left, s.right, s.cls, s.phys} - {None}
+            phys = [(lab, other) for lab in node.dim_labels for l2, other in node.connections.items()
+                    if l2 == lab and any(other is n for n in self.input_nodes)]
+            if len(phys) not in (1, 2):
+                raise NotImplementedError(f"{node.name}: expected one input node (or two for a 2-site block), found {len(phys)} "
+                                          "(this engine covers tensor-train chains; see DESIGN.md)")
+            # a 2-site (DMRG) block carries two physical legs; its site input is the Kronecker product of both
+            s.phys = phys[0][0] if len(phys) == 1 else tuple(lab for lab, _ in phys)
+            idxs = [next(i for i, n in enumerate(self.input_nodes) if n is other) for _, other in phys]
+            s.input_index = idxs[0] if len(phys) == 1 else tuple(idxs)
+            known = ({s.left, s.right, s.cls} | set(lab for lab, _ in phys)) - {None}
             extra = [l for l in node.dim_labels if l not in known]
             if extra:
                 raise NotImplementedError(f"{node.name}: unsupported legs {extra}")
@@ -221,19 +224,34 @@ class TensorNetwork:
         """Core k as a (r_l, c, f, r_r) tensor (a view when the label order already is canonical)."""
         s = self._plan()[k]
         node = s.node
-        order = [l for l in (s.left, s.cls, s.phys, s.right) if l is not None and l in node.dim_labels]
+        order = self._order(s)
         t = node.tensor.permute(*[node.dim_labels.index(l) for l in order])
         rl = node.dim_size(s.left) if s.left in node.dim_labels else 1
         c = node.dim_size(s.cls) if s.cls in node.dim_labels else 1
-        f = node.dim_size(s.phys)
+        f = self._phys_size(s)
         rr = node.dim_size(s.right) if s.right in node.dim_labels else 1
         return t.reshape(rl, c, f, rr)
+
+    @staticmethod
+    def _phys_labels(s):
+        return list(s.phys) if isinstance(s.phys, tuple) else [s.phys]
+
+    def _phys_size(self, s):
+        f = 1
+        for lab in self._phys_labels(s):
+            f *= s.node.dim_size(lab)
+        return f
+
+    def _order(self, s):
+        """Canonical leg order (left, class, physical..., right) restricted to the legs the node has."""
+        cand = [s.left, s.cls] + self._phys_labels(s) + [s.right]
+        return [l for l in cand if l is not None and l in s.node.dim_labels]
 
     def _from_canon(self, k, t4):
         """(r_l, c, f, r_r) tensor -> tensor in the node's own label order and shape."""
         s = self._plan()[k]
         node = s.node
-        order = [l for l in (s.left, s.cls, s.phys, s.right) if l is not None and l in node.dim_labels]
+        order = self._order(s)
         t = t4.reshape([node.dim_size(l) for l in order])
         return t.permute(*[order.index(l) for l in node.dim_labels]).contiguous()
 
@@ -245,27 +263,33 @@ class TensorNetwork:
         if isinstance(x, MappedInput):
             X = x.X
             for k, s in enumerate(sites):
+                if isinstance(s.phys, tuple):
+                    raise NotImplementedError("2-site blocks take explicit inputs, not a fused feature map")
                 if s.node.dim_size(s.phys) != x.f:
                     raise ValueError(f"site {k}: core has f={s.node.dim_size(s.phys)}, feature map gives {x.f}")
                 facs.append(Factor(X, m=x.f, map_kind=x.map_kind, col=s.input_index))
             return facs, X.shape[0], X.device
-        if isinstance(x, (list, tuple)):
-            for k, s in enumerate(sites):
-                t = x[s.input_index]
-                if t.dim() != 2 or t.stride(1) != 1:
-                    t = t.reshape(t.shape[0], -1).contiguous()
+
+        def tensor_of(j):
+            t = x[j] if isinstance(x, (list, tuple)) else x
+            if t.dim() != 2 or t.stride(1) != 1:
+                t = t.reshape(t.shape[0], -1).contiguous()
+            return t
+
+        for k, s in enumerate(sites):
+            if isinstance(s.phys, tuple):
+                ta, tb = tensor_of(s.input_index[0]), tensor_of(s.input_index[1])
+                fa, fb = (s.node.dim_size(l) for l in s.phys)
+                if ta.shape[1] != fa or tb.shape[1] != fb:
+                    raise ValueError(f"site {k}: inputs have {ta.shape[1]}x{tb.shape[1]} features, block expects {fa}x{fb}")
+                t = (ta[:, :, None] * tb[:, None, :]).reshape(ta.shape[0], fa * fb).contiguous()   # phi_L (x) phi_R per sample
+            else:
+                t = tensor_of(s.input_index)
                 if t.shape[1] != s.node.dim_size(s.phys):
                     raise ValueError(f"site {k}: input has {t.shape[1]} features, core expects {s.node.dim_size(s.phys)}")
-                facs.append(Factor(t, m=t.shape[1]))
-            return facs, x[0].shape[0], x[0].device
-        t = x
-        if t.dim() != 2 or t.stride(1) != 1:
-            t = t.reshape(t.shape[0], -1).contiguous()
-        for k, s in enumerate(sites):
-            if t.shape[1] != s.node.dim_size(s.phys):
-                raise ValueError(f"site {k}: input has {t.shape[1]} features, core expects {s.node.dim_size(s.phys)}")
             facs.append(Factor(t, m=t.shape[1]))
-        return facs, t.shape[0], t.device
+        t0 = tensor_of(0)
+        return facs, t0.shape[0], t0.device
 
     @staticmethod
     def _key_of(x):
@@ -575,7 +599,7 @@ class TensorNetwork:
         """(sizes of the node's legs in canonical order, permutation canonical -> node label order)."""
         s = self._plan()[k]
         node = s.node
-        order = [l for l in (s.left, s.cls, s.phys, s.right) if l is not None and l in node.dim_labels]
+        order = self._order(s)
         return [node.dim_size(l) for l in order], [order.index(l) for l in node.dim_labels]
 
     def solve_system(self, node, A, b, method="exact", eps=0.0):

@@ -1,0 +1,47 @@
+"""Shared body of the growing 2-site (DMRG-style) parity test."""
+import os
+
+import numpy as np
+import torch
+
+import golden_util as gu
+import tensornetworksfork_b200 as tnb
+
+
+def run(device, compare_cores):
+    z = np.load(os.path.join(gu.GOLDEN_DIR, "dmrg_growing.npz"))
+    X = torch.tensor(z["x"], device=device)
+    y = torch.tensor(z["y"], device=device)
+    torch.manual_seed(11)
+    layer = tnb.TensorTrainDMRGInfiLayer(4, 4, output_shape=1, constrict_bond=True)
+    layer.to(device)
+    losses = []
+    stage = 0
+
+    def check(tag):
+        pred = layer.tensor_network.forward(X, to_tensor=True).cpu().numpy()
+        ref = z[f"s{stage}_{tag}_pred"]
+        assert gu.relerr(pred.reshape(ref.shape), ref) < 1e-7, (stage, tag)
+        if compare_cores:
+            for i, n in enumerate(layer.nodes):
+                assert gu.relerr(n.tensor.cpu().numpy(), z[f"s{stage}_{tag}_core{i}"]) < 1e-7, (stage, tag, i)
+
+    check("init")
+    kw = dict(batch_size=-1, lr=1.0, orthonormalize=False, method="ridge_cholesky", num_swipes=5, skip_second=False, direction="l2r",
+              loss_callback=lambda NS, n, l: losses.append(l))
+    assert layer.tensor_network.accumulating_swipe(X, y, tnb.SquareBregFunction(), eps=1.0, **kw)
+    check("swept")
+    for carts in range(3, 6):
+        stage += 1
+        layer.grow_middle()
+        check("grown")
+        assert layer.tensor_network.accumulating_swipe(X, y, tnb.SquareBregFunction(), eps=0.05, **kw)
+        check("swept")
+        node = layer.nodes[layer.num_carriages // 2]
+        err = layer.split_node(node.dim_labels[:2], node.dim_labels[-2:], 4, err=1e-6, is_last=carts == 5)
+        assert abs(float(err) - float(z[f"s{stage}_split_err"])) <= 1e-7 * max(1.0, abs(float(z[f"s{stage}_split_err"])))
+        check("split")
+    ref_losses = z["losses"]
+    assert len(losses) == len(ref_losses)          # one update per block sweep: the turn-around skip
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= 1e-7 * max(1.0, abs(b))

@@ -74,3 +74,23 @@ if what in ("chol",):
         if A0 is not None:
             res = float((A0[:, :P] @ r - rhs).norm() / rhs.norm())
         print(json.dumps({"probe": "chol", "P": P, "ms": ms, "tflops": P ** 3 / 3 / ms / 1e9, "info": int(info.item()), "residual": res}))
+if what in ("env",):
+    for name, S, rin, f, rout, mk in (("cfg3", 515345, 24, 2, 24, ops.MAP_SINCOS), ("cfg3_ident", 515345, 24, 2, 24, ops.MAP_IDENTITY),
+                                      ("cfg4_class", 60000 * 9, 38, 2, 38, ops.MAP_SINCOS), ("cfg5a", 1000000, 38, 29, 38, ops.MAP_IDENTITY),
+                                      ("cfg5b", 1000000, 38, 6, 38, ops.MAP_POLY)):
+        g = torch.Generator(device=DEV).manual_seed(1)
+        env = torch.randn((S, rin), device=DEV, generator=g)
+        X = torch.rand((S, 32 if mk != ops.MAP_IDENTITY else f), device=DEV, generator=g)
+        core = torch.randn((rin, f, rout), device=DEV, generator=g)
+        dot = torch.randn((S, rout), device=DEV, generator=g)
+        fx = Factor(X, m=f, map_kind=mk, col=3 if mk != ops.MAP_IDENTITY else 0)
+        out = torch.empty((S, rout), device=DEV)
+        yh = torch.empty((S,), device=DEV)
+        ms_env = timeit(lambda: ops.env_update(env, fx, core, S, out=out), n=5)
+        ms_pred = timeit(lambda: ops.predict(env, fx, core, dot, S, out=yh), n=5)
+        xb = 8 * (f if mk == ops.MAP_IDENTITY else 1)
+        by_env = S * (8.0 * (rin + rout) + xb)
+        by_pred = S * (8.0 * (rin + rout) + xb + 8)
+        fl = 2.0 * S * rin * f * rout
+        print(json.dumps({"probe": "env", "site": name, "rows": S, "ms_env": ms_env, "GBs_env": by_env / ms_env / 1e6, "ms_predict": ms_pred,
+                          "GBs_predict": by_pred / ms_pred / 1e6, "tflops_env": fl / ms_env / 1e9}))
