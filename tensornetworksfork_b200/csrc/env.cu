@@ -18,7 +18,7 @@ constexpr int ENV_RT = 4;        // rows per thread
 // TXN column lanes x (256/TXN) row groups; each thread owns ENV_RT rows x CN columns (tx + TXN*j).
 // The contraction is ordered  out = sum_p phi_p * (sum_a env_a * core[a,p,:])  so the inner loop is pure FMA.
 template <int TXN, int CN>
-__global__ void __launch_bounds__(ENV_THREADS)
+__global__ void __launch_bounds__(ENV_THREADS, (CN <= 3) ? 3 : 2)
 env_kernel(const double* __restrict__ env_in, int64_t env_ld, int env_div, const double* __restrict__ x, int64_t x_ld,
            int map_kind, int f, int cdiv, const double* __restrict__ core, double* __restrict__ out,
            int64_t out_ld, const double* __restrict__ dot, int64_t dot_ld, int dot_div,
