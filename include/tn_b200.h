@@ -89,6 +89,16 @@ int tn_rhs_ksplit(int64_t rows, int ma, int mb, int mc);
 int tn_rhs_kr3(const tn_factor *fa, const tn_factor *fb, const tn_factor *fc, const double *w, int64_t rows,
                double *b, double *work, int ksplit, int accumulate, void *stream);
 
+/* Gram / right-hand side of a Jacobian WITHOUT Kronecker structure: column i of J is
+ * f1[t1[i]] * f2[t2[i]] * f3[t3[i]] (device int tables of length P).  Used for the cum-sum train, whose
+ * per-feature coupling J[s,a,p,b] = x[p] cumL[a,p] R[b,p] (reference tensor/layers.py:408-477, SURVEY.md
+ * Appendix C) is not a Kronecker product.  rhs_only == 0: out (P x P, dense, row stride P) (+)= J^T diag(w) J;
+ * rhs_only != 0: out (P) (+)= J^T w.  fp64.                                                            */
+int tn_generic_ksplit(int64_t rows, int P, int rhs_only);
+int tn_gram_generic(const tn_factor *f1, const tn_factor *f2, const tn_factor *f3, const int *t1, const int *t2,
+                    const int *t3, int P, const double *w, int64_t rows, double *out, int rhs_only, double *work,
+                    int ksplit, int accumulate, void *stream);
+
 /* ---- local solve: TensorNetwork.solve_system (tensor/network.py:293-327).
  * sigma_out[0] = mean_i |A_ii| computed from M (1 if 0).  role_of_pos[t] says which role
  * (0=a,1=b,2=c) parameter position t = 0,1,2 plays; m_pos[t] is its size.                       */

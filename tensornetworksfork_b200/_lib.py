@@ -37,6 +37,8 @@ PROTOTYPES = {
     "tn_gram_kr3": (i32, [i32, FP, FP, FP, vp, i64, vp, vp, i32, i32, vp]),
     "tn_rhs_ksplit": (i32, [i64, i32, i32, i32]),
     "tn_rhs_kr3": (i32, [FP, FP, FP, vp, i64, vp, vp, i32, i32, vp]),
+    "tn_generic_ksplit": (i32, [i64, i32, i32]),
+    "tn_gram_generic": (i32, [FP, FP, FP, vp, vp, vp, i32, vp, i64, vp, i32, vp, i32, i32, vp]),
     "tn_gram_sigma": (i32, [vp, IP, IP, vp, vp]),
     "tn_gram_expand": (i32, [vp, IP, IP, vp, f64, vp, i64, vp]),
     "tn_rhs_prepare": (i32, [vp, vp, vp, f64, vp, i64, vp]),

@@ -38,11 +38,16 @@ __device__ __forceinline__ void stage_factor(const FactorDev& f, double* dst, in
     }
 }
 
-// PAIR = true : Gram (pairs of each factor).  PAIR = false : right-hand side (plain products).
-template <bool PAIR>
+// MODE 1: Gram of a Kronecker Jacobian (pairs of each factor).  MODE 0: right-hand side (plain products).
+// MODE 2: Gram of a Jacobian whose column i is fa[t1[i]]*fb[t2[i]]*fc[t3[i]] (index tables; no Kronecker structure
+//         assumed -- the cum-sum train, reference layers.py:408-477): out is the full P x P matrix.
+// MODE 3: as 2 with V = 1 (one column): out = J^T w, the right-hand side.
+template <int MODE>
 __global__ void __launch_bounds__(GR_THREADS)
 kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restrict__ w, int64_t rows,
-               double* __restrict__ out, int nA, int nB, int nC, int64_t rows_per_split) {
+               double* __restrict__ out, int nA, int nB, int nC, int64_t rows_per_split,
+               const int* __restrict__ t1, const int* __restrict__ t2, const int* __restrict__ t3) {
+    constexpr bool PAIR = (MODE == 1);
     extern __shared__ double sm[];
     const int stA = fa.m | 1, stB = fb.m | 1, stC = fc.m | 1;
     double* sFA = sm;
@@ -57,6 +62,7 @@ kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
     short* tJB = tIB + GR_TU;
     short* tIC = tJB + GR_TU;
     short* tJC = tIC + GR_TV;
+    short* tKC = tJC + GR_TV;
 
     const int tid = threadIdx.x;
     const int64_t nU = (int64_t)nA * nB;
@@ -68,7 +74,9 @@ kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
     if (tid < GR_TU) {
         const int64_t gu = u0 + tid;
         int ia = -1, ja = 0, ib = 0, jb = 0;
-        if (gu < nU) {
+        if (MODE >= 2) {
+            if (gu < nU) { ia = t1[gu]; ib = t2[gu]; ja = t3[gu]; }
+        } else if (gu < nU) {
             const int qa = (int)(gu / nB), qb = (int)(gu - (int64_t)qa * nB);
             if (PAIR) {
                 pair_decode(qa, fa.m, ia, ja);
@@ -82,12 +90,16 @@ kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
     } else if (tid < GR_TU + GR_TV) {
         const int t = tid - GR_TU;
         const int gv = v0 + t;
-        int ic = -1, jc = 0;
-        if (gv < nC) {
+        int ic = -1, jc = 0, kc = 0;
+        if (MODE == 2) {
+            if (gv < nC) { ic = t1[gv]; jc = t2[gv]; kc = t3[gv]; }
+        } else if (MODE == 3) {
+            ic = (gv == 0) ? 0 : -1;
+        } else if (gv < nC) {
             if (PAIR) pair_decode(gv, fc.m, ic, jc);
             else ic = jc = gv;
         }
-        tIC[t] = (short)ic; tJC[t] = (short)jc;
+        tIC[t] = (short)ic; tJC[t] = (short)jc; tKC[t] = (short)kc;
     }
 
     const int tx = tid & 15, ty = tid >> 4;
@@ -114,7 +126,8 @@ kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
             if (ia >= 0) {
                 const double* a = sFA + k * stA;
                 const double* b = sFB + k * stB;
-                v = PAIR ? sW[k] * a[ia] * a[tJA[u]] * b[tIB[u]] * b[tJB[u]] : sW[k] * a[ia] * b[tIB[u]];
+                if (MODE >= 2) v = sW[k] * a[ia] * b[tIB[u]] * sFC[k * stC + tJA[u]];
+                else v = PAIR ? sW[k] * a[ia] * a[tJA[u]] * b[tIB[u]] * b[tJB[u]] : sW[k] * a[ia] * b[tIB[u]];
             }
             sU[idx] = v;
         }
@@ -124,7 +137,9 @@ kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
             double v = 0.0;
             if (ic >= 0) {
                 const double* c = sFC + k * stC;
-                v = PAIR ? c[ic] * c[tJC[t]] : c[ic];
+                if (MODE == 2) v = sFA[k * stA + ic] * sFB[k * stB + tJC[t]] * c[tKC[t]];
+                else if (MODE == 3) v = 1.0;
+                else v = PAIR ? c[ic] * c[tJC[t]] : c[ic];
             }
             sV[idx] = v;
         }
@@ -180,11 +195,14 @@ static int choose_ksplit(int64_t rows, int64_t nU, int64_t nV) {
     return (int)ks;
 }
 
-template <bool PAIR>
+template <int MODE>
 static int launch_kr3(const tn_factor* fa, const tn_factor* fb, const tn_factor* fc, const double* w, int64_t rows,
-                      double* dst, double* work, int ksplit, int accumulate, cudaStream_t st) {
+                      double* dst, double* work, int ksplit, int accumulate, cudaStream_t st, const int* t1 = nullptr,
+                      const int* t2 = nullptr, const int* t3 = nullptr, int P = 0) {
+    constexpr bool PAIR = (MODE == 1);
     const FactorDev a = to_dev(fa), b = to_dev(fb), c = to_dev(fc);
-    const int nA = PAIR ? npairs(a.m) : a.m, nB = PAIR ? npairs(b.m) : b.m, nC = PAIR ? npairs(c.m) : c.m;
+    int nA = PAIR ? npairs(a.m) : a.m, nB = PAIR ? npairs(b.m) : b.m, nC = PAIR ? npairs(c.m) : c.m;
+    if (MODE >= 2) { nA = P; nB = 1; nC = (MODE == 2) ? P : 1; }
     const int64_t nU = (int64_t)nA * nB;
     const int64_t n = nU * nC;
     if (ksplit < 1) ksplit = 1;
@@ -193,18 +211,18 @@ static int launch_kr3(const tn_factor* fa, const tn_factor* fb, const tn_factor*
     const bool direct = (ksplit == 1 && !accumulate);
     TN_CHECK_ARG(direct || work != nullptr, "kr3: ksplit=%d / accumulate need a work buffer", ksplit);
     const size_t smem = (size_t)(GR_KC * ((a.m | 1) + (b.m | 1) + (c.m | 1)) + GR_KC + GR_KC * GR_TU + GR_KC * GR_TV) * sizeof(double) +
-                        (size_t)(4 * GR_TU + 2 * GR_TV) * sizeof(short);
+                        (size_t)(4 * GR_TU + 3 * GR_TV) * sizeof(short);
     TN_CHECK_ARG(smem <= 227 * 1024, "kr3: factor sizes %d,%d,%d need %zu B of shared memory", a.m, b.m, c.m, smem);
     TN_CHECK_ARG(a.m < 32768 && b.m < 32768 && c.m < 32768, "kr3: factor too large");
-    static size_t configured[2] = {0, 0};
-    if (smem > configured[PAIR]) {
-        TN_CUDA(cudaFuncSetAttribute(kr3_f64_kernel<PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[PAIR] = smem;
+    static size_t configured[4] = {0, 0, 0, 0};
+    if (smem > configured[MODE]) {
+        TN_CUDA(cudaFuncSetAttribute(kr3_f64_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[MODE] = smem;
     }
     const int64_t gx = ceil_div64(nU, GR_TU), gy = ceil_div64(nC, GR_TV);
     TN_CHECK_ARG(gy <= 65535 && ksplit <= 65535 && gx <= 0x7fffffff, "kr3: grid too large");
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)ksplit);
-    kr3_f64_kernel<PAIR><<<grid, GR_THREADS, smem, st>>>(a, b, c, w, rows, direct ? dst : work, nA, nB, nC, rps);
+    kr3_f64_kernel<MODE><<<grid, GR_THREADS, smem, st>>>(a, b, c, w, rows, direct ? dst : work, nA, nB, nC, rps, t1, t2, t3);
     TN_LAUNCH_CHECK();
     if (!direct) {
         int64_t blocks = ceil_div64(n, 256);
@@ -367,7 +385,7 @@ extern "C" int tn_gram_kr3(int mode, const tn_factor* fa, const tn_factor* fb, c
     TN_CHECK_ARG(fa && fb && fc && M, "tn_gram_kr3: null argument");
     TN_CHECK_ARG(rows >= 0, "tn_gram_kr3: negative rows");
     TN_CHECK_ARG(fa->m >= 1 && fb->m >= 1 && fc->m >= 1, "tn_gram_kr3: empty factor");
-    if (mode == 0) return launch_kr3<true>(fa, fb, fc, w, rows, M, work, ksplit, accumulate, as_stream(stream));
+    if (mode == 0) return launch_kr3<1>(fa, fb, fc, w, rows, M, work, ksplit, accumulate, as_stream(stream));
     if (mode == 1 || mode == 2) return tn_gram_kr3_tc(mode, fa, fb, fc, w, rows, M, accumulate, stream);
     set_error("tn_gram_kr3: unknown mode %d", mode);
     return TN_EINVAL;
@@ -378,7 +396,20 @@ extern "C" int tn_rhs_kr3(const tn_factor* fa, const tn_factor* fb, const tn_fac
     using namespace tn;
     TN_CHECK_ARG(fa && fb && fc && b, "tn_rhs_kr3: null argument");
     TN_CHECK_ARG(rows >= 0, "tn_rhs_kr3: negative rows");
-    return launch_kr3<false>(fa, fb, fc, w, rows, b, work, ksplit, accumulate, as_stream(stream));
+    return launch_kr3<0>(fa, fb, fc, w, rows, b, work, ksplit, accumulate, as_stream(stream));
+}
+
+extern "C" int tn_generic_ksplit(int64_t rows, int P, int rhs_only) {
+    return tn::choose_ksplit(rows, P, rhs_only ? 1 : P);
+}
+
+extern "C" int tn_gram_generic(const tn_factor* f1, const tn_factor* f2, const tn_factor* f3, const int* t1, const int* t2,
+                               const int* t3, int P, const double* w, int64_t rows, double* out, int rhs_only, double* work,
+                               int ksplit, int accumulate, void* stream) {
+    using namespace tn;
+    TN_CHECK_ARG(f1 && f2 && f3 && t1 && t2 && t3 && out && P >= 1 && rows >= 0, "tn_gram_generic: bad arguments");
+    if (rhs_only) return launch_kr3<3>(f1, f2, f3, w, rows, out, work, ksplit, accumulate, as_stream(stream), t1, t2, t3, P);
+    return launch_kr3<2>(f1, f2, f3, w, rows, out, work, ksplit, accumulate, as_stream(stream), t1, t2, t3, P);
 }
 
 extern "C" int tn_gram_sigma(const double* M, const int* m_pos, const int* role_of_pos, double* sigma_out, void* stream) {

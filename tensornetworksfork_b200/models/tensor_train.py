@@ -13,7 +13,7 @@ from sklearn.base import BaseEstimator, RegressorMixin
 from sklearn.metrics import accuracy_score, r2_score, root_mean_squared_error
 
 from ..tensor.bregman import SquareBregFunction
-from ..tensor.layers import CPDLayer, TensorTrainLayer
+from ..tensor.layers import CPDLayer, CumSumLayer, TensorTrainLayer
 
 
 def root_mean_squared_error_torch(y_true, y_pred):
@@ -104,11 +104,14 @@ class TensorTrainRegressor(BaseEstimator, RegressorMixin):
         mt = self.model_type
         if "type1" in mt or "typeI" in mt:
             raise NotImplementedError("type-I (sum of networks) models are a 'next' row of the scope table (SURVEY.md §8f)")
-        if self.cum_sum or self.linear_dim is not None:
-            raise NotImplementedError("cum-sum / linear-projection layers are not built yet")
+        if self.linear_dim is not None:
+            raise NotImplementedError("linear-projection layers are a 'next' row of the scope table (SURVEY.md §8f)")
         if mt.startswith("cpd"):
             self._model = CPDLayer(self.N, self.r, self.input_dim, output_shape=self.output_dim, perturb=self.perturb,
                                    seed=self.seed).to(self.device)
+        elif mt.startswith("tt") and self.cum_sum:
+            self._model = CumSumLayer(self.N, self.r, self.input_dim, output_shape=self.output_dim,
+                                      constrict_bond=self.constrict_bond, perturb=self.perturb, seed=self.seed).to(self.device)
         elif mt.startswith("tt"):
             self._model = TensorTrainLayer(self.N, self.r, self.input_dim, output_shape=self.output_dim,
                                            constrict_bond=self.constrict_bond, perturb=self.perturb, seed=self.seed).to(self.device)

@@ -150,6 +150,27 @@ def rhs(fa: Factor, fb: Factor, fc: Factor, w, rows, b=None, accumulate=False):
     return b
 
 
+def gram_generic(f1: Factor, f2: Factor, f3: Factor, t1, t2, t3, w, rows, rhs_only=False, out=None, accumulate=False):
+    """Dense Gram J^T diag(w) J (P x P) or right-hand side J^T w (P) of J[:, i] = f1[t1[i]] f2[t2[i]] f3[t3[i]]."""
+    lib = _lib.load()
+    _need_cuda(f1.tensor, f2.tensor, f3.tensor, w)
+    P = t1.numel()
+    assert t1.dtype == torch.int32 and t2.dtype == torch.int32 and t3.dtype == torch.int32
+    n = P if rhs_only else P * P
+    dev = f1.tensor.device
+    if out is None:
+        out = torch.empty((n,), dtype=torch.float64, device=dev)
+        accumulate = False
+    ks = lib.tn_generic_ksplit(rows, P, 1 if rhs_only else 0)
+    work = torch.empty((ks * n,), dtype=torch.float64, device=dev) if (ks > 1 or accumulate) else None
+    a, b, c = f1.c(), f2.c(), f3.c()
+    rc = lib.tn_gram_generic(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.c_void_p(t1.data_ptr()),
+                             ctypes.c_void_p(t2.data_ptr()), ctypes.c_void_p(t3.data_ptr()), P, _p(w), rows, _p(out),
+                             1 if rhs_only else 0, _p(work), ks, 1 if accumulate else 0, _stream())
+    _lib.check(rc, "tn_gram_generic")
+    return out
+
+
 def _int3(v):
     return (ctypes.c_int * 3)(*v)
 

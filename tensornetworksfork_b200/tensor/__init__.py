@@ -2,5 +2,6 @@ from .node import TensorNode  # noqa: F401
 from .network import TensorNetwork, MappedInput, sweep_schedule  # noqa: F401
 from .cpd import CPDNetwork  # noqa: F401
 from .layers import (TensorNetworkLayer, TensorTrainLayer, CPDLayer, MainNodeLayer, InputNodeLayer,  # noqa: F401
-                     TensorTrainDMRGInfiLayer)
+                     TensorTrainDMRGInfiLayer, CumSumLayer)
+from .cumsum import CumSumNetwork  # noqa: F401
 from .bregman import SquareBregFunction, AutogradLoss, XEAutogradBregman, KLDivBregman  # noqa: F401

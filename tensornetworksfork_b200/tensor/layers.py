@@ -182,6 +182,29 @@ class TensorTrainLayer(TensorNetworkLayer):
                                               output_labels=self.main_node_layer.labels))
 
 
+class CumSumLayer(TensorNetworkLayer):
+    """Tensor train over ordered feature tuples (reference layers.py:425-477).  Same cores and draws as
+    ``TensorTrainLayer``; the reference's dense cum-sum operator nodes are replaced by the closed form in
+    ``cumsum.CumSumNetwork``.  Like the reference, ``seed`` is accepted and not applied here."""
+
+    def __init__(self, num_carriages, bond_dim, input_features, output_shape=tuple(), squeeze=True, constrict_bond=True,
+                 perturb=False, dtype=None, seed=None):
+        from .cumsum import CumSumNetwork
+        super().__init__()
+        self.num_carriages = num_carriages
+        self.input_features = input_features
+        self.main_node_layer = MainNodeLayer(num_carriages, bond_dim, input_features, output_shape=output_shape,
+                                             down_label="p{0}", constrict_bond=constrict_bond, perturb=perturb, dtype=dtype)
+        self.horizontal_connect(self.main_node_layer.nodes)
+        self.input_node_layer = InputNodeLayer(num_carriages, input_features, label="p{0}", dtype=dtype)
+        self.zip_connect(self.input_node_layer.nodes, self.main_node_layer.nodes, label="p{0}", priority=1)
+        if squeeze:
+            for n in self.main_node_layer.nodes:
+                n.squeeze(self.main_node_layer.labels)
+        self.set_tensor_network(CumSumNetwork(self.input_node_layer.nodes, self.main_node_layer.nodes,
+                                              output_labels=self.main_node_layer.labels))
+
+
 class CPDLayer(TensorNetworkLayer):
     """Rank-R canonical polyadic model: factor i is (b, p[, o]) (reference layers.py:1549-1625)."""
 

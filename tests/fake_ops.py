@@ -27,11 +27,15 @@ def ones_factor(like):
 def env_update(env_in, x, core3, rows, cdiv=1, env_div=1, out=None):
     phi = _rows(Factor(x.tensor, m=x.m, div=cdiv, map_kind=x.map_kind, col=x.col), rows)
     e = torch.ones(rows, 1, dtype=torch.float64) if env_in is None else env_in[torch.arange(rows) // env_div]
-    return torch.einsum("sa,sp,apb->sb", e, phi, core3)
+    res = torch.einsum("sa,sp,apb->sb", e, phi, core3)
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
 
 
 def predict(env_in, x, core3, dot, rows, cdiv=1, env_div=1, dot_div=1, out=None):
-    o = env_update(env_in, x, core3, rows, cdiv, env_div)
+    o = env_update(env_in, x, core3, rows, cdiv, env_div, out=None)
     d = dot[(torch.arange(rows) // dot_div).clamp(max=dot.shape[0] - 1)]
     y = (o * d).sum(1)
     if out is not None:
@@ -74,6 +78,19 @@ def rhs(fa, fb, fc, w, rows, b=None, accumulate=False):
     else:
         b.copy_(out)
     return b
+
+
+def gram_generic(f1, f2, f3, t1, t2, t3, w, rows, rhs_only=False, out=None, accumulate=False):
+    J = _rows(f1, rows)[:, t1.long()] * _rows(f2, rows)[:, t2.long()] * _rows(f3, rows)[:, t3.long()]
+    ww = torch.ones(rows, dtype=torch.float64) if w is None else w
+    res = (J.t() @ ww) if rhs_only else ((J * ww[:, None]).t() @ J).reshape(-1)
+    if out is None:
+        return res
+    if accumulate:
+        out += res
+    else:
+        out.copy_(res)
+    return out
 
 
 def _dense(M, m_pos, role_of_pos):
@@ -148,7 +165,7 @@ def matvec(fa, fb, fc, w, rows, v, out=None):
     return J.t() @ (ww * (J @ v))
 
 
-NAMES = ["ones_factor", "env_update", "predict", "class_rows", "gram", "rhs", "gram_sigma", "gram_expand", "rhs_prepare",
+NAMES = ["ones_factor", "env_update", "predict", "class_rows", "gram", "rhs", "gram_generic", "gram_sigma", "gram_expand", "rhs_prepare",
          "cholesky_solve", "update_node", "qr", "matvec"]
 
 
