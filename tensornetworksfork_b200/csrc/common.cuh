@@ -60,4 +60,10 @@ __device__ __forceinline__ double map_eval(int map_kind, const double* __restric
 
 int sm_count();
 
+// FP64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col): a = A[lane/4][lane%4], b = B[lane%4][lane/4],
+// d0/d1 = D[lane/4][2*(lane%4) + 0/1].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
+}
+
 }  // namespace tn

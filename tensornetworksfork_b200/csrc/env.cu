@@ -8,6 +8,7 @@
 // contiguous byte range; the site input is read once per sample and mapped in registers.
 // One CTA owns 64..128 rows; the core is streamed through shared memory in feature slabs that
 // every CTA re-reads from L2 (the core is at most a few hundred KB).
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace tn {
@@ -139,6 +140,289 @@ env_kernel(const double* __restrict__ env_in, int64_t env_ld, int env_div, const
     }
 }
 
+// ---- FP64 tensor-core variant (DMMA m8n8k4).  out = Z * G with Z[row, k=(a,p)] = env[row,a] * phi[row,p] formed in
+//      registers as the A fragment, G = core viewed as (r_in*f) x r_out read as the B fragment from shared memory.
+//      One CTA = 128 rows, 8 warps x 16 rows; NT 8-column tiles cover r_out.  Same contract as env_kernel.
+constexpr int ED_TR = 128;
+constexpr int ED_KC = 64;    // k per staged core slab
+
+template <int NT>
+__global__ void __launch_bounds__(ENV_THREADS, 2)
+env_dmma_kernel(const double* __restrict__ env_in, int64_t env_ld, int env_div, const double* __restrict__ x, int64_t x_ld,
+                int map_kind, int f, int cdiv, const double* __restrict__ core, double* __restrict__ out,
+                int64_t out_ld, const double* __restrict__ dot, int64_t dot_ld, int dot_div,
+                double* __restrict__ yhat, int64_t rows, int r_in, int r_out) {
+    constexpr int LDG = NT * 8 + 8;                  // core slab row stride: == 8 (mod 16) doubles, conflict-free B fragments
+    extern __shared__ double sm[];
+    const int in_st = (r_in + 5) | 1;                // + zero columns read by the padded tail of K
+    const int phi_st = f | 1;
+    double* s_in = sm;                               // [ED_TR][in_st]
+    double* s_phi = s_in + ED_TR * in_st;            // [ED_TR][phi_st]
+    double* s_g = s_phi + ED_TR * phi_st;            // [ED_KC][LDG]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t row0 = (int64_t)blockIdx.x * ED_TR;
+    const int K = r_in * f;
+
+    for (int idx = tid; idx < ED_TR * in_st; idx += ENV_THREADS) {
+        const int r = idx / in_st, a = idx - r * in_st;
+        const int64_t row = row0 + r;
+        double v = 0.0;
+        if (row < rows && a < r_in) v = env_in ? env_in[(env_div == 1 ? row : row / env_div) * env_ld + a] : 1.0;
+        s_in[idx] = v;
+    }
+    if (map_kind == TN_MAP_SINCOS) {
+        for (int r = tid; r < ED_TR; r += ENV_THREADS) {
+            const int64_t row = row0 + r;
+            double c = 0.0, sn = 0.0;
+            if (row < rows) sincos((0.5 * 3.14159265358979323846) * x[(cdiv == 1 ? row : row / cdiv) * x_ld], &sn, &c);
+            s_phi[r * phi_st] = c;
+            s_phi[r * phi_st + 1] = sn;
+        }
+    } else {
+        for (int idx = tid; idx < ED_TR * f; idx += ENV_THREADS) {
+            const int r = idx / f, p = idx - r * f;
+            const int64_t row = row0 + r;
+            s_phi[r * phi_st + p] = (row < rows) ? map_eval(map_kind, x + (cdiv == 1 ? row : row / cdiv) * x_ld, p) : 0.0;
+        }
+    }
+
+    double acc[2][NT][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int fr = lane >> 2, fk = lane & 3;
+    const int da = 4 / f, dp = 4 - da * f;            // (a, p) advance of this lane's k by 4
+    int ka = fk / f, kp = fk - ka * f;                // k = fk at the start
+    const double* in0 = s_in + (warp * 16 + fr) * in_st;
+    const double* in1 = in0 + 8 * in_st;
+    const double* ph0 = s_phi + (warp * 16 + fr) * phi_st;
+    const double* ph1 = ph0 + 8 * phi_st;
+
+    for (int k0 = 0; k0 < K; k0 += ED_KC) {
+        __syncthreads();
+        for (int idx = tid; idx < ED_KC * (NT * 8); idx += ENV_THREADS) {
+            const int kk = idx / (NT * 8), n = idx - kk * (NT * 8);
+            const int k = k0 + kk;
+            s_g[kk * LDG + n] = (k < K && n < r_out) ? core[(int64_t)k * r_out + n] : 0.0;
+        }
+        __syncthreads();
+        const int kend = min(ED_KC, ((K - k0) + 3) & ~3);   // the padded tail reads the zero columns of s_in
+#pragma unroll 4
+        for (int kk = 0; kk < kend; kk += 4) {
+            // A fragments: rows fr and fr+8 of this warp's 16, column k = k0 + kk + fk  ->  env[a] * phi[p]
+            const double a0 = in0[ka] * ph0[kp];
+            const double a1 = in1[ka] * ph1[kp];
+            kp += dp; ka += da;
+            if (kp >= f) { kp -= f; ++ka; }
+            const double* gp = s_g + (kk + fk) * LDG + fr;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const double b = gp[j * 8];
+                dmma884(acc[0][j][0], acc[0][j][1], a0, b);
+                dmma884(acc[1][j][0], acc[1][j][1], a1, b);
+            }
+        }
+    }
+    // epilogue: this lane owns rows (warp*16 + fr) and (+8), columns j*8 + 2*fk + {0,1}
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const int64_t row = row0 + warp * 16 + i * 8 + fr;
+        double yd = 0.0;
+        if (row < rows) {
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int b = j * 8 + 2 * fk + e;
+                    if (b < r_out) {
+                        if (dot) yd = fma(acc[i][j][e], dot[(dot_div == 1 ? row : row / dot_div) * dot_ld + b], yd);
+                        else out[row * out_ld + b] = acc[i][j][e];
+                    }
+                }
+            }
+        }
+        if (dot) {
+            yd += __shfl_xor_sync(0xffffffffu, yd, 1);
+            yd += __shfl_xor_sync(0xffffffffu, yd, 2);
+            if (fk == 0 && row < rows) yhat[row] = yd;
+        }
+    }
+}
+
+// ---- persistent, software-pipelined variant for small contractions (the whole core fits in shared memory):
+//      the HBM-bound case (f = 2: configs 3 and 4).  A CTA keeps the core resident, walks over row tiles and
+//      prefetches the next tile's environment rows and raw inputs with cp.async while it multiplies the current one.
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+
+template <int NT>
+__global__ void __launch_bounds__(ENV_THREADS, 2)
+env_dmma_persist_kernel(const double* __restrict__ env_in, int64_t env_ld, int env_div, const double* __restrict__ x, int64_t x_ld,
+                        int map_kind, int f, int cdiv, const double* __restrict__ core, double* __restrict__ out,
+                        int64_t out_ld, const double* __restrict__ dot, int64_t dot_ld, int dot_div,
+                        double* __restrict__ yhat, int64_t rows, int r_in, int r_out, int64_t ntiles) {
+    constexpr int LDG = NT * 8 + 8;
+    extern __shared__ double sm[];
+    const int in_st = (r_in + 5) | 1;
+    const int phi_st = f | 1;
+    const int K = r_in * f;
+    const int Kp = (K + 3) & ~3;
+    const int xraw = (map_kind == TN_MAP_IDENTITY) ? f : 1;      // raw input values per row
+    double* s_g = sm;                                            // [Kp][LDG]  resident
+    double* s_in = s_g + (size_t)Kp * LDG;                       // [2][ED_TR][in_st]
+    double* s_x = s_in + 2 * (size_t)ED_TR * in_st;              // [2][ED_TR][xraw]
+    double* s_phi = s_x + 2 * (size_t)ED_TR * xraw;              // [ED_TR][phi_st]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+    for (int idx = tid; idx < Kp * (NT * 8); idx += ENV_THREADS) {
+        const int k = idx / (NT * 8), n = idx - k * (NT * 8);
+        s_g[k * LDG + n] = (k < K && n < r_out) ? core[(int64_t)k * r_out + n] : 0.0;
+    }
+    for (int idx = tid; idx < 2 * ED_TR * in_st; idx += ENV_THREADS) s_in[idx] = (env_in == nullptr && (idx % in_st) == 0) ? 1.0 : 0.0;
+
+    auto prefetch = [&](int64_t tile, int buf) {
+        if (tile < ntiles) {
+            const int64_t row0 = tile * ED_TR;
+            if (env_in) {
+                double* dst = s_in + (size_t)buf * ED_TR * in_st;
+                for (int idx = tid; idx < ED_TR * r_in; idx += ENV_THREADS) {
+                    const int r = idx / r_in, a = idx - r * r_in;
+                    int64_t row = row0 + r;
+                    if (row >= rows) row = rows - 1;                 // clamped rows are never stored
+                    cp_async8(dst + r * in_st + a, env_in + (env_div == 1 ? row : row / env_div) * env_ld + a);
+                }
+            }
+            double* dx = s_x + (size_t)buf * ED_TR * xraw;
+            for (int idx = tid; idx < ED_TR * xraw; idx += ENV_THREADS) {
+                const int r = idx / xraw, q = idx - r * xraw;
+                int64_t row = row0 + r;
+                if (row >= rows) row = rows - 1;
+                cp_async8(dx + idx, x + (cdiv == 1 ? row : row / cdiv) * x_ld + q);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int fr = lane >> 2, fk = lane & 3;
+    const int da = 4 / f, dp = 4 - da * f;
+    int64_t tile = blockIdx.x;
+    int buf = 0;
+    __syncthreads();                 // zero / one fill of s_in done before the first async copies land on it
+    prefetch(tile, 0);
+    for (; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        __syncthreads();             // tile data visible to all; everyone is done with the other buffer and with s_phi
+        prefetch(tile + gridDim.x, buf ^ 1);
+        const int64_t row0 = tile * ED_TR;
+        const double* xin = s_x + (size_t)buf * ED_TR * xraw;
+        if (map_kind == TN_MAP_SINCOS) {
+            for (int r = tid; r < ED_TR; r += ENV_THREADS) {
+                double c, sn;
+                sincos((0.5 * 3.14159265358979323846) * xin[r], &sn, &c);
+                s_phi[r * phi_st] = c;
+                s_phi[r * phi_st + 1] = sn;
+            }
+        } else {
+            for (int idx = tid; idx < ED_TR * f; idx += ENV_THREADS) {
+                const int r = idx / f, p = idx - r * f;
+                s_phi[r * phi_st + p] = map_eval(map_kind, xin + r * xraw, p);
+            }
+        }
+        __syncthreads();
+        double acc[2][NT][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        int ka = fk / f, kp = fk - ka * f;
+        const double* in0 = s_in + (size_t)buf * ED_TR * in_st + (warp * 16 + fr) * in_st;
+        const double* in1 = in0 + 8 * in_st;
+        const double* ph0 = s_phi + (warp * 16 + fr) * phi_st;
+        const double* ph1 = ph0 + 8 * phi_st;
+#pragma unroll 4
+        for (int kk = 0; kk < Kp; kk += 4) {
+            const double a0 = in0[ka] * ph0[kp];
+            const double a1 = in1[ka] * ph1[kp];
+            kp += dp; ka += da;
+            if (kp >= f) { kp -= f; ++ka; }
+            const double* gp = s_g + (kk + fk) * LDG + fr;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const double b = gp[j * 8];
+                dmma884(acc[0][j][0], acc[0][j][1], a0, b);
+                dmma884(acc[1][j][0], acc[1][j][1], a1, b);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int64_t row = row0 + warp * 16 + i * 8 + fr;
+            double yd = 0.0;
+            if (row < rows) {
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+#pragma unroll
+                    for (int e = 0; e < 2; ++e) {
+                        const int b = j * 8 + 2 * fk + e;
+                        if (b < r_out) {
+                            if (dot) yd = fma(acc[i][j][e], dot[(dot_div == 1 ? row : row / dot_div) * dot_ld + b], yd);
+                            else out[row * out_ld + b] = acc[i][j][e];
+                        }
+                    }
+                }
+            }
+            if (dot) {
+                yd += __shfl_xor_sync(0xffffffffu, yd, 1);
+                yd += __shfl_xor_sync(0xffffffffu, yd, 2);
+                if (fk == 0 && row < rows) yhat[row] = yd;
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+}
+
+template <int NT>
+static int launch_env_dmma(const double* env_in, int64_t env_ld, int env_div, const double* x, int64_t x_ld, int map_kind, int f,
+                           int cdiv, const double* core, double* out, int64_t out_ld, const double* dot, int64_t dot_ld,
+                           int dot_div, double* yhat, int64_t rows, int r_in, int r_out, cudaStream_t st) {
+    {   // persistent pipelined kernel when the whole core slab stays resident
+        const int K = r_in * f, Kp = (K + 3) & ~3, xraw = (map_kind == TN_MAP_IDENTITY) ? f : 1;
+        const size_t psmem = ((size_t)Kp * (NT * 8 + 8) + 2 * (size_t)ED_TR * ((r_in + 5) | 1) + 2 * (size_t)ED_TR * xraw +
+                              (size_t)ED_TR * (f | 1)) * sizeof(double);
+        const int64_t ntiles = ceil_div64(rows, ED_TR);
+        if ((size_t)Kp * (NT * 8 + 8) * sizeof(double) <= 48 * 1024 && psmem <= 113 * 1024 && ntiles >= 4LL * sm_count() &&
+            !getenv("TN_ENV_NO_PERSIST")) {
+            static size_t pconfigured = 0;
+            if (psmem > pconfigured) {
+                TN_CUDA(cudaFuncSetAttribute(env_dmma_persist_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+                pconfigured = psmem;
+            }
+            int64_t grid = 2LL * sm_count();
+            if (grid > ntiles) grid = ntiles;
+            env_dmma_persist_kernel<NT><<<(unsigned)grid, ENV_THREADS, psmem, st>>>(env_in, env_ld, env_div, x, x_ld, map_kind, f, cdiv, core,
+                                                                               out, out_ld, dot, dot_ld, dot_div, yhat, rows, r_in, r_out,
+                                                                               ntiles);
+            TN_LAUNCH_CHECK();
+            return TN_OK;
+        }
+    }
+    const size_t smem = ((size_t)ED_TR * ((r_in + 5) | 1) + (size_t)ED_TR * (f | 1) + (size_t)ED_KC * (NT * 8 + 8)) * sizeof(double);
+    if (smem > 113 * 1024) return 1;   // would not leave room for two CTAs per SM: let the caller use the FMA kernel
+    static size_t configured = 0;
+    if (smem > configured) {
+        TN_CUDA(cudaFuncSetAttribute(env_dmma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    const int64_t grid = ceil_div64(rows, ED_TR);
+    TN_CHECK_ARG(grid <= 0x7fffffff, "tn_env_update: too many rows");
+    env_dmma_kernel<NT><<<(unsigned)grid, ENV_THREADS, smem, st>>>(env_in, env_ld, env_div, x, x_ld, map_kind, f, cdiv, core, out, out_ld,
+                                                                 dot, dot_ld, dot_div, yhat, rows, r_in, r_out);
+    TN_LAUNCH_CHECK();
+    return TN_OK;
+}
+
 __global__ void class_rows_kernel(const double* __restrict__ env, const double* __restrict__ U,
                                   const double* __restrict__ g, double* __restrict__ F, double* __restrict__ G,
                                   int64_t S, int C, int V, int r) {
@@ -181,6 +465,25 @@ extern "C" int tn_env_update(const double* env_in, int64_t env_ld, int env_div, 
     TN_CHECK_ARG(map_kind >= 0 && map_kind <= 2, "tn_env_update: unknown map_kind %d", map_kind);
     TN_CHECK_ARG(map_kind != TN_MAP_SINCOS || f == 2, "tn_env_update: sin-cos map has f == 2");
     if (rows == 0) return TN_OK;
+    // FP64 tensor-core path for every shape it covers (r_out <= 104, K = r_in*f >= 8); the FMA kernel below is the
+    // general one (very wide outputs, tiny contractions, shared-memory overflow).
+    if (r_out <= 104 && (int64_t)r_in * f >= 8 && !getenv("TN_ENV_NO_DMMA")) {
+        const int nt = (r_out + 7) / 8;
+        const int edv = env_div < 1 ? 1 : env_div;
+        cudaStream_t st = as_stream(stream);
+        int rc = 1;
+#define TN_ENV_DMMA(NTV) rc = launch_env_dmma<NTV>(env_in, env_ld, edv, x, x_ld, map_kind, f, cdiv, core, out, out_ld, dot, dot_ld, dot_div, yhat, rows, r_in, r_out, st)
+        if (nt <= 1) TN_ENV_DMMA(1);
+        else if (nt <= 2) TN_ENV_DMMA(2);
+        else if (nt <= 3) TN_ENV_DMMA(3);
+        else if (nt <= 4) TN_ENV_DMMA(4);
+        else if (nt <= 5) TN_ENV_DMMA(5);
+        else if (nt <= 6) TN_ENV_DMMA(6);
+        else if (nt <= 8) TN_ENV_DMMA(8);
+        else TN_ENV_DMMA(13);
+#undef TN_ENV_DMMA
+        if (rc <= 0) return rc;      // launched (0) or failed (<0); rc == 1 means "does not fit", fall through
+    }
     // column tiling: 8 lanes x ceil(r_out/8) columns per thread for narrow outputs (no padded work), 16 x 4 for wide ones
     int TXN = 8, CN = (r_out + 7) / 8;
     if (CN > 5) { TXN = 16; CN = 4; }

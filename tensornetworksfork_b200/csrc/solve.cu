@@ -217,9 +217,6 @@ constexpr int DS_STAGES = 3;
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(d0), "+d"(d1) : "d"(a), "d"(b));
-}
 
 __global__ void __launch_bounds__(256, 1)
 syrk_update_dmma_kernel(double* __restrict__ A, int64_t lda, int64_t P, int64_t c0, int64_t c1, int64_t k0, int kb,

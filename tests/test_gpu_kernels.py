@@ -42,6 +42,25 @@ def test_env_update_identity(S, rin, f, rout):
     assert gu.relerr(yh, (want * dot).sum(1)) < 1e-13
 
 
+@pytest.mark.parametrize("S,C,rin,f,rout", [(120000, 1, 24, 2, 24), (90001, 3, 6, 3, 5), (100000, 1, 1, 4, 7)])
+def test_env_update_persistent_pipelined_path(S, C, rin, f, rout):
+    """Enough row tiles to take the persistent cp.async-pipelined DMMA kernel (small contraction, core resident)."""
+    rng = np.random.default_rng(S)
+    env = rng.normal(size=(S * C, rin))
+    x = rng.uniform(-1, 1, size=(S, f))
+    core = rng.normal(size=(rin, f, rout))
+    dot = rng.normal(size=(S, rout))
+    xr = np.repeat(x, C, axis=0)
+    want = np.einsum("sa,sp,apb->sb", env, xr, core)
+    e = None if rin == 1 else T(env)
+    if rin == 1:
+        want = np.einsum("sp,pb->sb", xr, core[0])
+    got = ops.env_update(e, Factor(T(x), m=f), T(core), S * C, cdiv=C).cpu().numpy()
+    assert gu.relerr(got, want) < 1e-13
+    yh = ops.predict(e, Factor(T(x), m=f), T(core), T(dot), S * C, cdiv=C, dot_div=C).cpu().numpy()
+    assert gu.relerr(yh, (want * np.repeat(dot, C, axis=0)).sum(1)) < 1e-13
+
+
 def test_env_update_chain_end_and_class_rows():
     rng = np.random.default_rng(1)
     S, C, f, r = 300, 3, 4, 5
