@@ -180,28 +180,46 @@ tc_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict_
     }
 }
 
-// TMEM accumulator -> registers -> fp64 atomic adds into M.  Warp w may touch TMEM lanes 32*(w%4)..+31;
-// the two producer warps that share a lane quarter split the columns.
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,"
+                 "%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+                   "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]),
+                   "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]),
+                   "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+                 : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// TMEM accumulator -> registers -> (transpose through shared memory) -> fp64 atomic adds into M.
+// Warp w may touch TMEM lanes 32*(w%4)..+31 (= 32 rows of a U tile); the two producer warps that share a lane quarter
+// split the columns.  tcgen05.ld hands every lane one ROW; the 32x32 block is transposed through a padded shared
+// scratch so that each RED instruction adds 32 consecutive doubles of one row of M (coalesced) instead of 32 rows.
 __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_total, int BN, int warp, int lane, int64_t u0,
-                                               int64_t nU, int v0, int nC, double* __restrict__ M) {
+                                               int64_t nU, int v0, int nC, double* __restrict__ M, float* __restrict__ scratch) {
     const int q = warp & 3;
     const int half = (warp - 1) >> 2;
-    const int cols_half = ((cols_total / 16 + 1) / 2) * 16;
-    const int col_lo = half * cols_half;
-    const int col_hi = min(cols_total, col_lo + cols_half);
-    const int row_in_tile = q * 32 + lane;
-    for (int col = col_lo; col < col_hi; col += 16) {
-        uint32_t r[16];
-        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)col, r);
-        const int t = col / BN;
-        const int cbase = col - t * BN;
-        const int64_t gu = u0 + (int64_t)t * TC_M + row_in_tile;
-        if (gu < nU) {
-            double* dst = M + gu * nC + v0 + cbase;
+    const int ngroups = (cols_total + 31) / 32;
+    const int g_lo = half * ((ngroups + 1) / 2);
+    const int g_hi = min(ngroups, g_lo + (ngroups + 1) / 2);
+    float* sc = scratch + (size_t)(warp - 1) * (32 * 33);
+    for (int g = g_lo; g < g_hi; ++g) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 32), r);
 #pragma unroll
-            for (int e = 0; e < 16; ++e)
-                if (v0 + cbase + e < nC) atomicAdd(dst + e, (double)__uint_as_float(r[e]));
+        for (int e = 0; e < 32; ++e) sc[lane * 33 + e] = __uint_as_float(r[e]);
+        __syncwarp();
+        const int col = g * 32 + lane;                 // this lane's accumulator column
+        const int t = col / BN;
+        const int gv = v0 + (col - t * BN);
+        const bool col_ok = (col < cols_total) && (gv < nC);
+        const int64_t gu0 = u0 + (int64_t)t * TC_M + q * 32;
+        double* dst = M + gu0 * nC + gv;
+#pragma unroll 4
+        for (int rr = 0; rr < 32; ++rr) {
+            if (col_ok && gu0 + rr < nU) atomicAdd(dst + (int64_t)rr * nC, (double)sc[rr * 33 + lane]);
         }
+        __syncwarp();
     }
 }
 
@@ -412,7 +430,7 @@ gram_tc_kernel(TcParams p) {
                 mbar_wait(acc_full, acc_phase);
                 acc_phase ^= 1;
                 tc_fence_after();
-                drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M);
+                drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, reinterpret_cast<float*>(stage_base));
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty);
