@@ -240,6 +240,8 @@ def bench_b200(args):
     # ---- device-resident timed region
     counter[0] = 0
     timer.enabled = True
+    from tensornetworksfork_b200 import _lib as _tnlib
+    launches0 = _tnlib.load().tn_launch_count()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
@@ -251,6 +253,7 @@ def bench_b200(args):
     barrier()
     clk = clocks.stop() if rank == 0 else None
     timer.enabled = False
+    kernel_launches = int(_tnlib.load().tn_launch_count() - launches0)
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -303,7 +306,7 @@ def bench_b200(args):
         import peaks as _peaks
         measured = _peaks.measure()
     gram_ms = tot["gram"]
-    launches = sum(len(v) for v in tot.values())
+    launches = kernel_launches   # kernels of libtn_b200.so launched inside the timed region (counted by the library)
     issued = algo = 0.0
     for c in timer.extra["gram"]:
         i_, a_ = gram_flops(c)

@@ -53,6 +53,8 @@ int tn_version(void);
 const char *tn_last_error(void);
 /* Number of SMs of the current device (grid sizing on the host side). */
 int tn_sm_count(void);
+/* Number of kernels this library has launched in the process so far (bench bookkeeping). */
+int64_t tn_launch_count(void);
 
 /* ---- environments: TensorNetwork.compute_stacks / left|right_update_stacks / forward
  *      (tensor/network.py:55-71, 152-172, 115-137).

@@ -31,6 +31,7 @@ PROTOTYPES = {
     "tn_version": (i32, []),
     "tn_last_error": (ctypes.c_char_p, []),
     "tn_sm_count": (i32, []),
+    "tn_launch_count": (i64, []),
     "tn_env_update": (i32, [vp, i64, i32, vp, i64, i32, i32, i32, vp, vp, i64, vp, i64, i32, vp, i64, i32, i32, vp]),
     "tn_class_rows": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
     "tn_gram_ksplit": (i32, [i64, i32, i32, i32, i32]),

@@ -1,6 +1,7 @@
 // Error plumbing and device queries of the C ABI.
 #include <stdarg.h>
 #include <string.h>
+#include <atomic>
 #include "common.cuh"
 
 namespace tn {
@@ -11,6 +12,9 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 int sm_count() {
     static int cached = 0;
     if (cached) return cached;
@@ -25,3 +29,5 @@ int sm_count() {
 extern "C" int tn_version(void) { return 100; }
 extern "C" const char* tn_last_error(void) { return tn::g_err; }
 extern "C" int tn_sm_count(void) { return tn::sm_count(); }
+namespace tn { long long launches(); }
+extern "C" int64_t tn_launch_count(void) { return (int64_t)tn::launches(); }

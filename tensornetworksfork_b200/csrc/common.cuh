@@ -26,7 +26,11 @@ void set_error(const char* fmt, ...);
         }                                                                               \
     } while (0)
 
-#define TN_LAUNCH_CHECK() TN_CUDA(cudaGetLastError())
+#define TN_LAUNCH_CHECK()          \
+    do {                           \
+        tn::count_launch();        \
+        TN_CUDA(cudaGetLastError()); \
+    } while (0)
 
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
@@ -59,6 +63,7 @@ __device__ __forceinline__ double map_eval(int map_kind, const double* __restric
 }
 
 int sm_count();
+void count_launch(int n = 1);   // bookkeeping for tn_launch_count()
 
 // FP64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col): a = A[lane/4][lane%4], b = B[lane%4][lane/4],
 // d0/d1 = D[lane/4][2*(lane%4) + 0/1].

@@ -450,13 +450,16 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
             const int nb = (int)((Jend - j < CH_NB) ? Jend - j : CH_NB);
             double* Linv = work + (j / CH_NB) * CH_NB * CH_NB;
             potrf_diag_kernel<<<1, 256, kBlkSmem, st>>>(A, lda, j, nb, Linv, info);
+            count_launch();
             const int64_t below = P - (j + nb);
             if (below > 0) {
                 trsm_panel_kernel<<<(unsigned)ceil_div64(below, CH_NB), 256, kBlkSmem, st>>>(A, lda, j, nb, Linv, P, info);
+                count_launch();
                 if (j + nb < Jend) {
                     const int64_t c0 = j + nb;
                     dim3 grid((unsigned)ceil_div64(Jend - c0, 64), (unsigned)ceil_div64(P - c0, 64));
                     syrk_update_kernel<64><<<grid, 256, 0, st>>>(A, lda, P, c0, Jend, j, nb, info);
+                    count_launch();
                 }
             }
         }
@@ -491,21 +494,25 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
             const int nb = (int)((P - j < CH_NB) ? P - j : CH_NB);
             const double* Linv = work + (j / CH_NB) * CH_NB * CH_NB;
             trsv_diag_kernel<<<1, CH_NB, 0, st>>>(rhs, j, nb, Linv, 0, info);
+            count_launch();
             const int64_t below = P - (j + nb);
             if (below > 0) {
                 int64_t blocks = ceil_div64(below, 8);
                 if (blocks > 4LL * sms) blocks = 4LL * sms;
                 trsv_fwd_update_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, lda, P, j, nb, rhs, info);
+                count_launch();
             }
         }
         for (int64_t j = ((P - 1) / CH_NB) * CH_NB; j >= 0; j -= CH_NB) {
             const int nb = (int)((P - j < CH_NB) ? P - j : CH_NB);
             const double* Linv = work + (j / CH_NB) * CH_NB * CH_NB;
             trsv_diag_kernel<<<1, CH_NB, 0, st>>>(rhs, j, nb, Linv, 1, info);
+            count_launch();
             if (j > 0) {
                 int64_t blocks = ceil_div64(j, 256);
                 if (blocks > 4LL * sms) blocks = 4LL * sms;
                 trsv_bwd_update_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, lda, j, nb, rhs, info);
+                count_launch();
             }
         }
         TN_LAUNCH_CHECK();
