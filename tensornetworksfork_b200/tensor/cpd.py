@@ -138,6 +138,8 @@ class CPDNetwork(TensorNetwork):
         f = node.dim_size("p")
         O = self._num_outputs()
         yhat = self._predict(facs, S, self._Z)
+        if getattr(self, "_yhat_offset", None) is not None:
+            yhat = yhat + self._yhat_offset
         loss, g, U, lam = hessian_terms(loss_fn, yhat, y)
         g = g.reshape(S, O).contiguous()
         V = lam.shape[1]

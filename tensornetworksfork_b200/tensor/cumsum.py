@@ -125,6 +125,8 @@ class CumSumNetwork(TensorNetwork):
         L = self._get_left(k - 1)
         R = self._get_right(k + 1)
         yhat = self._predict_at(k, L, R, facs[k], S)
+        if getattr(self, "_yhat_offset", None) is not None:
+            yhat = yhat + self._yhat_offset
         out_labels = [l for l in self.output_labels if l != self.sample_dim]
         loss, g, U, lam = hessian_terms(loss_fn, yhat if out_labels else yhat[:, 0], y)
         V = lam.shape[1]

@@ -483,6 +483,8 @@ class TensorNetwork:
                 ops.predict(Lf, xk, G[:, c].contiguous(), Rf, S, dot_div=1 if R is not None else (1 << 30), out=yT[c])
             yhat = yT.t().contiguous()
 
+        if getattr(self, "_yhat_offset", None) is not None:
+            yhat = yhat + self._yhat_offset          # outputs of the other members of a SumOfNetworks (held fixed)
         out_labels = [l for l in self.output_labels if l != self.sample_dim]
         y_in = yhat if out_labels else yhat[:, 0]
         loss, g, U, lam = hessian_terms(loss_fn, y_in, y)
@@ -718,6 +720,10 @@ class TensorNetwork:
                                    n_total=self.shard_total if self.process_group is not None else S,
                                    group=self.process_group)
 
+    def _update_node(self, node, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss):
+        return self._one_update(self.main_nodes.index(node), y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm,
+                                need_loss)
+
     def accumulating_swipe(self, x, y_true, loss_fn, node_order=None, batch_size=-1, num_swipes=1, lr=1.0, method="exact",
                            eps=1e-12, eps_decay=None, convergence_criterion=None, orthonormalize=False, verbose=False,
                            skip_second=False, blocks_input=False, timeout=None, data_device=None, model_device=None,
@@ -757,10 +763,9 @@ class TensorNetwork:
             if timeout is not None and (time.time() - start) > timeout:
                 print(f"Timeout reached ({timeout} seconds). Stopping accumulating_swipe.")
                 return False
-            k = self.main_nodes.index(node)
             _method = "exact" if (eps_ == 0 and method == "ridge_exact") else method
             try:
-                loss = self._one_update(k, y, loss_fn, _method, eps_, lr, batch_size, adaptive_step, max_norm, need_loss)
+                loss = self._update_node(node, y, loss_fn, _method, eps_, lr, batch_size, adaptive_step, max_norm, need_loss)
             except torch.linalg.LinAlgError:
                 if verbose and verbose > 0:
                     print(f"Singular system for node {node.name}")
@@ -771,7 +776,8 @@ class TensorNetwork:
                     self.node_orthonormalize_left(node)
                 else:
                     self.node_orthonormalize_right(node)
-            if self.lean_envs:
+            if self.lean_envs and node in self.main_nodes:
+                k = self.main_nodes.index(node)
                 drop = self._right if going_right else self._left
                 for j in [j for j in drop if (j <= k + 1 if going_right else j >= k - 1)]:
                     del drop[j]
@@ -912,3 +918,133 @@ class _FixedTerms:
 
     def forward(self, y_pred, y):
         return torch.zeros(self.g.shape[0], dtype=self.g.dtype, device=self.g.device), self.g, self.H
+
+
+class SumOfNetworks(TensorNetwork):
+    """Sum of several networks fed by (feature slices of) the same input -- the reference's "type-I" models
+    (tensor/network.py:988-1060; built by models/tensor_train.py:138-189 as chains of 1..N cores).
+
+    The prediction is the sum of the members' predictions.  A node is updated inside its own member with the other
+    members' outputs held fixed (added to the member's prediction before the loss is evaluated), which is exactly what
+    the reference's inherited sweep does through ``forward`` (sum) + ``get_A_b`` (delegated to the member).
+    """
+
+    def __init__(self, networks, output_labels=("s",), sample_dim="s", train_operators=True):
+        input_nodes, main_nodes, train_nodes = [], [], []
+        for i, net in enumerate(networks, 1):
+            for n in net.input_nodes:
+                n.name = f"{n.name}_n{i}"
+            for n in net.main_nodes:
+                n.name = f"{n.name}_n{i}"
+            input_nodes.extend(net.input_nodes)
+            main_nodes.extend(net.main_nodes)
+            train_nodes.extend(net.train_nodes if train_operators else net.main_nodes)
+        super().__init__(input_nodes, main_nodes, train_nodes, output_labels=output_labels, sample_dim=sample_dim)
+        self.networks = list(networks)
+        self._member_pred = {}
+
+    def _plan(self):
+        raise NotImplementedError("SumOfNetworks delegates to its members")
+
+    def _member_of(self, node):
+        for j, net in enumerate(self.networks):
+            if any(node is n for n in net.main_nodes):
+                return j, net
+        raise ValueError("Node not found in any network")
+
+    @staticmethod
+    def _slice_for(net, x):
+        """Leading feature columns each member sees (reference network.py:1012)."""
+        def cut(t, node):
+            f = node.tensor.shape[1] if node.tensor.dim() > 1 else t.shape[1]
+            return t if t.shape[1] == f else t[:, :f]
+        if isinstance(x, (list, tuple)):
+            raise NotImplementedError("SumOfNetworks takes one matrix shared by all members")
+        feats = {n.tensor.shape[1] for n in net.input_nodes}
+        if len(feats) != 1:
+            raise NotImplementedError("members whose inputs differ in width")
+        return cut(x, net.input_nodes[0])
+
+    def _member_width(self, net):
+        s = net._plan()[0] if not hasattr(net, "_rank") else None
+        if s is not None:
+            return net._phys_size(s)
+        return net._plan()[0].dim_size("p")
+
+    def _member_input(self, net, x):
+        f = self._member_width(net)
+        return x if x.shape[1] == f else x[:, :f]
+
+    def forward(self, x, to_tensor=False):
+        y = None
+        for net in self.networks:
+            yj = net._chain_forward(self._member_input(net, x))
+            y = yj if y is None else y + yj
+        out_labels = [l for l in self.output_labels if l != self.sample_dim]
+        if not out_labels:
+            y = y[:, 0]
+        return y if to_tensor else TensorNode(y, [self.sample_dim] + out_labels, name="O")
+
+    def reset_stacks(self, node=None):
+        for net in self.networks:
+            net.reset_stacks()
+        self._member_pred = {}
+
+    def set_input(self, x):
+        key = self._key_of(x)
+        if key == self._data_key:
+            return False
+        self._data_key = key
+        self._data = (x, [self._member_input(net, x) for net in self.networks])
+        for net, xj in zip(self.networks, self._data[1]):
+            net.set_input(xj)
+        self._member_pred = {}
+        return True
+
+    def _require_cuda(self, dev):
+        for net in self.networks:
+            net._require_cuda(dev)
+
+    def _update_node(self, node, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss):
+        j, net = self._member_of(node)
+        xs = self._data[1]
+        offset = None
+        for i, other in enumerate(self.networks):
+            if i == j:
+                continue
+            stamp = other._stamp() if hasattr(other, "_stamp") else None
+            cached = self._member_pred.get(i)
+            if cached is None or cached[0] != stamp:
+                cached = (stamp, other._chain_forward(xs[i]))
+                self._member_pred[i] = cached
+            offset = cached[1] if offset is None else offset + cached[1]
+        net.process_group, net.shard_offset, net.shard_total = self.process_group, self.shard_offset, self.shard_total
+        net.gram_mode = self.gram_mode
+        net._yhat_offset = offset
+        try:
+            return net._one_update(net.main_nodes.index(node), y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm,
+                                   need_loss)
+        finally:
+            net._yhat_offset = None
+
+    def orthonormalize_left(self):
+        for net in self.networks:
+            net.orthonormalize_left()
+
+    def orthonormalize_right(self):
+        for net in self.networks:
+            net.orthonormalize_right()
+
+    def node_orthonormalize_left(self, node):
+        self._member_of(node)[1].node_orthonormalize_left(node)
+
+    def node_orthonormalize_right(self, node):
+        self._member_of(node)[1].node_orthonormalize_right(node)
+
+    def get_A_b(self, node, grad=None, hessian=None, method=None, y=None, loss_fn=None):
+        return self._member_of(node)[1].get_A_b(node, grad, hessian, method=method, y=y, loss_fn=loss_fn)
+
+    def lanczos_swipe(self, *a, **k):
+        raise NotImplementedError("matrix-free sweeps over a SumOfNetworks")
+
+    scipy_swipe = lanczos_swipe
