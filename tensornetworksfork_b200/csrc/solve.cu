@@ -6,6 +6,7 @@
 // below is a small GEMM with the inverted block, trailing updates are SYRK tiles (64x64 inside an
 // outer panel, 128x128 with K = outer panel width for the rest, so the C-tile read-modify-write is
 // amortised over a long K).  P ranges from 4 to 41 876 (14 GB) on the named configurations.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace tn {
@@ -443,7 +444,13 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
         configured = true;
     }
     TN_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
-    const int64_t NBO = (P > 4096) ? 256 : ((P > 1024) ? 128 : CH_NB);
+    // outer panel width: wider panels amortise the read-modify-write of the trailing matrix (measured at P = 41 876:
+    // 256 -> 1385 ms, 512 -> 1210 ms, 768 -> 1140 ms, 1024 -> 1125 ms)
+    int64_t NBO = (P > 16384) ? 768 : ((P > 8192) ? 512 : ((P > 4096) ? 256 : ((P > 1024) ? 128 : CH_NB)));
+    if (const char* e = getenv("TN_CHOL_NBO")) {
+        const int v = atoi(e);
+        if (v >= CH_NB && v % CH_NB == 0) NBO = v;
+    }
     for (int64_t J = 0; J < P; J += NBO) {
         const int64_t Jend = (J + NBO < P) ? J + NBO : P;
         for (int64_t j = J; j < Jend; j += CH_NB) {
@@ -457,8 +464,13 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
                 count_launch();
                 if (j + nb < Jend) {
                     const int64_t c0 = j + nb;
-                    dim3 grid((unsigned)ceil_div64(Jend - c0, 64), (unsigned)ceil_div64(P - c0, 64));
-                    syrk_update_kernel<64><<<grid, 256, 0, st>>>(A, lda, P, c0, Jend, j, nb, info);
+                    if (nb % DS_KC == 0 && lda % 2 == 0 && Jend - c0 >= DS_BT && P - c0 > 2048 && !getenv("TN_CHOL_INNER_FMA")) {
+                        dim3 grid((unsigned)ceil_div64(Jend - c0, DS_BT), (unsigned)ceil_div64(P - c0, DS_BT));
+                        syrk_update_dmma_kernel<<<grid, 256, kDmmaSmem, st>>>(A, lda, P, c0, Jend, j, nb, info);
+                    } else {
+                        dim3 grid((unsigned)ceil_div64(Jend - c0, 64), (unsigned)ceil_div64(P - c0, 64));
+                        syrk_update_kernel<64><<<grid, 256, 0, st>>>(A, lda, P, c0, Jend, j, nb, info);
+                    }
                     count_launch();
                 }
             }
