@@ -13,7 +13,8 @@ from sklearn.base import BaseEstimator, RegressorMixin
 from sklearn.metrics import accuracy_score, r2_score, root_mean_squared_error
 
 from ..tensor.bregman import SquareBregFunction
-from ..tensor.layers import CPDLayer, CumSumLayer, TensorTrainLayer
+from ..tensor.layers import CPDLayer, CumSumLayer, TensorNetworkLayer, TensorTrainLayer
+from ..tensor.network import SumOfNetworks
 
 
 def root_mean_squared_error_torch(y_true, y_pred):
@@ -103,7 +104,21 @@ class TensorTrainRegressor(BaseEstimator, RegressorMixin):
             raise ValueError("input_dim must be set")
         mt = self.model_type
         if "type1" in mt or "typeI" in mt:
-            raise NotImplementedError("type-I (sum of networks) models are a 'next' row of the scope table (SURVEY.md §8f)")
+            # sum of models with 1..N cores; members after the first do not see the bias column (reference :138-176)
+            def member(i):
+                f = self.input_dim - 1 if i != 1 else self.input_dim
+                if mt.startswith("cpd"):
+                    return CPDLayer(i, self.r, f, output_shape=self.output_dim, perturb=self.perturb, seed=self.seed + i)
+                cls = CumSumLayer if self.cum_sum else TensorTrainLayer
+                return cls(i, bond_dim=self.r, input_features=f, output_shape=self.output_dim, constrict_bond=self.constrict_bond,
+                           perturb=self.perturb, seed=self.seed + i)
+            if self.linear_dim is not None:
+                raise NotImplementedError("linear-projection layers are a 'next' row of the scope table (SURVEY.md §8f)")
+            nets = [member(i).tensor_network for i in range(1, self.N + 1)]
+            self._model = TensorNetworkLayer(SumOfNetworks(nets, output_labels=nets[0].output_labels,
+                                                           train_operators=self.train_operator)).to(self.device)
+            self._model.tensor_network.gram_mode = self.gram_mode
+            return
         if self.linear_dim is not None:
             raise NotImplementedError("linear-projection layers are a 'next' row of the scope table (SURVEY.md §8f)")
         if mt.startswith("cpd"):

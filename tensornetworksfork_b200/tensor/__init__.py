@@ -1,5 +1,5 @@
 from .node import TensorNode  # noqa: F401
-from .network import TensorNetwork, MappedInput, sweep_schedule  # noqa: F401
+from .network import TensorNetwork, SumOfNetworks, MappedInput, sweep_schedule  # noqa: F401
 from .cpd import CPDNetwork  # noqa: F401
 from .layers import (TensorNetworkLayer, TensorTrainLayer, CPDLayer, MainNodeLayer, InputNodeLayer,  # noqa: F401
                      TensorTrainDMRGInfiLayer, CumSumLayer)
