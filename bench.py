@@ -1,5 +1,8 @@
 #!/usr/bin/env python
-"""Benchmark of the per-site Gauss-Newton / ALS sweep (BASELINE.json metric: GN site-updates/s).
+"""Benchmark of the per-site Gauss-Newton / ALS sweep (BASELINE.json metric: GN site-updates/s and samples/s per sweep).
+
+``value`` is sample-site updates per second (rows x site updates / s) -- the whole-job aggregate that grows with the number
+of GPUs under weak scaling; ``site_updates_per_s`` is reported beside it.
 
     python bench.py --gpus N --steps K --warmup W [--workload cfg5a] [--rows ROWS_PER_GPU] [--gram-mode tf32x3]
     python bench.py --impl reference ...        # the reference's algorithm on the host cores (oracle port)
@@ -207,6 +210,10 @@ def bench_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    # libraries (NCCL prints its version banner) must not pollute stdout: rank 0 prints exactly ONE JSON line at the end
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the B200 path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -259,7 +266,8 @@ def bench_b200(args):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
     updates = counter[0]
-    value = updates / (ms / 1e3)
+    site_rate = updates / (ms / 1e3)               # site updates per second (does not grow with N under weak scaling)
+    value = site_rate * n * world                  # sample-site updates per second: the whole-job aggregate
 
     # ---- end to end: host (pinned) buffers in, loss scalar out, copies inside the timed region
     e2e = None
@@ -287,7 +295,8 @@ def bench_b200(args):
         dt = torch.tensor([time.perf_counter() - t0], device=dev)
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": counter2[0] / float(dt.item()), "unit": "site-updates/s",
+        e2e = {"value": counter2[0] / float(dt.item()) * n * world, "unit": "sample-site-updates/s",
+               "site_updates_per_s": counter2[0] / float(dt.item()),
                "h2d_bytes_per_step": int(Xh.numel() * 8 + yh.numel() * 8), "d2h_bytes_per_step": 8}
 
     if rank != 0:
@@ -338,18 +347,22 @@ def bench_b200(args):
     solve_info = {"kernel": "cholesky_solve[fp64]", "tflops": chol_flops / (sum(chol_ms) / 1e3) / 1e12 if chol_ms else None,
                   "share_of_step": sum(chol_ms) / ms, "peak": measured["fp64_tflops_sustained"] if measured else 35.5}
     shares = {k: sum(v) / ms for k, v in tot.items()}
-    out = {"metric": "gn_site_updates_per_s", "value": value, "unit": "site-updates/s", "n_gpus": world, "steps": args.steps,
+    out = {"metric": "gn_sample_site_updates_per_s", "value": value, "unit": "sample-site-updates/s", "site_updates_per_s": site_rate,
+           "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "f64" if args.gram_mode == "fp64" else f"f64+{args.gram_mode}", "data": "synthetic",
            "config": {"workload": f"{args.workload}: {wl['desc']}", "rows_per_gpu": n, "rows_total": n * world,
                       "site_updates_per_step": updates // max(args.steps, 1), "gram_mode": args.gram_mode, "eps": args.eps,
                       "l2": "inputs larger than L2 (per-site streams of rows*(r_l+f+r_r)*8 B)", "parallelism": f"sample-shard x{world}"},
-           "samples_per_s": value * n * world, "roofline": roofline, "solve": solve_info, "kernel_time_share": shares,
+           "roofline": roofline, "solve": solve_info, "kernel_time_share": shares,
            "gpu_launches": launches,
            "clocks": clk, "e2e": e2e}
     if not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(args, wl, n * world)
-    print(json.dumps(out))
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    print(json.dumps(out), flush=True)
+    os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
@@ -408,8 +421,8 @@ def cpu_baseline(args, wl, rows_total):
     t_batch, t_solve, n = cpu_site_time(wl, rows)
     per_sweep_sites = max(2 * n - 2, 1)
     t_all_sites = t_batch * (rows_total / rows) + t_solve     # every site once
-    value = n / t_all_sites
-    return {"value": value, "unit": "site-updates/s", "cores": os.cpu_count(), "kind": "port",
+    value = n / t_all_sites * rows_total
+    return {"value": value, "unit": "sample-site-updates/s", "site_updates_per_s": n / t_all_sites, "cores": os.cpu_count(), "kind": "port",
             "sample": f"oracle port (numpy/BLAS, all host threads): env + Jacobian + Gram + rhs of every site on one {rows}-row "
                       f"minibatch ({t_batch:.2f} s) plus the dense solves with P<=4096 ({t_solve:.2f} s; larger P not timed, "
                       f"which favours the CPU); per-row cost extrapolated linearly to {rows_total} rows"}
@@ -429,17 +442,18 @@ def bench_reference(args):
     vals = []
     for _ in range(args.steps):
         t_batch, t_solve, ns = cpu_site_time(wl, rows)
-        vals.append(ns / (t_batch * (n / rows) + t_solve))
+        vals.append(ns / (t_batch * (n / rows) + t_solve) * n)
     wall = time.perf_counter() - t0
     value = float(np.median(vals))
     sample = (f"oracle port of tensor/network.py (numpy/BLAS, {os.cpu_count()} host threads): per step, env+Jacobian+Gram+rhs of every "
               f"site on one {rows}-row minibatch and the dense solves with P<=4096, extrapolated linearly to {n} rows")
-    out = {"impl": "reference", "metric": "gn_site_updates_per_s", "value": value, "unit": "site-updates/s", "n_gpus": world,
+    out = {"impl": "reference", "metric": "gn_sample_site_updates_per_s", "value": value, "unit": "sample-site-updates/s",
+           "site_updates_per_s": value / n, "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
            "config": {"workload": f"{args.workload}: {wl['desc']}", "rows_total": n},
-           "cpu_baseline": {"value": value, "unit": "site-updates/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
-           "e2e": {"value": value, "unit": "site-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+           "cpu_baseline": {"value": value, "unit": "sample-site-updates/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+           "e2e": {"value": value, "unit": "sample-site-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
 
 
