@@ -42,6 +42,7 @@ struct TcFactor {
 };
 
 struct TcParams {
+    const unsigned long long* amax;   // max |fa|, |fb|, |fc|, |w| (bit patterns), see tc_absmax_kernel
     const float* Z;      // staged factors, feature-major: rows [w*fa (mA) | fa (mA) | fb (mB) | fc (mC)], each zpitch floats
     int64_t zpitch;      // floats per row of Z (rows rounded up to TC_KC, zero padded)
     int mA, mB, mC;
@@ -144,11 +145,51 @@ __device__ __forceinline__ void store_split(float4 v, uint32_t hi_addr, uint32_t
     if (SPLIT) sts128(lo_addr, make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w));
 }
 
+// ---- range scaling.  The operands are staged in fp32; factors of long chains span hundreds of binades (environments of a
+//      normalised 90-site train are ~1e-30), so each factor (and the weights) is scaled by a power of two to magnitude
+//      O(1) before the conversion, and the drain multiplies the result back: M = 2^(2(ea+eb+ec)+ew) * M_scaled, exactly.
+//      amax[0..3] = max |fa|, |fb|, |fc|, |w| (as ordered uint bit patterns of non-negative doubles).
+__global__ void __launch_bounds__(256)
+tc_absmax_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict__ w, int64_t rows, unsigned long long* __restrict__ amax) {
+    const int mA = fa.m, mB = fb.m, mC = fc.m;
+    const int msum = mA + mB + mC + 1;
+    double loc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int64_t total = rows * msum;
+    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = idx / msum;
+        const int i = (int)(idx - s * msum);
+        double v;
+        int which;
+        if (i < mA) { v = map_eval(fa.map_kind, fa.ptr + (fa.div == 1 ? s : s / fa.div) * fa.ld, i); which = 0; }
+        else if (i < mA + mB) { v = map_eval(fb.map_kind, fb.ptr + (fb.div == 1 ? s : s / fb.div) * fb.ld, i - mA); which = 1; }
+        else if (i < mA + mB + mC) { v = map_eval(fc.map_kind, fc.ptr + (fc.div == 1 ? s : s / fc.div) * fc.ld, i - mA - mB); which = 2; }
+        else { v = w ? w[s] : 1.0; which = 3; }
+        loc[which] = fmax(loc[which], fabs(v));
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        double v = loc[q];
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+        if ((threadIdx.x & 31) == 0 && v > 0.0) atomicMax(&amax[q], (unsigned long long)__double_as_longlong(v));
+    }
+}
+
+// exponent e such that x * 2^-e is in [0.5, 1) (0 for x == 0, inf or nan)
+__device__ __forceinline__ int tc_exponent(unsigned long long bits) {
+    const double x = __longlong_as_double((long long)bits);
+    if (!(x > 0.0) || isinf(x)) return 0;
+    int e;
+    frexp(x, &e);
+    return e;
+}
+
 // ---- pre-pass: factors (fp64, sample-major, possibly mapped / shared by V rows) -> Z (fp32, feature-major)
 __global__ void __launch_bounds__(256)
 tc_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict__ w, int64_t rows, float* __restrict__ Z,
-                int64_t zpitch) {
+                int64_t zpitch, const unsigned long long* __restrict__ amax) {
     __shared__ float tile[32][33];
+    const double sa = ldexp(1.0, -tc_exponent(amax[0])), sb = ldexp(1.0, -tc_exponent(amax[1]));
+    const double sc = ldexp(1.0, -tc_exponent(amax[2])), sw = ldexp(1.0, -tc_exponent(amax[3]));
     const int mA = fa.m, mB = fb.m, mC = fc.m;
     const int msum = mA + mB + mC;
     const int64_t s0 = (int64_t)blockIdx.x * 32;
@@ -163,7 +204,7 @@ tc_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict_
             const TcFactor& f = (i < mA) ? fa : ((i < mA + mB) ? fb : fc);
             const int il = (i < mA) ? i : ((i < mA + mB) ? i - mA : i - mA - mB);
             const int64_t ri = (f.div == 1) ? s : s / f.div;
-            v = (float)map_eval(f.map_kind, f.ptr + ri * f.ld, il);
+            v = (float)(map_eval(f.map_kind, f.ptr + ri * f.ld, il) * ((i < mA) ? sa : ((i < mA + mB) ? sb : sc)));
         }
         tile[r][tx] = v;
     }
@@ -175,7 +216,7 @@ tc_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict_
         if (i < msum && s < zpitch) {
             const float v = tile[tx][c];
             Z[(int64_t)(mA + i) * zpitch + s] = v;
-            if (i < mA) Z[(int64_t)i * zpitch + s] = (s < rows) ? v * (float)(w ? w[s] : 1.0) : 0.f;
+            if (i < mA) Z[(int64_t)i * zpitch + s] = (s < rows) ? v * (float)((w ? w[s] : 1.0) * sw) : 0.f;
         }
     }
 }
@@ -196,7 +237,8 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* r) {
 // split the columns.  tcgen05.ld hands every lane one ROW; the 32x32 block is transposed through a padded shared
 // scratch so that each RED instruction adds 32 consecutive doubles of one row of M (coalesced) instead of 32 rows.
 __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_total, int BN, int warp, int lane, int64_t u0,
-                                               int64_t nU, int v0, int nC, double* __restrict__ M, float* __restrict__ scratch) {
+                                               int64_t nU, int v0, int nC, double* __restrict__ M, float* __restrict__ scratch,
+                                               double unscale) {
     const int q = warp & 3;
     const int half = (warp - 1) >> 2;
     const int ngroups = (cols_total + 31) / 32;
@@ -217,7 +259,7 @@ __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_tota
         double* dst = M + gu0 * nC + gv;
 #pragma unroll 4
         for (int rr = 0; rr < 32; ++rr) {
-            if (col_ok && gu0 + rr < nU) atomicAdd(dst + (int64_t)rr * nC, (double)sc[rr * 33 + lane]);
+            if (col_ok && gu0 + rr < nU) atomicAdd(dst + (int64_t)rr * nC, unscale * (double)sc[rr * 33 + lane]);
         }
         __syncwarp();
     }
@@ -326,6 +368,8 @@ gram_tc_kernel(TcParams p) {
     } else {
         // =============================== producers / epilogue ===============================
         const int pt = tid - 32;  // 0..255
+        const double unscale = ldexp(1.0, 2 * (tc_exponent(p.amax[0]) + tc_exponent(p.amax[1]) + tc_exponent(p.amax[2])) +
+                                              tc_exponent(p.amax[3]));
         const uint32_t raw_s = smem_u32(raw_base);
         const uint32_t zero_row = z_rows * TC_KCP * 4;                 // byte offset of the zero row in a raw slot
         // -- rows of the operand tiles this thread synthesises (fixed for the kernel)
@@ -430,7 +474,7 @@ gram_tc_kernel(TcParams p) {
                 mbar_wait(acc_full, acc_phase);
                 acc_phase ^= 1;
                 tc_fence_after();
-                drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, reinterpret_cast<float*>(stage_base));
+                drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, reinterpret_cast<float*>(stage_base), unscale);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty);
@@ -494,12 +538,34 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     // ---- pre-pass: Z = [w*fa | fa | fb | fc] feature-major fp32, rows zero padded to a multiple of TC_KC
     p.zpitch = ceil_div64(rows, TC_KC) * TC_KC;
     const int z_rows = 2 * A.m + B.m + C.m;
+    {   // keep freed scratch in the stream-ordered pool: the default threshold (0) returns it to the OS at every sync,
+        // which made each call pay a fresh multi-hundred-MB allocation
+        static bool pool_ready = false;
+        if (!pool_ready) {
+            int dev = 0;
+            cudaMemPool_t pool;
+            TN_CUDA(cudaGetDevice(&dev));
+            TN_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+            unsigned long long keep = ~0ull;
+            TN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+            pool_ready = true;
+        }
+    }
     float* Z = nullptr;
-    TN_CUDA(cudaMallocAsync(&Z, (size_t)z_rows * p.zpitch * sizeof(float), st));
+    const size_t z_bytes = (size_t)z_rows * p.zpitch * sizeof(float);
+    TN_CUDA(cudaMallocAsync(&Z, z_bytes + 64, st));
+    unsigned long long* amax = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(Z) + z_bytes);
+    TN_CUDA(cudaMemsetAsync(amax, 0, 4 * sizeof(unsigned long long), st));
     p.Z = Z;
+    p.amax = amax;
     {
+        int64_t blocks = ceil_div64(rows * (A.m + B.m + C.m + 1), 256 * 8);
+        if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+        if (blocks < 1) blocks = 1;
+        tc_absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, B, C, w, rows, amax);
+        TN_LAUNCH_CHECK();
         dim3 grid((unsigned)ceil_div64(p.zpitch, 32), (unsigned)ceil_div64(A.m + B.m + C.m, 32));
-        tc_stage_kernel<<<grid, 256, 0, st>>>(A, B, C, w, rows, Z, p.zpitch);
+        tc_stage_kernel<<<grid, 256, 0, st>>>(A, B, C, w, rows, Z, p.zpitch, amax);
         TN_LAUNCH_CHECK();
     }
     const int64_t gx = ceil_div64(nU, (int64_t)TC_M * p.T), gy = ceil_div64(p.nC, p.BN);

@@ -100,3 +100,15 @@ def test_sweep_in_3xtf32_tracks_fp64_sweep():
     for a, b in zip(out["tf32x3"][0], out["fp64"][0]):
         assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (a, b)
     assert gu.relerr(out["tf32x3"][1].cpu().numpy(), out["fp64"][1].cpu().numpy()) < 1e-5
+
+
+def test_tc_gram_wide_dynamic_range():
+    """Factors of long normalised chains are tiny (1e-30) or large; the fp32 staging is range-scaled by powers of two."""
+    fa, fb, fc, w, rows = make(4000, 12, 3, 12, 1, seed=77)
+    fa = Factor(fa.tensor * 1e-28, m=12)
+    fc = Factor(fc.tensor * 3e17, m=12)
+    w = w.abs() * 1e-9
+    ref = ops.gram(ops.GRAM_FP64, fa, fb, fc, w, rows)
+    got = ops.gram(ops.GRAM_TF32X3, fa, fb, fc, w, rows)
+    assert torch.isfinite(got).all()
+    assert gu.relerr(got.cpu().numpy(), ref.cpu().numpy()) < 3e-5
