@@ -173,6 +173,69 @@ kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
     }
 }
 
+// Right-hand side for small cores (P <= 4096): up to four entries of b per thread, rows streamed through shared memory in tiles.
+// The GEMM-shaped kernel above wastes most of its 128 x 64 tile when P is a few hundred.
+constexpr int RS_ROWS = 64;
+constexpr int RS_PER = 4;     // entries of b per thread
+constexpr int RS_MAXP = 1024 * RS_PER;
+__global__ void __launch_bounds__(1024)
+rhs_small_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restrict__ w, int64_t rows, double* __restrict__ out,
+                 int64_t rows_per_cta) {
+    extern __shared__ double sm[];
+    const int stA = fa.m | 1, stB = fb.m | 1, stC = fc.m | 1;
+    double* sA = sm;
+    double* sB = sA + RS_ROWS * stA;
+    double* sC = sB + RS_ROWS * stB;
+    double* sW = sC + RS_ROWS * stC;
+    const int P = fa.m * fb.m * fc.m;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int ia[RS_PER], ib[RS_PER], ic[RS_PER];      // up to RS_PER entries of b per thread: i = tid + q * blockDim
+    double acc[RS_PER];
+#pragma unroll
+    for (int q = 0; q < RS_PER; ++q) {
+        const int i = min(tid + q * nt, P - 1);
+        ic[q] = i % fc.m;
+        ib[q] = (i / fc.m) % fb.m;
+        ia[q] = i / (fc.m * fb.m);
+        acc[q] = 0.0;
+    }
+    const int64_t k_begin = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t k_end = min(rows, k_begin + rows_per_cta);
+    for (int64_t kb = k_begin; kb < k_end; kb += RS_ROWS) {
+        __syncthreads();
+        for (int idx = tid; idx < RS_ROWS * fa.m; idx += nt) {
+            const int k = idx / fa.m, i = idx - k * fa.m;
+            const int64_t row = kb + k;
+            sA[k * stA + i] = (row < k_end) ? map_eval(fa.map_kind, fa.ptr + (fa.div == 1 ? row : row / fa.div) * fa.ld, i) : 0.0;
+        }
+        for (int idx = tid; idx < RS_ROWS * fb.m; idx += nt) {
+            const int k = idx / fb.m, i = idx - k * fb.m;
+            const int64_t row = kb + k;
+            sB[k * stB + i] = (row < k_end) ? map_eval(fb.map_kind, fb.ptr + (fb.div == 1 ? row : row / fb.div) * fb.ld, i) : 0.0;
+        }
+        for (int idx = tid; idx < RS_ROWS * fc.m; idx += nt) {
+            const int k = idx / fc.m, i = idx - k * fc.m;
+            const int64_t row = kb + k;
+            sC[k * stC + i] = (row < k_end) ? map_eval(fc.map_kind, fc.ptr + (fc.div == 1 ? row : row / fc.div) * fc.ld, i) : 0.0;
+        }
+        for (int k = tid; k < RS_ROWS; k += nt) {
+            const int64_t row = kb + k;
+            sW[k] = (row < k_end) ? (w ? w[row] : 1.0) : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int k = 0; k < RS_ROWS; ++k) {
+            const double wk = sW[k];
+#pragma unroll
+            for (int q = 0; q < RS_PER; ++q)
+                acc[q] = fma(wk * sA[k * stA + ia[q]], sB[k * stB + ib[q]] * sC[k * stC + ic[q]], acc[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < RS_PER; ++q)
+        if (tid + q * nt < P) out[(int64_t)blockIdx.x * P + tid + q * nt] = acc[q];
+}
+
 __global__ void reduce_splits_kernel(const double* __restrict__ work, double* __restrict__ dst, int64_t n, int ksplit,
                                      int accumulate) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -372,7 +435,15 @@ extern "C" int tn_gram_ksplit(int64_t rows, int ma, int mb, int mc, int mode) {
     return choose_ksplit(rows, (int64_t)npairs(ma) * npairs(mb), npairs(mc));
 }
 
+static int rhs_small_ctas(int64_t rows) {
+    int64_t n = tn::ceil_div64(rows, 8 * tn::RS_ROWS);
+    const int64_t cap = 2LL * tn::sm_count();
+    if (n > cap) n = cap;
+    return (int)(n < 1 ? 1 : n);
+}
+
 extern "C" int tn_rhs_ksplit(int64_t rows, int ma, int mb, int mc) {
+    if ((int64_t)ma * mb * mc <= tn::RS_MAXP) return rhs_small_ctas(rows);      // small-core kernel: one partial per CTA
     return tn::choose_ksplit(rows, (int64_t)ma * mb, mc);
 }
 
@@ -396,6 +467,29 @@ extern "C" int tn_rhs_kr3(const tn_factor* fa, const tn_factor* fb, const tn_fac
     using namespace tn;
     TN_CHECK_ARG(fa && fb && fc && b, "tn_rhs_kr3: null argument");
     TN_CHECK_ARG(rows >= 0, "tn_rhs_kr3: negative rows");
+    const int64_t P = (int64_t)fa->m * fb->m * fc->m;
+    if (P <= RS_MAXP) {
+        const FactorDev a = to_dev(fa), bb = to_dev(fb), c = to_dev(fc);
+        const int ctas = rhs_small_ctas(rows);
+        TN_CHECK_ARG(ksplit == ctas && work != nullptr, "tn_rhs_kr3: small-core path needs work for %d partials (got ksplit=%d)", ctas, ksplit);
+        const int64_t rpc = ceil_div64(ceil_div64(rows, ctas), RS_ROWS) * RS_ROWS;
+        int threads = (int)((ceil_div64(P, RS_PER) + 31) / 32) * 32;
+        if (threads < 128) threads = 128;
+        if (threads > 1024) threads = 1024;
+        const size_t smem = (size_t)RS_ROWS * ((a.m | 1) + (bb.m | 1) + (c.m | 1) + 1) * sizeof(double);
+        TN_CHECK_ARG(smem <= 200 * 1024, "tn_rhs_kr3: factors too wide for the small-core path");
+        static size_t configured = 0;
+        if (smem > configured) {
+            TN_CUDA(cudaFuncSetAttribute(rhs_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            configured = smem;
+        }
+        rhs_small_kernel<<<ctas, threads, smem, as_stream(stream)>>>(a, bb, c, w, rows, work, rpc);
+        TN_LAUNCH_CHECK();
+        int64_t blocks = ceil_div64(P, 256);
+        reduce_splits_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(work, b, P, ctas, accumulate);
+        TN_LAUNCH_CHECK();
+        return TN_OK;
+    }
     return launch_kr3<0>(fa, fb, fc, w, rows, b, work, ksplit, accumulate, as_stream(stream));
 }
 

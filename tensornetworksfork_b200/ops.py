@@ -142,7 +142,7 @@ def rhs(fa: Factor, fb: Factor, fc: Factor, w, rows, b=None, accumulate=False):
         b = torch.empty((n,), dtype=torch.float64, device=dev)
         accumulate = False
     ks = lib.tn_rhs_ksplit(rows, fa.m, fb.m, fc.m)
-    work = torch.empty((ks * n,), dtype=torch.float64, device=dev) if (ks > 1 or accumulate) else None
+    work = torch.empty((ks * n,), dtype=torch.float64, device=dev) if (ks > 1 or accumulate or n <= 4096) else None
     a, bb, c = fa.c(), fb.c(), fc.c()
     rc = lib.tn_rhs_kr3(ctypes.byref(a), ctypes.byref(bb), ctypes.byref(c), _p(w), rows, _p(b), _p(work), ks,
                         1 if accumulate else 0, _stream())
