@@ -7,6 +7,7 @@
 // outer panel, 128x128 with K = outer panel width for the rest, so the C-tile read-modify-write is
 // amortised over a long K).  P ranges from 4 to 41 876 (14 GB) on the named configurations.
 #include <stdlib.h>
+#include <cooperative_groups.h>
 #include "common.cuh"
 
 namespace tn {
@@ -18,51 +19,48 @@ constexpr int CH_NB = 64;
 // (no block barriers in the 64-step dependency chain).  Inversion: all 8 warps, 4 lanes per column of
 // L^{-1}; lane l keeps the entries x[q], q = l (mod 4), of its column in registers, so a row step is a
 // 16-term dot product, two shuffles and a divide.
-__global__ void __launch_bounds__(256)
-potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t j, int nb, double* __restrict__ Linv, int* __restrict__ info) {
-    extern __shared__ double dsm[];
+__device__ void potrf_diag_body(double* __restrict__ A, int64_t lda, int64_t j, int nb, double* __restrict__ Linv,
+                                int* __restrict__ info, double* dsm) {
     double (*a)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(dsm);
     __shared__ int bad;
+    __shared__ double s_piv;
+    __shared__ double s_rdiag[CH_NB];
     if (*info != 0) return;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
     if (tid == 0) bad = 0;
     for (int idx = tid; idx < CH_NB * CH_NB; idx += 256) {
         const int r = idx >> 6, c = idx & 63;
         a[r][c] = (r < nb && c <= r) ? A[(j + r) * lda + j + c] : ((r == c) ? 1.0 : 0.0);   // identity padding
     }
     __syncthreads();
-    if (warp == 0) {
-        const int r0 = lane, r1 = lane + 32;
-        int fail = 0;
+    // ---- factorisation, left-looking: thread (r, l) owns a quarter of row r's dot product
+    {
+        const int r = tid >> 2, l = tid & 3;
         for (int c = 0; c < nb; ++c) {
-            // v[r] = a[r][c] - sum_{t<c} L[r][t] L[c][t]   for this lane's rows r >= c
-            double s0 = 0.0, s1 = 0.0, t0 = 0.0, t1 = 0.0;
-            int t = 0;
-            for (; t + 1 < c; t += 2) {
-                const double l0 = a[c][t], l1 = a[c][t + 1];
-                s0 = fma(a[r0][t], l0, s0); t0 = fma(a[r0][t + 1], l1, t0);
-                s1 = fma(a[r1][t], l0, s1); t1 = fma(a[r1][t + 1], l1, t1);
+            double s0 = 0.0, s1 = 0.0;
+            int t = l;
+            for (; t + 4 < c; t += 8) {
+                s0 = fma(a[r][t], a[c][t], s0);
+                s1 = fma(a[r][t + 4], a[c][t + 4], s1);
             }
-            if (t < c) {
-                const double l0 = a[c][t];
-                s0 = fma(a[r0][t], l0, s0);
-                s1 = fma(a[r1][t], l0, s1);
-            }
-            const double v0 = a[r0][c] - (s0 + t0), v1 = a[r1][c] - (s1 + t1);
-            const double d = __shfl_sync(0xffffffffu, (c < 32) ? v0 : v1, c & 31);
-            if (!(d > 0.0)) {   // also catches NaN; uniform across the warp
-                fail = c + 1;
+            if (t < c) s0 = fma(a[r][t], a[c][t], s0);
+            double sd = s0 + s1;
+            sd += __shfl_xor_sync(0xffffffffu, sd, 1);
+            sd += __shfl_xor_sync(0xffffffffu, sd, 2);
+            const double v = a[r][c] - sd;
+            if (r == c && l == 0) s_piv = v;
+            __syncthreads();
+            const double d = s_piv;
+            if (!(d > 0.0)) {   // also catches NaN; uniform across the CTA
+                if (tid == 0) {
+                    bad = 1;
+                    *info = (int)(j + c + 1);
+                }
                 break;
             }
-            const double sd = sqrt(d);
-            __syncwarp();
-            if (r0 >= c) a[r0][c] = (r0 == c) ? sd : v0 / sd;
-            if (r1 >= c) a[r1][c] = (r1 == c) ? sd : v1 / sd;
-            __syncwarp();
-        }
-        if (fail && lane == 0) {
-            bad = 1;
-            *info = (int)(j + fail);
+            const double root = sqrt(d);
+            if (l == 0 && r >= c) a[r][c] = (r == c) ? root : v / root;
+            __syncthreads();
         }
     }
     __syncthreads();
@@ -71,26 +69,28 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t j, int nb, double
         const int r = idx / nb, c = idx % nb;
         if (c <= r) A[(j + r) * lda + j + c] = a[r][c];
     }
-    // ---- inverse: column t of X = L^{-1}, 4 lanes per column
+    if (tid < CH_NB) s_rdiag[tid] = 1.0 / a[tid][tid];
+    __syncthreads();
+    // ---- inverse: column t of X = L^{-1}, 4 lanes per column; lane l keeps x[q], q = l (mod 4), in registers
     {
         const int t = tid >> 2, l = tid & 3;
         double x[16];          // x[m] = X[4m + l][t]
 #pragma unroll
-        for (int m = 0; m < 16; ++m) x[m] = 0.0;
-#pragma unroll
-        for (int m = 0; m < 16; ++m)
-            if (4 * m + l == t) x[m] = 1.0 / a[t][t];
+        for (int m = 0; m < 16; ++m) x[m] = (4 * m + l == t) ? s_rdiag[t] : 0.0;
         for (int r = 1; r < CH_NB; ++r) {
-            double sdot = 0.0;
+            double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
 #pragma unroll
-            for (int m = 0; m < 16; ++m) {
-                const int q = 4 * m + l;
-                if (q < r) sdot = fma(a[r][q], x[m], sdot);      // x[m] is zero for q < t
+            for (int m = 0; m < 16; m += 4) {       // entries with q >= r are still zero in x, so no bound is needed... except q == r
+                s0 = fma(a[r][4 * m + l], x[m], s0);
+                s1 = fma(a[r][4 * (m + 1) + l], x[m + 1], s1);
+                s2 = fma(a[r][4 * (m + 2) + l], x[m + 2], s2);
+                s3 = fma(a[r][4 * (m + 3) + l], x[m + 3], s3);
             }
+            double sdot = (s0 + s1) + (s2 + s3);
             sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
             sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
             if (r > t) {
-                const double xr = -sdot / a[r][r];
+                const double xr = -sdot * s_rdiag[r];
 #pragma unroll
                 for (int m = 0; m < 16; ++m)
                     if (4 * m + l == r) x[m] = xr;
@@ -101,16 +101,19 @@ potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t j, int nb, double
     }
 }
 
-// ---- panel: X = B * Linv^T for the rows below the diagonal block -------------------------------
 __global__ void __launch_bounds__(256)
-trsm_panel_kernel(double* __restrict__ A, int64_t lda, int64_t j, int nb, const double* __restrict__ Linv, int64_t P,
-                  const int* __restrict__ info) {
+potrf_diag_kernel(double* __restrict__ A, int64_t lda, int64_t j, int nb, double* __restrict__ Linv, int* __restrict__ info) {
     extern __shared__ double dsm[];
+    potrf_diag_body(A, lda, j, nb, Linv, info, dsm);
+}
+
+// ---- panel: X = B * Linv^T for the rows below the diagonal block -------------------------------
+__device__ void trsm_panel_body(double* __restrict__ A, int64_t lda, int64_t j, int nb, const double* __restrict__ Linv, int64_t P,
+                                int64_t rb, double* dsm) {
     double (*b)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(dsm);
     double (*li)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(dsm + CH_NB * (CH_NB + 1));
-    if (*info != 0) return;
     const int tid = threadIdx.x;
-    const int64_t r0 = j + nb + (int64_t)blockIdx.x * CH_NB;
+    const int64_t r0 = j + nb + rb * CH_NB;
     for (int idx = tid; idx < CH_NB * CH_NB; idx += 256) {
         const int r = idx >> 6, c = idx & 63;
         const int64_t row = r0 + r;
@@ -147,18 +150,23 @@ trsm_panel_kernel(double* __restrict__ A, int64_t lda, int64_t j, int nb, const 
     }
 }
 
+__global__ void __launch_bounds__(256)
+trsm_panel_kernel(double* __restrict__ A, int64_t lda, int64_t j, int nb, const double* __restrict__ Linv, int64_t P,
+                  const int* __restrict__ info) {
+    extern __shared__ double dsm[];
+    if (*info != 0) return;
+    trsm_panel_body(A, lda, j, nb, Linv, P, blockIdx.x, dsm);
+}
+
 // ---- trailing update: C[i][q] -= sum_t A[i][k0+t] * A[q][k0+t] on the lower tiles of
 //      columns [c0, c1), rows [c0, P).  BT x BT tile per CTA, 256 threads, (BT/16)^2 per thread.
 template <int BT>
-__global__ void __launch_bounds__(256)
-syrk_update_kernel(double* __restrict__ A, int64_t lda, int64_t P, int64_t c0, int64_t c1, int64_t k0, int kb,
-                   const int* __restrict__ info) {
+__device__ void syrk_update_body(double* __restrict__ A, int64_t lda, int64_t P, int64_t c0, int64_t c1, int64_t k0, int kb,
+                                 int bi, int bj) {
     constexpr int TM = BT / 16;
     constexpr int KC = 16;
     __shared__ double sa[KC][BT + 2];
     __shared__ double sb[KC][BT + 2];
-    if (*info != 0) return;
-    const int bi = blockIdx.y, bj = blockIdx.x;
     if (bj > bi) return;  // tile strictly above the diagonal
     const int64_t r0 = c0 + (int64_t)bi * BT, q0 = c0 + (int64_t)bj * BT;
     if (r0 >= P || q0 >= c1) return;
@@ -205,6 +213,52 @@ syrk_update_kernel(double* __restrict__ A, int64_t lda, int64_t P, int64_t c0, i
             const int64_t col = q0 + tx + 16 * q;
             if (col < c1 && col <= row) A[row * lda + col] -= acc[i][q];
         }
+    }
+}
+
+template <int BT>
+__global__ void __launch_bounds__(256)
+syrk_update_kernel(double* __restrict__ A, int64_t lda, int64_t P, int64_t c0, int64_t c1, int64_t k0, int kb,
+                   const int* __restrict__ info) {
+    if (*info != 0) return;
+    syrk_update_body<BT>(A, lda, P, c0, c1, k0, kb, blockIdx.y, blockIdx.x);
+}
+
+// ---- whole factorisation in ONE cooperative launch for small systems (P <= CF_MAXP): the three phases of every
+//      64-column step are separated by grid-wide barriers instead of kernel boundaries (54 launches -> 1 at P = 1152).
+constexpr int CF_MAXP = 4096;
+__global__ void __launch_bounds__(256)
+cholesky_fused_kernel(double* __restrict__ A, int64_t lda, int P, double* __restrict__ Linv_all, int* __restrict__ info) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    extern __shared__ double dsm[];
+    const int nblk = (P + CH_NB - 1) / CH_NB;
+    for (int b = 0; b < nblk; ++b) {
+        const int64_t j = (int64_t)b * CH_NB;
+        const int nb = min(CH_NB, P - (int)j);
+        if (blockIdx.x == 0) potrf_diag_body(A, lda, j, nb, Linv_all + (size_t)b * CH_NB * CH_NB, info, dsm);
+        __threadfence();
+        grid.sync();
+        if (*reinterpret_cast<volatile int*>(info) != 0) return;      // uniform: every CTA reads the same flag after the barrier
+        const int below = P - (int)j - nb;
+        if (below <= 0) break;
+        const int nrb = (below + CH_NB - 1) / CH_NB;
+        for (int rb = blockIdx.x; rb < nrb; rb += gridDim.x) {
+            __syncthreads();
+            trsm_panel_body(A, lda, j, nb, Linv_all + (size_t)b * CH_NB * CH_NB, P, rb, dsm);
+        }
+        __threadfence();
+        grid.sync();
+        const int ntile = nrb * (nrb + 1) / 2;
+        for (int t = blockIdx.x; t < ntile; t += gridDim.x) {
+            int bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+            while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
+            while (bi * (bi + 1) / 2 > t) --bi;
+            const int bj = t - bi * (bi + 1) / 2;
+            __syncthreads();
+            syrk_update_body<64>(A, lda, P, j + nb, P, j, nb, bi, bj);
+        }
+        __threadfence();
+        grid.sync();
     }
 }
 
@@ -444,6 +498,25 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
         configured = true;
     }
     TN_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+    static int coop_ok = -1;
+    if (coop_ok < 0) {
+        int dev = 0, v = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev);
+        coop_ok = v;
+        if (v) TN_CUDA(cudaFuncSetAttribute(cholesky_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkSmem));
+    }
+    bool factored = false;
+    if (coop_ok && P <= CF_MAXP && P > CH_NB && !getenv("TN_CHOL_NO_FUSED")) {
+        int Pi = (int)P;
+        void* args[] = {(void*)&A, (void*)&lda, (void*)&Pi, (void*)&work, (void*)&info};
+        int grid = sm_count();
+        const int need = (int)(ceil_div64(P, CH_NB) * (ceil_div64(P, CH_NB) + 1) / 2);
+        if (grid > need) grid = need;
+        TN_CUDA(cudaLaunchCooperativeKernel((void*)cholesky_fused_kernel, dim3(grid), dim3(256), args, kBlkSmem, st));
+        count_launch();
+        factored = true;
+    }
     // outer panel width: wider panels amortise the read-modify-write of the trailing matrix (measured at P = 41 876:
     // 256 -> 1385 ms, 512 -> 1210 ms, 768 -> 1140 ms, 1024 -> 1125 ms)
     int64_t NBO = (P > 16384) ? 768 : ((P > 8192) ? 512 : ((P > 4096) ? 256 : ((P > 1024) ? 128 : CH_NB)));
@@ -451,7 +524,7 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
         const int v = atoi(e);
         if (v >= CH_NB && v % CH_NB == 0) NBO = v;
     }
-    for (int64_t J = 0; J < P; J += NBO) {
+    for (int64_t J = 0; J < P && !factored; J += NBO) {
         const int64_t Jend = (J + NBO < P) ? J + NBO : P;
         for (int64_t j = J; j < Jend; j += CH_NB) {
             const int nb = (int)((Jend - j < CH_NB) ? Jend - j : CH_NB);
