@@ -1,4 +1,4 @@
-// Gram build without the Jacobian: fp64 CUDA-core path, right-hand side, sigma, expansion.
+// Gram build without the Jacobian: fp64 path (FP64 tensor pipe, DMMA m8n8k4), right-hand side, sigma, expansion.
 //
 // Replaces TensorNetwork.get_A_b (reference tensor/network.py:174-217).  The local Jacobian
 // of a core is a row-wise Kronecker product J[row, (ia,ib,ic)] = fa[ia] fb[ib] fc[ic], so
@@ -15,8 +15,10 @@ namespace tn {
 
 constexpr int GR_TU = 128;      // U columns per CTA
 constexpr int GR_TV = 64;       // V columns per CTA
-constexpr int GR_KC = 16;       // rows per staged chunk
+constexpr int GR_KC = 32;       // rows per staged chunk
 constexpr int GR_THREADS = 256;
+constexpr int GR_SU = GR_TU + 4;   // padded tile rows: conflict-free DMMA fragment reads (row offset 4 doubles per k)
+constexpr int GR_SV = GR_TV + 4;
 
 struct FactorDev {
     const double* ptr;
@@ -54,9 +56,9 @@ kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
     double* sFB = sFA + GR_KC * stA;
     double* sFC = sFB + GR_KC * stB;
     double* sW = sFC + GR_KC * stC;
-    double* sU = sW + GR_KC;              // [GR_KC][GR_TU]
-    double* sV = sU + GR_KC * GR_TU;      // [GR_KC][GR_TV]
-    short* tIA = reinterpret_cast<short*>(sV + GR_KC * GR_TV);
+    double* sU = sW + GR_KC;              // [GR_KC][GR_SU]
+    double* sV = sU + GR_KC * GR_SU;      // [GR_KC][GR_SV]
+    short* tIA = reinterpret_cast<short*>(sV + GR_KC * GR_SV);
     short* tJA = tIA + GR_TU;
     short* tIB = tJA + GR_TU;
     short* tJB = tIB + GR_TU;
@@ -102,12 +104,15 @@ kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
         tIC[t] = (short)ic; tJC[t] = (short)jc; tKC[t] = (short)kc;
     }
 
-    const int tx = tid & 15, ty = tid >> 4;
-    double acc[8][4];
+    // 8 warps as 4 (u) x 2 (v): each warp owns a 32 x 32 block of the tile = 4 x 4 DMMA m8n8k4 accumulators
+    const int lane = tid & 31, warp = tid >> 5;
+    const int wu = (warp >> 1) * 32, wv = (warp & 1) * 32;
+    const int fr = lane >> 2, fk = lane & 3;
+    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     for (int64_t kb = k_begin; kb < k_end; kb += GR_KC) {
         __syncthreads();  // previous chunk's sU/sV fully consumed; tables visible on first pass
@@ -129,7 +134,7 @@ kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
                 if (MODE >= 2) v = sW[k] * a[ia] * b[tIB[u]] * sFC[k * stC + tJA[u]];
                 else v = PAIR ? sW[k] * a[ia] * a[tJA[u]] * b[tIB[u]] * b[tJB[u]] : sW[k] * a[ia] * b[tIB[u]];
             }
-            sU[idx] = v;
+            sU[k * GR_SU + u] = v;
         }
         for (int idx = tid; idx < GR_KC * GR_TV; idx += GR_THREADS) {
             const int k = idx >> 6, t = idx & (GR_TV - 1);
@@ -141,34 +146,38 @@ kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
                 else if (MODE == 3) v = 1.0;
                 else v = PAIR ? c[ic] * c[tJC[t]] : c[ic];
             }
-            sV[idx] = v;
+            sV[k * GR_SV + t] = v;
         }
         __syncthreads();
-#pragma unroll 4
-        for (int k = 0; k < GR_KC; ++k) {
-            double a[8], b[4];
-            const double2* up = reinterpret_cast<const double2*>(sU + k * GR_TU + ty * 8);
-            const double2 a0 = up[0], a1 = up[1], a2 = up[2], a3 = up[3];
-            a[0] = a0.x; a[1] = a0.y; a[2] = a1.x; a[3] = a1.y; a[4] = a2.x; a[5] = a2.y; a[6] = a3.x; a[7] = a3.y;
-            const double2 b0 = *reinterpret_cast<const double2*>(sV + k * GR_TV + 2 * tx);
-            const double2 b1 = *reinterpret_cast<const double2*>(sV + k * GR_TV + 32 + 2 * tx);
-            b[0] = b0.x; b[1] = b0.y; b[2] = b1.x; b[3] = b1.y;
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+        for (int k4 = 0; k4 < GR_KC; k4 += 4) {
+            // A fragment = U^T: a[m = u][k];  B fragment: b[k][n = v]
+            double af[4], bf[4];
+            const double* up = sU + (k4 + fk) * GR_SU + wu + fr;
+            const double* vp = sV + (k4 + fk) * GR_SV + wv + fr;
 #pragma unroll
-                for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            for (int i = 0; i < 4; ++i) af[i] = up[i * 8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = vp[j * 8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
     }
 
     double* o = out + (int64_t)blockIdx.z * nU * nC;
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int64_t gu = u0 + ty * 8 + i;
+    for (int i = 0; i < 4; ++i) {
+        const int64_t gu = u0 + wu + i * 8 + fr;
         if (gu >= nU) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const int gv = v0 + ((j < 2) ? (2 * tx + j) : (32 + 2 * tx + (j - 2)));
-            if (gv < nC) o[gu * nC + gv] = acc[i][j];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gv = v0 + wv + j * 8 + 2 * fk + e;
+                if (gv < nC) o[gu * nC + gv] = acc[i][j][e];
+            }
         }
     }
 }
@@ -273,7 +282,7 @@ static int launch_kr3(const tn_factor* fa, const tn_factor* fb, const tn_factor*
     if (rps < GR_KC) rps = GR_KC;
     const bool direct = (ksplit == 1 && !accumulate);
     TN_CHECK_ARG(direct || work != nullptr, "kr3: ksplit=%d / accumulate need a work buffer", ksplit);
-    const size_t smem = (size_t)(GR_KC * ((a.m | 1) + (b.m | 1) + (c.m | 1)) + GR_KC + GR_KC * GR_TU + GR_KC * GR_TV) * sizeof(double) +
+    const size_t smem = (size_t)(GR_KC * ((a.m | 1) + (b.m | 1) + (c.m | 1)) + GR_KC + GR_KC * GR_SU + GR_KC * GR_SV) * sizeof(double) +
                         (size_t)(4 * GR_TU + 3 * GR_TV) * sizeof(short);
     TN_CHECK_ARG(smem <= 227 * 1024, "kr3: factor sizes %d,%d,%d need %zu B of shared memory", a.m, b.m, c.m, smem);
     TN_CHECK_ARG(a.m < 32768 && b.m < 32768 && c.m < 32768, "kr3: factor too large");
