@@ -31,7 +31,7 @@ constexpr int TC_PROD_WARPS = 8;
 constexpr int TC_PROD = TC_PROD_WARPS * 32;
 constexpr int TC_THREADS = 32 + TC_PROD;
 constexpr int TC_RAW_SLOTS = 3;    // shared ring of raw-factor chunks filled by cp.async
-constexpr int TC_FLUSH_ROWS_DEFAULT = 1024;
+constexpr int TC_FLUSH_ROWS_DEFAULT = 2048;
 
 struct TcFactor {
     const double* ptr;

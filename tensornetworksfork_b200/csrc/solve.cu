@@ -273,7 +273,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 1)
+constexpr int DS_THREADS = 512;   // 16 warps as 4 x 4: warp tile 32 x 32 (four warps per scheduler hide the DMMA / LDS latency)
+__global__ void __launch_bounds__(DS_THREADS, 1)
 syrk_update_dmma_kernel(double* __restrict__ A, int64_t lda, int64_t P, int64_t c0, int64_t c1, int64_t k0, int kb,
                         const int* __restrict__ info) {
     extern __shared__ double dsm[];
@@ -283,21 +284,21 @@ syrk_update_dmma_kernel(double* __restrict__ A, int64_t lda, int64_t P, int64_t 
     const int64_t r0 = c0 + (int64_t)bi * DS_BT, q0 = c0 + (int64_t)bj * DS_BT;
     if (r0 >= P || q0 >= c1) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wm = warp >> 1, wn = warp & 1;          // 4 x 2 warps: warp tile 32 (rows) x 64 (cols)
+    const int wm = warp >> 2, wn = warp & 3;
     double* sA = dsm;                                  // [stage][128][DS_LD]
     double* sB = dsm + DS_STAGES * DS_BT * DS_LD;
 
-    double acc[4][8][2];
+    double acc[4][4][2];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    // each thread copies 4 + 4 sixteen-byte pieces per stage: piece = (row, half-pair index 0..7)
+    // each thread copies 2 + 2 sixteen-byte pieces per stage: piece = (row, half-pair index 0..7)
     auto issue = [&](int stage, int kk) {
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int piece = tid + u * 256;           // 0..1023
+        for (int u = 0; u < 2; ++u) {
+            const int piece = tid + u * DS_THREADS;    // 0..1023
             const int row = piece >> 3, part = piece & 7;
             int64_t ra = r0 + row, rb = q0 + row;
             if (ra >= P) ra = P - 1;                   // clamped rows are never stored
@@ -320,18 +321,18 @@ syrk_update_dmma_kernel(double* __restrict__ A, int64_t lda, int64_t P, int64_t 
         if (nxt < nk) issue(nxt % DS_STAGES, nxt * DS_KC);
         else asm volatile("cp.async.commit_group;" ::: "memory");
         const double* a_s = sA + ((size_t)(it % DS_STAGES) * DS_BT + wm * 32 + fr) * DS_LD + fk;
-        const double* b_s = sB + ((size_t)(it % DS_STAGES) * DS_BT + wn * 64 + fr) * DS_LD + fk;
+        const double* b_s = sB + ((size_t)(it % DS_STAGES) * DS_BT + wn * 32 + fr) * DS_LD + fk;
 #pragma unroll
         for (int k4 = 0; k4 < DS_KC; k4 += 4) {
-            double af[4], bf[8];
+            double af[4], bf[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) af[i] = a_s[(size_t)i * 8 * DS_LD + k4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) bf[j] = b_s[(size_t)j * 8 * DS_LD + k4];
+            for (int j = 0; j < 4; ++j) bf[j] = b_s[(size_t)j * 8 * DS_LD + k4];
 #pragma unroll
             for (int i = 0; i < 4; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
         }
     }
     asm volatile("cp.async.wait_group 0;" ::: "memory");
@@ -340,8 +341,8 @@ syrk_update_dmma_kernel(double* __restrict__ A, int64_t lda, int64_t P, int64_t 
         const int64_t row = r0 + wm * 32 + i * 8 + fr;
         if (row >= P) continue;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const int64_t col = q0 + wn * 64 + j * 8 + fk * 2;
+        for (int j = 0; j < 4; ++j) {
+            const int64_t col = q0 + wn * 32 + j * 8 + fk * 2;
             double* cptr = A + row * lda + col;
             if (col + 1 < c1 && col + 1 <= row) {
                 double2 v = *reinterpret_cast<double2*>(cptr);
@@ -539,7 +540,7 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
                     const int64_t c0 = j + nb;
                     if (nb % DS_KC == 0 && lda % 2 == 0 && Jend - c0 >= DS_BT && P - c0 > 2048 && !getenv("TN_CHOL_INNER_FMA")) {
                         dim3 grid((unsigned)ceil_div64(Jend - c0, DS_BT), (unsigned)ceil_div64(P - c0, DS_BT));
-                        syrk_update_dmma_kernel<<<grid, 256, kDmmaSmem, st>>>(A, lda, P, c0, Jend, j, nb, info);
+                        syrk_update_dmma_kernel<<<grid, DS_THREADS, kDmmaSmem, st>>>(A, lda, P, c0, Jend, j, nb, info);
                     } else {
                         dim3 grid((unsigned)ceil_div64(Jend - c0, 64), (unsigned)ceil_div64(P - c0, 64));
                         syrk_update_kernel<64><<<grid, 256, 0, st>>>(A, lda, P, c0, Jend, j, nb, info);
@@ -553,7 +554,7 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
             const int kbo = (int)(Jend - J);
             if (n > 512 && kbo % DS_KC == 0 && lda % 2 == 0) {
                 dim3 grid((unsigned)ceil_div64(n, DS_BT), (unsigned)ceil_div64(n, DS_BT));
-                syrk_update_dmma_kernel<<<grid, 256, kDmmaSmem, st>>>(A, lda, P, Jend, P, J, kbo, info);
+                syrk_update_dmma_kernel<<<grid, DS_THREADS, kDmmaSmem, st>>>(A, lda, P, Jend, P, J, kbo, info);
             } else if (n > 512) {
                 dim3 grid((unsigned)ceil_div64(n, 128), (unsigned)ceil_div64(n, 128));
                 syrk_update_kernel<128><<<grid, 256, 0, st>>>(A, lda, P, Jend, P, J, kbo, info);

@@ -3,7 +3,7 @@
 Stated tolerances (relative Frobenius error of the unique-entry tensor M against fp64):
   3xTF32 : <= 3e-5   products are fp32-grade (~3e-7), but tcgen05 accumulates in fp32 with TRUNCATION (measured:
                      error grows linearly with the rows accumulated between two fp64 flushes, ~7e-9 per row; 1024
-                     rows per flush by default -> ~1e-5).  The end-to-end bound that matters -- per-update loss of a
+                     rows per flush by default; 2048 in the library -> ~1.2e-5).  The end-to-end bound that matters -- per-update loss of a
                      free-running sweep within 1e-6 of the fp64 mode -- is asserted at the bottom of this file.
   TF32   : <= 2e-3
 """
@@ -112,3 +112,27 @@ def test_tc_gram_wide_dynamic_range():
     got = ops.gram(ops.GRAM_TF32X3, fa, fb, fc, w, rows)
     assert torch.isfinite(got).all()
     assert gu.relerr(got.cpu().numpy(), ref.cpu().numpy()) < 3e-5
+
+
+def test_tc_gram_config5a_site_full_width():
+    """BASELINE config-5a middle site (r=38, f=29: 741 x 435 x 741 unique entries, 1.9 GB) at 32 768 rows: the 3xTF32 tensor-core
+    Gram against the fp64 kernel, and additivity over row shards (what the multi-GPU all-reduce relies on)."""
+    S, ma, mb, mc = 32768, 38, 29, 38
+    g = torch.Generator(device=DEV).manual_seed(5)
+    Fa = torch.randn((S, ma), device=DEV, generator=g)
+    Fb = torch.rand((S, mb), device=DEV, generator=g) * 2 - 1
+    Fc = torch.randn((S, mc), device=DEV, generator=g)
+    w = torch.full((S,), 2.0, device=DEV)
+    fac = lambda lo, hi: (Factor(Fa[lo:hi], m=ma), Factor(Fb[lo:hi], m=mb), Factor(Fc[lo:hi], m=mc))
+    full = ops.gram(ops.GRAM_TF32X3, *fac(0, S), w, S)
+    ref = ops.gram(ops.GRAM_FP64, *fac(0, S), w, S)
+    err = float((full - ref).norm() / ref.norm())
+    assert err < 3e-5, err
+    half = S // 2 + 8
+    parts = ops.gram(ops.GRAM_TF32X3, *fac(0, half), w[:half], half)
+    parts = ops.gram(ops.GRAM_TF32X3, *fac(half, S), w[half:], S - half, M=parts, accumulate=True)
+    assert float((parts - ref).norm() / ref.norm()) < 3e-5
+    # the expanded system is symmetric positive semi-definite by construction: check a random Rayleigh quotient via matvec
+    v = torch.randn(ma * mb * mc, device=DEV, generator=g)
+    Av = ops.matvec(*fac(0, 4096), w[:4096], 4096, v)
+    assert float(torch.dot(v, Av)) >= 0.0
