@@ -53,6 +53,8 @@ def parse():
     ap.add_argument("--workload", default="cfg5a", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", dest="n", type=int, default=None, help="rows per GPU (default: the workload's)")
     ap.add_argument("--gram-mode", default="tf32x3", choices=["fp64", "tf32", "tf32x3"])
+    ap.add_argument("--solve-mode", default="auto", choices=["auto", "fp64", "mixed"],
+                    help="local solve: auto = tensor-core factorisation + fp64 refinement for P >= 8192 in the tf32 gram modes")
     ap.add_argument("--no-peaks", action="store_true", help="skip the cuBLAS TF32/FP64 peak measurement")
     ap.add_argument("--eps", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -170,7 +172,7 @@ class KernelTimer:
             # keep sizes only: holding the argument tensors would pin every 14 GB system matrix of the step
             if n == "gram":
                 self.extra[n].append((a[1].m, a[2].m, a[3].m, a[5]))
-            elif n == "cholesky_solve":
+            elif n in ("cholesky_solve", "cholesky_solve_mixed"):
                 self.extra[n].append(int(a[0].shape[0]))
             return out
 
@@ -224,6 +226,7 @@ def bench_b200(args):
     n = args.n if args.n is not None else wl["n"]
     layer, f = build_model(wl, dev, args.gram_mode)
     tn = layer.tensor_network
+    tn.solve_mode = args.solve_mode
     X, y = make_data(wl, n, seed=1000 + rank, device=dev)
     if world > 1:
         tn.process_group = dist.group.WORLD
@@ -233,7 +236,7 @@ def bench_b200(args):
     if wl.get("orthonormalize"):
         tn.orthonormalize_left()
 
-    timer = KernelTimer(ops, ["gram", "rhs", "env_update", "predict", "cholesky_solve", "gram_expand"])
+    timer = KernelTimer(ops, ["gram", "rhs", "env_update", "predict", "cholesky_solve", "cholesky_solve_mixed", "gram_expand"])
     timer.install()
     counter = [0]
 
@@ -342,10 +345,14 @@ def bench_b200(args):
                 "survey_equiv_tflops": algo / gsum / 1e12 if gsum > 0 else 0.0,
                 "share_of_step": gsum / (ms / 1e3), "launches": len(gram_ms), "measured_peaks": measured,
                 "bf16_peaks_file": {k: peaks.get(k) for k in ("bf16_tflops", "bf16_tflops_sustained", "hbm_gbs")}}
-    chol_ms = tot["cholesky_solve"]
-    chol_flops = sum(P_ ** 3 / 3.0 for P_ in timer.extra["cholesky_solve"])
-    solve_info = {"kernel": "cholesky_solve[fp64]", "tflops": chol_flops / (sum(chol_ms) / 1e3) / 1e12 if chol_ms else None,
-                  "share_of_step": sum(chol_ms) / ms, "peak": measured["fp64_tflops_sustained"] if measured else 35.5}
+    chol_ms = tot["cholesky_solve"] + tot["cholesky_solve_mixed"]
+    chol_flops = sum(P_ ** 3 / 3.0 for P_ in timer.extra["cholesky_solve"] + timer.extra["cholesky_solve_mixed"])
+    n_mixed = len(tot["cholesky_solve_mixed"])
+    solve_info = {"kernel": "cholesky_solve[fp64]" if n_mixed == 0 else "cholesky_solve_mixed[3xTF32 tcgen05 trailing updates + fp64 CG refinement] / cholesky_solve[fp64] for small systems",
+                  "tflops_equiv": chol_flops / (sum(chol_ms) / 1e3) / 1e12 if chol_ms else None,
+                  "share_of_step": sum(chol_ms) / ms, "fp64_peak": measured["fp64_tflops_sustained"] if measured else 35.5,
+                  "mode": tn.solve_mode, "stats": dict(tn.solve_stats),
+                  "largest_ms": max(chol_ms) if chol_ms else None}
     shares = {k: sum(v) / ms for k, v in tot.items()}
     out = {"metric": "gn_sample_site_updates_per_s", "value": value, "unit": "sample-site-updates/s", "site_updates_per_s": site_rate,
            "n_gpus": world, "steps": args.steps,

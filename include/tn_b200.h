@@ -117,6 +117,18 @@ int tn_rhs_prepare(const double *b, const double *theta, const double *sigma, do
 int64_t tn_cholesky_work_elems(int64_t P);
 int tn_cholesky_solve(double *A, int64_t lda, int64_t P, double *rhs, double *work, int *info, void *stream);
 
+/* Mixed-precision variant of tn_cholesky_solve for large systems whose matrix was itself accumulated on the tensor
+ * cores (gram modes 1, 2).  A must hold the FULL symmetric matrix.  The P^3/3 trailing updates of the factorisation run
+ * as 3xTF32 tcgen05 GEMMs (fp32 accumulate), panels and diagonal blocks in fp64; the resulting factor (accurate to ~1e-5)
+ * preconditions an fp64 conjugate-gradient refinement whose operator is read from the untouched strict upper triangle of A
+ * plus the saved diagonal, until ||A x - b|| <= rtol ||b|| or max_iter iterations.
+ * stats[0] = relative residual reached, stats[1] = refinement iterations used (device doubles; may be NULL).
+ * info as above; when info[0] != 0, or the residual stays above rtol, rhs does not hold a usable solution and the caller
+ * re-expands A and calls tn_cholesky_solve.  work: tn_cholesky_mixed_work_elems(P) doubles.                      */
+int64_t tn_cholesky_mixed_work_elems(int64_t P);
+int tn_cholesky_solve_mixed(double *A, int64_t lda, int64_t P, double *rhs, double *work, int *info, double rtol,
+                            int max_iter, double *stats, void *stream);
+
 /* theta <- theta + lr * step with the optional adaptive shrink / max-norm projection
  * (TensorNode.update_node, tensor/node.py:178-203).  max_norm <= 0 disables the projection.     */
 int tn_update_node(double *theta, const double *step, int64_t P, double lr, int adaptive_step, double max_norm,

@@ -45,6 +45,8 @@ PROTOTYPES = {
     "tn_rhs_prepare": (i32, [vp, vp, vp, f64, vp, i64, vp]),
     "tn_cholesky_work_elems": (i64, [i64]),
     "tn_cholesky_solve": (i32, [vp, i64, i64, vp, vp, vp, vp]),
+    "tn_cholesky_mixed_work_elems": (i64, [i64]),
+    "tn_cholesky_solve_mixed": (i32, [vp, i64, i64, vp, vp, vp, f64, i32, vp, vp]),
     "tn_update_node": (i32, [vp, vp, i64, f64, i32, f64, vp, vp]),
     "tn_qr": (i32, [vp, i32, i32, vp, vp]),
     "tn_matvec_work_elems": (i64, [i64, i32, i32, i32]),

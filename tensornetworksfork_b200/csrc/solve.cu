@@ -485,10 +485,122 @@ extern "C" int64_t tn_cholesky_work_elems(int64_t P) {
     return tn::ceil_div64(P, tn::CH_NB) * tn::CH_NB * tn::CH_NB;
 }
 
-extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs, double* work, int* info, void* stream) {
-    using namespace tn;
-    TN_CHECK_ARG(A && work && info && P >= 1 && lda >= P, "tn_cholesky_solve: bad arguments");
-    cudaStream_t st = as_stream(stream);
+namespace tn {
+
+// ---- substitution for large systems, 512-wide super-blocks: one CTA solves the 512 x 512 triangle (using the inverted
+//      64 x 64 diagonal blocks), then a grid-wide kernel applies the off-diagonal panel to the rest of the right-hand side.
+constexpr int TB_W = 512;
+
+// forward (transpose == 0): solve L[w,w] y = rhs[w] for the window w = [j0, j0+nbw); backward: L[w,w]^T z = rhs[w].
+__global__ void __launch_bounds__(1024)
+trsv_block_kernel(const double* __restrict__ A, int64_t lda, int64_t j0, int nbw, double* __restrict__ rhs,
+                  const double* __restrict__ Linv_all, int transpose, const int* __restrict__ stop) {
+    __shared__ double x[TB_W];
+    __shared__ double yb[CH_NB];
+    if (*stop != 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nblk = (nbw + CH_NB - 1) / CH_NB;
+    for (int i = tid; i < TB_W; i += 1024) x[i] = (i < nbw) ? rhs[j0 + i] : 0.0;
+    __syncthreads();
+    const int r = tid >> 4, l = tid & 15;
+    if (!transpose) {
+        for (int b = 0; b < nblk; ++b) {
+            const int j = b * CH_NB;
+            const double* Li = Linv_all + (size_t)((j0 + j) / CH_NB) * CH_NB * CH_NB;
+            double sdot = 0.0;
+            for (int q = l; q <= r; q += 16) sdot = fma(Li[r * CH_NB + q], x[j + q], sdot);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 8);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+            if (l == 0) yb[r] = sdot;
+            __syncthreads();
+            if (tid < CH_NB) x[j + tid] = (j + tid < nbw) ? yb[tid] : 0.0;
+            for (int i = j + CH_NB + warp; i < nbw; i += 32) {
+                const double* row = A + (j0 + i) * lda + j0 + j;
+                double sd = row[lane] * yb[lane] + row[lane + 32] * yb[lane + 32];
+                for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+                if (lane == 0) x[i] -= sd;
+            }
+            __syncthreads();
+        }
+    } else {
+        for (int b = nblk - 1; b >= 0; --b) {
+            const int j = b * CH_NB;
+            const int nb = min(CH_NB, nbw - j);
+            const double* Li = Linv_all + (size_t)((j0 + j) / CH_NB) * CH_NB * CH_NB;
+            double sdot = 0.0;
+            for (int q = r + l; q < CH_NB; q += 16) sdot = fma(Li[q * CH_NB + r], x[j + q], sdot);   // Linv^T
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 8);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 4);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 2);
+            sdot += __shfl_xor_sync(0xffffffffu, sdot, 1);
+            if (l == 0) yb[r] = sdot;
+            __syncthreads();
+            if (tid < CH_NB) x[j + tid] = (tid < nb) ? yb[tid] : 0.0;
+            for (int c = tid; c < j; c += 1024) {
+                double sd = 0.0;
+                for (int t = 0; t < nb; ++t) sd = fma(A[(j0 + j + t) * lda + j0 + c], yb[t], sd);
+                x[c] -= sd;
+            }
+            __syncthreads();
+        }
+    }
+    for (int i = tid; i < nbw; i += 1024) rhs[j0 + i] = x[i];
+}
+
+// forward panel: rhs[i] -= sum_t A[i][j0+t] * y[t], i >= j0+nbw.  One warp per row, the row piece (<= 512 doubles) coalesced.
+__global__ void __launch_bounds__(256)
+trsv_fwd_panel_kernel(const double* __restrict__ A, int64_t lda, int64_t P, int64_t j0, int nbw, double* __restrict__ rhs,
+                      const int* __restrict__ stop) {
+    __shared__ double y[TB_W];
+    if (*stop != 0) return;
+    for (int i = threadIdx.x; i < TB_W; i += 256) y[i] = (i < nbw) ? rhs[j0 + i] : 0.0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
+    for (int64_t i = j0 + nbw + (int64_t)blockIdx.x * 8 + wp; i < P; i += (int64_t)gridDim.x * 8) {
+        const double* row = A + i * lda + j0;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll 4
+        for (int t = lane * 2; t < nbw; t += 64) {        // nbw is even (multiple of 64) on this path
+            const double2 a = *reinterpret_cast<const double2*>(row + t);
+            s0 = fma(a.x, y[t], s0);
+            s1 = fma(a.y, y[t + 1], s1);
+        }
+        double sd = s0 + s1;
+        for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+        if (lane == 0) rhs[i] -= sd;
+    }
+}
+
+// backward panel: rhs[c] -= sum_t A[j0+t][c] * x[t], c < j0.  Thread per column (coalesced rows); blockIdx.y splits the
+// nbw rows into groups of 64 whose partial sums are added atomically.
+__global__ void __launch_bounds__(256)
+trsv_bwd_panel_kernel(const double* __restrict__ A, int64_t lda, int64_t j0, int nbw, double* __restrict__ rhs,
+                      const int* __restrict__ stop) {
+    __shared__ double x[CH_NB];
+    if (*stop != 0) return;
+    const int t0 = blockIdx.y * CH_NB;
+    if (t0 >= nbw) return;
+    const int nt = min(CH_NB, nbw - t0);
+    if (threadIdx.x < CH_NB) x[threadIdx.x] = (threadIdx.x < nt) ? rhs[j0 + t0 + threadIdx.x] : 0.0;
+    __syncthreads();
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= j0) return;
+    const double* col = A + (j0 + t0) * lda + c;
+    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    int t = 0;
+    for (; t + 3 < nt; t += 4) {
+        s0 = fma(col[(int64_t)t * lda], x[t], s0);
+        s1 = fma(col[(int64_t)(t + 1) * lda], x[t + 1], s1);
+        s2 = fma(col[(int64_t)(t + 2) * lda], x[t + 2], s2);
+        s3 = fma(col[(int64_t)(t + 3) * lda], x[t + 3], s3);
+    }
+    for (; t < nt; ++t) s0 = fma(col[(int64_t)t * lda], x[t], s0);
+    atomicAdd(rhs + c, -((s0 + s1) + (s2 + s3)));
+}
+
+static int cholesky_configure() {
     constexpr size_t kBlkSmem = 2 * CH_NB * (CH_NB + 1) * sizeof(double);   // trsm needs two blocks, potrf one
     constexpr size_t kDmmaSmem = (size_t)2 * DS_STAGES * DS_BT * DS_LD * sizeof(double);
     static bool configured = false;
@@ -498,7 +610,16 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
         TN_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkSmem));
         configured = true;
     }
-    TN_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+    return TN_OK;
+}
+
+// Blocked right-looking factorisation of the lower triangle, in place.  X != nullptr: the outer trailing updates with at least
+// tc_min_n rows run on the tensor cores in 3xTF32 (syrk_tc.cu); X must hold syrk_tc_work_floats(P, NBO) floats.
+static int cholesky_factorize(double* A, int64_t lda, int64_t P, double* work, int* info, cudaStream_t st, float* X, int64_t NBO) {
+    constexpr size_t kBlkSmem = 2 * CH_NB * (CH_NB + 1) * sizeof(double);
+    constexpr size_t kDmmaSmem = (size_t)2 * DS_STAGES * DS_BT * DS_LD * sizeof(double);
+    int rc = cholesky_configure();
+    if (rc != TN_OK) return rc;
     static int coop_ok = -1;
     if (coop_ok < 0) {
         int dev = 0, v = 0;
@@ -507,8 +628,7 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
         coop_ok = v;
         if (v) TN_CUDA(cudaFuncSetAttribute(cholesky_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkSmem));
     }
-    bool factored = false;
-    if (coop_ok && P <= CF_MAXP && P > CH_NB && !getenv("TN_CHOL_NO_FUSED")) {
+    if (coop_ok && P <= CF_MAXP && P > CH_NB && !X && !getenv("TN_CHOL_NO_FUSED")) {
         int Pi = (int)P;
         void* args[] = {(void*)&A, (void*)&lda, (void*)&Pi, (void*)&work, (void*)&info};
         int grid = sm_count();
@@ -516,16 +636,10 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
         if (grid > need) grid = need;
         TN_CUDA(cudaLaunchCooperativeKernel((void*)cholesky_fused_kernel, dim3(grid), dim3(256), args, kBlkSmem, st));
         count_launch();
-        factored = true;
+        return TN_OK;
     }
-    // outer panel width: wider panels amortise the read-modify-write of the trailing matrix (measured at P = 41 876:
-    // 256 -> 1385 ms, 512 -> 1210 ms, 768 -> 1140 ms, 1024 -> 1125 ms)
-    int64_t NBO = (P > 16384) ? 768 : ((P > 8192) ? 512 : ((P > 4096) ? 256 : ((P > 1024) ? 128 : CH_NB)));
-    if (const char* e = getenv("TN_CHOL_NBO")) {
-        const int v = atoi(e);
-        if (v >= CH_NB && v % CH_NB == 0) NBO = v;
-    }
-    for (int64_t J = 0; J < P && !factored; J += NBO) {
+    const int64_t tc_min_n = 1024;
+    for (int64_t J = 0; J < P; J += NBO) {
         const int64_t Jend = (J + NBO < P) ? J + NBO : P;
         for (int64_t j = J; j < Jend; j += CH_NB) {
             const int nb = (int)((Jend - j < CH_NB) ? Jend - j : CH_NB);
@@ -552,7 +666,10 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
         if (Jend < P) {
             const int64_t n = P - Jend;
             const int kbo = (int)(Jend - J);
-            if (n > 512 && kbo % DS_KC == 0 && lda % 2 == 0) {
+            if (X && n >= tc_min_n) {
+                rc = syrk_tc_update(A, lda, P, Jend, J, kbo, X, info, st);
+                if (rc != TN_OK) return rc;
+            } else if (n > 512 && kbo % DS_KC == 0 && lda % 2 == 0) {
                 dim3 grid((unsigned)ceil_div64(n, DS_BT), (unsigned)ceil_div64(n, DS_BT));
                 syrk_update_dmma_kernel<<<grid, DS_THREADS, kDmmaSmem, st>>>(A, lda, P, Jend, P, J, kbo, info);
             } else if (n > 512) {
@@ -565,43 +682,343 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
         }
         TN_LAUNCH_CHECK();
     }
-    if (rhs && P <= TS_MAXP) {
+    return TN_OK;
+}
+
+// rhs <- L^{-T} L^{-1} rhs with the factor in the lower triangle of A and the inverted diagonal blocks in work.
+// Every kernel returns at once when *stop != 0.
+static int cholesky_substitute(const double* A, int64_t lda, int64_t P, double* rhs, const double* work, const int* stop,
+                               cudaStream_t st) {
+    if (P <= TS_MAXP) {
         const size_t smem = ((size_t)ceil_div64(P, 64) * 64 + 64) * sizeof(double);
         static size_t ts_configured = 0;
         if (smem > ts_configured) {
             TN_CUDA(cudaFuncSetAttribute(trsv_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             ts_configured = smem;
         }
-        trsv_small_kernel<<<1, 1024, smem, st>>>(A, lda, (int)P, rhs, work, info);
+        trsv_small_kernel<<<1, 1024, smem, st>>>(A, lda, (int)P, rhs, work, stop);
         TN_LAUNCH_CHECK();
-    } else if (rhs) {
-        const int sms = sm_count();
+        return TN_OK;
+    }
+    const int sms = sm_count();
+    if (lda % 2 != 0) {      // unaligned rows: the 64-wide kernels
         for (int64_t j = 0; j < P; j += CH_NB) {
             const int nb = (int)((P - j < CH_NB) ? P - j : CH_NB);
             const double* Linv = work + (j / CH_NB) * CH_NB * CH_NB;
-            trsv_diag_kernel<<<1, CH_NB, 0, st>>>(rhs, j, nb, Linv, 0, info);
+            trsv_diag_kernel<<<1, CH_NB, 0, st>>>(rhs, j, nb, Linv, 0, stop);
             count_launch();
             const int64_t below = P - (j + nb);
             if (below > 0) {
                 int64_t blocks = ceil_div64(below, 8);
                 if (blocks > 4LL * sms) blocks = 4LL * sms;
-                trsv_fwd_update_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, lda, P, j, nb, rhs, info);
+                trsv_fwd_update_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, lda, P, j, nb, rhs, stop);
                 count_launch();
             }
         }
         for (int64_t j = ((P - 1) / CH_NB) * CH_NB; j >= 0; j -= CH_NB) {
             const int nb = (int)((P - j < CH_NB) ? P - j : CH_NB);
             const double* Linv = work + (j / CH_NB) * CH_NB * CH_NB;
-            trsv_diag_kernel<<<1, CH_NB, 0, st>>>(rhs, j, nb, Linv, 1, info);
+            trsv_diag_kernel<<<1, CH_NB, 0, st>>>(rhs, j, nb, Linv, 1, stop);
             count_launch();
             if (j > 0) {
                 int64_t blocks = ceil_div64(j, 256);
                 if (blocks > 4LL * sms) blocks = 4LL * sms;
-                trsv_bwd_update_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, lda, j, nb, rhs, info);
+                trsv_bwd_update_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, lda, j, nb, rhs, stop);
                 count_launch();
             }
         }
         TN_LAUNCH_CHECK();
+        return TN_OK;
     }
+    for (int64_t j0 = 0; j0 < P; j0 += TB_W) {
+        const int nbw = (int)((P - j0 < TB_W) ? P - j0 : TB_W);
+        trsv_block_kernel<<<1, 1024, 0, st>>>(A, lda, j0, nbw, rhs, work, 0, stop);
+        count_launch();
+        const int64_t below = P - (j0 + nbw);
+        if (below > 0) {
+            int64_t blocks = ceil_div64(below, 8);
+            if (blocks > 8LL * sms) blocks = 8LL * sms;
+            trsv_fwd_panel_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, lda, P, j0, nbw, rhs, stop);
+            count_launch();
+        }
+    }
+    for (int64_t j0 = ((P - 1) / TB_W) * TB_W; j0 >= 0; j0 -= TB_W) {
+        const int nbw = (int)((P - j0 < TB_W) ? P - j0 : TB_W);
+        trsv_block_kernel<<<1, 1024, 0, st>>>(A, lda, j0, nbw, rhs, work, 1, stop);
+        count_launch();
+        if (j0 > 0) {
+            dim3 grid((unsigned)ceil_div64(j0, 256), (unsigned)ceil_div64(nbw, CH_NB));
+            trsv_bwd_panel_kernel<<<grid, 256, 0, st>>>(A, lda, j0, nbw, rhs, stop);
+            count_launch();
+        }
+    }
+    TN_LAUNCH_CHECK();
+    return TN_OK;
+}
+
+static int64_t cholesky_default_nbo(int64_t P) {
+    // outer panel width: wider panels amortise the read-modify-write of the trailing matrix (measured at P = 41 876:
+    // 256 -> 1385 ms, 512 -> 1210 ms, 768 -> 1140 ms, 1024 -> 1125 ms)
+    int64_t NBO = (P > 16384) ? 768 : ((P > 8192) ? 512 : ((P > 4096) ? 256 : ((P > 1024) ? 128 : CH_NB)));
+    if (const char* e = getenv("TN_CHOL_NBO")) {
+        const int v = atoi(e);
+        if (v >= CH_NB && v % CH_NB == 0) NBO = v;
+    }
+    return NBO;
+}
+
+// ---- fp64 refinement around the tensor-core factor ------------------------------------------------------------------
+// The factorisation overwrites the lower triangle only, so the strict upper triangle of A still holds the system; with the
+// saved diagonal it gives the fp64 operator of the conjugate-gradient refinement without a second copy of A.
+__global__ void diag_save_kernel(const double* __restrict__ A, int64_t lda, int64_t P, double* __restrict__ d) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) d[i] = A[i * lda + i];
+}
+
+__global__ void symv_diag_kernel(const double* __restrict__ d, const double* __restrict__ x, double* __restrict__ y, int64_t P,
+                                 const int* __restrict__ stop) {
+    if (*stop != 0) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P; i += (int64_t)gridDim.x * blockDim.x) y[i] = d[i] * x[i];
+}
+
+// y += U x + U^T x, U = strict upper triangle of A.  64 x 256 tile per CTA, thread = column.
+__global__ void __launch_bounds__(256)
+symv_upper_kernel(const double* __restrict__ A, int64_t lda, int64_t P, const double* __restrict__ x, double* __restrict__ y,
+                  const int* __restrict__ stop) {
+    __shared__ double xi[64];
+    __shared__ double rowpart[64][8];
+    if (*stop != 0) return;
+    const int64_t i0 = (int64_t)blockIdx.y * 64, j0 = (int64_t)blockIdx.x * 256;
+    if (j0 + 255 <= i0) return;                 // no element with col > row in this tile
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid < 64) xi[tid] = (i0 + tid < P) ? x[i0 + tid] : 0.0;
+    __syncthreads();
+    const int64_t col = j0 + tid;
+    const double xj = (col < P) ? x[col] : 0.0;
+    const int64_t nrow = (P - i0 < 64) ? P - i0 : 64;
+    double colacc = 0.0;
+    const double* a = A + i0 * lda + col;
+#pragma unroll 8
+    for (int r = 0; r < 64; ++r) {
+        const double v = (r < nrow && col < P && col > i0 + r) ? a[(int64_t)r * lda] : 0.0;
+        colacc = fma(v, xi[r], colacc);
+        double rp = v * xj;
+        for (int o = 16; o > 0; o >>= 1) rp += __shfl_xor_sync(0xffffffffu, rp, o);
+        if (lane == 0) rowpart[r][warp] = rp;
+    }
+    if (col < P) atomicAdd(y + col, colacc);
+    __syncthreads();
+    if (tid < nrow) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += rowpart[tid][w];
+        atomicAdd(y + i0 + tid, s);
+    }
+}
+
+// out[0] += sum a[i] * b[i]
+__global__ void __launch_bounds__(256)
+dot_kernel(const double* __restrict__ a, const double* __restrict__ b, int64_t n, double* __restrict__ out, const int* __restrict__ stop) {
+    __shared__ double red[8];
+    if (*stop != 0) return;
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) s = fma(a[i], b[i], s);
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += red[k];
+        atomicAdd(out, t);
+    }
+}
+
+// r = b - q, rnorm2 += r.r, bnorm2 += b.b
+__global__ void __launch_bounds__(256)
+pcg_residual_kernel(const double* __restrict__ b, const double* __restrict__ q, double* __restrict__ r, int64_t n,
+                    double* __restrict__ scal, const int* __restrict__ stop) {
+    __shared__ double red[2][8];
+    if (*stop != 0) return;
+    double s = 0.0, sb = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double bi = b[i], v = bi - q[i];
+        r[i] = v;
+        s = fma(v, v, s);
+        sb = fma(bi, bi, sb);
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+    }
+    if ((threadIdx.x & 31) == 0) { red[0][threadIdx.x >> 5] = s; red[1][threadIdx.x >> 5] = sb; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0, tb = 0.0;
+        for (int k = 0; k < 8; ++k) { t += red[0][k]; tb += red[1][k]; }
+        atomicAdd(scal + 1, t);
+        atomicAdd(scal + 0, tb);
+    }
+}
+
+// scal: [0] |b|^2  [1] |r|^2  [2],[3] r.z (alternating by iteration parity)  [4] p.Ap  [5] iterations done
+//       [6] relative residual  [7] accumulator of the next |r|^2
+__global__ void pcg_latch_kernel(const int* __restrict__ info, int* __restrict__ stop) { *stop = (*info != 0) ? 1 : 0; }
+
+// Before iteration `it`: record the residual, stop when it is small enough (or NaN), clear the accumulators of the iteration.
+__global__ void pcg_check_kernel(double* __restrict__ scal, int* __restrict__ stop, double rtol, int it) {
+    if (*stop != 0) return;
+    const double bn = scal[0], rn = scal[1];
+    const double rel = (bn > 0.0) ? sqrt(rn / bn) : 0.0;
+    scal[6] = rel;
+    scal[5] = (double)it;
+    if (!(rel > rtol)) *stop = 1;
+    scal[4] = 0.0;
+    scal[7] = 0.0;
+    scal[2 + ((it + 1) & 1)] = 0.0;                 // the r.z slot this iteration accumulates into
+}
+
+__global__ void pcg_commit_kernel(double* __restrict__ scal, const int* __restrict__ stop) {
+    if (*stop == 0) scal[1] = scal[7];
+}
+
+__global__ void __launch_bounds__(256)
+pcg_direction_kernel(const double* __restrict__ z, double* __restrict__ p, int64_t n, const double* __restrict__ scal, int it,
+                     const int* __restrict__ stop) {
+    if (*stop != 0) return;
+    const double beta = (it == 0) ? 0.0 : scal[2 + ((it + 1) & 1)] / scal[2 + (it & 1)];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        p[i] = (it == 0) ? z[i] : fma(beta, p[i], z[i]);
+}
+
+// x += alpha p, r -= alpha q, |r|^2 (scal[1] must have been zeroed)
+__global__ void __launch_bounds__(256)
+pcg_step_kernel(double* __restrict__ x, double* __restrict__ r, const double* __restrict__ p, const double* __restrict__ q, int64_t n,
+                double* __restrict__ scal, double* __restrict__ rn_out, int it, const int* __restrict__ stop) {
+    __shared__ double red[8];
+    if (*stop != 0) return;
+    const double alpha = scal[2 + ((it + 1) & 1)] / scal[4];
+    double s = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        x[i] = fma(alpha, p[i], x[i]);
+        const double v = fma(-alpha, q[i], r[i]);
+        r[i] = v;
+        s = fma(v, v, s);
+    }
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int k = 0; k < 8; ++k) t += red[k];
+        atomicAdd(rn_out, t);
+    }
+}
+
+__global__ void pcg_finish_kernel(const double* __restrict__ x, double* __restrict__ rhs, int64_t n, const int* __restrict__ info,
+                                  const double* __restrict__ scal, double* __restrict__ stats) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && stats) {
+        stats[0] = scal[6];
+        stats[1] = scal[5];
+    }
+    if (*info != 0) return;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) rhs[i] = x[i];
+}
+
+}  // namespace tn
+
+extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs, double* work, int* info, void* stream) {
+    using namespace tn;
+    TN_CHECK_ARG(A && work && info && P >= 1 && lda >= P, "tn_cholesky_solve: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    TN_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+    int rc = cholesky_factorize(A, lda, P, work, info, st, nullptr, cholesky_default_nbo(P));
+    if (rc != TN_OK) return rc;
+    if (rhs) rc = cholesky_substitute(A, lda, P, rhs, work, info, st);
+    return rc;
+}
+
+extern "C" int64_t tn_cholesky_mixed_work_elems(int64_t P) {
+    const int64_t Pp = tn::ceil_div64(P, 64) * 64;
+    return tn::ceil_div64(P, tn::CH_NB) * tn::CH_NB * tn::CH_NB + 7 * Pp + 16;
+}
+
+extern "C" int tn_cholesky_solve_mixed(double* A, int64_t lda, int64_t P, double* rhs, double* work, int* info, double rtol,
+                                       int max_iter, double* stats, void* stream) {
+    using namespace tn;
+    TN_CHECK_ARG(A && rhs && work && info && P >= 1 && lda >= P && max_iter >= 0 && rtol > 0.0, "tn_cholesky_solve_mixed: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    const int64_t Pp = ceil_div64(P, 64) * 64;
+    double* vec = work + ceil_div64(P, CH_NB) * CH_NB * CH_NB;
+    double *d = vec, *b = vec + Pp, *x = vec + 2 * Pp, *r = vec + 3 * Pp, *z = vec + 4 * Pp, *p = vec + 5 * Pp, *q = vec + 6 * Pp;
+    double* scal = vec + 7 * Pp;                                   // 8 doubles + the stop flag
+    int* stop = reinterpret_cast<int*>(scal + 8);
+    const int sms = sm_count();
+    int64_t vb = ceil_div64(P, 256);
+    if (vb > 2LL * sms) vb = 2LL * sms;
+    const unsigned vblocks = (unsigned)vb;
+
+    TN_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+    TN_CUDA(cudaMemsetAsync(scal, 0, 16 * sizeof(double), st));
+    diag_save_kernel<<<vblocks, 256, 0, st>>>(A, lda, P, d);
+    TN_LAUNCH_CHECK();
+    TN_CUDA(cudaMemcpyAsync(b, rhs, (size_t)P * sizeof(double), cudaMemcpyDeviceToDevice, st));
+
+    int64_t NBO = (P > 8192) ? 1024 : cholesky_default_nbo(P);
+    if (const char* e = getenv("TN_CHOL_TC_NBO")) {
+        const int v = atoi(e);
+        if (v >= CH_NB && v % CH_NB == 0) NBO = v;
+    }
+    float* X = nullptr;
+    TN_CUDA(cudaMallocAsync(&X, (size_t)syrk_tc_work_floats(P, (int)NBO) * sizeof(float), st));
+    int rc = cholesky_factorize(A, lda, P, work, info, st, X, NBO);
+    cudaFreeAsync(X, st);
+    if (rc != TN_OK) return rc;
+
+    auto symv = [&](const double* v, double* out) -> int {
+        symv_diag_kernel<<<vblocks, 256, 0, st>>>(d, v, out, P, stop);
+        count_launch();
+        dim3 grid((unsigned)ceil_div64(P, 256), (unsigned)ceil_div64(P, 64));
+        symv_upper_kernel<<<grid, 256, 0, st>>>(A, lda, P, v, out, stop);
+        TN_LAUNCH_CHECK();
+        return TN_OK;
+    };
+    // x0 = (L L^T)^-1 b with the approximate factor; a failed factorisation (info != 0) switches everything below off
+    pcg_latch_kernel<<<1, 1, 0, st>>>(info, stop);
+    TN_LAUNCH_CHECK();
+    TN_CUDA(cudaMemcpyAsync(x, b, (size_t)P * sizeof(double), cudaMemcpyDeviceToDevice, st));
+    rc = cholesky_substitute(A, lda, P, x, work, stop, st);
+    if (rc != TN_OK) return rc;
+    rc = symv(x, q);
+    if (rc != TN_OK) return rc;
+    pcg_residual_kernel<<<vblocks, 256, 0, st>>>(b, q, r, P, scal, stop);
+    TN_LAUNCH_CHECK();
+    for (int it = 0; it < max_iter; ++it) {
+        pcg_check_kernel<<<1, 1, 0, st>>>(scal, stop, rtol, it);
+        count_launch();
+        if (it >= 1) {      // an iteration is ~10 ms of queued work; do not queue hundreds of no-op launches after convergence
+            int h_stop = 0;
+            TN_CUDA(cudaMemcpyAsync(&h_stop, stop, sizeof(int), cudaMemcpyDeviceToHost, st));
+            TN_CUDA(cudaStreamSynchronize(st));
+            if (h_stop) break;
+        }
+        TN_CUDA(cudaMemcpyAsync(z, r, (size_t)P * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        rc = cholesky_substitute(A, lda, P, z, work, stop, st);
+        if (rc != TN_OK) return rc;
+        dot_kernel<<<vblocks, 256, 0, st>>>(r, z, P, scal + 2 + ((it + 1) & 1), stop);
+        count_launch();
+        pcg_direction_kernel<<<vblocks, 256, 0, st>>>(z, p, P, scal, it, stop);
+        count_launch();
+        rc = symv(p, q);
+        if (rc != TN_OK) return rc;
+        dot_kernel<<<vblocks, 256, 0, st>>>(p, q, P, scal + 4, stop);
+        count_launch();
+        pcg_step_kernel<<<vblocks, 256, 0, st>>>(x, r, p, q, P, scal, scal + 7, it, stop);
+        TN_LAUNCH_CHECK();
+        pcg_commit_kernel<<<1, 1, 0, st>>>(scal, stop);
+        count_launch();
+    }
+    pcg_check_kernel<<<1, 1, 0, st>>>(scal, stop, rtol, max_iter);
+    count_launch();
+    pcg_finish_kernel<<<vblocks, 256, 0, st>>>(x, rhs, P, info, scal, stats);
+    TN_LAUNCH_CHECK();
     return TN_OK;
 }

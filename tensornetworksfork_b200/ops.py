@@ -215,6 +215,20 @@ def cholesky_solve(A, rhs_vec):
     return info
 
 
+def cholesky_solve_mixed(A, rhs_vec, rtol=1e-12, max_iter=12):
+    """Tensor-core (3xTF32) factorisation + fp64 conjugate-gradient refinement.  A (P x lda, full symmetric) is overwritten
+    below the diagonal, rhs_vec <- solution.  Returns (info, stats) device tensors; stats = [relative residual, iterations]."""
+    lib = _lib.load()
+    P = A.shape[0]
+    _need_cuda(A, rhs_vec)
+    work = torch.empty((lib.tn_cholesky_mixed_work_elems(P),), dtype=torch.float64, device=A.device)
+    info = torch.zeros((1,), dtype=torch.int32, device=A.device)
+    stats = torch.zeros((2,), dtype=torch.float64, device=A.device)
+    _lib.check(lib.tn_cholesky_solve_mixed(_p(A), A.stride(0), P, _p(rhs_vec), _p(work), ctypes.c_void_p(info.data_ptr()),
+                                           float(rtol), int(max_iter), _p(stats), _stream()), "tn_cholesky_solve_mixed")
+    return info, stats
+
+
 def update_node(theta, step, lr=1.0, adaptive_step=False, max_norm=None):
     """theta (contiguous) <- theta + lr*step, in place."""
     lib = _lib.load()

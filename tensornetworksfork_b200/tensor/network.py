@@ -140,6 +140,14 @@ class TensorNetwork:
         self.right_stacks = None
         self.nodes, self.node_indices = self._discover_nodes()
         self.gram_mode = "fp64"
+        # local solve: "fp64" = blocked fp64 Cholesky; "mixed" = tensor-core factorisation + fp64 refinement;
+        # "auto" = mixed for large systems whose Gram was itself built on the tensor cores, fp64 otherwise
+        self.solve_mode = "auto"
+        self.mixed_min_P = 8192
+        self.mixed_rtol = 1e-11         # residual the refinement aims for ...
+        self.mixed_accept = 1e-9        # ... and the one it must reach for the result to be used (else fp64 redo)
+        self.solve_stats = {"mixed": 0, "fp64": 0, "mixed_fallback": 0, "refine_iters": 0}
+        self._mixed_floor = 0.0         # ridge values at or below this made the mixed solve fall back; skip it there
         self.process_group = None       # torch.distributed group: x, y are then this rank's row shard
         self.shard_offset = 0           # global index of this rank's first row
         self.shard_total = None         # global number of rows
@@ -573,7 +581,28 @@ class TensorNetwork:
         sigma = ops.gram_sigma(M, m_pos, role_of_pos)
         A = ops.gram_expand(M, m_pos, role_of_pos, sigma, ridge)
         rhs = ops.rhs_prepare(b, theta, sigma, ridge)
-        info = ops.cholesky_solve(A, rhs)
+        P = rhs.numel()
+        use_mixed = self.solve_mode == "mixed" or (self.solve_mode == "auto" and self.gram_mode != "fp64"
+                                                   and P >= self.mixed_min_P and ridge > self._mixed_floor)
+        info = None
+        if use_mixed:
+            rhs0 = rhs.clone()
+            info, stats = ops.cholesky_solve_mixed(A, rhs, rtol=self.mixed_rtol)
+            bad, (rel, iters) = int(info.item()), stats.tolist()
+            if bad == 0 and rel <= self.mixed_accept:
+                self.solve_stats["mixed"] += 1
+                self.solve_stats["refine_iters"] += int(iters)
+            else:
+                # the ~1e-5 factor lost positive definiteness or preconditions too weakly: redo in fp64 (the lower
+                # triangle of A was overwritten, so expand again)
+                self.solve_stats["mixed_fallback"] += 1
+                self._mixed_floor = max(self._mixed_floor, ridge)
+                A = ops.gram_expand(M, m_pos, role_of_pos, sigma, ridge, A=A)
+                rhs = rhs0
+                info = None
+        if info is None:
+            self.solve_stats["fp64"] += 1
+            info = ops.cholesky_solve(A, rhs)
         bad = int(info.item())
         if bad != 0:
             raise torch.linalg.LinAlgError(

@@ -140,6 +140,11 @@ def cholesky_solve(A, rhs_vec):
     return info
 
 
+def cholesky_solve_mixed(A, rhs_vec, rtol=1e-12, max_iter=12):
+    info = cholesky_solve(A, rhs_vec)
+    return info, torch.tensor([0.0, 0.0], dtype=torch.float64)
+
+
 def update_node(theta, step, lr=1.0, adaptive_step=False, max_norm=None):
     if adaptive_step:
         sn, pn = torch.norm(step), torch.norm(theta)
