@@ -36,6 +36,10 @@ WORKLOADS = {
                  desc="CPD rank 100 california_housing-shaped N=20640 F=8(+1) 5 factors"),
     "cfg3": dict(kind="tt", sites=90, r=24, features=90, bias=False, basis="sin-cos", C=1, n=515345, constrict=True,
                  perturb=False, batch_size=512, orthonormalize=True, desc="TNML sin-cos year-shaped N=515345 F=90 r=24 90 sites"),
+    "cfg4a": dict(kind="tt", sites=784, r=38, features=784, bias=False, basis="sin-cos", C=9, n=60000, constrict=True,
+                  perturb=False, batch_size=1024, solver="cg", max_iter=500, tol=1e-3,
+                  desc="TNML sin-cos classifier MNIST-shaped N=60000 F=784 10 classes (C=9 logits, XE loss) r=38, matrix-free "
+                       "local solve scipy_swipe('cg', max_iter=500, tol=1e-3)"),
     "cfg5a": dict(kind="tt", sites=5, r=38, features=28, bias=True, basis=None, C=1, n=1000000, constrict=False,
                   perturb=False, batch_size=-1, desc="TT poly-mode higgs-shaped F=28(+1) r=38 5 cores (degree 5), P=41876"),
     "cfg5b": dict(kind="tt", sites=28, r=38, features=28, bias=False, basis="polynomial", degree=5, C=1, n=1000000,
@@ -60,6 +64,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--ref-rows", type=int, default=None)
+    ap.add_argument("--ref-matvecs", type=float, default=20.0,
+                    help="matvecs per site assumed by --impl reference on the matrix-free workloads (the b200 arm reports its own count)")
     return ap.parse_args()
 
 
@@ -71,6 +77,9 @@ def make_data(wl, n, seed, device):
     w1 = torch.randn((F, 1), generator=g, dtype=torch.float64) / F ** 0.5
     w2 = torch.randn((F, 1), generator=g, dtype=torch.float64) / F ** 0.5
     y = torch.tanh(X @ w1) + 0.5 * (X @ w2) ** 2 + 0.1 * torch.randn((n, 1), generator=g, dtype=torch.float64)
+    if wl["C"] > 1:     # balanced-ish classes from the argmax of a fixed random linear map, one-hot over C+1 classes
+        Wc = torch.randn((F, wl["C"] + 1), generator=torch.Generator(device="cpu").manual_seed(7), dtype=torch.float64)
+        y = torch.nn.functional.one_hot((X @ Wc).argmax(dim=1), num_classes=wl["C"] + 1).to(torch.float64)
     if wl["bias"]:
         X = torch.cat([X, torch.ones((n, 1), dtype=torch.float64)], dim=1)
     return X.to(device), y.to(device)
@@ -172,6 +181,11 @@ class KernelTimer:
             # keep sizes only: holding the argument tensors would pin every 14 GB system matrix of the step
             if n == "gram":
                 self.extra[n].append((a[1].m, a[2].m, a[3].m, a[5]))
+            elif n == "matvec":
+                fa, fb, fc, rows = a[0], a[1], a[2], a[4]
+                raw_b = 1 if fb.map_kind != 0 else fb.m
+                # two passes over the three factors (8 B each), J v written and read once, weights read once
+                self.extra[n].append(2 * 8.0 * rows * (fa.m / fa.div + raw_b / fb.div + fc.m / fc.div) + 3 * 8.0 * rows)
             elif n in ("cholesky_solve", "cholesky_solve_mixed"):
                 self.extra[n].append(int(a[0].shape[0]))
             return out
@@ -190,17 +204,25 @@ def gram_flops(call):
     return 2.0 * rows * npair(ma) * npair(mb) * npair(mc), float(rows) * P * (P + 1)
 
 
-def run_sweeps(layer, x, y, wl, args, steps, counter):
+def run_sweeps(layer, x, y, wl, args, steps, counter, data_device=None):
     import tensornetworksfork_b200 as tnb
     tn = layer.tensor_network
-    loss_fn = tnb.SquareBregFunction()
+    loss_fn = tnb.SquareBregFunction() if wl["C"] == 1 else tnb.XEAutogradBregman(w=1.0)
 
     def cb(NS, node):
         counter[0] += 1
 
+    if wl.get("solver"):
+        # matrix-free local solve (reference call shape: image_convolution_CG_MNIST.py:95); one step = L->R + R->L
+        ok = tn.scipy_swipe(x, y, loss_fn, wl["solver"], batch_size=wl["batch_size"], num_swipes=2 * steps, lr=1.0,
+                            max_iter=wl["max_iter"], tol=wl["tol"], block_callback=cb, data_device=data_device,
+                            model_device=layer.tensor_network.main_nodes[0].tensor.device)
+        if not ok:
+            raise RuntimeError("sweep timed out")
+        return
     ok = tn.accumulating_swipe(x, y, loss_fn, batch_size=wl["batch_size"], num_swipes=steps, lr=1.0, method="ridge_cholesky",
                                eps=args.eps, orthonormalize=wl.get("orthonormalize", False), block_callback=cb,
-                               model_device=layer.tensor_network.main_nodes[0].tensor.device)
+                               data_device=data_device, model_device=layer.tensor_network.main_nodes[0].tensor.device)
     if not ok:
         raise RuntimeError("sweep reported a singular system")
 
@@ -236,7 +258,7 @@ def bench_b200(args):
     if wl.get("orthonormalize"):
         tn.orthonormalize_left()
 
-    timer = KernelTimer(ops, ["gram", "rhs", "env_update", "predict", "cholesky_solve", "cholesky_solve_mixed", "gram_expand"])
+    timer = KernelTimer(ops, ["gram", "rhs", "env_update", "predict", "cholesky_solve", "cholesky_solve_mixed", "gram_expand", "matvec"])
     timer.install()
     counter = [0]
 
@@ -281,12 +303,10 @@ def bench_b200(args):
 
         def one_e2e():
             xin = wrap_input(wl, Xh)
-            tn.accumulating_swipe(xin, yh, tnb.SquareBregFunction(), batch_size=wl["batch_size"], num_swipes=1, lr=1.0,
-                                  method="ridge_cholesky", eps=args.eps, orthonormalize=wl.get("orthonormalize", False),
-                                  block_callback=lambda NS, node: counter2.__setitem__(0, counter2[0] + 1),
-                                  data_device=torch.device("cpu"), model_device=dev)
+            run_sweeps(layer, xin, yh, wl, args, 1, counter2, data_device=torch.device("cpu"))
             pred = tn.forward_batch(wrap_input(wl, X[:1024]), -1)
-            got.append(float(((pred - y[:1024]) ** 2).mean().item()))      # device -> host read of the result
+            yy = y[:1024] if wl["C"] == 1 else y[:1024, :wl["C"]]
+            got.append(float(((pred - yy) ** 2).mean().item()))      # device -> host read of the result
 
         one_e2e()
         barrier()
@@ -345,6 +365,19 @@ def bench_b200(args):
                 "survey_equiv_tflops": algo / gsum / 1e12 if gsum > 0 else 0.0,
                 "share_of_step": gsum / (ms / 1e3), "launches": len(gram_ms), "measured_peaks": measured,
                 "bf16_peaks_file": {k: peaks.get(k) for k in ("bf16_tflops", "bf16_tflops_sustained", "hbm_gbs")}}
+    if wl.get("solver"):
+        mv_ms = tot["matvec"]
+        mv_bytes = sum(timer.extra["matvec"])
+        mv_s = sum(mv_ms) / 1e3
+        hbm = peaks.get("hbm_gbs", 6550.7)
+        roofline = {"kernel": "matvec_kr3 (env_kernel dot epilogue + kr3 rhs pass)", "bound": "hbm",
+                    "achieved": mv_bytes / mv_s / 1e9 if mv_s > 0 else 0.0, "peak": hbm, "unit": "GB/s",
+                    "frac": (mv_bytes / mv_s / 1e9 / hbm) if mv_s > 0 else None, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6550.7 GB/s",
+                    "share_of_step": mv_s / (ms / 1e3), "launches": len(mv_ms),
+                    "matvecs_per_site_update": len(mv_ms) / max(updates, 1),
+                    "mean_us_per_matvec": 1e3 * sum(mv_ms) / max(len(mv_ms), 1), "measured_peaks": measured}
+        wl = dict(wl, _avg_matvecs=len(mv_ms) / max(updates, 1))
     chol_ms = tot["cholesky_solve"] + tot["cholesky_solve_mixed"]
     chol_flops = sum(P_ ** 3 / 3.0 for P_ in timer.extra["cholesky_solve"] + timer.extra["cholesky_solve_mixed"])
     n_mixed = len(tot["cholesky_solve_mixed"])
@@ -391,6 +424,11 @@ def cpu_site_time(wl, rows, reps=1):
     if wl["bias"]:
         X = np.concatenate([X, np.ones((rows, 1))], 1)
     y = rng.normal(size=(rows, 1))
+    loss_of = orc.loss_square
+    if wl["C"] > 1:
+        y = np.eye(wl["C"] + 1)[rng.integers(0, wl["C"] + 1, rows)]
+        loss_of = orc.loss_xe
+    nmv = wl.get("_avg_matvecs")
     xin = X if wl["basis"] is None else (orc.fbasis(X) if wl["basis"] == "sin-cos" else orc.polynomial_basis(X, wl.get("degree", 3)))
     n = len(cores)
     shapes = {}
@@ -409,8 +447,17 @@ def cpu_site_time(wl, rows, reps=1):
             phis = orc.site_inputs(xin, n)
             Ls, Rs = orc.left_envs(cores, phis), orc.right_envs(cores, phis)
             pred = Ls[-1][:, :, 0]
-            lo, g, H = orc.loss_square(pred, y)
+            lo, g, H = loss_of(pred, y)
             J = orc.jacobian(cores, phis, k, Ls[k - 1] if k > 0 else np.ones((rows, 1, 1)), Rs[k + 1] if k < n - 1 else np.ones((rows, 1, 1)))
+        if wl.get("solver"):
+            # matrix-free local solve (network.py:770-790): rhs + nmv matvecs, each J^T (H (J v)) on the materialised batch Jacobian
+            b = np.einsum("scP,sc->P", J, g)
+            t_batch += (time.perf_counter() - t0) * len(ks)
+            v = rng.normal(size=b.size)
+            t0 = time.perf_counter()
+            orc.matvec(J, H, v)
+            t_batch += (time.perf_counter() - t0) * len(ks) * nmv
+            continue
         A, b = orc.gram(J, g, H)
         t_batch += (time.perf_counter() - t0) * len(ks)
         P = b.size
@@ -424,11 +471,20 @@ def cpu_site_time(wl, rows, reps=1):
 
 
 def cpu_baseline(args, wl, rows_total):
-    rows = args.ref_rows or (256 if args.workload == "cfg5a" else 2048)
+    rows = args.ref_rows or (256 if args.workload == "cfg5a" else (128 if wl.get("solver") else 2048))
+    if wl.get("solver") and "_avg_matvecs" not in wl:
+        wl = dict(wl, _avg_matvecs=float(args.ref_matvecs))
     t_batch, t_solve, n = cpu_site_time(wl, rows)
     per_sweep_sites = max(2 * n - 2, 1)
     t_all_sites = t_batch * (rows_total / rows) + t_solve     # every site once
     value = n / t_all_sites * rows_total
+    if wl.get("solver"):
+        return {"value": value, "unit": "sample-site-updates/s", "site_updates_per_s": n / t_all_sites, "cores": os.cpu_count(),
+                "kind": "port",
+                "sample": f"oracle port (numpy/BLAS, all host threads) of the matrix-free site update: envs + batch Jacobian + rhs + "
+                          f"{wl['_avg_matvecs']:.1f} matvecs J^T(H(Jv)) per site (the count the GPU run needed on average) for every "
+                          f"distinct site shape on one {rows}-row minibatch ({t_batch:.2f} s for all sites); per-row cost "
+                          f"extrapolated linearly to {rows_total} rows"}
     return {"value": value, "unit": "sample-site-updates/s", "site_updates_per_s": n / t_all_sites, "cores": os.cpu_count(), "kind": "port",
             "sample": f"oracle port (numpy/BLAS, all host threads): env + Jacobian + Gram + rhs of every site on one {rows}-row "
                       f"minibatch ({t_batch:.2f} s) plus the dense solves with P<=4096 ({t_solve:.2f} s; larger P not timed, "
@@ -442,7 +498,9 @@ def bench_reference(args):
     wl = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n = (args.n if args.n is not None else wl["n"]) * world
-    rows = args.ref_rows or (256 if args.workload == "cfg5a" else 2048)
+    rows = args.ref_rows or (256 if args.workload == "cfg5a" else (128 if wl.get("solver") else 2048))
+    if wl.get("solver"):
+        wl = dict(wl, _avg_matvecs=float(args.ref_matvecs))
     for _ in range(args.warmup):
         cpu_site_time(wl, min(rows, 64))
     t0 = time.perf_counter()
@@ -454,6 +512,10 @@ def bench_reference(args):
     value = float(np.median(vals))
     sample = (f"oracle port of tensor/network.py (numpy/BLAS, {os.cpu_count()} host threads): per step, env+Jacobian+Gram+rhs of every "
               f"site on one {rows}-row minibatch and the dense solves with P<=4096, extrapolated linearly to {n} rows")
+    if wl.get("solver"):
+        sample = (f"oracle port of tensor/network.py:709-932 (numpy/BLAS, {os.cpu_count()} host threads): per step, envs + batch Jacobian + "
+                  f"rhs + {wl['_avg_matvecs']:.0f} matvecs per site (--ref-matvecs) of every distinct site shape on one {rows}-row "
+                  f"minibatch, extrapolated linearly to {n} rows")
     out = {"impl": "reference", "metric": "gn_sample_site_updates_per_s", "value": value, "unit": "sample-site-updates/s",
            "site_updates_per_s": value / n, "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3, "higher_is_better": True,

@@ -604,6 +604,15 @@ class TensorNetwork:
             self.solve_stats["fp64"] += 1
             info = ops.cholesky_solve(A, rhs)
         bad = int(info.item())
+        if self.process_group is not None:
+            # every rank solved the same all-reduced system, but the substitution / refinement kernels sum with atomics,
+            # so the last bits may differ between ranks: rank 0's step is the one everybody applies (cores stay identical)
+            import torch.distributed as dist
+            flag = torch.tensor([float(bad)], dtype=torch.float64, device=rhs.device)
+            src = dist.get_global_rank(self.process_group, 0)
+            dist.broadcast(flag, src=src, group=self.process_group)
+            dist.broadcast(rhs, src=src, group=self.process_group)
+            bad = int(flag.item())
         if bad != 0:
             raise torch.linalg.LinAlgError(
                 f"linalg.cholesky: The factorization could not be completed because the input is not positive-definite "
