@@ -144,6 +144,13 @@ int64_t tn_matvec_work_elems(int64_t rows, int ma, int mb, int mc);
 int tn_matvec_kr3(const tn_factor *fa, const tn_factor *fb, const tn_factor *fc, const double *w, int64_t rows,
                   const double *v, double *out, double *work, void *stream);
 
+/* ---- per-sample small matrix products of the patch/pixel ("conv-TT") layer
+ *      (TensorConvolutionTrainLayer, tensor/layers.py:791-890; closed forms in SURVEY.md Appendix C):
+ * out[s, i, j] (+)= sum_k A[s*sA + i*iA + k*kA] * B[s*sB + k*kB + j*jB],  out [S, I, J] contiguous.
+ * A stride sA or sB of 0 shares that operand between all samples.                                   */
+int tn_bmm(const double *A, int64_t sA, int64_t iA, int64_t kA, const double *B, int64_t sB, int64_t kB, int64_t jB,
+           double *out, int64_t S, int I, int K, int J, int accumulate, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "tn_update_node": (i32, [vp, vp, i64, f64, i32, f64, vp, vp]),
     "tn_qr": (i32, [vp, i32, i32, vp, vp]),
     "tn_matvec_work_elems": (i64, [i64, i32, i32, i32]),
+    "tn_bmm": (i32, [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i32, i32, i32, i32, vp]),
     "tn_matvec_kr3": (i32, [FP, FP, FP, vp, i64, vp, vp, vp, vp]),
 }
 

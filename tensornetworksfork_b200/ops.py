@@ -263,3 +263,22 @@ def matvec(fa: Factor, fb: Factor, fc: Factor, w, rows, v, out=None):
     _lib.check(lib.tn_matvec_kr3(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), _p(w), rows, _p(v), _p(out), _p(work),
                                  _stream()), "tn_matvec_kr3")
     return out
+
+
+def bmm(A, B, out=None, accumulate=False):
+    """Per-sample matrix products out[s] (+)= A[s] @ B[s].  A: (S, I, K) or (I, K) shared; B: (S, K, J) or (K, J) shared;
+    any strides (views are not copied).  Returns (S, I, J) contiguous."""
+    lib = _lib.load()
+    _need_cuda(A, B)
+    S = A.shape[0] if A.dim() == 3 else B.shape[0]
+    sA, (iA, kA) = (A.stride(0), A.stride()[1:]) if A.dim() == 3 else (0, A.stride())
+    sB, (kB, jB) = (B.stride(0), B.stride()[1:]) if B.dim() == 3 else (0, B.stride())
+    I, K = A.shape[-2:]
+    K2, J = B.shape[-2:]
+    assert K == K2, (A.shape, B.shape)
+    if out is None:
+        out = torch.empty((S, I, J), dtype=torch.float64, device=A.device)
+        accumulate = False
+    assert out.is_contiguous() and tuple(out.shape) == (S, I, J)
+    _lib.check(lib.tn_bmm(_p(A), sA, iA, kA, _p(B), sB, kB, jB, _p(out), S, I, K, J, 1 if accumulate else 0, _stream()), "tn_bmm")
+    return out

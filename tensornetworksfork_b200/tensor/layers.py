@@ -350,3 +350,81 @@ class TensorTrainDMRGInfiLayer(TensorNetworkLayer):
         self.num_carriages += 1
         self._rebuild([], node.tensor.device)
         return split_err
+
+
+class TensorConvolutionTrainLayer(TensorNetworkLayer):
+    """Patch/pixel "conv-TT": per column an input node x[s, patches, patch_pixels], a pixel core C_k over the pixels of a
+    patch (bond ``convolution_bond``) and a patch core A_k over the patches (bond ``bond_dim``); the output leg sits on A_1.
+
+    Same constructor, node names, labels, train-node order (C1, A1, C2, A2, ...) and random-number consumption as the
+    reference (tensor/layers.py:791-890), so the same ``torch.manual_seed`` gives the same initial cores; the network object
+    is the B200 engine ``ConvTrainNetwork`` (matrix-free sweeps)."""
+
+    def __init__(self, num_carriages, bond_dim, num_patches, patch_pixels, output_shape, ring=False, convolution_bond=-1, dtype=None,
+                 constrict_bond=True, perturb=False):
+        from .conv import ConvTrainNetwork
+        if ring:
+            raise NotImplementedError("Ring structure is not implemented for TensorConvolutionTrainLayer.")
+        self.num_carriages = num_carriages
+        self.bond_dim = bond_dim
+        self.num_patches = num_patches
+        self.patch_pixels = patch_pixels
+        self.output_shape = output_shape if isinstance(output_shape, tuple) else (output_shape,)
+        self.ring = ring
+        self.convolution_bond = convolution_bond
+        self.output_labels = ("s",)
+        n, Q, T, r, CB = num_carriages, num_patches, patch_pixels, bond_dim, convolution_bond
+
+        if perturb:
+            # first core random, every other core the identity on the bias patch (reference :812-836)
+            def bias_identity(rl, rr):
+                blk = torch.diag_embed(torch.ones(rr, dtype=dtype)) if rl == rr else torch.ones(rl, rr, dtype=dtype)
+                return torch.cat((torch.zeros(rl, Q - 1, rr), blk.unsqueeze(1)), dim=1)
+            first = torch.randn((1, Q, r), dtype=dtype)
+            blocks = [first] + [bias_identity(r, r) for _ in range(n - 2)] + [bias_identity(r, 1)]
+            blocks = [b.unsqueeze(1) for b in blocks]
+        else:
+            blocks = [(r if i != 1 else 1, self.output_shape[i - 1] if i <= len(self.output_shape) else 1, Q, r if i != n else 1)
+                      for i in range(1, n + 1)]
+
+        x_nodes, conv_blocks, train_blocks = [], [], []
+        for i in range(1, n + 1):
+            up = f"c{i}" if i - 1 < len(self.output_shape) else "c"
+            x_node = TensorNode((1, Q, T), ["s", "patches", "patch_pixels"], name=f"X{i}")
+            if CB > 0:
+                conv = TensorNode((CB if i != 1 else 1, T, CB if i != n else 1), [f"CB{i}", "patch_pixels", f"CB{i + 1}"],
+                                  l=f"CB{i}", r=f"CB{i + 1}", name=f"C{i}")
+            else:
+                conv = TensorNode((T,), ["patch_pixels"], name=f"C{i}")
+            train = TensorNode(blocks[i - 1], [f"r{i}", up, "patches", f"r{i + 1}"], l=f"r{i}", r=f"r{i + 1}", name=f"A{i}")
+            x_nodes.append(x_node)
+            conv_blocks.append(conv)
+            train_blocks.append(train)
+            if i < len(self.output_shape) + 1:
+                self.output_labels = self.output_labels + (f"c{i}",)
+
+        self.nodes = []
+        for xn, cb, tb in zip(x_nodes, conv_blocks, train_blocks):
+            xn.connect(tb, "patches")
+            cb.connect(xn, "patch_pixels")
+            self.nodes.append(cb)
+            self.nodes.append(tb)
+        for i in range(1, n):
+            train_blocks[i - 1].connect(train_blocks[i], f"r{i + 1}")
+        if CB > 0:
+            for i in range(1, n):
+                conv_blocks[i - 1].connect(conv_blocks[i], f"CB{i + 1}")
+        for nd in train_blocks + conv_blocks:
+            nd.squeeze()
+
+        self.x_nodes = x_nodes
+        self.conv_blocks = conv_blocks
+        self.train_blocks = train_blocks
+        self.labels = self.output_labels
+        super().__init__(ConvTrainNetwork(x_nodes, train_blocks, self.nodes, output_labels=self.labels))
+        self.input_nodes = x_nodes
+        self.main_nodes = train_blocks
+        self.train_nodes = train_blocks + conv_blocks
+
+    def grow_cart(self, new_bond=None, new_convolution_bond=None):
+        raise NotImplementedError("grow_cart (adding a column to a trained conv-TT, reference tensor/layers.py:892-947)")

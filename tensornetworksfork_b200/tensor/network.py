@@ -853,6 +853,19 @@ class TensorNetwork:
 
         return prob, b, matvec
 
+    def _krylov_problem(self, node, y, loss_fn):
+        """(per-row loss, right-hand side b, matvec v -> J^T H J v) of one node, everything flat in canonical order."""
+        prob, b, matvec = self._krylov_setup(self.main_nodes.index(node), y, loss_fn)
+        return prob["loss"], b, matvec
+
+    def _apply_step(self, node, step_c, lr):
+        k = self.main_nodes.index(node)
+        step = self._from_canon(k, step_c.reshape(self._canon(k).shape))
+        new = node.tensor.detach().clone().contiguous()
+        ops.update_node(new.view(-1), step.view(-1), lr=lr)
+        node.tensor = new
+        self._core_changed(k)
+
     def _krylov_swipe(self, x, y_true, loss_fn, solve, batch_size, num_swipes, lr, timeout, data_device, model_device,
                       block_callback, loss_callback, what):
         x, y = self._prepare_data(x, y_true, data_device, model_device)
@@ -864,20 +877,15 @@ class TensorNetwork:
                     print(f"Timeout reached ({timeout} seconds). Stopping {what}.")
                     return False
                 self._check_external()
-                k = self.main_nodes.index(node)
-                prob, b, matvec = self._krylov_setup(k, y, loss_fn)
+                loss_rows, b, matvec = self._krylov_problem(node, y, loss_fn)
                 if loss_callback is not None:
-                    S = prob["yhat"].shape[0]
-                    lv = batch_mean_of_means(prob["loss"], batch_size, row_offset=self.shard_offset,
+                    S = loss_rows.shape[0]
+                    lv = batch_mean_of_means(loss_rows, batch_size, row_offset=self.shard_offset,
                                              n_total=self.shard_total if self.process_group is not None else S,
                                              group=self.process_group)
                     loss_callback(float(lv.item()))
                 step_c = solve(node, matvec, b)                       # canonical order, flat
-                step = self._from_canon(k, step_c.reshape(self._canon(k).shape))
-                new = node.tensor.detach().clone().contiguous()
-                ops.update_node(new.view(-1), step.view(-1), lr=lr)
-                node.tensor = new
-                self._core_changed(k)
+                self._apply_step(node, step_c, lr)
                 if block_callback is not None:
                     block_callback(NS, node)
         return True

@@ -171,7 +171,7 @@ def matvec(fa, fb, fc, w, rows, v, out=None):
 
 
 NAMES = ["ones_factor", "env_update", "predict", "class_rows", "gram", "rhs", "gram_generic", "gram_sigma", "gram_expand", "rhs_prepare",
-         "cholesky_solve", "update_node", "qr", "matvec"]
+         "cholesky_solve", "cholesky_solve_mixed", "update_node", "qr", "matvec", "bmm"]
 
 
 def install(monkeypatch=None):
@@ -184,7 +184,22 @@ def install(monkeypatch=None):
             monkeypatch.setattr(real, n, getattr(me, n))
         else:
             setattr(real, n, getattr(me, n))
-    if monkeypatch is not None:
-        monkeypatch.setattr(network.TensorNetwork, "_require_cuda", lambda self, dev: None)
+    from tensornetworksfork_b200.tensor import conv
+    for cls in (network.TensorNetwork, conv.ConvTrainNetwork):
+        if monkeypatch is not None:
+            monkeypatch.setattr(cls, "_require_cuda", lambda self, dev: None)
+        else:
+            cls._require_cuda = lambda self, dev: None
+
+
+def bmm(A, B, out=None, accumulate=False):
+    r = torch.matmul(A, B)
+    if r.dim() == 2:
+        r = r.unsqueeze(0)
+    if out is None:
+        return r.contiguous()
+    if accumulate:
+        out += r
     else:
-        network.TensorNetwork._require_cuda = lambda self, dev: None
+        out.copy_(r)
+    return out

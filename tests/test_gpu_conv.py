@@ -1,0 +1,79 @@
+"""Conv-TT (TensorConvolutionTrainLayer) on the real kernels against the reference recordings and the numpy oracle (needs a B200)."""
+import numpy as np
+import pytest
+import torch
+
+import conv_cases as cc
+import golden_util as gu
+from oracle import conv_oracle as co
+
+pytestmark = pytest.mark.gpu
+torch.set_default_dtype(torch.float64)
+
+from tensornetworksfork_b200 import ops  # noqa: E402
+
+
+@pytest.mark.parametrize("S,I,K,J", [(1, 1, 1, 1), (7, 3, 4, 5), (1000, 50, 4, 38), (513, 144, 50, 17), (300, 36, 38, 68), (2049, 2, 3, 2)])
+def test_bmm_kernel(S, I, K, J):
+    rng = np.random.default_rng(S + I)
+    A, B = rng.normal(size=(S, I, K)), rng.normal(size=(S, K, J))
+    want = np.einsum("sik,skj->sij", A, B)
+    At, Bt = torch.tensor(A, device="cuda"), torch.tensor(B, device="cuda")
+    assert gu.relerr(ops.bmm(At, Bt).cpu().numpy(), want) < 1e-14
+    # strided views (the layouts the conv-TT engine passes) and a shared right operand
+    Av = torch.tensor(np.ascontiguousarray(A.transpose(2, 0, 1)), device="cuda").permute(1, 2, 0)      # (S, I, K) view of (K, S, I)
+    assert gu.relerr(ops.bmm(Av, Bt).cpu().numpy(), want) < 1e-14
+    want2 = np.einsum("sik,kj->sij", A, B[0])
+    assert gu.relerr(ops.bmm(At, Bt[0]).cpu().numpy(), want2) < 1e-14
+    out = torch.ones((S, I, J), device="cuda")
+    ops.bmm(At, Bt, out=out, accumulate=True)
+    assert gu.relerr(out.cpu().numpy(), want + 1.0) < 1e-14
+
+
+@pytest.mark.parametrize("name", ["conv_lanczos_xe", "conv_lanczos_reg"])
+@pytest.mark.parametrize("chunk", [None, 37])
+def test_conv_lanczos_swipe_gpu(name, chunk):
+    fwd, core, loss, pred = cc.run_case(name, "cuda", chunk_rows=chunk)
+    assert fwd < 1e-12 and core < 1e-8 and loss < 1e-9 and pred < 1e-8, (fwd, core, loss, pred)
+
+
+@pytest.mark.parametrize("name", ["conv_scipy_cg", "conv_scipy_minres", "conv_scipy_cg_2col"])
+def test_conv_scipy_swipe_gpu(name):
+    fwd, core, loss, pred = cc.run_case(name, "cuda", scipy_object=True)
+    assert fwd < 1e-12 and core < 5e-4 and loss < 5e-5, (fwd, core, loss, pred)
+    fwd, core, loss, pred = cc.run_case(name, "cuda", scipy_object=False)      # on-device fp64 CG / MINRES
+    assert loss < 5e-3, (core, loss)
+
+
+def test_conv_jacobians_and_matvec_against_oracle_mnist_like_shape():
+    """Config-4b-like column shapes (50 patches x 17 pixels, r = 12, CB = 4, 9 logits) on seeded data: the rhs and matvec of every
+    node against the dense Jacobian of the numpy oracle."""
+    import tensornetworksfork_b200 as tnb
+    torch.manual_seed(3)
+    rng = np.random.default_rng(3)
+    S, Q, T, C = 96, 50, 17, 9
+    layer = tnb.TensorConvolutionTrainLayer(num_carriages=3, bond_dim=12, num_patches=Q, patch_pixels=T, output_shape=C, convolution_bond=4)
+    tn = layer.tensor_network
+    for n in tn.train_nodes:                       # unit-norm random cores give vanishing outputs; scale them up a little
+        n.tensor = n.tensor * 3.0
+    names = [n.name for n in tn.train_nodes]
+    cores = [n.tensor.numpy().copy() for n in tn.train_nodes]
+    x = rng.uniform(-1, 1, size=(S, Q, T))
+    x[:, -1, :] = 0.0; x[:, :, -1] = 0.0; x[:, -1, -1] = 1.0
+    y = np.eye(C + 1)[rng.integers(0, C + 1, S)]
+    layer.to("cuda")
+    tn.chunk_rows = 40
+    X, Y = torch.tensor(x, device="cuda"), torch.tensor(y, device="cuda")
+    A, Cc = co.canon_cores(cores, names, C)
+    assert gu.relerr(layer(X).cpu().numpy(), co.forward(A, Cc, x)) < 1e-12
+    loss_fn = tnb.XEAutogradBregman(w=1.0)
+    tn._prepare_data(X, Y, None, None)
+    for idx, node in enumerate(tn.train_nodes):
+        lo, b, parts = co.site_problem(cores, names, C, x, y, "xe", idx, -1)
+        loss_rows, bg, mv = tn._krylov_problem(node, Y, loss_fn)
+        assert gu.relerr(bg.cpu().numpy(), b) < 1e-11, node.name
+        assert abs(float(loss_rows.mean().item()) - lo) < 1e-12
+        v = rng.normal(size=b.size)
+        want = co.matvec_of(parts)(v)
+        got = mv(torch.tensor(v, device="cuda")).cpu().numpy()
+        assert gu.relerr(got, want) < 1e-11, node.name
