@@ -40,6 +40,10 @@ WORKLOADS = {
                   perturb=False, batch_size=1024, solver="cg", max_iter=500, tol=1e-3,
                   desc="TNML sin-cos classifier MNIST-shaped N=60000 F=784 10 classes (C=9 logits, XE loss) r=38, matrix-free "
                        "local solve scipy_swipe('cg', max_iter=500, tol=1e-3)"),
+    "cfg4b": dict(kind="conv", sites=3, r=38, CB=4, patches=50, pixels=17, features=49 * 16, bias=False, basis=None, C=9, n=60000,
+                  batch_size=1024, solver="minres", max_iter=100, tol=1e-3,
+                  desc="conv-TT (TensorConvolutionTrainLayer) MNIST-shaped N=60000, 49+1 patches x 16+1 pixels, 3 columns, r=38, CB=4, "
+                       "9 logits (XE loss), matrix-free local solve scipy_swipe('minres', max_iter=100, tol=1e-3); P(A2)=72200"),
     "cfg5a": dict(kind="tt", sites=5, r=38, features=28, bias=True, basis=None, C=1, n=1000000, constrict=False,
                   perturb=False, batch_size=-1, desc="TT poly-mode higgs-shaped F=28(+1) r=38 5 cores (degree 5), P=41876"),
     "cfg5b": dict(kind="tt", sites=28, r=38, features=28, bias=False, basis="polynomial", degree=5, C=1, n=1000000,
@@ -63,6 +67,7 @@ def parse():
     ap.add_argument("--eps", type=float, default=1.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--max-iter", type=int, default=None, help="Krylov iterations per node (matrix-free workloads)")
     ap.add_argument("--ref-rows", type=int, default=None)
     ap.add_argument("--ref-matvecs", type=float, default=20.0,
                     help="matvecs per site assumed by --impl reference on the matrix-free workloads (the b200 arm reports its own count)")
@@ -73,6 +78,16 @@ def make_data(wl, n, seed, device):
     """Synthetic rows of the workload's shape: X ~ U(-1,1), y = smooth teacher + noise."""
     g = torch.Generator(device="cpu").manual_seed(seed)
     F = wl["features"]
+    if wl["kind"] == "conv":
+        # unfolded image patches with the bias patch / bias pixel of image_convolution_CG_MNIST.py:29-32
+        Q, T = wl["patches"], wl["pixels"]
+        X = torch.zeros((n, Q, T), dtype=torch.float64)
+        X[:, :-1, :-1] = torch.rand((n, Q - 1, T - 1), generator=g, dtype=torch.float64) * 2 - 1
+        X[:, -1, -1] = 1.0
+        Wc = torch.randn(((Q - 1) * (T - 1), wl["C"] + 1), generator=torch.Generator(device="cpu").manual_seed(7), dtype=torch.float64)
+        lab = (X[:, :-1, :-1].reshape(n, -1) @ Wc).argmax(dim=1)
+        y = torch.nn.functional.one_hot(lab, num_classes=wl["C"] + 1).to(torch.float64)
+        return X.to(device), y.to(device)
     X = torch.rand((n, F), generator=g, dtype=torch.float64) * 2 - 1
     w1 = torch.randn((F, 1), generator=g, dtype=torch.float64) / F ** 0.5
     w2 = torch.randn((F, 1), generator=g, dtype=torch.float64) / F ** 0.5
@@ -90,6 +105,11 @@ def build_model(wl, device, gram_mode):
     f = wl["features"] + 1 if wl["bias"] else (2 if wl["basis"] == "sin-cos" else wl.get("degree", 3) + 1)
     if wl["kind"] == "cpd":
         layer = tnb.CPDLayer(wl["sites"], wl["r"], f, output_shape=(wl["C"],), seed=42)
+    elif wl["kind"] == "conv":
+        torch.manual_seed(42)
+        layer = tnb.TensorConvolutionTrainLayer(wl["sites"], wl["r"], wl["patches"], wl["pixels"], wl["C"], convolution_bond=wl["CB"])
+        for nd in layer.tensor_network.train_nodes:      # unit-norm random cores give vanishing logits; start at O(1) outputs
+            nd.tensor = nd.tensor * 4.0
     else:
         layer = tnb.TensorTrainLayer(wl["sites"], wl["r"], f, output_shape=wl["C"], constrict_bond=wl["constrict"],
                                      perturb=wl["perturb"], seed=42)
@@ -181,6 +201,21 @@ class KernelTimer:
             # keep sizes only: holding the argument tensors would pin every 14 GB system matrix of the step
             if n == "gram":
                 self.extra[n].append((a[1].m, a[2].m, a[3].m, a[5]))
+            elif n in ("predict", "env_update"):
+                core = a[2]
+                self.extra[n].append(2.0 * a[3 if n == "env_update" else 4] * core.shape[0] * core.shape[1] * core.shape[2])
+            elif n == "outer_rows":      # (flops, algorithmic bytes: W streamed once, G read, out written)
+                rows_, m_, ra_ = a[1].shape[0], a[1].shape[1], a[0].shape[1]
+                self.extra[n].append((2.0 * rows_ * m_ * ra_, 8.0 * (rows_ * m_ + a[0].shape[0] * ra_ + ra_ * m_)))
+            elif n == "rows_dot":
+                rows_, m_, ra_ = a[0].shape[0], a[0].shape[1], a[1].shape[0]
+                self.extra[n].append((2.0 * rows_ * m_ * ra_, 8.0 * (rows_ * m_ + rows_ * ra_ + ra_ * m_)))
+            elif n == "bmm":
+                A_, B_ = a[0], a[1]
+                S_ = A_.shape[0] if A_.dim() == 3 else B_.shape[0]
+                self.extra[n].append(2.0 * S_ * A_.shape[-2] * A_.shape[-1] * B_.shape[-1])
+            elif n == "rhs":
+                self.extra[n].append(2.0 * a[4] * a[0].m * a[1].m * a[2].m)
             elif n == "matvec":
                 fa, fb, fc, rows = a[0], a[1], a[2], a[4]
                 raw_b = 1 if fb.map_kind != 0 else fb.m
@@ -245,6 +280,8 @@ def bench_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     wl = WORKLOADS[args.workload]
+    if args.max_iter is not None and wl.get("solver"):
+        wl = dict(wl, max_iter=args.max_iter)
     n = args.n if args.n is not None else wl["n"]
     layer, f = build_model(wl, dev, args.gram_mode)
     tn = layer.tensor_network
@@ -258,7 +295,7 @@ def bench_b200(args):
     if wl.get("orthonormalize"):
         tn.orthonormalize_left()
 
-    timer = KernelTimer(ops, ["gram", "rhs", "env_update", "predict", "cholesky_solve", "cholesky_solve_mixed", "gram_expand", "matvec"])
+    timer = KernelTimer(ops, ["gram", "rhs", "env_update", "predict", "cholesky_solve", "cholesky_solve_mixed", "gram_expand", "matvec", "outer_rows", "rows_dot", "bmm"])
     timer.install()
     counter = [0]
 
@@ -365,7 +402,25 @@ def bench_b200(args):
                 "survey_equiv_tflops": algo / gsum / 1e12 if gsum > 0 else 0.0,
                 "share_of_step": gsum / (ms / 1e3), "launches": len(gram_ms), "measured_peaks": measured,
                 "bf16_peaks_file": {k: peaks.get(k) for k in ("bf16_tflops", "bf16_tflops_sustained", "hbm_gbs")}}
-    if wl.get("solver"):
+    if wl["kind"] == "conv":
+        # dominant kernels: the two passes of the matrix-free matvec over the folded patch input (streamed once each): HBM-bound
+        hot = ("rows_dot", "outer_rows")
+        by = sum(b_ for k_ in hot for _, b_ in timer.extra[k_])
+        fl = sum(f_ for k_ in hot for f_, _ in timer.extra[k_])
+        sec = sum(sum(tot[k_]) for k_ in hot) / 1e3
+        hbm = peaks.get("hbm_gbs", 6550.7)
+        other = ("predict", "rhs", "env_update", "bmm")
+        roofline = {"kernel": "rows_dot_kernel + outer_rows_kernel (J v and J^T u passes of the matrix-free matvec over the folded patch input)",
+                    "bound": "hbm", "achieved": by / sec / 1e9 if sec > 0 else 0.0, "peak": hbm, "unit": "GB/s",
+                    "frac": by / sec / 1e9 / hbm if sec > 0 else None, "traffic": None,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6550.7 GB/s",
+                    "share_of_step": sec / (ms / 1e3), "launches": sum(len(tot[k_]) for k_ in hot),
+                    "fp64_tflops": fl / sec / 1e12 if sec > 0 else None,
+                    "matvecs_per_site_update": len(tot["rows_dot"]) / max(updates, 1),
+                    "other_kernels_tflops": {k_: (sum(timer.extra[k_]) / (sum(tot[k_]) / 1e3) / 1e12 if tot[k_] else None) for k_ in other},
+                    "measured_peaks": measured}
+        wl = dict(wl, _avg_matvecs=20.0)
+    elif wl.get("solver"):
         mv_ms = tot["matvec"]
         mv_bytes = sum(timer.extra["matvec"])
         mv_s = sum(mv_ms) / 1e3
@@ -413,6 +468,26 @@ def cpu_site_time(wl, rows, reps=1):
     (one minibatch), and the dense solve per site, on all host threads."""
     from oracle import tn_oracle as orc
     import tensornetworksfork_b200 as tnb
+    if wl["kind"] == "conv":
+        from oracle import conv_oracle as co
+        torch.manual_seed(42)
+        layer = tnb.TensorConvolutionTrainLayer(wl["sites"], wl["r"], wl["patches"], wl["pixels"], wl["C"], convolution_bond=wl["CB"])
+        tn_ = layer.tensor_network
+        names = [nd.name for nd in tn_.train_nodes]
+        cores = [nd.tensor.numpy().copy() * 4.0 for nd in tn_.train_nodes]
+        rng = np.random.default_rng(0)
+        X = rng.uniform(-1, 1, size=(rows, wl["patches"], wl["pixels"]))
+        y = np.eye(wl["C"] + 1)[rng.integers(0, wl["C"] + 1, rows)]
+        t_all = 0.0
+        for idx in range(len(cores)):
+            t0 = time.perf_counter()
+            lo, b, parts = co.site_problem(cores, names, wl["C"], X, y, "xe", idx, -1)
+            t_all += time.perf_counter() - t0
+            v = rng.normal(size=b.size)
+            t0 = time.perf_counter()
+            co.matvec_of(parts)(v)
+            t_all += (time.perf_counter() - t0) * wl.get("_avg_matvecs", 20.0)
+        return t_all, 0.0, len(cores)
     f = wl["features"] + 1 if wl["bias"] else (2 if wl["basis"] == "sin-cos" else wl.get("degree", 3) + 1)
     if wl["kind"] == "cpd":
         layer = tnb.CPDLayer(wl["sites"], wl["r"], f, output_shape=(wl["C"],), seed=42)
@@ -471,7 +546,7 @@ def cpu_site_time(wl, rows, reps=1):
 
 
 def cpu_baseline(args, wl, rows_total):
-    rows = args.ref_rows or (256 if args.workload == "cfg5a" else (128 if wl.get("solver") else 2048))
+    rows = args.ref_rows or (256 if args.workload == "cfg5a" else ((32 if wl["kind"] == "conv" else 128) if wl.get("solver") else 2048))
     if wl.get("solver") and "_avg_matvecs" not in wl:
         wl = dict(wl, _avg_matvecs=float(args.ref_matvecs))
     t_batch, t_solve, n = cpu_site_time(wl, rows)
@@ -498,7 +573,7 @@ def bench_reference(args):
     wl = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n = (args.n if args.n is not None else wl["n"]) * world
-    rows = args.ref_rows or (256 if args.workload == "cfg5a" else (128 if wl.get("solver") else 2048))
+    rows = args.ref_rows or (256 if args.workload == "cfg5a" else ((32 if wl["kind"] == "conv" else 128) if wl.get("solver") else 2048))
     if wl.get("solver"):
         wl = dict(wl, _avg_matvecs=float(args.ref_matvecs))
     for _ in range(args.warmup):

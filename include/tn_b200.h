@@ -151,6 +151,17 @@ int tn_matvec_kr3(const tn_factor *fa, const tn_factor *fb, const tn_factor *fc,
 int tn_bmm(const double *A, int64_t sA, int64_t iA, int64_t kA, const double *B, int64_t sB, int64_t kB, int64_t jB,
            double *out, int64_t S, int I, int K, int J, int accumulate, void *stream);
 
+/* Row-reduced outer product (right-hand side / J^T pass of a conv-TT patch core, get_b + the second einsum of the matvec,
+ * tensor/network.py:258-291, 790):  out[i, j] (+)= sum_row w[row] * G[(row / gdiv) * ldg + i] * W[row * ldw + j],
+ * out (ra x m) contiguous, ra <= 128, w may be NULL.  Row ranges are combined with fp64 atomics.                     */
+int tn_outer_rows(const double *G, int64_t ldg, int gdiv, int ra, const double *W, int64_t ldw, int m, const double *w,
+                  int64_t rows, double *out, int accumulate, void *stream);
+
+/* Row-wise products with a shared matrix (J v pass of a conv-TT patch core, tensor/network.py:789):
+ * z[row, i] = sum_j W[row * ldw + j] * V[i * ldv + j],  z (rows x ra) contiguous, ra <= 128.                          */
+int tn_rows_dot(const double *W, int64_t ldw, int m, const double *V, int64_t ldv, int ra, int64_t rows, double *z,
+                void *stream);
+
 #ifdef __cplusplus
 }
 #endif

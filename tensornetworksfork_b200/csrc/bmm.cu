@@ -48,6 +48,129 @@ bmm_kernel(const double* __restrict__ A, int64_t sA, int64_t iA, int64_t kA, con
     }
 }
 
+
+// ---- row-reduced outer product: out[i, j] (+)= sum_row w[row] * G[row*ldg + i] * W[row*ldw + j]      (ra x m, K = rows)
+// The right-hand side / J^T pass of a patch core whose folded site input W is thousands of columns wide (conv-TT): a
+// tall-skinny GEMM G^T W that streams W once (HBM-bound).  CTA tile: all ra rows x 64 columns, 16 sample rows per stage;
+// row ranges are split across blockIdx.y and combined with fp64 atomics.
+constexpr int OR_TN = 64, OR_KC = 16, OR_MAXRA = 128;
+__global__ void __launch_bounds__(256)
+outer_rows_kernel(const double* __restrict__ G, int64_t ldg, int gdiv, int ra, const double* __restrict__ W, int64_t ldw, int m,
+                  const double* __restrict__ w, int64_t rows, int64_t rows_per_split, double* __restrict__ out) {
+    __shared__ double sG[OR_KC][OR_MAXRA + 1];
+    __shared__ double sW[OR_KC][OR_TN + 1];
+    const int tid = threadIdx.x;
+    const int tj = tid & 15, ti = tid >> 4;            // 16 x 16 threads: columns tj + 16*q, rows ti + 16*p
+    const int j0 = blockIdx.x * OR_TN;
+    const int64_t k_begin = (int64_t)blockIdx.y * rows_per_split;
+    const int64_t k_end = (k_begin + rows_per_split < rows) ? k_begin + rows_per_split : rows;
+    double acc[OR_MAXRA / 16][4];
+#pragma unroll
+    for (int p = 0; p < OR_MAXRA / 16; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
+    const int np = (ra + 15) / 16;
+    for (int64_t k0 = k_begin; k0 < k_end; k0 += OR_KC) {
+        __syncthreads();
+        for (int idx = tid; idx < OR_KC * ra; idx += 256) {
+            const int kk = idx / ra, i = idx - kk * ra;
+            const int64_t row = k0 + kk;
+            double v = 0.0;
+            if (row < k_end) v = G[(gdiv == 1 ? row : row / gdiv) * ldg + i] * (w ? w[row] : 1.0);
+            sG[kk][i] = v;
+        }
+        for (int idx = tid; idx < OR_KC * OR_TN; idx += 256) {
+            const int kk = idx >> 6, j = idx & 63;
+            const int64_t row = k0 + kk;
+            sW[kk][j] = (row < k_end && j0 + j < m) ? W[row * ldw + j0 + j] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int kk = 0; kk < OR_KC; ++kk) {
+            double b[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) b[q] = sW[kk][tj + 16 * q];
+#pragma unroll
+            for (int p = 0; p < OR_MAXRA / 16; ++p) {
+                if (p < np) {
+                    const double a = sG[kk][ti + 16 * p];      // entries past ra are never stored below
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[p][q] = fma(a, b[q], acc[p][q]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < OR_MAXRA / 16; ++p) {
+        const int i = ti + 16 * p;
+        if (p < np && i < ra) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int j = j0 + tj + 16 * q;
+                if (j < m) atomicAdd(out + (int64_t)i * m + j, acc[p][q]);
+            }
+        }
+    }
+}
+
+// ---- row-wise products with a shared matrix: z[row, i] = sum_j W[row*ldw + j] * V[i*ldv + j]          (rows x ra, K = m)
+// The J v pass of a conv-TT patch core (first einsum of the matvec, tensor/network.py:789): W is streamed once.
+// CTA tile: 64 rows x all ra outputs, 16 columns of W / V per stage.
+constexpr int RD_TR = 64, RD_KC = 16;
+__global__ void __launch_bounds__(256)
+rows_dot_kernel(const double* __restrict__ W, int64_t ldw, int m, const double* __restrict__ V, int64_t ldv, int ra, int64_t rows,
+                double* __restrict__ z) {
+    __shared__ double sW[RD_TR][RD_KC + 1];
+    __shared__ double sV[OR_MAXRA][RD_KC + 1];
+    const int tid = threadIdx.x;
+    const int tr = tid & 15, ti = tid >> 4;            // rows tr + 16*q (4 per thread), outputs ti + 16*p
+    const int64_t r0 = (int64_t)blockIdx.x * RD_TR;
+    double acc[OR_MAXRA / 16][4];
+#pragma unroll
+    for (int p = 0; p < OR_MAXRA / 16; ++p)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[p][q] = 0.0;
+    const int np = (ra + 15) / 16;
+    for (int j0 = 0; j0 < m; j0 += RD_KC) {
+        __syncthreads();
+        for (int idx = tid; idx < RD_TR * RD_KC; idx += 256) {
+            const int rr = idx >> 4, jj = idx & 15;
+            const int64_t row = r0 + rr;
+            sW[rr][jj] = (row < rows && j0 + jj < m) ? W[row * ldw + j0 + jj] : 0.0;
+        }
+        for (int idx = tid; idx < ra * RD_KC; idx += 256) {
+            const int i = idx >> 4, jj = idx & 15;
+            sV[i][jj] = (j0 + jj < m) ? V[(int64_t)i * ldv + j0 + jj] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int jj = 0; jj < RD_KC; ++jj) {
+            double a[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) a[q] = sW[tr + 16 * q][jj];
+#pragma unroll
+            for (int p = 0; p < OR_MAXRA / 16; ++p) {
+                if (p < np) {
+                    const double b = sV[ti + 16 * p][jj];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) acc[p][q] = fma(a[q], b, acc[p][q]);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int p = 0; p < OR_MAXRA / 16; ++p) {
+        const int i = ti + 16 * p;
+        if (p < np && i < ra) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int64_t row = r0 + tr + 16 * q;
+                if (row < rows) z[row * ra + i] = acc[p][q];
+            }
+        }
+    }
+}
+
 }  // namespace tn
 
 extern "C" int tn_bmm(const double* A, int64_t sA, int64_t iA, int64_t kA, const double* B, int64_t sB, int64_t kB, int64_t jB,
@@ -71,6 +194,39 @@ extern "C" int tn_bmm(const double* A, int64_t sA, int64_t iA, int64_t kA, const
     int64_t blocks = ceil_div64(S, spb);
     if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
     bmm_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(A, sA, iA, kA, B, sB, kB, jB, out, S, I, K, J, accumulate, spb);
+    TN_LAUNCH_CHECK();
+    return TN_OK;
+}
+
+extern "C" int tn_outer_rows(const double* G, int64_t ldg, int gdiv, int ra, const double* W, int64_t ldw, int m, const double* w,
+                             int64_t rows, double* out, int accumulate, void* stream) {
+    using namespace tn;
+    TN_CHECK_ARG(G && W && out && ra >= 1 && ra <= OR_MAXRA && m >= 1 && rows >= 0 && gdiv >= 1, "tn_outer_rows: bad arguments (ra <= %d)", OR_MAXRA);
+    cudaStream_t st = as_stream(stream);
+    if (!accumulate) TN_CUDA(cudaMemsetAsync(out, 0, (size_t)ra * m * sizeof(double), st));
+    if (rows == 0) return TN_OK;
+    const int64_t gx = ceil_div64(m, OR_TN);
+    int64_t splits = ceil_div64(4LL * sm_count(), gx);
+    const int64_t max_splits = ceil_div64(rows, 4 * OR_KC);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
+    if (splits > 65535) splits = 65535;
+    const int64_t rps = ceil_div64(ceil_div64(rows, splits), OR_KC) * OR_KC;
+    splits = ceil_div64(rows, rps);
+    dim3 grid((unsigned)gx, (unsigned)splits);
+    outer_rows_kernel<<<grid, 256, 0, st>>>(G, ldg, gdiv, ra, W, ldw, m, w, rows, rps, out);
+    TN_LAUNCH_CHECK();
+    return TN_OK;
+}
+
+extern "C" int tn_rows_dot(const double* W, int64_t ldw, int m, const double* V, int64_t ldv, int ra, int64_t rows, double* z,
+                           void* stream) {
+    using namespace tn;
+    TN_CHECK_ARG(W && V && z && ra >= 1 && ra <= OR_MAXRA && m >= 1 && rows >= 0, "tn_rows_dot: bad arguments (ra <= %d)", OR_MAXRA);
+    if (rows == 0) return TN_OK;
+    const int64_t grid = ceil_div64(rows, RD_TR);
+    TN_CHECK_ARG(grid <= 0x7fffffff, "tn_rows_dot: too many rows");
+    rows_dot_kernel<<<(unsigned)grid, 256, 0, as_stream(stream)>>>(W, ldw, m, V, ldv, ra, rows, z);
     TN_LAUNCH_CHECK();
     return TN_OK;
 }

@@ -282,3 +282,31 @@ def bmm(A, B, out=None, accumulate=False):
     assert out.is_contiguous() and tuple(out.shape) == (S, I, J)
     _lib.check(lib.tn_bmm(_p(A), sA, iA, kA, _p(B), sB, kB, jB, _p(out), S, I, K, J, 1 if accumulate else 0, _stream()), "tn_bmm")
     return out
+
+
+def outer_rows(G, W, w=None, gdiv=1, out=None, accumulate=False):
+    """out (ra, m) (+)= sum_row w[row] * G[row // gdiv, :]^T W[row, :]; G (rows/gdiv, ra), W (rows, m), row strides free."""
+    lib = _lib.load()
+    _need_cuda(G, W, w)
+    assert G.dim() == 2 and W.dim() == 2 and G.stride(1) == 1 and W.stride(1) == 1
+    rows, m = W.shape
+    ra = G.shape[1]
+    if out is None:
+        out = torch.empty((ra, m), dtype=torch.float64, device=W.device)
+        accumulate = False
+    assert out.is_contiguous()
+    _lib.check(lib.tn_outer_rows(_p(G), G.stride(0), gdiv, ra, _p(W), W.stride(0), m, _p(w), rows, _p(out), 1 if accumulate else 0,
+                                 _stream()), "tn_outer_rows")
+    return out
+
+
+def rows_dot(W, V):
+    """z (rows, ra) = W (rows, m) @ V (ra, m)^T; row strides free, last dims contiguous."""
+    lib = _lib.load()
+    _need_cuda(W, V)
+    assert W.dim() == 2 and V.dim() == 2 and W.stride(1) == 1 and V.stride(1) == 1 and W.shape[1] == V.shape[1]
+    rows, m = W.shape
+    ra = V.shape[0]
+    z = torch.empty((rows, ra), dtype=torch.float64, device=W.device)
+    _lib.check(lib.tn_rows_dot(_p(W), W.stride(0), m, _p(V), V.stride(0), ra, rows, _p(z), _stream()), "tn_rows_dot")
+    return z

@@ -277,6 +277,14 @@ class ConvTrainNetwork(TensorNetwork):
         Rn = self._env_right(k + 1, xc, tag) if k < n - 1 else None                   # (s, a', r')
         Ep = self._env_left(k - 1, xc, tag) if k > 0 else None                        # (s, C, a, r)
 
+        def wide_rhs(G, W, w=None):
+            """(ra, m) flat = sum_rows w[row] G[row,:]^T W[row,:]: the right-hand-side / J^T reduction over the rows."""
+            return ops.outer_rows(G, W, w).view(-1)
+
+        def wide_dot(W, vmat):
+            """z (rows, ra) = W (rows, m) @ vmat (ra, m)^T: the J v pass over a wide per-row operand."""
+            return ops.rows_dot(W, vmat.contiguous())
+
         if kind == "A":
             # YR_a (s, Q*r'): the site input of the patch core with the right environment folded in
             YR = []
@@ -289,30 +297,28 @@ class ConvTrainNetwork(TensorNetwork):
             m = Q * r2
             if k == 0:
                 def rhs_fn(g):
-                    return ops.rhs(Factor(g, m=C), Factor(YR[0], m=m), one, None, s)
+                    return wide_rhs(g.contiguous(), YR[0])
 
                 def jv_fn(v):
-                    core = v.view(C, m).t().reshape(1, m, C)
-                    return ops.env_update(None, Factor(YR[0], m=m), core, s)
-
-                def jt_fn(u):
-                    return ops.rhs(Factor(u, m=C), Factor(YR[0], m=m), one, None, s)
-                return rhs_fn, jv_fn, jt_fn
+                    return wide_dot(YR[0], v.view(C, m))
+                return rhs_fn, jv_fn, rhs_fn
             Ea = [Ep[:, :, al, :].contiguous() for al in range(a)]               # (s, C, r) each
+            eye3 = torch.eye(r, dtype=torch.float64, device=dev).view(r, 1, r)
 
             def fold(w):
                 out = None
                 for al in range(a):
                     _, G = ops.class_rows(Ea[al], None, w)                        # (s, r) = sum_c w[s,c] E_a[s,c,:]
-                    o = ops.rhs(Factor(G, m=r), Factor(YR[al], m=m), one, None, s)
+                    o = wide_rhs(G, YR[al])
                     out = o if out is None else out.add_(o)
                 return out
 
             def jv_fn(v):
-                core = v.view(r, m, 1)
+                vm = v.view(r, m)
                 t = None
                 for al in range(a):
-                    o = ops.predict(Ea[al].view(s * C, r), Factor(YR[al], m=m), core, ones11, s * C, cdiv=C, dot_div=1 << 30)
+                    z = wide_dot(YR[al], vm)                                      # (s, r)
+                    o = ops.predict(Ea[al].view(s * C, r), one, eye3, z, s * C, cdiv=1 << 30, dot_div=C)
                     t = o if t is None else t.add_(o)
                 return t.view(s, C)
             return fold, jv_fn, fold
@@ -336,13 +342,12 @@ class ConvTrainNetwork(TensorNetwork):
         J = ops.bmm(K, xc)                                                         # (s, (c,a,b), T)
         P = a * T * a2
         J = J.view(s, C, a, a2, T).permute(0, 1, 2, 4, 3).contiguous().view(s * C, P)
-        Jf = Factor(J, m=P)
 
         def rhs_fn(g):
-            return ops.rhs(Jf, one, one, g.reshape(s * C).contiguous(), s * C)
+            return wide_rhs(g.reshape(s * C, 1).contiguous(), J)
 
         def jv_fn(v):
-            return ops.predict(J, one, v.view(P, 1, 1), ones11, s * C, cdiv=1 << 30, dot_div=1 << 30).view(s, C)
+            return wide_dot(J, v.view(1, P)).view(s, C)
         return rhs_fn, jv_fn, rhs_fn
 
     def _krylov_problem(self, node, y, loss_fn):

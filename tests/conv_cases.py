@@ -48,7 +48,7 @@ def build(name, device, chunk_rows=None):
     return case, fx, layer
 
 
-def run_case(name, device, scipy_object=True, chunk_rows=None):
+def run_case(name, device, scipy_object=True, chunk_rows=None, loss_prefix=None):
     """Returns (forward error, max relative core error over all updates, max loss error, final prediction error)."""
     case, fx, layer = build(name, device, chunk_rows)
     tn = layer.tensor_network
@@ -83,6 +83,7 @@ def run_case(name, device, scipy_object=True, chunk_rows=None):
     for (_, _, cores), u in zip(ups, fx["updates"]):
         for c, ref in zip(cores, u["after"]):
             core_err = max(core_err, gu.relerr(c, ref))
-    loss_err = float(np.max(np.abs(np.array(losses) - fx["losses"]) / np.maximum(1.0, np.abs(fx["losses"]))))
+    le = np.abs(np.array(losses) - fx["losses"]) / np.maximum(1.0, np.abs(fx["losses"]))
+    loss_err = float(np.max(le[:loss_prefix] if loss_prefix else le))
     pred_err = gu.relerr(layer(X).cpu().numpy(), fx["pred1"])
     return fwd_err, core_err, loss_err, pred_err

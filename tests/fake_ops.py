@@ -171,7 +171,7 @@ def matvec(fa, fb, fc, w, rows, v, out=None):
 
 
 NAMES = ["ones_factor", "env_update", "predict", "class_rows", "gram", "rhs", "gram_generic", "gram_sigma", "gram_expand", "rhs_prepare",
-         "cholesky_solve", "cholesky_solve_mixed", "update_node", "qr", "matvec", "bmm"]
+         "cholesky_solve", "cholesky_solve_mixed", "update_node", "qr", "matvec", "bmm", "outer_rows", "rows_dot"]
 
 
 def install(monkeypatch=None):
@@ -203,3 +203,22 @@ def bmm(A, B, out=None, accumulate=False):
     else:
         out.copy_(r)
     return out
+
+
+def outer_rows(G, W, w=None, gdiv=1, out=None, accumulate=False):
+    rows = W.shape[0]
+    Gr = G[torch.arange(rows) // gdiv]
+    if w is not None:
+        Gr = Gr * w[:, None]
+    r = Gr.t() @ W
+    if out is None:
+        return r.contiguous()
+    if accumulate:
+        out += r
+    else:
+        out.copy_(r)
+    return out
+
+
+def rows_dot(W, V):
+    return (W @ V.t()).contiguous()

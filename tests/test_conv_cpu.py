@@ -48,6 +48,13 @@ def test_conv_scipy_swipe_host_logic(name, monkeypatch):
     assert fwd < 1e-12 and core < 5e-4 and loss < 5e-5, (fwd, core, loss, pred)
 
 
+@pytest.mark.parametrize("name", ["conv_scipy_cg", "conv_scipy_minres"])
+def test_conv_device_krylov_solvers_track_the_float32_reference(name, monkeypatch):
+    fake_ops.install(monkeypatch)
+    fwd, core, loss, pred = cc.run_case(name, "cpu", scipy_object=False, loss_prefix=8)
+    assert loss < 5e-3, (core, loss)
+
+
 def test_conv_dense_sweep_is_refused(monkeypatch):
     fake_ops.install(monkeypatch)
     case, fx, layer = cc.build("conv_scipy_cg_2col", "cpu")
