@@ -516,11 +516,26 @@ trsv_block_kernel(const double* __restrict__ A, int64_t lda, int64_t j0, int nbw
             if (l == 0) yb[r] = sdot;
             __syncthreads();
             if (tid < CH_NB) x[j + tid] = (j + tid < nbw) ? yb[tid] : 0.0;
-            for (int i = j + CH_NB + warp; i < nbw; i += 32) {
-                const double* row = A + (j0 + i) * lda + j0 + j;
-                double sd = row[lane] * yb[lane] + row[lane + 32] * yb[lane + 32];
-                for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
-                if (lane == 0) x[i] -= sd;
+            {   // rows below the block, four per warp pass: all loads are issued before the reductions
+                const double y0 = yb[lane], y1 = yb[lane + 32];
+                for (int i0 = j + CH_NB + warp; i0 < nbw; i0 += 128) {
+                    double sd[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + 32 * u;
+                        const double* row = A + (j0 + (i < nbw ? i : i0)) * lda + j0 + j;
+                        sd[u] = row[lane] * y0 + row[lane + 32] * y1;
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) sd[u] += __shfl_xor_sync(0xffffffffu, sd[u], o);
+                    if (lane == 0) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (i0 + 32 * u < nbw) x[i0 + 32 * u] -= sd[u];
+                    }
+                }
             }
             __syncthreads();
         }
@@ -538,10 +553,24 @@ trsv_block_kernel(const double* __restrict__ A, int64_t lda, int64_t j0, int nbw
             if (l == 0) yb[r] = sdot;
             __syncthreads();
             if (tid < CH_NB) x[j + tid] = (tid < nb) ? yb[tid] : 0.0;
-            for (int c = tid; c < j; c += 1024) {
+            {   // columns left of the block: 2 threads per column (even / odd rows of the block), 4 independent sums each
+                const int c = tid >> 1, h = tid & 1;
                 double sd = 0.0;
-                for (int t = 0; t < nb; ++t) sd = fma(A[(j0 + j + t) * lda + j0 + c], yb[t], sd);
-                x[c] -= sd;
+                if (c < j) {
+                    const double* col = A + (j0 + j + h) * lda + j0 + c;
+                    double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+                    int t = h;
+                    for (; t + 6 < nb; t += 8) {
+                        s0 = fma(col[(int64_t)(t - h) * lda], yb[t], s0);
+                        s1 = fma(col[(int64_t)(t - h + 2) * lda], yb[t + 2], s1);
+                        s2 = fma(col[(int64_t)(t - h + 4) * lda], yb[t + 4], s2);
+                        s3 = fma(col[(int64_t)(t - h + 6) * lda], yb[t + 6], s3);
+                    }
+                    for (; t < nb; t += 2) s0 = fma(col[(int64_t)(t - h) * lda], yb[t], s0);
+                    sd = (s0 + s1) + (s2 + s3);
+                }
+                sd += __shfl_xor_sync(0xffffffffu, sd, 1);
+                if (h == 0 && c < j) x[c] -= sd;
             }
             __syncthreads();
         }

@@ -144,7 +144,7 @@ class TensorNetwork:
         # "auto" = mixed for large systems whose Gram was itself built on the tensor cores, fp64 otherwise
         self.solve_mode = "auto"
         self.mixed_min_P = 8192
-        self.mixed_rtol = 1e-11         # residual the refinement aims for ...
+        self.mixed_rtol = 1e-9          # residual the refinement aims for ...
         self.mixed_accept = 1e-9        # ... and the one it must reach for the result to be used (else fp64 redo)
         self.solve_stats = {"mixed": 0, "fp64": 0, "mixed_fallback": 0, "refine_iters": 0}
         self._mixed_floor = 0.0         # ridge values at or below this made the mixed solve fall back; skip it there
