@@ -140,7 +140,7 @@ tc_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict_
 // scratch so that each RED instruction adds 32 consecutive doubles of one row of M (coalesced) instead of 32 rows.
 __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_total, int BN, int warp, int lane, int64_t u0,
                                                int64_t nU, int v0, int nC, double* __restrict__ M, float* __restrict__ scratch,
-                                               double unscale) {
+                                               double unscale, int tile_stride = TC_M) {
     const int q = warp & 3;
     const int half = (warp - 1) >> 2;
     const int ngroups = (cols_total + 31) / 32;
@@ -157,7 +157,7 @@ __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_tota
         const int t = col / BN;
         const int gv = v0 + (col - t * BN);
         const bool col_ok = (col < cols_total) && (gv < nC);
-        const int64_t gu0 = u0 + (int64_t)t * TC_M + q * 32;
+        const int64_t gu0 = u0 + (int64_t)t * tile_stride + q * 32;
         double* dst = M + gu0 * nC + gv;
 #pragma unroll 4
         for (int rr = 0; rr < 32; ++rr) {
@@ -392,6 +392,285 @@ gram_tc_kernel(TcParams p) {
     }
 }
 
+
+// ---- CTA-pair variant (cta_group::2) for the large shapes (T == 2, BN == 256).
+// Two CTAs of a cluster (the two SMs of a TPC) execute every MMA together as M = 256 x N = 256: each CTA synthesises its own
+// 128 rows of the two U tiles and only HALF of the V tile (128 of the 256 rows of pair(fc)); the tensor cores of both SMs read
+// the two halves of V from both shared memories.  Per SM this removes a third of the operand bytes the MMAs fetch from shared
+// memory and a quarter of what the producers write -- the 1-CTA kernel is shared-memory-bandwidth bound (each K = 8 step moves
+// ~104 KB through a 128 B/clk port in the time the six MMAs need).  The leader CTA (cluster rank 0) issues all MMAs; the
+// producers of both CTAs arrive on the leader's full / acc_empty barriers (cluster-scope release), tcgen05.commit multicasts
+// the empty / acc_full arrivals to both CTAs.
+__device__ __forceinline__ uint32_t cluster_rank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive (release at cluster scope) on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+    asm volatile("{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
+                 "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)), "r"(cta) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+    for (uint32_t it = 0; it < (1u << 26); ++it) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+    }
+    mbar_timeout();
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma_commit2(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+constexpr int TP_BN = 256;          // V tile of the pair
+constexpr int TP_BH = TP_BN / 2;    // rows of it each CTA synthesises
+constexpr int TP_T = 2;             // U tiles (M = 256 each: 128 rows per CTA) per pair
+
+template <int SPLIT>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gram_tc_pair_kernel(TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int NS = p.nstages;
+    const int mA = p.mA, mB = p.mB, mC = p.mC;
+    const uint32_t rank = cluster_rank();
+
+    constexpr uint32_t a_tile_bytes = TC_M * TC_KC * 4;
+    constexpr uint32_t b_tile_bytes = TP_BH * TC_KC * 4;
+    constexpr uint32_t stage_bytes = 2 * TP_T * a_tile_bytes + 2 * b_tile_bytes;
+    const uint32_t z_rows = (uint32_t)(2 * mA + mB + mC);
+    const uint32_t raw_rows = z_rows + 1;
+    const uint32_t raw_bytes = raw_rows * TC_KCP * 4;
+    uint8_t* stage_base = smem_raw;
+    uint8_t* raw_base = smem_raw + (size_t)NS * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)TC_RAW_SLOTS * raw_bytes);
+    uint64_t* full = bars;              // [NS]  used in the leader: producers of both CTAs -> MMA
+    uint64_t* empty = bars + NS;        // [NS]  per CTA: multicast tcgen05.commit -> producers
+    uint64_t* acc_full = bars + 2 * NS;     // per CTA (multicast commit)
+    uint64_t* acc_empty = bars + 2 * NS + 1;   // used in the leader: drainers of both CTAs -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], 2 * TC_PROD_WARPS);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 2 * TC_PROD_WARPS);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < TC_RAW_SLOTS * TC_KCP; i += TC_THREADS)
+        reinterpret_cast<float*>(raw_base + (size_t)(i / TC_KCP) * raw_bytes)[z_rows * TC_KCP + (i % TC_KCP)] = 0.f;
+    cluster_sync_all();                  // barrier inits visible to the peer before anything arrives remotely
+    if (warp == 0) tmem_alloc2(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t k_begin = (int64_t)blockIdx.z * p.rows_per_split;
+    const int64_t k_end = min(p.zpitch, k_begin + p.rows_per_split);
+    const int64_t nchunks = (k_end > k_begin) ? (k_end - k_begin) / TC_KC : 0;
+    const int64_t chunks_per_flush = p.flush_rows / TC_KC;
+    const int64_t nU = (int64_t)p.nA * p.nB;
+    const int64_t u0_pair = (int64_t)(blockIdx.x >> 1) * (2 * TC_M * TP_T);     // 512 U rows per pair
+    const int v0 = blockIdx.y * TP_BN;
+
+    if (warp == 0) {
+        // =============================== MMA issuer (leader CTA only) ===============================
+        if (rank == 0 && lane == 0 && nchunks > 0) {
+            const uint32_t idesc = make_idesc(2 * TC_M, TP_BN);
+            constexpr uint32_t lbo_a = TC_M * 16, lbo_b = TP_BH * 16, sbo = 128;
+            uint32_t acc_phase = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            int64_t in_window = 0;
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const bool first_of_window = in_window == 0;
+                if (first_of_window && c > 0) {
+                    mbar_wait_cluster(acc_empty, acc_phase);
+                    acc_phase ^= 1;
+                    tc_fence_after();
+                }
+                mbar_wait_cluster(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(stage_base + (size_t)s * stage_bytes);
+                const uint32_t b_hi = sb + 2 * TP_T * a_tile_bytes;
+                const uint32_t b_lo = b_hi + b_tile_bytes;
+#pragma unroll
+                for (int t = 0; t < TP_T; ++t) {
+                    const uint32_t a_hi = sb + (uint32_t)t * 2 * a_tile_bytes;
+                    const uint32_t a_lo = a_hi + a_tile_bytes;
+                    const uint32_t d = tmem_base + (uint32_t)(t * TP_BN);
+#pragma unroll
+                    for (int j = 0; j < TC_KC / 8; ++j) {
+                        const uint32_t ao = (uint32_t)(2 * j) * lbo_a, bo = (uint32_t)(2 * j) * lbo_b;
+                        const uint32_t acc0 = (first_of_window && j == 0) ? 0u : 1u;
+                        umma2_tf32(d, make_desc(a_hi + ao, lbo_a, sbo), make_desc(b_hi + bo, lbo_b, sbo), idesc, acc0);
+                        if (SPLIT) {
+                            umma2_tf32(d, make_desc(a_hi + ao, lbo_a, sbo), make_desc(b_lo + bo, lbo_b, sbo), idesc, 1u);
+                            umma2_tf32(d, make_desc(a_lo + ao, lbo_a, sbo), make_desc(b_hi + bo, lbo_b, sbo), idesc, 1u);
+                        }
+                    }
+                }
+                umma_commit2(&empty[s]);
+                const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+                if (last_of_window) {
+                    umma_commit2(acc_full);
+                    in_window = 0;
+                }
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // =============================== producers / epilogue (both CTAs) ===============================
+        const int pt = tid - 32;
+        const double unscale = ldexp(1.0, 2 * (tc_exponent(p.amax[0]) + tc_exponent(p.amax[1]) + tc_exponent(p.amax[2])) +
+                                              tc_exponent(p.amax[3]));
+        const uint32_t raw_s = smem_u32(raw_base);
+        const uint32_t zero_row = z_rows * TC_KCP * 4;
+        uint32_t usrc[4] = {zero_row, zero_row, zero_row, zero_row};
+        const int u_tile = pt >> 7, u_row = pt & 127;
+        constexpr int U_NC = TC_KC / 4;
+        const int64_t u0_cta = u0_pair + (int64_t)rank * TC_M;        // tile t of this CTA covers rows u0_cta + t*256 + [0, 128)
+        {
+            const int64_t gu = u0_cta + (int64_t)u_tile * (2 * TC_M) + u_row;
+            if (gu < nU) {
+                const int qa = (int)(gu / p.nB), qb = (int)(gu - (int64_t)qa * p.nB);
+                int ia, ja, ib, jb;
+                pair_decode(qa, mA, ia, ja);
+                pair_decode(qb, mB, ib, jb);
+                usrc[0] = (uint32_t)(ia * TC_KCP * 4);
+                usrc[1] = (uint32_t)((mA + ja) * TC_KCP * 4);
+                usrc[2] = (uint32_t)((2 * mA + ib) * TC_KCP * 4);
+                usrc[3] = (uint32_t)((2 * mA + jb) * TC_KCP * 4);
+            }
+        }
+        uint32_t vsrc[2] = {zero_row, zero_row};
+        const int gv = v0 + (int)rank * TP_BH + pt;                    // this CTA's half of the V tile
+        if (pt < TP_BH && gv < p.nC) {
+            int ic, jc;
+            pair_decode(gv, mC, ic, jc);
+            vsrc[0] = (uint32_t)((2 * mA + mB + ic) * TC_KCP * 4);
+            vsrc[1] = (uint32_t)((2 * mA + mB + jc) * TC_KCP * 4);
+        }
+        const uint32_t udst = (uint32_t)u_tile * 2 * a_tile_bytes + (uint32_t)u_row * 16;
+        const uint32_t vdst = 2 * TP_T * a_tile_bytes + (uint32_t)pt * 16;
+        constexpr uint32_t lbo_b = TP_BH * 16;
+        const uint32_t stage_s = smem_u32(stage_base);
+
+        const int npieces = (int)z_rows * (TC_KC / 4);
+        auto issue_chunk = [&](int64_t chunk) {
+            if (chunk < nchunks) {
+                const float* src0 = p.Z + k_begin + chunk * TC_KC;
+                const uint32_t dst0 = raw_s + (uint32_t)(chunk % TC_RAW_SLOTS) * raw_bytes;
+                for (int pc = pt; pc < npieces; pc += TC_PROD) {
+                    const int row = pc >> 2, part = pc & 3;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)row * (TC_KCP * 4) + part * 16),
+                                 "l"(src0 + (int64_t)row * p.zpitch + part * 4) : "memory");
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        };
+        issue_chunk(0);
+        issue_chunk(1);
+
+        uint32_t acc_phase = 0;
+        int s = 0, rs = 0;
+        uint32_t ph = 0;
+        int64_t in_window = 0;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            asm volatile("cp.async.wait_group 1;" ::: "memory");
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");
+            issue_chunk(c + 2);
+            if (lane == 0) mbar_wait(&empty[s], ph ^ 1);
+            __syncwarp();
+            const uint32_t rb = raw_s + (uint32_t)rs * raw_bytes;
+            const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
+            {
+                float4 x0[U_NC], x1[U_NC], x2[U_NC], x3[U_NC];
+#pragma unroll
+                for (int cc = 0; cc < U_NC; ++cc) {
+                    const uint32_t o = (uint32_t)cc * 16;
+                    x0[cc] = lds128(rb + usrc[0] + o);
+                    x1[cc] = lds128(rb + usrc[1] + o);
+                    x2[cc] = lds128(rb + usrc[2] + o);
+                    x3[cc] = lds128(rb + usrc[3] + o);
+                }
+#pragma unroll
+                for (int cc = 0; cc < U_NC; ++cc) {
+                    const float4 v = mul4(mul4(x0[cc], x1[cc]), mul4(x2[cc], x3[cc]));
+                    const uint32_t d = sb + udst + (uint32_t)cc * (TC_M * 16);
+                    store_split<SPLIT>(v, d, d + a_tile_bytes);
+                }
+            }
+            if (pt < TP_BH) {
+                float4 y0[TC_KC / 4], y1[TC_KC / 4];
+#pragma unroll
+                for (int cc = 0; cc < TC_KC / 4; ++cc) {
+                    y0[cc] = lds128(rb + vsrc[0] + cc * 16);
+                    y1[cc] = lds128(rb + vsrc[1] + cc * 16);
+                }
+#pragma unroll
+                for (int cc = 0; cc < TC_KC / 4; ++cc) {
+                    const uint32_t d = sb + vdst + (uint32_t)cc * lbo_b;
+                    store_split<SPLIT>(mul4(y0[cc], y1[cc]), d, d + b_tile_bytes);
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&full[s], 0);           // on the leader's barrier
+            if (++s == NS) { s = 0; ph ^= 1; }
+            if (++rs == TC_RAW_SLOTS) rs = 0;
+            const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+            if (last_of_window) {
+                in_window = 0;
+                mbar_wait(acc_full, acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                drain_accumulator(tmem_base, TP_T * TP_BN, TP_BN, warp, lane, u0_cta, nU, v0, p.nC, p.M,
+                                  reinterpret_cast<float*>(stage_base), unscale, 2 * TC_M);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty, 0);
+            }
+        }
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncwarp();
+    cluster_sync_all();                  // the peer may still be reading this CTA's shared / tensor memory until here
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, 512);
+    }
+}
+
+static size_t tc_pair_smem_bytes(int mA, int mB, int mC, int NS) {
+    const size_t stage = 2 * (size_t)TP_T * TC_M * TC_KC * 4 + 2 * (size_t)TP_BH * TC_KC * 4;
+    const size_t raw = (size_t)(2 * mA + mB + mC + 1) * TC_KCP * 4;
+    return NS * stage + TC_RAW_SLOTS * raw + (2 * NS + 2) * 8 + 16;
+}
+
 static size_t tc_smem_bytes(int mA, int mB, int mC, int BN, int T, int NS) {
     const size_t stage = 2 * (size_t)T * TC_M * TC_KC * 4 + 2 * (size_t)BN * TC_KC * 4;
     const size_t raw = (size_t)(2 * mA + mB + mC + 1) * TC_KCP * 4;
@@ -469,6 +748,40 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
         dim3 grid((unsigned)ceil_div64(p.zpitch, 32), (unsigned)ceil_div64(A.m + B.m + C.m, 32));
         tc_stage_kernel<<<grid, 256, 0, st>>>(A, B, C, w, rows, Z, p.zpitch, amax);
         TN_LAUNCH_CHECK();
+    }
+    // CTA-pair kernel (opt-in, TN_TC_PAIR=1).  Measured on the config-5a middle site (131 072 rows, tools/tc_pair_probe.py):
+    // bit-identical M, but 530 vs 557 TF/s issued in 3xTF32 and 217 vs 268 in TF32 -- the 1-CTA kernel already runs at ~0.9 of
+    // the sustained (power-capped) tensor rate, so halving the operand traffic buys nothing and the cluster-scope barriers cost.
+    bool pair = (p.T == 2 && p.BN == TP_BN && nU >= 8LL * 512 && getenv("TN_TC_PAIR") && !getenv("TN_TC_NO_PAIR"));
+    int NSP = 5;
+    if (pair) {
+        while (NSP >= 2 && tc_pair_smem_bytes(A.m, B.m, C.m, NSP) > 226 * 1024) --NSP;
+        if (NSP < 2) pair = false;
+    }
+    if (pair) {
+        p.nstages = NSP;
+        const size_t psmem = tc_pair_smem_bytes(A.m, B.m, C.m, NSP);
+        const int64_t gxp = 2 * ceil_div64(nU, 2LL * TC_M * TP_T), gyp = ceil_div64(p.nC, TP_BN);
+        TN_CHECK_ARG(gyp <= 65535 && gxp <= 0x7fffffff, "tn_gram_kr3: grid too large");
+        int64_t ksp = ceil_div64((int64_t)sm_count(), gxp * gyp);
+        const int64_t max_ksp = ceil_div64(p.zpitch, 4 * TC_KC);
+        if (ksp > max_ksp) ksp = max_ksp;
+        if (ksp < 1) ksp = 1;
+        if (ksp > 65535) ksp = 65535;
+        p.rows_per_split = ceil_div64(ceil_div64(p.zpitch, ksp), TC_KC) * TC_KC;
+        ksp = ceil_div64(p.zpitch, p.rows_per_split);
+        using KernP = void (*)(TcParams);
+        static const KernP pk[2] = {gram_tc_pair_kernel<0>, gram_tc_pair_kernel<1>};
+        static size_t pconfigured[2] = {};
+        if (psmem > pconfigured[p.split]) {
+            TN_CUDA(cudaFuncSetAttribute(pk[p.split], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
+            pconfigured[p.split] = psmem;
+        }
+        dim3 pgrid((unsigned)gxp, (unsigned)gyp, (unsigned)ksp);
+        pk[p.split]<<<pgrid, TC_THREADS, psmem, st>>>(p);
+        TN_LAUNCH_CHECK();
+        TN_CUDA(cudaFreeAsync(Z, st));
+        return TN_OK;
     }
     const int64_t gx = ceil_div64(nU, (int64_t)TC_M * p.T), gy = ceil_div64(p.nC, p.BN);
     TN_CHECK_ARG(gy <= 65535 && gx <= 0x7fffffff, "tn_gram_kr3: grid too large");
