@@ -316,10 +316,12 @@ def bench_b200(args):
         clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    mv_count0 = getattr(tn, "matvec_count", 0)
     e0.record()
     run_sweeps(layer, x, y, wl, args, args.steps, counter)
     e1.record()
     barrier()
+    mv_count1 = getattr(tn, "matvec_count", 0)
     clk = clocks.stop() if rank == 0 else None
     timer.enabled = False
     kernel_launches = int(_tnlib.load().tn_launch_count() - launches0)
@@ -416,10 +418,10 @@ def bench_b200(args):
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6550.7 GB/s",
                     "share_of_step": sec / (ms / 1e3), "launches": sum(len(tot[k_]) for k_ in hot),
                     "fp64_tflops": fl / sec / 1e12 if sec > 0 else None,
-                    "matvecs_per_site_update": len(tot["rows_dot"]) / max(updates, 1),
+                    "matvecs_per_site_update": (mv_count1 - mv_count0) / max(updates, 1),
                     "other_kernels_tflops": {k_: (sum(timer.extra[k_]) / (sum(tot[k_]) / 1e3) / 1e12 if tot[k_] else None) for k_ in other},
                     "measured_peaks": measured}
-        wl = dict(wl, _avg_matvecs=20.0)
+        wl = dict(wl, _avg_matvecs=(mv_count1 - mv_count0) / max(updates, 1))
     elif wl.get("solver"):
         mv_ms = tot["matvec"]
         mv_bytes = sum(timer.extra["matvec"])

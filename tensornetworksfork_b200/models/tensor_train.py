@@ -13,7 +13,7 @@ from sklearn.base import BaseEstimator, RegressorMixin
 from sklearn.metrics import accuracy_score, r2_score, root_mean_squared_error
 
 from ..tensor.bregman import SquareBregFunction
-from ..tensor.layers import CPDLayer, CumSumLayer, TensorNetworkLayer, TensorTrainLayer
+from ..tensor.layers import CPDLayer, CumSumLayer, TensorNetworkLayer, TensorTrainLayer, TensorTrainLinearLayer
 from ..tensor.network import SumOfNetworks
 
 
@@ -112,15 +112,19 @@ class TensorTrainRegressor(BaseEstimator, RegressorMixin):
                 cls = CumSumLayer if self.cum_sum else TensorTrainLayer
                 return cls(i, bond_dim=self.r, input_features=f, output_shape=self.output_dim, constrict_bond=self.constrict_bond,
                            perturb=self.perturb, seed=self.seed + i)
-            if self.linear_dim is not None:
-                raise NotImplementedError("linear-projection layers are a 'next' row of the scope table (SURVEY.md §8f)")
+            if self.linear_dim is not None and self.linear_dim < self.input_dim:
+                raise NotImplementedError("type-I sums of linear-projection trains are not part of the B200 path")
             nets = [member(i).tensor_network for i in range(1, self.N + 1)]
             self._model = TensorNetworkLayer(SumOfNetworks(nets, output_labels=nets[0].output_labels,
                                                            train_operators=self.train_operator)).to(self.device)
             self._model.tensor_network.gram_mode = self.gram_mode
             return
-        if self.linear_dim is not None:
-            raise NotImplementedError("linear-projection layers are a 'next' row of the scope table (SURVEY.md §8f)")
+        if self.linear_dim is not None and self.linear_dim < self.input_dim and mt.startswith("tt") and not self.cum_sum:
+            # trainable linear projection in front of every core (reference models/tensor_train.py:191-197)
+            self._model = TensorTrainLinearLayer(self.N, self.r, self.input_dim, self.linear_dim, output_shape=self.output_dim,
+                                                 constrict_bond=self.constrict_bond, perturb=self.perturb, seed=self.seed).to(self.device)
+            self._model.tensor_network.gram_mode = self.gram_mode
+            return
         if mt.startswith("cpd"):
             self._model = CPDLayer(self.N, self.r, self.input_dim, output_shape=self.output_dim, perturb=self.perturb,
                                    seed=self.seed).to(self.device)

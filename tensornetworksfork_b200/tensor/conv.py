@@ -35,6 +35,7 @@ class ConvTrainNetwork(TensorNetwork):
         self._cols = None
         self._cache = {}
         self._ver = {}                  # node -> number of updates applied by this engine (part of every cache stamp)
+        self.matvec_count = 0           # matvecs served so far (bench bookkeeping)
 
     # ------------------------------------------------------------------ graph
     def _columns(self):
@@ -370,6 +371,7 @@ class ConvTrainNetwork(TensorNetwork):
             dist.all_reduce(b, group=self.process_group)
 
         def matvec(v):
+            self.matvec_count += 1
             v = v.contiguous().view(-1)
             out = None
             for jv_fn, jt_fn, U, lam in parts:

@@ -182,6 +182,41 @@ class TensorTrainLayer(TensorNetworkLayer):
                                               output_labels=self.main_node_layer.labels))
 
 
+class TensorTrainLinearLayer(TensorNetworkLayer):
+    """Tensor train whose cores see a trainable linear projection of the input: per column a core A_k over `linear_dim` and a
+    projection L_k (linear_dim x input_features); train-node order A1, L1, A2, L2, ... (reference layers.py:308-343; same
+    constructor, labels, names and random draws)."""
+
+    def __init__(self, num_carriages, bond_dim, input_features, linear_dim, output_shape=tuple(), squeeze=True, constrict_bond=True,
+                 perturb=False, dtype=None, seed=None):
+        super().__init__()
+        self.num_carriages = num_carriages
+        self.bond_dim = bond_dim
+        self.input_features = input_features
+        self.output_shape = output_shape if isinstance(output_shape, tuple) else (output_shape,)
+        self.linear_dim = linear_dim
+        if seed is not None:
+            torch.manual_seed(seed)
+            if torch.cuda.is_available():
+                torch.cuda.manual_seed(seed)
+        self.main_node_layer = MainNodeLayer(num_carriages, bond_dim, linear_dim, output_shape=output_shape, down_label="lin{0}",
+                                             constrict_bond=constrict_bond, perturb=perturb, dtype=dtype)
+        self.horizontal_connect(self.main_node_layer.nodes)
+        lin_nodes = [TensorNode((linear_dim, input_features), [f"lin{i}", f"p{i}"], name=f"L{i}", dtype=dtype)
+                     for i in range(1, num_carriages + 1)]
+        self.linear_layer = nn.Module()
+        self.linear_layer.nodes = lin_nodes
+        self.zip_connect(self.main_node_layer.nodes, lin_nodes, label="lin{0}", priority=2)
+        self.input_node_layer = InputNodeLayer(num_carriages, input_features, label="p{0}", dtype=dtype)
+        self.zip_connect(lin_nodes, self.input_node_layer.nodes, label="p{0}", priority=1)
+        if squeeze:
+            for n in self.main_node_layer.nodes:
+                n.squeeze(self.main_node_layer.labels)
+        train = [n for col in zip(self.main_node_layer.nodes, lin_nodes) for n in col]
+        self.set_tensor_network(TensorNetwork(self.input_node_layer.nodes, main_nodes=self.main_node_layer.nodes, train_nodes=train,
+                                              output_labels=self.main_node_layer.labels))
+
+
 class CumSumLayer(TensorNetworkLayer):
     """Tensor train over ordered feature tuples (reference layers.py:425-477).  Same cores and draws as
     ``TensorTrainLayer``; the reference's dense cum-sum operator nodes are replaced by the closed form in

@@ -16,7 +16,7 @@ from sklearn.base import BaseEstimator, RegressorMixin
 from sklearn.metrics import r2_score, root_mean_squared_error
 
 from .bregman import SquareBregFunction
-from .layers import CPDLayer, TensorNetworkLayer, TensorTrainLayer
+from .layers import CPDLayer, TensorNetworkLayer, TensorTrainLayer, TensorTrainLinearLayer
 from .network import SumOfNetworks
 
 
@@ -98,9 +98,13 @@ class TensorTrainRegressor(BaseEstimator, RegressorMixin):
     def _initialize_model(self):
         if self.input_dim is None:
             raise ValueError("input_dim must be set")
-        if self.linear_dim is not None and self.linear_dim < self.input_dim:
-            raise NotImplementedError("linear-projection layers (TensorTrainLinearLayer) are not part of the B200 path")
-        if self.model_type == "cpd":
+        use_linear = self.linear_dim is not None and self.linear_dim < self.input_dim
+        if use_linear and (self.model_type == "cpd" or self.model_type.startswith("tt_type1")):
+            raise NotImplementedError("type-I sums of linear-projection trains are not part of the B200 path")
+        if use_linear:
+            self._model = TensorTrainLinearLayer(self.N, self.r, self.input_dim, self.linear_dim, output_shape=self.output_dim,
+                                                 constrict_bond=self.constrict_bond, perturb=self.perturb, seed=self.seed)
+        elif self.model_type == "cpd":
             self._model = CPDLayer(self.N, self.r, self.input_dim, output_shape=self.output_dim, perturb=self.perturb, seed=self.seed)
         elif self.model_type.startswith("tt_type1"):
             nets = [TensorTrainLayer(i, bond_dim=self.r,

@@ -61,7 +61,7 @@ class MappedInput:
 
 
 class _Site:
-    __slots__ = ("node", "left", "right", "phys", "cls", "input_index")
+    __slots__ = ("node", "left", "right", "phys", "cls", "input_index", "linear")
 
 
 def sweep_schedule(first_cols, second_cols, num_swipes, eps, eps_decay=None, skip_second=False, direction="l2r",
@@ -202,6 +202,18 @@ class TensorNetwork:
             s.cls = cls[0] if cls else None
             phys = [(lab, other) for lab in node.dim_labels for l2, other in node.connections.items()
                     if l2 == lab and any(other is n for n in self.input_nodes)]
+            s.linear = None
+            if not phys:
+                # TensorTrainLinearLayer (reference layers.py:308-343): core -[lin]- W (lin, p) -[p]- input
+                for lab in node.dim_labels:
+                    other = node.connections.get(lab)
+                    if other is None or node.is_horizontal_bond(lab) or other.tensor.dim() != 2 or len(other.dim_labels) != 2:
+                        continue
+                    far = [(l2, n2) for l2, n2 in other.connections.items() if l2 != lab and any(n2 is n for n in self.input_nodes)]
+                    if len(far) == 1 and other.dim_labels == [lab, far[0][0]]:
+                        s.linear = other
+                        phys = [(lab, far[0][1])]
+                        break
             if len(phys) not in (1, 2):
                 raise NotImplementedError(f"{node.name}: expected one input node (or two for a 2-site block), found {len(phys)} "
                                           "(this engine covers tensor-train chains; see DESIGN.md)")
@@ -293,11 +305,28 @@ class TensorNetwork:
                 t = (ta[:, :, None] * tb[:, None, :]).reshape(ta.shape[0], fa * fb).contiguous()   # phi_L (x) phi_R per sample
             else:
                 t = tensor_of(s.input_index)
-                if t.shape[1] != s.node.dim_size(s.phys):
+                if s.linear is None and t.shape[1] != s.node.dim_size(s.phys):
                     raise ValueError(f"site {k}: input has {t.shape[1]} features, core expects {s.node.dim_size(s.phys)}")
             facs.append(Factor(t, m=t.shape[1]))
         t0 = tensor_of(0)
         return facs, t0.shape[0], t0.device
+
+    def _project(self, facs, S):
+        """Site inputs after the linear projections (phi_k = x W_k^T for sites with a linear node); returns (facs, raw)."""
+        sites = self._plan()
+        if not any(st.linear is not None for st in sites):
+            return facs, None
+        out = []
+        for st, fac in zip(sites, facs):
+            if st.linear is None:
+                out.append(fac)
+                continue
+            W = st.linear.tensor                                   # (lin, p)
+            if fac.m != W.shape[1]:
+                raise ValueError(f"{st.linear.name}: input has {fac.m} features, projection expects {W.shape[1]}")
+            phi = ops.env_update(None, fac, W.t().reshape(1, W.shape[1], W.shape[0]), S)
+            out.append(Factor(phi, m=W.shape[0]))
+        return out, facs
 
     @staticmethod
     def _key_of(x):
@@ -313,10 +342,17 @@ class TensorNetwork:
         if key == self._data_key:
             return False
         self._data_key = key
-        self._data = (x,) + self._bind(x)   # keep x alive so ids stay unique
+        self._rebind(x)
+        return True
+
+    def _rebind(self, x):
+        facs, S, dev = self._bind(x)
+        if any(st.linear is not None for st in self._plan()):
+            self._require_cuda(dev)
+        facs, self._raw_facs = self._project(facs, S)
+        self._data = (x, facs, S, dev)      # keep x alive so ids stay unique
         self._left.clear()
         self._right.clear()
-        return True
 
     def reset_stacks(self, node=None):
         self._left.clear()
@@ -325,11 +361,14 @@ class TensorNetwork:
         self.right_stacks = None
 
     def _stamp(self):
-        return [(id(s.node.tensor), s.node.tensor._version) for s in self._plan()]
+        return [(id(s.node.tensor), s.node.tensor._version) + ((id(s.linear.tensor), s.linear.tensor._version) if s.linear is not None else ())
+                for s in self._plan()]
 
     def _check_external(self):
         st = self._stamp()
         if self._stamps != st:
+            if self._data is not None and getattr(self, "_raw_facs", None) is not None:
+                self._rebind(self._data[0])      # a projection changed behind our back: re-project the bound data
             self._left.clear()
             self._right.clear()
             self._stamps = st
@@ -401,6 +440,7 @@ class TensorNetwork:
         """Prediction (S, C) for arbitrary data, without touching the training caches."""
         facs, S, dev = self._bind(x)
         self._require_cuda(dev)
+        facs, _ = self._project(facs, S)
         env = None
         for k in range(len(self._plan())):
             env = self._step(env, facs[k], k, True, S)
@@ -571,13 +611,17 @@ class TensorNetwork:
 
     def _solve(self, k, M, b, m_pos, role_of_pos, method, eps):
         """sigma-scaling, ridge and Cholesky solve (reference network.py:293-327) -> step in node layout."""
+        step = self._solve_flat(self._canon(k).contiguous().view(-1), M, b, m_pos, role_of_pos, method, eps)
+        return self._from_canon(k, step.reshape(self._canon(k).shape))
+
+    def _solve_flat(self, theta, M, b, m_pos, role_of_pos, method, eps):
+        """The local solve on flat canonical-order vectors; returns the flat step."""
         m = method.lower()
         if m == "gradient":
-            return self._from_canon(k, (-b).reshape(self._canon(k).shape))
+            return -b
         if m not in ("exact", "ridge_exact", "cholesky") and not m.startswith("ridge_cholesky"):
             raise ValueError(f"Unknown method: {method}")
         ridge = 0.0 if m in ("exact", "cholesky") else 2.0 * float(eps)
-        theta = self._canon(k).contiguous().view(-1)
         sigma = ops.gram_sigma(M, m_pos, role_of_pos)
         A = ops.gram_expand(M, m_pos, role_of_pos, sigma, ridge)
         rhs = ops.rhs_prepare(b, theta, sigma, ridge)
@@ -617,7 +661,7 @@ class TensorNetwork:
             raise torch.linalg.LinAlgError(
                 f"linalg.cholesky: The factorization could not be completed because the input is not positive-definite "
                 f"(the leading minor of order {bad} is not positive-definite).")
-        return self._from_canon(k, rhs.reshape(self._canon(k).shape))
+        return rhs
 
     def get_A_b(self, node, grad=None, hessian=None, method=None, y=None, loss_fn=None):
         """Dense (A, b) of one node in the reference's layout (network.py:174-217), built from the
@@ -758,7 +802,90 @@ class TensorNetwork:
                                    n_total=self.shard_total if self.process_group is not None else S,
                                    group=self.process_group)
 
+    def _linear_site(self, node):
+        """Index of the site whose linear-projection node `node` is, or None."""
+        for k, st in enumerate(self._plan()):
+            if getattr(st, "linear", None) is node:
+                return k
+        return None
+
+    def _linear_problem(self, k, y, loss_fn):
+        """Local problem of the projection W_k (lin, p) of a TensorTrainLinearLayer site (reference layers.py:308-343).
+
+        J[s, c, (l, p)] = Q[s, c, l] x[s, p] with Q = L G_k R contracted over both bonds: a Kronecker product of two factors, so the
+        Gram / rhs / matvec kernels of a core apply with m_pos = (lin, p, 1)."""
+        prob = self._site_problem(k, y, loss_fn)           # prediction and loss terms (through the projected input)
+        L, R, U, lam, g = prob["keep"]
+        _, _, S, dev = self._data
+        G = self._canon(k)
+        rl, ck, lin, rr = G.shape
+        owner = self._owner()
+        C = self._num_outputs()
+        xraw = self._raw_facs[k]
+        p_in = xraw.m
+        one = ops.ones_factor(G)
+        big = 1 << 30
+        if C == 1 or owner == k:
+            core = G.permute(0, 3, 1, 2).reshape(rl, rr, ck * lin)
+            Lf = None if L is None else L.reshape(S, rl)
+            if R is None:
+                Q = ops.env_update(Lf, one, core.reshape(rl, 1, ck * lin), S, cdiv=big)
+            else:
+                Q = ops.env_update(Lf, Factor(R.reshape(S, rr), m=rr), core, S)
+            Q = Q.view(S, C, lin)
+        elif owner < k:
+            core = G[:, 0].permute(0, 2, 1)                  # (rl, rr, lin)
+            if R is None:
+                Q = ops.env_update(L.reshape(S * C, rl), one, core.reshape(rl, 1, lin), S * C, cdiv=big)
+            else:
+                Q = ops.env_update(L.reshape(S * C, rl), Factor(R.reshape(S, rr), m=rr), core, S * C, cdiv=C)
+            Q = Q.view(S, C, lin)
+        else:
+            core = G[:, 0].permute(2, 0, 1)                  # (rr, rl, lin)
+            if L is None:
+                Q = ops.env_update(R.reshape(S * C, rr), one, core.reshape(rr, 1, lin), S * C, cdiv=big)
+            else:
+                Q = ops.env_update(R.reshape(S * C, rr), Factor(L.reshape(S, rl), m=rl), core, S * C, cdiv=C)
+            Q = Q.view(S, C, lin)
+        V = lam.shape[1]
+        if C == 1:
+            w = (lam.reshape(S, V) * U.reshape(S, V) ** 2).sum(dim=1).contiguous()
+            fq = Factor(Q.view(S, lin), m=lin)
+            out = dict(gram=(fq, xraw, one), gw=w, grows=S, rhs=(fq, xraw, one), rw=g.reshape(S).contiguous(), rrows=S)
+        else:
+            F, Gr = ops.class_rows(Q.contiguous(), U.contiguous(), g)
+            xv = Factor(xraw.tensor, m=xraw.m, div=V, map_kind=xraw.map_kind, col=xraw.col)
+            out = dict(gram=(Factor(F, m=lin), xv, one), gw=lam.reshape(S * V).contiguous(), grows=S * V,
+                       rhs=(Factor(Gr, m=lin), xraw, one), rw=None, rrows=S)
+        out.update(m_pos=(lin, p_in, 1), yhat=prob["yhat"], loss=prob["loss"], keep=(prob["keep"], Q))
+        return out
+
+    def _set_linear(self, k, new_tensor):
+        st = self._plan()[k]
+        st.linear.tensor = new_tensor
+        self._rebind(self._data[0])          # re-project the bound data; drops every cached environment
+        self._stamps = self._stamp()
+
+    def _one_linear_update(self, k, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss):
+        self._check_external()
+        prob = self._linear_problem(k, y, loss_fn)
+        M, b, role_of_pos = self._accumulate(prob)
+        W = self._plan()[k].linear.tensor
+        step = self._solve_flat(W.contiguous().view(-1), M, b, prob["m_pos"], role_of_pos, method, eps)
+        new = W.detach().clone().contiguous()
+        ops.update_node(new.view(-1), step.contiguous().view(-1), lr=lr, adaptive_step=adaptive_step, max_norm=max_norm)
+        self._set_linear(k, new)
+        if not need_loss:
+            return None
+        S = prob["yhat"].shape[0]
+        return batch_mean_of_means(prob["loss"], batch_size, row_offset=self.shard_offset,
+                                   n_total=self.shard_total if self.process_group is not None else S,
+                                   group=self.process_group)
+
     def _update_node(self, node, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss):
+        kl = self._linear_site(node)
+        if kl is not None:
+            return self._one_linear_update(kl, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss)
         return self._one_update(self.main_nodes.index(node), y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm,
                                 need_loss)
 
@@ -809,6 +936,8 @@ class TensorNetwork:
                     print(f"Singular system for node {node.name}")
                 return False
             going_right = half == 0     # the first half re-gauges to the left, the second to the right (network.py:487-488,585-586)
+            if orthonormalize and node not in self.main_nodes:
+                raise NotImplementedError("QR re-gauge of a linear-projection node")
             if orthonormalize:
                 if going_right:
                     self.node_orthonormalize_left(node)
@@ -836,8 +965,8 @@ class TensorNetwork:
         return True
 
     # ------------------------------------------------------------------ matrix-free sweeps
-    def _krylov_setup(self, k, y, loss_fn):
-        prob = self._site_problem(k, y, loss_fn)
+    def _krylov_setup(self, k, y, loss_fn, prob=None):
+        prob = self._site_problem(k, y, loss_fn) if prob is None else prob
         gf, rf = prob["gram"], prob["rhs"]
         b = ops.rhs(rf[0], rf[1], rf[2], prob["rw"], prob["rrows"])
         if self.process_group is not None:
@@ -855,10 +984,20 @@ class TensorNetwork:
 
     def _krylov_problem(self, node, y, loss_fn):
         """(per-row loss, right-hand side b, matvec v -> J^T H J v) of one node, everything flat in canonical order."""
+        kl = self._linear_site(node)
+        if kl is not None:
+            prob, b, matvec = self._krylov_setup(kl, y, loss_fn, prob=self._linear_problem(kl, y, loss_fn))
+            return prob["loss"], b, matvec
         prob, b, matvec = self._krylov_setup(self.main_nodes.index(node), y, loss_fn)
         return prob["loss"], b, matvec
 
     def _apply_step(self, node, step_c, lr):
+        kl = self._linear_site(node)
+        if kl is not None:
+            new = node.tensor.detach().clone().contiguous()
+            ops.update_node(new.view(-1), step_c.contiguous().view(-1), lr=lr)
+            self._set_linear(kl, new)
+            return
         k = self.main_nodes.index(node)
         step = self._from_canon(k, step_c.reshape(self._canon(k).shape))
         new = node.tensor.detach().clone().contiguous()

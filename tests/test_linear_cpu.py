@@ -1,0 +1,19 @@
+"""TensorTrainLinearLayer (reference tensor/layers.py:308-343): constructor draws and the engine's host logic on the CPU stand-in
+kernels against recordings of the reference."""
+import pytest
+import torch
+
+import fake_ops
+import linear_cases as lc
+
+torch.set_default_dtype(torch.float64)
+
+
+@pytest.mark.parametrize("name", sorted(lc.CASES))
+def test_linear_layer_sweeps_host_logic(name, monkeypatch):
+    fake_ops.install(monkeypatch)
+    init_err, fwd_err, core_err, loss_err, pred_err = lc.run_case(name, "cpu")
+    assert init_err == 0.0
+    tight = lc.CASES[name]["kind"] == "dense"
+    assert fwd_err < 1e-12 and core_err < 1e-7 and loss_err < (1e-9 if tight else 1e-6) and pred_err < (1e-7 if tight else 1e-4), \
+        (fwd_err, core_err, loss_err, pred_err)
