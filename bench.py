@@ -397,8 +397,20 @@ def bench_b200(args):
             peak, peak_src = bf16 / 2.0, "half of the sustained bf16 dense peak of MEASURED_PEAKS.json (TF32 rate = bf16/2); " + ("of measured" if peaks else "of fallback")
     mult = 3.0 if args.gram_mode == "tf32x3" else 1.0
     achieved = issued * mult / gsum / 1e12 if gsum > 0 else 0.0
+    traffic, traffic_note = None, None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["gram_tc_kernel<1,2>"]
+        big = max(timer.extra["gram"], key=lambda c_: gram_flops(c_)[0]) if timer.extra["gram"] else None
+        if big is not None and args.gram_mode == "tf32x3" and big[:3] == (38, 29, 38):
+            traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["rows"] * big[3]
+            traffic_note = (f"dram__bytes_read+write of the dominant launch (middle site, {big[3]} rows), scaled by rows from the "
+                            f"{tr['rows']}-row ncu --set full capture ({tr['source']}); it is the fp64 flush of the fp32 accumulators, "
+                            f"not operand re-reads: the algorithmic operand bytes are {8 * big[3] * (38 + 29 + 38 + 1)} B + 1.9e9 B of M")
+    except Exception:
+        pass
     roofline = {"kernel": f"gram_kr3[{args.gram_mode}]", "bound": "tensor" if args.gram_mode != "fp64" else "fp64", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
+                "traffic_note": traffic_note,
                 "peak_source": peak_src, "issued_flops_per_step": issued * mult / args.steps,
                 "survey_algorithmic_flops_per_step": algo / args.steps,
                 "survey_equiv_tflops": algo / gsum / 1e12 if gsum > 0 else 0.0,
