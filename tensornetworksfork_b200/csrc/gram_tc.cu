@@ -138,6 +138,17 @@ tc_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict_
 // Warp w may touch TMEM lanes 32*(w%4)..+31 (= 32 rows of a U tile); the two producer warps that share a lane quarter
 // split the columns.  tcgen05.ld hands every lane one ROW; the 32x32 block is transposed through a padded shared
 // scratch so that each RED instruction adds 32 consecutive doubles of one row of M (coalesced) instead of 32 rows.
+// fp64 reduction into M with an L2 evict_last hint: the tile of M a CTA owns is flushed again a few milliseconds later, and
+// the tiles of all resident CTAs together (148 x 512 KB) fit the L2 -- keep them there instead of round-tripping through HBM.
+__device__ __forceinline__ uint64_t l2_evict_last_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void red_add_f64_keep(double* addr, double v, uint64_t pol) {
+    asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(addr), "d"(v), "l"(pol) : "memory");
+}
+
 __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_total, int BN, int warp, int lane, int64_t u0,
                                                int64_t nU, int v0, int nC, double* __restrict__ M, float* __restrict__ scratch,
                                                double unscale, int tile_stride = TC_M) {
@@ -147,6 +158,7 @@ __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_tota
     const int g_lo = half * ((ngroups + 1) / 2);
     const int g_hi = min(ngroups, g_lo + (ngroups + 1) / 2);
     float* sc = scratch + (size_t)(warp - 1) * (32 * 33);
+    const uint64_t l2_keep = l2_evict_last_policy();
     for (int g = g_lo; g < g_hi; ++g) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 32), r);
@@ -161,7 +173,7 @@ __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_tota
         double* dst = M + gu0 * nC + gv;
 #pragma unroll 4
         for (int rr = 0; rr < 32; ++rr) {
-            if (col_ok && gu0 + rr < nU) atomicAdd(dst + (int64_t)rr * nC, unscale * (double)sc[rr * 33 + lane]);
+            if (col_ok && gu0 + rr < nU) red_add_f64_keep(dst + (int64_t)rr * nC, unscale * (double)sc[rr * 33 + lane], l2_keep);
         }
         __syncwarp();
     }
