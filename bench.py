@@ -304,7 +304,8 @@ def bench_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    run_sweeps(layer, x, y, wl, args, args.warmup, counter)
+    for _ in range(args.warmup):
+        run_sweeps(layer, x, y, wl, args, 1, counter)      # one step = one call = one full sweep (L->R then R->L), as in the e2e loop
     barrier()
     # ---- device-resident timed region
     counter[0] = 0
@@ -318,7 +319,8 @@ def bench_b200(args):
     barrier()
     mv_count0 = getattr(tn, "matvec_count", 0)
     e0.record()
-    run_sweeps(layer, x, y, wl, args, args.steps, counter)
+    for _ in range(args.steps):
+        run_sweeps(layer, x, y, wl, args, 1, counter)
     e1.record()
     barrier()
     mv_count1 = getattr(tn, "matvec_count", 0)
