@@ -459,6 +459,7 @@ extern "C" int tn_env_update(const double* env_in, int64_t env_ld, int env_div, 
                              void* stream) {
     using namespace tn;
     TN_CHECK_ARG(rows >= 0 && r_in >= 1 && r_out >= 1 && f >= 1 && cdiv >= 1, "tn_env_update: bad sizes");
+    if (rows == 0) return TN_OK;       // an empty shard / batch: nothing to read or write (the pointers may be null)
     TN_CHECK_ARG(env_in != nullptr || r_in == 1, "tn_env_update: env_in == NULL requires r_in == 1");
     TN_CHECK_ARG(x && core, "tn_env_update: null input");
     TN_CHECK_ARG(dot ? (yhat != nullptr && dot_div >= 1) : (out != nullptr), "tn_env_update: missing output");

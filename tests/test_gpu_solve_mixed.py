@@ -118,3 +118,43 @@ def test_sweep_with_mixed_solve_tracks_fp64_solve():
         if mode == "mixed":
             assert net.solve_stats["mixed"] >= 1, net.solve_stats        # middle core: P = 12*12*12 = 1728
     assert gu.relerr(preds["mixed"], preds["fp64"]) < 1e-8
+
+
+def test_mixed_solve_fallback_path_redoes_the_system_in_fp64():
+    """Forcing the acceptance test to fail exercises the loud fall-back: A is re-expanded (its lower triangle was overwritten by the
+    tensor-core factor) and solved by the fp64 Cholesky; the sweep must land exactly where the fp64 solve mode lands."""
+    import tensornetworksfork_b200 as tnb
+    rng = np.random.default_rng(6)
+    N, F = 3000, 9
+    X = np.concatenate([rng.uniform(-1, 1, size=(N, F)), np.ones((N, 1))], 1)
+    y = np.tanh(X[:, :1] - X[:, 1:2] * X[:, 2:3])
+    preds = {}
+    for mode in ("fp64", "mixed"):
+        layer = tnb.TensorTrainLayer(3, 10, F + 1, output_shape=1, constrict_bond=False, perturb=True, seed=1)
+        layer.to(DEV)
+        net = layer.tensor_network
+        net.solve_mode = mode
+        net.mixed_accept = -1.0            # nothing is ever accepted
+        xs, ys = torch.tensor(X, device=DEV), torch.tensor(y, device=DEV)
+        assert net.accumulating_swipe(xs, ys, tnb.SquareBregFunction(), batch_size=-1, num_swipes=1, method="ridge_cholesky", eps=[1.0, 0.1])
+        preds[mode] = net.forward(xs, to_tensor=True).cpu().numpy()
+        if mode == "mixed":
+            assert net.solve_stats["mixed_fallback"] >= 1 and net.solve_stats["mixed"] == 0, net.solve_stats
+            assert net._mixed_floor == 2.0          # the largest ridge (2 eps) that failed is remembered ...
+    assert np.array_equal(preds["mixed"], preds["fp64"])       # ... and the redo is the plain fp64 path, bit for bit
+
+
+def test_kernels_accept_empty_batches():
+    """rows == 0 (an empty shard / empty last batch) is a no-op, not an error."""
+    from tensornetworksfork_b200.ops import Factor
+    e = torch.empty((0, 4), device=DEV)
+    x = torch.empty((0, 3), device=DEV)
+    core = torch.randn((4, 3, 5), device=DEV)
+    assert tuple(ops.env_update(e, Factor(x, m=3), core, 0).shape) == (0, 5)
+    fa, fb, fc = Factor(e, m=4), Factor(x, m=3), Factor(torch.empty((0, 2), device=DEV), m=2)
+    w = torch.empty((0,), device=DEV)
+    for mode in (ops.GRAM_FP64, ops.GRAM_TF32X3):
+        M = ops.gram(mode, fa, fb, fc, w, 0)
+        assert M.numel() == 10 * 6 * 3 and float(M.abs().sum()) == 0.0
+    b = ops.rhs(fa, fb, fc, w, 0)
+    assert b.numel() == 24 and float(b.abs().sum()) == 0.0
