@@ -198,16 +198,19 @@ rhs_small_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restr
     double* sW = sC + RS_ROWS * stC;
     const int P = fa.m * fb.m * fc.m;
     const int tid = threadIdx.x, nt = blockDim.x;
-    int ia[RS_PER], ib[RS_PER], ic[RS_PER];      // up to RS_PER entries of b per thread: i = tid + q * blockDim
+    // RS_PER consecutive entries of b per thread (c index fastest): they usually share (ia, ib), so one product w*A*B per row
+    // feeds RS_PER fused multiply-adds with consecutive entries of C
+    int ia[RS_PER], ib[RS_PER], ic[RS_PER];
     double acc[RS_PER];
 #pragma unroll
     for (int q = 0; q < RS_PER; ++q) {
-        const int i = min(tid + q * nt, P - 1);
+        const int i = min(tid * RS_PER + q, P - 1);
         ic[q] = i % fc.m;
         ib[q] = (i / fc.m) % fb.m;
         ia[q] = i / (fc.m * fb.m);
         acc[q] = 0.0;
     }
+    const bool same_ab = (ia[0] == ia[RS_PER - 1]) && (ib[0] == ib[RS_PER - 1]) && (tid * RS_PER + RS_PER - 1 < P);
     const int64_t k_begin = (int64_t)blockIdx.x * rows_per_cta;
     const int64_t k_end = min(rows, k_begin + rows_per_cta);
     for (int64_t kb = k_begin; kb < k_end; kb += RS_ROWS) {
@@ -232,17 +235,29 @@ rhs_small_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restr
             sW[k] = (row < k_end) ? (w ? w[row] : 1.0) : 0.0;
         }
         __syncthreads();
+        if (same_ab) {
+            const double* pa = sA + ia[0];
+            const double* pb = sB + ib[0];
+            const double* pc = sC + ic[0];
 #pragma unroll 4
-        for (int k = 0; k < RS_ROWS; ++k) {
-            const double wk = sW[k];
+            for (int k = 0; k < RS_ROWS; ++k) {
+                const double t = (sW[k] * pa[k * stA]) * pb[k * stB];
 #pragma unroll
-            for (int q = 0; q < RS_PER; ++q)
-                acc[q] = fma(wk * sA[k * stA + ia[q]], sB[k * stB + ib[q]] * sC[k * stC + ic[q]], acc[q]);
+                for (int q = 0; q < RS_PER; ++q) acc[q] = fma(t, pc[k * stC + q], acc[q]);
+            }
+        } else {
+#pragma unroll 4
+            for (int k = 0; k < RS_ROWS; ++k) {
+                const double wk = sW[k];
+#pragma unroll
+                for (int q = 0; q < RS_PER; ++q)
+                    acc[q] = fma(wk * sA[k * stA + ia[q]], sB[k * stB + ib[q]] * sC[k * stC + ic[q]], acc[q]);
+            }
         }
     }
 #pragma unroll
     for (int q = 0; q < RS_PER; ++q)
-        if (tid + q * nt < P) out[(int64_t)blockIdx.x * P + tid + q * nt] = acc[q];
+        if (tid * RS_PER + q < P) out[(int64_t)blockIdx.x * P + tid * RS_PER + q] = acc[q];
 }
 
 __global__ void reduce_splits_kernel(const double* __restrict__ work, double* __restrict__ dst, int64_t n, int ksplit,
@@ -444,15 +459,25 @@ extern "C" int tn_gram_ksplit(int64_t rows, int ma, int mb, int mc, int mode) {
     return choose_ksplit(rows, (int64_t)npairs(ma) * npairs(mb), npairs(mc));
 }
 
-static int rhs_small_ctas(int64_t rows) {
+static int rhs_small_threads(int64_t P) {
+    int threads = (int)((tn::ceil_div64(P, tn::RS_PER) + 31) / 32) * 32;
+    if (threads < 128) threads = 128;
+    if (threads > 1024) threads = 1024;
+    return threads;
+}
+
+static int rhs_small_ctas(int64_t rows, int64_t P) {
     int64_t n = tn::ceil_div64(rows, 8 * tn::RS_ROWS);
-    const int64_t cap = 2LL * tn::sm_count();
+    int per_sm = 1536 / rhs_small_threads(P);        // enough warps per SM to hide the shared-memory latency of the row loop
+    if (per_sm < 2) per_sm = 2;
+    if (per_sm > 6) per_sm = 6;
+    const int64_t cap = (int64_t)per_sm * tn::sm_count();
     if (n > cap) n = cap;
     return (int)(n < 1 ? 1 : n);
 }
 
 extern "C" int tn_rhs_ksplit(int64_t rows, int ma, int mb, int mc) {
-    if ((int64_t)ma * mb * mc <= tn::RS_MAXP) return rhs_small_ctas(rows);      // small-core kernel: one partial per CTA
+    if ((int64_t)ma * mb * mc <= tn::RS_MAXP) return rhs_small_ctas(rows, (int64_t)ma * mb * mc);   // small-core kernel: one partial per CTA
     return tn::choose_ksplit(rows, (int64_t)ma * mb, mc);
 }
 
@@ -489,12 +514,10 @@ extern "C" int tn_rhs_kr3(const tn_factor* fa, const tn_factor* fb, const tn_fac
     }
     if (P <= RS_MAXP) {
         const FactorDev a = to_dev(fa), bb = to_dev(fb), c = to_dev(fc);
-        const int ctas = rhs_small_ctas(rows);
+        const int ctas = rhs_small_ctas(rows, P);
         TN_CHECK_ARG(ksplit == ctas && work != nullptr, "tn_rhs_kr3: small-core path needs work for %d partials (got ksplit=%d)", ctas, ksplit);
         const int64_t rpc = ceil_div64(ceil_div64(rows, ctas), RS_ROWS) * RS_ROWS;
-        int threads = (int)((ceil_div64(P, RS_PER) + 31) / 32) * 32;
-        if (threads < 128) threads = 128;
-        if (threads > 1024) threads = 1024;
+        const int threads = rhs_small_threads(P);
         const size_t smem = (size_t)RS_ROWS * ((a.m | 1) + (bb.m | 1) + (c.m | 1) + 1) * sizeof(double);
         TN_CHECK_ARG(smem <= 200 * 1024, "tn_rhs_kr3: factors too wide for the small-core path");
         static size_t configured = 0;
