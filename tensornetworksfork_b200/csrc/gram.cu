@@ -198,19 +198,16 @@ rhs_small_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restr
     double* sW = sC + RS_ROWS * stC;
     const int P = fa.m * fb.m * fc.m;
     const int tid = threadIdx.x, nt = blockDim.x;
-    // RS_PER consecutive entries of b per thread (c index fastest): they usually share (ia, ib), so one product w*A*B per row
-    // feeds RS_PER fused multiply-adds with consecutive entries of C
-    int ia[RS_PER], ib[RS_PER], ic[RS_PER];
+    int ia[RS_PER], ib[RS_PER], ic[RS_PER];      // up to RS_PER entries of b per thread: i = tid + q * blockDim
     double acc[RS_PER];
 #pragma unroll
     for (int q = 0; q < RS_PER; ++q) {
-        const int i = min(tid * RS_PER + q, P - 1);
+        const int i = min(tid + q * nt, P - 1);
         ic[q] = i % fc.m;
         ib[q] = (i / fc.m) % fb.m;
         ia[q] = i / (fc.m * fb.m);
         acc[q] = 0.0;
     }
-    const bool same_ab = (ia[0] == ia[RS_PER - 1]) && (ib[0] == ib[RS_PER - 1]) && (tid * RS_PER + RS_PER - 1 < P);
     const int64_t k_begin = (int64_t)blockIdx.x * rows_per_cta;
     const int64_t k_end = min(rows, k_begin + rows_per_cta);
     for (int64_t kb = k_begin; kb < k_end; kb += RS_ROWS) {
@@ -235,29 +232,84 @@ rhs_small_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restr
             sW[k] = (row < k_end) ? (w ? w[row] : 1.0) : 0.0;
         }
         __syncthreads();
-        if (same_ab) {
-            const double* pa = sA + ia[0];
-            const double* pb = sB + ib[0];
-            const double* pc = sC + ic[0];
 #pragma unroll 4
-            for (int k = 0; k < RS_ROWS; ++k) {
-                const double t = (sW[k] * pa[k * stA]) * pb[k * stB];
+        for (int k = 0; k < RS_ROWS; ++k) {
+            const double wk = sW[k];
 #pragma unroll
-                for (int q = 0; q < RS_PER; ++q) acc[q] = fma(t, pc[k * stC + q], acc[q]);
-            }
-        } else {
-#pragma unroll 4
-            for (int k = 0; k < RS_ROWS; ++k) {
-                const double wk = sW[k];
-#pragma unroll
-                for (int q = 0; q < RS_PER; ++q)
-                    acc[q] = fma(wk * sA[k * stA + ia[q]], sB[k * stB + ib[q]] * sC[k * stC + ic[q]], acc[q]);
-            }
+            for (int q = 0; q < RS_PER; ++q)
+                acc[q] = fma(wk * sA[k * stA + ia[q]], sB[k * stB + ib[q]] * sC[k * stC + ic[q]], acc[q]);
         }
     }
 #pragma unroll
     for (int q = 0; q < RS_PER; ++q)
-        if (tid * RS_PER + q < P) out[(int64_t)blockIdx.x * P + tid * RS_PER + q] = acc[q];
+        if (tid + q * nt < P) out[(int64_t)blockIdx.x * P + tid + q * nt] = acc[q];
+}
+
+// Variant for cores whose last factor is at least 8 wide: a thread owns RS_PER entries b[ia, ib, ic0 + q*chunks] of ONE
+// (ia, ib) pair (the tail is padded; consecutive lanes own consecutive ic0: conflict-free shared-memory reads), so one product w*A[ia]*B[ib] per sample feeds RS_PER fused multiply-adds
+// with consecutive entries of C and no thread of a warp takes a different path.
+__global__ void __launch_bounds__(1024)
+rhs_small_vec_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restrict__ w, int64_t rows, double* __restrict__ out,
+                     int64_t rows_per_cta) {
+    extern __shared__ double sm[];
+    const int stA = fa.m | 1, stB = fb.m | 1, stC = (fc.m + RS_PER) | 1;      // C rows padded: the last chunk may read past fc.m
+    double* sA = sm;
+    double* sB = sA + RS_ROWS * stA;
+    double* sC = sB + RS_ROWS * stB;
+    double* sW = sC + RS_ROWS * stC;
+    const int P = fa.m * fb.m * fc.m;
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int chunks = (fc.m + RS_PER - 1) / RS_PER;
+    const int slots = fa.m * fb.m * chunks;
+    const bool active = tid < slots;
+    const int pair = active ? tid / chunks : 0;
+    const int ic0 = active ? tid - pair * chunks : 0;        // entries ic0 + q*chunks: consecutive lanes read consecutive words of C
+    const int ia = pair / fb.m, ib = pair - ia * fb.m;
+    double acc[RS_PER];
+#pragma unroll
+    for (int q = 0; q < RS_PER; ++q) acc[q] = 0.0;
+    const int64_t k_begin = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t k_end = min(rows, k_begin + rows_per_cta);
+    for (int i = tid; i < RS_ROWS * stC; i += nt) sC[i] = 0.0;                 // the pad columns stay zero
+    for (int64_t kb = k_begin; kb < k_end; kb += RS_ROWS) {
+        __syncthreads();
+        for (int idx = tid; idx < RS_ROWS * fa.m; idx += nt) {
+            const int k = idx / fa.m, i = idx - k * fa.m;
+            const int64_t row = kb + k;
+            sA[k * stA + i] = (row < k_end) ? map_eval(fa.map_kind, fa.ptr + (fa.div == 1 ? row : row / fa.div) * fa.ld, i) : 0.0;
+        }
+        for (int idx = tid; idx < RS_ROWS * fb.m; idx += nt) {
+            const int k = idx / fb.m, i = idx - k * fb.m;
+            const int64_t row = kb + k;
+            sB[k * stB + i] = (row < k_end) ? map_eval(fb.map_kind, fb.ptr + (fb.div == 1 ? row : row / fb.div) * fb.ld, i) : 0.0;
+        }
+        for (int idx = tid; idx < RS_ROWS * fc.m; idx += nt) {
+            const int k = idx / fc.m, i = idx - k * fc.m;
+            const int64_t row = kb + k;
+            sC[k * stC + i] = (row < k_end) ? map_eval(fc.map_kind, fc.ptr + (fc.div == 1 ? row : row / fc.div) * fc.ld, i) : 0.0;
+        }
+        for (int k = tid; k < RS_ROWS; k += nt) {
+            const int64_t row = kb + k;
+            sW[k] = (row < k_end) ? (w ? w[row] : 1.0) : 0.0;
+        }
+        __syncthreads();
+        if (active) {
+            const double* pa = sA + ia;
+            const double* pb = sB + ib;
+            const double* pc = sC + ic0;
+#pragma unroll 4
+            for (int k = 0; k < RS_ROWS; ++k) {
+                const double t = (sW[k] * pa[k * stA]) * pb[k * stB];
+#pragma unroll
+                for (int q = 0; q < RS_PER; ++q) acc[q] = fma(t, pc[k * stC + q * chunks], acc[q]);
+            }
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int q = 0; q < RS_PER; ++q)
+            if (ic0 + q * chunks < fc.m) out[(int64_t)blockIdx.x * P + (int64_t)pair * fc.m + ic0 + q * chunks] = acc[q];
+    }
 }
 
 __global__ void reduce_splits_kernel(const double* __restrict__ work, double* __restrict__ dst, int64_t n, int ksplit,
@@ -517,15 +569,28 @@ extern "C" int tn_rhs_kr3(const tn_factor* fa, const tn_factor* fb, const tn_fac
         const int ctas = rhs_small_ctas(rows, P);
         TN_CHECK_ARG(ksplit == ctas && work != nullptr, "tn_rhs_kr3: small-core path needs work for %d partials (got ksplit=%d)", ctas, ksplit);
         const int64_t rpc = ceil_div64(ceil_div64(rows, ctas), RS_ROWS) * RS_ROWS;
-        const int threads = rhs_small_threads(P);
-        const size_t smem = (size_t)RS_ROWS * ((a.m | 1) + (bb.m | 1) + (c.m | 1) + 1) * sizeof(double);
-        TN_CHECK_ARG(smem <= 200 * 1024, "tn_rhs_kr3: factors too wide for the small-core path");
-        static size_t configured = 0;
-        if (smem > configured) {
-            TN_CUDA(cudaFuncSetAttribute(rhs_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            configured = smem;
+        const int slots = a.m * bb.m * ((c.m + RS_PER - 1) / RS_PER);
+        if (c.m >= 8 && slots <= 1024) {
+            const int vthreads = ((slots + 31) / 32) * 32 < 128 ? 128 : ((slots + 31) / 32) * 32;
+            const size_t vsmem = (size_t)RS_ROWS * ((a.m | 1) + (bb.m | 1) + ((c.m + RS_PER) | 1) + 1) * sizeof(double);
+            TN_CHECK_ARG(vsmem <= 200 * 1024, "tn_rhs_kr3: factors too wide for the small-core path");
+            static size_t vconfigured = 0;
+            if (vsmem > vconfigured) {
+                TN_CUDA(cudaFuncSetAttribute(rhs_small_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
+                vconfigured = vsmem;
+            }
+            rhs_small_vec_kernel<<<ctas, vthreads, vsmem, as_stream(stream)>>>(a, bb, c, w, rows, work, rpc);
+        } else {
+            const int threads = rhs_small_threads(P);
+            const size_t smem = (size_t)RS_ROWS * ((a.m | 1) + (bb.m | 1) + (c.m | 1) + 1) * sizeof(double);
+            TN_CHECK_ARG(smem <= 200 * 1024, "tn_rhs_kr3: factors too wide for the small-core path");
+            static size_t configured = 0;
+            if (smem > configured) {
+                TN_CUDA(cudaFuncSetAttribute(rhs_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                configured = smem;
+            }
+            rhs_small_kernel<<<ctas, threads, smem, as_stream(stream)>>>(a, bb, c, w, rows, work, rpc);
         }
-        rhs_small_kernel<<<ctas, threads, smem, as_stream(stream)>>>(a, bb, c, w, rows, work, rpc);
         TN_LAUNCH_CHECK();
         int64_t blocks = ceil_div64(P, 256);
         reduce_splits_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(work, b, P, ctas, accumulate);
