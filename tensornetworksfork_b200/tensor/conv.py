@@ -25,7 +25,6 @@ from .. import ops
 from ..ops import Factor
 from .bregman import hessian_terms
 from .network import TensorNetwork
-from .node import TensorNode
 
 
 class ConvTrainNetwork(TensorNetwork):

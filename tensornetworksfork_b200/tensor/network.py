@@ -13,7 +13,6 @@ so ``node_states()/load_node_states()`` snapshots and EarlyStopping keep working
 change of a core is noticed through tensor identity/version and drops the cached environments,
 the way ``set_input``/``reset_stacks`` do in the reference (network.py:78-81, 329-345).
 """
-import math
 import time
 
 import torch
