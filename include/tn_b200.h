@@ -157,10 +157,11 @@ int tn_bmm(const double *A, int64_t sA, int64_t iA, int64_t kA, const double *B,
 int tn_outer_rows(const double *G, int64_t ldg, int gdiv, int ra, const double *W, int64_t ldw, int m, const double *w,
                   int64_t rows, double *out, int accumulate, void *stream);
 
-/* Row-wise products with a shared matrix (J v pass of a conv-TT patch core, tensor/network.py:789):
- * z[row, i] = sum_j W[row * ldw + j] * V[i * ldv + j],  z (rows x ra) contiguous, ra <= 128.                          */
+/* Row-wise products with a shared matrix (J v pass of a conv-TT patch core, tensor/network.py:789; also the per-sample
+ * contractions of a conv-TT column with its shared cores):
+ * z[row * ldz + i] = sum_j W[row * ldw + j] * V[i * ldv + j],  i < ra (any ra), ldz >= ra.                            */
 int tn_rows_dot(const double *W, int64_t ldw, int m, const double *V, int64_t ldv, int ra, int64_t rows, double *z,
-                void *stream);
+                int64_t ldz, void *stream);
 
 #ifdef __cplusplus
 }

@@ -52,7 +52,7 @@ PROTOTYPES = {
     "tn_matvec_work_elems": (i64, [i64, i32, i32, i32]),
     "tn_bmm": (i32, [vp, i64, i64, i64, vp, i64, i64, i64, vp, i64, i32, i32, i32, i32, vp]),
     "tn_outer_rows": (i32, [vp, i64, i32, i32, vp, i64, i32, vp, i64, vp, i32, vp]),
-    "tn_rows_dot": (i32, [vp, i64, i32, vp, i64, i32, i64, vp, vp]),
+    "tn_rows_dot": (i32, [vp, i64, i32, vp, i64, i32, i64, vp, i64, vp]),
     "tn_matvec_kr3": (i32, [FP, FP, FP, vp, i64, vp, vp, vp, vp]),
 }
 

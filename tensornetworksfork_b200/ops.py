@@ -300,13 +300,17 @@ def outer_rows(G, W, w=None, gdiv=1, out=None, accumulate=False):
     return out
 
 
-def rows_dot(W, V):
-    """z (rows, ra) = W (rows, m) @ V (ra, m)^T; row strides free, last dims contiguous."""
+def rows_dot(W, V, out=None):
+    """z (rows, ra) = W (rows, m) @ V (ra, m)^T; row strides free, last dims contiguous.  ``out`` may be a 2-D view with its own row
+    stride (a column block of a larger tensor)."""
     lib = _lib.load()
     _need_cuda(W, V)
     assert W.dim() == 2 and V.dim() == 2 and W.stride(1) == 1 and V.stride(1) == 1 and W.shape[1] == V.shape[1]
     rows, m = W.shape
     ra = V.shape[0]
-    z = torch.empty((rows, ra), dtype=torch.float64, device=W.device)
-    _lib.check(lib.tn_rows_dot(_p(W), W.stride(0), m, _p(V), V.stride(0), ra, rows, _p(z), _stream()), "tn_rows_dot")
-    return z
+    if out is None:
+        out = torch.empty((rows, ra), dtype=torch.float64, device=W.device)
+    assert out.dim() == 2 and tuple(out.shape) == (rows, ra) and (out.stride(1) == 1 or ra == 1)
+    _lib.check(lib.tn_rows_dot(_p(W), W.stride(0), m, _p(V), V.stride(0), ra, rows, _p(out), out.stride(0) if rows > 1 else ra,
+                               _stream()), "tn_rows_dot")
+    return out

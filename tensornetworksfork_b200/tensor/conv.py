@@ -163,10 +163,15 @@ class ConvTrainNetwork(TensorNetwork):
             C3 = self._C3(k)
             a, T, a2 = C3.shape
             s, Q, _ = xc.shape
-            core = C3.permute(1, 0, 2).reshape(1, T, a * a2)
-            Y = ops.env_update(None, Factor(xc.view(s * Q, T), m=T), core, s * Q)          # (s*Q, a*a')
+            Y = ops.rows_dot(xc.view(s * Q, T), C3.permute(0, 2, 1).reshape(a * a2, T).contiguous())      # (s*Q, a*a')
             return Y.view(s, Q, a, a2).permute(2, 3, 0, 1).contiguous()
         return self._cached(("Y", k, tag), [Cn], build)
+
+    @staticmethod
+    def _AY(Yt_ab, Aperm, r, r2):
+        """AY[s, r, r'] = sum_q Y[s, q] A[r, q, r'] for one pixel-bond pair: the column's per-sample transfer block, contracted over
+        the patches FIRST (shared by all output legs) -- one tall-skinny product with the core as the shared matrix."""
+        return ops.rows_dot(Yt_ab, Aperm).view(-1, r, r2)
 
     def _env_left(self, k, xc, tag):
         """E_k (s, C, a', r') after columns 0..k."""
@@ -180,21 +185,19 @@ class ConvTrainNetwork(TensorNetwork):
             a, a2, s, _ = Yt.shape
             if k == 0:
                 E = torch.empty((s, c, a2, r2), dtype=torch.float64, device=xc.device)
-                core = A4[0].permute(1, 0, 2).reshape(1, Q, c * r2)
+                V = A4[0].permute(0, 2, 1).reshape(c * r2, Q).contiguous()           # ((c, r'), q)
                 for b in range(a2):
-                    E[:, :, b, :] = ops.env_update(None, Factor(Yt[0, b], m=Q), core, s).view(s, c, r2)
+                    E[:, :, b, :] = ops.rows_dot(Yt[0, b], V).view(s, c, r2)
                 return E
             Ep = self._env_left(k - 1, xc, tag)                       # (s, C, a, r)
             C = Ep.shape[1]
             E = torch.empty((s, C, a2, r2), dtype=torch.float64, device=xc.device)
-            core = A4[:, 0].contiguous()                          # (r, Q, r')
-            Ep3 = Ep.view(s * C, a, r)
+            Aperm = A4[:, 0].permute(0, 2, 1).reshape(r * r2, Q).contiguous()         # ((r, r'), q)
+            acc = torch.empty((s, C, r2), dtype=torch.float64, device=xc.device)
             for b in range(a2):
-                acc = None
                 for al in range(a):
-                    o = ops.env_update(Ep3[:, al, :], Factor(Yt[al, b], m=Q), core, s * C, cdiv=C)
-                    acc = o if acc is None else acc.add_(o)
-                E[:, :, b, :] = acc.view(s, C, r2)
+                    ops.bmm(Ep[:, :, al, :], self._AY(Yt[al, b], Aperm, r, r2), out=acc, accumulate=al > 0)
+                E[:, :, b, :] = acc
             return E
         return self._cached(("L", k, tag), deps, build)
 
@@ -211,18 +214,17 @@ class ConvTrainNetwork(TensorNetwork):
             a, a2, s, _ = Yt.shape
             R = torch.empty((s, a, r), dtype=torch.float64, device=xc.device)
             if k == n - 1:
-                core = A4[:, 0, :, 0].t().reshape(1, Q, r)
+                V = A4[:, 0, :, 0].contiguous()                                      # (r, q)
                 for al in range(a):
-                    R[:, al, :] = ops.env_update(None, Factor(Yt[al, 0], m=Q), core, s)
+                    R[:, al, :] = ops.rows_dot(Yt[al, 0], V)
                 return R
             Rn = self._env_right(k + 1, xc, tag)                      # (s, a', r')
-            core = A4[:, 0].permute(2, 1, 0).contiguous()         # (r', Q, r)
+            Aperm = A4[:, 0].permute(0, 2, 1).reshape(r * r2, Q).contiguous()
+            acc = torch.empty((s, r, 1), dtype=torch.float64, device=xc.device)
             for al in range(a):
-                acc = None
                 for b in range(a2):
-                    o = ops.env_update(Rn[:, b, :], Factor(Yt[al, b], m=Q), core, s)
-                    acc = o if acc is None else acc.add_(o)
-                R[:, al, :] = acc
+                    ops.bmm(self._AY(Yt[al, b], Aperm, r, r2), Rn[:, b, :].unsqueeze(-1), out=acc, accumulate=b > 0)
+                R[:, al, :] = acc.view(s, r)
             return R
         return self._cached(("R", k, tag), deps, build)
 
@@ -328,16 +330,14 @@ class ConvTrainNetwork(TensorNetwork):
         core_A = A4[:, 0]                                                          # (r, Q, r')
         if k == 0:
             # K[s,b,(c,q)] = sum_r' R[s,b,r'] A_1[c,q,r']
-            core = A4[0].permute(2, 0, 1).reshape(r2, 1, c * Q)
-            K = ops.env_update(Rn.view(s * a2, r2), one, core, s * a2, cdiv=1 << 30)
+            K = ops.rows_dot(Rn.view(s * a2, r2), A4[0].reshape(c * Q, r2))
             K = K.view(s, a2, c, Q).permute(0, 2, 1, 3).contiguous().view(s, c * a2, Q)          # (s, (c,b), q), a = 1
         elif Rn is None:
-            core = core_A[:, :, 0].reshape(r, 1, Q)
-            K = ops.env_update(Ep.view(s * C * a, r), one, core, s * C * a, cdiv=1 << 30).view(s, C * a, Q)   # a' = 1
+            K = ops.rows_dot(Ep.view(s * C * a, r), core_A[:, :, 0].t().contiguous()).view(s, C * a, Q)       # a' = 1
         else:
-            core = core_A.permute(0, 2, 1).contiguous()                            # (r, r', Q)
-            Ks = [ops.env_update(Ep.view(s * C * a, r), Factor(Rn[:, b, :], m=r2), core, s * C * a, cdiv=C * a).view(s, C * a, Q)
-                  for b in range(a2)]
+            # contract the right environment with the core first (no output leg there), then the left one per sample
+            AR = ops.rows_dot(Rn.view(s * a2, r2), core_A.reshape(r * Q, r2)).view(s, a2, r, Q)
+            Ks = [ops.bmm(Ep.view(s, C * a, r), AR[:, b]) for b in range(a2)]
             K = torch.stack(Ks, dim=2).view(s, C * a * a2, Q)                      # (s, (c,a,b), q)
         J = ops.bmm(K, xc)                                                         # (s, (c,a,b), T)
         P = a * T * a2

@@ -220,5 +220,9 @@ def outer_rows(G, W, w=None, gdiv=1, out=None, accumulate=False):
     return out
 
 
-def rows_dot(W, V):
-    return (W @ V.t()).contiguous()
+def rows_dot(W, V, out=None):
+    r = W @ V.t()
+    if out is None:
+        return r.contiguous()
+    out.copy_(r)
+    return out
