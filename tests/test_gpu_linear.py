@@ -13,5 +13,5 @@ def test_linear_layer_sweeps_gpu(name):
     init_err, fwd_err, core_err, loss_err, pred_err = lc.run_case(name, "cuda")
     assert init_err == 0.0
     tight = lc.CASES[name]["kind"] == "dense"
-    assert fwd_err < 1e-12 and core_err < 1e-7 and loss_err < (1e-9 if tight else 1e-5) and pred_err < (1e-7 if tight else 1e-3), \
+    assert fwd_err < 1e-12 and core_err < (1e-7 if tight else 1e-6) and loss_err < (1e-9 if tight else 1e-5) and pred_err < (1e-7 if tight else 1e-3), \
         (fwd_err, core_err, loss_err, pred_err)

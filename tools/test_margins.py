@@ -1,0 +1,16 @@
+import sys, os
+sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/tests")
+import torch
+torch.set_default_dtype(torch.float64)
+import conv_cases as cc, linear_cases as lc, krylov_cases as kc, growing_case as gc
+for name in ["conv_lanczos_xe", "conv_lanczos_reg"]:
+    for chunk in (None, 37):
+        print(name, chunk, cc.run_case(name, "cuda", chunk_rows=chunk))
+for name in ["conv_scipy_cg", "conv_scipy_minres", "conv_scipy_cg_2col"]:
+    print(name, cc.run_case(name, "cuda", scipy_object=True), cc.run_case(name, "cuda", scipy_object=False, loss_prefix=8))
+for name in sorted(lc.CASES):
+    print(name, lc.run_case(name, "cuda"))
+for name in ["krylov_lanczos_reg", "krylov_lanczos_xe"]:
+    print(name, kc.run_case(name, "cuda"))
+for tag in "ab":
+    print("growing", tag, gc.run(tag, "cuda"))
