@@ -65,7 +65,8 @@ __device__ __forceinline__ double map_eval(int map_kind, const double* __restric
 int sm_count();
 // tensor-core trailing update of the blocked Cholesky (syrk_tc.cu)
 int64_t syrk_tc_work_floats(int64_t n, int kb);
-int syrk_tc_update(double* A, int64_t lda, int64_t P, int64_t c0, int64_t k0, int kb, float* X, const int* info, cudaStream_t st);
+int syrk_tc_update(double* A, int64_t lda, int64_t P, int64_t c0, int64_t k0, int kb, float* X, const int* info, cudaStream_t st,
+                   int64_t col_limit = 0);
 void count_launch(int n = 1);   // bookkeeping for tn_launch_count()
 
 // FP64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col): a = A[lane/4][lane%4], b = B[lane%4][lane/4],

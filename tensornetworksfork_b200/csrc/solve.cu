@@ -668,26 +668,50 @@ static int cholesky_factorize(double* A, int64_t lda, int64_t P, double* work, i
         return TN_OK;
     }
     const int64_t tc_min_n = 1024;
+    // tensor-core path, two levels: inside an outer panel the 64-wide steps update only their own 256-wide sub-panel (DMMA); each
+    // finished sub-panel then updates the rest of the outer panel on the tensor cores (K = 256), and the outer panel the rest
+    // of the matrix (K = NBO)
+    const int64_t NBI = (X && NBO % 256 == 0 && NBO > 256 && !getenv("TN_CHOL_NO_MID")) ? 256 : NBO;
     for (int64_t J = 0; J < P; J += NBO) {
         const int64_t Jend = (J + NBO < P) ? J + NBO : P;
-        for (int64_t j = J; j < Jend; j += CH_NB) {
-            const int nb = (int)((Jend - j < CH_NB) ? Jend - j : CH_NB);
-            double* Linv = work + (j / CH_NB) * CH_NB * CH_NB;
-            potrf_diag_kernel<<<1, 256, kBlkSmem, st>>>(A, lda, j, nb, Linv, info);
-            count_launch();
-            const int64_t below = P - (j + nb);
-            if (below > 0) {
-                trsm_panel_kernel<<<(unsigned)ceil_div64(below, CH_NB), 256, kBlkSmem, st>>>(A, lda, j, nb, Linv, P, info);
+        for (int64_t I = J; I < Jend; I += NBI) {
+            const int64_t Iend = (I + NBI < Jend) ? I + NBI : Jend;
+            for (int64_t j = I; j < Iend; j += CH_NB) {
+                const int nb = (int)((Iend - j < CH_NB) ? Iend - j : CH_NB);
+                double* Linv = work + (j / CH_NB) * CH_NB * CH_NB;
+                potrf_diag_kernel<<<1, 256, kBlkSmem, st>>>(A, lda, j, nb, Linv, info);
                 count_launch();
-                if (j + nb < Jend) {
-                    const int64_t c0 = j + nb;
-                    if (nb % DS_KC == 0 && lda % 2 == 0 && Jend - c0 >= DS_BT && P - c0 > 2048 && !getenv("TN_CHOL_INNER_FMA")) {
-                        dim3 grid((unsigned)ceil_div64(Jend - c0, DS_BT), (unsigned)ceil_div64(P - c0, DS_BT));
-                        syrk_update_dmma_kernel<<<grid, DS_THREADS, kDmmaSmem, st>>>(A, lda, P, c0, Jend, j, nb, info);
-                    } else {
-                        dim3 grid((unsigned)ceil_div64(Jend - c0, 64), (unsigned)ceil_div64(P - c0, 64));
-                        syrk_update_kernel<64><<<grid, 256, 0, st>>>(A, lda, P, c0, Jend, j, nb, info);
+                const int64_t below = P - (j + nb);
+                if (below > 0) {
+                    trsm_panel_kernel<<<(unsigned)ceil_div64(below, CH_NB), 256, kBlkSmem, st>>>(A, lda, j, nb, Linv, P, info);
+                    count_launch();
+                    if (j + nb < Iend) {
+                        const int64_t c0 = j + nb;
+                        if (nb % DS_KC == 0 && lda % 2 == 0 && Iend - c0 >= DS_BT && P - c0 > 2048 && !getenv("TN_CHOL_INNER_FMA")) {
+                            dim3 grid((unsigned)ceil_div64(Iend - c0, DS_BT), (unsigned)ceil_div64(P - c0, DS_BT));
+                            syrk_update_dmma_kernel<<<grid, DS_THREADS, kDmmaSmem, st>>>(A, lda, P, c0, Iend, j, nb, info);
+                        } else {
+                            dim3 grid((unsigned)ceil_div64(Iend - c0, 64), (unsigned)ceil_div64(P - c0, 64));
+                            syrk_update_kernel<64><<<grid, 256, 0, st>>>(A, lda, P, c0, Iend, j, nb, info);
+                        }
+                        count_launch();
                     }
+                }
+            }
+            if (Iend < Jend) {
+                // sub-panel [I, Iend) -> columns [Iend, Jend) of the outer panel, rows [Iend, P)
+                const int64_t width = Jend - Iend;
+                const int kbi = (int)(Iend - I);
+                if (X && P - Iend >= tc_min_n && (width % 256 == 0 || Jend == P)) {
+                    rc = syrk_tc_update(A, lda, P, Iend, I, kbi, X, info, st, (Jend == P) ? 0 : width);
+                    if (rc != TN_OK) return rc;
+                } else if (kbi % DS_KC == 0 && lda % 2 == 0 && P - Iend > 512) {
+                    dim3 grid((unsigned)ceil_div64(width, DS_BT), (unsigned)ceil_div64(P - Iend, DS_BT));
+                    syrk_update_dmma_kernel<<<grid, DS_THREADS, kDmmaSmem, st>>>(A, lda, P, Iend, Jend, I, kbi, info);
+                    count_launch();
+                } else {
+                    dim3 grid((unsigned)ceil_div64(width, 64), (unsigned)ceil_div64(P - Iend, 64));
+                    syrk_update_kernel<64><<<grid, 256, 0, st>>>(A, lda, P, Iend, Jend, I, kbi, info);
                     count_launch();
                 }
             }

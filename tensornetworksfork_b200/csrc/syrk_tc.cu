@@ -36,6 +36,8 @@ struct SyrkTcParams {
     double* C;          // A + c0 * lda + c0
     int64_t lda;
     const int* info;
+    int nt;             // tile rows of the trailing matrix
+    int nct;            // tile columns to update (== nt: the whole lower triangle; smaller: only the leading column tiles)
 };
 
 __global__ void __launch_bounds__(256)
@@ -65,14 +67,19 @@ syrk_tc_kernel(SyrkTcParams p) {
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
 
-    // lower-triangular tile (bi >= bj) of this CTA
+    // lower tile (bi >= bj, bj < nct) of this CTA
     int bi, bj;
-    {
+    if (p.nct == p.nt) {
         const int t = blockIdx.x;
         bi = (int)((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
         while ((bi + 1) * (bi + 2) / 2 <= t) ++bi;
         while (bi * (bi + 1) / 2 > t) --bi;
         bj = t - bi * (bi + 1) / 2;
+    } else {
+        int t = blockIdx.x;
+        bj = 0;
+        while (t >= p.nt - bj) { t -= p.nt - bj; ++bj; }       // column bj holds nt - bj tiles; nct is small on this path
+        bi = bj + t;
     }
     const int64_t r0 = (int64_t)bi * ST_TILE, q0 = (int64_t)bj * ST_TILE;
 
@@ -239,7 +246,9 @@ int64_t syrk_tc_work_floats(int64_t n, int kb) {
 }
 
 // C = A[c0:, c0:] -= A[c0:, k0:k0+kb] * A[c0:, k0:k0+kb]^T on the lower 256 x 256 tiles.  X: syrk_tc_work_floats(P - c0, kb).
-int syrk_tc_update(double* A, int64_t lda, int64_t P, int64_t c0, int64_t k0, int kb, float* X, const int* info, cudaStream_t st) {
+// col_limit > 0 restricts the update to the first col_limit columns of C (a multiple of 256, or everything up to P).
+int syrk_tc_update(double* A, int64_t lda, int64_t P, int64_t c0, int64_t k0, int kb, float* X, const int* info, cudaStream_t st,
+                   int64_t col_limit) {
     const int64_t n = P - c0;
     if (n <= 0 || kb <= 0) return TN_OK;
     static bool configured = false;
@@ -261,7 +270,14 @@ int syrk_tc_update(double* A, int64_t lda, int64_t P, int64_t c0, int64_t k0, in
     if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
     syrk_tc_convert_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, lda, c0, k0, n, kb, X, p.pitch, n_pad);
     TN_LAUNCH_CHECK();
-    const int64_t ntiles = nt * (nt + 1) / 2;
+    int64_t nct = nt;
+    if (col_limit > 0 && col_limit < n) {
+        TN_CHECK_ARG(col_limit % ST_TILE == 0, "syrk_tc_update: column limit %lld is not a multiple of the tile", (long long)col_limit);
+        nct = col_limit / ST_TILE;
+    }
+    p.nt = (int)nt;
+    p.nct = (int)nct;
+    const int64_t ntiles = nct * nt - nct * (nct - 1) / 2;
     TN_CHECK_ARG(ntiles <= 0x7fffffff, "syrk_tc_update: grid too large");
     syrk_tc_kernel<<<(unsigned)ntiles, ST_THREADS, ST_SMEM, st>>>(p);
     TN_LAUNCH_CHECK();
