@@ -334,7 +334,7 @@ def site_update(cores, x, y, k, loss="square", batch_size=-1, method="ridge_chol
 
 def accumulating_swipe(cores, x, y, loss="square", batch_size=-1, num_swipes=1, lr=1.0, method="exact",
                        eps=1e-12, eps_decay=None, orthonormalize=False, skip_second=False, direction="l2r",
-                       loss_kwargs=None, trace=None, eps_per_node=False):
+                       loss_kwargs=None, trace=None, eps_per_node=False, adaptive_step=False, max_norm=None):
     """Site order, eps schedule and turn-around skip of network.py:409-608.
     ``cores`` is updated in place.  ``trace`` (a list) receives one dict per site
     update: NS, k, eps, loss.  Returns True, or False on a singular system."""
@@ -353,7 +353,7 @@ def accumulating_swipe(cores, x, y, loss="square", batch_size=-1, num_swipes=1, 
     def one(k, e, left):
         try:
             r = site_update(cores, x, y, k, loss=loss, batch_size=batch_size, method=("exact" if (e == 0 and method == "ridge_exact") else method),
-                            eps=e, lr=lr, loss_kwargs=loss_kwargs)
+                            eps=e, lr=lr, loss_kwargs=loss_kwargs, adaptive_step=adaptive_step, max_norm=max_norm)
         except np.linalg.LinAlgError:
             return False
         if orthonormalize:

@@ -50,6 +50,11 @@ def load(name):
             "updates": ups, "pred": z["pred"], "ok": bool(z["ok"])}
 
 
+def sweep_extras(meta):
+    """The accumulating_swipe keywords a fixture sets beyond the common ones."""
+    return {k: meta[k] for k in ("direction", "eps_per_node", "adaptive_step", "max_norm") if k in meta}
+
+
 def relerr(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)

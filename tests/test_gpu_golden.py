@@ -75,9 +75,15 @@ def test_teacher_forced_updates(name):
             with pytest.raises(torch.linalg.LinAlgError):
                 tn._one_update(k, y, lf, method, u["eps"], meta["lr"], meta["batch_size"], False, None, True)
             continue
-        got = tn._one_update(k, y, lf, method, u["eps"], meta["lr"], meta["batch_size"], False, None, True)
+        shaped = meta.get("adaptive_step", False) or meta.get("max_norm") is not None
+        got = tn._one_update(k, y, lf, method, u["eps"], meta["lr"], meta["batch_size"], meta.get("adaptive_step", False),
+                             meta.get("max_norm"), True)
         assert abs(float(got) - u["loss"]) <= 1e-12 * max(1.0, abs(u["loss"]))
         new = node.tensor.cpu().numpy()
+        if shaped:      # the applied step is shrunk / projected (node.py:178-203): compare the updated core only
+            cond_ = np.linalg.cond(u["A"].reshape(P, P) / (np.abs(np.diag(u["A"].reshape(P, P))).mean() or 1.0) + 2 * u["eps"] * np.eye(P))
+            assert gu.relerr(new, u["after"][k]) < 1e-12 * cond_ + 1e-11
+            continue
         step = (new - u["before"][k]) / meta["lr"]
         Aref = u["A"].reshape(P, P)
         sc = np.abs(np.diag(Aref)).mean() or 1.0
@@ -105,7 +111,8 @@ def test_free_running_sweep(name):
     ok = tn.accumulating_swipe(x, y, loss_of(meta), batch_size=meta["batch_size"], num_swipes=meta["num_swipes"], lr=meta["lr"],
                                method=meta["method"], eps=meta["eps"], eps_decay=meta.get("eps_decay"),
                                orthonormalize=meta.get("orthonormalize", False), skip_second=meta.get("skip_second", False),
-                               loss_callback=lambda NS, node, l: trace.append((NS, tn.train_nodes.index(node), l)))
+                               loss_callback=lambda NS, node, l: trace.append((NS, tn.train_nodes.index(node), l)),
+                               **gu.sweep_extras(meta))
     assert ok == fx["ok"]
     assert [(a, b) for a, b, _ in trace] == [(u["NS"], u["k"]) for u in fx["updates"]]
     for (_, _, l), u in zip(trace, fx["updates"]):

@@ -61,7 +61,7 @@ def test_sweep_schedule_matches_reference_trace(name):
     first = cols if direction == "l2r" else cols[::-1]
     second = cols[::-1] if direction == "l2r" else cols
     sched = sweep_schedule(first, second, meta["num_swipes"], meta["eps"], meta.get("eps_decay"),
-                           meta.get("skip_second", False), direction)
+                           meta.get("skip_second", False), direction, meta.get("eps_per_node", False))
     got = [(NS, (first, second)[half][i], e) for NS, half, i, e in sched]
     want = [(u["NS"], u["k"], u["eps"]) for u in fx["updates"]]
     assert [(a, b) for a, b, _ in got] == [(a, b) for a, b, _ in want]

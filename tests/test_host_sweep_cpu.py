@@ -39,7 +39,8 @@ def run(fx, layer, x, y, **extra):
     ok = tn.accumulating_swipe(x, y, loss_of(meta), batch_size=meta["batch_size"], num_swipes=meta["num_swipes"], lr=meta["lr"],
                                method=meta["method"], eps=meta["eps"], eps_decay=meta.get("eps_decay"),
                                orthonormalize=meta.get("orthonormalize", False), skip_second=meta.get("skip_second", False),
-                               loss_callback=lambda NS, node, l: trace.append((NS, tn.train_nodes.index(node), l)), **extra)
+                               loss_callback=lambda NS, node, l: trace.append((NS, tn.train_nodes.index(node), l)),
+                               **gu.sweep_extras(meta), **extra)
     return ok, trace
 
 

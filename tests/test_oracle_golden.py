@@ -9,7 +9,7 @@ from oracle import tn_oracle as orc
 def _site(fx, u, cores):
     meta = fx["meta"]
     kw = dict(loss=meta["loss"], batch_size=meta["batch_size"], method=u.get("method", meta["method"]),
-              eps=u["eps"], lr=meta["lr"], apply=False)
+              eps=u["eps"], lr=meta["lr"], apply=False, adaptive_step=meta.get("adaptive_step", False), max_norm=meta.get("max_norm"))
     if meta["loss"] == "xe":
         kw["loss_kwargs"] = {"w": meta["w"]}
     m = meta["method"]
@@ -17,6 +17,7 @@ def _site(fx, u, cores):
         m = "exact"
     kw["method"] = m
     if meta["kind"] == "cpd":
+        kw.pop("adaptive_step"), kw.pop("max_norm")
         return orc.cpd_site_update(cores, fx["x"], fx["y"], u["k"], **kw)
     return orc.site_update(cores, fx["x"], fx["y"], u["k"], **kw)
 
@@ -45,7 +46,8 @@ def test_teacher_forced_site_updates(name):
         cond = np.linalg.cond(M)
         assert gu.relerr(r["step"].ravel(), u["step"].ravel()) < 1e-13 * cond + 1e-12
         if not meta.get("orthonormalize"):
-            new = orc.update_node(u["before"][u["k"]], u["step"], lr=meta["lr"])
+            new = orc.update_node(u["before"][u["k"]], u["step"], lr=meta["lr"], adaptive_step=meta.get("adaptive_step", False),
+                                  max_norm=meta.get("max_norm"))
             assert gu.relerr(new, u["after"][u["k"]]) < 1e-13
 
 
@@ -86,7 +88,7 @@ def test_free_running_sweep(name):
     ok = orc.accumulating_swipe(cores, fx["x"], fx["y"], loss=meta["loss"], batch_size=meta["batch_size"],
                                 num_swipes=meta["num_swipes"], lr=meta["lr"], method=meta["method"], eps=meta["eps"],
                                 eps_decay=meta.get("eps_decay"), orthonormalize=meta.get("orthonormalize", False),
-                                skip_second=meta.get("skip_second", False), trace=trace, **kw)
+                                skip_second=meta.get("skip_second", False), trace=trace, **gu.sweep_extras(meta), **kw)
     assert ok == fx["ok"]
     assert [(t["NS"], t["k"]) for t in trace] == [(u["NS"], u["k"]) for u in fx["updates"]]
     for t, u in zip(trace, fx["updates"]):
