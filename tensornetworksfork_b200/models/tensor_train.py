@@ -113,8 +113,14 @@ class TensorTrainRegressor(BaseEstimator, RegressorMixin):
                 return cls(i, bond_dim=self.r, input_features=f, output_shape=self.output_dim, constrict_bond=self.constrict_bond,
                            perturb=self.perturb, seed=self.seed + i)
             if self.linear_dim is not None and self.linear_dim < self.input_dim:
-                raise NotImplementedError("type-I sums of linear-projection trains are not part of the B200 path")
-            nets = [member(i).tensor_network for i in range(1, self.N + 1)]
+                if not mt.startswith("tt") or self.cum_sum:
+                    raise NotImplementedError("linear projections exist for tensor-train members only")
+                nets = [TensorTrainLinearLayer(i, bond_dim=self.r, input_features=self.input_dim - 1 if i != 1 else self.input_dim,
+                                               linear_dim=self.linear_dim, output_shape=self.output_dim,
+                                               constrict_bond=self.constrict_bond, perturb=self.perturb,
+                                               seed=self.seed + i).tensor_network for i in range(1, self.N + 1)]
+            else:
+                nets = [member(i).tensor_network for i in range(1, self.N + 1)]
             self._model = TensorNetworkLayer(SumOfNetworks(nets, output_labels=nets[0].output_labels,
                                                            train_operators=self.train_operator)).to(self.device)
             self._model.tensor_network.gram_mode = self.gram_mode

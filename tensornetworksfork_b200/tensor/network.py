@@ -1132,7 +1132,7 @@ class SumOfNetworks(TensorNetwork):
 
     def _member_of(self, node):
         for j, net in enumerate(self.networks):
-            if any(node is n for n in net.main_nodes):
+            if any(node is n for n in net.main_nodes) or any(node is n for n in net.train_nodes):
                 return j, net
         raise ValueError("Node not found in any network")
 
@@ -1152,6 +1152,8 @@ class SumOfNetworks(TensorNetwork):
     def _member_width(self, net):
         s = net._plan()[0] if not hasattr(net, "_rank") else None
         if s is not None:
+            if getattr(s, "linear", None) is not None:
+                return s.linear.tensor.shape[1]          # members built from linear-projection trains see the raw features
             return net._phys_size(s)
         return net._plan()[0].dim_size("p")
 
@@ -1206,8 +1208,7 @@ class SumOfNetworks(TensorNetwork):
         net.gram_mode = self.gram_mode
         net._yhat_offset = offset
         try:
-            return net._one_update(net.main_nodes.index(node), y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm,
-                                   need_loss)
+            return net._update_node(node, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss)
         finally:
             net._yhat_offset = None
 
