@@ -35,6 +35,7 @@ class ConvTrainNetwork(TensorNetwork):
         self._cache = {}
         self._ver = {}                  # node -> number of updates applied by this engine (part of every cache stamp)
         self.matvec_count = 0           # matvecs served so far (bench bookkeeping)
+        self.dense_chunk_bytes = 1 << 30   # cap on the materialised Jacobian of one chunk in the dense sweep
 
     # ------------------------------------------------------------------ graph
     def _columns(self):
@@ -325,11 +326,50 @@ class ConvTrainNetwork(TensorNetwork):
                 return t.view(s, C)
             return fold, jv_fn, fold
 
-        # ---- pixel core: materialise J (s, C, a*T*a') through K[s,(c,a,b),q]
+        # ---- pixel core: its Jacobian is small, materialise it
+        J = self._jacobian_chunk(kind, k, xc, tag)
+        P = J.shape[1]
+
+        def rhs_fn(g):
+            return wide_rhs(g.reshape(s * C, 1).contiguous(), J)
+
+        def jv_fn(v):
+            return wide_dot(J, v.view(1, P)).view(s, C)
+        return rhs_fn, jv_fn, rhs_fn
+
+    def _jacobian_chunk(self, kind, k, xc, tag):
+        """Dense Jacobian J (s*C, P) of node (kind, k) on one row chunk, P in the node's own (canonical) order."""
+        cols = self._columns()
+        n = len(cols)
+        dev = xc.device
+        s = xc.shape[0]
+        A4 = self._A4(k)
+        r, c, Q, r2 = A4.shape
+        C = self._num_outputs()
+        Yt = self._Yt(k, xc, tag)
+        a, a2 = Yt.shape[0], Yt.shape[1]
+        Rn = self._env_right(k + 1, xc, tag) if k < n - 1 else None
+        Ep = self._env_left(k - 1, xc, tag) if k > 0 else None
+        if kind == "A":
+            m = Q * r2
+            YR = torch.empty((s, a, m), dtype=torch.float64, device=dev)
+            for al in range(a):
+                if Rn is None:
+                    YR[:, al, :] = Yt[al, 0]
+                else:
+                    YR[:, al, :] = ops.bmm(Yt[al].permute(1, 2, 0), Rn).view(s, m)
+            if k == 0:
+                # the core owns the output leg: J[s, c, (c', q, r')] = delta_cc' YR[s, (q, r')]
+                J = torch.zeros((s, C, C, m), dtype=torch.float64, device=dev)
+                for cc in range(C):
+                    J[:, cc, cc, :] = YR[:, 0, :]
+                return J.view(s * C, C * m)
+            # J[s, (c, r), (q, r')] = sum_a E[s, c, a, r] YR[s, a, (q, r')]: one small product per sample
+            Et = Ep.permute(0, 1, 3, 2).contiguous().view(s, C * r, a)
+            return ops.bmm(Et, YR).view(s * C, r * m)
         T = xc.shape[2]
         core_A = A4[:, 0]                                                          # (r, Q, r')
         if k == 0:
-            # K[s,b,(c,q)] = sum_r' R[s,b,r'] A_1[c,q,r']
             K = ops.rows_dot(Rn.view(s * a2, r2), A4[0].reshape(c * Q, r2))
             K = K.view(s, a2, c, Q).permute(0, 2, 1, 3).contiguous().view(s, c * a2, Q)          # (s, (c,b), q), a = 1
         elif Rn is None:
@@ -341,14 +381,7 @@ class ConvTrainNetwork(TensorNetwork):
             K = torch.stack(Ks, dim=2).view(s, C * a * a2, Q)                      # (s, (c,a,b), q)
         J = ops.bmm(K, xc)                                                         # (s, (c,a,b), T)
         P = a * T * a2
-        J = J.view(s, C, a, a2, T).permute(0, 1, 2, 4, 3).contiguous().view(s * C, P)
-
-        def rhs_fn(g):
-            return wide_rhs(g.reshape(s * C, 1).contiguous(), J)
-
-        def jv_fn(v):
-            return wide_dot(J, v.view(1, P)).view(s, C)
-        return rhs_fn, jv_fn, rhs_fn
+        return J.view(s, C, a, a2, T).permute(0, 1, 2, 4, 3).contiguous().view(s * C, P)
 
     def _krylov_problem(self, node, y, loss_fn):
         kind, k = self._locate(node)
@@ -389,14 +422,67 @@ class ConvTrainNetwork(TensorNetwork):
         node.tensor = new
         self._ver[node] = self._ver.get(node, 0) + 1     # every cached quantity that depends on this core is rebuilt on use
 
-    # ------------------------------------------------------------------ what this engine does not cover
-    def accumulating_swipe(self, *a, **k):
-        raise NotImplementedError("conv-TT cores are updated with the matrix-free sweeps (scipy_swipe / lanczos_swipe), as in "
-                                  "image_convolution_CG_MNIST.py / image_convolution_lanczos_MNIST.py; the dense-Gram sweep "
-                                  "is not part of the B200 path for this layer")
+    # ------------------------------------------------------------------ dense sweep (accumulating_swipe)
+    def _dense_A_b(self, node, y, loss_fn):
+        """A = sum J^T H J (P x P, dense), b = sum J^T g and the per-row loss, accumulated chunk by chunk (reference
+        tensor/network.py:174-217).  The Jacobian of a conv-TT core is a sum of Kronecker terms, not one, so it is materialised per
+        chunk and reduced with the row-reduced outer-product kernel; the matrix-free sweeps are the fast path for large patch cores."""
+        kind, k = self._locate(node)
+        _, xb, S, dev = self._data
+        P = node.tensor.numel()
+        C = self._num_outputs()
+        rows_cap = max(1, int(self.dense_chunk_bytes // (8 * C * P)))
+        A = torch.zeros((P, P), dtype=torch.float64, device=dev)
+        b = torch.zeros((1, P), dtype=torch.float64, device=dev)
+        losses = []
+        saved_chunk = self.chunk_rows
+        self.chunk_rows = min(self.chunk_rows, rows_cap)
+        try:
+            for ci, (lo, hi) in enumerate(self._chunks(S)):
+                xc = xb[lo:hi]
+                s = hi - lo
+                tag = ("dense", ci)
+                yhat = self._predict_chunk(xc, tag)
+                loss, g, U, lam = self._loss_terms(yhat, y[lo:hi], loss_fn)
+                J = self._jacobian_chunk(kind, k, xc, tag).view(s, C, P)
+                F, Gr = ops.class_rows(J, U, g)                      # virtual rows F (s*V, P), G (s, P) = sum_c g J
+                w = lam.reshape(-1).contiguous()
+                for i0 in range(0, P, 128):
+                    i1 = min(i0 + 128, P)
+                    ops.outer_rows(F[:, i0:i1], F, w, out=A[i0:i1], accumulate=True)
+                ops.outer_rows(torch.ones((s, 1), dtype=torch.float64, device=dev), Gr, None, out=b, accumulate=True)
+                losses.append(loss)
+                for key in [kk for kk in self._cache if kk[-1] == tag]:      # dense chunks are not revisited: free their caches
+                    del self._cache[key]
+        finally:
+            self.chunk_rows = saved_chunk
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(A, group=self.process_group)
+            dist.all_reduce(b, group=self.process_group)
+        return A, b.view(-1), (torch.cat(losses, dim=0) if len(losses) != 1 else losses[0])
 
-    def get_A_b(self, *a, **k):
-        raise NotImplementedError("dense (A, b) of a conv-TT node")
+    def get_A_b(self, node, grad=None, hessian=None, method=None, y=None, loss_fn=None):
+        if loss_fn is None:
+            from .network import _FixedTerms
+            loss_fn = _FixedTerms(grad, hessian)
+        A, b, _ = self._dense_A_b(node, y, loss_fn)
+        shp = tuple(node.tensor.shape)
+        return A.reshape(shp + shp), b.reshape(shp)
+
+    def _update_node(self, node, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss):
+        A, b, loss_rows = self._dense_A_b(node, y, loss_fn)
+        step = self.solve_system(node, A, b, method=method, eps=eps)
+        new = node.tensor.detach().clone().contiguous()
+        ops.update_node(new.view(-1), step.contiguous().view(-1), lr=lr, adaptive_step=adaptive_step, max_norm=max_norm)
+        node.tensor = new
+        self._ver[node] = self._ver.get(node, 0) + 1
+        if not need_loss:
+            return None
+        from .network import batch_mean_of_means
+        S = loss_rows.shape[0]
+        return batch_mean_of_means(loss_rows, batch_size, row_offset=self.shard_offset,
+                                   n_total=self.shard_total if self.process_group is not None else S, group=self.process_group)
 
     def orthonormalize_left(self):
         raise NotImplementedError("QR re-gauge of a conv-TT")

@@ -23,6 +23,12 @@ CASES = {
     "conv_scipy_cg_2col": dict(kind="scipy", solver="cg", ctor=dict(num_carriages=2, bond_dim=3, num_patches=5, patch_pixels=4, output_shape=1, convolution_bond=2),
                                loss=lambda: tnb.SquareBregFunction(), oloss="square",
                                kw=dict(batch_size=-1, num_swipes=1, lr=1.0, max_iter=25, tol=1e-5)),
+    "conv_dense_xe": dict(kind="dense", ctor=dict(num_carriages=3, bond_dim=3, num_patches=5, patch_pixels=4, output_shape=2, convolution_bond=2),
+                          loss=lambda: tnb.XEAutogradBregman(w=1.0), oloss="xe",
+                          kw=dict(batch_size=50, num_swipes=1, lr=1.0, method="ridge_exact", eps=1.0, eps_decay=0.5)),
+    "conv_dense_reg": dict(kind="dense", ctor=dict(num_carriages=3, bond_dim=3, num_patches=6, patch_pixels=5, output_shape=1, convolution_bond=2),
+                           loss=lambda: tnb.SquareBregFunction(), oloss="square",
+                           kw=dict(batch_size=-1, num_swipes=2, lr=1.0, method="ridge_cholesky", eps=0.5, eps_decay=0.7)),
 }
 
 
@@ -60,7 +66,10 @@ def run_case(name, device, scipy_object=True, chunk_rows=None, loss_prefix=None)
     def block_callback(NS, node):
         ups.append((NS, tn.train_nodes.index(node), [n.tensor.cpu().numpy().copy() for n in tn.train_nodes]))
 
-    if case["kind"] == "lanczos":
+    if case["kind"] == "dense":
+        ok = tn.accumulating_swipe(X, y, case["loss"](), block_callback=block_callback,
+                                   loss_callback=lambda NS, node, l: losses.append(l), **case["kw"])
+    elif case["kind"] == "lanczos":
         x0s = [u["x0"] for u in fx["updates"]]
         cnt = [0]
 

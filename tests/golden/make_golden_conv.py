@@ -105,5 +105,49 @@ def main():
     record("scipy", "conv_scipy_cg_2col", layer, X, y, SquareBregFunction(), solver="cg", batch_size=-1, num_swipes=1, lr=1.0, max_iter=25, tol=1e-5)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and len(sys.argv) == 1:
     main()
+
+
+def record_dense(name, layer, X, y, loss_fn, **kw):
+    """accumulating_swipe on the conv layer (image_convolution_MNIST.py:120 call shape)."""
+    tn = layer.tensor_network
+    cores0 = [n.tensor.detach().numpy().copy() for n in tn.train_nodes]
+    names = [n.name for n in tn.train_nodes]
+    pred0 = tn.forward(X, to_tensor=True).detach().numpy().copy()
+    tn.reset_stacks()
+    ups, losses = [], []
+
+    def block_callback(NS, node):
+        ups.append({"NS": NS, "k": tn.train_nodes.index(node), "after": [n.tensor.detach().numpy().copy() for n in tn.train_nodes]})
+
+    ok = tn.accumulating_swipe(X, y, loss_fn, block_callback=block_callback, loss_callback=lambda NS, node, l: losses.append(float(l)), **kw)
+    tn.reset_stacks()
+    pred1 = tn.forward(X, to_tensor=True).detach().numpy().copy()
+    flat = {"x": X.numpy(), "y": y.numpy(), "n_cores": np.array(len(cores0)), "n_updates": np.array(len(ups)), "ok": np.array(bool(ok)),
+            "losses": np.array(losses), "names": np.array(names), "pred0": pred0, "pred1": pred1}
+    for i, c in enumerate(cores0):
+        flat[f"cores0_{i}"] = c
+    for ui, u in enumerate(ups):
+        flat[f"u{ui}_scal"] = np.array([u["NS"], u["k"]])
+        for i, c in enumerate(u["after"]):
+            flat[f"u{ui}_after_{i}"] = c
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **flat)
+    print(name, names, len(ups), "updates", "ok", ok, "losses", losses[:3], "->", losses[-1])
+
+
+def main_dense():
+    torch.manual_seed(15)
+    X, y = data(5, 130, 5, 4, K=3)
+    layer = TensorConvolutionTrainLayer(num_carriages=3, bond_dim=3, num_patches=5, patch_pixels=4, output_shape=2, convolution_bond=2)
+    record_dense("conv_dense_xe", layer, X, y, XEAutogradBregman(w=1.0), batch_size=50, num_swipes=1, lr=1.0, method="ridge_exact", eps=1.0,
+                 eps_decay=0.5)
+    torch.manual_seed(16)
+    X, y = data(6, 140, 6, 5, C=1)
+    layer = TensorConvolutionTrainLayer(num_carriages=3, bond_dim=3, num_patches=6, patch_pixels=5, output_shape=1, convolution_bond=2)
+    record_dense("conv_dense_reg", layer, X, y, SquareBregFunction(), batch_size=-1, num_swipes=2, lr=1.0, method="ridge_cholesky", eps=0.5,
+                 eps_decay=0.7)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "dense":
+    main_dense()

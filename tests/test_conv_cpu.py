@@ -55,11 +55,16 @@ def test_conv_device_krylov_solvers_track_the_float32_reference(name, monkeypatc
     assert loss < 2e-2, (core, loss)
 
 
-def test_conv_dense_sweep_is_refused(monkeypatch):
+@pytest.mark.parametrize("name", ["conv_dense_xe", "conv_dense_reg"])
+@pytest.mark.parametrize("chunk_bytes", [1 << 30, 20000])
+def test_conv_dense_sweep_host_logic(name, chunk_bytes, monkeypatch):
+    """accumulating_swipe on the conv layer (image_convolution_MNIST.py:120 call shape) against the reference recording; the small
+    byte cap forces several Jacobian chunks per node."""
     fake_ops.install(monkeypatch)
-    case, fx, layer = cc.build("conv_scipy_cg_2col", "cpu")
-    with pytest.raises(NotImplementedError):
-        layer.tensor_network.accumulating_swipe(torch.tensor(fx["x"]), torch.tensor(fx["y"]), case["loss"]())
+    from tensornetworksfork_b200.tensor import conv
+    monkeypatch.setattr(conv.ConvTrainNetwork, "dense_chunk_bytes", chunk_bytes, raising=False)
+    fwd, core, loss, pred = cc.run_case(name, "cpu")
+    assert fwd < 1e-12 and core < 1e-8 and loss < 1e-10 and pred < 1e-8, (fwd, core, loss, pred)
 
 
 def _conv_shard_worker(rank, world, port, name, out_dir):

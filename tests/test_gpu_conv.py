@@ -71,6 +71,12 @@ def test_conv_scipy_swipe_gpu(name):
     assert loss < 2e-2, (core, loss)
 
 
+@pytest.mark.parametrize("name", ["conv_dense_xe", "conv_dense_reg"])
+def test_conv_dense_sweep_gpu(name):
+    fwd, core, loss, pred = cc.run_case(name, "cuda")
+    assert fwd < 1e-12 and core < 1e-7 and loss < 1e-9 and pred < 1e-7, (fwd, core, loss, pred)
+
+
 def test_conv_jacobians_and_matvec_against_oracle_mnist_like_shape():
     """Config-4b-like column shapes (50 patches x 17 pixels, r = 12, CB = 4, 9 logits) on seeded data: the rhs and matvec of every
     node against the dense Jacobian of the numpy oracle."""
