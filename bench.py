@@ -23,6 +23,12 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+if "reference" in sys.argv and os.environ.get("OMP_NUM_THREADS") == "1":
+    # torchrun exports OMP_NUM_THREADS=1 for every rank; the CPU arm runs on rank 0 alone and is meant to use all host cores.
+    # The BLAS / OpenMP pools read this when numpy / torch are imported, so it has to be lifted before the imports below.
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(os.cpu_count() or 1)
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -468,7 +474,7 @@ def bench_b200(args):
            "roofline": roofline, "solve": solve_info, "kernel_time_share": shares,
            "gpu_launches": launches,
            "clocks": clk, "e2e": e2e}
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:      # the CPU baseline is a rank-0, N = 1 figure (the driver's reference arm covers N > 1)
         out["cpu_baseline"] = cpu_baseline(args, wl, n * world)
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
@@ -561,7 +567,23 @@ def cpu_site_time(wl, rows, reps=1):
     return t_batch, t_solve, n
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core.  Returns the thread count in effect."""
+    ncpu = os.cpu_count() or 1
+    try:
+        torch.set_num_threads(ncpu)
+    except Exception:
+        pass
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=ncpu)          # numpy's BLAS / OpenMP pools
+    except Exception:
+        pass
+    return ncpu
+
+
 def cpu_baseline(args, wl, rows_total):
+    use_all_host_threads()
     rows = args.ref_rows or (256 if args.workload == "cfg5a" else ((32 if wl["kind"] == "conv" else 128) if wl.get("solver") else 2048))
     if wl.get("solver") and "_avg_matvecs" not in wl:
         wl = dict(wl, _avg_matvecs=float(args.ref_matvecs))
@@ -587,6 +609,7 @@ def bench_reference(args):
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
+    use_all_host_threads()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n = (args.n if args.n is not None else wl["n"]) * world
     rows = args.ref_rows or (256 if args.workload == "cfg5a" else ((32 if wl["kind"] == "conv" else 128) if wl.get("solver") else 2048))
