@@ -70,20 +70,30 @@ class ConvTrainNetwork(TensorNetwork):
             raise NotImplementedError(f"{node.name}: label order {node.dim_labels} is not the constructor's")
         return node.tensor.reshape([node.dim_size(l) if l in node.dim_labels else 1 for l in order])
 
+    def _bonds(self, k, which):
+        """(left, right) bond labels of the patch (which = 0) or pixel (which = 1) core of column k, read from the connections to the
+        neighbouring columns: grow_cart gives the old last cores a right bond without listing it in ``right_labels``."""
+        cols = self._columns()
+        node = cols[k][which]
+
+        def towards(j):
+            if not 0 <= j < len(cols):
+                return None
+            return next((lab for lab, other in node.connections.items() if other is cols[j][which] and lab in node.dim_labels), None)
+        return towards(k - 1) or "_l", towards(k + 1) or "_r"
+
     def _A4(self, k):
         """Patch core k as (r, c, Q, r')."""
         A = self._columns()[k][0]
         out_labels = [l for l in self.output_labels if l != self.sample_dim]
         cls = next((l for l in A.dim_labels if l in out_labels), "_c")
-        left = A.left_labels[0] if A.left_labels else "_l"
-        right = A.right_labels[0] if A.right_labels else "_r"
+        left, right = self._bonds(k, 0)
         return self._to_canon(A, [left, cls, "patches", right])
 
     def _C3(self, k):
         """Pixel core k as (a, T, a')."""
         Cn = self._columns()[k][1]
-        left = Cn.left_labels[0] if Cn.left_labels else "_l"
-        right = Cn.right_labels[0] if Cn.right_labels else "_r"
+        left, right = self._bonds(k, 1)
         return self._to_canon(Cn, [left, "patch_pixels", right])
 
     def _num_outputs(self):

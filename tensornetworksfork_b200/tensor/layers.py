@@ -462,4 +462,43 @@ class TensorConvolutionTrainLayer(TensorNetworkLayer):
         self.train_nodes = train_blocks + conv_blocks
 
     def grow_cart(self, new_bond=None, new_convolution_bond=None):
-        raise NotImplementedError("grow_cart (adding a column to a trained conv-TT, reference tensor/layers.py:892-947)")
+        """Append one column to a (trained) conv-TT (reference tensor/layers.py:892-947; image_convolution_growing_MNIST.py:88).
+
+        The old last patch / pixel cores get a new right bond by broadcasting (every slice equal); the new patch core is
+        ``1/new_bond`` on the bias patch and zero elsewhere, so with the new pixel core on the bias pixel the function is
+        unchanged up to that pixel core's scale; the new pixel core is a fresh unit-norm random draw.  New tensors are created on
+        the CPU, like the reference's: call ``.cuda()`` on the layer afterwards.  The network object is rebuilt (every cached
+        environment belongs to the old topology); its engine settings carry over."""
+        n = self.num_carriages
+        Q, T = self.num_patches, self.patch_pixels
+        new_bond = self.bond_dim if new_bond is None else new_bond
+        CB = self.convolution_bond if new_convolution_bond is None else new_convolution_bond
+        if CB <= 0:
+            raise NotImplementedError("convolution_bond <= 0 (pixel vector) is not part of the B200 path")
+        rb, cb = f"r{n + 1}", f"CB{n + 1}"
+        x_new = TensorNode((1, Q, T), ["s", "patches", "patch_pixels"], name=f"X{n + 1}")
+        core = torch.zeros((new_bond, 1, Q, 1))
+        core[:, :, -1] = 1.0 / new_bond
+        A_new = TensorNode(core, [rb, f"c{n + 1}", "patches", f"r{n + 2}"], l=rb, r=f"r{n + 2}", name=f"A{n + 1}")
+        x_new.connect(A_new, "patches")
+        # the new last pixel core has no right bond (the reference's size expression reduces to this)
+        C_new = TensorNode((CB if n != 1 else 1, T, 1), [cb, "patch_pixels", f"CB{n + 2}"], l=cb, r=f"CB{n + 2}", name=f"C{n + 1}")
+        x_new.connect(C_new, "patch_pixels")
+        self.x_nodes.append(x_new)
+
+        A_last, C_last = self.train_blocks[-1], self.conv_blocks[-1]
+        A_last.expand_labels(A_last.dim_labels + [rb], tuple(A_last.shape) + (new_bond,))
+        A_new.connect(A_last, rb)
+        A_new.squeeze()
+        self.train_blocks.append(A_new)
+        C_last.expand_labels(C_last.dim_labels + [cb], tuple(C_last.shape) + (CB,))
+        C_last.connect(C_new, cb)
+        C_new.squeeze()
+        self.conv_blocks.append(C_new)
+        self.num_carriages = n + 1
+
+        from .conv import ConvTrainNetwork
+        old = self.tensor_network
+        self.tensor_network = ConvTrainNetwork(self.x_nodes, self.train_blocks, old.train_nodes + [C_new, A_new], output_labels=self.labels)
+        for attr in ("chunk_rows", "dense_chunk_bytes", "process_group", "shard_offset", "shard_total", "gram_mode", "solve_mode"):
+            setattr(self.tensor_network, attr, getattr(old, attr))

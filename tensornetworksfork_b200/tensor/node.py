@@ -103,6 +103,17 @@ class TensorNode:
         self.dim_labels = list(labels)
         return self
 
+    def expand_labels(self, labels, size):
+        """Append the missing labels as new trailing legs and broadcast the listed legs to ``size`` (a stride-0 view, as in
+        the reference, node.py:243-253; the first update of the node replaces it by a dense tensor)."""
+        labels = list(labels)
+        for lab in labels:
+            if lab not in self.dim_labels:
+                self.tensor = self.tensor.unsqueeze(-1)
+                self.dim_labels = self.dim_labels + [lab]
+        self.tensor = self.tensor.expand(*[size[labels.index(lab)] if lab in labels else -1 for lab in self.dim_labels])
+        return self
+
     def permute_first(self, *labels, expand=True):
         rest = [lab for lab in self.dim_labels if lab not in labels]
         order = [lab for lab in list(labels) + rest if expand or lab in self.dim_labels]

@@ -96,3 +96,67 @@ def run_case(name, device, scipy_object=True, chunk_rows=None, loss_prefix=None)
     loss_err = float(np.max(le[:loss_prefix] if loss_prefix else le))
     pred_err = gu.relerr(layer(X).cpu().numpy(), fx["pred1"])
     return fwd_err, core_err, loss_err, pred_err
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# growing flow (grow_cart): tests/golden/make_golden_conv_grow.py
+GROW_CTOR = dict(num_carriages=2, bond_dim=3, num_patches=5, patch_pixels=4, output_shape=2, convolution_bond=2)
+GROW_PHASES = [
+    dict(grow=None, kw=dict(batch_size=-1, num_swipes=1, lr=1.0, method="ridge_exact", eps=[1.0, 0.5])),
+    dict(grow=(3, 2), kw=dict(batch_size=-1, num_swipes=1, lr=1.0, method="ridge_exact", eps=[0.8, 0.4], direction="r2l")),
+    dict(grow=(None, None), kw=dict(batch_size=48, num_swipes=1, lr=1.0, method="ridge_cholesky", eps=0.6, eps_decay=0.5)),
+]
+
+
+def load_grow():
+    return np.load(os.path.join(gu.GOLDEN_DIR, "conv_grow.npz"), allow_pickle=False)
+
+
+def run_grow(device):
+    """The three phases of the recording on one layer; per phase (forward error after the growth, max relative core error over
+    all updates, max loss error, final prediction error).  After each growth the cores the growth touched (broadcast old last
+    cores, constant new patch core) must agree with the reference's; the freshly drawn pixel core is taken from the recording
+    (its draw depends on the RNG state; test_grow_cart_reproduces_reference_cores_bit_for_bit covers the draw itself)."""
+    z = load_grow()
+    X = torch.tensor(z["x"], device=device)
+    y = torch.tensor(z["y"], device=device)
+    layer = tnb.TensorConvolutionTrainLayer(**GROW_CTOR)
+    out = []
+    for pi, ph in enumerate(GROW_PHASES):
+        pre = f"p{pi}_"
+        if ph["grow"] is not None:
+            layer.grow_cart(*ph["grow"])
+        tn = layer.tensor_network
+        names = [str(s) for s in z[pre + "names"]]
+        assert [n.name for n in tn.train_nodes] == names
+        fresh = names[-2] if ph["grow"] is not None else None          # the new pixel core (train-node order ..., C_new, A_new)
+        for i, n in enumerate(tn.train_nodes):
+            ref = z[pre + f"cores0_{i}"]
+            assert tuple(n.tensor.shape) == ref.shape, (n.name, tuple(n.tensor.shape), ref.shape)
+            if pi == 0 or n.name == fresh:
+                n.tensor = torch.tensor(ref, device=device)
+            elif ph["grow"] is not None and n.name in names[-4:]:
+                # cores touched by the growth: broadcast old last cores and the constant new patch core
+                assert gu.relerr(n.tensor.cpu().numpy(), ref) < 1e-7, n.name
+        if device != "cpu":
+            layer.cuda()
+        fwd_err = gu.relerr(layer(X).cpu().numpy(), z[pre + "pred0"])
+        ups, losses = [], []
+
+        def block_callback(NS, node, tn=tn, ups=ups):
+            ups.append((NS, tn.train_nodes.index(node), [n.tensor.cpu().numpy().copy() for n in tn.train_nodes]))
+
+        ok = tn.accumulating_swipe(X, y, tnb.XEAutogradBregman(w=1.0), block_callback=block_callback,
+                                   loss_callback=lambda NS, node, l, losses=losses: losses.append(float(l)), **ph["kw"])
+        assert ok
+        nu = int(z[pre + "n_updates"])
+        assert [(a, b) for a, b, _ in ups] == [tuple(int(v) for v in z[pre + f"u{ui}_scal"]) for ui in range(nu)]
+        core_err = 0.0
+        for ui, (_, _, cores) in enumerate(ups):
+            for i, c in enumerate(cores):
+                core_err = max(core_err, gu.relerr(c, z[pre + f"u{ui}_after_{i}"]))
+        ref_losses = z[pre + "losses"]
+        loss_err = float(np.max(np.abs(np.array(losses) - ref_losses) / np.maximum(1.0, np.abs(ref_losses))))
+        pred_err = gu.relerr(layer(X).cpu().numpy(), z[pre + "pred1"])
+        out.append((fwd_err, core_err, loss_err, pred_err))
+    return out

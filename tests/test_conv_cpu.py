@@ -67,6 +67,33 @@ def test_conv_dense_sweep_host_logic(name, chunk_bytes, monkeypatch):
     assert fwd < 1e-12 and core < 1e-8 and loss < 1e-10 and pred < 1e-8, (fwd, core, loss, pred)
 
 
+def test_grow_cart_reproduces_reference_cores_bit_for_bit():
+    """Same seed, same constructor, two growths (reference tensor/layers.py:892-947): names, label order, shapes and values of all
+    train nodes, including the random draw of the new pixel cores."""
+    import tensornetworksfork_b200 as tnb
+    z = cc.load_grow()
+    torch.manual_seed(33)
+    layer = tnb.TensorConvolutionTrainLayer(**cc.GROW_CTOR)
+    layer.grow_cart(3, 2)
+    layer.grow_cart()
+    tn = layer.tensor_network
+    assert [n.name for n in tn.train_nodes] == [str(s) for s in z["seed_names"]]
+    assert [n.name for n in tn.main_nodes] == ["A1", "A2", "A3", "A4"] and len(tn.input_nodes) == 4
+    assert layer.num_carriages == 4
+    for i, n in enumerate(tn.train_nodes):
+        ref = z[f"seed_core_{i}"]
+        assert tuple(n.tensor.shape) == ref.shape, n.name
+        assert np.array_equal(n.tensor.numpy(), ref), n.name
+
+
+def test_conv_growing_flow_host_logic(monkeypatch):
+    """Sweep, grow_cart, sweep 'r2l', grow_cart, minibatched sweep against the reference recording (call shape of
+    image_convolution_growing_MNIST.py:84-103) on the CPU stand-in kernels."""
+    fake_ops.install(monkeypatch)
+    for pi, (fwd, core, loss, pred) in enumerate(cc.run_grow("cpu")):
+        assert fwd < 1e-12 and core < 1e-8 and loss < 1e-10 and pred < 1e-8, (pi, fwd, core, loss, pred)
+
+
 def _conv_shard_worker(rank, world, port, name, out_dir):
     import os
     import sys

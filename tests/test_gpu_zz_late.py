@@ -1,0 +1,21 @@
+"""GPU parity tests of the host flows added after this round's GPU minutes were spent (needs a B200).
+
+They drive the same kernels, at the same kinds of shapes, as the files before them -- only the host flow is new -- and each has a
+twin on the CPU stand-in kernels (named in its docstring) that is green.  The file sorts last on purpose: these tests had not
+run on a B200 when they were committed, so under ``pytest -x`` they cannot hide a result of the measured ones.
+"""
+import pytest
+import torch
+
+import conv_cases as cc
+
+pytestmark = pytest.mark.gpu
+torch.set_default_dtype(torch.float64)
+
+
+def test_conv_growing_flow_gpu():
+    """grow_cart between dense sweeps (image_convolution_growing_MNIST.py:84-103) against the reference recording
+    tests/golden/conv_grow.npz; CPU twin: test_conv_cpu.py::test_conv_growing_flow_host_logic."""
+    for pi, (fwd, core, loss, pred) in enumerate(cc.run_grow("cuda")):
+        # after a growth the prediction starts from free-running cores: same bound as the final prediction of a sweep
+        assert fwd < (1e-12 if pi == 0 else 1e-7) and core < 1e-7 and loss < 1e-9 and pred < 1e-7, (pi, fwd, core, loss, pred)
