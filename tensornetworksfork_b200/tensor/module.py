@@ -127,7 +127,9 @@ class TensorTrainRegressor(BaseEstimator, RegressorMixin):
     def _with_bias(X):
         return torch.cat((X, torch.ones((X.shape[0], 1), dtype=torch.float64, device=X.device)), dim=1)
 
-    def fit(self, X, y, X_val=None, y_val=None, validation_split=0.1, split_train=True):
+    def _split(self, X, y, X_val, y_val, validation_split, split_train):
+        """Tensors with the bias column, the model (built on first use) and the train / validation split of the reference's
+        ``fit`` (tensor/module.py:186-229)."""
         X, y = self._with_bias(self._t(X)), self._t(y, col=True)
         if self._model is None:
             self.input_dim = X.shape[1]
@@ -137,25 +139,30 @@ class TensorTrainRegressor(BaseEstimator, RegressorMixin):
                 idx = np.arange(X.shape[0])
                 np.random.RandomState(self.seed).shuffle(idx)
                 cut = int(X.shape[0] * (1 - validation_split))
-                X_train, y_train, X_val, y_val = X[idx[:cut]], y[idx[:cut]], X[idx[cut:]], y[idx[cut:]]
-            else:
-                X_train, y_train, X_val, y_val = X, y, X, y
-        else:
-            X_val, y_val = self._t(X_val), self._t(y_val, col=True)
-            X_train, y_train = X, y
-            if X_val.shape[1] != X_train.shape[1]:
-                X_val = self._with_bias(X_val)
+                return X[idx[:cut]], y[idx[:cut]], X[idx[cut:]], y[idx[cut:]]
+            return X, y, X, y
+        X_val, y_val = self._t(X_val), self._t(y_val, col=True)
+        if X_val.shape[1] != X.shape[1]:
+            X_val = self._with_bias(X_val)
+        return X, y, X_val, y_val
+
+    def _validate(self, X_val, y_val, epoch):
+        """One trajectory entry: validation RMSE (and accuracy for several outputs), reference tensor/module.py:234-249."""
+        log = {"epoch": epoch}
+        pred = self._model.tensor_network.forward_batch(X_val, self.batch_size)
+        log["val_rmse"] = root_mean_squared_error_torch(pred, y_val)
+        if y_val.shape[1] > 1:
+            log["val_accuracy"] = (torch.argmax(pred, dim=1) == torch.argmax(y_val, dim=1)).float().mean().item()
+        if self.verbose > 0:
+            print(", ".join(f"{k}: {v:.4f}" if isinstance(v, float) else f"{k}: {v}" for k, v in log.items()))
+        self.trajectory.append(log)
+
+    def fit(self, X, y, X_val=None, y_val=None, validation_split=0.1, split_train=True):
+        X_train, y_train, X_val, y_val = self._split(X, y, X_val, y_val, validation_split, split_train)
         self.trajectory = []
 
         def convergence_criterion():
-            log = {"epoch": len(self.trajectory) + 1}
-            pred = self._model.tensor_network.forward_batch(X_val, self.batch_size)
-            log["val_rmse"] = root_mean_squared_error_torch(pred, y_val)
-            if y_val.shape[1] > 1:
-                log["val_accuracy"] = (torch.argmax(pred, dim=1) == torch.argmax(y_val, dim=1)).float().mean().item()
-            if self.verbose > 0:
-                print(", ".join(f"{k}: {v:.4f}" if isinstance(v, float) else f"{k}: {v}" for k, v in log.items()))
-            self.trajectory.append(log)
+            self._validate(X_val, y_val, len(self.trajectory) + 1)
             return False
 
         self._model.tensor_network.accumulating_swipe(
@@ -220,4 +227,79 @@ class TensorTrainRegressorEarlyStopping(TensorTrainRegressor):
         self._singular = not converged
         if best["best_state_dict"] is not None:
             self._model.load_node_states(best["best_state_dict"], set_value=True)
+        return self
+
+
+def mirrored_cycle(seq, one_cycle=False):
+    """first .. last .. second, first .. : the back-and-forth visiting order of the cores (reference tensor/module.py:290-306).
+    ``one_cycle`` stops after one forward pass and the way back without the last element."""
+    seq = list(seq)
+    if not seq:
+        return
+    if one_cycle:
+        yield from seq + seq[-2::-1]
+        return
+    pattern = seq + seq[-2:0:-1]
+    while True:
+        yield from pattern
+
+
+class TensorTrainBatchRegressor(TensorTrainRegressor):
+    """Stochastic variant: every minibatch of a shuffled epoch drives its own ``accumulating_swipe`` (reference
+    tensor/module.py:308-500; train_mnist_batch.py:54-73).  ``swipe_method``:
+
+    * ``'batch_unique'`` -- one core per minibatch, cores visited back and forth across minibatches;
+    * ``'batch_same'``   -- a full ``num_swipes`` sweep of all cores on every minibatch, validation after each;
+    * ``'batch_block'``  -- one core at a time, updated on every minibatch of the epoch in turn.
+
+    Each call binds a new batch, so the environments are rebuilt per call; the per-call work is one small Gram + solve."""
+
+    def __init__(self, *args, batch_size=1024, swipe_method="batch_unique", **kwargs):
+        super().__init__(*args, batch_size=batch_size, **kwargs)
+        self.swipe_method = swipe_method
+
+    def fit(self, X, y, X_val=None, y_val=None, validation_split=0.1, split_train=True):
+        X_train, y_train, X_val, y_val = self._split(X, y, X_val, y_val, validation_split, split_train)
+        if self.verbose > 0:
+            print("Number of parameters:", self._model.num_parameters())
+        tn = self._model.tensor_network
+        n_train = X_train.shape[0]
+        bs = self.batch_size
+        n_batches = (n_train + bs - 1) // bs
+        self.trajectory = []
+        epoch = [0]
+        counter = [0]
+
+        def end_of_epoch():
+            # validation only when the running minibatch count closes an epoch (reference :363-384)
+            if counter[0] % n_batches == 0:
+                epoch[0] += 1
+                self._validate(X_val, y_val, epoch[0])
+            return False
+
+        common = dict(batch_size=-1, lr=self.lr, eps=self.epss, orthonormalize=False, method=self.method, verbose=self.verbose,
+                      skip_second=False, direction="l2r", disable_tqdm=self.verbose < 3, eps_per_node=len(self.epss) == self.N)
+        rng = np.random.RandomState(self.seed)
+        for _ in range(self.num_swipes):
+            order = rng.permutation(n_train)
+            batches = [order[lo:lo + bs] for lo in range(0, n_train, bs)]
+            if self.swipe_method == "batch_unique":
+                cores = mirrored_cycle(tn.train_nodes, one_cycle=False)
+                for rows in batches:
+                    counter[0] += 1
+                    tn.accumulating_swipe(X_train[rows], y_train[rows], self.bf, node_order=[next(cores)], num_swipes=1,
+                                          convergence_criterion=end_of_epoch, **common)
+            elif self.swipe_method == "batch_same":
+                for rows in batches:
+                    counter[0] += 1
+                    tn.accumulating_swipe(X_train[rows], y_train[rows], self.bf, num_swipes=self.num_swipes, **common)
+                    epoch[0] += 1
+                    self._validate(X_val, y_val, epoch[0])
+            elif self.swipe_method == "batch_block":
+                for core in mirrored_cycle(tn.train_nodes, one_cycle=True):
+                    for rows in batches:
+                        counter[0] += 1
+                        tn.accumulating_swipe(X_train[rows], y_train[rows], self.bf, node_order=[core], num_swipes=1,
+                                              convergence_criterion=end_of_epoch, **common)
+            # any other value: the reference's loop does nothing either
         return self

@@ -19,3 +19,12 @@ def test_conv_growing_flow_gpu():
     for pi, (fwd, core, loss, pred) in enumerate(cc.run_grow("cuda")):
         # after a growth the prediction starts from free-running cores: same bound as the final prediction of a sweep
         assert fwd < (1e-12 if pi == 0 else 1e-7) and core < 1e-7 and loss < 1e-9 and pred < 1e-7, (pi, fwd, core, loss, pred)
+
+
+@pytest.mark.parametrize("tag", ["unique", "same", "block"])
+def test_minibatch_estimator_gpu(tag):
+    """TensorTrainBatchRegressor (reference tensor/module.py:308-500) against tests/golden/batch_tt.npz; CPU twin:
+    test_growing_cpu.py::test_minibatch_estimator_swipe_methods (errors there: 1e-16 trajectory, 3e-14 cores)."""
+    import batch_case as bc
+    traj_err, pred_err, core_err = bc.run(tag, "cuda")
+    assert traj_err < 1e-8 and pred_err < 1e-7 and core_err < 1e-6, (traj_err, pred_err, core_err)
