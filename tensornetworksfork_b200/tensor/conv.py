@@ -28,6 +28,8 @@ from .network import TensorNetwork
 
 
 class ConvTrainNetwork(TensorNetwork):
+    _supports_gradient = False
+
     def __init__(self, input_nodes, main_nodes, train_nodes=None, output_labels=("s",), sample_dim="s"):
         super().__init__(input_nodes, main_nodes, train_nodes, output_labels=output_labels, sample_dim=sample_dim)
         self.chunk_rows = 16384         # rows processed at a time (bounds the per-chunk temporaries)

@@ -15,6 +15,8 @@ from .network import TensorNetwork, MappedInput
 
 
 class CPDNetwork(TensorNetwork):
+    _supports_gradient = False
+
     def __init__(self, *args, **kwargs):
         super().__init__(*args, **kwargs)
         self._Z = {}

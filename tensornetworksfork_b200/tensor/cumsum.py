@@ -22,6 +22,8 @@ from .network import TensorNetwork, MappedInput, batch_mean_of_means
 
 
 class CumSumNetwork(TensorNetwork):
+    _supports_gradient = False
+
     def _plan(self):
         sites = super()._plan()
         for s in sites:

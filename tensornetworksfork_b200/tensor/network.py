@@ -129,6 +129,8 @@ def batch_mean_of_means(loss_rows, batch_size, row_offset=0, n_total=None, group
 
 
 class TensorNetwork:
+    _supports_gradient = True       # method='gradient' (per-minibatch first-order steps); engines with their own update say False
+
     def __init__(self, input_nodes, main_nodes, train_nodes=None, output_labels=("s",), sample_dim="s"):
         self.input_nodes = input_nodes
         self.main_nodes = main_nodes
@@ -485,11 +487,12 @@ class TensorNetwork:
         return s.node.dim_size(s.cls)
 
     # ------------------------------------------------------------------ local system of one site
-    def _site_problem(self, k, y, loss_fn):
+    def _site_problem(self, k, y, loss_fn, rows=None):
         """Prediction, loss terms and the three Kronecker factors of site k's Jacobian.
 
         Returns dict with: yhat (S,C), loss (S[,C]), gram factors + weights + rows, rhs factors + weights,
         m_pos (sizes of the three parameter positions in canonical (a,c,p,b) order, merged to three).
+        ``rows = (lo, hi)`` restricts the problem to that range of the bound rows (one minibatch of ``method='gradient'``).
         """
         _, facs, S, dev = self._data
         G = self._canon(k)
@@ -499,6 +502,15 @@ class TensorNetwork:
         owner = self._owner()
         C = self._num_outputs()
         xk = facs[k]
+        yoff = getattr(self, "_yhat_offset", None)
+        if rows is not None:
+            lo, hi = rows
+            L = None if L is None else L[lo:hi]
+            R = None if R is None else R[lo:hi]
+            xk = Factor(xk.tensor[lo:hi], m=xk.m, div=xk.div, map_kind=xk.map_kind, col=xk.col)
+            y = y[lo:hi]
+            yoff = None if yoff is None else yoff[lo:hi]
+            S = hi - lo
         if self.gram_mode != "fp64" and xk.map_kind != ops.MAP_IDENTITY:
             # tensor-core Gram: evaluate the feature map once per site (S x f) so the kernel stays on its fast path
             phi = ops.env_update(None, xk, torch.eye(f, dtype=torch.float64, device=dev).reshape(1, f, f), S)
@@ -530,8 +542,8 @@ class TensorNetwork:
                 ops.predict(Lf, xk, G[:, c].contiguous(), Rf, S, dot_div=1 if R is not None else (1 << 30), out=yT[c])
             yhat = yT.t().contiguous()
 
-        if getattr(self, "_yhat_offset", None) is not None:
-            yhat = yhat + self._yhat_offset          # outputs of the other members of a SumOfNetworks (held fixed)
+        if yoff is not None:
+            yhat = yhat + yoff                       # outputs of the other members of a SumOfNetworks (held fixed)
         out_labels = [l for l in self.output_labels if l != self.sample_dim]
         y_in = yhat if out_labels else yhat[:, 0]
         loss, g, U, lam = hessian_terms(loss_fn, y_in, y)
@@ -881,8 +893,77 @@ class TensorNetwork:
                                    n_total=self.shard_total if self.process_group is not None else S,
                                    group=self.process_group)
 
+    def _gradient_update(self, k, y, loss_fn, lr, batch_size, adaptive_step, max_norm, need_loss):
+        """``method='gradient'`` (reference network.py:458-470): minibatch by minibatch, theta += lr * J^T g with the prediction,
+        g and J of that minibatch at the CURRENT theta -- the sign is the reference's (ascent for lr > 0).  The environments do
+        not depend on the core being updated, so they are built once; per minibatch this is one prediction and one
+        right-hand-side pass over its rows.  Under sharding the minibatches are ranges of global rows and each rank adds the
+        part it owns."""
+        self._check_external()
+        node = self.main_nodes[k]
+        S = self._data[2]
+        dev = self._data[3]
+        group = self.process_group
+        N = self.shard_total if group is not None else S
+        bs = N if batch_size <= 0 else batch_size
+        nb = (N + bs - 1) // bs
+        P = node.tensor.numel()
+        total = 0.0
+        for bi in range(nb):
+            lo = max(bi * bs, self.shard_offset) - self.shard_offset
+            hi = min(min((bi + 1) * bs, N), self.shard_offset + S) - self.shard_offset
+            buf = torch.zeros((P + 2,), dtype=torch.float64, device=dev)       # [b | sum of row losses | rows]
+            if hi > lo:
+                prob = self._site_problem(k, y, loss_fn, rows=(lo, hi))
+                rf = prob["rhs"]
+                ops.rhs(rf[0], rf[1], rf[2], prob["rw"], prob["rrows"], b=buf[:P])
+                rl = prob["loss"].reshape(hi - lo, -1).mean(dim=1)
+                buf[P] = rl.sum()
+                buf[P + 1] = float(hi - lo)
+            if group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(buf, group=group)
+            step = self._from_canon(k, buf[:P].reshape(self._canon(k).shape))
+            new = node.tensor.detach().clone().contiguous()
+            ops.update_node(new.view(-1), step.contiguous().view(-1), lr=lr, adaptive_step=adaptive_step, max_norm=max_norm)
+            node.tensor = new
+            self._core_changed(k)
+            if need_loss:
+                total += float((buf[P] / buf[P + 1]).item())
+        return torch.tensor(total / nb, dtype=torch.float64) if need_loss else None
+
+    def _gradient_full_update(self, k, y, loss_fn, lr, batch_size, adaptive_step, max_norm, need_loss):
+        """``method='gradient'`` in the second (returning) half of a sweep: the reference has no per-minibatch branch there
+        (network.py:558-584), so b is accumulated over all minibatches at fixed theta and the step is the ``-b`` of
+        ``solve_system`` (:321-322) -- one full-batch step, of the opposite sign to the first half's.  A is not needed."""
+        self._check_external()
+        prob = self._site_problem(k, y, loss_fn)
+        rf = prob["rhs"]
+        b = ops.rhs(rf[0], rf[1], rf[2], prob["rw"], prob["rrows"])
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(b, group=self.process_group)
+        step = self._from_canon(k, (-b).reshape(self._canon(k).shape))
+        node = self.main_nodes[k]
+        new = node.tensor.detach().clone().contiguous()
+        ops.update_node(new.view(-1), step.contiguous().view(-1), lr=lr, adaptive_step=adaptive_step, max_norm=max_norm)
+        node.tensor = new
+        self._core_changed(k)
+        if not need_loss:
+            return None
+        S = prob["yhat"].shape[0]
+        return batch_mean_of_means(prob["loss"], batch_size, row_offset=self.shard_offset,
+                                   n_total=self.shard_total if self.process_group is not None else S, group=self.process_group)
+
     def _update_node(self, node, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss):
         kl = self._linear_site(node)
+        if method.lower().startswith("gradient"):
+            if kl is not None:
+                raise NotImplementedError("method='gradient' on a linear-projection node")
+            k = self.main_nodes.index(node)
+            if method.lower() == "gradient@batch":
+                return self._gradient_update(k, y, loss_fn, lr, batch_size, adaptive_step, max_norm, need_loss)
+            return self._gradient_full_update(k, y, loss_fn, lr, batch_size, adaptive_step, max_norm, need_loss)
         if kl is not None:
             return self._one_linear_update(kl, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss)
         return self._one_update(self.main_nodes.index(node), y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm,
@@ -899,13 +980,14 @@ class TensorNetwork:
         Differences that do not change results: A and b of a node are built from the whole data set in
         one pass (they are sums over minibatches at fixed cores); ``batch_size`` only shapes the
         reported mean-of-batch-means loss.  ``update_or_reset_stack`` is accepted; environments are
-        always kept incrementally.  ``method='gradient'`` (per-batch ascent quirk, network.py:469-470)
-        is not provided.
+        always kept incrementally.  ``method='gradient'`` walks the minibatches one by one in the first half of a sweep
+        (theta += lr * J^T g per minibatch, network.py:458-470) and takes one full-batch step theta -= lr * b in the second
+        (:558-584, :321-322), see ``_gradient_update`` / ``_gradient_full_update``.
         """
         if blocks_input:
             raise NotImplementedError("blocks_input (compressed-data experiment) is outside the sweep path")
-        if method == "gradient":
-            raise NotImplementedError("method='gradient' is not part of the B200 path")
+        if method == "gradient" and not self._supports_gradient:
+            raise NotImplementedError(f"method='gradient' is provided for tensor-train cores only, not for {type(self).__name__}")
         x, y = self._prepare_data(x, y_true, data_device, model_device)
         # node lists of the two half-sweeps, exactly as network.py:418-425,520-527 derive them
         if node_order is None:
@@ -928,6 +1010,8 @@ class TensorNetwork:
                 print(f"Timeout reached ({timeout} seconds). Stopping accumulating_swipe.")
                 return False
             _method = "exact" if (eps_ == 0 and method == "ridge_exact") else method
+            if method == "gradient" and half == 0:
+                _method = "gradient@batch"      # per-minibatch steps exist in the first half only (network.py:469-470 vs :558-584)
             try:
                 loss = self._update_node(node, y, loss_fn, _method, eps_, lr, batch_size, adaptive_step, max_norm, need_loss)
             except torch.linalg.LinAlgError:
@@ -1207,6 +1291,8 @@ class SumOfNetworks(TensorNetwork):
         net.process_group, net.shard_offset, net.shard_total = self.process_group, self.shard_offset, self.shard_total
         net.gram_mode = self.gram_mode
         net._yhat_offset = offset
+        if method.lower().startswith("gradient") and not net._supports_gradient:
+            raise NotImplementedError(f"method='gradient' is provided for tensor-train cores only, not for {type(net).__name__}")
         try:
             return net._update_node(node, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss)
         finally:

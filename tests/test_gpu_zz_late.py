@@ -28,3 +28,12 @@ def test_minibatch_estimator_gpu(tag):
     import batch_case as bc
     traj_err, pred_err, core_err = bc.run(tag, "cuda")
     assert traj_err < 1e-8 and pred_err < 1e-7 and core_err < 1e-6, (traj_err, pred_err, core_err)
+
+
+@pytest.mark.parametrize("name", ["grad_tt_reg", "grad_tt_xe", "grad_type1"])
+def test_gradient_method_gpu(name):
+    """accumulating_swipe(method='gradient') (reference network.py:458-470, :558-584) against tests/golden/grad_*.npz: row-range
+    right-hand sides per minibatch; CPU twin: test_host_sweep_cpu.py::test_gradient_method_matches_reference_recording."""
+    import gradient_case as gcase
+    core_err, loss_err = gcase.run(name, "cuda")
+    assert core_err < 1e-10 and loss_err < 1e-10, (core_err, loss_err)

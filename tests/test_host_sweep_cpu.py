@@ -118,3 +118,48 @@ def test_sample_sharded_sweep_world2_gloo(name, tmp_path):
     last = fx["updates"][-1]["after"]
     for i in range(nc):
         assert gu.relerr(r0[f"core{i}"], last[i]) < 1e-6
+
+
+@pytest.mark.parametrize("name", ["grad_tt_reg", "grad_tt_xe", "grad_type1"])
+def test_gradient_method_matches_reference_recording(name, monkeypatch):
+    """method='gradient' (reference network.py:458-470): per-minibatch first-order steps at the current core, with the step
+    control of update_node; regression with a short last minibatch, class leg + cross-entropy, and a type-I sum."""
+    import gradient_case as gcase
+    fake_ops.install(monkeypatch)
+    core_err, loss_err = gcase.run(name, "cpu")
+    assert core_err < 1e-12 and loss_err < 1e-12, (core_err, loss_err)
+
+
+def test_gradient_method_refused_where_not_built(monkeypatch):
+    fake_ops.install(monkeypatch)
+    layer = tnb.CPDLayer(3, 4, 5, output_shape=(1,), seed=1)
+    X, y = torch.rand(20, 5), torch.rand(20, 1)
+    with pytest.raises(NotImplementedError):
+        layer.tensor_network.accumulating_swipe(X, y, tnb.SquareBregFunction(), method="gradient")
+
+
+def _gradient_shard_worker(rank, world, port, name, out_dir):
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.set_default_dtype(torch.float64)
+    torch.set_num_threads(1)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fake_ops as fo
+    import gradient_case as gcase
+    fo.install()
+    N = gu.load_krylov(name)["y"].shape[0]
+    cut = [0, N // 2 + 7, N][rank:rank + 2]          # uneven shards: the minibatch [128, 192) straddles the cut at 132
+    core_err, loss_err = gcase.run(name, "cpu", group=dist.group.WORLD, shard=(cut[0], cut[1]))
+    np.savez(os.path.join(out_dir, f"rank{rank}.npz"), core_err=core_err, loss_err=loss_err)
+    dist.destroy_process_group()
+
+
+def test_gradient_method_sample_sharded_world2_gloo(tmp_path):
+    """Minibatches are ranges of global rows; each rank adds the part of a minibatch it owns (one all-reduce of [b | loss | rows] per
+    minibatch) and every rank must follow the single-process recording."""
+    port = _free_port()
+    mp.spawn(_gradient_shard_worker, args=(2, port, "grad_tt_reg", str(tmp_path)), nprocs=2, join=True)
+    for r in (0, 1):
+        z = np.load(tmp_path / f"rank{r}.npz")
+        assert float(z["core_err"]) < 1e-12 and float(z["loss_err"]) < 1e-12, (r, float(z["core_err"]), float(z["loss_err"]))
