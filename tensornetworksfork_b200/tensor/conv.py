@@ -51,9 +51,7 @@ class ConvTrainNetwork(TensorNetwork):
             xn = A.connections["patches"]
             if "patch_pixels" not in xn.connections:
                 raise NotImplementedError(f"{xn.name}: input node without a pixel core")
-            Cn = xn.connections["patch_pixels"]
-            if Cn.tensor.dim() == 1:
-                raise NotImplementedError("convolution_bond <= 0 (pixel vector) is not part of the B200 path")
+            Cn = xn.connections["patch_pixels"]        # a plain pixel vector (one column, or convolution_bond <= 0) is a core with bonds 1
             cols.append((A, Cn))
         out_labels = [l for l in self.output_labels if l != self.sample_dim]
         owners = [k for k, (A, _) in enumerate(cols) if any(l in out_labels for l in A.dim_labels)]
@@ -145,6 +143,14 @@ class ConvTrainNetwork(TensorNetwork):
 
     def _check_external(self):
         pass    # every cached quantity carries the stamps of the cores it was built from
+
+    def _stamp(self):
+        return self._stamp_nodes(self.train_nodes)
+
+    def _with_offset(self, yhat, lo, hi):
+        """Add the outputs of the other members of a SumOfNetworks (held fixed while a node of this member is updated)."""
+        off = getattr(self, "_yhat_offset", None)
+        return yhat if off is None else yhat + off[lo:hi]
 
     def _require_cuda(self, dev):
         if dev.type != "cuda":
@@ -381,6 +387,10 @@ class ConvTrainNetwork(TensorNetwork):
             return ops.bmm(Et, YR).view(s * C, r * m)
         T = xc.shape[2]
         core_A = A4[:, 0]                                                          # (r, Q, r')
+        if k == 0 and Rn is None:
+            # a single column: J[s, c, t] = sum_q A[c, q] x[s, q, t], one tall-skinny product with the core as the shared matrix
+            Jt = ops.rows_dot(xc.transpose(1, 2).contiguous().view(s * T, Q), A4[0, :, :, 0].contiguous())     # (s*T, c)
+            return Jt.view(s, T, c).permute(0, 2, 1).contiguous().view(s * C, T)
         if k == 0:
             K = ops.rows_dot(Rn.view(s * a2, r2), A4[0].reshape(c * Q, r2))
             K = K.view(s, a2, c, Q).permute(0, 2, 1, 3).contiguous().view(s, c * a2, Q)          # (s, (c,b), q), a = 1
@@ -403,7 +413,7 @@ class ConvTrainNetwork(TensorNetwork):
         losses = []
         for ci, (lo, hi) in enumerate(self._chunks(S)):
             xc = xb[lo:hi]
-            yhat = self._predict_chunk(xc, ci)
+            yhat = self._with_offset(self._predict_chunk(xc, ci), lo, hi)
             loss, g, U, lam = self._loss_terms(yhat, y[lo:hi], loss_fn)
             rhs_fn, jv_fn, jt_fn = self._node_chunk(kind, k, xc, ci)
             bc = rhs_fn(g)
@@ -454,7 +464,7 @@ class ConvTrainNetwork(TensorNetwork):
                 xc = xb[lo:hi]
                 s = hi - lo
                 tag = ("dense", ci)
-                yhat = self._predict_chunk(xc, tag)
+                yhat = self._with_offset(self._predict_chunk(xc, tag), lo, hi)
                 loss, g, U, lam = self._loss_terms(yhat, y[lo:hi], loss_fn)
                 J = self._jacobian_chunk(kind, k, xc, tag).view(s, C, P)
                 F, Gr = ops.class_rows(J, U, g)                      # virtual rows F (s*V, P), G (s, P) = sum_c g J

@@ -473,16 +473,17 @@ class TensorConvolutionTrainLayer(TensorNetworkLayer):
         Q, T = self.num_patches, self.patch_pixels
         new_bond = self.bond_dim if new_bond is None else new_bond
         CB = self.convolution_bond if new_convolution_bond is None else new_convolution_bond
-        if CB <= 0:
-            raise NotImplementedError("convolution_bond <= 0 (pixel vector) is not part of the B200 path")
         rb, cb = f"r{n + 1}", f"CB{n + 1}"
         x_new = TensorNode((1, Q, T), ["s", "patches", "patch_pixels"], name=f"X{n + 1}")
         core = torch.zeros((new_bond, 1, Q, 1))
         core[:, :, -1] = 1.0 / new_bond
         A_new = TensorNode(core, [rb, f"c{n + 1}", "patches", f"r{n + 2}"], l=rb, r=f"r{n + 2}", name=f"A{n + 1}")
         x_new.connect(A_new, "patches")
-        # the new last pixel core has no right bond (the reference's size expression reduces to this)
-        C_new = TensorNode((CB if n != 1 else 1, T, 1), [cb, "patch_pixels", f"CB{n + 2}"], l=cb, r=f"CB{n + 2}", name=f"C{n + 1}")
+        if CB > 0:
+            # the new last pixel core has no right bond (the reference's size expression reduces to this)
+            C_new = TensorNode((CB if n != 1 else 1, T, 1), [cb, "patch_pixels", f"CB{n + 2}"], l=cb, r=f"CB{n + 2}", name=f"C{n + 1}")
+        else:
+            C_new = TensorNode((T,), ["patch_pixels"], name=f"C{n + 1}")
         x_new.connect(C_new, "patch_pixels")
         self.x_nodes.append(x_new)
 
@@ -491,8 +492,9 @@ class TensorConvolutionTrainLayer(TensorNetworkLayer):
         A_new.connect(A_last, rb)
         A_new.squeeze()
         self.train_blocks.append(A_new)
-        C_last.expand_labels(C_last.dim_labels + [cb], tuple(C_last.shape) + (CB,))
-        C_last.connect(C_new, cb)
+        if CB > 0:
+            C_last.expand_labels(C_last.dim_labels + [cb], tuple(C_last.shape) + (CB,))
+            C_last.connect(C_new, cb)
         C_new.squeeze()
         self.conv_blocks.append(C_new)
         self.num_carriages = n + 1

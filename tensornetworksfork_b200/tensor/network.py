@@ -1220,19 +1220,6 @@ class SumOfNetworks(TensorNetwork):
                 return j, net
         raise ValueError("Node not found in any network")
 
-    @staticmethod
-    def _slice_for(net, x):
-        """Leading feature columns each member sees (reference network.py:1012)."""
-        def cut(t, node):
-            f = node.tensor.shape[1] if node.tensor.dim() > 1 else t.shape[1]
-            return t if t.shape[1] == f else t[:, :f]
-        if isinstance(x, (list, tuple)):
-            raise NotImplementedError("SumOfNetworks takes one matrix shared by all members")
-        feats = {n.tensor.shape[1] for n in net.input_nodes}
-        if len(feats) != 1:
-            raise NotImplementedError("members whose inputs differ in width")
-        return cut(x, net.input_nodes[0])
-
     def _member_width(self, net):
         s = net._plan()[0] if not hasattr(net, "_rank") else None
         if s is not None:
@@ -1242,6 +1229,13 @@ class SumOfNetworks(TensorNetwork):
         return net._plan()[0].dim_size("p")
 
     def _member_input(self, net, x):
+        if hasattr(net, "_columns"):
+            # conv-TT member (AAMNST.py:160-168): members after the first see x[:, :patches-1, :pixels-1], i.e. the leading part
+            # of every non-sample axis up to the size its input nodes were built with (reference network.py:1012)
+            want = tuple(net.input_nodes[0].tensor.shape[1:])
+            if x.dim() != 1 + len(want) or any(w > h for w, h in zip(want, x.shape[1:])):
+                raise ValueError(f"input of shape {tuple(x.shape)} cannot feed a member built for {want} per sample")
+            return x if tuple(x.shape[1:]) == want else x[(slice(None),) + tuple(slice(0, w) for w in want)]
         f = self._member_width(net)
         return x if x.shape[1] == f else x[:, :f]
 
@@ -1250,7 +1244,10 @@ class SumOfNetworks(TensorNetwork):
         for net in self.networks:
             yj = net._chain_forward(self._member_input(net, x))
             y = yj if y is None else y + yj
-        out_labels = [l for l in self.output_labels if l != self.sample_dim]
+        # the members' output legs survive even when the sum itself was declared with ('s',) only (AAMNST.py:168 does that;
+        # the reference's forward only moves the listed labels to the front, network.py:1013-1015)
+        first = self.networks[0]
+        out_labels = [l for l in self.output_labels if l != self.sample_dim] or [l for l in first.output_labels if l != first.sample_dim]
         if not out_labels:
             y = y[:, 0]
         return y if to_tensor else TensorNode(y, [self.sample_dim] + out_labels, name="O")

@@ -29,7 +29,22 @@ CASES = {
     "conv_dense_reg": dict(kind="dense", ctor=dict(num_carriages=3, bond_dim=3, num_patches=6, patch_pixels=5, output_shape=1, convolution_bond=2),
                            loss=lambda: tnb.SquareBregFunction(), oloss="square",
                            kw=dict(batch_size=-1, num_swipes=2, lr=1.0, method="ridge_cholesky", eps=0.5, eps_decay=0.7)),
+    # type-I image model (AAMNST.py:157-168): sum of conv-TTs with 1..3 columns, members after the first without bias patch / pixel
+    "conv_type1": dict(kind="dense", builder=lambda: _conv_type1(), loss=lambda: tnb.XEAutogradBregman(w=1.0), oloss="xe",
+                       kw=dict(batch_size=50, num_swipes=1, lr=1.0, method="ridge_cholesky", eps=1.0, eps_decay=0.5)),
+    "conv_onecol": dict(kind="dense", ctor=dict(num_carriages=1, bond_dim=3, num_patches=5, patch_pixels=4, output_shape=2, convolution_bond=2),
+                        loss=lambda: tnb.SquareBregFunction(), oloss="square",
+                        kw=dict(batch_size=40, num_swipes=2, lr=1.0, method="ridge_cholesky", eps=0.5, eps_decay=0.5)),
+    "conv_nocb": dict(kind="dense", ctor=dict(num_carriages=3, bond_dim=3, num_patches=5, patch_pixels=4, output_shape=2, convolution_bond=-1),
+                      loss=lambda: tnb.XEAutogradBregman(w=1.0), oloss="xe",
+                      kw=dict(batch_size=-1, num_swipes=1, lr=1.0, method="ridge_exact", eps=0.8, eps_decay=0.5)),
 }
+
+
+def _conv_type1():
+    nets = [tnb.TensorConvolutionTrainLayer(num_carriages=i, bond_dim=3, num_patches=5 if i == 1 else 4, patch_pixels=4 if i == 1 else 3,
+                                            output_shape=2, convolution_bond=2).tensor_network for i in range(1, 4)]
+    return tnb.TensorNetworkLayer(tnb.SumOfNetworks(nets, train_operators=True))
 
 
 def load(name):
@@ -43,14 +58,15 @@ def load(name):
 def build(name, device, chunk_rows=None):
     case = CASES[name]
     fx = load(name)
-    layer = tnb.TensorConvolutionTrainLayer(**case["ctor"])
+    layer = case["builder"]() if "builder" in case else tnb.TensorConvolutionTrainLayer(**case["ctor"])
     tn = layer.tensor_network
     assert [n.name for n in tn.train_nodes] == fx["names"]
     for n, c in zip(tn.train_nodes, fx["cores0"]):
         assert tuple(n.tensor.shape) == c.shape, (n.name, n.tensor.shape, c.shape)
         n.tensor = torch.tensor(c, device=device)
     if chunk_rows is not None:
-        tn.chunk_rows = chunk_rows
+        for net in getattr(tn, "networks", [tn]):
+            net.chunk_rows = chunk_rows
     return case, fx, layer
 
 

@@ -55,6 +55,16 @@ def test_conv_device_krylov_solvers_track_the_float32_reference(name, monkeypatc
     assert loss < 2e-2, (core, loss)
 
 
+@pytest.mark.parametrize("name", ["conv_type1", "conv_onecol", "conv_nocb"])
+@pytest.mark.parametrize("chunk", [None, 37])
+def test_conv_type1_and_degenerate_columns_host_logic(name, chunk, monkeypatch):
+    """Type-I image model (sum of conv-TTs with 1..3 columns, AAMNST.py:157-203), a single column on its own, and
+    convolution_bond = -1 (pixel vectors), each against its reference recording under the dense sweep."""
+    fake_ops.install(monkeypatch)
+    fwd, core, loss, pred = cc.run_case(name, "cpu", chunk_rows=chunk)
+    assert fwd < 1e-12 and core < 1e-8 and loss < 1e-10 and pred < 1e-8, (fwd, core, loss, pred)
+
+
 @pytest.mark.parametrize("name", ["conv_dense_xe", "conv_dense_reg"])
 @pytest.mark.parametrize("chunk_bytes", [1 << 30, 20000])
 def test_conv_dense_sweep_host_logic(name, chunk_bytes, monkeypatch):

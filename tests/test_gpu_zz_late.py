@@ -37,3 +37,11 @@ def test_gradient_method_gpu(name):
     import gradient_case as gcase
     core_err, loss_err = gcase.run(name, "cuda")
     assert core_err < 1e-10 and loss_err < 1e-10, (core_err, loss_err)
+
+
+@pytest.mark.parametrize("name", ["conv_type1", "conv_onecol", "conv_nocb"])
+def test_conv_type1_and_degenerate_columns_gpu(name):
+    """Type-I image model (sum of conv-TTs with 1..3 columns, AAMNST.py:157-203), a single column, convolution_bond = -1, against
+    their reference recordings; CPU twin: test_conv_cpu.py::test_conv_type1_and_degenerate_columns_host_logic."""
+    fwd, core, loss, pred = cc.run_case(name, "cuda")
+    assert fwd < 1e-12 and core < 1e-7 and loss < 1e-9 and pred < 1e-7, (fwd, core, loss, pred)
