@@ -87,9 +87,10 @@ class CumSumNetwork(TensorNetwork):
             self._right[i] = env
         return env
 
-    def _predict_at(self, k, L, R, fac, S):
-        """yhat[s] = sum_p x_p sum_{a,b} Lc[s,p,a] G_k[a,p,b] Rc[s,p,b]."""
-        G = self._canon(k)
+    def _predict_at(self, k, L, R, fac, S, G=None):
+        """yhat[s] = sum_p x_p sum_{a,b} Lc[s,p,a] G_k[a,p,b] Rc[s,p,b]; ``G`` (rl, 1, f, rr) stands in for core k (the J v pass
+        of the matrix-free sweeps: the prediction is linear in the core)."""
+        G = self._canon(k) if G is None else G
         rl, _, f, rr = G.shape
         dev = G.device
         one = torch.ones((1, 1), dtype=torch.float64, device=dev)
@@ -164,10 +165,43 @@ class CumSumNetwork(TensorNetwork):
 
     node_orthonormalize_right = node_orthonormalize_left
 
-    def lanczos_swipe(self, *a, **k):
-        raise NotImplementedError("matrix-free sweeps are not built for the cum-sum train")
+    def _krylov_problem(self, node, y, loss_fn):
+        """(per-row loss, b, matvec) of one core for ``lanczos_swipe`` / ``scipy_swipe`` (the reference runs them on the operator-node
+        graph, network.py:709-932).  J v is the prediction with v in place of the core, J^T u the table-driven right-hand-side
+        pass with row weights u; everything flat in canonical (a, p, b) order."""
+        k = self.main_nodes.index(node)
+        _, facs, S, dev = self._data
+        G = self._canon(k)
+        rl, _, f, rr = G.shape
+        L = self._get_left(k - 1)
+        R = self._get_right(k + 1)
+        yhat = self._predict_at(k, L, R, facs[k], S)
+        if getattr(self, "_yhat_offset", None) is not None:
+            yhat = yhat + self._yhat_offset
+        out_labels = [l for l in self.output_labels if l != self.sample_dim]
+        loss, g, U, lam = hessian_terms(loss_fn, yhat if out_labels else yhat[:, 0], y)
+        V = lam.shape[1]
+        w = (lam.reshape(S, V) * U.reshape(S, V) ** 2).sum(dim=1).contiguous()
+        one = ops.ones_factor(G)
+        f1 = one if L is None else Factor(L.reshape(S, f * rl), m=f * rl)
+        f3 = one if R is None else Factor(R.reshape(S, f * rr), m=f * rr)
+        t1, t2, t3 = self._tables(rl, f, rr, L is not None, R is not None, dev)
+        P = rl * f * rr
+        group = self.process_group
 
-    scipy_swipe = lanczos_swipe
+        def jt(u):
+            out = torch.empty((P,), dtype=torch.float64, device=dev)
+            ops.gram_generic(f1, facs[k], f3, t1, t2, t3, u.contiguous(), S, rhs_only=True, out=out)
+            if group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(out, group=group)
+            return out
+
+        def matvec(v):
+            jv = self._predict_at(k, L, R, facs[k], S, G=v.contiguous().view(rl, 1, f, rr))
+            return jt(w * jv.view(S))
+
+        return loss, jt(g.reshape(S)), matvec
 
 
 class _Theta:

@@ -14,6 +14,11 @@ CASES = {
                             kw=dict(batch_size=60, num_swipes=2, lr=1.0, max_iter=25, tol=1e-5)),
     "krylov_scipy_minres": dict(kind="scipy", solver="minres", n=4, r=3, f=4, C=1, loss=lambda: tnb.SquareBregFunction(),
                                 kw=dict(batch_size=60, num_swipes=2, lr=1.0, max_iter=25, tol=1e-5)),
+    # cum-sum train (CumSumLayer): J v = prediction with v in place of the core, J^T u = table-driven right-hand-side pass
+    "krylov_cumsum_lanczos": dict(kind="lanczos", cumsum=True, n=3, r=3, f=4, C=1, loss=lambda: tnb.SquareBregFunction(),
+                                  kw=dict(batch_size=60, num_swipes=2, lr=1.0, max_iter=6, tol=1e-12)),
+    "krylov_cumsum_cg": dict(kind="scipy", solver="cg", cumsum=True, n=4, r=2, f=4, C=1, loss=lambda: tnb.SquareBregFunction(),
+                             kw=dict(batch_size=-1, num_swipes=2, lr=1.0, max_iter=8, tol=1e-5)),
 }
 
 
@@ -21,8 +26,12 @@ def run_case(name, device, scipy_object=True):
     """Returns (max relative core error over all updates, max loss error) against the reference recording."""
     case = CASES[name]
     fx = gu.load_krylov(name)
-    layer = tnb.TensorTrainLayer(case["n"], case["r"], case["f"], output_shape=case["C"], constrict_bond=False, seed=0)
+    if case.get("cumsum"):
+        layer = tnb.CumSumLayer(case["n"], case["r"], case["f"], output_shape=case["C"], constrict_bond=False, perturb=False)
+    else:
+        layer = tnb.TensorTrainLayer(case["n"], case["r"], case["f"], output_shape=case["C"], constrict_bond=False, seed=0)
     tn = layer.tensor_network
+    assert [tuple(n.tensor.shape) for n in tn.train_nodes] == [c.shape for c in fx["cores0"]]
     for n, c in zip(tn.train_nodes, fx["cores0"]):
         n.tensor = torch.tensor(c, device=device)
     X = torch.tensor(fx["x"], device=device)

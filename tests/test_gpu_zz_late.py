@@ -45,3 +45,12 @@ def test_conv_type1_and_degenerate_columns_gpu(name):
     their reference recordings; CPU twin: test_conv_cpu.py::test_conv_type1_and_degenerate_columns_host_logic."""
     fwd, core, loss, pred = cc.run_case(name, "cuda")
     assert fwd < 1e-12 and core < 1e-7 and loss < 1e-9 and pred < 1e-7, (fwd, core, loss, pred)
+
+
+def test_cumsum_matrix_free_sweeps_gpu():
+    """lanczos_swipe / scipy_swipe on the cum-sum train against tests/golden/krylov_cumsum_*.npz; CPU twins in test_krylov_cpu.py."""
+    import krylov_cases as kc
+    core_err, loss_err = kc.run_case("krylov_cumsum_lanczos", "cuda")
+    assert core_err < 1e-7 and loss_err < 1e-8, (core_err, loss_err)
+    core_err, loss_err = kc.run_case("krylov_cumsum_cg", "cuda", scipy_object=True)
+    assert core_err < 5e-4 and loss_err < 5e-5, (core_err, loss_err)

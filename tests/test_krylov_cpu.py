@@ -30,3 +30,16 @@ def test_device_krylov_solvers_track_the_float32_reference(name, monkeypatch):
     fake_ops.install(monkeypatch)
     core_err, loss_err = kc.run_case(name, "cpu", scipy_object=False)
     assert loss_err < 5e-3, (core_err, loss_err)
+
+
+def test_cumsum_lanczos_swipe_with_injected_start_vector(monkeypatch):
+    """Matrix-free sweep of the cum-sum train (the reference runs lanczos_swipe on the operator-node graph of CumSumLayer)."""
+    fake_ops.install(monkeypatch)
+    core_err, loss_err = kc.run_case("krylov_cumsum_lanczos", "cpu")
+    assert core_err < 1e-8 and loss_err < 1e-9, (core_err, loss_err)
+
+
+def test_cumsum_scipy_swipe_float32_host_recurrences(monkeypatch):
+    fake_ops.install(monkeypatch)
+    core_err, loss_err = kc.run_case("krylov_cumsum_cg", "cpu", scipy_object=True)
+    assert core_err < 5e-4 and loss_err < 5e-5, (core_err, loss_err)
