@@ -655,10 +655,22 @@ class TensorNetwork:
                 A = ops.gram_expand(M, m_pos, role_of_pos, sigma, ridge, A=A)
                 rhs = rhs0
                 info = None
+        lu_methods = m in ("exact", "ridge_exact")
+        rhs_lu = None
         if info is None:
             self.solve_stats["fp64"] += 1
+            rhs_lu = rhs.clone() if lu_methods else None
             info = ops.cholesky_solve(A, rhs)
         bad = int(info.item())
+        if bad != 0 and lu_methods and rhs_lu is not None:
+            # 'exact' / 'ridge_exact' are LU solves in the reference (torch.linalg.solve, network.py:305-310), which also accept
+            # systems that are not numerically positive definite.  The Cholesky path is the fast one; when it reports a lost
+            # pivot the system is expanded again and handed to the LU solver of the library (rare, off the hot path).  An exactly
+            # singular matrix still raises LinAlgError there, as in the reference.
+            A = ops.gram_expand(M, m_pos, role_of_pos, sigma, ridge, A=A)
+            rhs = torch.linalg.solve(A[:, :P], rhs_lu)
+            self.solve_stats["lu_fallback"] = self.solve_stats.get("lu_fallback", 0) + 1
+            bad = 0
         if self.process_group is not None:
             # every rank solved the same all-reduced system, but the substitution / refinement kernels sum with atomics,
             # so the last bits may differ between ranks: rank 0's step is the one everybody applies (cores stay identical)
@@ -714,10 +726,16 @@ class TensorNetwork:
         Ap[:, :P] = A_f / scale
         Ap.diagonal().add_(ridge)
         rhs = -(b.reshape(P) / scale + ridge * node.tensor.reshape(P))
+        rhs_lu = rhs.clone() if m in ("exact", "ridge_exact") else None
         info = ops.cholesky_solve(Ap, rhs)
         if int(info.item()) != 0:
-            raise torch.linalg.LinAlgError("linalg.cholesky: The factorization could not be completed because the "
-                                           "input is not positive-definite")
+            if rhs_lu is None:
+                raise torch.linalg.LinAlgError("linalg.cholesky: The factorization could not be completed because the "
+                                               "input is not positive-definite")
+            # LU methods of the reference (network.py:305-310): library LU when the fast Cholesky path loses a pivot
+            A_lu = A_f / scale
+            A_lu.diagonal().add_(ridge)
+            rhs = torch.linalg.solve(A_lu, rhs_lu)
         return rhs.reshape(b.shape)
 
     # ------------------------------------------------------------------ QR re-gauge

@@ -59,3 +59,94 @@ def test_engine_runs_reference_built_graph(monkeypatch):
     states = layer2.node_states()                       # reference's checkpoint hooks still work on the new engine
     layer2.load_node_states(states, set_value=True)
     assert float((fast.forward_batch(X, 64) - ref_pred).norm() / ref_pred.norm()) < 1e-8
+
+
+def _pair(seed=7, n=4, r=3, F=3, C=1):
+    """The same model twice: the reference's layer with its own engine, and the mirrored layer on the stand-in kernels."""
+    ref_layers, ref_breg = _import_reference()
+    import tensornetworksfork_b200 as tnb
+    rng = np.random.default_rng(seed)
+    N = 150
+    X = torch.tensor(np.concatenate([rng.uniform(-1, 1, size=(N, F)), np.ones((N, 1))], 1))
+    y = torch.tensor(np.tanh(X[:, :C].numpy()) + 0.1 * rng.normal(size=(N, C)))
+    ref = ref_layers.TensorTrainLayer(n, r, F + 1, output_shape=C, constrict_bond=False, seed=seed)
+    mine = tnb.TensorTrainLayer(n, r, F + 1, output_shape=C, constrict_bond=False, seed=seed)
+    return ref, mine, X, y, ref_breg.SquareBregFunction(), tnb.SquareBregFunction()
+
+
+def _trace(tn, X, y, loss, **kw):
+    """(return value, [(callback kind, NS, node index)], final prediction) of one accumulating_swipe call."""
+    ev = []
+    idx = lambda node: tn.train_nodes.index(node)
+    ret = tn.accumulating_swipe(X, y, loss, loss_callback=lambda NS, nd, l: ev.append(("loss", NS, idx(nd), round(float(l), 9))),
+                                block_callback=lambda NS, nd: ev.append(("block", NS, idx(nd))), **kw)
+    return ret, ev, tn.forward(X, to_tensor=True)
+
+
+@pytest.mark.parametrize("kw", [
+    dict(num_swipes=0),
+    dict(num_swipes=2, skip_second=True, eps=[0.5, 0.25]),
+    dict(num_swipes=1, direction="r2l", eps=[0.5, 0.25]),
+    dict(num_swipes=1, node_order="middle_two"),
+    dict(num_swipes=1, node_order="tuple"),
+    dict(num_swipes=1, timeout=0.0),
+    dict(num_swipes=2, stop_after=3),
+    # becomes 'exact' (reference network.py:478-479): unregularised, nearly singular systems solved by LU in both engines, so only
+    # the control flow and the first losses are comparable
+    dict(num_swipes=1, method="ridge_exact", eps=0, loose=True),
+    dict(num_swipes=1, batch_size=1000),                       # larger than the data set: one batch
+    dict(num_swipes=1, batch_size=1, update_or_reset_stack="update"),
+], ids=lambda kw: ",".join(f"{k}={v}" for k, v in kw.items()))
+def test_sweep_control_flow_matches_live_reference(kw, monkeypatch):
+    """Return value, order and arguments of the callbacks, and the fitted function for the keyword combinations of SURVEY.md
+    Appendix D that steer the sweep rather than the arithmetic (side by side with the reference's own engine)."""
+    import fake_ops
+    fake_ops.install(monkeypatch)
+    ref, mine, X, y, ref_loss, my_loss = _pair()
+    outs = []
+    for layer, loss in ((ref, ref_loss), (mine, my_loss)):
+        tn = layer.tensor_network
+        k = dict(batch_size=40, lr=1.0, method="ridge_cholesky", eps=0.5)
+        k.update(kw)
+        order = k.pop("node_order", None)
+        if order == "middle_two":
+            k["node_order"] = tn.train_nodes[1:3]
+        elif order == "tuple":
+            k["node_order"] = (tn.train_nodes[:2], tn.train_nodes[2:])
+        loose = k.pop("loose", False)
+        stop = k.pop("stop_after", None)
+        if stop is not None:
+            calls = [0]
+
+            def crit(calls=calls, stop=stop):
+                calls[0] += 1
+                return calls[0] >= stop
+            k["convergence_criterion"] = crit
+        outs.append(_trace(tn, X, y, loss, **k))
+    (r_ret, r_ev, r_pred), (m_ret, m_ev, m_pred) = outs
+    assert m_ret == r_ret
+    assert [e[:3] for e in m_ev] == [e[:3] for e in r_ev]
+    for a, b in zip(m_ev, r_ev):
+        if a[0] == "loss":
+            assert abs(a[3] - b[3]) <= (1e-2 if loose else 1e-7) * max(1.0, abs(b[3])), (a, b)
+    if not loose:
+        assert float((m_pred - r_pred).norm() / r_pred.norm()) < 1e-7
+
+
+def test_unknown_method_raises_like_reference(monkeypatch):
+    import fake_ops
+    fake_ops.install(monkeypatch)
+    ref, mine, X, y, ref_loss, my_loss = _pair()
+    for layer, loss in ((ref, ref_loss), (mine, my_loss)):
+        with pytest.raises(ValueError):
+            layer.tensor_network.accumulating_swipe(X, y, loss, method="dogleg", eps=0.5)
+
+
+def test_singular_system_returns_false_like_reference(monkeypatch):
+    """A non-positive-definite local system (all-zero data, no ridge) ends the sweep with False (reference network.py:481-484)."""
+    import fake_ops
+    fake_ops.install(monkeypatch)
+    ref, mine, X, y, ref_loss, my_loss = _pair()
+    X0 = torch.zeros_like(X)
+    for layer, loss in ((ref, ref_loss), (mine, my_loss)):
+        assert layer.tensor_network.accumulating_swipe(X0, y, loss, method="cholesky", eps=0.0) is False

@@ -70,10 +70,20 @@ def test_teacher_forced_updates(name):
         losses = []
         method = meta["method"] if not (meta["method"] == "ridge_exact" and u["eps"] == 0) else "exact"
         if method == "exact":
-            # unregularised system, singular by gauge freedom: the reference's LU returns an arbitrary solution,
-            # this engine factorises by Cholesky and reports the system as singular (deviations)
-            with pytest.raises(torch.linalg.LinAlgError):
+            # unregularised system, singular by gauge freedom: the reference's LU returns an arbitrary solution of the consistent
+            # system.  Here the Cholesky loses a pivot and the engine falls back to the library LU (deviations): any
+            # solution with a residual like the reference's is right; an LU that hits an exact zero pivot may raise instead.
+            try:
                 tn._one_update(k, y, lf, method, u["eps"], meta["lr"], meta["batch_size"], False, None, True)
+            except torch.linalg.LinAlgError:
+                continue
+            step = (node.tensor.cpu().numpy() - u["before"][k]) / meta["lr"]
+            Aref = u["A"].reshape(P, P)
+            sc = np.abs(np.diag(Aref)).mean() or 1.0
+            rhs = u["b"].ravel() / sc
+            res = np.linalg.norm(Aref / sc @ step.ravel() + rhs) / max(np.linalg.norm(rhs), 1e-300)
+            res_ref = np.linalg.norm(Aref / sc @ u["step"].ravel() + rhs) / max(np.linalg.norm(rhs), 1e-300)
+            assert res <= max(100 * res_ref, 1e-9), (res, res_ref)
             continue
         shaped = meta.get("adaptive_step", False) or meta.get("max_norm") is not None
         got = tn._one_update(k, y, lf, method, u["eps"], meta["lr"], meta["batch_size"], meta.get("adaptive_step", False),
