@@ -601,7 +601,9 @@ def cpu_baseline(args, wl, rows_total):
     return {"value": value, "unit": "sample-site-updates/s", "site_updates_per_s": n / t_all_sites, "cores": os.cpu_count(), "kind": "port",
             "sample": f"oracle port (numpy/BLAS, all host threads): env + Jacobian + Gram + rhs of every site on one {rows}-row "
                       f"minibatch ({t_batch:.2f} s) plus the dense solves with P<=4096 ({t_solve:.2f} s; larger P not timed, "
-                      f"which favours the CPU); per-row cost extrapolated linearly to {rows_total} rows"}
+                      f"which favours the CPU); per-row cost extrapolated linearly to {rows_total} rows.  Calibration of the port "
+                      f"against the unmodified reference on one 8-core host (profiles/r1_reference_vs_port_cpu.json): 23-48x faster "
+                      f"than the reference verbatim (S x P x P einsum temporary), 1.1-2.8x slower than the reference with opt_einsum"}
 
 
 def bench_reference(args):

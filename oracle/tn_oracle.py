@@ -204,6 +204,20 @@ def gram(J, g, H):
     return A, b
 
 
+def _cholesky_solve(A_f, rhs):
+    """Cholesky factorisation + two TRIANGULAR substitutions (torch.linalg.cholesky + torch.cholesky_solve, network.py:313-315).
+    The factorisation stays in numpy's BLAS (the Gram GEMM just ran there; a second BLAS pool -- SciPy's or torch's -- would
+    fight it for the cores and cost 5-10x); the O(P^2) substitutions go through SciPy's dtrsv, with a general-solve fallback that
+    gives the same numbers.  Not positive definite -> np.linalg.LinAlgError."""
+    Lc = np.linalg.cholesky(A_f)
+    try:
+        from scipy.linalg import solve_triangular
+    except ImportError:
+        return np.linalg.solve(Lc.T, np.linalg.solve(Lc, rhs))
+    y = solve_triangular(Lc, rhs, lower=True, check_finite=False)
+    return solve_triangular(Lc, y, lower=True, trans="T", check_finite=False)
+
+
 def solve_system(A, b, theta, method="exact", eps=0.0):
     """Scaled / ridge-regularised local solve.  network.py:293-327.
     Raises np.linalg.LinAlgError where torch raises LinAlgError."""
@@ -226,9 +240,7 @@ def solve_system(A, b, theta, method="exact", eps=0.0):
         if m != "cholesky":
             A_f = A_f + (2 * eps) * np.eye(P)
             b_f = b_f + (2 * eps) * np.asarray(theta).reshape(P)
-        Lc = np.linalg.cholesky(A_f)
-        y = np.linalg.solve(Lc, -b_f)
-        x = np.linalg.solve(Lc.T, y)
+        x = _cholesky_solve(A_f, -b_f)
     elif m == "gradient":
         x = -np.asarray(b, dtype=np.float64).reshape(P)
     else:
