@@ -571,15 +571,48 @@ def use_all_host_threads():
     """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every host core.  Returns the thread count in effect."""
     ncpu = os.cpu_count() or 1
     try:
-        torch.set_num_threads(ncpu)
+        # the port's arithmetic is numpy/BLAS; torch only draws the initial cores.  Its OpenMP workers spin for a while after every
+        # parallel region and would steal the cores from the BLAS pool in the timed section right after: keep torch on one thread
+        torch.set_num_threads(1)
     except Exception:
         pass
     try:
         from threadpoolctl import threadpool_limits
-        threadpool_limits(limits=ncpu)          # numpy's BLAS / OpenMP pools
+        threadpool_limits(limits={"blas": ncpu, "openmp": 1})          # numpy's BLAS pool wide, the OpenMP pools (torch) out of its way
     except Exception:
         pass
     return ncpu
+
+
+def wake_host_cores(max_seconds=8.0):
+    """Multi-threaded GEMMs until their time settles.  After an idle stretch (the host idles while the GPU arm runs) the first
+    seconds of multi-threaded BLAS on these virtualised hosts run 20-400x slow (measured: every call of a fresh process ~0.8 s
+    instead of ~2 ms, until the vCPUs are back); a CPU number taken then says nothing about the CPU."""
+    a = np.random.default_rng(0).normal(size=(1024, 1024))
+    t_start = time.perf_counter()
+    prev = None
+    while time.perf_counter() - t_start < max_seconds:
+        t0 = time.perf_counter()
+        for _ in range(4):
+            a @ a
+        dt = time.perf_counter() - t0
+        if prev is not None and dt < 0.25 and abs(dt - prev) < 0.2 * prev and time.perf_counter() - t_start > 1.0:
+            break
+        prev = dt
+
+
+def cpu_site_time_warm(wl, rows):
+    """cpu_site_time without first-call effects (BLAS / LAPACK thread pools, lazy imports: ~1 s, 50x the cost of a small
+    workload): a short untimed call first, and the faster of two timed calls when one call is cheap."""
+    wake_host_cores()
+    cpu_site_time(wl, min(rows, 64))
+    t0 = time.perf_counter()
+    best = cpu_site_time(wl, rows)
+    if time.perf_counter() - t0 < 10.0:
+        again = cpu_site_time(wl, rows)
+        if again[0] + again[1] < best[0] + best[1]:
+            best = again
+    return best
 
 
 def cpu_baseline(args, wl, rows_total):
@@ -587,7 +620,7 @@ def cpu_baseline(args, wl, rows_total):
     rows = args.ref_rows or (256 if args.workload == "cfg5a" else ((32 if wl["kind"] == "conv" else 128) if wl.get("solver") else 2048))
     if wl.get("solver") and "_avg_matvecs" not in wl:
         wl = dict(wl, _avg_matvecs=float(args.ref_matvecs))
-    t_batch, t_solve, n = cpu_site_time(wl, rows)
+    t_batch, t_solve, n = cpu_site_time_warm(wl, rows)
     per_sweep_sites = max(2 * n - 2, 1)
     t_all_sites = t_batch * (rows_total / rows) + t_solve     # every site once
     value = n / t_all_sites * rows_total
@@ -622,12 +655,14 @@ def bench_reference(args):
     t0 = time.perf_counter()
     vals = []
     for _ in range(args.steps):
-        t_batch, t_solve, ns = cpu_site_time(wl, rows)
+        t_batch, t_solve, ns = cpu_site_time_warm(wl, rows) if not vals else cpu_site_time(wl, rows)
         vals.append(ns / (t_batch * (n / rows) + t_solve) * n)
     wall = time.perf_counter() - t0
     value = float(np.median(vals))
     sample = (f"oracle port of tensor/network.py (numpy/BLAS, {os.cpu_count()} host threads): per step, env+Jacobian+Gram+rhs of every "
-              f"site on one {rows}-row minibatch and the dense solves with P<=4096, extrapolated linearly to {n} rows")
+              f"site on one {rows}-row minibatch and the dense solves with P<=4096, extrapolated linearly to {n} rows; the Python "
+              f"reference cannot travel to this box -- measured beside it on an 8-core host the port is 23-48x faster than the "
+              f"reference verbatim and 1.1-2.8x slower than the reference with opt_einsum (profiles/r1_reference_vs_port_cpu.json)")
     if wl.get("solver"):
         sample = (f"oracle port of tensor/network.py:709-932 (numpy/BLAS, {os.cpu_count()} host threads): per step, envs + batch Jacobian + "
                   f"rhs + {wl['_avg_matvecs']:.0f} matvecs per site (--ref-matvecs) of every distinct site shape on one {rows}-row "

@@ -204,18 +204,22 @@ def gram(J, g, H):
     return A, b
 
 
+try:                                         # imported here, not inside the solve: the import costs ~1 s once
+    from scipy.linalg import solve_triangular as _solve_triangular
+except ImportError:
+    _solve_triangular = None
+
+
 def _cholesky_solve(A_f, rhs):
     """Cholesky factorisation + two TRIANGULAR substitutions (torch.linalg.cholesky + torch.cholesky_solve, network.py:313-315).
     The factorisation stays in numpy's BLAS (the Gram GEMM just ran there; a second BLAS pool -- SciPy's or torch's -- would
     fight it for the cores and cost 5-10x); the O(P^2) substitutions go through SciPy's dtrsv, with a general-solve fallback that
     gives the same numbers.  Not positive definite -> np.linalg.LinAlgError."""
     Lc = np.linalg.cholesky(A_f)
-    try:
-        from scipy.linalg import solve_triangular
-    except ImportError:
+    if _solve_triangular is None:
         return np.linalg.solve(Lc.T, np.linalg.solve(Lc, rhs))
-    y = solve_triangular(Lc, rhs, lower=True, check_finite=False)
-    return solve_triangular(Lc, y, lower=True, trans="T", check_finite=False)
+    y = _solve_triangular(Lc, rhs, lower=True, check_finite=False)
+    return _solve_triangular(Lc, y, lower=True, trans="T", check_finite=False)
 
 
 def solve_system(A, b, theta, method="exact", eps=0.0):
