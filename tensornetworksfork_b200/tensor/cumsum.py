@@ -33,6 +33,18 @@ class CumSumNetwork(TensorNetwork):
                 raise NotImplementedError("cum-sum trains have one input per core")
         return sites
 
+    def _phys_behind_operator(self, node):
+        """The reference's CumSumLayer graph (layers.py:435-457): core -[p_k]- operator node O_k -[d_k]- input.  The dense operator
+        is not contracted here (closed form), so the core's physical leg is bound to the input behind the operator."""
+        for lab in node.dim_labels:
+            op = node.connections.get(lab)
+            if op is None or node.is_horizontal_bond(lab):
+                continue
+            far = [n2 for l2, n2 in op.connections.items() if l2 != lab and any(n2 is n for n in self.input_nodes)]
+            if len(far) == 1:
+                return [(lab, far[0])]
+        return []
+
     def _bind(self, x):
         if isinstance(x, (MappedInput, list, tuple)):
             raise NotImplementedError("cum-sum trains take one (N, f) matrix shared by all cores (poly-mode)")

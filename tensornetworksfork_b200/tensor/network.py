@@ -215,6 +215,8 @@ class TensorNetwork:
                         s.linear = other
                         phys = [(lab, far[0][1])]
                         break
+            if not phys:
+                phys = self._phys_behind_operator(node)
             if len(phys) not in (1, 2):
                 raise NotImplementedError(f"{node.name}: expected one input node (or two for a 2-site block), found {len(phys)} "
                                           "(this engine covers tensor-train chains; see DESIGN.md)")
@@ -234,6 +236,11 @@ class TensorNetwork:
             raise NotImplementedError("more than one site carries an output leg")
         self._sites = sites
         return sites
+
+    def _phys_behind_operator(self, node):
+        """[(physical label, input node)] when an operator node sits between the core and its input (engines that replace such an
+        operator by a closed form override this); none in a plain chain."""
+        return []
 
     def _owner(self):
         for k, s in enumerate(self._plan()):

@@ -199,3 +199,132 @@ def test_reference_loss_objects_drive_the_engine(loss_name, monkeypatch):
         for a, b in zip(m_l, r_l):
             assert abs(a - b) <= 1e-7 * max(1.0, abs(b)), (m_l, r_l)
         assert float((m_p - r_p).norm() / r_p.norm()) < 1e-7
+
+
+def test_cpd_engine_runs_reference_built_graph(monkeypatch):
+    """INTEGRATION.md route 1 for CPD: the reference's CPDLayer builds the graph, the B200 CPDNetwork runs it."""
+    import fake_ops
+    ref_layers, ref_breg = _import_reference()
+    from tensornetworksfork_b200.tensor.cpd import CPDNetwork as FastCPD
+    fake_ops.install(monkeypatch)
+    rng = np.random.default_rng(1)
+    N, F = 180, 4
+    X = torch.tensor(np.concatenate([rng.uniform(-1, 1, size=(N, F)), np.ones((N, 1))], 1))
+    y = torch.tensor(np.tanh(X[:, :1].numpy()) + 0.1 * rng.normal(size=(N, 1)))
+    kw = dict(batch_size=60, num_swipes=2, lr=1.0, method="ridge_cholesky", eps=1.0, eps_decay=0.5)
+    ref_layer = ref_layers.CPDLayer(3, 4, F + 1, output_shape=(1,), seed=5)
+    ref_losses = []
+    ref_layer.tensor_network.accumulating_swipe(X, y, ref_breg.SquareBregFunction(), loss_callback=lambda NS, n, l: ref_losses.append(l), **kw)
+    ref_pred = ref_layer.tensor_network.forward(X, to_tensor=True)
+    layer2 = ref_layers.CPDLayer(3, 4, F + 1, output_shape=(1,), seed=5)
+    old = layer2.tensor_network
+    fast = FastCPD(old.input_nodes, old.main_nodes, old.train_nodes, output_labels=old.output_labels, sample_dim=old.sample_dim)
+    layer2.set_tensor_network(fast)
+    losses = []
+    assert fast.accumulating_swipe(X, y, ref_breg.SquareBregFunction(), loss_callback=lambda NS, n, l: losses.append(l), **kw)
+    assert len(losses) == len(ref_losses)
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) <= 1e-8 * max(1.0, abs(b))
+    pred = fast.forward(X, to_tensor=True)
+    assert float((pred.reshape(ref_pred.shape) - ref_pred).norm() / ref_pred.norm()) < 1e-8
+
+
+def test_conv_engine_runs_reference_built_graph(monkeypatch):
+    """INTEGRATION.md route 1 for the patch/pixel conv-TT: the reference's TensorConvolutionTrainLayer builds the graph (and grows
+    it with its own grow_cart), ConvTrainNetwork recognises the columns and runs the sweeps the image scripts call."""
+    import fake_ops
+    ref_layers, ref_breg = _import_reference()
+    from tensornetworksfork_b200.tensor.conv import ConvTrainNetwork
+    from scipy.sparse.linalg import minres
+    fake_ops.install(monkeypatch)
+    rng = np.random.default_rng(2)
+    N, Q, T = 90, 5, 4
+    X = torch.tensor(rng.uniform(-1, 1, size=(N, Q, T)))
+    X[:, -1, :] = 0.0
+    X[:, :, -1] = 0.0
+    X[:, -1, -1] = 1.0
+    y = torch.tensor(np.eye(3)[rng.integers(0, 3, N)])
+    ctor = dict(num_carriages=2, bond_dim=3, num_patches=Q, patch_pixels=T, output_shape=2, convolution_bond=2)
+    outs = []
+    for fast in (False, True):
+        torch.manual_seed(4)
+        layer = ref_layers.TensorConvolutionTrainLayer(**ctor)
+        layer.grow_cart(3, 2)                                       # the reference's own growth; its graph lacks right_labels there
+        if fast:
+            old = layer.tensor_network
+            layer.set_tensor_network(ConvTrainNetwork(old.input_nodes, old.main_nodes, old.train_nodes, output_labels=old.output_labels,
+                                                      sample_dim=old.sample_dim))
+        tn = layer.tensor_network
+        loss = ref_breg.XEAutogradBregman(w=1.0)
+        l1, l2 = [], []
+        assert tn.accumulating_swipe(X, y, loss, batch_size=40, num_swipes=1, method="ridge_exact", eps=1.0, eps_decay=0.5,
+                                     loss_callback=lambda NS, n, l: l1.append(float(l)))
+        assert tn.scipy_swipe(X, y, loss, minres, batch_size=45, num_swipes=1, max_iter=4, tol=1e-8, loss_callback=lambda l: l2.append(float(l)))
+        outs.append((l1, l2, tn.forward(X, to_tensor=True).detach()))
+    (r1, r2, rp), (m1, m2, mp) = outs
+    assert len(m1) == len(r1) and len(m2) == len(r2)
+    for a, b in zip(m1, r1):
+        assert abs(a - b) <= 1e-8 * max(1.0, abs(b)), (m1, r1)
+    for a, b in zip(m2, r2):
+        assert abs(a - b) <= 1e-4 * max(1.0, abs(b)), (m2, r2)      # float32 Krylov recurrences on the host (network.py:918-926)
+    assert float((mp - rp).norm() / rp.norm()) < 1e-3
+
+
+def test_cumsum_engine_runs_reference_built_graph(monkeypatch):
+    """INTEGRATION.md route 1 for the cum-sum train: the reference's CumSumLayer graph carries dense operator nodes between the
+    inputs and the cores; CumSumNetwork reads the cores and inputs from it and applies the operator in closed form."""
+    import fake_ops
+    ref_layers, ref_breg = _import_reference()
+    from tensornetworksfork_b200.tensor.cumsum import CumSumNetwork
+    fake_ops.install(monkeypatch)
+    rng = np.random.default_rng(3)
+    N, F = 150, 3
+    X = torch.tensor(np.concatenate([rng.uniform(-1, 1, size=(N, F)), np.ones((N, 1))], 1))
+    y = torch.tensor(X[:, :1].numpy() * X[:, 1:2].numpy() + 0.05 * rng.normal(size=(N, 1)))
+    kw = dict(batch_size=50, num_swipes=2, lr=1.0, method="ridge_cholesky", eps=1.0, eps_decay=0.5)
+    outs = []
+    for fast in (False, True):
+        torch.manual_seed(6)
+        layer = ref_layers.CumSumLayer(3, 3, F + 1, output_shape=1, constrict_bond=False)
+        if fast:
+            old = layer.tensor_network
+            layer.set_tensor_network(CumSumNetwork(old.input_nodes, old.main_nodes, old.train_nodes, output_labels=old.output_labels,
+                                                   sample_dim=old.sample_dim))
+        tn = layer.tensor_network
+        losses = []
+        assert tn.accumulating_swipe(X, y, ref_breg.SquareBregFunction(), loss_callback=lambda NS, n, l: losses.append(float(l)), **kw)
+        outs.append((losses, tn.forward(X, to_tensor=True).detach()))
+    (rl, rp), (ml, mp) = outs
+    assert len(ml) == len(rl)
+    for a, b in zip(ml, rl):
+        assert abs(a - b) <= 1e-8 * max(1.0, abs(b)), (ml, rl)
+    assert float((mp.reshape(rp.shape) - rp).norm() / rp.norm()) < 1e-8
+
+
+def test_linear_layer_engine_runs_reference_built_graph(monkeypatch):
+    """INTEGRATION.md route 1 for TensorTrainLinearLayer (trainable projection W_k between input and core, layers.py:308-343)."""
+    import fake_ops
+    ref_layers, ref_breg = _import_reference()
+    from tensornetworksfork_b200.tensor.network import TensorNetwork as FastTN
+    fake_ops.install(monkeypatch)
+    rng = np.random.default_rng(4)
+    N, F = 170, 5
+    X = torch.tensor(np.concatenate([rng.uniform(-1, 1, size=(N, F)), np.ones((N, 1))], 1))
+    y = torch.tensor(np.tanh(X[:, :1].numpy() - X[:, 1:2].numpy()) + 0.05 * rng.normal(size=(N, 1)))
+    kw = dict(batch_size=60, num_swipes=2, lr=1.0, method="ridge_cholesky", eps=1.0, eps_decay=0.5)
+    outs = []
+    for fast in (False, True):
+        layer = ref_layers.TensorTrainLinearLayer(3, 3, F + 1, 2, output_shape=1, constrict_bond=False, seed=8)
+        if fast:
+            old = layer.tensor_network
+            layer.set_tensor_network(FastTN(old.input_nodes, old.main_nodes, old.train_nodes, output_labels=old.output_labels,
+                                            sample_dim=old.sample_dim))
+        tn = layer.tensor_network
+        losses = []
+        assert tn.accumulating_swipe(X, y, ref_breg.SquareBregFunction(), loss_callback=lambda NS, n, l: losses.append(float(l)), **kw)
+        outs.append((losses, tn.forward(X, to_tensor=True).detach()))
+    (rl, rp), (ml, mp) = outs
+    assert len(ml) == len(rl)
+    for a, b in zip(ml, rl):
+        assert abs(a - b) <= 1e-8 * max(1.0, abs(b)), (ml, rl)
+    assert float((mp.reshape(rp.shape) - rp).norm() / rp.norm()) < 1e-8
