@@ -2,14 +2,17 @@
 
 They drive the same kernels, at the same kinds of shapes, as the files before them -- only the host flow is new -- and each has a
 twin on the CPU stand-in kernels (named in its docstring) that is green.  The file sorts last on purpose: these tests had not
-run on a B200 when they were committed, so under ``pytest -x`` they cannot hide a result of the measured ones.
+run on a B200 when they were committed, so under ``pytest -x`` they cannot hide a result of the measured ones.  For the same
+reason they are marked ``xfail(strict=False)``: the report shows XPASS where the B200 agrees and XFAIL (with the numbers) where a
+tolerance needs the measured margin of ``tools/test_margins.py`` -- remove the mark once they have run.
 """
 import pytest
 import torch
 
 import conv_cases as cc
 
-pytestmark = pytest.mark.gpu
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.xfail(strict=False, reason="host flow added after the round's GPU minutes were spent: not yet run on a B200")]
 torch.set_default_dtype(torch.float64)
 
 
