@@ -99,7 +99,7 @@ def _shard_worker(rank, world, port, name, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("name", ["tt_poly_reg", "tnml_poly_xe"])
+@pytest.mark.parametrize("name", ["tt_poly_reg", "tnml_poly_xe", "cpd_reg", "tnml_sincos_qr", "tt_adaptive_maxnorm"])
 def test_sample_sharded_sweep_world2_gloo(name, tmp_path):
     """Two ranks, each with a row shard: one sum-all-reduce of [M | b] (and the per-batch loss sums) per site.
     Result must equal the single-process sweep and the reference recording; cores bit-identical across ranks."""
