@@ -68,7 +68,9 @@ class ConvTrainNetwork(TensorNetwork):
         present = [l for l in order if l in node.dim_labels]
         if present != list(node.dim_labels):
             raise NotImplementedError(f"{node.name}: label order {node.dim_labels} is not the constructor's")
-        return node.tensor.reshape([node.dim_size(l) if l in node.dim_labels else 1 for l in order])
+        # grow_cart leaves the old last cores as stride-0 broadcasts until their first update: the kernels read dense rows
+        t = node.tensor if node.tensor.is_contiguous() else node.tensor.contiguous()
+        return t.reshape([node.dim_size(l) if l in node.dim_labels else 1 for l in order])
 
     def _bonds(self, k, which):
         """(left, right) bond labels of the patch (which = 0) or pixel (which = 1) core of column k, read from the connections to the

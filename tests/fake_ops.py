@@ -8,8 +8,14 @@ from tensornetworksfork_b200 import ops as real
 from tensornetworksfork_b200.ops import Factor, npairs  # noqa: F401
 
 
+def _unit_rows(t, what):
+    """The kernels read ``t`` as rows with stride ``t.stride(0)`` and unit stride inside a row (ops.Factor.ld, env_ld, dot_ld, out_ld)."""
+    assert t is None or t.dim() == 1 or (t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1)), (what, tuple(t.shape), t.stride())
+
+
 def _rows(f: Factor, rows):
     t = f.tensor
+    _unit_rows(t, "factor")
     idx = torch.arange(rows) // max(f.div, 1)
     idx = idx.clamp(max=t.shape[0] - 1)
     if f.map_kind == real.MAP_IDENTITY:
@@ -25,6 +31,8 @@ def ones_factor(like):
 
 
 def env_update(env_in, x, core3, rows, cdiv=1, env_div=1, out=None):
+    _unit_rows(env_in, "env_in")
+    _unit_rows(out, "out")
     phi = _rows(Factor(x.tensor, m=x.m, div=cdiv, map_kind=x.map_kind, col=x.col), rows)
     e = torch.ones(rows, 1, dtype=torch.float64) if env_in is None else env_in[torch.arange(rows) // env_div]
     res = torch.einsum("sa,sp,apb->sb", e, phi, core3)
@@ -35,6 +43,7 @@ def env_update(env_in, x, core3, rows, cdiv=1, env_div=1, out=None):
 
 
 def predict(env_in, x, core3, dot, rows, cdiv=1, env_div=1, dot_div=1, out=None):
+    _unit_rows(dot, "dot")
     o = env_update(env_in, x, core3, rows, cdiv, env_div, out=None)
     d = dot[(torch.arange(rows) // dot_div).clamp(max=dot.shape[0] - 1)]
     y = (o * d).sum(1)
@@ -159,9 +168,10 @@ def update_node(theta, step, lr=1.0, adaptive_step=False, max_norm=None):
 
 
 def qr(a):
+    assert a.is_contiguous() and a.dim() == 2
     Q, R = torch.linalg.qr(a, mode="reduced")
     a.copy_(Q)
-    return R
+    return R.contiguous()        # the real entry point returns a dense row-major R
 
 
 def matvec(fa, fb, fc, w, rows, v, out=None):
@@ -193,6 +203,7 @@ def install(monkeypatch=None):
 
 
 def bmm(A, B, out=None, accumulate=False):
+    assert out is None or out.is_contiguous()
     r = torch.matmul(A, B)
     if r.dim() == 2:
         r = r.unsqueeze(0)
@@ -206,6 +217,9 @@ def bmm(A, B, out=None, accumulate=False):
 
 
 def outer_rows(G, W, w=None, gdiv=1, out=None, accumulate=False):
+    # the layout contract of the real entry point (ops.outer_rows): the stand-in must refuse what the kernel would misread
+    assert G.dim() == 2 and W.dim() == 2 and G.stride(1) == 1 and W.stride(1) == 1, (G.stride(), W.stride())
+    assert out is None or out.is_contiguous()
     rows = W.shape[0]
     Gr = G[torch.arange(rows) // gdiv]
     if w is not None:
@@ -221,6 +235,8 @@ def outer_rows(G, W, w=None, gdiv=1, out=None, accumulate=False):
 
 
 def rows_dot(W, V, out=None):
+    assert W.dim() == 2 and V.dim() == 2 and W.stride(1) == 1 and V.stride(1) == 1 and W.shape[1] == V.shape[1], (W.stride(), V.stride())
+    assert out is None or (out.dim() == 2 and (out.stride(1) == 1 or V.shape[0] == 1))
     r = W @ V.t()
     if out is None:
         return r.contiguous()
