@@ -46,6 +46,13 @@ def _need_cuda(*ts):
             raise _lib.TnError(f"fp64 tensors expected, got {t.dtype}")
 
 
+def _bare(*ts):
+    """Buffers handed to the library as bare pointers (weights, vectors, outputs) must be dense: the kernels index them linearly."""
+    for t in ts:
+        if t is not None and not t.is_contiguous():
+            raise _lib.TnError(f"dense tensor expected, got shape {tuple(t.shape)} with strides {t.stride()}")
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -116,6 +123,7 @@ def gram(mode, fa: Factor, fb: Factor, fc: Factor, w, rows, M=None, accumulate=F
     """M[qa,qb,qc] (+)= sum_rows w * pair(fa)[qa] * pair(fb)[qb] * pair(fc)[qc]."""
     lib = _lib.load()
     _need_cuda(fa.tensor, fb.tensor, fc.tensor, w)
+    _bare(w, M)
     n = npairs(fa.m) * npairs(fb.m) * npairs(fc.m)
     dev = fa.tensor.device
     if M is None:
@@ -136,6 +144,7 @@ def rhs(fa: Factor, fb: Factor, fc: Factor, w, rows, b=None, accumulate=False):
     """b[ia,ib,ic] (+)= sum_rows w * fa[ia] fb[ib] fc[ic]."""
     lib = _lib.load()
     _need_cuda(fa.tensor, fb.tensor, fc.tensor, w)
+    _bare(w, b)
     n = fa.m * fb.m * fc.m
     dev = fa.tensor.device
     if b is None:
@@ -154,6 +163,7 @@ def gram_generic(f1: Factor, f2: Factor, f3: Factor, t1, t2, t3, w, rows, rhs_on
     """Dense Gram J^T diag(w) J (P x P) or right-hand side J^T w (P) of J[:, i] = f1[t1[i]] f2[t2[i]] f3[t3[i]]."""
     lib = _lib.load()
     _need_cuda(f1.tensor, f2.tensor, f3.tensor, w)
+    _bare(w, out, t1, t2, t3)
     P = t1.numel()
     assert t1.dtype == torch.int32 and t2.dtype == torch.int32 and t3.dtype == torch.int32
     n = P if rhs_only else P * P
@@ -254,6 +264,7 @@ def matvec(fa: Factor, fb: Factor, fc: Factor, w, rows, v, out=None):
     """out = J^T diag(w) J v with J[row,(ia,ib,ic)] = fa fb fc."""
     lib = _lib.load()
     _need_cuda(fa.tensor, fb.tensor, fc.tensor, w, v)
+    _bare(w, out)
     n = fa.m * fb.m * fc.m
     if out is None:
         out = torch.empty((n,), dtype=torch.float64, device=v.device)
@@ -288,6 +299,7 @@ def outer_rows(G, W, w=None, gdiv=1, out=None, accumulate=False):
     """out (ra, m) (+)= sum_row w[row] * G[row // gdiv, :]^T W[row, :]; G (rows/gdiv, ra), W (rows, m), row strides free."""
     lib = _lib.load()
     _need_cuda(G, W, w)
+    _bare(w)
     assert G.dim() == 2 and W.dim() == 2 and G.stride(1) == 1 and W.stride(1) == 1
     rows, m = W.shape
     ra = G.shape[1]

@@ -13,6 +13,12 @@ def _unit_rows(t, what):
     assert t is None or t.dim() == 1 or (t.dim() == 2 and (t.stride(1) == 1 or t.shape[1] == 1)), (what, tuple(t.shape), t.stride())
 
 
+def _bare(*ts):
+    """Buffers the kernels take as bare pointers (weights, outputs, vectors) must be dense."""
+    for t in ts:
+        assert t is None or t.is_contiguous(), (tuple(t.shape), t.stride())
+
+
 def _rows(f: Factor, rows):
     t = f.tensor
     _unit_rows(t, "factor")
@@ -65,6 +71,7 @@ def _pairs(F):
 
 
 def gram(mode, fa, fb, fc, w, rows, M=None, accumulate=False):
+    _bare(w, M)
     A, B, C = _pairs(_rows(fa, rows)), _pairs(_rows(fb, rows)), _pairs(_rows(fc, rows))
     ww = torch.ones(rows, dtype=torch.float64) if w is None else w
     out = torch.einsum("s,sa,sb,sc->abc", ww, A, B, C).reshape(-1)
@@ -78,6 +85,7 @@ def gram(mode, fa, fb, fc, w, rows, M=None, accumulate=False):
 
 
 def rhs(fa, fb, fc, w, rows, b=None, accumulate=False):
+    _bare(w, b)
     ww = torch.ones(rows, dtype=torch.float64) if w is None else w
     out = torch.einsum("s,sa,sb,sc->abc", ww, _rows(fa, rows), _rows(fb, rows), _rows(fc, rows)).reshape(-1)
     if b is None:
@@ -90,6 +98,7 @@ def rhs(fa, fb, fc, w, rows, b=None, accumulate=False):
 
 
 def gram_generic(f1, f2, f3, t1, t2, t3, w, rows, rhs_only=False, out=None, accumulate=False):
+    _bare(w, out, t1, t2, t3)
     J = _rows(f1, rows)[:, t1.long()] * _rows(f2, rows)[:, t2.long()] * _rows(f3, rows)[:, t3.long()]
     ww = torch.ones(rows, dtype=torch.float64) if w is None else w
     res = (J.t() @ ww) if rhs_only else ((J * ww[:, None]).t() @ J).reshape(-1)
@@ -175,6 +184,7 @@ def qr(a):
 
 
 def matvec(fa, fb, fc, w, rows, v, out=None):
+    _bare(w, out)
     J = torch.einsum("sa,sb,sc->sabc", _rows(fa, rows), _rows(fb, rows), _rows(fc, rows)).reshape(rows, -1)
     ww = torch.ones(rows, dtype=torch.float64) if w is None else w
     return J.t() @ (ww * (J @ v))
@@ -219,6 +229,7 @@ def bmm(A, B, out=None, accumulate=False):
 def outer_rows(G, W, w=None, gdiv=1, out=None, accumulate=False):
     # the layout contract of the real entry point (ops.outer_rows): the stand-in must refuse what the kernel would misread
     assert G.dim() == 2 and W.dim() == 2 and G.stride(1) == 1 and W.stride(1) == 1, (G.stride(), W.stride())
+    _bare(w)
     assert out is None or out.is_contiguous()
     rows = W.shape[0]
     Gr = G[torch.arange(rows) // gdiv]
