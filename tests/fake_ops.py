@@ -22,8 +22,12 @@ def _bare(*ts):
 def _rows(f: Factor, rows):
     t = f.tensor
     _unit_rows(t, "factor")
+    assert t.dtype == torch.float64, t.dtype                     # ops._need_cuda: the kernels read fp64
     idx = torch.arange(rows) // max(f.div, 1)
-    idx = idx.clamp(max=t.shape[0] - 1)
+    # the kernels read row (rows - 1) // div of the factor: it must exist (no clamping on the device)
+    assert rows == 0 or (rows - 1) // max(f.div, 1) < t.shape[0], (rows, f.div, tuple(t.shape))
+    need = (f.col + f.m) if f.map_kind == real.MAP_IDENTITY else (f.col + 1)
+    assert t.dim() != 2 or need <= t.shape[1], (f.col, f.m, tuple(t.shape))
     if f.map_kind == real.MAP_IDENTITY:
         return t[idx][:, f.col:f.col + f.m]
     x = t[idx][:, f.col]
@@ -39,6 +43,8 @@ def ones_factor(like):
 def env_update(env_in, x, core3, rows, cdiv=1, env_div=1, out=None):
     _unit_rows(env_in, "env_in")
     _unit_rows(out, "out")
+    assert env_in is None or (env_in.dtype == torch.float64 and (rows - 1) // env_div < env_in.shape[0] and env_in.shape[1] >= core3.shape[0])
+    assert core3.dtype == torch.float64 and core3.dim() == 3
     phi = _rows(Factor(x.tensor, m=x.m, div=cdiv, map_kind=x.map_kind, col=x.col), rows)
     e = torch.ones(rows, 1, dtype=torch.float64) if env_in is None else env_in[torch.arange(rows) // env_div]
     res = torch.einsum("sa,sp,apb->sb", e, phi, core3)
@@ -50,6 +56,7 @@ def env_update(env_in, x, core3, rows, cdiv=1, env_div=1, out=None):
 
 def predict(env_in, x, core3, dot, rows, cdiv=1, env_div=1, dot_div=1, out=None):
     _unit_rows(dot, "dot")
+    assert dot.dtype == torch.float64 and dot.shape[-1] >= core3.shape[2] and (dot_div >= (1 << 30) or (rows - 1) // dot_div < dot.shape[0])
     o = env_update(env_in, x, core3, rows, cdiv, env_div, out=None)
     d = dot[(torch.arange(rows) // dot_div).clamp(max=dot.shape[0] - 1)]
     y = (o * d).sum(1)
