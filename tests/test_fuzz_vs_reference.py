@@ -1,0 +1,172 @@
+"""Randomised side-by-side runs against the UNMODIFIED reference (build container only: needs /root/reference): seeded random
+model shapes, losses and accumulating_swipe keyword combinations, the mirrored layer on the CPU stand-in kernels against the
+reference layer on its own engine.  Well-conditioned settings only (ridge >= 0.3), so free-running sweeps stay comparable."""
+import importlib
+import os
+import sys
+import types
+
+import numpy as np
+import pytest
+import torch
+
+REF = "/root/reference"
+pytestmark = pytest.mark.skipif(not os.path.isdir(os.path.join(REF, "tensor")), reason="reference tree not mounted")
+torch.set_default_dtype(torch.float64)
+
+
+def _ref(module):
+    for name in ("matplotlib", "matplotlib.pyplot"):
+        if name not in sys.modules:
+            sys.modules[name] = types.ModuleType(name)
+    sys.modules["matplotlib"].pyplot = sys.modules["matplotlib.pyplot"]
+    if REF not in sys.path:
+        sys.path.append(REF)
+    return importlib.import_module(module)
+
+
+def _draw(seed):
+    rng = np.random.default_rng(1000 + seed)
+    kind = ["tt", "tt", "tnml", "cpd"][seed % 4]
+    n = int(rng.integers(1, 6)) if kind != "cpd" else int(rng.integers(2, 5))
+    r = int(rng.integers(2, 5))
+    F = int(rng.integers(2, 5))
+    C = int(rng.choice([1, 1, 2, 3]))
+    xe = C > 1 and bool(rng.integers(0, 2))
+    N = int(rng.integers(40, 120))
+    half_sweeps = int(rng.integers(1, 4))
+    kw = dict(batch_size=int(rng.choice([-1, 16, 37, 1000])), num_swipes=half_sweeps, lr=float(rng.choice([1.0, 0.6])),
+              method=str(rng.choice(["ridge_cholesky", "ridge_exact"])), skip_second=bool(rng.integers(0, 2)),
+              direction=str(rng.choice(["l2r", "r2l"])))
+    n_eps = half_sweeps if kw["skip_second"] else 2 * half_sweeps
+    style = int(rng.integers(0, 3))
+    if style == 0:
+        kw["eps"] = float(rng.uniform(0.3, 2.0))
+    elif style == 1:
+        kw["eps"], kw["eps_decay"] = float(rng.uniform(1.0, 2.0)), float(rng.uniform(0.7, 0.95))
+    else:
+        kw["eps"] = [float(v) for v in rng.uniform(0.3, 2.0, size=n_eps)]
+    if kind == "tt" and rng.integers(0, 3) == 0:
+        kw["adaptive_step"], kw["max_norm"] = True, float(rng.uniform(1.0, 4.0))
+    if kind == "tnml" and n > 1 and rng.integers(0, 2) == 0:
+        kw["orthonormalize"] = True
+    return dict(kind=kind, n=n, r=r, F=F, C=C, xe=xe, N=N, kw=kw, perturb=bool(kind == "tt" and C == 1 and rng.integers(0, 2)),
+                constrict=bool(rng.integers(0, 2)), seed=int(rng.integers(0, 1000)))
+
+
+@pytest.mark.parametrize("seed", range(32))
+def test_random_configuration_side_by_side(seed, monkeypatch):
+    import fake_ops
+    fake_ops.install(monkeypatch)
+    ref_layers, ref_breg = _ref("tensor.layers"), _ref("tensor.bregman")
+    import tensornetworksfork_b200 as tnb
+    c = _draw(seed)
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-1, 1, size=(c["N"], c["F"]))
+    if c["xe"]:
+        y = torch.tensor(np.eye(c["C"] + 1)[rng.integers(0, c["C"] + 1, c["N"])])
+    else:
+        y = torch.tensor(np.tanh(X @ rng.normal(size=(c["F"], c["C"]))) + 0.1 * rng.normal(size=(c["N"], c["C"])))
+    outs = []
+    for mod, breg in ((ref_layers, ref_breg), (tnb, tnb)):
+        if c["kind"] == "tnml":       # one site per feature, sin-cos map (models/tnml.py:11-16), a list of per-site inputs
+            xs = [torch.tensor(np.stack([np.cos(0.5 * np.pi * X[:, j]), np.sin(0.5 * np.pi * X[:, j])], 1)) for j in range(c["F"])]
+            layer = mod.TensorTrainLayer(c["F"], c["r"], 2, output_shape=c["C"], constrict_bond=c["constrict"], seed=c["seed"])
+            x = xs
+        else:
+            x = torch.tensor(np.concatenate([X, np.ones((c["N"], 1))], 1))
+            if c["kind"] == "cpd":
+                layer = mod.CPDLayer(c["n"], c["r"], c["F"] + 1, output_shape=(c["C"],), seed=c["seed"])
+            else:
+                layer = mod.TensorTrainLayer(c["n"], c["r"], c["F"] + 1, output_shape=c["C"], constrict_bond=c["constrict"],
+                                             perturb=c["perturb"], seed=c["seed"])
+        loss = breg.XEAutogradBregman(w=1.0) if c["xe"] else breg.SquareBregFunction()
+        tn = layer.tensor_network
+        ev = []
+        ret = tn.accumulating_swipe(x, y, loss, loss_callback=lambda NS, nd, l: ev.append((NS, tn.train_nodes.index(nd), float(l))), **c["kw"])
+        outs.append((ret, ev, tn.forward(x, to_tensor=True).detach()))
+    (r_ret, r_ev, r_p), (m_ret, m_ev, m_p) = outs
+    assert m_ret == r_ret, c
+    assert [e[:2] for e in m_ev] == [e[:2] for e in r_ev], c
+    for a, b in zip(m_ev, r_ev):
+        assert abs(a[2] - b[2]) <= 1e-6 * max(1.0, abs(b[2])), (c, a, b)
+    assert float((m_p.reshape(r_p.shape) - r_p).norm() / max(float(r_p.norm()), 1e-12)) < 1e-6, c
+
+
+def _draw_special(seed):
+    rng = np.random.default_rng(5000 + seed)
+    kind = ["type1", "cumsum", "linear", "conv", "conv_krylov", "type1_cpd"][seed % 6]
+    c = dict(kind=kind, r=int(rng.integers(2, 4)), F=int(rng.integers(2, 5)), N=int(rng.integers(40, 100)), seed=int(rng.integers(0, 1000)),
+             n=int(rng.integers(2, 4)), C=1, xe=False)
+    if kind in ("conv", "conv_krylov", "linear"):
+        c["C"] = int(rng.choice([1, 2]))
+        c["xe"] = c["C"] > 1
+    half = int(rng.integers(1, 3))
+    c["kw"] = dict(batch_size=int(rng.choice([-1, 23, 64])), num_swipes=half, lr=1.0, method=str(rng.choice(["ridge_cholesky", "ridge_exact"])),
+                   eps=float(rng.uniform(0.5, 2.0)), eps_decay=float(rng.uniform(0.7, 1.0)), direction=str(rng.choice(["l2r", "r2l"])))
+    if kind == "conv_krylov":
+        c["kw"] = dict(batch_size=int(rng.choice([16, 40])), num_swipes=1, lr=1.0, max_iter=int(rng.integers(2, 6)), tol=1e-10)
+    return c
+
+
+@pytest.mark.parametrize("seed", range(30))
+def test_random_special_model_side_by_side(seed, monkeypatch):
+    """Type-I sums (TT and CPD members), cum-sum train, linear-projection train, conv-TT (dense and matrix-free), random shapes."""
+    import fake_ops
+    fake_ops.install(monkeypatch)
+    ref_layers, ref_breg, ref_net = _ref("tensor.layers"), _ref("tensor.bregman"), _ref("tensor.network")
+    import tensornetworksfork_b200 as tnb
+    c = _draw_special(seed)
+    rng = np.random.default_rng(seed)
+    N, F, C = c["N"], c["F"], c["C"]
+    if c["kind"].startswith("conv"):
+        Q, T = F + 2, F + 1
+        X = rng.uniform(-1, 1, size=(N, Q, T))
+        X[:, -1, :] = 0.0
+        X[:, :, -1] = 0.0
+        X[:, -1, -1] = 1.0
+        x = torch.tensor(X)
+        feat = X[:, :-1, :-1].reshape(N, -1)
+    else:
+        X = rng.uniform(-1, 1, size=(N, F))
+        x = torch.tensor(np.concatenate([X, np.ones((N, 1))], 1))
+        feat = X
+    if c["xe"]:
+        y = torch.tensor(np.eye(C + 1)[rng.integers(0, C + 1, N)])
+    else:
+        y = torch.tensor(np.tanh(feat @ rng.normal(size=(feat.shape[1], C)) / np.sqrt(feat.shape[1])) + 0.1 * rng.normal(size=(N, C)))
+    outs = []
+    for mod, breg, netmod in ((ref_layers, ref_breg, ref_net), (tnb, tnb, tnb)):
+        torch.manual_seed(c["seed"])              # layers that do not apply their seed argument draw from the global generator
+        k = c["kind"]
+        if k == "type1":
+            nets = [mod.TensorTrainLayer(i, bond_dim=c["r"], input_features=F if i != 1 else F + 1, output_shape=1, constrict_bond=True,
+                                         perturb=True, seed=c["seed"] + i).tensor_network for i in range(1, c["n"] + 1)]
+            layer = mod.TensorNetworkLayer(netmod.SumOfNetworks(nets, output_labels=nets[0].output_labels))
+        elif k == "type1_cpd":
+            nets = [mod.CPDLayer(i, c["r"], F if i != 1 else F + 1, output_shape=(1,), seed=c["seed"] + i).tensor_network
+                    for i in range(1, c["n"] + 1)]
+            layer = mod.TensorNetworkLayer(netmod.SumOfNetworks(nets, output_labels=nets[0].output_labels))
+        elif k == "cumsum":
+            layer = mod.CumSumLayer(c["n"], c["r"], F + 1, output_shape=1, constrict_bond=False)
+        elif k == "linear":
+            layer = mod.TensorTrainLinearLayer(c["n"], c["r"], F + 1, 2, output_shape=C, constrict_bond=False, seed=c["seed"])
+        else:
+            layer = mod.TensorConvolutionTrainLayer(num_carriages=c["n"], bond_dim=c["r"], num_patches=x.shape[1], patch_pixels=x.shape[2],
+                                                    output_shape=C, convolution_bond=2)
+        loss = breg.XEAutogradBregman(w=1.0) if c["xe"] else breg.SquareBregFunction()
+        tn = layer.tensor_network
+        ev = []
+        if k == "conv_krylov":
+            from scipy.sparse.linalg import minres
+            ret = tn.scipy_swipe(x, y, loss, minres, loss_callback=lambda l: ev.append(float(l)), **c["kw"])
+        else:
+            ret = tn.accumulating_swipe(x, y, loss, loss_callback=lambda NS, nd, l: ev.append(float(l)), **c["kw"])
+        outs.append((ret, ev, tn.forward(x, to_tensor=True).detach()))
+    (r_ret, r_ev, r_p), (m_ret, m_ev, m_p) = outs
+    tol = 1e-3 if c["kind"] == "conv_krylov" else 1e-6        # float32 Krylov recurrences on the host (network.py:918-926)
+    assert m_ret == r_ret, c
+    assert len(m_ev) == len(r_ev), c
+    for a, b in zip(m_ev, r_ev):
+        assert abs(a - b) <= tol * max(1.0, abs(b)), (c, m_ev, r_ev)
+    assert float((m_p.reshape(r_p.shape) - r_p).norm() / max(float(r_p.norm()), 1e-12)) < (1e-2 if c["kind"] == "conv_krylov" else 1e-6), c
