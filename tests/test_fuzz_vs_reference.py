@@ -170,3 +170,42 @@ def test_random_special_model_side_by_side(seed, monkeypatch):
     for a, b in zip(m_ev, r_ev):
         assert abs(a - b) <= tol * max(1.0, abs(b)), (c, m_ev, r_ev)
     assert float((m_p.reshape(r_p.shape) - r_p).norm() / max(float(r_p.norm()), 1e-12)) < (1e-2 if c["kind"] == "conv_krylov" else 1e-6), c
+
+
+@pytest.mark.parametrize("seed", [s for s in range(32) if s % 4 != 3])
+def test_oracle_tracks_reference_on_random_configurations(seed):
+    """The numpy oracle (the checker the GPU tests and smoke() use where no recording exists) against the live reference on the
+    same random TT / TNML configurations: per-update loss trace and final prediction."""
+    ref_layers, ref_breg = _ref("tensor.layers"), _ref("tensor.bregman")
+    from oracle import tn_oracle as orc
+    c = _draw(seed)
+    rng = np.random.default_rng(seed)
+    X = rng.uniform(-1, 1, size=(c["N"], c["F"]))
+    if c["xe"]:
+        y = np.eye(c["C"] + 1)[rng.integers(0, c["C"] + 1, c["N"])]
+    else:
+        y = np.tanh(X @ rng.normal(size=(c["F"], c["C"]))) + 0.1 * rng.normal(size=(c["N"], c["C"]))
+    if c["kind"] == "tnml":
+        xs = [np.stack([np.cos(0.5 * np.pi * X[:, j]), np.sin(0.5 * np.pi * X[:, j])], 1) for j in range(c["F"])]
+        layer = ref_layers.TensorTrainLayer(c["F"], c["r"], 2, output_shape=c["C"], constrict_bond=c["constrict"], seed=c["seed"])
+        x_np, x_t = xs, [torch.tensor(t) for t in xs]
+    else:
+        x_np = np.concatenate([X, np.ones((c["N"], 1))], 1)
+        x_t = torch.tensor(x_np)
+        layer = ref_layers.TensorTrainLayer(c["n"], c["r"], c["F"] + 1, output_shape=c["C"], constrict_bond=c["constrict"],
+                                            perturb=c["perturb"], seed=c["seed"])
+    tn = layer.tensor_network
+    cores = [n.tensor.detach().numpy().copy() for n in tn.train_nodes]
+    loss = ref_breg.XEAutogradBregman(w=1.0) if c["xe"] else ref_breg.SquareBregFunction()
+    ref_ev = []
+    ret = tn.accumulating_swipe(x_t, torch.tensor(y), loss, loss_callback=lambda NS, nd, l: ref_ev.append((NS, tn.train_nodes.index(nd), float(l))),
+                                **c["kw"])
+    trace = []
+    ok = orc.accumulating_swipe(cores, x_np, y, loss="xe" if c["xe"] else "square", trace=trace, **c["kw"])
+    assert ok == ret
+    assert [(t["NS"], t["k"]) for t in trace] == [e[:2] for e in ref_ev], c
+    for t, e in zip(trace, ref_ev):
+        assert abs(t["loss"] - e[2]) <= 1e-6 * max(1.0, abs(e[2])), (c, t["loss"], e)
+    pred = orc.forward(cores, x_np)
+    ref_pred = tn.forward(x_t, to_tensor=True).detach().numpy()
+    assert np.linalg.norm(pred.reshape(ref_pred.shape) - ref_pred) / max(np.linalg.norm(ref_pred), 1e-12) < 1e-6, c
