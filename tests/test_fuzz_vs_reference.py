@@ -209,3 +209,55 @@ def test_oracle_tracks_reference_on_random_configurations(seed):
     pred = orc.forward(cores, x_np)
     ref_pred = tn.forward(x_t, to_tensor=True).detach().numpy()
     assert np.linalg.norm(pred.reshape(ref_pred.shape) - ref_pred) / max(np.linalg.norm(ref_pred), 1e-12) < 1e-6, c
+
+
+@pytest.mark.parametrize("seed", range(24))
+def test_random_matrix_free_sweeps_side_by_side(seed, monkeypatch):
+    """lanczos_swipe (same torch seed -> same random start vectors in both engines) and scipy_swipe (cg / minres) on random TT,
+    TNML, cum-sum and linear-projection models.  Few Krylov steps: the unregularised local systems are singular by gauge freedom and
+    long recurrences amplify rounding differences."""
+    import fake_ops
+    fake_ops.install(monkeypatch)
+    ref_layers, ref_breg = _ref("tensor.layers"), _ref("tensor.bregman")
+    import tensornetworksfork_b200 as tnb
+    from scipy.sparse.linalg import cg, minres
+    rng = np.random.default_rng(9000 + seed)
+    kind = ["tt", "tnml", "cumsum", "linear"][seed % 4]
+    solver = ["lanczos", "cg", "minres"][seed % 3]
+    n, r, F = int(rng.integers(2, 5)), int(rng.integers(2, 4)), int(rng.integers(2, 5))
+    C = 1 if kind == "cumsum" else int(rng.choice([1, 2]))
+    xe = C > 1
+    N = int(rng.integers(50, 110))
+    X = rng.uniform(-1, 1, size=(N, F))
+    y = torch.tensor(np.eye(C + 1)[rng.integers(0, C + 1, N)] if xe else np.tanh(X @ rng.normal(size=(F, C))) + 0.1 * rng.normal(size=(N, C)))
+    kw = dict(batch_size=int(rng.choice([20, 64, 500])), num_swipes=int(rng.integers(1, 3)), lr=1.0, max_iter=int(rng.integers(2, 5)), tol=1e-10)
+    mseed = int(rng.integers(0, 1000))
+    outs = []
+    for mod, breg in ((ref_layers, ref_breg), (tnb, tnb)):
+        torch.manual_seed(mseed)
+        if kind == "tnml":
+            x = [torch.tensor(np.stack([np.cos(0.5 * np.pi * X[:, j]), np.sin(0.5 * np.pi * X[:, j])], 1)) for j in range(F)]
+            layer = mod.TensorTrainLayer(F, r, 2, output_shape=C, constrict_bond=True, seed=mseed)
+        else:
+            x = torch.tensor(np.concatenate([X, np.ones((N, 1))], 1))
+            if kind == "cumsum":
+                layer = mod.CumSumLayer(n, r, F + 1, output_shape=1, constrict_bond=False)
+            elif kind == "linear":
+                layer = mod.TensorTrainLinearLayer(n, r, F + 1, 2, output_shape=C, constrict_bond=False, seed=mseed)
+            else:
+                layer = mod.TensorTrainLayer(n, r, F + 1, output_shape=C, constrict_bond=False, seed=mseed)
+        loss = breg.XEAutogradBregman(w=1.0) if xe else breg.SquareBregFunction()
+        tn = layer.tensor_network
+        ev = []
+        torch.manual_seed(mseed + 1)              # the Lanczos start vectors
+        if solver == "lanczos":
+            ret = tn.lanczos_swipe(x, y, loss, loss_callback=lambda l: ev.append(float(l)), **kw)
+        else:
+            ret = tn.scipy_swipe(x, y, loss, {"cg": cg, "minres": minres}[solver], loss_callback=lambda l: ev.append(float(l)), **kw)
+        outs.append((ret, ev, tn.forward(x, to_tensor=True).detach()))
+    (r_ret, r_ev, r_p), (m_ret, m_ev, m_p) = outs
+    assert m_ret == r_ret and len(m_ev) == len(r_ev)
+    tol = 1e-6 if solver == "lanczos" else 2e-3          # SciPy path: float32 recurrences on the host (network.py:918-926)
+    for a, b in zip(m_ev, r_ev):
+        assert abs(a - b) <= tol * max(1.0, abs(b)), (kind, solver, m_ev, r_ev)
+    assert float((m_p.reshape(r_p.shape) - r_p).norm() / max(float(r_p.norm()), 1e-12)) < 10 * tol, (kind, solver)
