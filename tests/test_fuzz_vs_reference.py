@@ -261,3 +261,61 @@ def test_random_matrix_free_sweeps_side_by_side(seed, monkeypatch):
     for a, b in zip(m_ev, r_ev):
         assert abs(a - b) <= tol * max(1.0, abs(b)), (kind, solver, m_ev, r_ev)
     assert float((m_p.reshape(r_p.shape) - r_p).norm() / max(float(r_p.norm()), 1e-12)) < 10 * tol, (kind, solver)
+
+
+@pytest.mark.parametrize("seed", range(18))
+def test_random_driver_keywords_side_by_side(seed, monkeypatch):
+    """The keywords the first fuzz does not draw: method='gradient' (its two halves differ, network.py:458-470 vs :558-584),
+    eps_per_node, explicit node orders (list / tuple of two lists / subsets), convergence_criterion stops, timeout=0."""
+    import fake_ops
+    fake_ops.install(monkeypatch)
+    ref_layers, ref_breg = _ref("tensor.layers"), _ref("tensor.bregman")
+    import tensornetworksfork_b200 as tnb
+    rng = np.random.default_rng(7000 + seed)
+    n, r, F = int(rng.integers(2, 6)), int(rng.integers(2, 4)), int(rng.integers(2, 5))
+    C = int(rng.choice([1, 1, 2]))
+    N = int(rng.integers(50, 120))
+    X = rng.uniform(-1, 1, size=(N, F))
+    x = torch.tensor(np.concatenate([X, np.ones((N, 1))], 1))
+    y = torch.tensor(np.tanh(X @ rng.normal(size=(F, C))) + 0.1 * rng.normal(size=(N, C)))
+    mode = ["gradient", "per_node", "order_list", "order_tuple", "converge", "timeout"][seed % 6]
+    kw = dict(batch_size=int(rng.choice([-1, 19, 50])), num_swipes=int(rng.integers(1, 3)), lr=1.0, method="ridge_cholesky",
+              eps=float(rng.uniform(0.5, 2.0)), direction=str(rng.choice(["l2r", "r2l"])))
+    if mode == "gradient":
+        kw.update(method="gradient", lr=-float(rng.uniform(1e-4, 2e-3)), skip_second=bool(rng.integers(0, 2)))
+    elif mode == "per_node":
+        kw.update(eps=[float(v) for v in rng.uniform(0.3, 2.0, size=n)], eps_per_node=True, num_swipes=1, skip_second=bool(rng.integers(0, 2)))
+    elif mode == "timeout":
+        kw.update(timeout=0.0)
+    mseed = int(rng.integers(0, 1000))
+    pick = sorted(rng.choice(n, size=max(1, n - 1), replace=False).tolist())
+    split = int(rng.integers(1, n)) if n > 1 else 1
+    stop = int(rng.integers(1, 2 * n))
+    outs = []
+    for mod, breg in ((ref_layers, ref_breg), (tnb, tnb)):
+        layer = mod.TensorTrainLayer(n, r, F + 1, output_shape=C, constrict_bond=bool(seed % 2), seed=mseed)
+        tn = layer.tensor_network
+        k = dict(kw)
+        if mode == "order_list":
+            k["node_order"] = [tn.train_nodes[i] for i in pick]
+        elif mode == "order_tuple":
+            k["node_order"] = (tn.train_nodes[:split], tn.train_nodes[split:][::-1] or tn.train_nodes[:1])
+        elif mode == "converge":
+            calls = [0]
+
+            def crit(calls=calls):
+                calls[0] += 1
+                return calls[0] >= stop
+            k["convergence_criterion"] = crit
+        ev = []
+        ret = tn.accumulating_swipe(x, y, breg.SquareBregFunction(), loss_callback=lambda NS, nd, l: ev.append((NS, tn.train_nodes.index(nd), float(l))),
+                                    block_callback=lambda NS, nd: ev.append((NS, tn.train_nodes.index(nd), None)), **k)
+        outs.append((ret, ev, tn.forward(x, to_tensor=True).detach()))
+    (r_ret, r_ev, r_p), (m_ret, m_ev, m_p) = outs
+    assert m_ret == r_ret, (mode, kw)
+    assert [e[:2] for e in m_ev] == [e[:2] for e in r_ev], (mode, kw)
+    for a, b in zip(m_ev, r_ev):
+        assert (a[2] is None) == (b[2] is None)
+        if a[2] is not None:
+            assert abs(a[2] - b[2]) <= 1e-6 * max(1.0, abs(b[2])), (mode, kw, a, b)
+    assert float((m_p.reshape(r_p.shape) - r_p).norm() / max(float(r_p.norm()), 1e-12)) < 1e-6, (mode, kw)
