@@ -319,3 +319,48 @@ def test_random_driver_keywords_side_by_side(seed, monkeypatch):
         if a[2] is not None:
             assert abs(a[2] - b[2]) <= 1e-6 * max(1.0, abs(b[2])), (mode, kw, a, b)
     assert float((m_p.reshape(r_p.shape) - r_p).norm() / max(float(r_p.norm()), 1e-12)) < 1e-6, (mode, kw)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_external_core_changes_between_and_inside_sweeps(seed, monkeypatch):
+    """Cores changed behind the engine's back -- load_node_states in place / by replacement between sweeps on the SAME data
+    object (cached environments must be dropped), and a callback that rescales a core in the middle of a sweep -- side by side
+    with the reference, whose reset_stacks / set_input policy the engine replaces by identity + version stamps."""
+    import fake_ops
+    fake_ops.install(monkeypatch)
+    ref_layers, ref_breg = _ref("tensor.layers"), _ref("tensor.bregman")
+    import tensornetworksfork_b200 as tnb
+    rng = np.random.default_rng(8000 + seed)
+    n, r, F = int(rng.integers(2, 5)), int(rng.integers(2, 4)), int(rng.integers(2, 5))
+    N = int(rng.integers(50, 100))
+    X = rng.uniform(-1, 1, size=(N, F))
+    x = torch.tensor(np.concatenate([X, np.ones((N, 1))], 1))
+    xv = torch.tensor(np.concatenate([rng.uniform(-1, 1, size=(30, F)), np.ones((30, 1))], 1))
+    y = torch.tensor(np.tanh(X[:, :1]) + 0.1 * rng.normal(size=(N, 1)))
+    kw = dict(batch_size=-1 if seed % 2 else 33, num_swipes=1, lr=1.0, method="ridge_cholesky", eps=1.0)
+    scale = float(rng.uniform(0.5, 1.5))
+    which = int(rng.integers(0, n))
+    outs = []
+    for mod, breg in ((ref_layers, ref_breg), (tnb, tnb)):
+        layer = mod.TensorTrainLayer(n, r, F + 1, output_shape=1, constrict_bond=False, seed=seed)
+        tn = layer.tensor_network
+        ev = []
+        seen = [0]
+
+        def meddle(NS, node, layer=layer, tn=tn, seen=seen):
+            seen[0] += 1
+            ev.append(float(layer(xv).abs().sum()))                       # a foreign forward in the middle of the sweep
+            if seen[0] == 2:
+                tn.train_nodes[which].tensor = tn.train_nodes[which].tensor * scale    # replaced from outside
+
+        assert tn.accumulating_swipe(x, y, breg.SquareBregFunction(), block_callback=meddle, loss_callback=lambda NS, nd, l: ev.append(float(l)), **kw)
+        snap = layer.node_states()
+        assert tn.accumulating_swipe(x, y, breg.SquareBregFunction(), loss_callback=lambda NS, nd, l: ev.append(float(l)), **kw)
+        layer.load_node_states(snap, set_value=bool(seed % 2))            # back to the snapshot, in place or by replacement
+        assert tn.accumulating_swipe(x, y, breg.SquareBregFunction(), loss_callback=lambda NS, nd, l: ev.append(float(l)), **kw)
+        outs.append((ev, layer(x).detach()))
+    (r_ev, r_p), (m_ev, m_p) = outs
+    assert len(m_ev) == len(r_ev)
+    for a, b in zip(m_ev, r_ev):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (m_ev, r_ev)
+    assert float((m_p.reshape(r_p.shape) - r_p).norm() / float(r_p.norm())) < 1e-6
