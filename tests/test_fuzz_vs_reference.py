@@ -364,3 +364,63 @@ def test_external_core_changes_between_and_inside_sweeps(seed, monkeypatch):
     for a, b in zip(m_ev, r_ev):
         assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (m_ev, r_ev)
     assert float((m_p.reshape(r_p.shape) - r_p).norm() / float(r_p.norm())) < 1e-6
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_random_growing_flows_side_by_side(seed, monkeypatch):
+    """Topology changes between sweeps: the 2-site DMRG growth (grow_middle / block sweep / split_node, growing_DMRG.py:51-62)
+    and the conv-TT growth (grow_cart, image_convolution_growing_MNIST.py:84-103), random sizes, against the reference."""
+    import fake_ops
+    fake_ops.install(monkeypatch)
+    ref_layers, ref_breg = _ref("tensor.layers"), _ref("tensor.bregman")
+    import tensornetworksfork_b200 as tnb
+    rng = np.random.default_rng(6000 + seed)
+    N = int(rng.integers(60, 110))
+    outs = []
+    if seed % 2 == 0:
+        F, r = int(rng.integers(2, 5)), int(rng.integers(2, 5))
+        X = rng.uniform(-1, 1, size=(N, F))
+        x = torch.tensor(np.concatenate([X, np.ones((N, 1))], 1))
+        y = torch.tensor(np.tanh(X[:, :1] * X[:, 1:2]) + 0.1 * rng.normal(size=(N, 1)))
+        grows = int(rng.integers(1, 3))
+        for mod, breg in ((ref_layers, ref_breg), (tnb, tnb)):
+            torch.manual_seed(seed)
+            layer = mod.TensorTrainDMRGInfiLayer(r, F + 1, output_shape=1, constrict_bond=True)
+            ev = []
+            kw = dict(batch_size=-1, lr=1.0, method="ridge_cholesky", num_swipes=3, loss_callback=lambda NS, nd, l: ev.append(float(l)))
+            assert layer.tensor_network.accumulating_swipe(x, y, breg.SquareBregFunction(), eps=1.0, **kw)
+            for g in range(grows):
+                layer.grow_middle()
+                ev.append(float(layer(x).abs().sum()))
+                assert layer.tensor_network.accumulating_swipe(x, y, breg.SquareBregFunction(), eps=0.3, **kw)
+                node = layer.nodes[layer.num_carriages // 2]
+                err = layer.split_node(node.dim_labels[:2], node.dim_labels[-2:], r, err=1e-8, is_last=g == grows - 1)
+                ev.append(float(err))
+            outs.append((ev, layer(x).detach()))
+    else:
+        Q, T, r, CB = int(rng.integers(3, 6)), int(rng.integers(3, 5)), int(rng.integers(2, 4)), int(rng.integers(1, 3))
+        X = rng.uniform(-1, 1, size=(N, Q, T))
+        X[:, -1, :] = 0.0
+        X[:, :, -1] = 0.0
+        X[:, -1, -1] = 1.0
+        x = torch.tensor(X)
+        y = torch.tensor(np.eye(3)[rng.integers(0, 3, N)])
+        n0 = int(rng.integers(2, 4))          # (a single column under the cross-entropy loss raises inside the reference's own solve_system)
+        for mod, breg in ((ref_layers, ref_breg), (tnb, tnb)):
+            torch.manual_seed(seed)
+            layer = mod.TensorConvolutionTrainLayer(num_carriages=n0, bond_dim=r, num_patches=Q, patch_pixels=T, output_shape=2, convolution_bond=CB)
+            ev = []
+            kw = dict(batch_size=40, lr=1.0, method="ridge_exact", eps=1.0, eps_decay=0.7, num_swipes=1)
+            loss = breg.XEAutogradBregman(w=1.0)
+            assert layer.tensor_network.accumulating_swipe(x, y, loss, loss_callback=lambda NS, nd, l: ev.append(float(l)), **kw)
+            for g in range(2):
+                layer.grow_cart(r, CB) if g == 0 else layer.grow_cart()
+                ev.append(float(layer(x).abs().sum()))
+                assert layer.tensor_network.accumulating_swipe(x, y, loss, direction="r2l" if g == 0 else "l2r",
+                                                               loss_callback=lambda NS, nd, l: ev.append(float(l)), **kw)
+            outs.append((ev, layer(x).detach()))
+    (r_ev, r_p), (m_ev, m_p) = outs
+    assert len(m_ev) == len(r_ev)
+    for a, b in zip(m_ev, r_ev):
+        assert abs(a - b) <= 1e-6 * max(1.0, abs(b)), (m_ev, r_ev)
+    assert float((m_p.reshape(r_p.shape) - r_p).norm() / float(r_p.norm())) < 1e-6
