@@ -45,6 +45,8 @@ def env_update(env_in, x, core3, rows, cdiv=1, env_div=1, out=None):
     _unit_rows(out, "out")
     assert env_in is None or (env_in.dtype == torch.float64 and (rows - 1) // env_div < env_in.shape[0] and env_in.shape[1] >= core3.shape[0])
     assert core3.dtype == torch.float64 and core3.dim() == 3
+    assert env_in is not None or core3.shape[0] == 1            # tn_env_update: env_in == NULL requires r_in == 1
+    assert x.map_kind != real.MAP_SINCOS or core3.shape[1] == 2  # sin-cos map has f == 2
     phi = _rows(Factor(x.tensor, m=x.m, div=cdiv, map_kind=x.map_kind, col=x.col), rows)
     e = torch.ones(rows, 1, dtype=torch.float64) if env_in is None else env_in[torch.arange(rows) // env_div]
     res = torch.einsum("sa,sp,apb->sb", e, phi, core3)
@@ -221,6 +223,7 @@ def install(monkeypatch=None):
 
 def bmm(A, B, out=None, accumulate=False):
     assert out is None or out.is_contiguous()
+    assert 8 * (A.shape[-2] * A.shape[-1] + B.shape[-2] * B.shape[-1]) <= 200 * 1024   # tn_bmm: one sample's operands fit shared memory
     r = torch.matmul(A, B)
     if r.dim() == 2:
         r = r.unsqueeze(0)
@@ -238,6 +241,7 @@ def outer_rows(G, W, w=None, gdiv=1, out=None, accumulate=False):
     assert G.dim() == 2 and W.dim() == 2 and G.stride(1) == 1 and W.stride(1) == 1, (G.stride(), W.stride())
     _bare(w)
     assert out is None or out.is_contiguous()
+    assert 1 <= G.shape[1] <= 128, G.shape                      # tn_outer_rows: ra <= OR_MAXRA
     rows = W.shape[0]
     Gr = G[torch.arange(rows) // gdiv]
     if w is not None:
