@@ -179,7 +179,14 @@ __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_tota
     }
 }
 
-template <int SPLIT, int T>
+// PLANAR selects the layout of a raw-factor slot.  false: row-major, one Z row = TC_KC floats + 4 of padding (80 B), the layout all
+// measurements of round 1 were taken with.  true (opt-in, TN_TC_RAW_PLANAR=1, not yet run on hardware): four planes, one per
+// 4-sample piece, plane p holding 16 B per Z row at p * plane_stride + row * 16 with plane_stride = 32 (mod 128).  The round-1
+// ncu capture (profiles/r1_ncu_gram_tc_v6_hotspots.txt) attributes 6.1e9 of the kernel's 8.2e9 excessive shared-memory wavefronts to
+// the cp.async writes of the row-major layout (four consecutive threads write 64 contiguous bytes, the next four start 80 B on:
+// 3.7 wavefronts per ideal one); in the planar layout the eight 16-byte pieces of a quarter warp fall into eight different
+// 4-bank groups, and the operand loads of consecutive Z rows become contiguous.
+template <int SPLIT, int T, bool PLANAR = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gram_tc_kernel(TcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -194,7 +201,10 @@ gram_tc_kernel(TcParams p) {
     const uint32_t stage_bytes = 2 * T * a_tile_bytes + 2 * b_tile_bytes;
     const uint32_t z_rows = (uint32_t)(2 * mA + mB + mC);
     const uint32_t raw_rows = z_rows + 1;                      // + an all-zero row for the padding rows of the tiles
-    const uint32_t raw_bytes = raw_rows * TC_KCP * 4;
+    const uint32_t raw_bytes = raw_rows * TC_KCP * 4;          // slot pitch (the planar layout needs less and keeps the pitch)
+    const uint32_t plane_stride = ((raw_rows * 16 + 95) / 128) * 128 + 32;     // >= raw_rows * 16, = 32 (mod 128)
+    const uint32_t row_pitch = PLANAR ? 16u : (uint32_t)(TC_KCP * 4);          // bytes between two Z rows of a slot
+    const uint32_t piece_pitch = PLANAR ? plane_stride : 16u;                  // bytes between two 4-sample pieces of a Z row
     uint8_t* stage_base = smem_raw;
     uint8_t* raw_base = smem_raw + (size_t)NS * stage_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)TC_RAW_SLOTS * raw_bytes);
@@ -217,8 +227,15 @@ gram_tc_kernel(TcParams p) {
         mbar_init(acc_empty, TC_PROD_WARPS);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    for (int i = tid; i < TC_RAW_SLOTS * TC_KCP; i += TC_THREADS)   // the zero row of every raw slot
-        reinterpret_cast<float*>(raw_base + (size_t)(i / TC_KCP) * raw_bytes)[z_rows * TC_KCP + (i % TC_KCP)] = 0.f;
+    if (PLANAR) {
+        for (int i = tid; i < TC_RAW_SLOTS * TC_KC; i += TC_THREADS) {   // the zero row of every raw slot: 4 floats in each plane
+            const int slot = i / TC_KC, e = i % TC_KC;
+            reinterpret_cast<float*>(raw_base + (size_t)slot * raw_bytes + (size_t)(e >> 2) * plane_stride + (size_t)z_rows * 16)[e & 3] = 0.f;
+        }
+    } else {
+        for (int i = tid; i < TC_RAW_SLOTS * TC_KCP; i += TC_THREADS)   // the zero row of every raw slot
+            reinterpret_cast<float*>(raw_base + (size_t)(i / TC_KCP) * raw_bytes)[z_rows * TC_KCP + (i % TC_KCP)] = 0.f;
+    }
     if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
     tc_fence_before();
     __syncthreads();
@@ -285,7 +302,7 @@ gram_tc_kernel(TcParams p) {
         const double unscale = ldexp(1.0, 2 * (tc_exponent(p.amax[0]) + tc_exponent(p.amax[1]) + tc_exponent(p.amax[2])) +
                                               tc_exponent(p.amax[3]));
         const uint32_t raw_s = smem_u32(raw_base);
-        const uint32_t zero_row = z_rows * TC_KCP * 4;                 // byte offset of the zero row in a raw slot
+        const uint32_t zero_row = z_rows * row_pitch;                  // byte offset of the zero row in a raw slot
         // -- rows of the operand tiles this thread synthesises (fixed for the kernel)
         uint32_t usrc[4] = {zero_row, zero_row, zero_row, zero_row};   // byte offsets of w*fa[ia], fa[ja], fb[ib], fb[jb]
         int u_tile = 0, u_row = pt & 127, u_c0 = 0;
@@ -299,18 +316,18 @@ gram_tc_kernel(TcParams p) {
                 int ia, ja, ib, jb;
                 pair_decode(qa, mA, ia, ja);
                 pair_decode(qb, mB, ib, jb);
-                usrc[0] = (uint32_t)(ia * TC_KCP * 4);
-                usrc[1] = (uint32_t)((mA + ja) * TC_KCP * 4);
-                usrc[2] = (uint32_t)((2 * mA + ib) * TC_KCP * 4);
-                usrc[3] = (uint32_t)((2 * mA + jb) * TC_KCP * 4);
+                usrc[0] = (uint32_t)ia * row_pitch;
+                usrc[1] = (uint32_t)(mA + ja) * row_pitch;
+                usrc[2] = (uint32_t)(2 * mA + ib) * row_pitch;
+                usrc[3] = (uint32_t)(2 * mA + jb) * row_pitch;
             }
         }
         uint32_t vsrc[2] = {zero_row, zero_row};
         if (pt < BN && v0 + pt < p.nC) {
             int ic, jc;
             pair_decode(v0 + pt, mC, ic, jc);
-            vsrc[0] = (uint32_t)((2 * mA + mB + ic) * TC_KCP * 4);
-            vsrc[1] = (uint32_t)((2 * mA + mB + jc) * TC_KCP * 4);
+            vsrc[0] = (uint32_t)(2 * mA + mB + ic) * row_pitch;
+            vsrc[1] = (uint32_t)(2 * mA + mB + jc) * row_pitch;
         }
         const uint32_t udst = (uint32_t)u_tile * 2 * a_tile_bytes + (uint32_t)u_row * 16 + (uint32_t)u_c0 * (TC_M * 16);
         const uint32_t vdst = 2 * T * a_tile_bytes + (uint32_t)pt * 16;
@@ -325,7 +342,7 @@ gram_tc_kernel(TcParams p) {
                 const uint32_t dst0 = raw_s + (uint32_t)(chunk % TC_RAW_SLOTS) * raw_bytes;
                 for (int pc = pt; pc < npieces; pc += TC_PROD) {
                     const int row = pc >> 2, part = pc & 3;
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)row * (TC_KCP * 4) + part * 16),
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst0 + (uint32_t)row * row_pitch + (uint32_t)part * piece_pitch),
                                  "l"(src0 + (int64_t)row * p.zpitch + part * 4) : "memory");
                 }
             }
@@ -350,7 +367,7 @@ gram_tc_kernel(TcParams p) {
                 float4 x0[U_NC], x1[U_NC], x2[U_NC], x3[U_NC];
 #pragma unroll
                 for (int cc = 0; cc < U_NC; ++cc) {
-                    const uint32_t o = (uint32_t)(u_c0 + cc) * 16;
+                    const uint32_t o = (uint32_t)(u_c0 + cc) * piece_pitch;
                     x0[cc] = lds128(rb + usrc[0] + o);
                     x1[cc] = lds128(rb + usrc[1] + o);
                     x2[cc] = lds128(rb + usrc[2] + o);
@@ -367,8 +384,8 @@ gram_tc_kernel(TcParams p) {
                 float4 y0[TC_KC / 4], y1[TC_KC / 4];
 #pragma unroll
                 for (int cc = 0; cc < TC_KC / 4; ++cc) {
-                    y0[cc] = lds128(rb + vsrc[0] + cc * 16);
-                    y1[cc] = lds128(rb + vsrc[1] + cc * 16);
+                    y0[cc] = lds128(rb + vsrc[0] + (uint32_t)cc * piece_pitch);
+                    y1[cc] = lds128(rb + vsrc[1] + (uint32_t)cc * piece_pitch);
                 }
 #pragma unroll
                 for (int cc = 0; cc < TC_KC / 4; ++cc) {
@@ -806,12 +823,17 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     p.rows_per_split = ceil_div64(ceil_div64(p.zpitch, ks), TC_KC) * TC_KC;
     ks = ceil_div64(p.zpitch, p.rows_per_split);
     using Kern = void (*)(TcParams);
-    static const Kern kerns[2][2] = {{gram_tc_kernel<0, 1>, gram_tc_kernel<0, 2>}, {gram_tc_kernel<1, 1>, gram_tc_kernel<1, 2>}};
-    static size_t configured[2][2] = {};
-    Kern k = kerns[p.split][p.T - 1];
-    if (smem > configured[p.split][p.T - 1]) {
+    static const Kern kerns[2][2][2] = {{{gram_tc_kernel<0, 1, false>, gram_tc_kernel<0, 2, false>},
+                                         {gram_tc_kernel<1, 1, false>, gram_tc_kernel<1, 2, false>}},
+                                        {{gram_tc_kernel<0, 1, true>, gram_tc_kernel<0, 2, true>},
+                                         {gram_tc_kernel<1, 1, true>, gram_tc_kernel<1, 2, true>}}};
+    static size_t configured[2][2][2] = {};
+    // planar raw slots: opt-in until measured (the slot pitch of the row-major layout, 80 B per Z row, covers 4 * plane_stride)
+    const int planar = (getenv("TN_TC_RAW_PLANAR") && 4 * ((((size_t)(z_rows + 1) * 16 + 95) / 128) * 128 + 32) <= (size_t)(z_rows + 1) * TC_KCP * 4) ? 1 : 0;
+    Kern k = kerns[planar][p.split][p.T - 1];
+    if (smem > configured[planar][p.split][p.T - 1]) {
         TN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[p.split][p.T - 1] = smem;
+        configured[planar][p.split][p.T - 1] = smem;
     }
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)ks);
     k<<<grid, TC_THREADS, smem, st>>>(p);

@@ -62,3 +62,22 @@ def test_cumsum_matrix_free_sweeps_gpu():
     assert core_err < 1e-6 and loss_err < 1e-7, (core_err, loss_err)
     core_err, loss_err = kc.run_case("krylov_cumsum_cg", "cuda", scipy_object=True)
     assert core_err < 5e-4 and loss_err < 5e-5, (core_err, loss_err)
+
+
+@pytest.mark.xfail(strict=False, reason="opt-in kernel variant written without GPU access at the end of round 1: not yet run on a B200")
+@pytest.mark.parametrize("shape", [(64, 2, 2, 2, 1), (5000, 6, 9, 6, 1), (20000, 24, 2, 24, 1), (3000, 38, 6, 38, 1), (2500, 38, 29, 1, 1),
+                                   (1200, 5, 3, 4, 3)])
+def test_tc_gram_planar_raw_slots_match_the_default_layout(shape, monkeypatch):
+    """TN_TC_RAW_PLANAR=1 (gram_tc.cu: planar layout of the raw-factor ring, conflict-free cp.async writes) must give the same M as
+    the row-major layout -- only shared-memory addresses change, not the arithmetic or its order -- or, where the factors are too
+    small for the planar slot, fall back to it."""
+    from tensornetworksfork_b200 import ops
+    import test_gpu_gram_tc as tg
+    fa, fb, fc, w, rows = tg.make(*shape, seed=sum(shape))
+    monkeypatch.delenv("TN_TC_RAW_PLANAR", raising=False)
+    ref = ops.gram(ops.GRAM_TF32X3, fa, fb, fc, w, rows)
+    monkeypatch.setenv("TN_TC_RAW_PLANAR", "1")
+    got = ops.gram(ops.GRAM_TF32X3, fa, fb, fc, w, rows)
+    torch.cuda.synchronize()
+    # fp64 atomics of different CTAs land in a different order from run to run: compare to rounding, not bit for bit
+    assert float((got - ref).norm() / ref.norm()) < 1e-12
