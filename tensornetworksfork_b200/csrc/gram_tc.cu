@@ -56,6 +56,7 @@ struct TcParams {
     int nstages;
     int split;        // 1 = 3xTF32, 0 = TF32
     int flush_rows;   // rows accumulated in fp32 before a drain to fp64 (multiple of TC_KC)
+    int planar;       // 1: Z is staged piece-planar, Z[((s/16)*4 + (s%16)/4) * z_rows + row][s%4] (see gram_tc_kernel<.., PLANAR>)
 };
 
 // ---- range scaling.  The operands are staged in fp32; factors of long chains span hundreds of binades (environments of a
@@ -99,7 +100,7 @@ __device__ __forceinline__ int tc_exponent(unsigned long long bits) {
 // ---- pre-pass: factors (fp64, sample-major, possibly mapped / shared by V rows) -> Z (fp32, feature-major)
 __global__ void __launch_bounds__(256)
 tc_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict__ w, int64_t rows, float* __restrict__ Z,
-                int64_t zpitch, const unsigned long long* __restrict__ amax) {
+                int64_t zpitch, const unsigned long long* __restrict__ amax, int planar = 0) {
     __shared__ float tile[32][33];
     const double sa = ldexp(1.0, -tc_exponent(amax[0])), sb = ldexp(1.0, -tc_exponent(amax[1]));
     const double sc = ldexp(1.0, -tc_exponent(amax[2])), sw = ldexp(1.0, -tc_exponent(amax[3]));
@@ -128,8 +129,13 @@ tc_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict_
         const int64_t s = s0 + tx;
         if (i < msum && s < zpitch) {
             const float v = tile[tx][c];
-            Z[(int64_t)(mA + i) * zpitch + s] = v;
-            if (i < mA) Z[(int64_t)i * zpitch + s] = (s < rows) ? v * (float)((w ? w[s] : 1.0) * sw) : 0.f;
+            const int64_t zr = 2 * mA + mB + mC;                         // Z rows
+            // row-major: Z[row][s];  piece-planar: the 16 bytes (4 samples) of every row of one piece are contiguous
+            auto at = [&](int64_t row) -> int64_t {
+                return planar ? ((((s >> 4) * 4 + ((s >> 2) & 3)) * zr + row) * 4 + (s & 3)) : (row * zpitch + s);
+            };
+            Z[at(mA + i)] = v;
+            if (i < mA) Z[at(i)] = (s < rows) ? v * (float)((w ? w[s] : 1.0) * sw) : 0.f;
         }
     }
 }
@@ -181,11 +187,14 @@ __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_tota
 
 // PLANAR selects the layout of a raw-factor slot.  false: row-major, one Z row = TC_KC floats + 4 of padding (80 B), the layout all
 // measurements of round 1 were taken with.  true (opt-in, TN_TC_RAW_PLANAR=1, not yet run on hardware): four planes, one per
-// 4-sample piece, plane p holding 16 B per Z row at p * plane_stride + row * 16 with plane_stride = 32 (mod 128).  The round-1
-// ncu capture (profiles/r1_ncu_gram_tc_v6_hotspots.txt) attributes 6.1e9 of the kernel's 8.2e9 excessive shared-memory wavefronts to
-// the cp.async writes of the row-major layout (four consecutive threads write 64 contiguous bytes, the next four start 80 B on:
-// 3.7 wavefronts per ideal one); in the planar layout the eight 16-byte pieces of a quarter warp fall into eight different
-// 4-bank groups, and the operand loads of consecutive Z rows become contiguous.
+// 4-sample piece, plane p holding 16 B per Z row at p * plane_stride + row * 16 with plane_stride = 32 (mod 128), filled by FOUR
+// BULK COPIES (cp.async.bulk, one per plane, issued by one thread, completion on an mbarrier) from a staging buffer that the
+// pre-pass writes piece-planar.  Why: the round-1 ncu capture (profiles/r1_ncu_gram_tc_v6_hotspots.txt) attributes 6.1e9 of the
+// kernel's 8.2e9 excessive shared-memory wavefronts to the cp.async (LDGSTS) writes of the ring -- 3.7 wavefronts per ideal one
+// here and 8 per ideal one in syrk_tc_kernel, whose LDS of the very same addresses is conflict free: LDGSTS spends about one
+// shared-memory wavefront per 32-byte global sector, whatever the lanes' bank pattern.  The bulk-copy engine writes whole lines,
+// takes the fill off the LSU pipe and off the producers' instruction stream, and the operand loads of consecutive Z rows become
+// contiguous in the planar slot.
 template <int SPLIT, int T, bool PLANAR = false>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gram_tc_kernel(TcParams p) {
@@ -213,6 +222,7 @@ gram_tc_kernel(TcParams p) {
     uint64_t* acc_full = bars + 2 * NS;
     uint64_t* acc_empty = bars + 2 * NS + 1;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
+    uint64_t* raw_full = bars + 2 * NS + 3;      // [TC_RAW_SLOTS], PLANAR only (the launcher adds their bytes)
 
     const uint32_t tmem_cols_needed = (uint32_t)(T * BN);
     uint32_t tmem_cols = 32;
@@ -225,6 +235,8 @@ gram_tc_kernel(TcParams p) {
         }
         mbar_init(acc_full, 1);
         mbar_init(acc_empty, TC_PROD_WARPS);
+        if (PLANAR)
+            for (int i = 0; i < TC_RAW_SLOTS; ++i) mbar_init(&raw_full[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (PLANAR) {
@@ -337,6 +349,23 @@ gram_tc_kernel(TcParams p) {
         // -- cp.async plan: 16-byte pieces (4 samples of one Z row) of a chunk, spread over the producer threads
         const int npieces = (int)z_rows * (TC_KC / 4);
         auto issue_chunk = [&](int64_t chunk) {
+            if (PLANAR) {
+                // one thread: expect the bytes of the four planes on the slot's barrier, then one bulk copy per plane
+                if (chunk < nchunks && pt == 0) {
+                    const int slot = (int)(chunk % TC_RAW_SLOTS);
+                    const uint32_t bar = smem_u32(&raw_full[slot]);
+                    const uint32_t plane_bytes = z_rows * 16;
+                    const uint32_t dst0 = raw_s + (uint32_t)slot * raw_bytes;
+                    const float* src0 = p.Z + ((k_begin / TC_KC + chunk) * 4) * (int64_t)z_rows * 4;
+                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(4 * plane_bytes) : "memory");
+#pragma unroll
+                    for (int part = 0; part < 4; ++part)
+                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                     ::"r"(dst0 + (uint32_t)part * plane_stride), "l"(src0 + (int64_t)part * z_rows * 4), "r"(plane_bytes), "r"(bar)
+                                     : "memory");
+                }
+                return;
+            }
             if (chunk < nchunks) {
                 const float* src0 = p.Z + k_begin + chunk * TC_KC;
                 const uint32_t dst0 = raw_s + (uint32_t)(chunk % TC_RAW_SLOTS) * raw_bytes;
@@ -356,9 +385,10 @@ gram_tc_kernel(TcParams p) {
         uint32_t ph = 0;
         int64_t in_window = 0;
         for (int64_t c = 0; c < nchunks; ++c) {
-            asm volatile("cp.async.wait_group 1;" ::: "memory");       // this thread's pieces of chunk c have landed
+            if (!PLANAR) asm volatile("cp.async.wait_group 1;" ::: "memory");       // this thread's pieces of chunk c have landed
             asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");  // everyone's have; chunk c-1 is fully consumed
             issue_chunk(c + 2);                                          // reuses the slot chunk c-1 occupied
+            if (PLANAR) mbar_wait(&raw_full[rs], (uint32_t)((c / TC_RAW_SLOTS) & 1));   // every reader waits: the bulk copies of chunk c landed
             if (lane == 0) mbar_wait(&empty[s], ph ^ 1);                 // first pass over the ring returns immediately
             __syncwarp();
             const uint32_t rb = raw_s + (uint32_t)rs * raw_bytes;
@@ -723,6 +753,7 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     p.nB = npairs(B.m);
     p.nC = npairs(C.m);
     p.split = (mode == 2) ? 1 : 0;
+    p.planar = 0;
     p.flush_rows = TC_FLUSH_ROWS_DEFAULT;
     if (const char* e = getenv("TN_TC_FLUSH_ROWS")) {
         const int v = atoi(e);
@@ -775,7 +806,12 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
         tc_absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, B, C, w, rows, amax);
         TN_LAUNCH_CHECK();
         dim3 grid((unsigned)ceil_div64(p.zpitch, 32), (unsigned)ceil_div64(A.m + B.m + C.m, 32));
-        tc_stage_kernel<<<grid, 256, 0, st>>>(A, B, C, w, rows, Z, p.zpitch, amax);
+        // planar raw slots + bulk-copy fill: opt-in until measured.  Needs the four planes to fit the slot pitch of the row-major
+        // layout (80 B per Z row) and 32 more bytes of shared memory for the slots' barriers; the CTA-pair kernel stays row-major.
+        p.planar = (getenv("TN_TC_RAW_PLANAR") && !getenv("TN_TC_PAIR") &&
+                    4 * ((((size_t)(z_rows + 1) * 16 + 95) / 128) * 128 + 32) <= (size_t)(z_rows + 1) * TC_KCP * 4 &&
+                    smem + 32 <= 227 * 1024) ? 1 : 0;
+        tc_stage_kernel<<<grid, 256, 0, st>>>(A, B, C, w, rows, Z, p.zpitch, amax, p.planar);
         TN_LAUNCH_CHECK();
     }
     // CTA-pair kernel (opt-in, TN_TC_PAIR=1).  Measured on the config-5a middle site (131 072 rows, tools/tc_pair_probe.py):
@@ -828,15 +864,15 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
                                         {{gram_tc_kernel<0, 1, true>, gram_tc_kernel<0, 2, true>},
                                          {gram_tc_kernel<1, 1, true>, gram_tc_kernel<1, 2, true>}}};
     static size_t configured[2][2][2] = {};
-    // planar raw slots: opt-in until measured (the slot pitch of the row-major layout, 80 B per Z row, covers 4 * plane_stride)
-    const int planar = (getenv("TN_TC_RAW_PLANAR") && 4 * ((((size_t)(z_rows + 1) * 16 + 95) / 128) * 128 + 32) <= (size_t)(z_rows + 1) * TC_KCP * 4) ? 1 : 0;
+    const int planar = p.planar;
+    const size_t smem_k = smem + (planar ? 32 : 0);          // + the three barriers of the raw slots
     Kern k = kerns[planar][p.split][p.T - 1];
-    if (smem > configured[planar][p.split][p.T - 1]) {
-        TN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[planar][p.split][p.T - 1] = smem;
+    if (smem_k > configured[planar][p.split][p.T - 1]) {
+        TN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k));
+        configured[planar][p.split][p.T - 1] = smem_k;
     }
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)ks);
-    k<<<grid, TC_THREADS, smem, st>>>(p);
+    k<<<grid, TC_THREADS, smem_k, st>>>(p);
     TN_LAUNCH_CHECK();
     TN_CUDA(cudaFreeAsync(Z, st));
     return TN_OK;
