@@ -81,3 +81,16 @@ def test_tc_gram_planar_raw_slots_match_the_default_layout(shape, monkeypatch):
     torch.cuda.synchronize()
     # fp64 atomics of different CTAs land in a different order from run to run: compare to rounding, not bit for bit
     assert float((got - ref).norm() / ref.norm()) < 1e-12
+
+
+@pytest.mark.xfail(strict=False, reason="full-size recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
+@pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3"])
+def test_baseline_config1_full_size_gpu(gram_mode):
+    """BASELINE config 1 at full size against tests/golden/cfg1_full.npz (recorded from the unmodified reference): the first two
+    half-sweeps (ridge 0.075, 2.8e-3) to rounding / to the 3xTF32 bound, the third (1e-4) loosely; beyond that the reference's own
+    trajectory is chaotic and only the level of the final loss is compared.  CPU twin: test_host_sweep_cpu.py."""
+    import cfg1_case as c1
+    loss_err, pred_err, core_err = c1.run("cuda", gram_mode=gram_mode)
+    tight = 1e-9 if gram_mode == "fp64" else 1e-5
+    assert loss_err[:5].max() < tight and loss_err[5:7].max() < 1e-3, loss_err
+    assert loss_err[-1] < 0.2, loss_err

@@ -163,3 +163,15 @@ def test_gradient_method_sample_sharded_world2_gloo(tmp_path):
     for r in (0, 1):
         z = np.load(tmp_path / f"rank{r}.npz")
         assert float(z["core_err"]) < 1e-12 and float(z["loss_err"]) < 1e-12, (r, float(z["core_err"]), float(z["loss_err"]))
+
+
+def test_baseline_config1_full_size_against_reference_recording(monkeypatch):
+    """BASELINE config 1 at full size (N = 4177, 8 features + bias, 3 cores, rank 6; the call of default_train.py:101-129 with its
+    own epsilon list 0.075 ... 7e-12) against a recording of the unmodified reference.  The schedule drives the ridge to 1e-11, where
+    the reference's own trajectory is chaotic: the first two half-sweeps agree to rounding, the third to
+    1e-8, and after that only the level of the loss is comparable."""
+    import cfg1_case as c1
+    fake_ops.install(monkeypatch)
+    loss_err, pred_err, core_err = c1.run("cpu")
+    assert loss_err[:5].max() < 1e-12 and loss_err[5:7].max() < 1e-8, loss_err
+    assert loss_err.max() < 0.2 and loss_err[-1] < 0.05, loss_err
