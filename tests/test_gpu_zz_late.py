@@ -94,3 +94,14 @@ def test_baseline_config1_full_size_gpu(gram_mode):
     tight = 1e-9 if gram_mode == "fp64" else 1e-5
     assert loss_err[:5].max() < tight and loss_err[5:7].max() < 1e-3, loss_err
     assert loss_err[-1] < 0.2, loss_err
+
+
+@pytest.mark.xfail(strict=False, reason="full-size recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
+@pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3"])
+def test_baseline_config2_full_size_gpu(gram_mode):
+    """BASELINE config 2 at full size (CPD rank 100, 20640 x 9, 5 factors, two sweeps with the wrapper's ridge schedule 1.0 * 0.5^NS)
+    against tests/golden/cfg2_full.npz, recorded from the unmodified reference: all 17 per-update losses and the final prediction."""
+    import cfg2_case as c2
+    loss_err, pred_err = c2.run("cuda", gram_mode=gram_mode)
+    tol = 1e-7 if gram_mode == "fp64" else 1e-4
+    assert loss_err.max() < tol and pred_err < 10 * tol, (loss_err, pred_err)

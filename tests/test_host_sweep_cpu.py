@@ -175,3 +175,18 @@ def test_baseline_config1_full_size_against_reference_recording(monkeypatch):
     loss_err, pred_err, core_err = c1.run("cpu")
     assert loss_err[:5].max() < 1e-12 and loss_err[5:7].max() < 1e-8, loss_err
     assert loss_err.max() < 0.2 and loss_err[-1] < 0.05, loss_err
+
+
+def test_baseline_config2_full_size_fixture_and_first_loss(monkeypatch):
+    """BASELINE config 2 at full size (CPD rank 100, N = 20640, 5 factors; recorded from the unmodified reference on its authors'
+    einsum path).  The full sweep runs on the GPU (tests/test_gpu_zz_late.py); here: the fixture, the regenerated data, identical
+    initial factors for the same seed, and the loss the first update reports (mean of per-minibatch means at the initial factors)."""
+    import cfg2_case as c2
+    from tensornetworksfork_b200.tensor.network import batch_mean_of_means
+    fake_ops.install(monkeypatch)
+    z, X, y = c2.load()
+    assert z["trace"].shape == (17, 3) and bool(z["ok"])
+    layer = tnb.CPDLayer(c2.FACTORS, c2.RANK, c2.F + 1, output_shape=(1,), seed=42)
+    pred = layer.tensor_network.forward(torch.tensor(X), to_tensor=True)
+    loss0 = float(batch_mean_of_means((pred.reshape(-1, 1) - torch.tensor(y)) ** 2, 512))
+    assert abs(loss0 - z["trace"][0, 2]) <= 1e-12 * abs(z["trace"][0, 2]), (loss0, z["trace"][0, 2])

@@ -56,7 +56,8 @@ __version__ = "3.3.0"
 
 def contract_path(*args, **kwargs):
     n = sum(1 for a in args[1:] if hasattr(a, "shape")) if isinstance(args[0], str) else len(args) // 2
-    path = [(1, 2), (0, 1)] if n == 3 else [tuple(range(n))]
+    # three operands = the Gram einsum (J*, J, H): (J H) first, as opt_einsum would choose; otherwise left to right, pairwise
+    path = [(1, 2), (0, 1)] if n == 3 else [(0, 1)] * max(n - 1, 1)
     return path, None
 '''
 
