@@ -105,3 +105,12 @@ def test_baseline_config2_full_size_gpu(gram_mode):
     loss_err, pred_err = c2.run("cuda", gram_mode=gram_mode)
     tol = 1e-7 if gram_mode == "fp64" else 1e-4
     assert loss_err.max() < tol and pred_err < 10 * tol, (loss_err, pred_err)
+
+
+@pytest.mark.xfail(strict=False, reason="recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
+def test_baseline_config3_chain_gpu():
+    """BASELINE config 3's 90-site chain (sin-cos map, rank 24, QR re-gauge) on a 4096-row subsample, one full sweep = 179 updates,
+    against tests/golden/cfg3_chain90.npz recorded from the unmodified reference; fused feature map (what TNMLRegressor passes)."""
+    import cfg3_case as c3
+    loss_err, pred_err = c3.run("cuda")
+    assert loss_err.max() < 1e-6 and pred_err < 1e-5, (loss_err.max(), pred_err)

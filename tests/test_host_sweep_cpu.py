@@ -190,3 +190,14 @@ def test_baseline_config2_full_size_fixture_and_first_loss(monkeypatch):
     pred = layer.tensor_network.forward(torch.tensor(X), to_tensor=True)
     loss0 = float(batch_mean_of_means((pred.reshape(-1, 1) - torch.tensor(y)) ** 2, 512))
     assert abs(loss0 - z["trace"][0, 2]) <= 1e-12 * abs(z["trace"][0, 2]), (loss0, z["trace"][0, 2])
+
+
+@pytest.mark.parametrize("fused_map", [True, False])
+def test_baseline_config3_chain_first_updates(fused_map, monkeypatch):
+    """BASELINE config 3's full chain (90 sites, sin-cos map, rank 24, QR re-gauge after every update, models/tnml.py:149,218-227) on a
+    4096-row subsample, against a recording of the unmodified reference: the first 14 updates of the sweep (the bonds grow
+    1, 2, 4, 8, 16, 24, ...), with the fused feature map and with 90 pre-mapped tensors.  The whole sweep (179 updates) is a GPU test."""
+    import cfg3_case as c3
+    fake_ops.install(monkeypatch)
+    loss_err, _ = c3.run("cpu", max_updates=14, fused_map=fused_map)
+    assert loss_err.max() < 1e-12, loss_err
