@@ -114,3 +114,15 @@ def test_baseline_config3_chain_gpu():
     import cfg3_case as c3
     loss_err, pred_err = c3.run("cuda")
     assert loss_err.max() < 1e-6 and pred_err < 1e-5, (loss_err.max(), pred_err)
+
+
+@pytest.mark.xfail(strict=False, reason="recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
+@pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3"])
+def test_baseline_config5b_chain_gpu(gram_mode):
+    """BASELINE config 5b's chain (28 sites, polynomial degree 5, rank 38, QR re-gauge, P up to 8664 -- with 'tf32x3' the mixed
+    tensor-core solve is on the path) on a 2048-row subsample, one sweep = 55 updates, against tests/golden/cfg5b_chain28.npz
+    recorded from the unmodified reference."""
+    import cfg5b_case as c5
+    loss_err, pred_err = c5.run("cuda", gram_mode=gram_mode)
+    tol = 1e-6 if gram_mode == "fp64" else 1e-4
+    assert loss_err.max() < tol and pred_err < 10 * tol, (loss_err.max(), pred_err)

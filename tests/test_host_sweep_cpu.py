@@ -216,3 +216,13 @@ def test_baseline_configs_full_recordings_on_standin_kernels(which, monkeypatch)
         import cfg3_case as c3
         loss_err, pred_err = c3.run("cpu")
     assert loss_err.max() < 1e-10 and pred_err < 1e-9, (loss_err.max(), pred_err)
+
+
+def test_baseline_config5b_chain_first_updates(monkeypatch):
+    """BASELINE config 5 in its TNML reading (28 sites, polynomial basis of degree 5 evaluated inside the kernels, rank 38, QR re-gauge;
+    local systems up to P = 8664) on a 2048-row subsample against a recording of the unmodified reference: the first three updates
+    (bonds 1, 6, 36, 38) here, the whole sweep of 55 updates in the GPU twin."""
+    import cfg5b_case as c5
+    fake_ops.install(monkeypatch)
+    loss_err, _ = c5.run("cpu", max_updates=3)
+    assert loss_err.max() < 1e-12, loss_err
