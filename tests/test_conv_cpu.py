@@ -155,3 +155,13 @@ def test_conv_sample_sharded_lanczos_world2_gloo(tmp_path):
         assert np.array_equal(r0[f"core{i}"], r1[f"core{i}"]), "ranks diverged"
         assert gu.relerr(r0[f"core{i}"], fx["updates"][-1]["after"][i]) < 1e-7
     assert np.max(np.abs(r0["losses"] - fx["losses"])) < 1e-9
+
+
+def test_baseline_config4b_full_model_size_against_reference_recording(monkeypatch):
+    """BASELINE config 4 in its conv-TT reading at full model size (50 patches x 17 pixels, r = 38, CB = 4, 9 logits; the middle patch
+    core has 72 200 parameters) under scipy_swipe(minres), 256 rows, against a recording of the unmodified reference: same initial
+    cores from the same seed, the six per-node losses and the prediction."""
+    import cfg4b_case as c4
+    fake_ops.install(monkeypatch)
+    loss_err, pred_err = c4.run("cpu")
+    assert loss_err.max() < 1e-9 and pred_err < 1e-9, (loss_err, pred_err)

@@ -126,3 +126,12 @@ def test_baseline_config5b_chain_gpu(gram_mode):
     loss_err, pred_err = c5.run("cuda", gram_mode=gram_mode)
     tol = 1e-6 if gram_mode == "fp64" else 1e-4
     assert loss_err.max() < tol and pred_err < 10 * tol, (loss_err.max(), pred_err)
+
+
+@pytest.mark.xfail(strict=False, reason="recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
+def test_baseline_config4b_full_model_size_gpu():
+    """BASELINE config 4b at full model size (r = 38, CB = 4, 72 200-parameter patch core) under scipy_swipe(minres) against
+    tests/golden/cfg4b_shape.npz recorded from the unmodified reference; CPU twin in test_conv_cpu.py (exact losses, 7e-16)."""
+    import cfg4b_case as c4
+    loss_err, pred_err = c4.run("cuda")
+    assert loss_err.max() < 1e-5 and pred_err < 1e-4, (loss_err, pred_err)        # float32 Krylov recurrences on the host
