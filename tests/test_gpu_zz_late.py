@@ -135,3 +135,17 @@ def test_baseline_config4b_full_model_size_gpu():
     import cfg4b_case as c4
     loss_err, pred_err = c4.run("cuda")
     assert loss_err.max() < 1e-5 and pred_err < 1e-4, (loss_err, pred_err)        # float32 Krylov recurrences on the host
+
+
+@pytest.mark.xfail(strict=False, reason="recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
+@pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3"])
+def test_baseline_config5a_gram_fingerprint_gpu(gram_mode):
+    """The north-star shape (5 cores, rank 38, 28 features + bias): the dense 41 876 x 41 876 system of the middle core, expanded from
+    the unique entries the Gram kernel accumulates (fp64 DMMA / tcgen05 3xTF32), against b, diag(A), A v and the Frobenius norm of the
+    reference's own get_A_b (tests/golden/cfg5a_gram.npz).  14 GB for A."""
+    import cfg5a_case as c5
+    b_err, diag_err, av_err, fro_err, asym = c5.dense("cuda", gram_mode)
+    tol = 1e-12 if gram_mode == "fp64" else 3e-5
+    assert b_err < 1e-12 and diag_err < tol and av_err < tol and fro_err < tol and asym == 0.0, (b_err, diag_err, av_err, fro_err, asym)
+    mf = c5.matrix_free("cuda")
+    assert max(mf) < 1e-12, mf

@@ -230,3 +230,13 @@ def test_baseline_config5b_chain_first_updates(monkeypatch):
     fake_ops.install(monkeypatch)
     loss_err, _ = c5.run("cpu", max_updates=3)
     assert loss_err.max() < 1e-12, loss_err
+
+
+def test_baseline_config5a_gram_fingerprint_matrix_free(monkeypatch):
+    """BASELINE config 5a's local problem at the middle core (P = 38 * 29 * 38 = 41 876) against a fingerprint of the reference's own
+    get_A_b on a 512-row minibatch: prediction, per-row loss, b, and A v for a seeded v -- with A v = J^T diag(w) J v from the three
+    Kronecker factors the engine hands its kernels (the 14 GB matrix itself is expanded and checked in the GPU twin)."""
+    import cfg5a_case as c5
+    fake_ops.install(monkeypatch)
+    pred_err, loss_err, b_err, av_err = c5.matrix_free("cpu")
+    assert pred_err < 1e-13 and loss_err < 1e-13 and b_err < 1e-13 and av_err < 1e-13, (pred_err, loss_err, b_err, av_err)
