@@ -146,6 +146,6 @@ def test_baseline_config5a_gram_fingerprint_gpu(gram_mode):
     import cfg5a_case as c5
     b_err, diag_err, av_err, fro_err, asym = c5.dense("cuda", gram_mode)
     tol = 1e-12 if gram_mode == "fp64" else 3e-5
-    assert b_err < 1e-12 and diag_err < tol and av_err < tol and fro_err < tol and asym == 0.0, (b_err, diag_err, av_err, fro_err, asym)
+    assert b_err < 1e-12 and diag_err < tol and av_err < tol and fro_err < tol and asym < 1e-16, (b_err, diag_err, av_err, fro_err, asym)
     mf = c5.matrix_free("cuda")
     assert max(mf) < 1e-12, mf
