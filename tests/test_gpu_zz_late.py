@@ -149,3 +149,12 @@ def test_baseline_config5a_gram_fingerprint_gpu(gram_mode):
     assert b_err < 1e-12 and diag_err < tol and av_err < tol and fro_err < tol and asym < 1e-16, (b_err, diag_err, av_err, fro_err, asym)
     mf = c5.matrix_free("cuda")
     assert max(mf) < 1e-12, mf
+
+
+@pytest.mark.xfail(strict=False, reason="recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
+def test_baseline_config4a_local_size_chain_gpu():
+    """BASELINE config 4a at its full local size (rank 38, 9 logits, P up to 2888) on a 16-site chain under scipy_swipe(cg) against
+    tests/golden/cfg4a_chain16.npz recorded from the unmodified reference; CPU twin in test_krylov_cpu.py (2e-16 / 7e-16)."""
+    import cfg4a_case as c4
+    loss_err, pred_err = c4.run("cuda")
+    assert loss_err.max() < 1e-5 and pred_err < 1e-4, (loss_err.max(), pred_err)      # float32 Krylov recurrences on the host

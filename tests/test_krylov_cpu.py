@@ -43,3 +43,14 @@ def test_cumsum_scipy_swipe_float32_host_recurrences(monkeypatch):
     fake_ops.install(monkeypatch)
     core_err, loss_err = kc.run_case("krylov_cumsum_cg", "cpu", scipy_object=True)
     assert core_err < 5e-4 and loss_err < 5e-5, (core_err, loss_err)
+
+
+@pytest.mark.parametrize("fused_map", [True, False])
+def test_baseline_config4a_local_size_chain_against_reference_recording(fused_map, monkeypatch):
+    """BASELINE config 4a (TNML classifier: sin-cos map, 9 logits on the first core, cross-entropy, rank 38 -> local systems of up to
+    2888 parameters, scipy_swipe(cg)) on a 16-site chain and 512 rows against a recording of the unmodified reference: the 32 per-node
+    losses and the prediction (the 784-site chain takes the reference the better part of an hour per pass)."""
+    import cfg4a_case as c4
+    fake_ops.install(monkeypatch)
+    loss_err, pred_err = c4.run("cpu", fused_map=fused_map)
+    assert loss_err.max() < 1e-9 and pred_err < 1e-9, (loss_err.max(), pred_err)
