@@ -25,3 +25,14 @@ for name in grc.CASES:
     print(name, grc.run(name, "cuda"))
 print("krylov_cumsum_lanczos", kc.run_case("krylov_cumsum_lanczos", "cuda"))
 print("krylov_cumsum_cg", kc.run_case("krylov_cumsum_cg", "cuda", scipy_object=True))
+# recordings at the BASELINE configurations' own sizes (tests/golden/make_golden_cfg*.py)
+import cfg1_case, cfg2_case, cfg3_case, cfg4a_case, cfg4b_case, cfg5a_case, cfg5b_case
+for gm in ("fp64", "tf32x3"):
+    le, pe, ce = cfg1_case.run("cuda", gram_mode=gm); print("cfg1", gm, le, pe, ce)
+    le, pe = cfg2_case.run("cuda", gram_mode=gm); print("cfg2", gm, le.max(), pe)
+    le, pe = cfg5b_case.run("cuda", gram_mode=gm); print("cfg5b", gm, le.max(), pe)
+    print("cfg5a dense", gm, cfg5a_case.dense("cuda", gm))
+le, pe = cfg3_case.run("cuda"); print("cfg3", le.max(), pe)
+print("cfg4a", [float(v.max()) if hasattr(v, "max") else v for v in cfg4a_case.run("cuda")])
+print("cfg4b", [float(v.max()) if hasattr(v, "max") else v for v in cfg4b_case.run("cuda")])
+print("cfg5a matrix-free", cfg5a_case.matrix_free("cuda"))
