@@ -81,6 +81,11 @@ def test_tc_gram_planar_raw_slots_match_the_default_layout(shape, monkeypatch):
     torch.cuda.synchronize()
     # fp64 atomics of different CTAs land in a different order from run to run: compare to rounding, not bit for bit
     assert float((got - ref).norm() / ref.norm()) < 1e-12
+    # ... and with the V operand delivered as ready hi / lo tiles by bulk copies (tc_vstage_kernel): the same fp32 products and split
+    monkeypatch.setenv("TN_TC_V_PRESTAGE", "1")
+    got = ops.gram(ops.GRAM_TF32X3, fa, fb, fc, w, rows)
+    torch.cuda.synchronize()
+    assert float((got - ref).norm() / ref.norm()) < 1e-12
 
 
 @pytest.mark.xfail(strict=False, reason="full-size recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
