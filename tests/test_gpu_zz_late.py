@@ -64,30 +64,6 @@ def test_cumsum_matrix_free_sweeps_gpu():
     assert core_err < 5e-4 and loss_err < 5e-5, (core_err, loss_err)
 
 
-@pytest.mark.xfail(strict=False, reason="opt-in kernel variant written without GPU access at the end of round 1: not yet run on a B200")
-@pytest.mark.parametrize("shape", [(64, 2, 2, 2, 1), (5000, 6, 9, 6, 1), (20000, 24, 2, 24, 1), (3000, 38, 6, 38, 1), (2500, 38, 29, 1, 1),
-                                   (1200, 5, 3, 4, 3)])
-def test_tc_gram_planar_raw_slots_match_the_default_layout(shape, monkeypatch):
-    """TN_TC_RAW_PLANAR=1 (gram_tc.cu: planar layout of the raw-factor ring, conflict-free cp.async writes) must give the same M as
-    the row-major layout -- only shared-memory addresses change, not the arithmetic or its order -- or, where the factors are too
-    small for the planar slot, fall back to it."""
-    from tensornetworksfork_b200 import ops
-    import test_gpu_gram_tc as tg
-    fa, fb, fc, w, rows = tg.make(*shape, seed=sum(shape))
-    monkeypatch.delenv("TN_TC_RAW_PLANAR", raising=False)
-    ref = ops.gram(ops.GRAM_TF32X3, fa, fb, fc, w, rows)
-    monkeypatch.setenv("TN_TC_RAW_PLANAR", "1")
-    got = ops.gram(ops.GRAM_TF32X3, fa, fb, fc, w, rows)
-    torch.cuda.synchronize()
-    # fp64 atomics of different CTAs land in a different order from run to run: compare to rounding, not bit for bit
-    assert float((got - ref).norm() / ref.norm()) < 1e-12
-    # ... and with the V operand delivered as ready hi / lo tiles by bulk copies (tc_vstage_kernel): the same fp32 products and split
-    monkeypatch.setenv("TN_TC_V_PRESTAGE", "1")
-    got = ops.gram(ops.GRAM_TF32X3, fa, fb, fc, w, rows)
-    torch.cuda.synchronize()
-    assert float((got - ref).norm() / ref.norm()) < 1e-12
-
-
 @pytest.mark.xfail(strict=False, reason="full-size recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
 @pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3"])
 def test_baseline_config1_full_size_gpu(gram_mode):
@@ -163,3 +139,28 @@ def test_baseline_config4a_local_size_chain_gpu():
     import cfg4a_case as c4
     loss_err, pred_err = c4.run("cuda")
     assert loss_err.max() < 1e-5 and pred_err < 1e-4, (loss_err.max(), pred_err)      # float32 Krylov recurrences on the host
+
+
+# last on purpose: an untested kernel variant that trapped would take the CUDA context of this process with it
+@pytest.mark.xfail(strict=False, reason="opt-in kernel variant written without GPU access at the end of round 1: not yet run on a B200")
+@pytest.mark.parametrize("shape", [(64, 2, 2, 2, 1), (5000, 6, 9, 6, 1), (20000, 24, 2, 24, 1), (3000, 38, 6, 38, 1), (2500, 38, 29, 1, 1),
+                                   (1200, 5, 3, 4, 3)])
+def test_tc_gram_planar_raw_slots_match_the_default_layout(shape, monkeypatch):
+    """TN_TC_RAW_PLANAR=1 (gram_tc.cu: planar layout of the raw-factor ring, conflict-free cp.async writes) must give the same M as
+    the row-major layout -- only shared-memory addresses change, not the arithmetic or its order -- or, where the factors are too
+    small for the planar slot, fall back to it."""
+    from tensornetworksfork_b200 import ops
+    import test_gpu_gram_tc as tg
+    fa, fb, fc, w, rows = tg.make(*shape, seed=sum(shape))
+    monkeypatch.delenv("TN_TC_RAW_PLANAR", raising=False)
+    ref = ops.gram(ops.GRAM_TF32X3, fa, fb, fc, w, rows)
+    monkeypatch.setenv("TN_TC_RAW_PLANAR", "1")
+    got = ops.gram(ops.GRAM_TF32X3, fa, fb, fc, w, rows)
+    torch.cuda.synchronize()
+    # fp64 atomics of different CTAs land in a different order from run to run: compare to rounding, not bit for bit
+    assert float((got - ref).norm() / ref.norm()) < 1e-12
+    # ... and with the V operand delivered as ready hi / lo tiles by bulk copies (tc_vstage_kernel): the same fp32 products and split
+    monkeypatch.setenv("TN_TC_V_PRESTAGE", "1")
+    got = ops.gram(ops.GRAM_TF32X3, fa, fb, fc, w, rows)
+    torch.cuda.synchronize()
+    assert float((got - ref).norm() / ref.norm()) < 1e-12
