@@ -179,7 +179,7 @@ def test_baseline_config1_full_size_against_reference_recording(monkeypatch):
 
 def test_baseline_config2_full_size_fixture_and_first_loss(monkeypatch):
     """BASELINE config 2 at full size (CPD rank 100, N = 20640, 5 factors; recorded from the unmodified reference on its authors'
-    einsum path).  The full sweep runs on the GPU (tests/test_gpu_zz_late.py); here: the fixture, the regenerated data, identical
+    einsum path).  The full sweep runs on the GPU (tests/test_zz_gpu_late.py); here: the fixture, the regenerated data, identical
     initial factors for the same seed, and the loss the first update reports (mean of per-minibatch means at the initial factors)."""
     import cfg2_case as c2
     from tensornetworksfork_b200.tensor.network import batch_mean_of_means
@@ -208,7 +208,7 @@ def test_baseline_config3_chain_first_updates(fused_map, monkeypatch):
 @pytest.mark.parametrize("which", ["cfg2", "cfg3", "cfg5b"])
 def test_baseline_configs_full_recordings_on_standin_kernels(which, monkeypatch):
     """The complete recordings of BASELINE configs 2 (17 updates at full size), 3 (179 updates of the 90-site chain) and 5b (55 updates
-    of the 28-site rank-38 chain) through the host driver on the CPU stand-in kernels -- what the GPU twins in tests/test_gpu_zz_late.py run on the real kernels."""
+    of the 28-site rank-38 chain) through the host driver on the CPU stand-in kernels -- what the GPU twins in tests/test_zz_gpu_late.py run on the real kernels."""
     fake_ops.install(monkeypatch)
     if which == "cfg2":
         import cfg2_case as c2

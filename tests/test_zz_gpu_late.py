@@ -145,7 +145,7 @@ def test_baseline_config4a_local_size_chain_gpu():
 
 # Opt-in (TN_TEST_EXPERIMENTAL_KERNELS=1) and last: an untested kernel variant that trapped (the kernels' barrier waits are bounded and
 # trap instead of hanging) would take the CUDA context of the whole pytest process with it -- including the GPU tests of the files
-# that sort after this one.  Run it on its own first:  TN_TEST_EXPERIMENTAL_KERNELS=1 pytest tests/test_gpu_zz_late.py -k planar
+# that sort after this one.  Run it on its own first:  TN_TEST_EXPERIMENTAL_KERNELS=1 pytest tests/test_zz_gpu_late.py -k planar
 @pytest.mark.skipif(not os.environ.get("TN_TEST_EXPERIMENTAL_KERNELS"), reason="untested kernel variants: set TN_TEST_EXPERIMENTAL_KERNELS=1")
 @pytest.mark.xfail(strict=False, reason="opt-in kernel variant written without GPU access at the end of round 1: not yet run on a B200")
 @pytest.mark.parametrize("shape", [(64, 2, 2, 2, 1), (5000, 6, 9, 6, 1), (20000, 24, 2, 24, 1), (3000, 38, 6, 38, 1), (2500, 38, 29, 1, 1),

@@ -14,7 +14,7 @@ for name in ["krylov_lanczos_reg", "krylov_lanczos_xe"]:
     print(name, kc.run_case(name, "cuda"))
 for tag in "ab":
     print("growing", tag, gc.run(tag, "cuda"))
-# flows added after the round-1 GPU minutes were spent (tests/test_gpu_zz_late.py): measure, then tighten those tolerances
+# flows added after the round-1 GPU minutes were spent (tests/test_zz_gpu_late.py): measure, then tighten those tolerances
 import batch_case as bc, gradient_case as grc
 print("conv grow", cc.run_grow("cuda"))
 for name in ["conv_type1", "conv_onecol", "conv_nocb", "conv_dense_xe", "conv_dense_reg"]:
