@@ -29,6 +29,13 @@ if "reference" in sys.argv and os.environ.get("OMP_NUM_THREADS") == "1":
     for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[_v] = str(os.cpu_count() or 1)
 
+_REF_ROOT = None
+if "reference" in sys.argv:
+    # the unmodified reference (oracle/_ref, recipe oracle/make_ref.py) and its authors' environment (the opt_einsum stand-in has to
+    # be importable before torch is): only the CPU arm ever imports these
+    from oracle import make_ref as _make_ref
+    _REF_ROOT = _make_ref.activate()
+
 import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
@@ -75,6 +82,9 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--max-iter", type=int, default=None, help="Krylov iterations per node (matrix-free workloads)")
     ap.add_argument("--ref-rows", type=int, default=None)
+    ap.add_argument("--ref-quick", action="store_true",
+                    help="reference arm as the b200 arm's cpu_baseline leg: one bounded sample (10-30 s), large solves extrapolated")
+    ap.add_argument("--ref-port", action="store_true", help="reference arm on the numpy port of oracle/ even when oracle/_ref exists")
     ap.add_argument("--ref-matvecs", type=float, default=20.0,
                     help="matvecs per site assumed by --impl reference on the matrix-free workloads (the b200 arm reports its own count)")
     return ap.parse_args()
@@ -305,69 +315,80 @@ def bench_b200(args):
     timer.install()
     counter = [0]
 
+    # ---- ONE loop gives both numbers (the two-loop version of round 1 doubled the wall time and broke the driver's limit):
+    # every step is the public call with HOST (pinned) buffers -- accumulating_swipe(x_host, y_host, model_device=cuda) copies
+    # them to the device, sweeps, and the step ends with a device->host read of the fit's error.  `e2e` is the wall clock
+    # over the K timed steps; `value` is the device time of the same K sweeps between the event the engine's data-ready hook
+    # records once the copies are enqueued (inputs resident in HBM) and the event after the last kernel of the sweep.
+    e2e_mode = not args.no_e2e
+    if e2e_mode:
+        Xh, yh = X.cpu().pin_memory(), y.cpu().pin_memory()
+        x_head = wrap_input(wl, X[:1024].clone())
+        y_head = (y[:1024] if wl["C"] == 1 else y[:1024, :wl["C"]]).clone()
+        del x, X, y                       # device copies of the inputs only come from the per-step host->device copies below
+        x = X = y = None
+    got = []
+    step_events = []
+    pending = {}
+    tn.on_data_ready = lambda: pending.__setitem__("e0", _rec())
+
+    def _rec():
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def one_step():
+        if e2e_mode:
+            run_sweeps(layer, wrap_input(wl, Xh), yh, wl, args, 1, counter, data_device=torch.device("cpu"))
+        else:
+            run_sweeps(layer, x, y, wl, args, 1, counter)
+        step_events.append((pending.pop("e0"), _rec()))
+        if e2e_mode:
+            pred = tn.forward_batch(x_head, -1)
+            got.append(float(((pred - y_head) ** 2).mean().item()))      # device -> host read of the result
+
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
     for _ in range(args.warmup):
-        run_sweeps(layer, x, y, wl, args, 1, counter)      # one step = one call = one full sweep (L->R then R->L), as in the e2e loop
+        one_step()                       # one step = one call = one full sweep (L->R then R->L)
     barrier()
-    # ---- device-resident timed region
     counter[0] = 0
+    step_events.clear()
     timer.enabled = True
     from tensornetworksfork_b200 import _lib as _tnlib
     launches0 = _tnlib.load().tn_launch_count()
     clocks = ClockSampler(local)
     if rank == 0:
         clocks.start()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     mv_count0 = getattr(tn, "matvec_count", 0)
-    e0.record()
+    t0 = time.perf_counter()
     for _ in range(args.steps):
-        run_sweeps(layer, x, y, wl, args, 1, counter)
-    e1.record()
+        one_step()
     barrier()
+    wall = time.perf_counter() - t0
     mv_count1 = getattr(tn, "matvec_count", 0)
     clk = clocks.stop() if rank == 0 else None
     timer.enabled = False
     kernel_launches = int(_tnlib.load().tn_launch_count() - launches0)
-    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    both = torch.tensor([sum(a_.elapsed_time(b_) for a_, b_ in step_events), wall * 1e3], device=dev)
     if world > 1:
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    ms = float(ms.item())
+        dist.all_reduce(both, op=dist.ReduceOp.MAX)
+    ms, wall_ms = (float(v) for v in both.tolist())
     updates = counter[0]
     site_rate = updates / (ms / 1e3)               # site updates per second (does not grow with N under weak scaling)
     value = site_rate * n * world                  # sample-site updates per second: the whole-job aggregate
-
-    # ---- end to end: host (pinned) buffers in, loss scalar out, copies inside the timed region
     e2e = None
-    if not args.no_e2e:
-        Xh, yh = X.cpu().pin_memory(), y.cpu().pin_memory()
-        got = []
-        counter2 = [0]
-
-        def one_e2e():
-            xin = wrap_input(wl, Xh)
-            run_sweeps(layer, xin, yh, wl, args, 1, counter2, data_device=torch.device("cpu"))
-            pred = tn.forward_batch(wrap_input(wl, X[:1024]), -1)
-            yy = y[:1024] if wl["C"] == 1 else y[:1024, :wl["C"]]
-            got.append(float(((pred - yy) ** 2).mean().item()))      # device -> host read of the result
-
-        one_e2e()
-        barrier()
-        counter2[0] = 0
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            one_e2e()
-        barrier()
-        dt = torch.tensor([time.perf_counter() - t0], device=dev)
-        if world > 1:
-            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-        e2e = {"value": counter2[0] / float(dt.item()) * n * world, "unit": "sample-site-updates/s",
-               "site_updates_per_s": counter2[0] / float(dt.item()),
-               "h2d_bytes_per_step": int(Xh.numel() * 8 + yh.numel() * 8), "d2h_bytes_per_step": 8}
+    if e2e_mode:
+        e2e = {"value": updates / (wall_ms / 1e3) * n * world, "unit": "sample-site-updates/s",
+               "site_updates_per_s": updates / (wall_ms / 1e3), "ms_per_step": wall_ms / args.steps,
+               "h2d_bytes_per_step": int(Xh.numel() * Xh.element_size() + yh.numel() * yh.element_size()), "d2h_bytes_per_step": 8,
+               "how": "same K steps as `value`: wall clock around accumulating_swipe(x_host_pinned, y_host_pinned, model_device=cuda) "
+                      "+ forward on 1024 rows + .item() of its MSE; `value` is the device time of those sweeps after the copies",
+               "fit_mse_last": got[-1] if got else None}
 
     if rank != 0:
         if world > 1:
@@ -380,10 +401,17 @@ def bench_b200(args):
         pass
     tot = timer.totals()
     measured = None
-    if not args.no_peaks:
+    if not args.no_peaks and world == 1:
         sys.path.insert(0, os.path.join(ROOT, "tools"))
         import peaks as _peaks
         measured = _peaks.measure()
+    elif not args.no_peaks:
+        # N > 1: the other ranks are waiting in destroy_process_group -- reuse the cuBLAS TF32 / FP64 peaks measured by an N = 1 run
+        # on this pool (same file the N = 1 line's in-run measurement is checked against)
+        try:
+            measured = dict(json.load(open(os.path.join(ROOT, "profiles", "r1_peaks_tf32_fp64.json"))), source="profiles/r1_peaks_tf32_fp64.json (not re-measured at N > 1)")
+        except Exception:
+            measured = None
     gram_ms = tot["gram"]
     launches = kernel_launches   # kernels of libtn_b200.so launched inside the timed region (counted by the library)
     issued = algo = 0.0
@@ -404,24 +432,37 @@ def bench_b200(args):
             bf16 = peaks.get("bf16_tflops_sustained", 1400.0)
             peak, peak_src = bf16 / 2.0, "half of the sustained bf16 dense peak of MEASURED_PEAKS.json (TF32 rate = bf16/2); " + ("of measured" if peaks else "of fallback")
     mult = 3.0 if args.gram_mode == "tf32x3" else 1.0
-    achieved = issued * mult / gsum / 1e12 if gsum > 0 else 0.0
+    issued_tf = issued * mult / gsum / 1e12 if gsum > 0 else 0.0
+    # the figure `roofline.achieved` quotes is the ALGORITHMIC work N*P*(P+1) per site update (symmetric Gram, unique
+    # entries x 2 flop) over the CUDA-event time of the Gram launches; the MMA flop the tensor pipe actually executes (Kronecker-
+    # symmetric unique entries, x3 passes in 3xTF32) is reported beside it as issued_tflops / pipe_frac -- both labelled.
+    achieved = algo / gsum / 1e12 if gsum > 0 else 0.0
+    file_peak = None
+    if args.gram_mode != "fp64":
+        bf16 = peaks.get("bf16_tflops_sustained")
+        file_peak = bf16 / 2.0 if bf16 else 1400.0 / 2.0
     traffic, traffic_note = None, None
     try:
-        tr = json.load(open(os.path.join(ROOT, "profiles", "r1_traffic.json")))["gram_tc_kernel<1,2>"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))["gram_tc_kernel"]
         big = max(timer.extra["gram"], key=lambda c_: gram_flops(c_)[0]) if timer.extra["gram"] else None
         if big is not None and args.gram_mode == "tf32x3" and sorted(big[:3]) == [29, 38, 38]:
             traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) / tr["rows"] * big[3]
             traffic_note = (f"dram__bytes_read+write of the dominant launch (middle site, {big[3]} rows), scaled by rows from the "
-                            f"{tr['rows']}-row ncu --set full capture ({tr['source']}); it is the fp64 flush of the fp32 accumulators, "
-                            f"not operand re-reads: the algorithmic operand bytes are {8 * big[3] * (38 + 29 + 38 + 1)} B + 1.9e9 B of M")
+                            f"{tr['rows']}-row ncu capture ({tr['source']}); algorithmic bytes: {8 * big[3] * (38 + 29 + 38 + 1)} B of "
+                            f"operands + 1.9e9 B of M written once")
     except Exception:
         pass
     roofline = {"kernel": f"gram_kr3[{args.gram_mode}]", "bound": "tensor" if args.gram_mode != "fp64" else "fp64", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                 "traffic_note": traffic_note,
-                "peak_source": peak_src, "issued_flops_per_step": issued * mult / args.steps,
-                "survey_algorithmic_flops_per_step": algo / args.steps,
-                "survey_equiv_tflops": algo / gsum / 1e12 if gsum > 0 else 0.0,
+                "achieved_is": "algorithmic N*P*(P+1) flop per site update (SURVEY 8d) / CUDA-event time of the Gram launches",
+                "peak_source": peak_src,
+                "frac_of_half_bf16_sustained_file": (achieved / file_peak) if file_peak else None,
+                "half_bf16_sustained_file": file_peak,
+                "issued_tflops": issued_tf, "pipe_frac": issued_tf / peak if peak else None,
+                "issued_is": "MMA flop the tensor pipe executes: 2*rows*n_a*n_b*n_c unique Kronecker-pair entries" + (" x3 (hi*hi, hi*lo, lo*hi)" if mult == 3.0 else ""),
+                "issued_flops_per_step": issued * mult / args.steps,
+                "algorithmic_flops_per_step": algo / args.steps,
                 "share_of_step": gsum / (ms / 1e3), "launches": len(gram_ms), "measured_peaks": measured,
                 "bf16_peaks_file": {k: peaks.get(k) for k in ("bf16_tflops", "bf16_tflops_sustained", "hbm_gbs")}}
     if wl["kind"] == "conv":
@@ -475,7 +516,7 @@ def bench_b200(args):
            "gpu_launches": launches,
            "clocks": clk, "e2e": e2e}
     if not args.no_cpu_baseline and world == 1:      # the CPU baseline is a rank-0, N = 1 figure (the driver's reference arm covers N > 1)
-        out["cpu_baseline"] = cpu_baseline(args, wl, n * world)
+        out["cpu_baseline"] = cpu_baseline_leg(args, wl, n * world)
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)
     print(json.dumps(out), flush=True)
@@ -615,6 +656,27 @@ def cpu_site_time_warm(wl, rows):
     return best
 
 
+def cpu_baseline_leg(args, wl, rows_total):
+    """cpu_baseline of the b200 line: the unmodified reference (oracle/_ref) on a bounded sample in a child process (its opt_einsum
+    stand-in has to be on sys.path before torch is imported, and its thread pools should not inherit this process's), else the port."""
+    from oracle import make_ref
+    if make_ref.ref_root() is not None and not wl.get("solver") and wl["kind"] in ("tt", "cpd"):
+        env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE", "OMP_NUM_THREADS", "MKL_NUM_THREADS")}
+        cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", args.workload, "--steps", "1",
+               "--warmup", "1", "--ref-quick", "--rows", str(rows_total), "--eps", str(args.eps)]
+        if args.ref_rows:
+            cmd += ["--ref-rows", str(args.ref_rows)]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
+            return json.loads(line)["cpu_baseline"]
+        except Exception as e:      # fall through to the port, and say why
+            base = cpu_baseline(args, wl, rows_total)
+            base["sample"] += f" [reference child failed: {type(e).__name__}]"
+            return base
+    return cpu_baseline(args, wl, rows_total)
+
+
 def cpu_baseline(args, wl, rows_total):
     use_all_host_threads()
     rows = args.ref_rows or (256 if args.workload == "cfg5a" else ((32 if wl["kind"] == "conv" else 128) if wl.get("solver") else 2048))
@@ -639,14 +701,180 @@ def cpu_baseline(args, wl, rows_total):
                       f"than the reference verbatim (S x P x P einsum temporary), 1.1-2.8x slower than the reference with opt_einsum"}
 
 
+# ------------------------------------------------------------------------------------------ CPU side: the unmodified reference
+def _ref_model(wl, rows):
+    """The reference's own layer + inputs for a workload (tensor/layers.py of oracle/_ref), on `rows` synthetic rows."""
+    from tensor.layers import TensorTrainLayer, CPDLayer          # the REFERENCE's modules (oracle/_ref on sys.path)
+    from tensor.bregman import SquareBregFunction
+    f = wl["features"] + 1 if wl["bias"] else (2 if wl["basis"] == "sin-cos" else wl.get("degree", 3) + 1)
+    if wl["kind"] == "cpd":
+        layer = CPDLayer(wl["sites"], wl["r"], f, output_shape=(wl["C"],), seed=42)
+    else:
+        layer = TensorTrainLayer(wl["sites"], wl["r"], f, output_shape=wl["C"], constrict_bond=wl["constrict"], perturb=wl["perturb"], seed=42)
+    X, y = make_data(wl, rows, seed=1000, device="cpu")
+    if wl["basis"] == "sin-cos":
+        x = [torch.stack([torch.cos(0.5 * np.pi * X[:, j]), torch.sin(0.5 * np.pi * X[:, j])], 1) for j in range(X.shape[1])]
+    elif wl["basis"] == "polynomial":
+        x = [torch.stack([X[:, j] ** d for d in range(wl.get("degree", 3) + 1)], 1) for j in range(X.shape[1])]
+    else:
+        x = X
+    tn = layer.tensor_network
+    if wl.get("orthonormalize"):
+        tn.orthonormalize_left()
+    return tn, x, y, SquareBregFunction()
+
+
+class _SolveTimer:
+    """Instrumentation around the reference's own `solve_system` (instance attribute; the class is untouched): times every call and,
+    for systems above `skip_above`, returns a zero step instead of solving (their cost is measured once, separately)."""
+
+    def __init__(self, tn, skip_above):
+        self.orig = tn.solve_system
+        self.skip_above = skip_above
+        self.seconds = 0.0
+        self.skipped = []
+        tn.solve_system = self
+
+    def __call__(self, node, A, b, method="exact", eps=0.0):
+        P = b.numel()
+        if P > self.skip_above:
+            self.skipped.append(P)
+            return torch.zeros_like(b)
+        t0 = time.perf_counter()
+        out = self.orig(node, A, b, method=method, eps=eps)
+        self.seconds += time.perf_counter() - t0
+        return out
+
+
+def _ref_solve_seconds(tn, P, eps, budget_s, note):
+    """Seconds of the reference's own solve_system(ridge_cholesky) at size P on the host cores: measured when the memory and the
+    time budget allow (predicted from a P = 6144 solve, cubic), else that cubic extrapolation -- `note` says which."""
+    node = tn.train_nodes[0]
+
+    def run(Pq):
+        g = torch.Generator().manual_seed(Pq)
+        Bm = torch.randn((Pq, 64), generator=g)
+        A = Bm @ Bm.t()
+        A.diagonal().add_(float(Pq))
+        b = torch.randn((Pq,), generator=g)
+
+        class _N:                      # solve_system only reads node.tensor for the ridge term
+            tensor = torch.zeros((Pq,))
+        t0 = time.perf_counter()
+        tn.solve_system(_N, A, b, method="ridge_cholesky", eps=eps)
+        return time.perf_counter() - t0
+
+    Pq = min(P, 6144)
+    run(min(Pq, 1024))
+    tq = run(Pq)
+    if Pq == P:
+        note.append(f"solve_system at P={P} measured: {tq:.2f} s")
+        return tq
+    pred = tq * (P / Pq) ** 3
+    avail = None
+    try:
+        import psutil
+        avail = psutil.virtual_memory().available
+    except Exception:
+        pass
+    need = 5.5 * 8.0 * P * P               # A, A/scale, eye, A+ridge, L (network.py:296-315)
+    if pred <= budget_s and avail is not None and avail > 1.3 * need:
+        t = run(P)
+        note.append(f"solve_system at P={P} measured once: {t:.1f} s (cubic prediction from P={Pq}: {pred:.1f} s)")
+        return t
+    note.append(f"solve_system at P={P} NOT run ({'predicted %.0f s > budget %.0f s' % (pred, budget_s) if pred > budget_s else 'host memory'}): "
+                f"cubic extrapolation {pred:.1f} s from the measured {tq:.2f} s at P={Pq}")
+    return pred
+
+
+def reference_arm(args, wl, n_total, steps, warmup, quick):
+    """Sample-site updates/s of the UNMODIFIED reference (oracle/_ref: tensor/network.py:379-608) on the host cores.
+
+    A step = the reference's own accumulating_swipe(node_order=[node], skip_second=True, ...) -- forward, loss, get_A_b, solve_system,
+    update_node -- for every distinct core shape of the train, on one `rows`-row sample of the workload's data.  Time per sweep at
+    N rows = sum over the sweep's site updates of [t_sample(shape) * N / rows + t_solve(shape)]: everything but the solve is linear in
+    the rows (the reference loops over minibatches), the solve is not; solves above P = 4096 are stubbed out of the sample (zero
+    step) and their cost is measured once by calling the reference's solve_system at that size."""
+    from tensornetworksfork_b200.tensor.network import sweep_schedule
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(ncpu)
+    rows = args.ref_rows or (256 if args.workload == "cfg5a" else 2048)
+    tn, x, y, loss_fn = _ref_model(wl, rows)
+    nodes = list(tn.train_nodes)
+    shapes = {}
+    for k, nd in enumerate(nodes):
+        shapes.setdefault(tuple(nd.tensor.shape), k)
+    sched = sweep_schedule(list(range(len(nodes))), list(reversed(range(len(nodes)))), 1, args.eps)
+    visits = [nodes[(i if half == 0 else len(nodes) - 1 - i)] for _, half, i, _ in sched]
+    count = {shp: sum(1 for nd in visits if tuple(nd.tensor.shape) == shp) for shp in shapes}
+    st = _SolveTimer(tn, skip_above=4096)
+    note = []
+
+    def sample():
+        per = {}
+        for shp, k in shapes.items():
+            s0 = st.seconds
+            t0 = time.perf_counter()
+            ok = tn.accumulating_swipe(x, y, loss_fn, node_order=[nodes[k]], batch_size=-1, num_swipes=1, skip_second=True,
+                                       method="ridge_cholesky", eps=args.eps, orthonormalize=False)
+            dt = time.perf_counter() - t0
+            assert ok
+            per[shp] = (dt - (st.seconds - s0), st.seconds - s0)        # (linear-in-rows part, small solve)
+        return per
+
+    tn.solve_system = st.orig
+    big = sorted({int(np.prod(shp)) for shp in shapes if int(np.prod(shp)) > 4096})
+    t_big = {P: _ref_solve_seconds(tn, P, args.eps, 0.0 if quick else 150.0, note) for P in big}
+    tn.solve_system = st
+    wake_host_cores()
+    for _ in range(warmup):
+        sample()
+    vals, walls = [], []
+    for _ in range(max(steps, 1)):
+        t0 = time.perf_counter()
+        per = sample()
+        walls.append(time.perf_counter() - t0)
+        t_sweep = 0.0
+        for shp, (t_lin, t_small) in per.items():
+            P = int(np.prod(shp))
+            t_sweep += count[shp] * (t_lin * (n_total / rows) + (t_big[P] if P in t_big else t_small))
+        vals.append(len(visits) * n_total / t_sweep)
+    value = float(np.median(vals))
+    sample_txt = (f"UNMODIFIED reference (oracle/_ref = tensor/ + models/ of the reference tree, opt_einsum stand-in as in its authors' "
+                  f"environment; torch {torch.__version__}, {torch.get_num_threads()} threads of {ncpu} host cores): per step its own "
+                  f"accumulating_swipe(node_order=[node], skip_second=True, method='ridge_cholesky') on one {rows}-row sample for each of the "
+                  f"{len(shapes)} distinct core shapes ({float(np.median(walls)):.2f} s per step); a sweep of {len(visits)} site updates at "
+                  f"{n_total} rows = sample time x rows/{rows} + the solves; " + "; ".join(note))
+    return value, {"value": value, "unit": "sample-site-updates/s", "site_updates_per_s": value / n_total, "cores": ncpu,
+                   "kind": "reference", "sample": sample_txt, "opt_einsum_path": bool(torch.backends.opt_einsum.is_available())}, float(np.mean(walls))
+
+
 def bench_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     wl = WORKLOADS[args.workload]
-    use_all_host_threads()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     n = (args.n if args.n is not None else wl["n"]) * world
+    use_ref = _REF_ROOT is not None and not args.ref_port and not wl.get("solver") and wl["kind"] in ("tt", "cpd")
+    if use_ref:
+        value, base, step_s = reference_arm(args, wl, n, args.steps, args.warmup, args.ref_quick)
+    else:
+        value, base, step_s = port_arm(args, wl, n)
+    out = {"impl": "reference", "metric": "gn_sample_site_updates_per_s", "value": value, "unit": "sample-site-updates/s",
+           "site_updates_per_s": value / n, "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+           "config": {"workload": f"{args.workload}: {wl['desc']}", "rows_per_gpu": n // world, "rows_total": n, "eps": args.eps,
+                      "parallelism": f"host cores ({os.cpu_count()})"},
+           "cpu_baseline": base,
+           "e2e": {"value": value, "unit": "sample-site-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(out))
+
+
+def port_arm(args, wl, n):
+    """The numpy port of oracle/ on the host cores: used where oracle/_ref is absent and for the matrix-free workloads."""
+    use_all_host_threads()
     rows = args.ref_rows or (256 if args.workload == "cfg5a" else ((32 if wl["kind"] == "conv" else 128) if wl.get("solver") else 2048))
     if wl.get("solver"):
         wl = dict(wl, _avg_matvecs=float(args.ref_matvecs))
@@ -654,27 +882,19 @@ def bench_reference(args):
         cpu_site_time(wl, min(rows, 64))
     t0 = time.perf_counter()
     vals = []
-    for _ in range(args.steps):
+    for _ in range(max(args.steps, 1)):
         t_batch, t_solve, ns = cpu_site_time_warm(wl, rows) if not vals else cpu_site_time(wl, rows)
         vals.append(ns / (t_batch * (n / rows) + t_solve) * n)
     wall = time.perf_counter() - t0
     value = float(np.median(vals))
     sample = (f"oracle port of tensor/network.py (numpy/BLAS, {os.cpu_count()} host threads): per step, env+Jacobian+Gram+rhs of every "
-              f"site on one {rows}-row minibatch and the dense solves with P<=4096, extrapolated linearly to {n} rows; the Python "
-              f"reference cannot travel to this box -- measured beside it on an 8-core host the port is 23-48x faster than the "
-              f"reference verbatim and 1.1-2.8x slower than the reference with opt_einsum (profiles/r1_reference_vs_port_cpu.json)")
+              f"site on one {rows}-row minibatch and the dense solves with P<=4096, extrapolated linearly to {n} rows (oracle/_ref not "
+              f"present or workload not covered by the reference arm)")
     if wl.get("solver"):
         sample = (f"oracle port of tensor/network.py:709-932 (numpy/BLAS, {os.cpu_count()} host threads): per step, envs + batch Jacobian + "
                   f"rhs + {wl['_avg_matvecs']:.0f} matvecs per site (--ref-matvecs) of every distinct site shape on one {rows}-row "
                   f"minibatch, extrapolated linearly to {n} rows")
-    out = {"impl": "reference", "metric": "gn_sample_site_updates_per_s", "value": value, "unit": "sample-site-updates/s",
-           "site_updates_per_s": value / n, "n_gpus": world,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": wall / max(args.steps, 1) * 1e3, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"{args.workload}: {wl['desc']}", "rows_total": n},
-           "cpu_baseline": {"value": value, "unit": "sample-site-updates/s", "cores": os.cpu_count(), "kind": "port", "sample": sample},
-           "e2e": {"value": value, "unit": "sample-site-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(out))
+    return value, {"value": value, "unit": "sample-site-updates/s", "cores": os.cpu_count(), "kind": "port", "sample": sample}, wall / max(args.steps, 1)
 
 
 if __name__ == "__main__":

@@ -160,6 +160,7 @@ class TensorNetwork:
         self._data_key = None
         self._data = None
         self.last_site_seconds = None
+        self.on_data_ready = None       # optional hook, called once the (possibly host-resident) data has been enqueued to the device
 
     # ------------------------------------------------------------------ graph / plan
     def _discover_nodes(self):
@@ -819,6 +820,8 @@ class TensorNetwork:
         self.set_input(xm)
         if ym.dtype != torch.float64:
             ym = ym.to(torch.float64)
+        if self.on_data_ready is not None:
+            self.on_data_ready()
         return xm, ym
 
     def _one_update(self, k, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss):

@@ -1,4 +1,5 @@
-"""bench.py --impl reference (the CPU arm: the oracle port timed on the host cores) prints ONE JSON line with the contract keys,
+"""bench.py --impl reference (the CPU arm: the unmodified reference of oracle/_ref -- or the oracle port where that is absent -- timed on
+the host cores) prints ONE JSON line with the contract keys, oracle/_ref is a byte-identical copy of the reference's packages,
 and the mixed-solve fall-back bookkeeping of the sweep engine works on the CPU stand-in kernels."""
 import json
 import os
@@ -23,9 +24,35 @@ def test_reference_arm_json_line():
               "dtype", "data", "config", "cpu_baseline", "e2e"):
         assert k in d, k
     assert d["impl"] == "reference" and d["value"] > 0 and d["vs_baseline"] is None
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    have_ref = os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "tensor", "network.py")) or os.path.isdir("/root/reference/tensor")
+    assert d["cpu_baseline"]["kind"] == ("reference" if have_ref else "port")
+    assert d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"]
+
+
+def test_reference_arm_port_fallback_json_line():
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--ref-port", "--workload", "cfg1", "--steps", "1",
+                          "--warmup", "0", "--ref-rows", "64"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads([l for l in out.stdout.splitlines() if l.strip()][-1])
+    assert d["impl"] == "reference" and d["cpu_baseline"]["kind"] == "port" and d["value"] > 0
+
+
+def test_oracle_ref_is_the_unmodified_reference():
+    """oracle/_ref (recipe: oracle/make_ref.py) holds the reference's tensor/ and models/ byte for byte."""
+    import hashlib
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    if not os.path.isfile(os.path.join(ref_dir, "MANIFEST.json")):
+        import pytest
+        pytest.skip("oracle/_ref not built (run python oracle/make_ref.py where /root/reference is mounted)")
+    man = json.load(open(os.path.join(ref_dir, "MANIFEST.json")))["files"]
+    assert "tensor/network.py" in man and "models/tensor_train.py" in man
+    for rel, digest in man.items():
+        assert hashlib.sha256(open(os.path.join(ref_dir, rel), "rb").read()).hexdigest() == digest, rel
+        src = os.path.join("/root/reference", rel)
+        if os.path.isfile(src):
+            assert open(src, "rb").read() == open(os.path.join(ref_dir, rel), "rb").read(), rel
 
 
 def test_mixed_solve_fallback_bookkeeping(monkeypatch):

@@ -20,8 +20,6 @@ pytestmark = pytest.mark.gpu
 torch.set_default_dtype(torch.float64)
 
 
-@pytest.mark.xfail(strict=False, reason="failed on the B200 at the end of round 1 (stride-0 broadcast core passed to tn_rows_dot); "
-                                        "fixed in conv._to_canon and reproduced / verified on the CPU stand-ins, not yet re-run on hardware")
 def test_conv_growing_flow_gpu():
     """grow_cart between dense sweeps (image_convolution_growing_MNIST.py:84-103) against the reference recording
     tests/golden/conv_grow.npz; CPU twin: test_conv_cpu.py::test_conv_growing_flow_host_logic."""
@@ -66,7 +64,6 @@ def test_cumsum_matrix_free_sweeps_gpu():
     assert core_err < 5e-4 and loss_err < 5e-5, (core_err, loss_err)
 
 
-@pytest.mark.xfail(strict=False, reason="full-size recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
 @pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3"])
 def test_baseline_config1_full_size_gpu(gram_mode):
     """BASELINE config 1 at full size against tests/golden/cfg1_full.npz (recorded from the unmodified reference): the first two
@@ -79,7 +76,6 @@ def test_baseline_config1_full_size_gpu(gram_mode):
     assert loss_err[-1] < 0.2, loss_err
 
 
-@pytest.mark.xfail(strict=False, reason="full-size recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
 @pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3"])
 def test_baseline_config2_full_size_gpu(gram_mode):
     """BASELINE config 2 at full size (CPD rank 100, 20640 x 9, 5 factors, two sweeps with the wrapper's ridge schedule 1.0 * 0.5^NS)
@@ -90,7 +86,6 @@ def test_baseline_config2_full_size_gpu(gram_mode):
     assert loss_err.max() < tol and pred_err < 10 * tol, (loss_err, pred_err)
 
 
-@pytest.mark.xfail(strict=False, reason="recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
 def test_baseline_config3_chain_gpu():
     """BASELINE config 3's 90-site chain (sin-cos map, rank 24, QR re-gauge) on a 4096-row subsample, one full sweep = 179 updates,
     against tests/golden/cfg3_chain90.npz recorded from the unmodified reference; fused feature map (what TNMLRegressor passes)."""
@@ -99,7 +94,6 @@ def test_baseline_config3_chain_gpu():
     assert loss_err.max() < 1e-6 and pred_err < 1e-5, (loss_err.max(), pred_err)
 
 
-@pytest.mark.xfail(strict=False, reason="recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
 @pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3"])
 def test_baseline_config5b_chain_gpu(gram_mode):
     """BASELINE config 5b's chain (28 sites, polynomial degree 5, rank 38, QR re-gauge, P up to 8664 -- with 'tf32x3' the mixed
@@ -111,7 +105,6 @@ def test_baseline_config5b_chain_gpu(gram_mode):
     assert loss_err.max() < tol and pred_err < 10 * tol, (loss_err.max(), pred_err)
 
 
-@pytest.mark.xfail(strict=False, reason="recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
 def test_baseline_config4b_full_model_size_gpu():
     """BASELINE config 4b at full model size (r = 38, CB = 4, 72 200-parameter patch core) under scipy_swipe(minres) against
     tests/golden/cfg4b_shape.npz recorded from the unmodified reference; CPU twin in test_conv_cpu.py (exact losses, 7e-16)."""
@@ -120,7 +113,6 @@ def test_baseline_config4b_full_model_size_gpu():
     assert loss_err.max() < 1e-5 and pred_err < 1e-4, (loss_err, pred_err)        # float32 Krylov recurrences on the host
 
 
-@pytest.mark.xfail(strict=False, reason="recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
 @pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3"])
 def test_baseline_config5a_gram_fingerprint_gpu(gram_mode):
     """The north-star shape (5 cores, rank 38, 28 features + bias): the dense 41 876 x 41 876 system of the middle core, expanded from
@@ -134,7 +126,6 @@ def test_baseline_config5a_gram_fingerprint_gpu(gram_mode):
     assert max(mf) < 1e-12, mf
 
 
-@pytest.mark.xfail(strict=False, reason="recording added after the round's GPU minutes were spent: margins not yet measured on a B200")
 def test_baseline_config4a_local_size_chain_gpu():
     """BASELINE config 4a at its full local size (rank 38, 9 logits, P up to 2888) on a 16-site chain under scipy_swipe(cg) against
     tests/golden/cfg4a_chain16.npz recorded from the unmodified reference; CPU twin in test_krylov_cpu.py (2e-16 / 7e-16)."""
@@ -147,7 +138,6 @@ def test_baseline_config4a_local_size_chain_gpu():
 # trap instead of hanging) would take the CUDA context of the whole pytest process with it -- including the GPU tests of the files
 # that sort after this one.  Run it on its own first:  TN_TEST_EXPERIMENTAL_KERNELS=1 pytest tests/test_zz_gpu_late.py -k planar
 @pytest.mark.skipif(not os.environ.get("TN_TEST_EXPERIMENTAL_KERNELS"), reason="untested kernel variants: set TN_TEST_EXPERIMENTAL_KERNELS=1")
-@pytest.mark.xfail(strict=False, reason="opt-in kernel variant written without GPU access at the end of round 1: not yet run on a B200")
 @pytest.mark.parametrize("shape", [(64, 2, 2, 2, 1), (5000, 6, 9, 6, 1), (20000, 24, 2, 24, 1), (3000, 38, 6, 38, 1), (2500, 38, 29, 1, 1),
                                    (1200, 5, 3, 4, 3)])
 def test_tc_gram_planar_raw_slots_match_the_default_layout(shape, monkeypatch):
