@@ -2,6 +2,9 @@
 #include <stdarg.h>
 #include <string.h>
 #include <atomic>
+#include <map>
+#include <mutex>
+#include <utility>
 #include "common.cuh"
 
 namespace tn {
@@ -16,13 +19,26 @@ static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launches() { return g_launches.load(std::memory_order_relaxed); }
 int sm_count() {
-    static int cached = 0;
-    if (cached) return cached;
+    static std::atomic<int> cached[64];
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64 && (n = cached[dev].load(std::memory_order_relaxed)) > 0) return n;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) return 148;
-    cached = n;
+    if (dev >= 0 && dev < 64) cached[dev].store(n, std::memory_order_relaxed);
     return n;
+}
+cudaError_t ensure_dyn_smem(const void* func, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void*>, size_t> done;
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t& have = done[std::make_pair(dev, func)];
+    if (bytes <= have) return cudaSuccess;
+    e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
 }
 }  // namespace tn
 

@@ -343,11 +343,7 @@ extern "C" int tn_bmm(const double* A, int64_t sA, int64_t iA, int64_t kA, const
     while (spb > 1 && spb * per > 64 * 1024) --spb;
     if (spb > S) spb = (int)S;
     const size_t smem = spb * per;
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        TN_CUDA(cudaFuncSetAttribute(bmm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    if (smem > 48 * 1024) TN_SMEM(bmm_kernel, smem);
     int64_t blocks = ceil_div64(S, spb);
     if (blocks > 16LL * sm_count()) blocks = 16LL * sm_count();
     bmm_kernel<<<(unsigned)blocks, 256, smem, as_stream(stream)>>>(A, sA, iA, kA, B, sB, kB, jB, out, S, I, K, J, accumulate, spb);

@@ -62,7 +62,12 @@ __device__ __forceinline__ double map_eval(int map_kind, const double* __restric
     return v;
 }
 
-int sm_count();
+int sm_count();   // of the calling thread's current device (cached per device)
+// Raise a kernel's dynamic shared-memory limit to at least `bytes` on the CURRENT device.  The attribute is per device and per
+// function; what has been set is remembered per (device, function) under a mutex, so a process that drives several GPUs (or
+// several host threads) configures each of them.
+cudaError_t ensure_dyn_smem(const void* func, size_t bytes);
+#define TN_SMEM(kernel, bytes) TN_CUDA(tn::ensure_dyn_smem(reinterpret_cast<const void*>(kernel), (size_t)(bytes)))
 // tensor-core trailing update of the blocked Cholesky (syrk_tc.cu)
 int64_t syrk_tc_work_floats(int64_t n, int kb);
 int syrk_tc_update(double* A, int64_t lda, int64_t P, int64_t c0, int64_t k0, int kb, float* X, const int* info, cudaStream_t st,

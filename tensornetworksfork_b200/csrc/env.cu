@@ -394,11 +394,7 @@ static int launch_env_dmma(const double* env_in, int64_t env_ld, int env_div, co
         const int64_t ntiles = ceil_div64(rows, ED_TR);
         if ((size_t)Kp * (NT * 8 + 8) * sizeof(double) <= 48 * 1024 && psmem <= 113 * 1024 && ntiles >= 4LL * sm_count() &&
             !getenv("TN_ENV_NO_PERSIST")) {
-            static size_t pconfigured = 0;
-            if (psmem > pconfigured) {
-                TN_CUDA(cudaFuncSetAttribute(env_dmma_persist_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-                pconfigured = psmem;
-            }
+            TN_SMEM(env_dmma_persist_kernel<NT>, psmem);
             int64_t grid = 2LL * sm_count();
             if (grid > ntiles) grid = ntiles;
             env_dmma_persist_kernel<NT><<<(unsigned)grid, ENV_THREADS, psmem, st>>>(env_in, env_ld, env_div, x, x_ld, map_kind, f, cdiv, core,
@@ -410,11 +406,7 @@ static int launch_env_dmma(const double* env_in, int64_t env_ld, int env_div, co
     }
     const size_t smem = ((size_t)ED_TR * ((r_in + 5) | 1) + (size_t)ED_TR * (f | 1) + (size_t)ED_KC * (NT * 8 + 8)) * sizeof(double);
     if (smem > 113 * 1024) return 1;   // would not leave room for two CTAs per SM: let the caller use the FMA kernel
-    static size_t configured = 0;
-    if (smem > configured) {
-        TN_CUDA(cudaFuncSetAttribute(env_dmma_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = smem;
-    }
+    TN_SMEM(env_dmma_kernel<NT>, smem);
     const int64_t grid = ceil_div64(rows, ED_TR);
     TN_CHECK_ARG(grid <= 0x7fffffff, "tn_env_update: too many rows");
     env_dmma_kernel<NT><<<(unsigned)grid, ENV_THREADS, smem, st>>>(env_in, env_ld, env_div, x, x_ld, map_kind, f, cdiv, core, out, out_ld,
@@ -497,12 +489,8 @@ extern "C" int tn_env_update(const double* env_in, int64_t env_ld, int env_div, 
     using Kern = void (*)(const double*, int64_t, int, const double*, int64_t, int, int, int, const double*, double*, int64_t,
                           const double*, int64_t, int, double*, int64_t, int, int, int);
     static const Kern kerns[6] = {env_kernel<8, 1>, env_kernel<8, 2>, env_kernel<8, 3>, env_kernel<8, 4>, env_kernel<8, 5>, env_kernel<16, 4>};
-    static size_t configured[6] = {0, 0, 0, 0, 0, 0};
     const int ki = (TXN == 16) ? 5 : CN - 1;
-    if (smem > configured[ki]) {
-        TN_CUDA(cudaFuncSetAttribute(kerns[ki], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[ki] = smem;
-    }
+    TN_SMEM(kerns[ki], smem);
     const int64_t grid = ceil_div64(rows, TR);
     TN_CHECK_ARG(grid <= 0x7fffffff, "tn_env_update: too many rows");
     kerns[ki]<<<(unsigned)grid, ENV_THREADS, smem, as_stream(stream)>>>(env_in, env_ld, env_div < 1 ? 1 : env_div, x, x_ld, map_kind, f,

@@ -353,11 +353,7 @@ static int launch_kr3(const tn_factor* fa, const tn_factor* fb, const tn_factor*
                         (size_t)(4 * GR_TU + 3 * GR_TV) * sizeof(short);
     TN_CHECK_ARG(smem <= 227 * 1024, "kr3: factor sizes %d,%d,%d need %zu B of shared memory", a.m, b.m, c.m, smem);
     TN_CHECK_ARG(a.m < 32768 && b.m < 32768 && c.m < 32768, "kr3: factor too large");
-    static size_t configured[4] = {0, 0, 0, 0};
-    if (smem > configured[MODE]) {
-        TN_CUDA(cudaFuncSetAttribute(kr3_f64_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured[MODE] = smem;
-    }
+    TN_SMEM(kr3_f64_kernel<MODE>, smem);
     const int64_t gx = ceil_div64(nU, GR_TU), gy = ceil_div64(nC, GR_TV);
     TN_CHECK_ARG(gy <= 65535 && ksplit <= 65535 && gx <= 0x7fffffff, "kr3: grid too large");
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)ksplit);
@@ -574,21 +570,13 @@ extern "C" int tn_rhs_kr3(const tn_factor* fa, const tn_factor* fb, const tn_fac
             const int vthreads = ((slots + 31) / 32) * 32 < 128 ? 128 : ((slots + 31) / 32) * 32;
             const size_t vsmem = (size_t)RS_ROWS * ((a.m | 1) + (bb.m | 1) + ((c.m + RS_PER) | 1) + 1) * sizeof(double);
             TN_CHECK_ARG(vsmem <= 200 * 1024, "tn_rhs_kr3: factors too wide for the small-core path");
-            static size_t vconfigured = 0;
-            if (vsmem > vconfigured) {
-                TN_CUDA(cudaFuncSetAttribute(rhs_small_vec_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)vsmem));
-                vconfigured = vsmem;
-            }
+            TN_SMEM(rhs_small_vec_kernel, vsmem);
             rhs_small_vec_kernel<<<ctas, vthreads, vsmem, as_stream(stream)>>>(a, bb, c, w, rows, work, rpc);
         } else {
             const int threads = rhs_small_threads(P);
             const size_t smem = (size_t)RS_ROWS * ((a.m | 1) + (bb.m | 1) + (c.m | 1) + 1) * sizeof(double);
             TN_CHECK_ARG(smem <= 200 * 1024, "tn_rhs_kr3: factors too wide for the small-core path");
-            static size_t configured = 0;
-            if (smem > configured) {
-                TN_CUDA(cudaFuncSetAttribute(rhs_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                configured = smem;
-            }
+            TN_SMEM(rhs_small_kernel, smem);
             rhs_small_kernel<<<ctas, threads, smem, as_stream(stream)>>>(a, bb, c, w, rows, work, rpc);
         }
         TN_LAUNCH_CHECK();

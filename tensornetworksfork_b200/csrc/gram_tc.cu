@@ -19,6 +19,7 @@
 // tiles, and drain the accumulator at flush points.  Operand stages are handed over with mbarriers:
 // full[s] (producers -> MMA, after fence.proxy.async) and empty[s] (tcgen05.commit -> producers).
 #include <stdlib.h>
+#include <atomic>
 #include <type_traits>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -57,8 +58,6 @@ struct TcParams {
     int split;        // 1 = 3xTF32, 0 = TF32
     int flush_rows;   // rows accumulated in fp32 before a drain to fp64 (multiple of TC_KC)
     int planar;       // 1: Z is staged piece-planar, Z[((s/16)*4 + (s%16)/4) * z_rows + row][s%4] (see gram_tc_kernel<.., PLANAR>)
-    const float* Vp;  // PLANAR + pre-staged V: ready hi / lo operand tiles, Vp[chunk][hi|lo][piece][q_c < nCp][4] (tc_vstage_kernel); else null
-    int nCp;          // q_c padded to whole V tiles
 };
 
 // ---- range scaling.  The operands are staged in fp32; factors of long chains span hundreds of binades (environments of a
@@ -142,31 +141,6 @@ tc_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict_
     }
 }
 
-// ---- optional second pre-pass (PLANAR only): the V operand, pair(f_c) split into hi / lo, exactly as the producers synthesise it
-//      (fp32 product of the two staged factor rows, hi = tf32_rn(v), lo = v - hi), written as ready tiles in the UMMA K-major order
-//      [16-row chunk][hi | lo][4-sample piece][q_c][4 samples]: a CTA's V tile of one piece is BN * 16 contiguous bytes.
-__global__ void __launch_bounds__(256)
-tc_vstage_kernel(const float* __restrict__ Z, int64_t zr, int vrow0, int mC, int nC, int nCp, int64_t npieces_total, float* __restrict__ Vp) {
-    const int64_t total = npieces_total * nCp;
-    for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t piece = idx / nCp;                 // = chunk * 4 + piece-in-chunk
-        const int q = (int)(idx - piece * nCp);
-        float4 h = make_float4(0.f, 0.f, 0.f, 0.f), l = h;
-        if (q < nC) {
-            int ic, jc;
-            pair_decode(q, mC, ic, jc);
-            const float4 a = *reinterpret_cast<const float4*>(Z + (piece * zr + vrow0 + ic) * 4);
-            const float4 b = *reinterpret_cast<const float4*>(Z + (piece * zr + vrow0 + jc) * 4);
-            const float4 v = mul4(a, b);
-            h = make_float4(tf32_rn(v.x), tf32_rn(v.y), tf32_rn(v.z), tf32_rn(v.w));
-            l = make_float4(v.x - h.x, v.y - h.y, v.z - h.z, v.w - h.w);
-        }
-        const int64_t chunk = piece >> 2, kp = piece & 3;
-        *reinterpret_cast<float4*>(Vp + (((chunk * 2 + 0) * 4 + kp) * nCp + q) * 4) = h;
-        *reinterpret_cast<float4*>(Vp + (((chunk * 2 + 1) * 4 + kp) * nCp + q) * 4) = l;
-    }
-}
-
 // TMEM accumulator -> registers -> (transpose through shared memory) -> fp64 atomic adds into M.
 // Warp w may touch TMEM lanes 32*(w%4)..+31 (= 32 rows of a U tile); the two producer warps that share a lane quarter
 // split the columns.  tcgen05.ld hands every lane one ROW; the 32x32 block is transposed through a padded shared
@@ -213,7 +187,7 @@ __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_tota
 }
 
 // PLANAR selects the layout of a raw-factor slot.  false: row-major, one Z row = TC_KC floats + 4 of padding (80 B), the layout all
-// measurements of round 1 were taken with.  true (opt-in, TN_TC_RAW_PLANAR=1, not yet run on hardware): four planes, one per
+// measurements of round 1 were taken with.  true (the default since round 2; TN_TC_RAW_ROWMAJOR=1 selects false): four planes, one per
 // 4-sample piece, plane p holding 16 B per Z row at p * plane_stride + row * 16 with plane_stride = 32 (mod 128), filled by FOUR
 // BULK COPIES (cp.async.bulk, one per plane, issued by one thread, completion on an mbarrier) from a staging buffer that the
 // pre-pass writes piece-planar.  Why: the round-1 ncu capture (profiles/r1_ncu_gram_tc_v6_hotspots.txt) attributes 6.1e9 of the
@@ -257,7 +231,7 @@ gram_tc_kernel(TcParams p) {
 
     if (tid == 0) {
         for (int s = 0; s < NS; ++s) {
-            mbar_init(&full[s], TC_PROD_WARPS + ((PLANAR && p.Vp) ? 1 : 0));   // + the thread that expects the bytes of the V tiles
+            mbar_init(&full[s], TC_PROD_WARPS);
             mbar_init(&empty[s], 1);
         }
         mbar_init(acc_full, 1);
@@ -437,21 +411,7 @@ gram_tc_kernel(TcParams p) {
                     store_split<SPLIT>(v, d, d + a_tile_bytes);
                 }
             }
-            const bool v_ready = PLANAR && p.Vp != nullptr;
-            if (v_ready) {
-                // ---- V tiles arrive ready-made: eight bulk copies of BN * 16 bytes (hi / lo x four pieces) completing on full[s]
-                if (pt == 0) {
-                    const uint32_t bar = smem_u32(&full[s]);
-                    const uint32_t tile_piece = (uint32_t)BN * 16;
-                    const float* src = p.Vp + (((k_begin / TC_KC + c) * 2) * 4 * (int64_t)p.nCp + v0) * 4;
-                    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(8 * tile_piece) : "memory");
-#pragma unroll
-                    for (int hp = 0; hp < 8; ++hp)      // hp = half * 4 + piece
-                        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                     ::"r"(sb + 2 * T * a_tile_bytes + (uint32_t)(hp >> 2) * b_tile_bytes + (uint32_t)(hp & 3) * lbo_b),
-                                       "l"(src + (int64_t)hp * p.nCp * 4), "r"(tile_piece), "r"(bar) : "memory");
-                }
-            } else if (pt < BN) {   // ---- V rows
+            if (pt < BN) {   // ---- V rows
                 float4 y0[TC_KC / 4], y1[TC_KC / 4];
 #pragma unroll
                 for (int cc = 0; cc < TC_KC / 4; ++cc) {
@@ -795,8 +755,6 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     p.nC = npairs(C.m);
     p.split = (mode == 2) ? 1 : 0;
     p.planar = 0;
-    p.Vp = nullptr;
-    p.nCp = 0;
     p.flush_rows = TC_FLUSH_ROWS_DEFAULT;
     if (const char* e = getenv("TN_TC_FLUSH_ROWS")) {
         const int v = atoi(e);
@@ -824,15 +782,15 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     const int z_rows = 2 * A.m + B.m + C.m;
     {   // keep freed scratch in the stream-ordered pool: the default threshold (0) returns it to the OS at every sync,
         // which made each call pay a fresh multi-hundred-MB allocation
-        static bool pool_ready = false;
-        if (!pool_ready) {
-            int dev = 0;
+        static std::atomic<unsigned long long> pool_ready{0};     // one bit per device
+        int dev = 0;
+        TN_CUDA(cudaGetDevice(&dev));
+        if (!((pool_ready.load(std::memory_order_relaxed) >> (dev & 63)) & 1ull)) {
             cudaMemPool_t pool;
-            TN_CUDA(cudaGetDevice(&dev));
             TN_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
             unsigned long long keep = ~0ull;
             TN_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-            pool_ready = true;
+            pool_ready.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
         }
     }
     float* Z = nullptr;
@@ -849,26 +807,15 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
         tc_absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, B, C, w, rows, amax);
         TN_LAUNCH_CHECK();
         dim3 grid((unsigned)ceil_div64(p.zpitch, 32), (unsigned)ceil_div64(A.m + B.m + C.m, 32));
-        // planar raw slots + bulk-copy fill: opt-in until measured.  Needs the four planes to fit the slot pitch of the row-major
-        // layout (80 B per Z row) and 32 more bytes of shared memory for the slots' barriers; the CTA-pair kernel stays row-major.
-        p.planar = (getenv("TN_TC_RAW_PLANAR") && !getenv("TN_TC_PAIR") &&
+        // planar raw slots + bulk-copy fill: the default since round 2 (measured on the config-5a middle site, 131 072 rows:
+        // 588 vs 575 TF/s issued, M bit-identical; profiles/r2_tc_variants.txt); TN_TC_RAW_ROWMAJOR=1 selects the cp.async ring.
+        // Needs the four planes to fit the slot pitch of the row-major layout (80 B per Z row) and 32 more bytes of shared
+        // memory for the slots' barriers; the CTA-pair kernel stays row-major.
+        p.planar = (!getenv("TN_TC_RAW_ROWMAJOR") && !getenv("TN_TC_PAIR") &&
                     4 * ((((size_t)(z_rows + 1) * 16 + 95) / 128) * 128 + 32) <= (size_t)(z_rows + 1) * TC_KCP * 4 &&
                     smem + 32 <= 227 * 1024) ? 1 : 0;
         tc_stage_kernel<<<grid, 256, 0, st>>>(A, B, C, w, rows, Z, p.zpitch, amax, p.planar);
         TN_LAUNCH_CHECK();
-    }
-    // pre-staged V operand (opt-in on top of the planar ring, 3xTF32 only): TN_TC_V_PRESTAGE=1
-    float* Vp = nullptr;
-    if (p.planar && p.split && getenv("TN_TC_V_PRESTAGE")) {
-        p.nCp = (int)(ceil_div64(p.nC, p.BN) * p.BN);
-        const size_t v_bytes = (size_t)p.zpitch * 2 * p.nCp * sizeof(float);
-        TN_CUDA(cudaMallocAsync(&Vp, v_bytes, st));
-        const int64_t npieces_total = p.zpitch / 4;
-        int64_t blocks = ceil_div64(npieces_total * p.nCp, 256);
-        if (blocks > 64LL * sm_count()) blocks = 64LL * sm_count();
-        tc_vstage_kernel<<<(unsigned)blocks, 256, 0, st>>>(Z, (int64_t)z_rows, 2 * A.m + B.m, C.m, p.nC, p.nCp, npieces_total, Vp);
-        TN_LAUNCH_CHECK();
-        p.Vp = Vp;
     }
     // CTA-pair kernel (opt-in, TN_TC_PAIR=1).  Measured on the config-5a middle site (131 072 rows, tools/tc_pair_probe.py):
     // bit-identical M, but 530 vs 557 TF/s issued in 3xTF32 and 217 vs 268 in TF32 -- the 1-CTA kernel already runs at ~0.9 of
@@ -893,11 +840,7 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
         ksp = ceil_div64(p.zpitch, p.rows_per_split);
         using KernP = void (*)(TcParams);
         static const KernP pk[2] = {gram_tc_pair_kernel<0>, gram_tc_pair_kernel<1>};
-        static size_t pconfigured[2] = {};
-        if (psmem > pconfigured[p.split]) {
-            TN_CUDA(cudaFuncSetAttribute(pk[p.split], cudaFuncAttributeMaxDynamicSharedMemorySize, (int)psmem));
-            pconfigured[p.split] = psmem;
-        }
+        TN_SMEM(pk[p.split], psmem);
         dim3 pgrid((unsigned)gxp, (unsigned)gyp, (unsigned)ksp);
         pk[p.split]<<<pgrid, TC_THREADS, psmem, st>>>(p);
         TN_LAUNCH_CHECK();
@@ -919,18 +862,13 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
                                          {gram_tc_kernel<1, 1, false>, gram_tc_kernel<1, 2, false>}},
                                         {{gram_tc_kernel<0, 1, true>, gram_tc_kernel<0, 2, true>},
                                          {gram_tc_kernel<1, 1, true>, gram_tc_kernel<1, 2, true>}}};
-    static size_t configured[2][2][2] = {};
     const int planar = p.planar;
     const size_t smem_k = smem + (planar ? 32 : 0);          // + the three barriers of the raw slots
     Kern k = kerns[planar][p.split][p.T - 1];
-    if (smem_k > configured[planar][p.split][p.T - 1]) {
-        TN_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_k));
-        configured[planar][p.split][p.T - 1] = smem_k;
-    }
+    TN_SMEM(k, smem_k);
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)ks);
     k<<<grid, TC_THREADS, smem_k, st>>>(p);
     TN_LAUNCH_CHECK();
-    if (Vp) TN_CUDA(cudaFreeAsync(Vp, st));
     TN_CUDA(cudaFreeAsync(Z, st));
     return TN_OK;
 }

@@ -100,11 +100,7 @@ extern "C" int tn_qr(double* a, int m, int n, double* r, void* stream) {
     double* q_g = nullptr;
     cudaStream_t st = as_stream(stream);
     if (!use_smem) TN_CUDA(cudaMallocAsync(&q_g, (size_t)m * n * sizeof(double), st));
-    static size_t configured = 0;
-    if (use_smem && bytes > configured) {
-        TN_CUDA(cudaFuncSetAttribute(qr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-        configured = bytes;
-    }
+    if (use_smem) TN_SMEM(qr_kernel, bytes);
     qr_kernel<<<1, QR_THREADS, use_smem ? bytes : 0, st>>>(a, m, n, r, q_g, use_smem);
     TN_LAUNCH_CHECK();
     if (q_g) TN_CUDA(cudaFreeAsync(q_g, st));

@@ -632,13 +632,9 @@ trsv_bwd_panel_kernel(const double* __restrict__ A, int64_t lda, int64_t j0, int
 static int cholesky_configure() {
     constexpr size_t kBlkSmem = 2 * CH_NB * (CH_NB + 1) * sizeof(double);   // trsm needs two blocks, potrf one
     constexpr size_t kDmmaSmem = (size_t)2 * DS_STAGES * DS_BT * DS_LD * sizeof(double);
-    static bool configured = false;
-    if (!configured) {
-        TN_CUDA(cudaFuncSetAttribute(syrk_update_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDmmaSmem));
-        TN_CUDA(cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkSmem));
-        TN_CUDA(cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkSmem));
-        configured = true;
-    }
+    TN_SMEM(syrk_update_dmma_kernel, kDmmaSmem);
+    TN_SMEM(potrf_diag_kernel, kBlkSmem);
+    TN_SMEM(trsm_panel_kernel, kBlkSmem);
     return TN_OK;
 }
 
@@ -649,13 +645,12 @@ static int cholesky_factorize(double* A, int64_t lda, int64_t P, double* work, i
     constexpr size_t kDmmaSmem = (size_t)2 * DS_STAGES * DS_BT * DS_LD * sizeof(double);
     int rc = cholesky_configure();
     if (rc != TN_OK) return rc;
-    static int coop_ok = -1;
-    if (coop_ok < 0) {
-        int dev = 0, v = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev);
-        coop_ok = v;
-        if (v) TN_CUDA(cudaFuncSetAttribute(cholesky_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kBlkSmem));
+    int coop_ok = 0;
+    {
+        int dev = 0;
+        TN_CUDA(cudaGetDevice(&dev));
+        TN_CUDA(cudaDeviceGetAttribute(&coop_ok, cudaDevAttrCooperativeLaunch, dev));
+        if (coop_ok) TN_SMEM(cholesky_fused_kernel, kBlkSmem);
     }
     if (coop_ok && P <= CF_MAXP && P > CH_NB && !X && !getenv("TN_CHOL_NO_FUSED")) {
         int Pi = (int)P;
@@ -744,11 +739,7 @@ static int cholesky_substitute(const double* A, int64_t lda, int64_t P, double* 
                                cudaStream_t st) {
     if (P <= TS_MAXP) {
         const size_t smem = ((size_t)ceil_div64(P, 64) * 64 + 64) * sizeof(double);
-        static size_t ts_configured = 0;
-        if (smem > ts_configured) {
-            TN_CUDA(cudaFuncSetAttribute(trsv_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            ts_configured = smem;
-        }
+        TN_SMEM(trsv_small_kernel, smem);
         trsv_small_kernel<<<1, 1024, smem, st>>>(A, lda, (int)P, rhs, work, stop);
         TN_LAUNCH_CHECK();
         return TN_OK;

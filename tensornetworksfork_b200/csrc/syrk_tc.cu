@@ -251,11 +251,7 @@ int syrk_tc_update(double* A, int64_t lda, int64_t P, int64_t c0, int64_t k0, in
                    int64_t col_limit) {
     const int64_t n = P - c0;
     if (n <= 0 || kb <= 0) return TN_OK;
-    static bool configured = false;
-    if (!configured) {
-        TN_CUDA(cudaFuncSetAttribute(syrk_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ST_SMEM));
-        configured = true;
-    }
+    TN_SMEM(syrk_tc_kernel, ST_SMEM);
     SyrkTcParams p;
     p.pitch = ceil_div64(kb, ST_KC) * ST_KC;
     const int64_t nt = ceil_div64(n, ST_TILE);

@@ -5,6 +5,7 @@ hand-written kernels of libtn_b200.so on torch's current CUDA stream.  No functi
 implementation: a non-CUDA tensor raises.
 """
 import ctypes
+import functools
 from dataclasses import dataclass
 
 import torch
@@ -25,6 +26,9 @@ class Factor:
     map_kind: int = MAP_IDENTITY
     col: int = 0  # first column read (raw feature index for SINCOS / POLY)
 
+    def __post_init__(self):
+        _unit_rows(self.tensor, "factor")
+
     @property
     def ld(self):
         return self.tensor.stride(0) if self.tensor.dim() == 2 else 1
@@ -36,7 +40,19 @@ class Factor:
         return tn_factor(self.ptr(), self.ld, self.m, self.div, self.map_kind, 0)
 
 
+def _unit_rows(t, what="operand"):
+    """Layout contract of every row-indexed operand (factors, environments, outputs): at most 2-D, unit stride inside a row, a
+    non-negative row stride (0 = one row shared by all samples, which the kernels only ever pair with a huge divisor) -- a transposed
+    or broadcast view would be read out of layout, so it is refused here instead."""
+    if t is None:
+        return
+    if t.dim() > 2 or (t.dim() >= 1 and t.shape[-1] > 1 and t.stride(-1) != 1) or (t.dim() == 2 and t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        raise _lib.TnError(f"{what}: rows with unit inner stride expected, got shape {tuple(t.shape)} with strides {t.stride()}")
+
+
 def _need_cuda(*ts):
+    """All operands are fp64 CUDA tensors on ONE device; returns that device."""
+    dev = None
     for t in ts:
         if t is None:
             continue
@@ -44,6 +60,50 @@ def _need_cuda(*ts):
             raise _lib.TnError("tensornetworksfork_b200 kernels need CUDA tensors; there is no CPU path")
         if t.dtype != torch.float64:
             raise _lib.TnError(f"fp64 tensors expected, got {t.dtype}")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise _lib.TnError(f"operands live on different devices ({dev} and {t.device})")
+    return dev
+
+
+class _on:
+    """Make `dev` the current CUDA device for the duration of a call (kernels launch on the calling thread's current device, and
+    the stream handed to the library has to belong to it); free when it already is."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.ctx = None
+
+    def __enter__(self):
+        if self.dev is not None and self.dev.index is not None and self.dev.index != torch.cuda.current_device():
+            self.ctx = torch.cuda.device(self.dev)
+            self.ctx.__enter__()
+        return self
+
+    def __exit__(self, *a):
+        if self.ctx is not None:
+            self.ctx.__exit__(*a)
+        return False
+
+
+def _op(fn):
+    """Run a wrapper with the operands' device current (a process driving several GPUs launched on the wrong one)."""
+
+    @functools.wraps(fn)
+    def inner(*a, **k):
+        dev = None
+        for v in list(a) + list(k.values()):
+            t = v.tensor if isinstance(v, Factor) else v
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                if dev is None:
+                    dev = t.device
+                elif t.device != dev:
+                    raise _lib.TnError(f"operands live on different devices ({dev} and {t.device})")
+        with _on(dev):
+            return fn(*a, **k)
+
+    return inner
 
 
 def _bare(*ts):
@@ -51,6 +111,13 @@ def _bare(*ts):
     for t in ts:
         if t is not None and not t.is_contiguous():
             raise _lib.TnError(f"dense tensor expected, got shape {tuple(t.shape)} with strides {t.stride()}")
+
+
+def _system_layout(A, rhs_vec, P):
+    if A.dim() != 2 or A.stride(1) != 1 or A.stride(0) < P or A.shape[1] < P:
+        raise _lib.TnError(f"system matrix must be ({P}, >= {P}) with unit inner stride, got {tuple(A.shape)} / {A.stride()}")
+    if rhs_vec.numel() != P or not rhs_vec.is_contiguous():
+        raise _lib.TnError(f"right-hand side must be a dense vector of {P}, got {tuple(rhs_vec.shape)} / {rhs_vec.stride()}")
 
 
 def _stream():
@@ -65,12 +132,15 @@ def ones_factor(like):
     return Factor(torch.ones(1, 1, dtype=torch.float64, device=like.device), m=1, div=1 << 30)
 
 
+@_op
 def env_update(env_in, x: Factor, core3, rows, cdiv=1, env_div=1, out=None):
     """out[row,b] = sum_{a,p} env_in[row/env_div,a] phi[row/cdiv,p] core3[a,p,b]."""
     lib = _lib.load()
     r_in, f, r_out = core3.shape
     core3 = core3.contiguous()
-    _need_cuda(env_in, x.tensor, core3)
+    _need_cuda(env_in, x.tensor, core3, out)
+    _unit_rows(env_in, "env_in")
+    _unit_rows(out, "out")
     if out is None:
         out = torch.empty((rows, r_out), dtype=torch.float64, device=core3.device)
     env_ld = env_in.stride(0) if env_in is not None else 0
@@ -80,12 +150,16 @@ def env_update(env_in, x: Factor, core3, rows, cdiv=1, env_div=1, out=None):
     return out
 
 
+@_op
 def predict(env_in, x: Factor, core3, dot, rows, cdiv=1, env_div=1, dot_div=1, out=None):
     """yhat[row] = sum_{a,p,b} env_in[row/env_div,a] phi[row/cdiv,p] core3[a,p,b] dot[row/dot_div,b]."""
     lib = _lib.load()
     r_in, f, r_out = core3.shape
     core3 = core3.contiguous()
-    _need_cuda(env_in, x.tensor, core3, dot)
+    _need_cuda(env_in, x.tensor, core3, dot, out)
+    _unit_rows(env_in, "env_in")
+    _unit_rows(dot, "dot")
+    _bare(out)
     if out is None:
         out = torch.empty((rows,), dtype=torch.float64, device=core3.device)
     env_ld = env_in.stride(0) if env_in is not None else 0
@@ -95,6 +169,7 @@ def predict(env_in, x: Factor, core3, dot, rows, cdiv=1, env_div=1, dot_div=1, o
     return out
 
 
+@_op
 def class_rows(env, U, g):
     """F[(s,t),a] = sum_c U[s,t,c] env[s,c,a];  G[s,a] = sum_c g[s,c] env[s,c,a]."""
     lib = _lib.load()
@@ -119,6 +194,7 @@ def npairs(m):
     return m * (m + 1) // 2
 
 
+@_op
 def gram(mode, fa: Factor, fb: Factor, fc: Factor, w, rows, M=None, accumulate=False):
     """M[qa,qb,qc] (+)= sum_rows w * pair(fa)[qa] * pair(fb)[qb] * pair(fc)[qc]."""
     lib = _lib.load()
@@ -140,6 +216,7 @@ def gram(mode, fa: Factor, fb: Factor, fc: Factor, w, rows, M=None, accumulate=F
     return M
 
 
+@_op
 def rhs(fa: Factor, fb: Factor, fc: Factor, w, rows, b=None, accumulate=False):
     """b[ia,ib,ic] (+)= sum_rows w * fa[ia] fb[ib] fc[ic]."""
     lib = _lib.load()
@@ -159,6 +236,7 @@ def rhs(fa: Factor, fb: Factor, fc: Factor, w, rows, b=None, accumulate=False):
     return b
 
 
+@_op
 def gram_generic(f1: Factor, f2: Factor, f3: Factor, t1, t2, t3, w, rows, rhs_only=False, out=None, accumulate=False):
     """Dense Gram J^T diag(w) J (P x P) or right-hand side J^T w (P) of J[:, i] = f1[t1[i]] f2[t2[i]] f3[t3[i]]."""
     lib = _lib.load()
@@ -185,6 +263,7 @@ def _int3(v):
     return (ctypes.c_int * 3)(*v)
 
 
+@_op
 def gram_sigma(M, m_pos, role_of_pos):
     lib = _lib.load()
     sigma = torch.empty((1,), dtype=torch.float64, device=M.device)
@@ -192,6 +271,7 @@ def gram_sigma(M, m_pos, role_of_pos):
     return sigma
 
 
+@_op
 def gram_expand(M, m_pos, role_of_pos, sigma, ridge, A=None):
     """Dense scaled system A = expand(M)/sigma + ridge*I, row stride padded to a multiple of 8."""
     lib = _lib.load()
@@ -199,11 +279,16 @@ def gram_expand(M, m_pos, role_of_pos, sigma, ridge, A=None):
     lda = (P + 7) // 8 * 8
     if A is None:
         A = torch.empty((P, lda), dtype=torch.float64, device=M.device)
+    elif A.dim() != 2 or A.shape[0] != P or A.stride(1) != 1 or A.stride(0) < P:
+        raise _lib.TnError(f"gram_expand: A must be ({P}, >= {P}) with unit inner stride, got {tuple(A.shape)} / {A.stride()}")
+    _need_cuda(M, sigma, A)
+    _bare(M)
     _lib.check(lib.tn_gram_expand(_p(M), _int3(m_pos), _int3(role_of_pos), _p(sigma), float(ridge), _p(A), A.stride(0),
                                   _stream()), "tn_gram_expand")
     return A
 
 
+@_op
 def rhs_prepare(b, theta, sigma, ridge):
     lib = _lib.load()
     P = b.numel()
@@ -213,11 +298,13 @@ def rhs_prepare(b, theta, sigma, ridge):
     return out
 
 
+@_op
 def cholesky_solve(A, rhs_vec):
     """In place: A (P x lda) <- its Cholesky factor (lower), rhs_vec <- solution.  Returns info tensor."""
     lib = _lib.load()
     P = A.shape[0]
     _need_cuda(A, rhs_vec)
+    _system_layout(A, rhs_vec, P)
     work = torch.empty((lib.tn_cholesky_work_elems(P),), dtype=torch.float64, device=A.device)
     info = torch.zeros((1,), dtype=torch.int32, device=A.device)
     _lib.check(lib.tn_cholesky_solve(_p(A), A.stride(0), P, _p(rhs_vec), _p(work), ctypes.c_void_p(info.data_ptr()),
@@ -225,12 +312,14 @@ def cholesky_solve(A, rhs_vec):
     return info
 
 
+@_op
 def cholesky_solve_mixed(A, rhs_vec, rtol=1e-12, max_iter=12):
     """Tensor-core (3xTF32) factorisation + fp64 conjugate-gradient refinement.  A (P x lda, full symmetric) is overwritten
     below the diagonal, rhs_vec <- solution.  Returns (info, stats) device tensors; stats = [relative residual, iterations]."""
     lib = _lib.load()
     P = A.shape[0]
     _need_cuda(A, rhs_vec)
+    _system_layout(A, rhs_vec, P)
     work = torch.empty((lib.tn_cholesky_mixed_work_elems(P),), dtype=torch.float64, device=A.device)
     info = torch.zeros((1,), dtype=torch.int32, device=A.device)
     stats = torch.zeros((2,), dtype=torch.float64, device=A.device)
@@ -239,6 +328,7 @@ def cholesky_solve_mixed(A, rhs_vec, rtol=1e-12, max_iter=12):
     return info, stats
 
 
+@_op
 def update_node(theta, step, lr=1.0, adaptive_step=False, max_norm=None):
     """theta (contiguous) <- theta + lr*step, in place."""
     lib = _lib.load()
@@ -249,6 +339,7 @@ def update_node(theta, step, lr=1.0, adaptive_step=False, max_norm=None):
     return theta
 
 
+@_op
 def qr(a):
     """a (m x n contiguous, m >= n) <- Q in place; returns R (n x n)."""
     lib = _lib.load()
@@ -260,6 +351,7 @@ def qr(a):
     return r
 
 
+@_op
 def matvec(fa: Factor, fb: Factor, fc: Factor, w, rows, v, out=None):
     """out = J^T diag(w) J v with J[row,(ia,ib,ic)] = fa fb fc."""
     lib = _lib.load()
@@ -276,6 +368,7 @@ def matvec(fa: Factor, fb: Factor, fc: Factor, w, rows, v, out=None):
     return out
 
 
+@_op
 def bmm(A, B, out=None, accumulate=False):
     """Per-sample matrix products out[s] (+)= A[s] @ B[s].  A: (S, I, K) or (I, K) shared; B: (S, K, J) or (K, J) shared;
     any strides (views are not copied).  Returns (S, I, J) contiguous."""
@@ -295,6 +388,7 @@ def bmm(A, B, out=None, accumulate=False):
     return out
 
 
+@_op
 def outer_rows(G, W, w=None, gdiv=1, out=None, accumulate=False):
     """out (ra, m) (+)= sum_row w[row] * G[row // gdiv, :]^T W[row, :]; G (rows/gdiv, ra), W (rows, m), row strides free."""
     lib = _lib.load()
@@ -312,6 +406,7 @@ def outer_rows(G, W, w=None, gdiv=1, out=None, accumulate=False):
     return out
 
 
+@_op
 def rows_dot(W, V, out=None):
     """z (rows, ra) = W (rows, m) @ V (ra, m)^T; row strides free, last dims contiguous.  ``out`` may be a 2-D view with its own row
     stride (a column block of a larger tensor)."""
