@@ -237,8 +237,10 @@ class KernelTimer:
                 raw_b = 1 if fb.map_kind != 0 else fb.m
                 # two passes over the three factors (8 B each), J v written and read once, weights read once
                 self.extra[n].append(2 * 8.0 * rows * (fa.m / fa.div + raw_b / fb.div + fc.m / fc.div) + 3 * 8.0 * rows)
-            elif n in ("cholesky_solve", "cholesky_solve_mixed"):
+            elif n in ("cholesky_solve", "cholesky_solve_mixed", "cholesky_factor"):
                 self.extra[n].append(int(a[0].shape[0]))
+            elif n in ("cg", "minres", "lanczos"):
+                self.extra[n].append(out[1])          # the stats tensor (device): read after the timed region
             return out
 
         return inner
@@ -311,7 +313,8 @@ def bench_b200(args):
     if wl.get("orthonormalize"):
         tn.orthonormalize_left()
 
-    timer = KernelTimer(ops, ["gram", "rhs", "env_update", "predict", "cholesky_solve", "cholesky_solve_mixed", "gram_expand", "matvec", "outer_rows", "rows_dot", "bmm"])
+    timer = KernelTimer(ops, ["gram", "rhs", "env_update", "predict", "cholesky_solve", "cholesky_solve_mixed", "cholesky_factor", "cg", "minres",
+                              "lanczos", "gram_trace", "gram_expand", "matvec", "outer_rows", "rows_dot", "bmm"])
     timer.install()
     counter = [0]
 
@@ -390,6 +393,32 @@ def bench_b200(args):
                       "+ forward on 1024 rows + .item() of its MSE; `value` is the device time of those sweeps after the copies",
                "fit_mse_last": got[-1] if got else None}
 
+    # ---- accuracy of the timed mode, measured (untimed) on a row subsample of this rank's data: the tensor-core Gram of the largest
+    # site against the fp64 Gram kernel on the same rows, and what the refinement did inside the timed sweeps
+    accuracy = None
+    if args.gram_mode != "fp64" and wl["kind"] in ("tt", "cpd") and not wl.get("solver") and rank == 0:
+        try:
+            sub = min(n, 32768)
+            xs = wrap_input(wl, (Xh[:sub] if e2e_mode else X[:sub]).to(dev))
+            ys = (yh[:sub] if e2e_mode else y[:sub]).to(dev)
+            tn.set_input(xs)
+            tn._check_external()
+            sizes = [nd.tensor.numel() for nd in tn.main_nodes]
+            kbig = int(np.argmax(sizes))
+            pg, tn.process_group = tn.process_group, None
+            prob = tn._site_problem(kbig, ys, tnb.SquareBregFunction() if wl["C"] == 1 else tnb.XEAutogradBregman(w=1.0))
+            M_tc = tn._accumulate(prob, args.gram_mode)[0].clone()
+            M_64 = tn._accumulate(prob, "fp64")[0]
+            tn.process_group = pg
+            accuracy = {"gram_rel_err": float(((M_tc - M_64).norm() / M_64.norm()).item()), "gram_rel_err_rows": sub,
+                        "gram_rel_err_site": kbig, "tc_flush_rows": tn.tc_flush_rows if tn.refine == "exact" else 2048,
+                        "gram_rel_err_is": "relative Frobenius error of the unique Gram entries M, timed mode vs fp64 kernel, same rows",
+                        "refine": tn.refine, "refine_rtol": tn.refine_rtol,
+                        "refine_note": "refine='exact': M only preconditions conjugate gradients on the fp64 matrix-free operator; the step "
+                                       "solves the reference's fp64 system to refine_max_rel (solve.stats)"}
+            del M_tc, M_64, prob
+        except Exception as e:          # the accuracy probe must never cost the line
+            accuracy = {"error": f"{type(e).__name__}: {e}"}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -496,13 +525,22 @@ def bench_b200(args):
                     "matvecs_per_site_update": len(mv_ms) / max(updates, 1),
                     "mean_us_per_matvec": 1e3 * sum(mv_ms) / max(len(mv_ms), 1), "measured_peaks": measured}
         wl = dict(wl, _avg_matvecs=len(mv_ms) / max(updates, 1))
-    chol_ms = tot["cholesky_solve"] + tot["cholesky_solve_mixed"]
-    chol_flops = sum(P_ ** 3 / 3.0 for P_ in timer.extra["cholesky_solve"] + timer.extra["cholesky_solve_mixed"])
-    n_mixed = len(tot["cholesky_solve_mixed"])
-    solve_info = {"kernel": "cholesky_solve[fp64]" if n_mixed == 0 else "cholesky_solve_mixed[3xTF32 tcgen05 trailing updates + fp64 CG refinement] / cholesky_solve[fp64] for small systems",
+    chol_ms = tot["cholesky_solve"] + tot["cholesky_solve_mixed"] + tot["cholesky_factor"]
+    chol_flops = sum(P_ ** 3 / 3.0 for P_ in timer.extra["cholesky_solve"] + timer.extra["cholesky_solve_mixed"] + timer.extra["cholesky_factor"])
+    n_mixed = len(tot["cholesky_solve_mixed"]) + int(tn.solve_stats.get("mixed", 0) > 0)
+    cg_stats = [st.tolist() for st in timer.extra["cg"]]
+    refine_info = None
+    if cg_stats and not wl.get("solver"):
+        refine_info = {"solves": len(cg_stats), "iterations_mean": float(np.mean([c_[1] for c_ in cg_stats])),
+                       "iterations_max": float(np.max([c_[1] for c_ in cg_stats])), "rel_residual_max": float(np.max([c_[0] for c_ in cg_stats])),
+                       "ms_mean": float(np.mean(tot["cg"])), "share_of_step": sum(tot["cg"]) / ms,
+                       "what": "tn_cg: conjugate gradients on the fp64 matrix-free operator J^T W J / sigma + ridge, preconditioned by the "
+                               "Cholesky factor of the tensor-core Gram; the residual is that of the reference's fp64 system"}
+    solve_info = {"kernel": "cholesky[fp64]" if n_mixed == 0 else "cholesky[3xTF32 tcgen05 trailing updates] for P >= 8192 / cholesky[fp64] for small systems",
                   "tflops_equiv": chol_flops / (sum(chol_ms) / 1e3) / 1e12 if chol_ms else None,
-                  "share_of_step": sum(chol_ms) / ms, "fp64_peak": measured["fp64_tflops_sustained"] if measured else 35.5,
-                  "mode": tn.solve_mode, "stats": dict(tn.solve_stats),
+                  "share_of_step": (sum(chol_ms) + sum(tot["cg"])) / ms, "factor_share_of_step": sum(chol_ms) / ms,
+                  "fp64_peak": measured["fp64_tflops_sustained"] if measured else 35.5,
+                  "mode": tn.solve_mode, "stats": dict(tn.solve_stats), "refinement": refine_info,
                   "largest_ms": max(chol_ms) if chol_ms else None}
     shares = {k: sum(v) / ms for k, v in tot.items()}
     out = {"metric": "gn_sample_site_updates_per_s", "value": value, "unit": "sample-site-updates/s", "site_updates_per_s": site_rate,
@@ -514,7 +552,7 @@ def bench_b200(args):
                       "l2": "inputs larger than L2 (per-site streams of rows*(r_l+f+r_r)*8 B)", "parallelism": f"sample-shard x{world}"},
            "roofline": roofline, "solve": solve_info, "kernel_time_share": shares,
            "gpu_launches": launches,
-           "clocks": clk, "e2e": e2e}
+           "clocks": clk, "e2e": e2e, "accuracy": accuracy}
     if not args.no_cpu_baseline and world == 1:      # the CPU baseline is a rank-0, N = 1 figure (the driver's reference arm covers N > 1)
         out["cpu_baseline"] = cpu_baseline_leg(args, wl, n * world)
     sys.stdout.flush()

@@ -86,6 +86,10 @@ int tn_gram_ksplit(int64_t rows, int ma, int mb, int mc, int mode);
 int tn_gram_kr3(int mode, const tn_factor *fa, const tn_factor *fb, const tn_factor *fc, const double *w,
                 int64_t rows, double *M, double *work, int ksplit, int accumulate, void *stream);
 
+/* Tensor-core modes: rows accumulated in fp32 (TMEM) between two fp64 flushes, for later calls of the calling thread; returns
+ * the previous value; 0 = default (2048), negative = query only.                                    */
+int tn_gram_tc_flush_rows(int rows);
+
 /* b[ia, ib, ic] (+)= sum_rows w[row] * fa[ia] * fb[ib] * fc[ic]    (network.py:215)            */
 int tn_rhs_ksplit(int64_t rows, int ma, int mb, int mc);
 int tn_rhs_kr3(const tn_factor *fa, const tn_factor *fb, const tn_factor *fc, const double *w, int64_t rows,
@@ -143,6 +147,65 @@ int tn_qr(double *a, int m, int n, double *r, void *stream);
 int64_t tn_matvec_work_elems(int64_t rows, int ma, int mb, int mc);
 int tn_matvec_kr3(const tn_factor *fa, const tn_factor *fb, const tn_factor *fc, const double *w, int64_t rows,
                   const double *v, double *out, double *work, void *stream);
+
+/* ---- on-device Krylov drivers: the local solves of lanczos_swipe / scipy_swipe (tensor/network.py:770-832, 896-932; the
+ *      reference runs SciPy's cg / minres on the host in float32, or an eager torch loop for Lanczos), and the exact
+ *      refinement of the tensor-core Gram modes.  The operator is
+ *          Op v = A0 v / sigma[0] + ridge * v          (sigma == NULL: 1)
+ *      with A0 either built in -- J^T diag(w) J of this rank's rows from three Kronecker factors (apply == NULL) -- or
+ *      enqueued by the caller's `apply` callback; `allreduce`, when set, sums the P-vector A0 v over the ranks of a
+ *      sample-sharded run (replaces the missing collective of the reference) before the scaling.
+ *      All recurrence scalars stay on the device.  Unlike the other entry points these drivers SYNCHRONISE the stream every
+ *      `poll_every` iterations to read the convergence flag (poll_every == 0: never -- a fixed sequence of launches whose
+ *      kernels turn into no-ops once converged, capturable in a CUDA graph).
+ *      stats (4 device doubles, may be NULL): [0] relative residual reached (cg: |b - Op x| / |b|; minres: its estimate
+ *      phibar / |b|; lanczos: the last beta), [1] iterations, [2] 1 if stopped by the tolerance, [3] operator applications. */
+typedef int (*tn_apply_fn)(void *ctx, const double *v, double *out, void *stream);
+typedef int (*tn_allreduce_fn)(void *ctx, double *buf, int64_t n, void *stream);
+typedef struct tn_operator {
+    const tn_factor *fa, *fb, *fc; /* built-in operator (apply == NULL); only fb may carry a feature map      */
+    const double *w;               /* row weights or NULL                                                     */
+    int64_t rows;
+    tn_apply_fn apply;             /* or: enqueue out = A0 v on `stream`                                      */
+    void *apply_ctx;
+    tn_allreduce_fn allreduce;     /* optional: enqueue the in-place sum of buf[0..n) over the ranks          */
+    void *allreduce_ctx;
+    const double *sigma;           /* device scalar or NULL                                                   */
+    double ridge;
+    int64_t P;
+    int32_t apply_is_global;       /* != 0: `apply` already sums over the ranks; `allreduce` then only serves the
+                                      collective convergence decision (ranks must leave the iteration together) */
+    int32_t _pad;
+} tn_operator;
+
+/* Conjugate gradients on Op x = b (scipy.sparse.linalg.cg as called at network.py:921-925: stop at |r| <= rtol |b| or
+ * max_iter), optionally preconditioned by the Cholesky factor L (lower triangle, row stride lda, with the `Lwork` and `Linfo`
+ * of tn_cholesky_factor; Linfo[0] != 0 turns the call into a no-op).  use_x0 == 0: x starts at 0, or at (L L^T)^-1 b when
+ * L is given.  With L the factor of the TF32 / 3xTF32 Gram and the built-in fp64 operator this is the refinement that
+ * makes the tensor-core Gram modes solve the fp64 system of solve_system (network.py:293-327).                          */
+int64_t tn_cg_work_elems(const tn_operator *op);
+int tn_cg(const tn_operator *op, const double *L, int64_t lda, const double *Lwork, const int *Linfo, const double *b,
+          double *x, int use_x0, int max_iter, double rtol, int poll_every, double *work, double *stats, void *stream);
+/* MINRES without preconditioner or shift (scipy.sparse.linalg.minres as called at network.py:921-925). */
+int64_t tn_minres_work_elems(const tn_operator *op);
+int tn_minres(const tn_operator *op, const double *b, double *x, int use_x0, int max_iter, double rtol, int poll_every,
+              double *work, double *stats, void *stream);
+/* Lanczos-Galerkin solve of lanczos_swipe (network.py:793-824): r0 = b - Op x0 (x0 may be NULL = 0), max_iter Lanczos
+ * vectors without re-orthogonalisation (stop when |w_j| < tol), x = x0 + V T^-1 (|r0| e1).                              */
+int64_t tn_lanczos_work_elems(const tn_operator *op, int max_iter);
+int tn_lanczos(const tn_operator *op, const double *b, const double *x0, double *x, int max_iter, double tol,
+               int poll_every, double *work, double *stats, void *stream);
+
+/* Factorisation alone (the preconditioner of tn_cg): lower triangle of A <- L, work (tn_cholesky_work_elems(P)) <- the
+ * inverted 64 x 64 diagonal blocks.  tensor_core != 0: trailing updates as 3xTF32 tcgen05 GEMMs (factor accurate to ~1e-5).
+ * tn_cholesky_apply: x <- L^-T L^-1 x.                                                                               */
+int tn_cholesky_factor(double *A, int64_t lda, int64_t P, int tensor_core, double *work, int *info, void *stream);
+int tn_cholesky_apply(const double *L, int64_t lda, int64_t P, double *x, const double *work, const int *info, void *stream);
+
+/* out[0] (+)= sum_rows w |fa|^2 |fb|^2 |fc|^2 = trace(J^T diag(w) J) in fp64, out[1] (+)= the same with |w|: the exact
+ * sigma = mean |A_ii| of solve_system (network.py:298) for the tensor-core Gram modes when no weight is negative.       */
+int tn_gram_trace(const tn_factor *fa, const tn_factor *fb, const tn_factor *fc, const double *w, int64_t rows, double *out,
+                  int accumulate, void *stream);
 
 /* ---- per-sample small matrix products of the patch/pixel ("conv-TT") layer
  *      (TensorConvolutionTrainLayer, tensor/layers.py:791-890; closed forms in SURVEY.md Appendix C):

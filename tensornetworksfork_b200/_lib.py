@@ -23,6 +23,18 @@ class tn_factor(ctypes.Structure):
                 ("map_kind", ctypes.c_int32), ("_pad", ctypes.c_int32)]
 
 
+class tn_operator(ctypes.Structure):
+    """Mirror of tn_operator (include/tn_b200.h); the two callbacks are stored as raw addresses (0 = NULL)."""
+    _fields_ = [("fa", ctypes.POINTER(tn_factor)), ("fb", ctypes.POINTER(tn_factor)), ("fc", ctypes.POINTER(tn_factor)),
+                ("w", ctypes.c_void_p), ("rows", ctypes.c_int64), ("apply", ctypes.c_void_p), ("apply_ctx", ctypes.c_void_p),
+                ("allreduce", ctypes.c_void_p), ("allreduce_ctx", ctypes.c_void_p), ("sigma", ctypes.c_void_p),
+                ("ridge", ctypes.c_double), ("P", ctypes.c_int64), ("apply_is_global", ctypes.c_int32), ("_pad", ctypes.c_int32)]
+
+
+APPLY_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p)
+ALLREDUCE_FN = ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p)
+OP = ctypes.POINTER(tn_operator)
+
 FP = ctypes.POINTER(tn_factor)
 IP = ctypes.POINTER(ctypes.c_int)
 
@@ -36,6 +48,7 @@ PROTOTYPES = {
     "tn_class_rows": (i32, [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp]),
     "tn_gram_ksplit": (i32, [i64, i32, i32, i32, i32]),
     "tn_gram_kr3": (i32, [i32, FP, FP, FP, vp, i64, vp, vp, i32, i32, vp]),
+    "tn_gram_tc_flush_rows": (i32, [i32]),
     "tn_rhs_ksplit": (i32, [i64, i32, i32, i32]),
     "tn_rhs_kr3": (i32, [FP, FP, FP, vp, i64, vp, vp, i32, i32, vp]),
     "tn_generic_ksplit": (i32, [i64, i32, i32]),
@@ -54,6 +67,15 @@ PROTOTYPES = {
     "tn_outer_rows": (i32, [vp, i64, i32, i32, vp, i64, i32, vp, i64, vp, i32, vp]),
     "tn_rows_dot": (i32, [vp, i64, i32, vp, i64, i32, i64, vp, i64, vp]),
     "tn_matvec_kr3": (i32, [FP, FP, FP, vp, i64, vp, vp, vp, vp]),
+    "tn_cg_work_elems": (i64, [OP]),
+    "tn_cg": (i32, [OP, vp, i64, vp, vp, vp, vp, i32, i32, f64, i32, vp, vp, vp]),
+    "tn_minres_work_elems": (i64, [OP]),
+    "tn_minres": (i32, [OP, vp, vp, i32, i32, f64, i32, vp, vp, vp]),
+    "tn_lanczos_work_elems": (i64, [OP, i32]),
+    "tn_lanczos": (i32, [OP, vp, vp, vp, i32, f64, i32, vp, vp, vp]),
+    "tn_cholesky_factor": (i32, [vp, i64, i64, i32, vp, vp, vp]),
+    "tn_cholesky_apply": (i32, [vp, i64, i64, vp, vp, vp, vp]),
+    "tn_gram_trace": (i32, [FP, FP, FP, vp, i64, vp, i32, vp]),
 }
 
 _lib = None

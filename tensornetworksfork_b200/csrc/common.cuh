@@ -73,6 +73,14 @@ int64_t syrk_tc_work_floats(int64_t n, int kb);
 int syrk_tc_update(double* A, int64_t lda, int64_t P, int64_t c0, int64_t k0, int kb, float* X, const int* info, cudaStream_t st,
                    int64_t col_limit = 0);
 void count_launch(int n = 1);   // bookkeeping for tn_launch_count()
+// blocked Cholesky internals shared with the Krylov drivers (solve.cu)
+int cholesky_factorize(double* A, int64_t lda, int64_t P, double* work, int* info, cudaStream_t st, float* X, int64_t NBO);
+int cholesky_substitute(const double* A, int64_t lda, int64_t P, double* rhs, const double* work, const int* stop, cudaStream_t st);
+int64_t cholesky_default_nbo(int64_t P);
+// environment step with an optional per-row scale of the prediction epilogue (env.cu): yhat[row] *= yscale[row]
+int env_update_scaled(const double* env_in, int64_t env_ld, int env_div, const double* x, int64_t x_ld, int map_kind, int f, int cdiv,
+                      const double* core, double* out, int64_t out_ld, const double* dot, int64_t dot_ld, int dot_div, double* yhat,
+                      const double* yscale, int64_t rows, int r_in, int r_out, cudaStream_t st);
 
 // FP64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col): a = A[lane/4][lane%4], b = B[lane%4][lane/4],
 // d0/d1 = D[lane/4][2*(lane%4) + 0/1].

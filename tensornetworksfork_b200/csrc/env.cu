@@ -23,7 +23,7 @@ __global__ void __launch_bounds__(ENV_THREADS, (CN <= 3) ? 3 : 2)
 env_kernel(const double* __restrict__ env_in, int64_t env_ld, int env_div, const double* __restrict__ x, int64_t x_ld,
            int map_kind, int f, int cdiv, const double* __restrict__ core, double* __restrict__ out,
            int64_t out_ld, const double* __restrict__ dot, int64_t dot_ld, int dot_div,
-           double* __restrict__ yhat, int64_t rows, int r_in, int r_out, int p_chunk) {
+           double* __restrict__ yhat, const double* __restrict__ yscale, int64_t rows, int r_in, int r_out, int p_chunk) {
     constexpr int TR = (ENV_THREADS / TXN) * ENV_RT;   // rows per CTA
     constexpr int TC = TXN * CN;                        // columns per pass
     extern __shared__ double sm[];
@@ -135,7 +135,7 @@ env_kernel(const double* __restrict__ env_in, int64_t env_ld, int env_div, const
 #pragma unroll
             for (int o = TXN / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
             const int64_t row = row0 + ty * ENV_RT + i;
-            if (tx == 0 && row < rows) yhat[row] = v;
+            if (tx == 0 && row < rows) yhat[row] = yscale ? v * yscale[row] : v;
         }
     }
 }
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(ENV_THREADS, 2)
 env_dmma_kernel(const double* __restrict__ env_in, int64_t env_ld, int env_div, const double* __restrict__ x, int64_t x_ld,
                 int map_kind, int f, int cdiv, const double* __restrict__ core, double* __restrict__ out,
                 int64_t out_ld, const double* __restrict__ dot, int64_t dot_ld, int dot_div,
-                double* __restrict__ yhat, int64_t rows, int r_in, int r_out) {
+                double* __restrict__ yhat, const double* __restrict__ yscale, int64_t rows, int r_in, int r_out) {
     constexpr int LDG = NT * 8 + 8;                  // core slab row stride: == 8 (mod 16) doubles, conflict-free B fragments
     extern __shared__ double sm[];
     const int in_st = (r_in + 5) | 1;                // + zero columns read by the padded tail of K
@@ -246,7 +246,7 @@ env_dmma_kernel(const double* __restrict__ env_in, int64_t env_ld, int env_div, 
         if (dot) {
             yd += __shfl_xor_sync(0xffffffffu, yd, 1);
             yd += __shfl_xor_sync(0xffffffffu, yd, 2);
-            if (fk == 0 && row < rows) yhat[row] = yd;
+            if (fk == 0 && row < rows) yhat[row] = yscale ? yd * yscale[row] : yd;
         }
     }
 }
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(ENV_THREADS, 2)
 env_dmma_persist_kernel(const double* __restrict__ env_in, int64_t env_ld, int env_div, const double* __restrict__ x, int64_t x_ld,
                         int map_kind, int f, int cdiv, const double* __restrict__ core, double* __restrict__ out,
                         int64_t out_ld, const double* __restrict__ dot, int64_t dot_ld, int dot_div,
-                        double* __restrict__ yhat, int64_t rows, int r_in, int r_out, int64_t ntiles) {
+                        double* __restrict__ yhat, const double* __restrict__ yscale, int64_t rows, int r_in, int r_out, int64_t ntiles) {
     constexpr int LDG = NT * 8 + 8;
     extern __shared__ double sm[];
     const int in_st = (r_in + 5) | 1;
@@ -376,7 +376,7 @@ env_dmma_persist_kernel(const double* __restrict__ env_in, int64_t env_ld, int e
             if (dot) {
                 yd += __shfl_xor_sync(0xffffffffu, yd, 1);
                 yd += __shfl_xor_sync(0xffffffffu, yd, 2);
-                if (fk == 0 && row < rows) yhat[row] = yd;
+                if (fk == 0 && row < rows) yhat[row] = yscale ? yd * yscale[row] : yd;
             }
         }
     }
@@ -386,7 +386,7 @@ env_dmma_persist_kernel(const double* __restrict__ env_in, int64_t env_ld, int e
 template <int NT>
 static int launch_env_dmma(const double* env_in, int64_t env_ld, int env_div, const double* x, int64_t x_ld, int map_kind, int f,
                            int cdiv, const double* core, double* out, int64_t out_ld, const double* dot, int64_t dot_ld,
-                           int dot_div, double* yhat, int64_t rows, int r_in, int r_out, cudaStream_t st) {
+                           int dot_div, double* yhat, const double* yscale, int64_t rows, int r_in, int r_out, cudaStream_t st) {
     {   // persistent pipelined kernel when the whole core slab stays resident
         const int K = r_in * f, Kp = (K + 3) & ~3, xraw = (map_kind == TN_MAP_IDENTITY) ? f : 1;
         const size_t psmem = ((size_t)Kp * (NT * 8 + 8) + 2 * (size_t)ED_TR * ((r_in + 5) | 1) + 2 * (size_t)ED_TR * xraw +
@@ -398,7 +398,7 @@ static int launch_env_dmma(const double* env_in, int64_t env_ld, int env_div, co
             int64_t grid = 2LL * sm_count();
             if (grid > ntiles) grid = ntiles;
             env_dmma_persist_kernel<NT><<<(unsigned)grid, ENV_THREADS, psmem, st>>>(env_in, env_ld, env_div, x, x_ld, map_kind, f, cdiv, core,
-                                                                               out, out_ld, dot, dot_ld, dot_div, yhat, rows, r_in, r_out,
+                                                                               out, out_ld, dot, dot_ld, dot_div, yhat, yscale, rows, r_in, r_out,
                                                                                ntiles);
             TN_LAUNCH_CHECK();
             return TN_OK;
@@ -410,7 +410,7 @@ static int launch_env_dmma(const double* env_in, int64_t env_ld, int env_div, co
     const int64_t grid = ceil_div64(rows, ED_TR);
     TN_CHECK_ARG(grid <= 0x7fffffff, "tn_env_update: too many rows");
     env_dmma_kernel<NT><<<(unsigned)grid, ENV_THREADS, smem, st>>>(env_in, env_ld, env_div, x, x_ld, map_kind, f, cdiv, core, out, out_ld,
-                                                                 dot, dot_ld, dot_div, yhat, rows, r_in, r_out);
+                                                                 dot, dot_ld, dot_div, yhat, yscale, rows, r_in, r_out);
     TN_LAUNCH_CHECK();
     return TN_OK;
 }
@@ -449,6 +449,13 @@ extern "C" int tn_env_update(const double* env_in, int64_t env_ld, int env_div, 
                              int cdiv, const double* core, double* out, int64_t out_ld, const double* dot,
                              int64_t dot_ld, int dot_div, double* yhat, int64_t rows, int r_in, int r_out,
                              void* stream) {
+    return tn::env_update_scaled(env_in, env_ld, env_div, x, x_ld, map_kind, f, cdiv, core, out, out_ld, dot, dot_ld, dot_div, yhat, nullptr,
+                                 rows, r_in, r_out, tn::as_stream(stream));
+}
+
+int tn::env_update_scaled(const double* env_in, int64_t env_ld, int env_div, const double* x, int64_t x_ld, int map_kind, int f, int cdiv,
+                          const double* core, double* out, int64_t out_ld, const double* dot, int64_t dot_ld, int dot_div, double* yhat,
+                          const double* yscale, int64_t rows, int r_in, int r_out, cudaStream_t stream) {
     using namespace tn;
     TN_CHECK_ARG(rows >= 0 && r_in >= 1 && r_out >= 1 && f >= 1 && cdiv >= 1, "tn_env_update: bad sizes");
     if (rows == 0) return TN_OK;       // an empty shard / batch: nothing to read or write (the pointers may be null)
@@ -463,9 +470,9 @@ extern "C" int tn_env_update(const double* env_in, int64_t env_ld, int env_div, 
     if (r_out <= 104 && (int64_t)r_in * f >= 8 && !getenv("TN_ENV_NO_DMMA")) {
         const int nt = (r_out + 7) / 8;
         const int edv = env_div < 1 ? 1 : env_div;
-        cudaStream_t st = as_stream(stream);
+        cudaStream_t st = stream;
         int rc = 1;
-#define TN_ENV_DMMA(NTV) rc = launch_env_dmma<NTV>(env_in, env_ld, edv, x, x_ld, map_kind, f, cdiv, core, out, out_ld, dot, dot_ld, dot_div, yhat, rows, r_in, r_out, st)
+#define TN_ENV_DMMA(NTV) rc = launch_env_dmma<NTV>(env_in, env_ld, edv, x, x_ld, map_kind, f, cdiv, core, out, out_ld, dot, dot_ld, dot_div, yhat, yscale, rows, r_in, r_out, st)
         if (nt <= 1) TN_ENV_DMMA(1);
         else if (nt <= 2) TN_ENV_DMMA(2);
         else if (nt <= 3) TN_ENV_DMMA(3);
@@ -487,14 +494,14 @@ extern "C" int tn_env_update(const double* env_in, int64_t env_ld, int env_div, 
     const size_t smem = ((size_t)TR * (r_in | 1) + (size_t)TR * (f | 1) + (size_t)p_chunk * r_in * TC) * sizeof(double);
     TN_CHECK_ARG(smem <= 227 * 1024, "tn_env_update: r_in=%d f=%d needs %zu B of shared memory", r_in, f, smem);
     using Kern = void (*)(const double*, int64_t, int, const double*, int64_t, int, int, int, const double*, double*, int64_t,
-                          const double*, int64_t, int, double*, int64_t, int, int, int);
+                          const double*, int64_t, int, double*, const double*, int64_t, int, int, int);
     static const Kern kerns[6] = {env_kernel<8, 1>, env_kernel<8, 2>, env_kernel<8, 3>, env_kernel<8, 4>, env_kernel<8, 5>, env_kernel<16, 4>};
     const int ki = (TXN == 16) ? 5 : CN - 1;
     TN_SMEM(kerns[ki], smem);
     const int64_t grid = ceil_div64(rows, TR);
     TN_CHECK_ARG(grid <= 0x7fffffff, "tn_env_update: too many rows");
-    kerns[ki]<<<(unsigned)grid, ENV_THREADS, smem, as_stream(stream)>>>(env_in, env_ld, env_div < 1 ? 1 : env_div, x, x_ld, map_kind, f,
-                                                                       cdiv, core, out, out_ld, dot, dot_ld, dot_div, yhat, rows,
+    kerns[ki]<<<(unsigned)grid, ENV_THREADS, smem, stream>>>(env_in, env_ld, env_div < 1 ? 1 : env_div, x, x_ld, map_kind, f,
+                                                                       cdiv, core, out, out_ld, dot, dot_ld, dot_div, yhat, yscale, rows,
                                                                        r_in, r_out, p_chunk);
     TN_LAUNCH_CHECK();
     return TN_OK;

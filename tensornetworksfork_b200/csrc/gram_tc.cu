@@ -739,6 +739,17 @@ static size_t tc_smem_bytes(int mA, int mB, int mC, int BN, int T, int NS) {
 
 }  // namespace tn
 
+namespace tn { static thread_local int g_tc_flush_rows = 0; }
+
+// Rows accumulated in the fp32 TMEM accumulators between two fp64 flushes, for the calling thread's later tn_gram_kr3 calls
+// (0 = the default, 2048).  Longer windows are faster and less accurate (relative error of M ~ 6e-9 per row of the window): the
+// exact refinement of the sweep (tn_cg on the fp64 operator) only needs M as a preconditioner and uses 8192.
+extern "C" int tn_gram_tc_flush_rows(int rows) {
+    const int prev = tn::g_tc_flush_rows;
+    if (rows >= 0) tn::g_tc_flush_rows = (rows / tn::TC_KC) * tn::TC_KC;
+    return prev;
+}
+
 int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_factor* fc, const double* w, int64_t rows,
                    double* M, int accumulate, void* stream) {
     using namespace tn;
@@ -755,7 +766,7 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     p.nC = npairs(C.m);
     p.split = (mode == 2) ? 1 : 0;
     p.planar = 0;
-    p.flush_rows = TC_FLUSH_ROWS_DEFAULT;
+    p.flush_rows = (tn::g_tc_flush_rows > 0) ? tn::g_tc_flush_rows : TC_FLUSH_ROWS_DEFAULT;
     if (const char* e = getenv("TN_TC_FLUSH_ROWS")) {
         const int v = atoi(e);
         if (v >= TC_KC) p.flush_rows = (v / TC_KC) * TC_KC;

@@ -640,7 +640,7 @@ static int cholesky_configure() {
 
 // Blocked right-looking factorisation of the lower triangle, in place.  X != nullptr: the outer trailing updates with at least
 // tc_min_n rows run on the tensor cores in 3xTF32 (syrk_tc.cu); X must hold syrk_tc_work_floats(P, NBO) floats.
-static int cholesky_factorize(double* A, int64_t lda, int64_t P, double* work, int* info, cudaStream_t st, float* X, int64_t NBO) {
+int cholesky_factorize(double* A, int64_t lda, int64_t P, double* work, int* info, cudaStream_t st, float* X, int64_t NBO) {
     constexpr size_t kBlkSmem = 2 * CH_NB * (CH_NB + 1) * sizeof(double);
     constexpr size_t kDmmaSmem = (size_t)2 * DS_STAGES * DS_BT * DS_LD * sizeof(double);
     int rc = cholesky_configure();
@@ -735,8 +735,8 @@ static int cholesky_factorize(double* A, int64_t lda, int64_t P, double* work, i
 
 // rhs <- L^{-T} L^{-1} rhs with the factor in the lower triangle of A and the inverted diagonal blocks in work.
 // Every kernel returns at once when *stop != 0.
-static int cholesky_substitute(const double* A, int64_t lda, int64_t P, double* rhs, const double* work, const int* stop,
-                               cudaStream_t st) {
+int cholesky_substitute(const double* A, int64_t lda, int64_t P, double* rhs, const double* work, const int* stop,
+                        cudaStream_t st) {
     if (P <= TS_MAXP) {
         const size_t smem = ((size_t)ceil_div64(P, 64) * 64 + 64) * sizeof(double);
         TN_SMEM(trsv_small_kernel, smem);
@@ -800,7 +800,7 @@ static int cholesky_substitute(const double* A, int64_t lda, int64_t P, double* 
     return TN_OK;
 }
 
-static int64_t cholesky_default_nbo(int64_t P) {
+int64_t cholesky_default_nbo(int64_t P) {
     // outer panel width: wider panels amortise the read-modify-write of the trailing matrix (measured at P = 41 876:
     // 256 -> 1385 ms, 512 -> 1210 ms, 768 -> 1140 ms, 1024 -> 1125 ms)
     int64_t NBO = (P > 16384) ? 768 : ((P > 8192) ? 512 : ((P > 4096) ? 256 : ((P > 1024) ? 128 : CH_NB)));
@@ -1065,4 +1065,30 @@ extern "C" int tn_cholesky_solve_mixed(double* A, int64_t lda, int64_t P, double
     pcg_finish_kernel<<<vblocks, 256, 0, st>>>(x, rhs, P, info, scal, stats);
     TN_LAUNCH_CHECK();
     return TN_OK;
+}
+
+// Factorisation only (the preconditioner of tn_cg): lower triangle of A <- L, work <- inverted diagonal blocks.
+extern "C" int tn_cholesky_factor(double* A, int64_t lda, int64_t P, int tensor_core, double* work, int* info, void* stream) {
+    using namespace tn;
+    TN_CHECK_ARG(A && work && info && P >= 1 && lda >= P, "tn_cholesky_factor: bad arguments");
+    cudaStream_t st = as_stream(stream);
+    TN_CUDA(cudaMemsetAsync(info, 0, sizeof(int), st));
+    if (!tensor_core) return cholesky_factorize(A, lda, P, work, info, st, nullptr, cholesky_default_nbo(P));
+    int64_t NBO = (P > 8192) ? 1024 : cholesky_default_nbo(P);
+    if (const char* e = getenv("TN_CHOL_TC_NBO")) {
+        const int v = atoi(e);
+        if (v >= CH_NB && v % CH_NB == 0) NBO = v;
+    }
+    float* X = nullptr;
+    TN_CUDA(cudaMallocAsync(&X, (size_t)syrk_tc_work_floats(P, (int)NBO) * sizeof(float), st));
+    const int rc = cholesky_factorize(A, lda, P, work, info, st, X, NBO);
+    cudaFreeAsync(X, st);
+    return rc;
+}
+
+// x <- L^-T L^-1 x with the factor and work of tn_cholesky_factor / tn_cholesky_solve (skipped when info[0] != 0).
+extern "C" int tn_cholesky_apply(const double* L, int64_t lda, int64_t P, double* x, const double* work, const int* info, void* stream) {
+    using namespace tn;
+    TN_CHECK_ARG(L && x && work && info && P >= 1 && lda >= P, "tn_cholesky_apply: bad arguments");
+    return cholesky_substitute(L, lda, P, x, work, info, as_stream(stream));
 }

@@ -195,9 +195,16 @@ def npairs(m):
 
 
 @_op
-def gram(mode, fa: Factor, fb: Factor, fc: Factor, w, rows, M=None, accumulate=False):
-    """M[qa,qb,qc] (+)= sum_rows w * pair(fa)[qa] * pair(fb)[qb] * pair(fc)[qc]."""
+def gram(mode, fa: Factor, fb: Factor, fc: Factor, w, rows, M=None, accumulate=False, flush_rows=None):
+    """M[qa,qb,qc] (+)= sum_rows w * pair(fa)[qa] * pair(fb)[qb] * pair(fc)[qc].  ``flush_rows``: fp32 accumulation window of the
+    tensor-core modes for this call (None = the library default)."""
     lib = _lib.load()
+    if flush_rows is not None and mode != GRAM_FP64:
+        prev = lib.tn_gram_tc_flush_rows(int(flush_rows))
+        try:
+            return gram(mode, fa, fb, fc, w, rows, M=M, accumulate=accumulate)
+        finally:
+            lib.tn_gram_tc_flush_rows(prev)
     _need_cuda(fa.tensor, fb.tensor, fc.tensor, w)
     _bare(w, M)
     n = npairs(fa.m) * npairs(fb.m) * npairs(fc.m)
@@ -421,3 +428,221 @@ def rows_dot(W, V, out=None):
     _lib.check(lib.tn_rows_dot(_p(W), W.stride(0), m, _p(V), V.stride(0), ra, rows, _p(out), out.stride(0) if rows > 1 else ra,
                                _stream()), "tn_rows_dot")
     return out
+
+
+# ------------------------------------------------------------------------------------------ on-device Krylov drivers
+class Operator:
+    """The linear operator of a matrix-free local solve: ``Op v = A0 v / sigma + ridge v``.
+
+    ``A0`` is ``J^T diag(w) J`` of this rank's rows given by three Kronecker ``factors`` (the built-in two-pass kernels), or an
+    arbitrary ``matvec`` callable (conv-TT, cum-sum: their Jacobians are not Kronecker products); ``group`` sums ``A0 v`` over
+    the ranks of a sample-sharded run.  Calling the object applies ``A0`` alone (plus the all-reduce) to a tensor -- the
+    interface the SciPy bridge and tests use.
+    """
+
+    def __init__(self, P, factors=None, w=None, rows=0, matvec=None, group=None, sigma=None, ridge=0.0, device=None):
+        if (factors is None) == (matvec is None):
+            raise ValueError("Operator needs either three factors or a matvec callable")
+        self.P = int(P)
+        self.factors = factors
+        self.w = w
+        self.rows = int(rows)
+        self.matvec = matvec
+        self.group = group
+        self.sigma = sigma
+        self.ridge = float(ridge)
+        self.device = device if device is not None else (factors[0].tensor.device if factors is not None else None)
+        self.applies = 0            # operator applications served (bench bookkeeping)
+
+    def with_shift(self, sigma, ridge):
+        out = Operator(self.P, self.factors, self.w, self.rows, self.matvec, self.group, sigma, ridge, self.device)
+        return out
+
+    def __call__(self, v):
+        self.applies += 1
+        if self.matvec is not None:
+            return self.matvec(v)
+        fa, fb, fc = self.factors
+        out = matvec(fa, fb, fc, self.w, self.rows, v.contiguous().view(-1))
+        if self.group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(out, group=self.group)
+        return out
+
+
+class _OpBinding:
+    """ctypes image of an Operator for the duration of one driver call: keeps the factor structs and callback thunks alive, maps
+    the raw pointers the driver hands to the callbacks back to views of the tensors they point into, and carries a Python
+    exception raised inside a callback across the C frame."""
+
+    def __init__(self, op: Operator, buffers):
+        self.op = op
+        self.buffers = [t for t in buffers if t is not None]
+        self.error = None
+        self.keep = []
+        c = _lib.tn_operator()
+        if op.factors is not None:
+            facs = [f.c() for f in op.factors]
+            self.keep.append(facs)
+            c.fa, c.fb, c.fc = (ctypes.pointer(f) for f in facs)
+            c.w = 0 if op.w is None else op.w.data_ptr()
+            c.rows = op.rows
+            c.apply = 0
+        else:
+            cb = _lib.APPLY_FN(self._apply)
+            self.keep.append(cb)
+            c.apply = ctypes.cast(cb, ctypes.c_void_p).value
+        c.apply_is_global = 1 if (op.group is not None and op.factors is None) else 0      # a python matvec does its own reduction
+        if op.group is not None:
+            cb = _lib.ALLREDUCE_FN(self._allreduce)
+            self.keep.append(cb)
+            c.allreduce = ctypes.cast(cb, ctypes.c_void_p).value
+        else:
+            c.allreduce = 0
+        c.apply_ctx = c.allreduce_ctx = 0
+        c.sigma = 0 if op.sigma is None else op.sigma.data_ptr()
+        c.ridge = op.ridge
+        c.P = op.P
+        self.c = c
+
+    def view(self, ptr, n):
+        for t in self.buffers:
+            base = t.data_ptr()
+            if base <= ptr and ptr + 8 * n <= base + 8 * t.numel():
+                off = (ptr - base) // 8
+                return t.view(-1)[off:off + n]
+        raise _lib.TnError("krylov callback: pointer outside the buffers of the call")
+
+    def _apply(self, ctx, v_ptr, out_ptr, stream):
+        try:
+            v = self.view(v_ptr, self.op.P)
+            out = self.view(out_ptr, self.op.P)
+            self.op.applies += 1
+            out.copy_(self.op.matvec(v).reshape(-1))
+            return 0
+        except BaseException as e:       # must not propagate through the C frame
+            self.error = e
+            return -1
+
+    def _allreduce(self, ctx, buf_ptr, n, stream):
+        try:
+            import torch.distributed as dist
+            dist.all_reduce(self.view(buf_ptr, n), group=self.op.group)
+            return 0
+        except BaseException as e:
+            self.error = e
+            return -1
+
+    def finish(self, rc, what):
+        if self.error is not None:
+            raise self.error
+        _lib.check(rc, what)
+
+
+def _krylov_common(op: Operator, b, x0):
+    _need_cuda(b, x0, op.sigma, op.w)
+    _bare(b, x0, op.w)
+    if b.numel() != op.P or (x0 is not None and x0.numel() != op.P):
+        raise _lib.TnError(f"krylov: vectors of {op.P} expected")
+    return b.device
+
+
+def _poll(op, poll_every):
+    if poll_every is not None:
+        return int(poll_every)
+    return 1 if op.P >= 4096 else 4
+
+
+@_op
+def cholesky_factor(A, tensor_core=False):
+    """In place: lower triangle of A (P x lda) <- its Cholesky factor.  Returns (work, info) for cholesky_apply / cg."""
+    lib = _lib.load()
+    P = A.shape[0]
+    _need_cuda(A)
+    if A.dim() != 2 or A.stride(1) != 1 or A.stride(0) < P:
+        raise _lib.TnError(f"system matrix must be ({P}, >= {P}) with unit inner stride, got {tuple(A.shape)} / {A.stride()}")
+    work = torch.empty((lib.tn_cholesky_work_elems(P),), dtype=torch.float64, device=A.device)
+    info = torch.zeros((1,), dtype=torch.int32, device=A.device)
+    _lib.check(lib.tn_cholesky_factor(_p(A), A.stride(0), P, 1 if tensor_core else 0, _p(work), ctypes.c_void_p(info.data_ptr()),
+                                      _stream()), "tn_cholesky_factor")
+    return work, info
+
+
+@_op
+def cholesky_apply(L, work, info, x):
+    """x <- L^-T L^-1 x in place."""
+    lib = _lib.load()
+    P = L.shape[0]
+    _need_cuda(L, work, x)
+    _system_layout(L, x, P)
+    _lib.check(lib.tn_cholesky_apply(_p(L), L.stride(0), P, _p(x), _p(work), ctypes.c_void_p(info.data_ptr()), _stream()),
+               "tn_cholesky_apply")
+    return x
+
+
+@_op
+def gram_trace(fa: Factor, fb: Factor, fc: Factor, w, rows, out=None):
+    """out[0] = sum_rows w |fa|^2 |fb|^2 |fc|^2 (the trace of the local Gram, fp64), out[1] the same with |w|."""
+    lib = _lib.load()
+    _need_cuda(fa.tensor, fb.tensor, fc.tensor, w, out)
+    _bare(w, out)
+    if out is None:
+        out = torch.empty((2,), dtype=torch.float64, device=fa.tensor.device)
+    a, b, c = fa.c(), fb.c(), fc.c()
+    _lib.check(lib.tn_gram_trace(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), _p(w), rows, _p(out), 0, _stream()), "tn_gram_trace")
+    return out
+
+
+def cg(op: Operator, b, x0=None, precond=None, max_iter=50, rtol=1e-6, poll_every=None):
+    """Conjugate gradients on Op x = b on the device.  ``precond = (L, work, info)`` from cholesky_factor.
+    Returns (x, stats) with stats = [relative residual, iterations, stopped-by-tolerance, operator applications] (device)."""
+    lib = _lib.load()
+    dev = _krylov_common(op, b, x0)
+    with _on(dev):
+        x = torch.empty_like(b) if x0 is None else x0.clone().reshape(-1)
+        stats = torch.zeros((4,), dtype=torch.float64, device=dev)
+        bind = _OpBinding(op, [b, x])
+        work = torch.empty((lib.tn_cg_work_elems(ctypes.byref(bind.c)),), dtype=torch.float64, device=dev)
+        bind.buffers.append(work)
+        L, lwork, linfo = precond if precond is not None else (None, None, None)
+        if L is not None:
+            _need_cuda(L, lwork)
+            _system_layout(L, b, op.P)
+        rc = lib.tn_cg(ctypes.byref(bind.c), _p(L), 0 if L is None else L.stride(0), _p(lwork),
+                       ctypes.c_void_p(0 if linfo is None else linfo.data_ptr()), _p(b), _p(x), 0 if x0 is None else 1, int(max_iter),
+                       float(rtol), _poll(op, poll_every), _p(work), _p(stats), _stream())
+        bind.finish(rc, "tn_cg")
+    return x, stats
+
+
+def minres(op: Operator, b, x0=None, max_iter=50, rtol=1e-6, poll_every=None):
+    """MINRES on Op x = b on the device; returns (x, stats) as cg."""
+    lib = _lib.load()
+    dev = _krylov_common(op, b, x0)
+    with _on(dev):
+        x = torch.empty_like(b) if x0 is None else x0.clone().reshape(-1)
+        stats = torch.zeros((4,), dtype=torch.float64, device=dev)
+        bind = _OpBinding(op, [b, x])
+        work = torch.empty((lib.tn_minres_work_elems(ctypes.byref(bind.c)),), dtype=torch.float64, device=dev)
+        bind.buffers.append(work)
+        rc = lib.tn_minres(ctypes.byref(bind.c), _p(b), _p(x), 0 if x0 is None else 1, int(max_iter), float(rtol), _poll(op, poll_every),
+                           _p(work), _p(stats), _stream())
+        bind.finish(rc, "tn_minres")
+    return x, stats
+
+
+def lanczos(op: Operator, b, x0=None, max_iter=50, tol=1e-6, poll_every=None):
+    """Lanczos-Galerkin solve of Op x = b started at x0 (reference network.py:793-824); returns (x, stats)."""
+    lib = _lib.load()
+    dev = _krylov_common(op, b, x0)
+    with _on(dev):
+        x = torch.empty_like(b)
+        x0c = None if x0 is None else x0.contiguous().reshape(-1)
+        stats = torch.zeros((4,), dtype=torch.float64, device=dev)
+        bind = _OpBinding(op, [b, x, x0c])
+        work = torch.empty((lib.tn_lanczos_work_elems(ctypes.byref(bind.c), int(max_iter)),), dtype=torch.float64, device=dev)
+        bind.buffers.append(work)
+        rc = lib.tn_lanczos(ctypes.byref(bind.c), _p(b), _p(x0c), _p(x), int(max_iter), float(tol), _poll(op, poll_every), _p(work),
+                            _p(stats), _stream())
+        bind.finish(rc, "tn_lanczos")
+    return x, stats

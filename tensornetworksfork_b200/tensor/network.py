@@ -147,8 +147,19 @@ class TensorNetwork:
         self.mixed_min_P = 8192
         self.mixed_rtol = 1e-9          # residual the refinement aims for ...
         self.mixed_accept = 1e-9        # ... and the one it must reach for the result to be used (else fp64 redo)
-        self.solve_stats = {"mixed": 0, "fp64": 0, "mixed_fallback": 0, "refine_iters": 0}
+        self.solve_stats = {"mixed": 0, "fp64": 0, "mixed_fallback": 0, "refine_iters": 0, "refined": 0, "gram_fp64_fallback": 0}
         self._mixed_floor = 0.0         # ridge values at or below this made the mixed solve fall back; skip it there
+        # tensor-core Gram modes: "exact" = the TF32 / 3xTF32 Gram only preconditions (through its Cholesky factor) a conjugate-
+        # gradient iteration on the fp64 matrix-free operator J^T W J / sigma + ridge, so the step solves the reference's fp64
+        # system (network.py:293-327) to `refine_rtol`; "gram" = round 1's behaviour (the step solves the tensor-core Gram's system)
+        self.refine = "exact"
+        self.refine_rtol = 1e-11
+        self.refine_accept = 1e-9       # residual the refinement must reach, else the site is redone with an fp64 Gram
+        self.refine_max_iter = 30
+        self._refine_floor = -1.0       # ridge values at or below this needed the fp64 Gram; go there directly
+        # fp32 accumulation window (rows) of the tensor-core Gram when it only preconditions the exact refinement: longer = faster,
+        # coarser (None = the library default of 2048, the window the stand-alone accuracy figures of the Gram are quoted for)
+        self.tc_flush_rows = 8192
         self.process_group = None       # torch.distributed group: x, y are then this rank's row shard
         self.shard_offset = 0           # global index of this rank's first row
         self.shard_total = None         # global number of rows
@@ -609,31 +620,85 @@ class TensorNetwork:
         role_of_pos[c] = 2
         return role_of_pos, (others[0], others[1], c)
 
-    def _accumulate(self, prob):
-        """Local Gram (unique entries M), right-hand side b and the bookkeeping needed to expand them."""
-        mode = _GRAM_MODES[self.gram_mode]
+    def _accumulate(self, prob, gram_mode=None):
+        """Local Gram (unique entries M), right-hand side b and the bookkeeping needed to expand them.  In the tensor-core
+        modes the exact fp64 trace of the Gram rides along (two numbers) for the scaling of the system."""
+        gram_mode = self.gram_mode if gram_mode is None else gram_mode
+        mode = _GRAM_MODES[gram_mode]
         m_pos = prob["m_pos"]
         role_of_pos, order = self._roles(m_pos)
         gf = prob["gram"]
         nM = ops.npairs(m_pos[0]) * ops.npairs(m_pos[1]) * ops.npairs(m_pos[2])
         P = m_pos[0] * m_pos[1] * m_pos[2]
         dev = prob["yhat"].device
-        buf = torch.empty((nM + P,), dtype=torch.float64, device=dev)
-        M, b = buf[:nM], buf[nM:]
-        ops.gram(mode, gf[order[0]], gf[order[1]], gf[order[2]], prob["gw"], prob["grows"], M=M)
+        extra = 2 if gram_mode != "fp64" else 0
+        buf = torch.empty((nM + P + extra,), dtype=torch.float64, device=dev)
+        M, b = buf[:nM], buf[nM:nM + P]
+        flush = self.tc_flush_rows if (extra and self.refine == "exact") else None
+        ops.gram(mode, gf[order[0]], gf[order[1]], gf[order[2]], prob["gw"], prob["grows"], M=M, flush_rows=flush)
         rf = prob["rhs"]
         ops.rhs(rf[0], rf[1], rf[2], prob["rw"], prob["rrows"], b=b)
+        if extra:
+            ops.gram_trace(gf[0], gf[1], gf[2], prob["gw"], prob["grows"], out=buf[nM + P:])
         if self.process_group is not None:
             import torch.distributed as dist
             dist.all_reduce(buf, group=self.process_group)
+        prob["trace"] = buf[nM + P:] if extra else None
+        prob["gram_mode_used"] = gram_mode
         return M, b, role_of_pos
 
-    def _solve(self, k, M, b, m_pos, role_of_pos, method, eps):
+    def _solve(self, k, M, b, m_pos, role_of_pos, method, eps, prob=None):
         """sigma-scaling, ridge and Cholesky solve (reference network.py:293-327) -> step in node layout."""
-        step = self._solve_flat(self._canon(k).contiguous().view(-1), M, b, m_pos, role_of_pos, method, eps)
+        step = self._solve_flat(self._canon(k).contiguous().view(-1), M, b, m_pos, role_of_pos, method, eps, prob=prob)
         return self._from_canon(k, step.reshape(self._canon(k).shape))
 
-    def _solve_flat(self, theta, M, b, m_pos, role_of_pos, method, eps):
+    @staticmethod
+    def _ridge_of(method, eps):
+        m = method.lower()
+        return 0.0 if m in ("exact", "cholesky", "gradient") or m.startswith("gradient") else 2.0 * float(eps)
+
+    def _gram_mode_for(self, method, eps):
+        """Gram mode of one site update: the tensor-core mode, unless a ridge this small already needed the fp64 Gram."""
+        if self.gram_mode != "fp64" and self.refine == "exact" and self._ridge_of(method, eps) <= self._refine_floor:
+            return "fp64"
+        return self.gram_mode
+
+    def _solve_refined(self, theta, M, b, m_pos, role_of_pos, ridge, prob):
+        """Tensor-core Gram modes: Cholesky factor of the TF32 / 3xTF32 Gram as the preconditioner of conjugate gradients on the
+        fp64 matrix-free operator of the same rows.  The iteration solves  (J^T W J / sigma + ridge) x = -(b / sigma + ridge theta)
+        with sigma the exact mean diagonal (fp64 trace), i.e. the reference's own system, to ``refine_rtol``."""
+        P = m_pos[0] * m_pos[1] * m_pos[2]
+        sigma = ops.gram_sigma(M, m_pos, role_of_pos)
+        tr = prob.get("trace")
+        if tr is not None:
+            exact = tr[0:1] / float(P)
+            sigma = torch.where((tr[0:1] == tr[1:2]) & (tr[0:1] > 0), exact, sigma)      # no negative weights: |A_ii| = A_ii
+        A = ops.gram_expand(M, m_pos, role_of_pos, sigma, ridge)
+        rhs = ops.rhs_prepare(b, theta, sigma, ridge)
+        tensor_core = self.solve_mode != "fp64" and P >= self.mixed_min_P
+        work, info = ops.cholesky_factor(A, tensor_core=tensor_core)
+        op = ops.Operator(P, factors=prob["gram"], w=prob["gw"], rows=prob["grows"], group=self.process_group, sigma=sigma, ridge=ridge)
+        x, stats = ops.cg(op, rhs, precond=(A, work, info), max_iter=self.refine_max_iter, rtol=self.refine_rtol)
+        bad = int(info.item())
+        rel, iters = stats.tolist()[:2]
+        if self.process_group is not None:
+            # the ranks' iterates agree to rounding only (atomics in the reductions): rank 0's step and verdict are the ones applied
+            import torch.distributed as dist
+            flag = torch.tensor([float(bad), rel], dtype=torch.float64, device=x.device)
+            src = dist.get_global_rank(self.process_group, 0)
+            dist.broadcast(flag, src=src, group=self.process_group)
+            dist.broadcast(x, src=src, group=self.process_group)
+            bad, rel = int(flag[0].item()), float(flag[1].item())
+        if bad != 0 or not (rel <= self.refine_accept):
+            self._refine_floor = max(self._refine_floor, ridge)
+            raise _NeedExactGram(f"refinement reached {rel:.2e} in {int(iters)} iterations (info {bad}) at ridge {ridge:g}")
+        self.solve_stats["refined"] += 1
+        self.solve_stats["refine_iters"] += int(iters)
+        self.solve_stats["refine_max_rel"] = max(self.solve_stats.get("refine_max_rel", 0.0), float(rel))
+        self.solve_stats["mixed" if tensor_core else "fp64"] += 1
+        return x
+
+    def _solve_flat(self, theta, M, b, m_pos, role_of_pos, method, eps, prob=None):
         """The local solve on flat canonical-order vectors; returns the flat step."""
         m = method.lower()
         if m == "gradient":
@@ -641,6 +706,8 @@ class TensorNetwork:
         if m not in ("exact", "ridge_exact", "cholesky") and not m.startswith("ridge_cholesky"):
             raise ValueError(f"Unknown method: {method}")
         ridge = 0.0 if m in ("exact", "cholesky") else 2.0 * float(eps)
+        if prob is not None and prob.get("gram_mode_used", "fp64") != "fp64" and self.refine == "exact":
+            return self._solve_refined(theta, M, b, m_pos, role_of_pos, ridge, prob)
         sigma = ops.gram_sigma(M, m_pos, role_of_pos)
         A = ops.gram_expand(M, m_pos, role_of_pos, sigma, ridge)
         rhs = ops.rhs_prepare(b, theta, sigma, ridge)
@@ -827,8 +894,16 @@ class TensorNetwork:
     def _one_update(self, k, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss):
         self._check_external()
         prob = self._site_problem(k, y, loss_fn)
-        M, b, role_of_pos = self._accumulate(prob)
-        step = self._solve(k, M, b, prob["m_pos"], role_of_pos, method, eps)
+        M, b, role_of_pos = self._accumulate(prob, self._gram_mode_for(method, eps))
+        try:
+            step = self._solve(k, M, b, prob["m_pos"], role_of_pos, method, eps, prob=prob)
+        except _NeedExactGram:
+            # the tensor-core Gram was too coarse a preconditioner for this ridge (or lost positive definiteness): the site is
+            # redone with the fp64 Gram and the fp64 factorisation -- loudly counted, and remembered for smaller ridges
+            self.solve_stats["gram_fp64_fallback"] += 1
+            del M, b
+            M, b, role_of_pos = self._accumulate(prob, "fp64")
+            step = self._solve(k, M, b, prob["m_pos"], role_of_pos, method, eps, prob=prob)
         node = self.main_nodes[k]
         new = node.tensor.detach().clone().contiguous()
         ops.update_node(new.view(-1), step.view(-1), lr=lr, adaptive_step=adaptive_step, max_norm=max_norm)
@@ -908,9 +983,15 @@ class TensorNetwork:
     def _one_linear_update(self, k, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss):
         self._check_external()
         prob = self._linear_problem(k, y, loss_fn)
-        M, b, role_of_pos = self._accumulate(prob)
+        M, b, role_of_pos = self._accumulate(prob, self._gram_mode_for(method, eps))
         W = self._plan()[k].linear.tensor
-        step = self._solve_flat(W.contiguous().view(-1), M, b, prob["m_pos"], role_of_pos, method, eps)
+        try:
+            step = self._solve_flat(W.contiguous().view(-1), M, b, prob["m_pos"], role_of_pos, method, eps, prob=prob)
+        except _NeedExactGram:
+            self.solve_stats["gram_fp64_fallback"] += 1
+            del M, b
+            M, b, role_of_pos = self._accumulate(prob, "fp64")
+            step = self._solve_flat(W.contiguous().view(-1), M, b, prob["m_pos"], role_of_pos, method, eps, prob=prob)
         new = W.detach().clone().contiguous()
         ops.update_node(new.view(-1), step.contiguous().view(-1), lr=lr, adaptive_step=adaptive_step, max_norm=max_norm)
         self._set_linear(k, new)
@@ -1083,15 +1164,12 @@ class TensorNetwork:
         if self.process_group is not None:
             import torch.distributed as dist
             dist.all_reduce(b, group=self.process_group)
-
-        def matvec(v):
-            out = ops.matvec(gf[0], gf[1], gf[2], prob["gw"], prob["grows"], v.contiguous().view(-1))
-            if self.process_group is not None:
-                import torch.distributed as dist
-                dist.all_reduce(out, group=self.process_group)
-            return out
-
-        return prob, b, matvec
+        # v -> J^T H J v on the virtual rows: the built-in operator of the on-device Krylov drivers (csrc/krylov.cu); calling the
+        # object applies it to a tensor (SciPy bridge)
+        m_pos = prob["m_pos"]
+        op = ops.Operator(m_pos[0] * m_pos[1] * m_pos[2], factors=gf, w=prob["gw"], rows=prob["grows"], group=self.process_group)
+        op.keep = prob["keep"]
+        return prob, b, op
 
     def _krylov_problem(self, node, y, loss_fn):
         """(per-row loss, right-hand side b, matvec v -> J^T H J v) of one node, everything flat in canonical order."""
@@ -1147,36 +1225,12 @@ class TensorNetwork:
         The start vector is random there (``randn_like``, :793); ``x0_fn(node, b)`` lets a caller inject one."""
 
         def solve(node, matvec, b):
+            from ..krylov import lanczos
             rhs = -b
             x0 = x0_fn(node, b) if x0_fn is not None else torch.randn_like(rhs)
-            x0 = x0.reshape(-1)
-            vs = [torch.zeros_like(x0)]
-            alphas = []
-            betas = [None]
-            r0 = rhs - matvec(x0)
-            beta1 = torch.norm(r0)
-            betas.append(beta1)
-            vs.append(r0 / beta1)
-            j = 0
-            for j in range(1, max_iter + 1):
-                wv = matvec(vs[j]) - betas[j] * vs[j - 1] if j > 1 else matvec(vs[j])
-                a_j = (wv * vs[j]).sum()
-                alphas.append(a_j)
-                wv = wv - a_j * vs[j]
-                b_j = torch.norm(wv)
-                betas.append(b_j)
-                vs.append(wv / b_j)
-                if float(b_j.item()) < tol:
-                    break
-            Vm = torch.stack(vs[1:j + 1], dim=-1)
-            Tm = torch.diag(torch.stack(alphas))
-            if len(alphas) > 1:
-                off = torch.stack(betas[2:j + 1])
-                Tm = Tm + torch.diag(off, 1) + torch.diag(off, -1)
-            e1 = torch.zeros(len(alphas), dtype=x0.dtype, device=x0.device)
-            e1[0] = beta1
-            yv = torch.linalg.solve(Tm, e1)                          # j x j tridiagonal, j <= max_iter
-            return x0 + Vm @ yv
+            # r0 = rhs - A x0, max_iter Lanczos vectors (stop when |w_j| < tol), x = x0 + V T^-1 |r0| e1: the recurrence of
+            # network.py:793-824 inside libtn_b200.so (tn_lanczos), scalars on the device
+            return lanczos(matvec, rhs.contiguous().view(-1), x0.contiguous().reshape(-1), maxiter=max_iter, tol=tol)
 
         return self._krylov_swipe(x, y_true, loss_fn, solve, batch_size, num_swipes, lr, timeout, data_device, model_device,
                                   block_callback, loss_callback, "lanczos_swipe")
@@ -1204,6 +1258,10 @@ class TensorNetwork:
 
         return self._krylov_swipe(x, y_true, loss_fn, solve, batch_size, num_swipes, lr, timeout, data_device, model_device,
                                   block_callback, loss_callback, "scipy_swipe")
+
+
+class _NeedExactGram(Exception):
+    """The refinement of a tensor-core Gram mode did not reach its residual: redo the site with the fp64 Gram."""
 
 
 class _FixedTerms:

@@ -79,7 +79,7 @@ def _pairs(F):
     return torch.stack([F[:, i] * F[:, j] for i in range(m) for j in range(i, m)], dim=1)
 
 
-def gram(mode, fa, fb, fc, w, rows, M=None, accumulate=False):
+def gram(mode, fa, fb, fc, w, rows, M=None, accumulate=False, flush_rows=None):
     _bare(w, M)
     A, B, C = _pairs(_rows(fa, rows)), _pairs(_rows(fb, rows)), _pairs(_rows(fc, rows))
     ww = torch.ones(rows, dtype=torch.float64) if w is None else w
@@ -199,8 +199,168 @@ def matvec(fa, fb, fc, w, rows, v, out=None):
     return J.t() @ (ww * (J @ v))
 
 
+def cholesky_factor(A, tensor_core=False):
+    P = A.shape[0]
+    info = torch.zeros(1, dtype=torch.int32)
+    try:
+        L = torch.linalg.cholesky(A[:, :P])
+    except torch.linalg.LinAlgError:
+        info[0] = 1
+        return torch.zeros(1, dtype=torch.float64), info
+    A[:, :P] = torch.tril(L) + torch.triu(A[:, :P], 1)       # the factor overwrites the lower triangle only
+    return torch.zeros(1, dtype=torch.float64), info
+
+
+def cholesky_apply(L, work, info, x):
+    P = L.shape[0]
+    if int(info[0]) == 0:
+        x.copy_(torch.cholesky_solve(x.unsqueeze(-1), torch.tril(L[:, :P])).squeeze(-1))
+    return x
+
+
+def gram_trace(fa, fb, fc, w, rows, out=None):
+    _bare(w, out)
+    q = (_rows(fa, rows) ** 2).sum(1) * (_rows(fb, rows) ** 2).sum(1) * (_rows(fc, rows) ** 2).sum(1)
+    ww = torch.ones(rows, dtype=torch.float64) if w is None else w
+    res = torch.stack([(ww * q).sum(), (ww.abs() * q).sum()])
+    if out is not None:
+        out.copy_(res)
+        return out
+    return res
+
+
+def _apply(op, v):
+    out = op(v)
+    if op.sigma is not None:
+        out = out / op.sigma
+    return out + op.ridge * v if op.ridge != 0.0 else out
+
+
+def cg(op, b, x0=None, precond=None, max_iter=50, rtol=1e-6, poll_every=None):
+    """Stand-in of tn_cg: the recurrences of csrc/krylov.cu in torch."""
+    L, lwork, linfo = precond if precond is not None else (None, None, None)
+    stats = torch.zeros(4, dtype=torch.float64)
+    if linfo is not None and int(linfo[0]) != 0:
+        stats[2] = 1.0
+        return (torch.zeros_like(b) if x0 is None else x0.clone().reshape(-1)), stats
+
+    def prec(r):
+        return r if L is None else cholesky_apply(L, lwork, linfo, r.clone())
+
+    if x0 is not None:
+        x = x0.clone().reshape(-1)
+    elif L is not None:
+        x = prec(b)
+    else:
+        x = torch.zeros_like(b)
+    r = b - _apply(op, x) if (x0 is not None or L is not None) else b.clone()
+    bn = float(torch.dot(b, b))
+    rz_old, p, it = None, None, 0
+    for it in range(max_iter + 1):
+        rel = float(torch.sqrt(torch.dot(r, r) / bn)) if bn > 0 else 0.0
+        stats[0], stats[1] = rel, it
+        if not rel > rtol:
+            stats[2] = 1.0
+            break
+        if it == max_iter:
+            break
+        z = prec(r)
+        rz = torch.dot(r, z)
+        p = z if p is None else z + (rz / rz_old) * p
+        q = _apply(op, p)
+        alpha = rz / torch.dot(p, q)
+        x = x + alpha * p
+        r = r - alpha * q
+        rz_old = rz
+    stats[3] = op.applies
+    return x, stats
+
+
+def minres(op, b, x0=None, max_iter=50, rtol=1e-6, poll_every=None):
+    """Stand-in of tn_minres (Paige & Saunders, as scipy.sparse.linalg.minres without preconditioner or shift)."""
+    stats = torch.zeros(4, dtype=torch.float64)
+    x = torch.zeros_like(b) if x0 is None else x0.clone().reshape(-1)
+    r1 = b - _apply(op, x) if x0 is not None else b.clone()
+    beta1 = float(torch.norm(r1))
+    if beta1 == 0.0:
+        stats[2] = 1.0
+        return x, stats
+    bnorm = float(torch.norm(b))
+    y = r1
+    r2 = r1.clone()
+    oldb, beta, dbar, epsln, phibar = 0.0, beta1, 0.0, 0.0, beta1
+    cs, sn = -1.0, 0.0
+    w = torch.zeros_like(b)
+    w2 = torch.zeros_like(b)
+    for itn in range(1, max_iter + 1):
+        v = y / beta
+        y = _apply(op, v)
+        if itn >= 2:
+            y = y - (beta / oldb) * r1
+        alfa = float(torch.dot(v, y))
+        y = y - (alfa / beta) * r2
+        r1 = r2
+        r2 = y
+        oldb = beta
+        beta = float(torch.norm(r2))
+        oldeps = epsln
+        delta = cs * dbar + sn * alfa
+        gbar = sn * dbar - cs * alfa
+        epsln = sn * beta
+        dbar = -cs * beta
+        gamma = max(float(np.hypot(gbar, beta)), 1e-300)
+        cs, sn = gbar / gamma, beta / gamma
+        phi = cs * phibar
+        phibar = sn * phibar
+        w1 = w2
+        w2 = w
+        w = (v - oldeps * w1 - delta * w2) / gamma
+        x = x + phi * w
+        stats[0], stats[1] = (phibar / bnorm if bnorm > 0 else 0.0), itn
+        if phibar <= rtol * bnorm or beta == 0.0:
+            stats[2] = 1.0
+            break
+    stats[3] = op.applies
+    return x, stats
+
+
+def lanczos(op, b, x0=None, max_iter=50, tol=1e-6, poll_every=None):
+    """Stand-in of tn_lanczos: the reference's own recurrence (tensor/network.py:793-824)."""
+    stats = torch.zeros(4, dtype=torch.float64)
+    x0v = torch.zeros_like(b) if x0 is None else x0.reshape(-1)
+    vs = [torch.zeros_like(b)]
+    alphas, betas = [], [None]
+    r0 = b - _apply(op, x0v) if x0 is not None else b.clone()
+    beta1 = torch.norm(r0)
+    betas.append(beta1)
+    vs.append(r0 / beta1)
+    j = 0
+    for j in range(1, max_iter + 1):
+        wv = _apply(op, vs[j]) - betas[j] * vs[j - 1] if j > 1 else _apply(op, vs[j])
+        a_j = (wv * vs[j]).sum()
+        alphas.append(a_j)
+        wv = wv - a_j * vs[j]
+        b_j = torch.norm(wv)
+        betas.append(b_j)
+        vs.append(wv / b_j)
+        if float(b_j) < tol:
+            stats[2] = 1.0
+            break
+    Vm = torch.stack(vs[1:j + 1], dim=-1)
+    Tm = torch.diag(torch.stack(alphas))
+    if len(alphas) > 1:
+        off = torch.stack(betas[2:j + 1])
+        Tm = Tm + torch.diag(off, 1) + torch.diag(off, -1)
+    e1 = torch.zeros(len(alphas), dtype=b.dtype)
+    e1[0] = beta1
+    yv = torch.linalg.solve(Tm, e1)
+    stats[0], stats[1], stats[3] = float(betas[-1]), j, op.applies
+    return x0v + Vm @ yv, stats
+
+
 NAMES = ["ones_factor", "env_update", "predict", "class_rows", "gram", "rhs", "gram_generic", "gram_sigma", "gram_expand", "rhs_prepare",
-         "cholesky_solve", "cholesky_solve_mixed", "update_node", "qr", "matvec", "bmm", "outer_rows", "rows_dot"]
+         "cholesky_solve", "cholesky_solve_mixed", "update_node", "qr", "matvec", "bmm", "outer_rows", "rows_dot", "cholesky_factor",
+         "cholesky_apply", "gram_trace", "cg", "minres", "lanczos"]
 
 
 def install(monkeypatch=None):

@@ -71,8 +71,9 @@ def test_baseline_config1_full_size_gpu(gram_mode):
     trajectory is chaotic and only the level of the final loss is compared.  CPU twin: test_host_sweep_cpu.py."""
     import cfg1_case as c1
     loss_err, pred_err, core_err = c1.run("cuda", gram_mode=gram_mode)
-    tight = 1e-9 if gram_mode == "fp64" else 1e-5
-    assert loss_err[:5].max() < tight and loss_err[5:7].max() < 1e-3, loss_err
+    # both modes: in 'tf32x3' the Gram only preconditions the exact refinement (network.py::_solve_refined), and the ridges it is too
+    # coarse for (below ~1e-4 here) are redone with the fp64 Gram
+    assert loss_err[:5].max() < 1e-9 and loss_err[5:7].max() < 1e-3, loss_err
     assert loss_err[-1] < 0.2, loss_err
 
 
@@ -82,7 +83,7 @@ def test_baseline_config2_full_size_gpu(gram_mode):
     against tests/golden/cfg2_full.npz, recorded from the unmodified reference: all 17 per-update losses and the final prediction."""
     import cfg2_case as c2
     loss_err, pred_err = c2.run("cuda", gram_mode=gram_mode)
-    tol = 1e-7 if gram_mode == "fp64" else 1e-4
+    tol = 1e-7          # both modes: the tensor-core Gram only preconditions the exact refinement
     assert loss_err.max() < tol and pred_err < 10 * tol, (loss_err, pred_err)
 
 
@@ -101,7 +102,7 @@ def test_baseline_config5b_chain_gpu(gram_mode):
     recorded from the unmodified reference."""
     import cfg5b_case as c5
     loss_err, pred_err = c5.run("cuda", gram_mode=gram_mode)
-    tol = 1e-6 if gram_mode == "fp64" else 1e-4
+    tol = 1e-6          # both modes (north_star: <= 1e-6 for fp64 / 3xTF32)
     assert loss_err.max() < tol and pred_err < 10 * tol, (loss_err.max(), pred_err)
 
 
