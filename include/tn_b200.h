@@ -158,8 +158,9 @@ int tn_matvec_kr3(const tn_factor *fa, const tn_factor *fb, const tn_factor *fc,
  *      All recurrence scalars stay on the device.  Unlike the other entry points these drivers SYNCHRONISE the stream every
  *      `poll_every` iterations to read the convergence flag (poll_every == 0: never -- a fixed sequence of launches whose
  *      kernels turn into no-ops once converged, capturable in a CUDA graph).
- *      stats (4 device doubles, may be NULL): [0] relative residual reached (cg: |b - Op x| / |b|; minres: its estimate
- *      phibar / |b|; lanczos: the last beta), [1] iterations, [2] 1 if stopped by the tolerance, [3] operator applications. */
+ *      stats (5 device doubles, may be NULL): [0] relative residual reached (cg: |b - Op x| / |b|; minres: its estimate
+ *      phibar / |b|; lanczos: the last beta), [1] iterations, [2] 1 if stopped by the tolerance, [3] operator applications,
+ *      [4] (cg only) the value of the stopping criterion.                                                                */
 typedef int (*tn_apply_fn)(void *ctx, const double *v, double *out, void *stream);
 typedef int (*tn_allreduce_fn)(void *ctx, double *buf, int64_t n, void *stream);
 typedef struct tn_operator {
@@ -181,7 +182,9 @@ typedef struct tn_operator {
 /* Conjugate gradients on Op x = b (scipy.sparse.linalg.cg as called at network.py:921-925: stop at |r| <= rtol |b| or
  * max_iter), optionally preconditioned by the Cholesky factor L (lower triangle, row stride lda, with the `Lwork` and `Linfo`
  * of tn_cholesky_factor; Linfo[0] != 0 turns the call into a no-op).  use_x0 == 0: x starts at 0, or at (L L^T)^-1 b when
- * L is given.  With L the factor of the TF32 / 3xTF32 Gram and the built-in fp64 operator this is the refinement that
+ * L is given.  With L the stopping test is |L^-T L^-1 r| <= rtol |x|: z = (L L^T)^-1 r estimates the ERROR of x when L L^T is
+ * close to Op, so the forward error is bounded whatever the condition number (a residual test lets it float with it).
+ * With L the factor of the TF32 / 3xTF32 Gram and the built-in fp64 operator this is the refinement that
  * makes the tensor-core Gram modes solve the fp64 system of solve_system (network.py:293-327).                          */
 int64_t tn_cg_work_elems(const tn_operator *op);
 int tn_cg(const tn_operator *op, const double *L, int64_t lda, const double *Lwork, const int *Linfo, const double *b,

@@ -164,17 +164,33 @@ kr_residual_kernel(const double* __restrict__ b, const double* __restrict__ q, d
 //       [6] relative residual  [7] accumulator of the next |r|^2
 __global__ void cg_latch_kernel(const int* __restrict__ info, int* __restrict__ stop) { *stop = (info && *info != 0) ? 1 : 0; }
 
-// Before iteration `it`: record the residual, stop when it is small enough (or NaN, or b == 0), clear the accumulators.
-__global__ void cg_check_kernel(double* __restrict__ scal, int* __restrict__ stop, double rtol, int it) {
+// Start of iteration `it`: clear the accumulators of the iteration (r.z slot, p.Ap, next |r|^2, |z|^2, |x|^2).
+__global__ void cg_clear_kernel(double* __restrict__ scal, const int* __restrict__ stop, int it) {
+    if (*stop != 0) return;
+    scal[4] = 0.0;
+    scal[7] = 0.0;
+    scal[8] = 0.0;
+    scal[9] = 0.0;
+    scal[2 + ((it + 1) & 1)] = 0.0;
+}
+
+// Convergence test of the iterate x_it.  Unpreconditioned: |r| <= tol |b| (SciPy's criterion).  Preconditioned by a factor of
+// (nearly) the operator itself, z = M^-1 r is (nearly) the ERROR of x, so the test is on the forward error: |z| <= tol |x| --
+// a residual test would let the error float with the condition number of the system.
+__global__ void cg_check_kernel(double* __restrict__ scal, int* __restrict__ stop, double tol, int it, int preconditioned) {
     if (*stop != 0) return;
     const double bn = scal[0], rn = scal[1];
     const double rel = (bn > 0.0) ? sqrt(rn / bn) : 0.0;
+    double crit = rel;
+    if (preconditioned) {
+        const double zz = scal[8], xx = scal[9];
+        crit = (xx > 0.0) ? sqrt(zz / xx) : ((zz > 0.0) ? 1.0 : 0.0);
+        if (!(bn > 0.0)) crit = 0.0;
+    }
     scal[6] = rel;
+    scal[10] = crit;
     scal[5] = (double)it;
-    if (!(rel > rtol)) *stop = 1;
-    scal[4] = 0.0;
-    scal[7] = 0.0;
-    scal[2 + ((it + 1) & 1)] = 0.0;
+    if (!(crit > tol)) *stop = 1;
 }
 
 __global__ void cg_commit_kernel(double* __restrict__ scal, const int* __restrict__ stop) {
@@ -212,6 +228,7 @@ __global__ void kr_stats_kernel(const double* __restrict__ scal, const int* __re
     stats[1] = scal[5];
     stats[2] = (double)*stop;
     stats[3] = applies;
+    stats[4] = scal[10];
 }
 
 // ---- MINRES (Paige & Saunders), the recurrences of scipy.sparse.linalg.minres without a preconditioner or shift -------
@@ -506,21 +523,27 @@ extern "C" int tn_cg(const tn_operator* op, const double* L, int64_t lda, const 
     }
     kr_residual_kernel<<<vb, 256, 0, st>>>(b, use_x0 ? q : nullptr, r, P, scal, stop);
     TN_LAUNCH_CHECK();
-    for (int it = 0; it < max_iter; ++it) {
-        cg_check_kernel<<<1, 1, 0, st>>>(scal, stop, rtol, it);
+    for (int it = 0; it <= max_iter; ++it) {
+        cg_clear_kernel<<<1, 1, 0, st>>>(scal, stop, it);
         TN_LAUNCH_CHECK();
-        if (poll_every > 0 && it > 0 && it % poll_every == 0) {
-            int h = 0;
-            rc = poll_stop(op, stop, scal + 12, st, &h);
-            if (rc != TN_OK) return rc;
-            if (h) break;
-        }
         const double* zz = r;
         if (L) {
             TN_CUDA(cudaMemcpyAsync(z, r, (size_t)P * sizeof(double), cudaMemcpyDeviceToDevice, st));
             rc = cholesky_substitute(L, lda, P, z, Lwork, stop, st);
             if (rc != TN_OK) return rc;
             zz = z;
+            kr_dot_kernel<<<vb, 256, 0, st>>>(z, z, P, scal + 8, stop);
+            kr_dot_kernel<<<vb, 256, 0, st>>>(x, x, P, scal + 9, stop);
+            count_launch(2);
+        }
+        cg_check_kernel<<<1, 1, 0, st>>>(scal, stop, rtol, it, L ? 1 : 0);
+        TN_LAUNCH_CHECK();
+        if (it == max_iter) break;
+        if (poll_every > 0 && it > 0 && it % poll_every == 0) {
+            int h = 0;
+            rc = poll_stop(op, stop, scal + 12, st, &h);
+            if (rc != TN_OK) return rc;
+            if (h) break;
         }
         kr_dot_kernel<<<vb, 256, 0, st>>>(r, zz, P, scal + 2 + ((it + 1) & 1), stop);
         cg_direction_kernel<<<vb, 256, 0, st>>>(zz, p, P, scal, it, stop);
@@ -533,8 +556,6 @@ extern "C" int tn_cg(const tn_operator* op, const double* L, int64_t lda, const 
         count_launch(3);
         TN_CUDA(cudaGetLastError());
     }
-    cg_check_kernel<<<1, 1, 0, st>>>(scal, stop, rtol, max_iter);
-    TN_LAUNCH_CHECK();
     if (stats) {
         kr_stats_kernel<<<1, 1, 0, st>>>(scal, stop, stats, (double)run.applies);
         TN_LAUNCH_CHECK();

@@ -202,9 +202,13 @@ def gram(mode, fa: Factor, fb: Factor, fc: Factor, w, rows, M=None, accumulate=F
     if flush_rows is not None and mode != GRAM_FP64:
         prev = lib.tn_gram_tc_flush_rows(int(flush_rows))
         try:
-            return gram(mode, fa, fb, fc, w, rows, M=M, accumulate=accumulate)
+            return _gram(lib, mode, fa, fb, fc, w, rows, M, accumulate)
         finally:
             lib.tn_gram_tc_flush_rows(prev)
+    return _gram(lib, mode, fa, fb, fc, w, rows, M, accumulate)
+
+
+def _gram(lib, mode, fa, fb, fc, w, rows, M, accumulate):
     _need_cuda(fa.tensor, fb.tensor, fc.tensor, w)
     _bare(w, M)
     n = npairs(fa.m) * npairs(fb.m) * npairs(fc.m)
@@ -594,13 +598,15 @@ def gram_trace(fa: Factor, fb: Factor, fc: Factor, w, rows, out=None):
 
 
 def cg(op: Operator, b, x0=None, precond=None, max_iter=50, rtol=1e-6, poll_every=None):
-    """Conjugate gradients on Op x = b on the device.  ``precond = (L, work, info)`` from cholesky_factor.
-    Returns (x, stats) with stats = [relative residual, iterations, stopped-by-tolerance, operator applications] (device)."""
+    """Conjugate gradients on Op x = b on the device.  ``precond = (L, work, info)`` from cholesky_factor.  Stops at
+    |r| <= rtol |b|, or -- preconditioned -- at |L^-T L^-1 r| <= rtol |x| (an estimate of the relative forward error).
+    Returns (x, stats) with stats = [relative residual, iterations, stopped-by-tolerance, operator applications, value of the
+    stopping criterion] (device)."""
     lib = _lib.load()
     dev = _krylov_common(op, b, x0)
     with _on(dev):
         x = torch.empty_like(b) if x0 is None else x0.clone().reshape(-1)
-        stats = torch.zeros((4,), dtype=torch.float64, device=dev)
+        stats = torch.zeros((5,), dtype=torch.float64, device=dev)
         bind = _OpBinding(op, [b, x])
         work = torch.empty((lib.tn_cg_work_elems(ctypes.byref(bind.c)),), dtype=torch.float64, device=dev)
         bind.buffers.append(work)

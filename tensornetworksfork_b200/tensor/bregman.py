@@ -110,11 +110,24 @@ class XEAutogradBregman(nn.Module):
 
 
 class KLDivBregman(XEAutogradBregman):
-    """Closed-form twin of XEAutogradBregman in the reference (tensor/bregman.py:100-146)."""
+    """KL divergence to a target probability vector on logits [w*x, 0] (reference tensor/bregman.py:100-146): the reported loss is
+    the cross-entropy of the arg-max label (:127), but the gradient uses the target vector ITSELF, g = w (p - y)[:-1] (:143) -- soft
+    labels pull towards y, not towards its arg-max.  The Hessian is that of XEAutogradBregman."""
 
     def __init__(self, w=1.0, grad_clip=1e3):
         super().__init__(w=w)
-        self.grad_clip = grad_clip
+        self.grad_clip = grad_clip          # kept for the signature; the reference's clipped expression is commented out (:134-139)
+
+    def forward(self, x, y, only_loss=False):
+        out = super().forward(x, y, only_loss=only_loss)
+        if only_loss:
+            return out
+        loss, _, H = out
+        return loss, self.w * (self._p(x).exp() - y)[..., :-1], H
+
+    def rank1_terms(self, x, y):
+        loss, _, U, lam = super().rank1_terms(x, y)
+        return loss, self.w * (self._p(x).exp() - y)[..., :-1], U, lam
 
 
 def hessian_terms(loss_fn, y_pred, y):

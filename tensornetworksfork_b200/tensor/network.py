@@ -153,8 +153,8 @@ class TensorNetwork:
         # gradient iteration on the fp64 matrix-free operator J^T W J / sigma + ridge, so the step solves the reference's fp64
         # system (network.py:293-327) to `refine_rtol`; "gram" = round 1's behaviour (the step solves the tensor-core Gram's system)
         self.refine = "exact"
-        self.refine_rtol = 1e-11
-        self.refine_accept = 1e-9       # residual the refinement must reach, else the site is redone with an fp64 Gram
+        self.refine_rtol = 1e-11        # stopping test of the refinement: estimated relative forward error of the step ...
+        self.refine_accept = 1e-9       # ... and what it must reach for the step to be used, else the site is redone with an fp64 Gram
         self.refine_max_iter = 30
         self._refine_floor = -1.0       # ridge values at or below this needed the fp64 Gram; go there directly
         # fp32 accumulation window (rows) of the tensor-core Gram when it only preconditions the exact refinement: longer = faster,
@@ -680,7 +680,8 @@ class TensorNetwork:
         op = ops.Operator(P, factors=prob["gram"], w=prob["gw"], rows=prob["grows"], group=self.process_group, sigma=sigma, ridge=ridge)
         x, stats = ops.cg(op, rhs, precond=(A, work, info), max_iter=self.refine_max_iter, rtol=self.refine_rtol)
         bad = int(info.item())
-        rel, iters = stats.tolist()[:2]
+        st = stats.tolist()
+        rel, iters = st[4], st[1]            # value of the stopping criterion (forward-error estimate), iterations
         if self.process_group is not None:
             # the ranks' iterates agree to rounding only (atomics in the reductions): rank 0's step and verdict are the ones applied
             import torch.distributed as dist

@@ -255,16 +255,23 @@ def cg(op, b, x0=None, precond=None, max_iter=50, rtol=1e-6, poll_every=None):
         x = torch.zeros_like(b)
     r = b - _apply(op, x) if (x0 is not None or L is not None) else b.clone()
     bn = float(torch.dot(b, b))
+    stats = torch.zeros(5, dtype=torch.float64)
     rz_old, p, it = None, None, 0
     for it in range(max_iter + 1):
         rel = float(torch.sqrt(torch.dot(r, r) / bn)) if bn > 0 else 0.0
-        stats[0], stats[1] = rel, it
-        if not rel > rtol:
+        z = prec(r)
+        crit = rel
+        if L is not None:
+            xx, zz = float(torch.dot(x, x)), float(torch.dot(z, z))
+            crit = (zz / xx) ** 0.5 if xx > 0 else (1.0 if zz > 0 else 0.0)
+            if not bn > 0:
+                crit = 0.0
+        stats[0], stats[1], stats[4] = rel, it, crit
+        if not crit > rtol:
             stats[2] = 1.0
             break
         if it == max_iter:
             break
-        z = prec(r)
         rz = torch.dot(r, z)
         p = z if p is None else z + (rz / rz_old) * p
         q = _apply(op, p)

@@ -10,7 +10,7 @@ GOLDEN_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 def names():
     return sorted(n for n in (os.path.splitext(os.path.basename(p))[0] for p in glob.glob(os.path.join(GOLDEN_DIR, "*.npz")))
-                  if not n.startswith(("krylov_", "dmrg_", "cumsum_", "type1_", "conv_", "growing_", "linear_", "batch_", "grad_", "cfg1_", "cfg2_", "cfg3_", "cfg5b_", "cfg4b_", "cfg5a_", "cfg4a_")))
+                  if not n.startswith(("krylov_", "dmrg_", "cumsum_", "type1_", "conv_", "growing_", "linear_", "batch_", "grad_", "cfg1_", "cfg2_", "cfg3_", "cfg5b_", "cfg4b_", "cfg5a_", "cfg4a_", "wrappers")))
 
 
 def load_krylov(name):

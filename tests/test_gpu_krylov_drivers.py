@@ -54,7 +54,7 @@ def test_cg_with_and_without_preconditioner(shape):
     facs, w = factors(t, V, DEV)
     op = ops.Operator(P, factors=facs, w=w, rows=rows, sigma=torch.tensor([sigma], device=DEV), ridge=ridge)
     x, stats = ops.cg(op, torch.tensor(b, device=DEV), max_iter=4 * P, rtol=1e-12)
-    rel, iters, stopped, applies = stats.tolist()
+    rel, iters, stopped, applies = stats.tolist()[:4]
     assert stopped == 1.0 and rel <= 1e-12 and gu.relerr(x.cpu().numpy(), want) < 1e-9, (rel, iters)
     # preconditioned by the factor of a PERTURBED matrix (1e-4: coarser than the 3xTF32 Gram): same solution, few iterations
     Ap = A * (1.0 + 1e-4 * rng.normal(size=A.shape))
@@ -65,8 +65,8 @@ def test_cg_with_and_without_preconditioner(shape):
     work, info = ops.cholesky_factor(Ad)
     assert int(info.item()) == 0
     x2, stats2 = ops.cg(op, torch.tensor(b, device=DEV), precond=(Ad, work, info), max_iter=50, rtol=1e-12)
-    rel2, iters2 = stats2.tolist()[:2]
-    assert rel2 <= 1e-12 and iters2 <= 12 and gu.relerr(x2.cpu().numpy(), want) < 1e-10, (rel2, iters2)
+    rel2, iters2, crit2 = stats2[0].item(), stats2[1].item(), stats2[4].item()
+    assert crit2 <= 1e-12 and iters2 <= 12 and gu.relerr(x2.cpu().numpy(), want) < 1e-10, (rel2, iters2, crit2)
     # the factor applied alone is the solve of the perturbed system
     y = ops.cholesky_apply(Ad, work, info, torch.tensor(b, device=DEV))
     assert gu.relerr(y.cpu().numpy(), np.linalg.solve(Ap, b)) < 1e-9
@@ -101,7 +101,7 @@ def test_minres_matches_scipy_and_the_cpu_restatement(shape):
     b = rng.normal(size=P)
     facs_c, w_c = factors(t, V, "cpu")
     facs_d, w_d = factors(t, V, DEV)
-    for iters in (2, 9, 40):
+    for iters in (2, 5, min(12, P // 3)):       # well below P: past that the Lanczos basis has lost orthogonality and iterates differ
         op_c = ops.Operator(P, matvec=lambda v: fake_ops.matvec(*facs_c, w_c, rows, v), device="cpu")
         want, st_c = fake_ops.minres(op_c, torch.tensor(b), max_iter=iters, rtol=1e-10)
         got, st_d = ops.minres(ops.Operator(P, factors=facs_d, w=w_d, rows=rows), torch.tensor(b, device=DEV), max_iter=iters, rtol=1e-10)
@@ -146,7 +146,7 @@ def test_callback_operator_and_early_stop():
     for fn in (ops.cg, ops.minres):
         calls[0] = 0
         x, stats = fn(ops.Operator(P, matvec=mv, device=b.device), b, max_iter=500, rtol=1e-10)
-        rel, iters, stopped, applies = stats.tolist()
+        rel, iters, stopped, applies = stats.tolist()[:4]
         assert stopped == 1.0 and iters < 100 and float((x - want).norm() / want.norm()) < 1e-8
         assert calls[0] == int(applies) and calls[0] <= iters + 8          # polled every few iterations, not run to max_iter
     x, stats = ops.lanczos(ops.Operator(P, matvec=mv, device=b.device), b, x0=torch.zeros_like(b), max_iter=60, tol=1e-9)

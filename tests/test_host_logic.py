@@ -139,3 +139,28 @@ def test_loss_closed_forms_match_rank1_terms():
         Hf = H.expand(7, 3, 3) if H.shape[-1] == 1 else H
         assert torch.allclose(Hr, Hf, atol=1e-14)
         assert torch.allclose(g, g2) and torch.allclose(loss, l2)
+
+
+def test_kl_divergence_uses_the_soft_target_in_its_gradient():
+    """KLDivBregman (reference tensor/bregman.py:100-146): loss from the arg-max label, gradient from the probability vector itself."""
+    import importlib.util
+    import sys
+    import types
+    torch.manual_seed(0)
+    x = torch.randn(40, 3)
+    y = torch.softmax(torch.randn(40, 4), dim=-1)          # soft labels
+    loss, g, H = tnb.KLDivBregman(w=0.7).forward(x, y)
+    z = torch.cat((0.7 * x, torch.zeros(40, 1)), dim=-1)
+    p = torch.softmax(z, dim=-1)
+    assert torch.allclose(g, 0.7 * (p - y)[:, :-1], atol=1e-14)
+    assert torch.allclose(loss, -torch.log(p).gather(1, y.argmax(1, keepdim=True)).squeeze(1), atol=1e-13)
+    t = tnb.KLDivBregman(w=0.7).rank1_terms(x, y)
+    assert torch.allclose(t[1], g) and torch.allclose(torch.einsum("sv,svi,svj->sij", t[3], t[2], t[2]), H, atol=1e-13)
+    if os.path.isdir("/root/reference/tensor"):
+        for name in ("matplotlib", "matplotlib.pyplot"):
+            sys.modules.setdefault(name, types.ModuleType(name))
+        spec = importlib.util.spec_from_file_location("_ref_bregman", "/root/reference/tensor/bregman.py")
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        rl, rg, rH = mod.KLDivBregman(w=0.7).forward(x, y)
+        assert torch.allclose(rl, loss, atol=1e-13) and torch.allclose(rg, g, atol=1e-13) and torch.allclose(rH, H, atol=1e-13)
