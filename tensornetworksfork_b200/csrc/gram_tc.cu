@@ -773,7 +773,10 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     }
     const int64_t nU = (int64_t)p.nA * p.nB;
     const int64_t n = nU * p.nC;
-    p.BN = (p.nC >= 256) ? 256 : ((p.nC + 15) / 16) * 16;
+    {   // V tiles of equal width: nC = 300 (config 3) becomes 2 x 160 columns instead of 2 x 256 (41 % of them padding)
+        const int ntile = (p.nC + 255) / 256;
+        p.BN = (((p.nC + ntile - 1) / ntile + 15) / 16) * 16;
+    }
     p.T = (nU > TC_M && p.BN * 2 <= 512) ? 2 : 1;
     int NS = 4;
     while (NS >= 2 && tc_smem_bytes(A.m, B.m, C.m, p.BN, p.T, NS) > 226 * 1024) --NS;

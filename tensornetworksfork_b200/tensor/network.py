@@ -671,8 +671,11 @@ class TensorNetwork:
         sigma = ops.gram_sigma(M, m_pos, role_of_pos)
         tr = prob.get("trace")
         if tr is not None:
+            # mean |A_ii| = trace / P whenever no diagonal entry is negative -- every positive semi-definite output Hessian, whatever
+            # the signs of the individual virtual-row weights.  The exact trace is used when it agrees with the mean |diagonal| of the
+            # tensor-core Gram to that Gram's accuracy; an indefinite Hessian with negative diagonal entries keeps the latter.
             exact = tr[0:1] / float(P)
-            sigma = torch.where((tr[0:1] == tr[1:2]) & (tr[0:1] > 0), exact, sigma)      # no negative weights: |A_ii| = A_ii
+            sigma = torch.where((exact - sigma).abs() <= 1e-3 * sigma.abs(), exact, sigma)
         A = ops.gram_expand(M, m_pos, role_of_pos, sigma, ridge)
         rhs = ops.rhs_prepare(b, theta, sigma, ridge)
         tensor_core = self.solve_mode != "fp64" and P >= self.mixed_min_P

@@ -5,11 +5,7 @@ import numpy as np, torch
 torch.set_default_dtype(torch.float64)
 import cfg1_case, cfg2_case, cfg5b_case
 np.set_printoptions(precision=2, linewidth=250)
-for gm in ("fp64", "tf32x3"):
+for gm in ("fp64", "tf32x3", "tf32"):
     le, pe, ce = cfg1_case.run("cuda", gram_mode=gm); print("cfg1", gm, "loss_err", le, "pred", pe, "core", ce, flush=True)
     le, pe = cfg2_case.run("cuda", gram_mode=gm); print("cfg2", gm, "loss_err", le, "pred", pe, flush=True)
     le, pe = cfg5b_case.run("cuda", gram_mode=gm); print("cfg5b", gm, "loss_err", le, "pred", pe, flush=True)
-for fr in (256, 512, 1024):
-    os.environ["TN_TC_FLUSH_ROWS"] = str(fr)
-    le, pe, ce = cfg1_case.run("cuda", gram_mode="tf32x3"); print("cfg1 tf32x3 flush", fr, le, pe, ce, flush=True)
-    le, pe = cfg5b_case.run("cuda", gram_mode="tf32x3"); print("cfg5b tf32x3 flush", fr, le.max(), pe, flush=True)
