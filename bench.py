@@ -73,7 +73,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg5a", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", dest="n", type=int, default=None, help="rows per GPU (default: the workload's)")
-    ap.add_argument("--gram-mode", default="tf32", choices=["fp64", "tf32", "tf32x3"],
+    ap.add_argument("--gram-mode", default="tf32", choices=["fp64", "tf32", "tf32x3", "f16"],
                     help="precision of the Gram build; in the tensor-core modes the Gram only preconditions the exact fp64 refinement "
                          "(TensorNetwork.refine = 'exact'), so 'tf32' (one MMA pass) gives the same step as 'tf32x3' and 'fp64'")
     ap.add_argument("--flush-rows", type=int, default=None, help="fp32 accumulation window of the tensor-core Gram (default: the engine's)")
@@ -243,7 +243,14 @@ class KernelTimer:
             elif n in ("cholesky_solve", "cholesky_solve_mixed", "cholesky_factor"):
                 self.extra[n].append(int(a[0].shape[0]))
             elif n in ("cg", "minres", "lanczos"):
-                self.extra[n].append(out[1])          # the stats tensor (device): read after the timed region
+                op_ = a[0]
+                by_ = 0.0
+                if op_.factors is not None:
+                    fa, fb, fc = op_.factors
+                    raw_b = 1 if fb.map_kind != 0 else fb.m
+                    # two passes over the three factors (8 B each), w*(J v) written and read once, weights read once
+                    by_ = 2 * 8.0 * op_.rows * (fa.m / fa.div + raw_b / fb.div + fc.m / fc.div) + 3 * 8.0 * op_.rows
+                self.extra[n].append((out[1], by_))          # the stats tensor (device): read after the timed region
             return out
 
         return inner
@@ -523,22 +530,27 @@ def bench_b200(args):
                     "measured_peaks": measured}
         wl = dict(wl, _avg_matvecs=(mv_count1 - mv_count0) / max(updates, 1))
     elif wl.get("solver"):
-        mv_ms = tot["matvec"]
-        mv_bytes = sum(timer.extra["matvec"])
-        mv_s = sum(mv_ms) / 1e3
+        # the matvecs run inside the on-device Krylov drivers (tn_cg / tn_minres): time of the driver calls, operator applications
+        # from their device counters, algorithmic bytes of the two passes per application
+        drv = "cg" if timer.extra["cg"] else "minres"
+        st_ = [(st.tolist(), by_) for st, by_ in timer.extra[drv]]
+        applies = sum(s_[3] for s_, _ in st_)
+        mv_bytes = sum(s_[3] * by_ for s_, by_ in st_)
+        mv_s = sum(tot[drv]) / 1e3
         hbm = peaks.get("hbm_gbs", 6550.7)
-        roofline = {"kernel": "matvec_kr3 (env_kernel dot epilogue + kr3 rhs pass)", "bound": "hbm",
-                    "achieved": mv_bytes / mv_s / 1e9 if mv_s > 0 else 0.0, "peak": hbm, "unit": "GB/s",
+        roofline = {"kernel": f"tn_{drv}: env pass with weighted prediction epilogue + kr3 rhs pass per operator application (+ the recurrence's vector kernels)",
+                    "bound": "hbm", "achieved": mv_bytes / mv_s / 1e9 if mv_s > 0 else 0.0, "peak": hbm, "unit": "GB/s",
                     "frac": (mv_bytes / mv_s / 1e9 / hbm) if mv_s > 0 else None, "traffic": None,
                     "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6550.7 GB/s",
-                    "share_of_step": mv_s / (ms / 1e3), "launches": len(mv_ms),
-                    "matvecs_per_site_update": len(mv_ms) / max(updates, 1),
-                    "mean_us_per_matvec": 1e3 * sum(mv_ms) / max(len(mv_ms), 1), "measured_peaks": measured}
-        wl = dict(wl, _avg_matvecs=len(mv_ms) / max(updates, 1))
+                    "share_of_step": mv_s / (ms / 1e3), "launches": len(st_),
+                    "matvecs_per_site_update": applies / max(updates, 1),
+                    "iterations_mean": float(np.mean([s_[1] for s_, _ in st_])) if st_ else None,
+                    "mean_us_per_matvec": 1e6 * mv_s / max(applies, 1), "measured_peaks": measured}
+        wl = dict(wl, _avg_matvecs=applies / max(updates, 1))
     chol_ms = tot["cholesky_solve"] + tot["cholesky_solve_mixed"] + tot["cholesky_factor"]
     chol_flops = sum(P_ ** 3 / 3.0 for P_ in timer.extra["cholesky_solve"] + timer.extra["cholesky_solve_mixed"] + timer.extra["cholesky_factor"])
     n_mixed = len(tot["cholesky_solve_mixed"]) + int(tn.solve_stats.get("mixed", 0) > 0)
-    cg_stats = [st.tolist() for st in timer.extra["cg"]]
+    cg_stats = [st.tolist() for st, _ in timer.extra["cg"]]
     refine_info = None
     if cg_stats and not wl.get("solver"):
         refine_info = {"solves": len(cg_stats), "iterations_mean": float(np.mean([c_[1] for c_ in cg_stats])),

@@ -80,8 +80,10 @@ int tn_class_rows(const double *env, const double *U, const double *g, double *F
  * M has na*nb*nc entries, n = m(m+1)/2: the unique entries of A = J^T H J under the
  * Kronecker symmetry.  `w` may be NULL (all ones).  `work` holds ksplit partial copies of M
  * (ksplit >= 1 chosen by tn_gram_ksplit); the result is reduced into M deterministically.
- * mode: 0 = fp64 (CUDA-core FMA), 1 = TF32 tcgen05, 2 = 3xTF32 tcgen05 (fp64 flush every
- * `flush_rows` rows).  accumulate != 0 adds to M instead of overwriting.                        */
+ * mode: 0 = fp64 (FP64 tensor pipe, DMMA), 1 = TF32 tcgen05, 2 = 3xTF32 tcgen05, 3 = FP16 operands on tcgen05 (kind::f16,
+ * fp32 accumulate; factors scaled per factor to [0.5, 1) first: a preconditioner-grade Gram for the exact refinement of
+ * tn_cg, twice the samples per shared-memory transaction of mode 1).  Modes 1-3 accumulate in fp32 (TMEM) and flush to fp64
+ * every `flush_rows` rows.  accumulate != 0 adds to M instead of overwriting.                     */
 int tn_gram_ksplit(int64_t rows, int ma, int mb, int mc, int mode);
 int tn_gram_kr3(int mode, const tn_factor *fa, const tn_factor *fb, const tn_factor *fc, const double *w,
                 int64_t rows, double *M, double *work, int ksplit, int accumulate, void *stream);

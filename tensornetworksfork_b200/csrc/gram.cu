@@ -538,14 +538,14 @@ extern "C" int tn_gram_kr3(int mode, const tn_factor* fa, const tn_factor* fb, c
     TN_CHECK_ARG(fa && fb && fc && M, "tn_gram_kr3: null argument");
     TN_CHECK_ARG(rows >= 0, "tn_gram_kr3: negative rows");
     TN_CHECK_ARG(fa->m >= 1 && fb->m >= 1 && fc->m >= 1, "tn_gram_kr3: empty factor");
-    TN_CHECK_ARG(mode >= 0 && mode <= 2, "tn_gram_kr3: unknown mode %d", mode);
+    TN_CHECK_ARG(mode >= 0 && mode <= 3, "tn_gram_kr3: unknown mode %d", mode);
     if (rows == 0) {                   // an empty shard contributes nothing
         if (!accumulate)
             TN_CUDA(cudaMemsetAsync(M, 0, (size_t)npairs(fa->m) * npairs(fb->m) * npairs(fc->m) * sizeof(double), as_stream(stream)));
         return TN_OK;
     }
     if (mode == 0) return launch_kr3<1>(fa, fb, fc, w, rows, M, work, ksplit, accumulate, as_stream(stream));
-    if (mode == 1 || mode == 2) return tn_gram_kr3_tc(mode, fa, fb, fc, w, rows, M, accumulate, stream);
+    if (mode >= 1 && mode <= 3) return tn_gram_kr3_tc(mode, fa, fb, fc, w, rows, M, accumulate, stream);
     set_error("tn_gram_kr3: unknown mode %d", mode);
     return TN_EINVAL;
 }

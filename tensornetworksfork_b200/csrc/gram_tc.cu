@@ -20,6 +20,7 @@
 // full[s] (producers -> MMA, after fence.proxy.async) and empty[s] (tcgen05.commit -> producers).
 #include <stdlib.h>
 #include <atomic>
+#include <cuda_fp16.h>
 #include <type_traits>
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -102,6 +103,8 @@ __device__ __forceinline__ int tc_exponent(unsigned long long bits) {
 __global__ void __launch_bounds__(256)
 tc_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict__ w, int64_t rows, float* __restrict__ Z,
                 int64_t zpitch, const unsigned long long* __restrict__ amax, int planar = 0) {
+    // planar: 0 = row-major fp32, 1 = planes of 4 fp32 samples (16 B per Z row), 2 = planes of 8 fp16 samples (16 B per Z row)
+    __half* Zh = reinterpret_cast<__half*>(Z);
     __shared__ float tile[32][33];
     const double sa = ldexp(1.0, -tc_exponent(amax[0])), sb = ldexp(1.0, -tc_exponent(amax[1]));
     const double sc = ldexp(1.0, -tc_exponent(amax[2])), sw = ldexp(1.0, -tc_exponent(amax[3]));
@@ -133,10 +136,17 @@ tc_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict_
             const int64_t zr = 2 * mA + mB + mC;                         // Z rows
             // row-major: Z[row][s];  piece-planar: the 16 bytes (4 samples) of every row of one piece are contiguous
             auto at = [&](int64_t row) -> int64_t {
+                if (planar == 2) return (((s >> 5) * 4 + ((s >> 3) & 3)) * zr + row) * 8 + (s & 7);
                 return planar ? ((((s >> 4) * 4 + ((s >> 2) & 3)) * zr + row) * 4 + (s & 3)) : (row * zpitch + s);
             };
-            Z[at(mA + i)] = v;
-            if (i < mA) Z[at(i)] = (s < rows) ? v * (float)((w ? w[s] : 1.0) * sw) : 0.f;
+            const float vw = (i < mA && s < rows) ? v * (float)((w ? w[s] : 1.0) * sw) : 0.f;
+            if (planar == 2) {
+                Zh[at(mA + i)] = __float2half_rn(v);
+                if (i < mA) Zh[at(i)] = __float2half_rn(vw);
+            } else {
+                Z[at(mA + i)] = v;
+                if (i < mA) Z[at(i)] = vw;
+            }
         }
     }
 }
@@ -152,20 +162,27 @@ __device__ __forceinline__ uint64_t l2_evict_last_policy() {
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+// The LAST flush of a CTA: its tile of M is not touched again by this CTA, so it should leave the L2 first and not compete
+// (as an evict_last line) with the tiles of the CTAs that are still accumulating.
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void red_add_f64_keep(double* addr, double v, uint64_t pol) {
     asm volatile("red.global.add.L2::cache_hint.f64 [%0], %1, %2;" ::"l"(addr), "d"(v), "l"(pol) : "memory");
 }
 
 __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_total, int BN, int warp, int lane, int64_t u0,
                                                int64_t nU, int v0, int nC, double* __restrict__ M, float* __restrict__ scratch,
-                                               double unscale, int tile_stride = TC_M) {
+                                               double unscale, int tile_stride = TC_M, bool final_flush = false) {
     const int q = warp & 3;
     const int half = (warp - 1) >> 2;
     const int ngroups = (cols_total + 31) / 32;
     const int g_lo = half * ((ngroups + 1) / 2);
     const int g_hi = min(ngroups, g_lo + (ngroups + 1) / 2);
     float* sc = scratch + (size_t)(warp - 1) * (32 * 33);
-    const uint64_t l2_keep = l2_evict_last_policy();
+    const uint64_t l2_keep = final_flush ? l2_evict_first_policy() : l2_evict_last_policy();
     for (int g = g_lo; g < g_hi; ++g) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 32), r);
@@ -436,7 +453,7 @@ gram_tc_kernel(TcParams p) {
                 mbar_wait(acc_full, acc_phase);
                 acc_phase ^= 1;
                 tc_fence_after();
-                drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, reinterpret_cast<float*>(stage_base), unscale);
+                drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, reinterpret_cast<float*>(stage_base), unscale, TC_M, (c + 1) == nchunks);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty);
@@ -452,6 +469,268 @@ gram_tc_kernel(TcParams p) {
     }
 }
 
+
+// ---- FP16 operand variant (mode 3).  Same pipeline as gram_tc_kernel<0, T, true>, with the operand tiles in fp16:
+// a 16-byte piece of a tile row holds 8 samples instead of 4, a stage covers 32 samples (two tcgen05.mma kind::f16, K = 16), the
+// raw-factor ring holds fp16 rows and the producers multiply with packed half2 arithmetic.  Per sample this halves every
+// shared-memory transaction of the kernel -- raw-factor loads, tile stores, the tensor core's operand fetch -- which is what
+// bounds the one-pass TF32 kernel (its shared-memory data pipe is ~90 % busy at 43 % of the TF32 MMA rate).  fp16 has the
+// mantissa of tf32 (11 bits) but a narrow exponent: the factors are scaled to [0.5, 1) per factor as in the other modes, so
+// entries below 6e-5 of a factor's largest lose relative precision and entries below 6e-8 vanish.  The mode exists for the
+// sweep's exact refinement (TensorNetwork.refine = 'exact'), where the Gram is only a preconditioner; measured as one
+// (tools/precond_experiment.py): the same conjugate-gradient iteration counts as TF32 operands.
+constexpr int H_KC = 32;            // samples per stage
+constexpr int H_NP = H_KC / 8;      // 16-byte pieces (8 samples) of a row per stage
+
+__device__ __forceinline__ uint4 lds128u(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ void sts128u(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ uint32_t hmul2u(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint4 hmul8(uint4 a, uint4 b) {
+    return make_uint4(hmul2u(a.x, b.x), hmul2u(a.y, b.y), hmul2u(a.z, b.z), hmul2u(a.w, b.w));
+}
+__device__ __forceinline__ void umma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// Instruction descriptor for kind::f16 with fp16 operands, fp32 accumulate, both operands K-major.
+__device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
+    return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int T>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gram_tc16_kernel(TcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int BN = p.BN, NS = p.nstages;
+    const int mA = p.mA, mB = p.mB, mC = p.mC;
+
+    // ---- shared memory: [NS operand stages][TC_RAW_SLOTS raw-factor slots of four planes][mbarriers][tmem slot]
+    constexpr uint32_t a_tile_bytes = TC_M * H_KC * 2;         // one U tile of one stage: [piece][row][16 B]
+    const uint32_t b_tile_bytes = (uint32_t)BN * H_KC * 2;
+    const uint32_t stage_bytes = T * a_tile_bytes + b_tile_bytes;
+    const uint32_t z_rows = (uint32_t)(2 * mA + mB + mC);
+    const uint32_t raw_rows = z_rows + 1;                       // + an all-zero row for the padding rows of the tiles
+    const uint32_t plane_stride = ((raw_rows * 16 + 95) / 128) * 128 + 32;
+    const uint32_t raw_bytes = H_NP * plane_stride;
+    uint8_t* stage_base = smem_raw;
+    uint8_t* raw_base = smem_raw + (size_t)NS * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)TC_RAW_SLOTS * raw_bytes);
+    uint64_t* full = bars;              // [NS]
+    uint64_t* empty = bars + NS;        // [NS]
+    uint64_t* acc_full = bars + 2 * NS;
+    uint64_t* acc_empty = bars + 2 * NS + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
+    uint64_t* raw_full = bars + 2 * NS + 3;      // [TC_RAW_SLOTS]
+
+    const uint32_t tmem_cols_needed = (uint32_t)(T * BN);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], TC_PROD_WARPS);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, TC_PROD_WARPS);
+        for (int i = 0; i < TC_RAW_SLOTS; ++i) mbar_init(&raw_full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < TC_RAW_SLOTS * H_NP * 4; i += TC_THREADS) {      // the zero row of every plane of every slot (16 B each)
+        const int slot = i / (H_NP * 4), e = i % (H_NP * 4);
+        reinterpret_cast<uint32_t*>(raw_base + (size_t)slot * raw_bytes + (size_t)(e >> 2) * plane_stride + (size_t)z_rows * 16)[e & 3] = 0u;
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t k_begin = (int64_t)blockIdx.z * p.rows_per_split;          // multiples of H_KC; Z is zero padded
+    const int64_t k_end = min(p.zpitch, k_begin + p.rows_per_split);
+    const int64_t nchunks = (k_end > k_begin) ? (k_end - k_begin) / H_KC : 0;
+    const int64_t chunks_per_flush = p.flush_rows / H_KC;
+    const int64_t nU = (int64_t)p.nA * p.nB;
+    const int64_t u0 = (int64_t)blockIdx.x * (TC_M * T);
+    const int v0 = blockIdx.y * BN;
+
+    if (warp == 0) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0 && nchunks > 0) {
+            const uint32_t idesc = make_idesc_f16(TC_M, BN);
+            const uint32_t lbo_a = TC_M * 16, lbo_b = (uint32_t)BN * 16, sbo = 128;
+            uint32_t acc_phase = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            int64_t in_window = 0;
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const bool first_of_window = in_window == 0;
+                if (first_of_window && c > 0) {
+                    mbar_wait(acc_empty, acc_phase);   // accumulator drained by the producers
+                    acc_phase ^= 1;
+                    tc_fence_after();
+                }
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(stage_base + (size_t)s * stage_bytes);
+                const uint32_t b_base = sb + T * a_tile_bytes;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    const uint32_t a_base = sb + (uint32_t)t * a_tile_bytes;
+                    const uint32_t d = tmem_base + (uint32_t)(t * BN);
+#pragma unroll
+                    for (int j = 0; j < H_KC / 16; ++j) {          // one MMA = 16 samples = two 16-byte pieces
+                        const uint32_t ao = (uint32_t)(2 * j) * lbo_a, bo = (uint32_t)(2 * j) * lbo_b;
+                        const uint32_t acc0 = (first_of_window && j == 0) ? 0u : 1u;
+                        umma_f16(d, make_desc(a_base + ao, lbo_a, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
+                    }
+                }
+                umma_commit(&empty[s]);
+                const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+                if (last_of_window) {
+                    umma_commit(acc_full);
+                    in_window = 0;
+                }
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // =============================== producers / epilogue ===============================
+        const int pt = tid - 32;  // 0..255
+        const double unscale = ldexp(1.0, 2 * (tc_exponent(p.amax[0]) + tc_exponent(p.amax[1]) + tc_exponent(p.amax[2])) +
+                                              tc_exponent(p.amax[3]));
+        const uint32_t raw_s = smem_u32(raw_base);
+        const uint32_t zero_row = z_rows * 16;
+        uint32_t usrc[4] = {zero_row, zero_row, zero_row, zero_row};   // byte offsets of w*fa[ia], fa[ja], fb[ib], fb[jb] in a plane
+        int u_tile = 0, u_row = pt & 127, u_c0 = 0;
+        constexpr int U_NC = (T == 2) ? H_NP : H_NP / 2;                // pieces per thread and stage
+        if (T == 2) u_tile = pt >> 7;
+        else u_c0 = (pt >> 7) * U_NC;
+        {
+            const int64_t gu = u0 + (int64_t)u_tile * TC_M + u_row;
+            if (gu < nU) {
+                const int qa = (int)(gu / p.nB), qb = (int)(gu - (int64_t)qa * p.nB);
+                int ia, ja, ib, jb;
+                pair_decode(qa, mA, ia, ja);
+                pair_decode(qb, mB, ib, jb);
+                usrc[0] = (uint32_t)ia * 16;
+                usrc[1] = (uint32_t)(mA + ja) * 16;
+                usrc[2] = (uint32_t)(2 * mA + ib) * 16;
+                usrc[3] = (uint32_t)(2 * mA + jb) * 16;
+            }
+        }
+        uint32_t vsrc[2] = {zero_row, zero_row};
+        if (pt < BN && v0 + pt < p.nC) {
+            int ic, jc;
+            pair_decode(v0 + pt, mC, ic, jc);
+            vsrc[0] = (uint32_t)(2 * mA + mB + ic) * 16;
+            vsrc[1] = (uint32_t)(2 * mA + mB + jc) * 16;
+        }
+        const uint32_t udst = (uint32_t)u_tile * a_tile_bytes + (uint32_t)u_row * 16 + (uint32_t)u_c0 * (TC_M * 16);
+        const uint32_t vdst = T * a_tile_bytes + (uint32_t)pt * 16;
+        const uint32_t lbo_b = (uint32_t)BN * 16;
+        const uint32_t stage_s = smem_u32(stage_base);
+        const __half* Zh = reinterpret_cast<const __half*>(p.Z);
+
+        auto issue_chunk = [&](int64_t chunk) {
+            // one thread: expect the bytes of the four planes on the slot's barrier, then one bulk copy per plane
+            if (chunk < nchunks && pt == 0) {
+                const int slot = (int)(chunk % TC_RAW_SLOTS);
+                const uint32_t bar = smem_u32(&raw_full[slot]);
+                const uint32_t plane_bytes = z_rows * 16;
+                const uint32_t dst0 = raw_s + (uint32_t)slot * raw_bytes;
+                const __half* src0 = Zh + ((k_begin / H_KC + chunk) * H_NP) * (int64_t)z_rows * 8;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(H_NP * plane_bytes) : "memory");
+#pragma unroll
+                for (int part = 0; part < H_NP; ++part)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst0 + (uint32_t)part * plane_stride), "l"(src0 + (int64_t)part * z_rows * 8), "r"(plane_bytes), "r"(bar)
+                                 : "memory");
+            }
+        };
+        issue_chunk(0);
+        issue_chunk(1);
+
+        uint32_t acc_phase = 0;
+        int s = 0, rs = 0;
+        uint32_t ph = 0;
+        int64_t in_window = 0;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");  // chunk c-1 is fully consumed by every producer
+            issue_chunk(c + 2);                                          // reuses the slot chunk c-1 occupied
+            mbar_wait(&raw_full[rs], (uint32_t)((c / TC_RAW_SLOTS) & 1));   // the bulk copies of chunk c have landed
+            if (lane == 0) mbar_wait(&empty[s], ph ^ 1);                 // first pass over the ring returns immediately
+            __syncwarp();
+            const uint32_t rb = raw_s + (uint32_t)rs * raw_bytes;
+            const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
+            {   // ---- U rows: all loads, then the products, then the stores
+                uint4 x0[U_NC], x1[U_NC], x2[U_NC], x3[U_NC];
+#pragma unroll
+                for (int cc = 0; cc < U_NC; ++cc) {
+                    const uint32_t o = (uint32_t)(u_c0 + cc) * plane_stride;
+                    x0[cc] = lds128u(rb + usrc[0] + o);
+                    x1[cc] = lds128u(rb + usrc[1] + o);
+                    x2[cc] = lds128u(rb + usrc[2] + o);
+                    x3[cc] = lds128u(rb + usrc[3] + o);
+                }
+#pragma unroll
+                for (int cc = 0; cc < U_NC; ++cc)
+                    sts128u(sb + udst + (uint32_t)cc * (TC_M * 16), hmul8(hmul8(x0[cc], x1[cc]), hmul8(x2[cc], x3[cc])));
+            }
+            if (pt < BN) {   // ---- V rows
+                uint4 y0[H_NP], y1[H_NP];
+#pragma unroll
+                for (int cc = 0; cc < H_NP; ++cc) {
+                    y0[cc] = lds128u(rb + vsrc[0] + (uint32_t)cc * plane_stride);
+                    y1[cc] = lds128u(rb + vsrc[1] + (uint32_t)cc * plane_stride);
+                }
+#pragma unroll
+                for (int cc = 0; cc < H_NP; ++cc) sts128u(sb + vdst + (uint32_t)cc * lbo_b, hmul8(y0[cc], y1[cc]));
+            }
+            fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+            if (++s == NS) { s = 0; ph ^= 1; }
+            if (++rs == TC_RAW_SLOTS) rs = 0;
+            const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+            if (last_of_window) {
+                in_window = 0;
+                mbar_wait(acc_full, acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, reinterpret_cast<float*>(stage_base), unscale, TC_M, (c + 1) == nchunks);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+static size_t tc16_smem_bytes(int mA, int mB, int mC, int BN, int T, int NS) {
+    const size_t stage = (size_t)T * TC_M * H_KC * 2 + (size_t)BN * H_KC * 2;
+    const size_t plane = (((size_t)(2 * mA + mB + mC + 1) * 16 + 95) / 128) * 128 + 32;
+    return NS * stage + TC_RAW_SLOTS * H_NP * plane + (2 * NS + 2) * 8 + 16 + 32;
+}
 
 // ---- CTA-pair variant (cta_group::2) for the large shapes (T == 2, BN == 256).
 // Two CTAs of a cluster (the two SMs of a TPC) execute every MMA together as M = 256 x N = 256: each CTA synthesises its own
@@ -708,7 +987,7 @@ gram_tc_pair_kernel(TcParams p) {
                 acc_phase ^= 1;
                 tc_fence_after();
                 drain_accumulator(tmem_base, TP_T * TP_BN, TP_BN, warp, lane, u0_cta, nU, v0, p.nC, p.M,
-                                  reinterpret_cast<float*>(stage_base), unscale, 2 * TC_M);
+                                  reinterpret_cast<float*>(stage_base), unscale, 2 * TC_M, (c + 1) == nchunks);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(acc_empty, 0);
@@ -764,13 +1043,17 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     p.nA = npairs(A.m);
     p.nB = npairs(B.m);
     p.nC = npairs(C.m);
+    const bool f16 = (mode == 3);
+    const int KC = f16 ? H_KC : TC_KC;             // samples per pipeline stage
     p.split = (mode == 2) ? 1 : 0;
     p.planar = 0;
     p.flush_rows = (tn::g_tc_flush_rows > 0) ? tn::g_tc_flush_rows : TC_FLUSH_ROWS_DEFAULT;
     if (const char* e = getenv("TN_TC_FLUSH_ROWS")) {
         const int v = atoi(e);
-        if (v >= TC_KC) p.flush_rows = (v / TC_KC) * TC_KC;
+        if (v >= KC) p.flush_rows = v;
     }
+    p.flush_rows = (p.flush_rows / KC) * KC;
+    if (p.flush_rows < KC) p.flush_rows = KC;
     const int64_t nU = (int64_t)p.nA * p.nB;
     const int64_t n = nU * p.nC;
     {   // V tiles of equal width: nC = 300 (config 3) becomes 2 x 160 columns instead of 2 x 256 (41 % of them padding)
@@ -778,21 +1061,22 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
         p.BN = (((p.nC + ntile - 1) / ntile + 15) / 16) * 16;
     }
     p.T = (nU > TC_M && p.BN * 2 <= 512) ? 2 : 1;
+    auto smem_of = [&](int T_, int NS_) { return f16 ? tc16_smem_bytes(A.m, B.m, C.m, p.BN, T_, NS_) : tc_smem_bytes(A.m, B.m, C.m, p.BN, T_, NS_); };
     int NS = 4;
-    while (NS >= 2 && tc_smem_bytes(A.m, B.m, C.m, p.BN, p.T, NS) > 226 * 1024) --NS;
+    while (NS >= 2 && smem_of(p.T, NS) > 226 * 1024) --NS;
     if (NS < 2 && p.T == 2) {
         p.T = 1;
         NS = 4;
-        while (NS >= 2 && tc_smem_bytes(A.m, B.m, C.m, p.BN, p.T, NS) > 226 * 1024) --NS;
+        while (NS >= 2 && smem_of(p.T, NS) > 226 * 1024) --NS;
     }
     TN_CHECK_ARG(NS >= 2, "tn_gram_kr3 (tensor-core modes): factor sizes %d+%d+%d do not fit the shared-memory pipeline", A.m, B.m, C.m);
     p.nstages = NS;
-    const size_t smem = tc_smem_bytes(A.m, B.m, C.m, p.BN, p.T, NS);
+    const size_t smem = smem_of(p.T, NS);
     if (!accumulate) TN_CUDA(cudaMemsetAsync(M, 0, (size_t)n * sizeof(double), st));
     if (rows == 0) return TN_OK;
 
     // ---- pre-pass: Z = [w*fa | fa | fb | fc] feature-major fp32, rows zero padded to a multiple of TC_KC
-    p.zpitch = ceil_div64(rows, TC_KC) * TC_KC;
+    p.zpitch = ceil_div64(rows, KC) * KC;
     const int z_rows = 2 * A.m + B.m + C.m;
     {   // keep freed scratch in the stream-ordered pool: the default threshold (0) returns it to the OS at every sync,
         // which made each call pay a fresh multi-hundred-MB allocation
@@ -808,7 +1092,7 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
         }
     }
     float* Z = nullptr;
-    const size_t z_bytes = (size_t)z_rows * p.zpitch * sizeof(float);
+    const size_t z_bytes = (size_t)z_rows * p.zpitch * (f16 ? sizeof(__half) : sizeof(float));
     TN_CUDA(cudaMallocAsync(&Z, z_bytes + 64, st));
     unsigned long long* amax = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(Z) + z_bytes);
     TN_CUDA(cudaMemsetAsync(amax, 0, 4 * sizeof(unsigned long long), st));
@@ -828,13 +1112,14 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
         p.planar = (!getenv("TN_TC_RAW_ROWMAJOR") && !getenv("TN_TC_PAIR") &&
                     4 * ((((size_t)(z_rows + 1) * 16 + 95) / 128) * 128 + 32) <= (size_t)(z_rows + 1) * TC_KCP * 4 &&
                     smem + 32 <= 227 * 1024) ? 1 : 0;
+        if (f16) p.planar = 2;                     // planes of eight fp16 samples
         tc_stage_kernel<<<grid, 256, 0, st>>>(A, B, C, w, rows, Z, p.zpitch, amax, p.planar);
         TN_LAUNCH_CHECK();
     }
     // CTA-pair kernel (opt-in, TN_TC_PAIR=1).  Measured on the config-5a middle site (131 072 rows, tools/tc_pair_probe.py):
     // bit-identical M, but 530 vs 557 TF/s issued in 3xTF32 and 217 vs 268 in TF32 -- the 1-CTA kernel already runs at ~0.9 of
     // the sustained (power-capped) tensor rate, so halving the operand traffic buys nothing and the cluster-scope barriers cost.
-    bool pair = (p.T == 2 && p.BN == TP_BN && nU >= 8LL * 512 && getenv("TN_TC_PAIR") && !getenv("TN_TC_NO_PAIR"));
+    bool pair = (!f16 && p.T == 2 && p.BN == TP_BN && nU >= 8LL * 512 && getenv("TN_TC_PAIR") && !getenv("TN_TC_NO_PAIR"));
     int NSP = 5;
     if (pair) {
         while (NSP >= 2 && tc_pair_smem_bytes(A.m, B.m, C.m, NSP) > 226 * 1024) --NSP;
@@ -865,12 +1150,22 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     TN_CHECK_ARG(gy <= 65535 && gx <= 0x7fffffff, "tn_gram_kr3: grid too large");
     // split the rows when there are too few tiles to fill the machine (flushes are atomic adds, so splits compose)
     int64_t ks = ceil_div64((int64_t)sm_count(), gx * gy);
-    const int64_t max_ks = ceil_div64(p.zpitch, 4 * TC_KC);
+    const int64_t max_ks = ceil_div64(p.zpitch, 4 * KC);
     if (ks > max_ks) ks = max_ks;
     if (ks < 1) ks = 1;
     if (ks > 65535) ks = 65535;
-    p.rows_per_split = ceil_div64(ceil_div64(p.zpitch, ks), TC_KC) * TC_KC;
+    p.rows_per_split = ceil_div64(ceil_div64(p.zpitch, ks), KC) * KC;
     ks = ceil_div64(p.zpitch, p.rows_per_split);
+    if (f16) {
+        using Kern16 = void (*)(TcParams);
+        Kern16 k16 = (p.T == 2) ? gram_tc16_kernel<2> : gram_tc16_kernel<1>;
+        TN_SMEM(k16, smem);
+        dim3 grid16((unsigned)gx, (unsigned)gy, (unsigned)ks);
+        k16<<<grid16, TC_THREADS, smem, st>>>(p);
+        TN_LAUNCH_CHECK();
+        TN_CUDA(cudaFreeAsync(Z, st));
+        return TN_OK;
+    }
     using Kern = void (*)(TcParams);
     static const Kern kerns[2][2][2] = {{{gram_tc_kernel<0, 1, false>, gram_tc_kernel<0, 2, false>},
                                          {gram_tc_kernel<1, 1, false>, gram_tc_kernel<1, 2, false>}},

@@ -22,7 +22,7 @@ from ..ops import Factor
 from .bregman import hessian_terms
 from .node import TensorNode
 
-_GRAM_MODES = {"fp64": ops.GRAM_FP64, "tf32": ops.GRAM_TF32, "tf32x3": ops.GRAM_TF32X3, "3xtf32": ops.GRAM_TF32X3}
+_GRAM_MODES = {"fp64": ops.GRAM_FP64, "tf32": ops.GRAM_TF32, "tf32x3": ops.GRAM_TF32X3, "3xtf32": ops.GRAM_TF32X3, "f16": ops.GRAM_F16}
 
 
 class MappedInput:

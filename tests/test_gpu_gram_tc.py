@@ -20,7 +20,7 @@ from tensornetworksfork_b200 import ops  # noqa: E402
 from tensornetworksfork_b200.ops import Factor  # noqa: E402
 
 DEV = "cuda"
-TOL = {ops.GRAM_TF32X3: 3e-5, ops.GRAM_TF32: 2e-3}
+TOL = {ops.GRAM_TF32X3: 3e-5, ops.GRAM_TF32: 2e-3, ops.GRAM_F16: 5e-3}      # fp16 operands: every product rounded to 11 bits
 
 SHAPES = [
     # rows, ma, mb, mc, V
@@ -46,7 +46,7 @@ def make(rows, ma, mb, mc, V, seed):
     return Factor(Fa, m=ma), Factor(Fb, m=mb, div=V), Factor(Fc, m=mc, div=V), w, S * V
 
 
-@pytest.mark.parametrize("mode", [ops.GRAM_TF32X3, ops.GRAM_TF32])
+@pytest.mark.parametrize("mode", [ops.GRAM_TF32X3, ops.GRAM_TF32, ops.GRAM_F16])
 @pytest.mark.parametrize("shape", SHAPES)
 def test_tc_gram_matches_fp64(shape, mode):
     fa, fb, fc, w, rows = make(*shape, seed=sum(shape))
@@ -136,3 +136,38 @@ def test_tc_gram_config5a_site_full_width():
     v = torch.randn(ma * mb * mc, device=DEV, generator=g)
     Av = ops.matvec(*fac(0, 4096), w[:4096], 4096, v)
     assert float(torch.dot(v, Av)) >= 0.0
+
+
+def test_f16_gram_special_cases():
+    """FP16-operand mode (kind::f16, mode 3): feature-map factor, class rows with signed weights, accumulation over row shards, a
+    wide dynamic range (per-factor power-of-two scaling keeps it finite) and the config-5a middle site."""
+    g = torch.Generator(device=DEV).manual_seed(9)
+    S = 7000
+    X = torch.rand((S, 12), device=DEV, generator=g) * 2 - 1
+    L = torch.randn((S, 16), device=DEV, generator=g)
+    R = torch.randn((S, 16), device=DEV, generator=g)
+    w = torch.full((S,), 2.0, device=DEV)
+    fb = Factor(X, m=2, map_kind=ops.MAP_SINCOS, col=7)
+    ref = ops.gram(ops.GRAM_FP64, Factor(L, m=16), fb, Factor(R, m=16), w, S)
+    got = ops.gram(ops.GRAM_F16, Factor(L, m=16), fb, Factor(R, m=16), w, S)
+    assert gu.relerr(got.cpu().numpy(), ref.cpu().numpy()) < 5e-3
+    half = S // 2 + 8
+    parts = ops.gram(ops.GRAM_F16, Factor(L[:half], m=16), Factor(X[:half], m=2, map_kind=ops.MAP_SINCOS, col=7), Factor(R[:half], m=16), w[:half], half)
+    parts = ops.gram(ops.GRAM_F16, Factor(L[half:], m=16), Factor(X[half:], m=2, map_kind=ops.MAP_SINCOS, col=7), Factor(R[half:], m=16), w[half:],
+                     S - half, M=parts, accumulate=True)
+    assert gu.relerr(parts.cpu().numpy(), ref.cpu().numpy()) < 5e-3
+    fa, fb2, fc, w2, rows = make(4000, 12, 3, 12, 1, seed=77)
+    fa = Factor(fa.tensor * 1e-28, m=12)
+    fc = Factor(fc.tensor * 3e17, m=12)
+    w2 = w2.abs() * 1e-9
+    ref = ops.gram(ops.GRAM_FP64, fa, fb2, fc, w2, rows)
+    got = ops.gram(ops.GRAM_F16, fa, fb2, fc, w2, rows)
+    assert torch.isfinite(got).all() and gu.relerr(got.cpu().numpy(), ref.cpu().numpy()) < 5e-3
+    S, ma, mb, mc = 16384, 38, 29, 38
+    Fa = torch.randn((S, ma), device=DEV, generator=g)
+    Fb = torch.rand((S, mb), device=DEV, generator=g) * 2 - 1
+    Fc = torch.randn((S, mc), device=DEV, generator=g)
+    w = torch.full((S,), 2.0, device=DEV)
+    full = ops.gram(ops.GRAM_F16, Factor(Fa, m=ma), Factor(Fb, m=mb), Factor(Fc, m=mc), w, S)
+    ref = ops.gram(ops.GRAM_FP64, Factor(Fa, m=ma), Factor(Fb, m=mb), Factor(Fc, m=mc), w, S)
+    assert float((full - ref).norm() / ref.norm()) < 5e-3

@@ -169,7 +169,7 @@ def test_gram_trace_is_the_exact_trace():
         assert abs(tr[0] - np.trace(A)) <= 1e-11 * np.trace(Aabs) and abs(tr[1] - np.trace(Aabs)) <= 1e-11 * np.trace(Aabs)
 
 
-@pytest.mark.parametrize("gram_mode", ["tf32x3", "tf32"])
+@pytest.mark.parametrize("gram_mode", ["tf32x3", "tf32", "f16"])
 @pytest.mark.parametrize("name", ["tt_poly_reg", "tnml_poly_xe", "cpd_reg", "tnml_sincos_qr", "tt_poly5_full"])
 def test_tensor_core_modes_are_exact_after_refinement(name, gram_mode):
     """A free-running sweep in a tensor-core Gram mode against the REFERENCE recording at fp64 tolerances: the Gram (1e-5 /

@@ -64,7 +64,7 @@ def test_cumsum_matrix_free_sweeps_gpu():
     assert core_err < 5e-4 and loss_err < 5e-5, (core_err, loss_err)
 
 
-@pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3", "tf32"])
+@pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3", "tf32", "f16"])
 def test_baseline_config1_full_size_gpu(gram_mode):
     """BASELINE config 1 at full size against tests/golden/cfg1_full.npz (recorded from the unmodified reference): the first two
     half-sweeps (ridge 0.075, 2.8e-3) to rounding / to the 3xTF32 bound, the third (1e-4) loosely; beyond that the reference's own
@@ -77,7 +77,7 @@ def test_baseline_config1_full_size_gpu(gram_mode):
     assert loss_err[-1] < 0.2, loss_err
 
 
-@pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3", "tf32"])
+@pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3", "tf32", "f16"])
 def test_baseline_config2_full_size_gpu(gram_mode):
     """BASELINE config 2 at full size (CPD rank 100, 20640 x 9, 5 factors, two sweeps with the wrapper's ridge schedule 1.0 * 0.5^NS)
     against tests/golden/cfg2_full.npz, recorded from the unmodified reference: all 17 per-update losses and the final prediction."""
@@ -95,7 +95,7 @@ def test_baseline_config3_chain_gpu():
     assert loss_err.max() < 1e-6 and pred_err < 1e-5, (loss_err.max(), pred_err)
 
 
-@pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3", "tf32"])
+@pytest.mark.parametrize("gram_mode", ["fp64", "tf32x3", "tf32", "f16"])
 def test_baseline_config5b_chain_gpu(gram_mode):
     """BASELINE config 5b's chain (28 sites, polynomial degree 5, rank 38, QR re-gauge, P up to 8664 -- with 'tf32x3' the mixed
     tensor-core solve is on the path) on a 2048-row subsample, one sweep = 55 updates, against tests/golden/cfg5b_chain28.npz

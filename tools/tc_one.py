@@ -6,7 +6,7 @@ torch.set_default_dtype(torch.float64)
 from tensornetworksfork_b200 import ops
 from tensornetworksfork_b200.ops import Factor
 S = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-mode = {"tf32x3": ops.GRAM_TF32X3, "tf32": ops.GRAM_TF32, "fp64": ops.GRAM_FP64}[sys.argv[2] if len(sys.argv) > 2 else "tf32x3"]
+mode = {"tf32x3": ops.GRAM_TF32X3, "tf32": ops.GRAM_TF32, "fp64": ops.GRAM_FP64, "f16": ops.GRAM_F16}[sys.argv[2] if len(sys.argv) > 2 else "tf32x3"]
 ma, mb, mc = (int(v) for v in (sys.argv[3].split(",") if len(sys.argv) > 3 else "38,29,38".split(",")))
 g = torch.Generator(device="cuda").manual_seed(0)
 Fa = torch.randn((S, ma), device="cuda", generator=g); Fb = torch.rand((S, mb), device="cuda", generator=g); Fc = torch.randn((S, mc), device="cuda", generator=g)
