@@ -73,9 +73,9 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="cfg5a", choices=sorted(WORKLOADS))
     ap.add_argument("--rows", dest="n", type=int, default=None, help="rows per GPU (default: the workload's)")
-    ap.add_argument("--gram-mode", default="tf32", choices=["fp64", "tf32", "tf32x3", "f16"],
-                    help="precision of the Gram build; in the tensor-core modes the Gram only preconditions the exact fp64 refinement "
-                         "(TensorNetwork.refine = 'exact'), so 'tf32' (one MMA pass) gives the same step as 'tf32x3' and 'fp64'")
+    ap.add_argument("--gram-mode", default="f16", choices=["fp64", "tf32", "tf32x3", "f16"],
+                    help="operand precision of the Gram build; in the tensor-core modes the Gram only preconditions the exact fp64 refinement "
+                         "(TensorNetwork.refine = 'exact'), so 'f16' / 'tf32' (one MMA pass) give the same step as 'tf32x3' and 'fp64'")
     ap.add_argument("--flush-rows", type=int, default=None, help="fp32 accumulation window of the tensor-core Gram (default: the engine's)")
     ap.add_argument("--solve-mode", default="auto", choices=["auto", "fp64", "mixed"],
                     help="local solve: auto = tensor-core factorisation + fp64 refinement for P >= 8192 in the tf32 gram modes")
@@ -466,6 +466,10 @@ def bench_b200(args):
             peak, peak_src = measured["fp64_tflops_sustained"], "cuBLAS DGEMM 8192^3 measured in this run (sustained)"
         else:
             peak, peak_src = 35.5, "cuBLAS DGEMM measured on this pool earlier (profiles/r1_peaks_tf32_fp64.json)"
+    elif args.gram_mode == "f16":
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        peak_src = ("sustained 16-bit dense tensor peak (cuBLAS bf16 8192^3, MEASURED_PEAKS.json bf16_tflops_sustained: kernel timed inside a long "
+                    "step; fp16 and bf16 run at the same rate) -- " + ("of measured" if peaks else "of fallback 1400"))
     else:
         if measured:
             peak, peak_src = measured["tf32_tflops_sustained"], "cuBLAS TF32 GEMM 8192^3 measured in this run (sustained; kernel is timed inside a long step)"
@@ -484,7 +488,7 @@ def bench_b200(args):
     file_peak = None
     if args.gram_mode != "fp64":
         bf16 = peaks.get("bf16_tflops_sustained")
-        file_peak = bf16 / 2.0 if bf16 else 1400.0 / 2.0
+        file_peak = (bf16 if bf16 else 1400.0) / (1.0 if args.gram_mode == "f16" else 2.0)
     traffic, traffic_note = None, None
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "r2_traffic.json")))[f"gram_tc_kernel[{args.gram_mode}]"]
@@ -502,8 +506,8 @@ def bench_b200(args):
                 "achieved_is": "executed MMA flop: 2*rows*n_a*n_b*n_c unique Kronecker-pair entries" + (" x3 (hi*hi, hi*lo, lo*hi)" if mult == 3.0 else "")
                                + " / CUDA-event time of the Gram launches",
                 "peak_source": peak_src,
-                "frac_of_half_bf16_sustained_file": (achieved / file_peak) if file_peak else None,
-                "half_bf16_sustained_file": file_peak,
+                "frac_of_file_peak": (achieved / file_peak) if file_peak else None,
+                "file_peak": file_peak, "file_peak_is": "MEASURED_PEAKS.json bf16_tflops_sustained" + ("" if args.gram_mode == "f16" else " / 2 (TF32 rate)"),
                 "survey_equiv_tflops": algo / gsum / 1e12 if gsum > 0 else 0.0,
                 "survey_equiv_is": "SURVEY 8(d) count rows*P*(P+1) of a plain symmetric Gram over the same time: an equivalent rate (the kernel "
                                    "skips the 3.67x of it that the Kronecker symmetry makes redundant), not a utilisation",

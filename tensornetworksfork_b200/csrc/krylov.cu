@@ -505,6 +505,7 @@ extern "C" int tn_cg(const tn_operator* op, const double* L, int64_t lda, const 
     const unsigned vb = run.vblocks;
 
     TN_CUDA(cudaMemsetAsync(scal, 0, 24 * sizeof(double), st));
+    const bool caller_x0 = use_x0 != 0;
     cg_latch_kernel<<<1, 1, 0, st>>>(Linfo, stop);      // a failed factorisation switches everything below off
     TN_LAUNCH_CHECK();
     if (!use_x0) {
@@ -539,7 +540,7 @@ extern "C" int tn_cg(const tn_operator* op, const double* L, int64_t lda, const 
         cg_check_kernel<<<1, 1, 0, st>>>(scal, stop, rtol, it, L ? 1 : 0);
         TN_LAUNCH_CHECK();
         if (it == max_iter) break;
-        if (poll_every > 0 && it > 0 && it % poll_every == 0) {
+        if (poll_every > 0 && (it > 0 || caller_x0) && it % poll_every == 0) {      // a caller's x0 (warm start) may already do
             int h = 0;
             rc = poll_stop(op, stop, scal + 12, st, &h);
             if (rc != TN_OK) return rc;
