@@ -77,6 +77,9 @@ void count_launch(int n = 1);   // bookkeeping for tn_launch_count()
 int cholesky_factorize(double* A, int64_t lda, int64_t P, double* work, int* info, cudaStream_t st, float* X, int64_t NBO);
 int cholesky_substitute(const double* A, int64_t lda, int64_t P, double* rhs, const double* work, const int* stop, cudaStream_t st);
 int64_t cholesky_default_nbo(int64_t P);
+// one-launch matrix-free operator for small cores (matvec_fused.cu): TN_OK = launched, 1 = shape outside its range
+int matvec_fused(const tn_factor* fa, const tn_factor* fb, const tn_factor* fc, const double* w, int64_t rows, const double* v, double* out,
+                 const int* stop, cudaStream_t st);
 // environment step with an optional per-row scale of the prediction epilogue (env.cu): yhat[row] *= yscale[row]
 int env_update_scaled(const double* env_in, int64_t env_ld, int env_div, const double* x, int64_t x_ld, int map_kind, int f, int cdiv,
                       const double* core, double* out, int64_t out_ld, const double* dot, int64_t dot_ld, int dot_div, double* yhat,

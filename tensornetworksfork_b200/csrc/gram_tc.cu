@@ -479,8 +479,7 @@ gram_tc_kernel(TcParams p) {
 // entries below 6e-5 of a factor's largest lose relative precision and entries below 6e-8 vanish.  The mode exists for the
 // sweep's exact refinement (TensorNetwork.refine = 'exact'), where the Gram is only a preconditioner; measured as one
 // (tools/precond_experiment.py): the same conjugate-gradient iteration counts as TF32 operands.
-constexpr int H_KC = 32;            // samples per stage
-constexpr int H_NP = H_KC / 8;      // 16-byte pieces (8 samples) of a row per stage
+constexpr int H_KC_DEFAULT = 32;    // samples per stage (two MMAs of K = 16); 64 is the other instantiation
 
 __device__ __forceinline__ uint4 lds128u(uint32_t addr) {
     uint4 v;
@@ -508,9 +507,10 @@ __device__ __forceinline__ uint32_t make_idesc_f16(int M, int N) {
     return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-template <int T>
+template <int T, int H_KC>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gram_tc16_kernel(TcParams p) {
+    constexpr int H_NP = H_KC / 8;      // 16-byte pieces (8 samples) of a row per stage
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -676,29 +676,35 @@ gram_tc16_kernel(TcParams p) {
             __syncwarp();
             const uint32_t rb = raw_s + (uint32_t)rs * raw_bytes;
             const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
-            {   // ---- U rows: all loads, then the products, then the stores
-                uint4 x0[U_NC], x1[U_NC], x2[U_NC], x3[U_NC];
+            // ---- U rows, four pieces at a time: all loads, then the products, then the stores
 #pragma unroll
-                for (int cc = 0; cc < U_NC; ++cc) {
-                    const uint32_t o = (uint32_t)(u_c0 + cc) * plane_stride;
+            for (int g0 = 0; g0 < U_NC; g0 += 4) {
+                constexpr int G = (U_NC < 4) ? U_NC : 4;
+                uint4 x0[G], x1[G], x2[G], x3[G];
+#pragma unroll
+                for (int cc = 0; cc < G; ++cc) {
+                    const uint32_t o = (uint32_t)(u_c0 + g0 + cc) * plane_stride;
                     x0[cc] = lds128u(rb + usrc[0] + o);
                     x1[cc] = lds128u(rb + usrc[1] + o);
                     x2[cc] = lds128u(rb + usrc[2] + o);
                     x3[cc] = lds128u(rb + usrc[3] + o);
                 }
 #pragma unroll
-                for (int cc = 0; cc < U_NC; ++cc)
-                    sts128u(sb + udst + (uint32_t)cc * (TC_M * 16), hmul8(hmul8(x0[cc], x1[cc]), hmul8(x2[cc], x3[cc])));
+                for (int cc = 0; cc < G; ++cc)
+                    sts128u(sb + udst + (uint32_t)(g0 + cc) * (TC_M * 16), hmul8(hmul8(x0[cc], x1[cc]), hmul8(x2[cc], x3[cc])));
             }
-            if (pt < BN) {   // ---- V rows
-                uint4 y0[H_NP], y1[H_NP];
+            if (pt < BN) {   // ---- V rows, four pieces at a time
 #pragma unroll
-                for (int cc = 0; cc < H_NP; ++cc) {
-                    y0[cc] = lds128u(rb + vsrc[0] + (uint32_t)cc * plane_stride);
-                    y1[cc] = lds128u(rb + vsrc[1] + (uint32_t)cc * plane_stride);
+                for (int g0 = 0; g0 < H_NP; g0 += 4) {
+                    uint4 y0[4], y1[4];
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) {
+                        y0[cc] = lds128u(rb + vsrc[0] + (uint32_t)(g0 + cc) * plane_stride);
+                        y1[cc] = lds128u(rb + vsrc[1] + (uint32_t)(g0 + cc) * plane_stride);
+                    }
+#pragma unroll
+                    for (int cc = 0; cc < 4; ++cc) sts128u(sb + vdst + (uint32_t)(g0 + cc) * lbo_b, hmul8(y0[cc], y1[cc]));
                 }
-#pragma unroll
-                for (int cc = 0; cc < H_NP; ++cc) sts128u(sb + vdst + (uint32_t)cc * lbo_b, hmul8(y0[cc], y1[cc]));
             }
             fence_proxy_async();          // generic-proxy writes -> visible to the tensor core (async proxy)
             __syncwarp();
@@ -726,10 +732,10 @@ gram_tc16_kernel(TcParams p) {
     }
 }
 
-static size_t tc16_smem_bytes(int mA, int mB, int mC, int BN, int T, int NS) {
-    const size_t stage = (size_t)T * TC_M * H_KC * 2 + (size_t)BN * H_KC * 2;
+static size_t tc16_smem_bytes(int mA, int mB, int mC, int BN, int T, int NS, int kc) {
+    const size_t stage = (size_t)T * TC_M * kc * 2 + (size_t)BN * kc * 2;
     const size_t plane = (((size_t)(2 * mA + mB + mC + 1) * 16 + 95) / 128) * 128 + 32;
-    return NS * stage + TC_RAW_SLOTS * H_NP * plane + (2 * NS + 2) * 8 + 16 + 32;
+    return NS * stage + TC_RAW_SLOTS * (kc / 8) * plane + (2 * NS + 2) * 8 + 16 + 32;
 }
 
 // ---- CTA-pair variant (cta_group::2) for the large shapes (T == 2, BN == 256).
@@ -1044,7 +1050,9 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     p.nB = npairs(B.m);
     p.nC = npairs(C.m);
     const bool f16 = (mode == 3);
-    const int KC = f16 ? H_KC : TC_KC;             // samples per pipeline stage
+    int kc16 = H_KC_DEFAULT;
+    if (const char* e = getenv("TN_TC16_KC")) kc16 = (atoi(e) == 64) ? 64 : 32;
+    const int KC = f16 ? kc16 : TC_KC;             // samples per pipeline stage
     p.split = (mode == 2) ? 1 : 0;
     p.planar = 0;
     p.flush_rows = (tn::g_tc_flush_rows > 0) ? tn::g_tc_flush_rows : TC_FLUSH_ROWS_DEFAULT;
@@ -1061,7 +1069,7 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
         p.BN = (((p.nC + ntile - 1) / ntile + 15) / 16) * 16;
     }
     p.T = (nU > TC_M && p.BN * 2 <= 512) ? 2 : 1;
-    auto smem_of = [&](int T_, int NS_) { return f16 ? tc16_smem_bytes(A.m, B.m, C.m, p.BN, T_, NS_) : tc_smem_bytes(A.m, B.m, C.m, p.BN, T_, NS_); };
+    auto smem_of = [&](int T_, int NS_) { return f16 ? tc16_smem_bytes(A.m, B.m, C.m, p.BN, T_, NS_, kc16) : tc_smem_bytes(A.m, B.m, C.m, p.BN, T_, NS_); };
     int NS = 4;
     while (NS >= 2 && smem_of(p.T, NS) > 226 * 1024) --NS;
     if (NS < 2 && p.T == 2) {
@@ -1158,7 +1166,8 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     ks = ceil_div64(p.zpitch, p.rows_per_split);
     if (f16) {
         using Kern16 = void (*)(TcParams);
-        Kern16 k16 = (p.T == 2) ? gram_tc16_kernel<2> : gram_tc16_kernel<1>;
+        Kern16 k16 = (kc16 == 64) ? ((p.T == 2) ? gram_tc16_kernel<2, 64> : gram_tc16_kernel<1, 64>)
+                                  : ((p.T == 2) ? gram_tc16_kernel<2, 32> : gram_tc16_kernel<1, 32>);
         TN_SMEM(k16, smem);
         dim3 grid16((unsigned)gx, (unsigned)gy, (unsigned)ks);
         k16<<<grid16, TC_THREADS, smem, st>>>(p);

@@ -50,11 +50,15 @@ static int op_apply(OpRun& r, const double* v, double* out) {
         }
     } else {
         const tn_factor *fa = op->fa, *fb = op->fb, *fc = op->fc;
+        rc = matvec_fused(fa, fb, fc, op->w, op->rows, v, out, r.stop, r.st);      // small cores: both passes in one launch
+        if (rc < 0) return rc;
+        if (rc == 1) {
         rc = env_update_scaled(fa->ptr, fa->ld, fa->div, fb->ptr, fb->ld, fb->map_kind, fb->m, fb->div < 1 ? 1 : fb->div, v, nullptr, 0,
                                fc->ptr, fc->ld, fc->div < 1 ? 1 : fc->div, r.t, op->w, op->rows, fa->m, fc->m, r.st);
         if (rc != TN_OK) return rc;
         rc = tn_rhs_kr3(fa, fb, fc, r.t, op->rows, out, r.rhs_work, r.ks, 0, (void*)r.st);
         if (rc != TN_OK) return rc;
+        }
     }
     if (op->allreduce && !(op->apply && op->apply_is_global)) {
         rc = op->allreduce(op->allreduce_ctx, out, op->P, (void*)r.st);

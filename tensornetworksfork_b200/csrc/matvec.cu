@@ -26,8 +26,10 @@ extern "C" int tn_matvec_kr3(const tn_factor* fa, const tn_factor* fb, const tn_
     using namespace tn;
     TN_CHECK_ARG(fa && fb && fc && v && out && work, "tn_matvec_kr3: null argument");
     TN_CHECK_ARG(fa->map_kind == TN_MAP_IDENTITY && fc->map_kind == TN_MAP_IDENTITY, "tn_matvec_kr3: only the middle factor may carry a feature map");
+    int rc = matvec_fused(fa, fb, fc, w, rows, v, out, nullptr, as_stream(stream));      // small cores: both passes in one launch
+    if (rc <= 0) return rc;
     double* t = work;
-    int rc = tn_env_update(fa->ptr, fa->ld, fa->div, fb->ptr, fb->ld, fb->map_kind, fb->m, fb->div, v, nullptr, 0, fc->ptr,
+    rc = tn_env_update(fa->ptr, fa->ld, fa->div, fb->ptr, fb->ld, fb->map_kind, fb->m, fb->div, v, nullptr, 0, fc->ptr,
                            fc->ld, fc->div, t, rows, fa->m, fc->m, stream);
     if (rc != TN_OK) return rc;
     if (w && rows > 0) {

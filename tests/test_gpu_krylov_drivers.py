@@ -195,3 +195,33 @@ def test_tensor_core_modes_are_exact_after_refinement(name, gram_mode):
     assert gu.relerr(pred.reshape(fx["pred"].shape), fx["pred"]) < 1e-7
     assert tn.solve_stats["refined"] + tn.solve_stats["gram_fp64_fallback"] == len(trace), tn.solve_stats
     assert tn.solve_stats["refined"] >= len(trace) - 1, tn.solve_stats
+
+
+@pytest.mark.parametrize("case", [(5000, 24, 2, 24, 1, "sincos"), (3001, 38, 2, 38, 10, "sincos"), (700, 3, 4, 3, 1, None), (2000, 6, 2, 6, 1, None),
+                                  (4000, 12, 3, 9, 3, None), (9000, 32, 4, 64, 1, "poly"), (300, 24, 2, 24, 1, "sincos"), (6000, 38, 6, 38, 1, "poly")])
+def test_one_launch_matvec_matches_dense(case):
+    """tn_matvec_kr3: the fused kernel (both passes on DMMA, factors read once; csrc/matvec_fused.cu) for small cores, the two-pass
+    path otherwise (few rows, wide cores) -- against the dense J^T diag(w) J v, with feature maps and class rows (row divisors)."""
+    rows, ma, mb, mc, V, fmap = case
+    g = torch.Generator().manual_seed(sum(case[:5]))
+    S = rows
+    Fa = torch.randn((S * V, ma), generator=g)
+    Fc = torch.randn((S, mc), generator=g)
+    w = torch.randn((S * V,), generator=g)
+    if fmap is None:
+        Xb = torch.rand((S, mb), generator=g) * 2 - 1
+        fb_c = Factor(Xb, m=mb, div=V)
+        fb_d = Factor(Xb.to(DEV), m=mb, div=V)
+    else:
+        X = torch.rand((S, 7), generator=g) * 2 - 1
+        kind = ops.MAP_SINCOS if fmap == "sincos" else ops.MAP_POLY
+        fb_c = Factor(X, m=mb, div=V, map_kind=kind, col=3)
+        fb_d = Factor(X.to(DEV), m=mb, div=V, map_kind=kind, col=3)
+    v = torch.randn((ma * mb * mc,), generator=g)
+    want = fake_ops.matvec(Factor(Fa, m=ma), fb_c, Factor(Fc, m=mc, div=V), w, S * V, v)
+    got = ops.matvec(Factor(Fa.to(DEV), m=ma), fb_d, Factor(Fc.to(DEV), m=mc, div=V), w.to(DEV), S * V, v.to(DEV))
+    torch.cuda.synchronize()
+    assert gu.relerr(got.cpu().numpy(), want.numpy()) < 1e-12
+    got2 = ops.matvec(Factor(Fa.to(DEV), m=ma), fb_d, Factor(Fc.to(DEV), m=mc, div=V), None, S * V, v.to(DEV))
+    want2 = fake_ops.matvec(Factor(Fa, m=ma), fb_c, Factor(Fc, m=mc, div=V), None, S * V, v)
+    assert gu.relerr(got2.cpu().numpy(), want2.numpy()) < 1e-12
