@@ -479,7 +479,9 @@ gram_tc_kernel(TcParams p) {
 // entries below 6e-5 of a factor's largest lose relative precision and entries below 6e-8 vanish.  The mode exists for the
 // sweep's exact refinement (TensorNetwork.refine = 'exact'), where the Gram is only a preconditioner; measured as one
 // (tools/precond_experiment.py): the same conjugate-gradient iteration counts as TF32 operands.
-constexpr int H_KC_DEFAULT = 32;    // samples per stage (two MMAs of K = 16); 64 is the other instantiation
+constexpr int H_KC_DEFAULT = 64;    // samples per stage (four MMAs of K = 16 per tile); measured on the config-5a middle site, 262 144
+                                    // rows: 701 TF/s against 590 with 32-sample stages (TN_TC16_KC=32), same bits -- the per-stage
+                                    // barriers, fences and bulk-copy bookkeeping are paid half as often
 
 __device__ __forceinline__ uint4 lds128u(uint32_t addr) {
     uint4 v;
@@ -1051,7 +1053,7 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     p.nC = npairs(C.m);
     const bool f16 = (mode == 3);
     int kc16 = H_KC_DEFAULT;
-    if (const char* e = getenv("TN_TC16_KC")) kc16 = (atoi(e) == 64) ? 64 : 32;
+    if (const char* e = getenv("TN_TC16_KC")) kc16 = (atoi(e) == 32) ? 32 : 64;
     const int KC = f16 ? kc16 : TC_KC;             // samples per pipeline stage
     p.split = (mode == 2) ? 1 : 0;
     p.planar = 0;

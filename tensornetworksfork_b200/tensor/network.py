@@ -160,6 +160,7 @@ class TensorNetwork:
         # fp32 accumulation window (rows) of the tensor-core Gram when it only preconditions the exact refinement: longer = faster,
         # coarser (None = the library default of 2048, the window the stand-alone accuracy figures of the Gram are quoted for)
         self.tc_flush_rows = 8192
+        self.small_site_fp64 = 2.0e9    # rows x unique Gram entries below which a site is built in fp64 outright (~0.5 ms of DMMA)
         self.process_group = None       # torch.distributed group: x, y are then this rank's row shard
         self.shard_offset = 0           # global index of this rank's first row
         self.shard_total = None         # global number of rows
@@ -657,10 +658,19 @@ class TensorNetwork:
         m = method.lower()
         return 0.0 if m in ("exact", "cholesky", "gradient") or m.startswith("gradient") else 2.0 * float(eps)
 
-    def _gram_mode_for(self, method, eps):
-        """Gram mode of one site update: the tensor-core mode, unless a ridge this small already needed the fp64 Gram."""
-        if self.gram_mode != "fp64" and self.refine == "exact" and self._ridge_of(method, eps) <= self._refine_floor:
+    def _gram_mode_for(self, method, eps, prob=None):
+        """Gram mode of one site update: the tensor-core mode, unless a ridge this small already needed the fp64 Gram, or the
+        site is so small that the fp64 Gram costs less than the refinement's factor-and-iterate overhead (config 1: 4177 rows,
+        P <= 324 -- a few launches of latency either way)."""
+        if self.gram_mode == "fp64" or self.refine != "exact":
+            return self.gram_mode
+        if self._ridge_of(method, eps) <= self._refine_floor:
             return "fp64"
+        if prob is not None and self.small_site_fp64 > 0:
+            m = prob["m_pos"]
+            work = float(prob["grows"]) * ops.npairs(m[0]) * ops.npairs(m[1]) * ops.npairs(m[2])
+            if self.process_group is None and work <= self.small_site_fp64:
+                return "fp64"
         return self.gram_mode
 
     def _solve_refined(self, theta, M, b, m_pos, role_of_pos, ridge, prob):
@@ -898,7 +908,7 @@ class TensorNetwork:
     def _one_update(self, k, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss):
         self._check_external()
         prob = self._site_problem(k, y, loss_fn)
-        M, b, role_of_pos = self._accumulate(prob, self._gram_mode_for(method, eps))
+        M, b, role_of_pos = self._accumulate(prob, self._gram_mode_for(method, eps, prob))
         try:
             step = self._solve(k, M, b, prob["m_pos"], role_of_pos, method, eps, prob=prob)
         except _NeedExactGram:
@@ -987,7 +997,7 @@ class TensorNetwork:
     def _one_linear_update(self, k, y, loss_fn, method, eps, lr, batch_size, adaptive_step, max_norm, need_loss):
         self._check_external()
         prob = self._linear_problem(k, y, loss_fn)
-        M, b, role_of_pos = self._accumulate(prob, self._gram_mode_for(method, eps))
+        M, b, role_of_pos = self._accumulate(prob, self._gram_mode_for(method, eps, prob))
         W = self._plan()[k].linear.tensor
         try:
             step = self._solve_flat(W.contiguous().view(-1), M, b, prob["m_pos"], role_of_pos, method, eps, prob=prob)

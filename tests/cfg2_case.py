@@ -32,6 +32,7 @@ def run(device, gram_mode="fp64"):
     layer.to(device)
     tn = layer.tensor_network
     tn.gram_mode = gram_mode
+    tn.small_site_fp64 = 0          # exercise the requested Gram mode even where the site is small
     trace = []
     ok = tn.accumulating_swipe(torch.tensor(X, device=device), torch.tensor(y, device=device), tnb.SquareBregFunction(), batch_size=512, lr=1.0,
                                eps=1.0, eps_decay=0.5, orthonormalize=False, method="ridge_cholesky", num_swipes=NUM_SWIPES, skip_second=False,

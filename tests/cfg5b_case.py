@@ -28,6 +28,7 @@ def run(device, max_updates=None, gram_mode="fp64"):
     layer.to(device)
     tn = layer.tensor_network
     tn.gram_mode = gram_mode
+    tn.small_site_fp64 = 0          # exercise the requested Gram mode even where the site is small
     x = tnb.MappedInput(torch.tensor(X, device=device), "polynomial", degree=DEG)
     tn.orthonormalize_left()
     trace = []

@@ -181,6 +181,7 @@ def test_tensor_core_modes_are_exact_after_refinement(name, gram_mode):
     tg.set_cores(layer, fx["cores0"])
     tn = layer.tensor_network
     tn.gram_mode = gram_mode
+    tn.small_site_fp64 = 0          # tiny fixtures: keep them on the refined path
     x, y = tg.data(fx)
     trace = []
     ok = tn.accumulating_swipe(x, y, tg.loss_of(meta), batch_size=meta["batch_size"], num_swipes=meta["num_swipes"], lr=meta["lr"],

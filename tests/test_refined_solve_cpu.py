@@ -31,6 +31,7 @@ def test_refined_solve_follows_the_reference_recording(name, monkeypatch):
     layer = hs.build(fx)
     tn = layer.tensor_network
     tn.gram_mode = "tf32x3"
+    tn.small_site_fp64 = 0          # these fixtures are tiny: keep them on the refined path they are here to exercise
     x, y = _data(fx)
     ok, trace = hs.run(fx, layer, x, y)
     assert ok == fx["ok"]
@@ -62,6 +63,7 @@ def test_a_coarse_gram_is_only_a_preconditioner(monkeypatch):
     layer = hs.build(fx)
     tn = layer.tensor_network
     tn.gram_mode = "tf32x3"
+    tn.small_site_fp64 = 0          # these fixtures are tiny: keep them on the refined path they are here to exercise
     ok, trace = hs.run(fx, layer, x, y)
     assert ok and tn.solve_stats["gram_fp64_fallback"] == 0
     assert tn.solve_stats["refine_iters"] > 0          # the perturbed factor is not exact, so the iteration had work to do
@@ -78,6 +80,7 @@ def test_refinement_failure_falls_back_to_the_fp64_gram_and_remembers(monkeypatc
     layer = hs.build(fx)
     tn = layer.tensor_network
     tn.gram_mode = "tf32x3"
+    tn.small_site_fp64 = 0          # these fixtures are tiny: keep them on the refined path they are here to exercise
     tn.refine_accept = -1.0             # never accept: every site must be redone with the fp64 Gram
     ok, trace = hs.run(fx, layer, x, y)
     assert ok
@@ -102,6 +105,7 @@ def _worker(rank, world, port, name, out_dir):
     layer = hs.build(fx)
     tn = layer.tensor_network
     tn.gram_mode = "tf32x3"
+    tn.small_site_fp64 = 0          # these fixtures are tiny: keep them on the refined path they are here to exercise
     N = fx["y"].shape[0]
     cut = [0, N // 2 + 7, N][rank:rank + 2]
     sl = slice(cut[0], cut[1])
