@@ -152,7 +152,7 @@ env_dmma_kernel(const double* __restrict__ env_in, int64_t env_ld, int env_div, 
                 int map_kind, int f, int cdiv, const double* __restrict__ core, double* __restrict__ out,
                 int64_t out_ld, const double* __restrict__ dot, int64_t dot_ld, int dot_div,
                 double* __restrict__ yhat, const double* __restrict__ yscale, int64_t rows, int r_in, int r_out) {
-    constexpr int LDG = NT * 8 + 8;                  // core slab row stride: == 8 (mod 16) doubles, conflict-free B fragments
+    constexpr int LDG = NT * 8 + 4;                  // core slab row stride == 4 (mod 8) doubles: the 16 lanes of a half warp (fr 0..3 x fk 0..3) read fk * LDG + fr from 16 distinct 8-byte banks (NT * 8 + 8 gave 2- and 4-way conflicts: profiles/r2_ncu_env_warp.txt)
     extern __shared__ double sm[];
     const int in_st = (r_in + 5) | 1;                // + zero columns read by the padded tail of K
     const int phi_st = f | 1;
@@ -264,7 +264,7 @@ env_dmma_persist_kernel(const double* __restrict__ env_in, int64_t env_ld, int e
                         int map_kind, int f, int cdiv, const double* __restrict__ core, double* __restrict__ out,
                         int64_t out_ld, const double* __restrict__ dot, int64_t dot_ld, int dot_div,
                         double* __restrict__ yhat, const double* __restrict__ yscale, int64_t rows, int r_in, int r_out, int64_t ntiles) {
-    constexpr int LDG = NT * 8 + 8;
+    constexpr int LDG = NT * 8 + 4;
     extern __shared__ double sm[];
     const int in_st = (r_in + 5) | 1;
     const int phi_st = f | 1;
@@ -383,16 +383,236 @@ env_dmma_persist_kernel(const double* __restrict__ env_in, int64_t env_ld, int e
     asm volatile("cp.async.wait_group 0;" ::: "memory");
 }
 
+// ---- warp-per-tile variant: every warp owns 16-row tiles and its own double-buffered pipeline, no block barrier in the loop.
+//      The environment rows of a tile are one contiguous byte range (sample-major layout), so one elected lane fetches them with
+//      a bulk copy (cp.async.bulk, the 1-D TMA path: UBLKCP) that completes on the warp's mbarrier; the raw site inputs (one or
+//      f strided values per row) come by cp.async; the result tile goes back through shared memory as one bulk store.  The core
+//      stays resident as the B operand.  With ~20 such independent pipelines per SM the FP64 tensor pipe and the HBM stream
+//      overlap instead of alternating between the three block barriers per 128-row tile of the kernel above.
+//      Preconditions (checked by the launcher): env rows dense (env_ld == r_in, env_div == 1, 16-byte aligned), r_in * 16 * 8 bytes
+//      a multiple of 16 (always), the whole core in shared memory.
+constexpr int EW_TR = 16;          // rows per warp tile
+constexpr int EW_WARPS = 8;
+
+__device__ __forceinline__ void ew_mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(count));
+}
+__device__ __forceinline__ bool ew_mbar_try(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.b32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"((uint32_t)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void ew_mbar_wait(uint64_t* bar, uint32_t parity) {
+    for (uint32_t it = 0; it < (1u << 26); ++it)
+        if (ew_mbar_try(bar, parity)) return;
+    __trap();      // a protocol bug traps instead of hanging the GPU
+}
+
+template <int NT>
+__global__ void __launch_bounds__(EW_WARPS * 32, 2)
+env_warp_kernel(const double* __restrict__ env_in, int64_t env_ld, const double* __restrict__ x, int64_t x_ld, int map_kind, int f, int cdiv,
+                const double* __restrict__ core, double* __restrict__ out, int64_t out_ld, const double* __restrict__ dot, int64_t dot_ld,
+                int dot_div, double* __restrict__ yhat, const double* __restrict__ yscale, int64_t rows, int r_in, int r_out,
+                int64_t ntiles) {
+    constexpr int LDG = NT * 8 + 4;
+    extern __shared__ __align__(128) double sm[];
+    const int phi_st = f | 1;
+    const int K = r_in * f;
+    const int Kp = (K + 3) & ~3;
+    const int xraw = (map_kind == TN_MAP_IDENTITY) ? f : 1;
+    const int in_st = r_in + ((12 - (r_in & 7)) & 7);         // row stride == 4 (mod 8) doubles: the A fragments of a half warp (4 rows x 2..4 k) hit distinct banks
+    const int in_elems = EW_TR * in_st + 8;                   // padded tile (pad words stay zero: the padded tail of K reads them)
+    const int out_st = NT * 8;                                // staging row stride when the result is not stored densely
+    // per-warp region (doubles): [2][in_elems] [2][EW_TR * xraw] [EW_TR * phi_st] [EW_TR * out_st] + 2 barriers, rounded to 16 B
+    const int per_warp = (2 * in_elems + 2 * EW_TR * xraw + EW_TR * phi_st + EW_TR * out_st + 2 + 1) & ~1;
+    double* s_g = sm;                                         // [Kp][LDG] resident core
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double* wbase = s_g + (((size_t)Kp * LDG + 1) & ~(size_t)1) + (size_t)warp * per_warp;
+    double* s_in = wbase;
+    double* s_x = s_in + 2 * in_elems;
+    double* s_phi = s_x + 2 * EW_TR * xraw;
+    double* s_out = s_phi + EW_TR * phi_st;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_out + EW_TR * out_st);
+
+    for (int idx = tid; idx < Kp * (NT * 8); idx += EW_WARPS * 32) {
+        const int k = idx / (NT * 8), n = idx - k * (NT * 8);
+        s_g[k * LDG + n] = (k < K && n < r_out) ? core[(int64_t)k * r_out + n] : 0.0;
+    }
+    for (int i = lane; i < 2 * in_elems; i += 32) s_in[i] = (env_in == nullptr && (i % in_elems) % in_st == 0 && (i % in_elems) < EW_TR * in_st) ? 1.0 : 0.0;
+    if (lane == 0) {
+        ew_mbar_init(&bars[0], 1);
+        ew_mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();                   // core resident, barriers initialised (the only block barrier of the kernel)
+
+    const int64_t nwarps = (int64_t)gridDim.x * EW_WARPS;
+    const bool dense_out = (dot == nullptr) && (out_ld == r_out);
+    auto prefetch = [&](int64_t tile, int buf) {
+        if (tile < ntiles) {
+            const int64_t row0 = tile * EW_TR;
+            const int nrow = (int)((rows - row0 < EW_TR) ? rows - row0 : EW_TR);
+            if (env_in) {
+                // one bulk copy per row (lane = row) into the padded tile; lane 0 announces the tile's bytes first
+                const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&bars[buf]);
+                if (lane == 0) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(nrow * r_in) * 8u) : "memory");
+                __syncwarp();
+                if (lane < nrow)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"((uint32_t)__cvta_generic_to_shared(s_in + (size_t)buf * in_elems + (size_t)lane * in_st)),
+                                   "l"(env_in + (row0 + lane) * env_ld), "r"((uint32_t)r_in * 8u), "r"(bar) : "memory");
+            }
+            double* dx = s_x + (size_t)buf * EW_TR * xraw;
+            for (int idx = lane; idx < EW_TR * xraw; idx += 32) {
+                const int r = idx / xraw, q = idx - r * xraw;
+                int64_t row = row0 + r;
+                if (row >= rows) row = rows - 1;                      // clamped rows are never stored
+                cp_async8(dx + idx, x + (cdiv == 1 ? row : row / cdiv) * x_ld + q);
+            }
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+
+    const int fr = lane >> 2, fk = lane & 3;
+    const int da = 4 / f, dp = 4 - da * f;
+    int64_t tile = (int64_t)blockIdx.x * EW_WARPS + warp;
+    int buf = 0;
+    uint32_t phase[2] = {0u, 0u};
+    prefetch(tile, 0);
+    for (; tile < ntiles; tile += nwarps, buf ^= 1) {
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        if (env_in) {
+            ew_mbar_wait(&bars[buf], phase[buf]);
+            phase[buf] ^= 1u;
+        }
+        __syncwarp();
+        if (dense_out) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");      // the previous bulk store has left s_out
+        prefetch(tile + nwarps, buf ^ 1);
+        const int64_t row0 = tile * EW_TR;
+        const double* xin = s_x + (size_t)buf * EW_TR * xraw;
+        if (map_kind == TN_MAP_SINCOS) {
+            if (lane < EW_TR) {
+                double c, sn;
+                sincos((0.5 * 3.14159265358979323846) * xin[lane], &sn, &c);
+                s_phi[lane * phi_st] = c;
+                s_phi[lane * phi_st + 1] = sn;
+            }
+        } else {
+            for (int idx = lane; idx < EW_TR * f; idx += 32) {
+                const int r = idx / f, p = idx - r * f;
+                s_phi[r * phi_st + p] = map_eval(map_kind, xin + r * xraw, p);
+            }
+        }
+        __syncwarp();
+        double acc[2][NT][2];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+            for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        int ka = fk / f, kp = fk - ka * f;
+        const double* in0 = s_in + (size_t)buf * in_elems + fr * in_st;      // a tail k reads past the row: multiplied by a zero row of the core
+        const double* in1 = in0 + 8 * in_st;
+        const double* ph0 = s_phi + fr * phi_st;
+        const double* ph1 = ph0 + 8 * phi_st;
+#pragma unroll 4
+        for (int kk = 0; kk < Kp; kk += 4) {
+            const int kpc = (kp < f) ? kp : 0;
+            const double a0 = in0[ka] * ph0[kpc];
+            const double a1 = in1[ka] * ph1[kpc];
+            kp += dp; ka += da;
+            if (kp >= f) { kp -= f; ++ka; }
+            const double* gp = s_g + (kk + fk) * LDG + fr;
+#pragma unroll
+            for (int j = 0; j < NT; ++j) {
+                const double b = gp[j * 8];
+                dmma884(acc[0][j][0], acc[0][j][1], a0, b);
+                dmma884(acc[1][j][0], acc[1][j][1], a1, b);
+            }
+        }
+        // epilogue: this lane owns rows fr and fr + 8 of the tile, columns j*8 + 2*fk + {0,1}
+        if (dot) {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int64_t row = row0 + i * 8 + fr;
+                double yd = 0.0;
+                if (row < rows) {
+#pragma unroll
+                    for (int j = 0; j < NT; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int b = j * 8 + 2 * fk + e;
+                            if (b < r_out) yd = fma(acc[i][j][e], dot[(dot_div == 1 ? row : row / dot_div) * dot_ld + b], yd);
+                        }
+                }
+                yd += __shfl_xor_sync(0xffffffffu, yd, 1);
+                yd += __shfl_xor_sync(0xffffffffu, yd, 2);
+                if (fk == 0 && row < rows) yhat[row] = yscale ? yd * yscale[row] : yd;
+            }
+        } else if (dense_out) {
+            // stage the 16 x r_out tile densely and hand it to the bulk-copy engine as one store
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < NT; ++j) {
+                    const int b = j * 8 + 2 * fk;                  // r_out is even on this path: the pair (b, b + 1) is inside or outside together
+                    if (b < r_out) *reinterpret_cast<double2*>(s_out + (i * 8 + fr) * r_out + b) = make_double2(acc[i][j][0], acc[i][j][1]);
+                }
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                const int nrow = (int)((rows - row0 < EW_TR) ? rows - row0 : EW_TR);
+                asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                             ::"l"(out + row0 * r_out), "r"((uint32_t)__cvta_generic_to_shared(s_out)), "r"((uint32_t)(nrow * r_out) * 8u) : "memory");
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int64_t row = row0 + i * 8 + fr;
+                if (row < rows) {
+#pragma unroll
+                    for (int j = 0; j < NT; ++j)
+#pragma unroll
+                        for (int e = 0; e < 2; ++e) {
+                            const int b = j * 8 + 2 * fk + e;
+                            if (b < r_out) out[row * out_ld + b] = acc[i][j][e];
+                        }
+                }
+            }
+        }
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    if (dense_out) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 template <int NT>
 static int launch_env_dmma(const double* env_in, int64_t env_ld, int env_div, const double* x, int64_t x_ld, int map_kind, int f,
                            int cdiv, const double* core, double* out, int64_t out_ld, const double* dot, int64_t dot_ld,
                            int dot_div, double* yhat, const double* yscale, int64_t rows, int r_in, int r_out, cudaStream_t st) {
+    {   // warp-per-tile kernel with bulk-copy (TMA) staging: dense environment rows, the whole core resident
+        const int K = r_in * f, Kp = (K + 3) & ~3, xraw = (map_kind == TN_MAP_IDENTITY) ? f : 1;
+        const int in_elems = EW_TR * (r_in + ((12 - (r_in & 7)) & 7)) + 8;
+        const int per_warp = (2 * in_elems + 2 * EW_TR * xraw + EW_TR * (f | 1) + EW_TR * NT * 8 + 2 + 1) & ~1;
+        const size_t wsmem = ((((size_t)Kp * (NT * 8 + 4) + 1) & ~(size_t)1) + (size_t)EW_WARPS * per_warp) * sizeof(double);
+        const bool dense_in = (env_in == nullptr) || (env_div == 1 && env_ld % 2 == 0 && (reinterpret_cast<uintptr_t>(env_in) & 15) == 0 && (r_in % 2 == 0));   // every row is a 16-byte aligned bulk copy
+        const bool out_ok = dot != nullptr || out_ld != r_out || ((reinterpret_cast<uintptr_t>(out) & 15) == 0 && (r_out % 2 == 0));
+        const int64_t wtiles = ceil_div64(rows, EW_TR);
+        if (dense_in && out_ok && wsmem <= 220 * 1024 && wtiles >= 8LL * EW_WARPS * sm_count() && !getenv("TN_ENV_NO_WARP")) {
+            TN_SMEM(env_warp_kernel<NT>, wsmem);
+            int64_t grid = (wsmem <= 110 * 1024 ? 2LL : 1LL) * sm_count();      // two CTAs (16 warp pipelines) per SM when they fit
+            env_warp_kernel<NT><<<(unsigned)grid, EW_WARPS * 32, wsmem, st>>>(env_in, env_ld, x, x_ld, map_kind, f, cdiv, core, out, out_ld, dot, dot_ld,
+                                                                         dot_div, yhat, yscale, rows, r_in, r_out, wtiles);
+            TN_LAUNCH_CHECK();
+            return TN_OK;
+        }
+    }
     {   // persistent pipelined kernel when the whole core slab stays resident
         const int K = r_in * f, Kp = (K + 3) & ~3, xraw = (map_kind == TN_MAP_IDENTITY) ? f : 1;
-        const size_t psmem = ((size_t)Kp * (NT * 8 + 8) + 2 * (size_t)ED_TR * ((r_in + 5) | 1) + 2 * (size_t)ED_TR * xraw +
+        const size_t psmem = ((size_t)Kp * (NT * 8 + 4) + 2 * (size_t)ED_TR * ((r_in + 5) | 1) + 2 * (size_t)ED_TR * xraw +
                               (size_t)ED_TR * (f | 1)) * sizeof(double);
         const int64_t ntiles = ceil_div64(rows, ED_TR);
-        if ((size_t)Kp * (NT * 8 + 8) * sizeof(double) <= 48 * 1024 && psmem <= 113 * 1024 && ntiles >= 4LL * sm_count() &&
+        if ((size_t)Kp * (NT * 8 + 4) * sizeof(double) <= 48 * 1024 && psmem <= 113 * 1024 && ntiles >= 4LL * sm_count() &&
             !getenv("TN_ENV_NO_PERSIST")) {
             TN_SMEM(env_dmma_persist_kernel<NT>, psmem);
             int64_t grid = 2LL * sm_count();
@@ -404,7 +624,7 @@ static int launch_env_dmma(const double* env_in, int64_t env_ld, int env_div, co
             return TN_OK;
         }
     }
-    const size_t smem = ((size_t)ED_TR * ((r_in + 5) | 1) + (size_t)ED_TR * (f | 1) + (size_t)ED_KC * (NT * 8 + 8)) * sizeof(double);
+    const size_t smem = ((size_t)ED_TR * ((r_in + 5) | 1) + (size_t)ED_TR * (f | 1) + (size_t)ED_KC * (NT * 8 + 4)) * sizeof(double);
     if (smem > 113 * 1024) return 1;   // would not leave room for two CTAs per SM: let the caller use the FMA kernel
     TN_SMEM(env_dmma_kernel<NT>, smem);
     const int64_t grid = ceil_div64(rows, ED_TR);

@@ -734,6 +734,273 @@ gram_tc16_kernel(TcParams p) {
     }
 }
 
+// ---- fp16 kernel, run-ordered producers (T = 2 U tiles, 64-sample stages).
+// The capture of gram_tc16_kernel (profiles/r2_ncu_gram_tc16_v1.txt) shows the shared-memory data pipe 73 % busy at 27 % tensor
+// activity: per 64-sample stage 1409 wavefronts of producer loads, 598 of producer stores, 768 of tensor-core operand fetch.  The
+// loads are the part that can shrink: a U entry is w fa[ia] fa[ja] fb[ib] * fb[jb], and along consecutive rows of a tile only jb
+// changes (runs of mB - ib rows share the first three factors); a V entry is fc[ic] * fc[jc] with runs of mC - ic.  Here a producer
+// thread owns ONE 16-byte piece (8 samples) of EIGHT consecutive tile rows (= one 8-row core matrix of the UMMA layout) instead
+// of all pieces of one row: it builds the (at most two, else a slow path reloads per row) run prefixes of its rows once per stage
+// and then spends one LDS.128, four HMUL2 and one STS.128 per tile piece -- 24 loads per thread and stage instead of 48.
+// Bank conflicts: the 8 lanes of a quarter warp own 8 different core matrices (128 B apart, i.e. the same banks), so lane l walks
+// its rows in the rotated order (i + l) % 8: the eight 16-byte stores of an instruction then fall into eight different bank
+// groups, and so do the eight fb[jb] / fc[jc] loads inside a run (row indices 8 l + (i + l) % 8 are distinct modulo 8).
+struct RunRows {            // per thread: its eight rows in processing order
+    uint32_t key[8];        // the three prefix rows of a U row (10 bits each) / the fc[ic] row of a V row
+    uint32_t last[8];       // the row of the last factor (fb[jb] / fc[jc])
+    uint32_t keyA, keyB;    // the (at most) two distinct prefixes handled without reloading
+    uint32_t selB;          // bit i: row i uses prefix B
+    uint32_t slow;          // bit i: row i has a third prefix: reload it in the loop
+};
+__device__ __forceinline__ void run_rows_finish(RunRows& r) {
+    r.keyA = r.key[0];
+    r.keyB = r.key[0];
+    r.selB = 0u;
+    r.slow = 0u;
+#pragma unroll
+    for (int i = 1; i < 8; ++i) {
+        if (r.key[i] != r.keyA && r.keyB == r.keyA) r.keyB = r.key[i];
+        if (r.key[i] != r.keyA) {
+            if (r.key[i] == r.keyB) r.selB |= 1u << i;
+            else r.slow |= 1u << i;
+        }
+    }
+}
+__device__ __forceinline__ uint4 sel8(bool b, uint4 x, uint4 y) { return b ? x : y; }
+
+__global__ void __launch_bounds__(TC_THREADS, 1)
+gram_tc16_run_kernel(TcParams p) {
+    constexpr int T = 2, H_KC = 64, H_NP = 8;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int BN = p.BN, NS = p.nstages;
+    const int mA = p.mA, mB = p.mB, mC = p.mC;
+
+    constexpr uint32_t a_tile_bytes = TC_M * H_KC * 2;
+    const uint32_t b_tile_bytes = (uint32_t)BN * H_KC * 2;
+    const uint32_t stage_bytes = T * a_tile_bytes + b_tile_bytes;
+    const uint32_t z_rows = (uint32_t)(2 * mA + mB + mC);
+    const uint32_t raw_rows = z_rows + 1;
+    const uint32_t plane_stride = ((raw_rows * 16 + 95) / 128) * 128 + 32;
+    const uint32_t raw_bytes = H_NP * plane_stride;
+    uint8_t* stage_base = smem_raw;
+    uint8_t* raw_base = smem_raw + (size_t)NS * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)TC_RAW_SLOTS * raw_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NS;
+    uint64_t* acc_full = bars + 2 * NS;
+    uint64_t* acc_empty = bars + 2 * NS + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
+    uint64_t* raw_full = bars + 2 * NS + 3;
+
+    const uint32_t tmem_cols_needed = (uint32_t)(T * BN);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], TC_PROD_WARPS);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, TC_PROD_WARPS);
+        for (int i = 0; i < TC_RAW_SLOTS; ++i) mbar_init(&raw_full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < TC_RAW_SLOTS * H_NP * 4; i += TC_THREADS) {
+        const int slot = i / (H_NP * 4), e = i % (H_NP * 4);
+        reinterpret_cast<uint32_t*>(raw_base + (size_t)slot * raw_bytes + (size_t)(e >> 2) * plane_stride + (size_t)z_rows * 16)[e & 3] = 0u;
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t k_begin = (int64_t)blockIdx.z * p.rows_per_split;
+    const int64_t k_end = min(p.zpitch, k_begin + p.rows_per_split);
+    const int64_t nchunks = (k_end > k_begin) ? (k_end - k_begin) / H_KC : 0;
+    const int64_t chunks_per_flush = p.flush_rows / H_KC;
+    const int64_t nU = (int64_t)p.nA * p.nB;
+    const int64_t u0 = (int64_t)blockIdx.x * (TC_M * T);
+    const int v0 = blockIdx.y * BN;
+
+    if (warp == 0) {
+        // =============================== MMA issuer (as in gram_tc16_kernel) ===============================
+        if (lane == 0 && nchunks > 0) {
+            const uint32_t idesc = make_idesc_f16(TC_M, BN);
+            const uint32_t lbo_a = TC_M * 16, lbo_b = (uint32_t)BN * 16, sbo = 128;
+            uint32_t acc_phase = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            int64_t in_window = 0;
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const bool first_of_window = in_window == 0;
+                if (first_of_window && c > 0) {
+                    mbar_wait(acc_empty, acc_phase);
+                    acc_phase ^= 1;
+                    tc_fence_after();
+                }
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(stage_base + (size_t)s * stage_bytes);
+                const uint32_t b_base = sb + T * a_tile_bytes;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    const uint32_t a_base = sb + (uint32_t)t * a_tile_bytes;
+                    const uint32_t d = tmem_base + (uint32_t)(t * BN);
+#pragma unroll
+                    for (int j = 0; j < H_KC / 16; ++j) {
+                        const uint32_t ao = (uint32_t)(2 * j) * lbo_a, bo = (uint32_t)(2 * j) * lbo_b;
+                        const uint32_t acc0 = (first_of_window && j == 0) ? 0u : 1u;
+                        umma_f16(d, make_desc(a_base + ao, lbo_a, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
+                    }
+                }
+                umma_commit(&empty[s]);
+                const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+                if (last_of_window) {
+                    umma_commit(acc_full);
+                    in_window = 0;
+                }
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // =============================== producers / epilogue ===============================
+        const int pt = tid - 32;              // 0..255
+        const int pc = pt >> 5;               // this warp's piece of the stage (8 samples)
+        const int grp = lane;                 // this lane's 8-row core matrix: U rows 8 grp .. 8 grp + 7 of the CTA's 256, V rows likewise
+        const int rot = lane & 7;
+        const double unscale = ldexp(1.0, 2 * (tc_exponent(p.amax[0]) + tc_exponent(p.amax[1]) + tc_exponent(p.amax[2])) +
+                                              tc_exponent(p.amax[3]));
+        const uint32_t raw_s = smem_u32(raw_base);
+        RunRows ur, vr;
+        const bool v_active = 8 * grp < BN;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int j = (i + rot) & 7;
+            const int64_t gu = u0 + 8 * grp + j;
+            uint32_t key = z_rows | (z_rows << 10) | (z_rows << 20), last = z_rows;      // the zero row
+            if (gu < nU) {
+                const int qa = (int)(gu / p.nB), qb = (int)(gu - (int64_t)qa * p.nB);
+                int ia, ja, ib, jb;
+                pair_decode(qa, mA, ia, ja);
+                pair_decode(qb, mB, ib, jb);
+                key = (uint32_t)ia | ((uint32_t)(mA + ja) << 10) | ((uint32_t)(2 * mA + ib) << 20);
+                last = (uint32_t)(2 * mA + jb);
+            }
+            ur.key[i] = key;
+            ur.last[i] = last * 16u;
+            const int gv = v0 + 8 * grp + j;
+            uint32_t vkey = z_rows, vlast = z_rows;
+            if (v_active && gv < p.nC) {
+                int ic, jc;
+                pair_decode(gv, mC, ic, jc);
+                vkey = (uint32_t)(2 * mA + mB + ic);
+                vlast = (uint32_t)(2 * mA + mB + jc);
+            }
+            vr.key[i] = vkey;
+            vr.last[i] = vlast * 16u;
+        }
+        run_rows_finish(ur);
+        run_rows_finish(vr);
+        // destinations: tile (8 grp) / 128, row (8 grp) % 128 + j; piece pc
+        const uint32_t udst = (uint32_t)(grp >> 4) * a_tile_bytes + (uint32_t)pc * (TC_M * 16) + (uint32_t)((8 * grp) & 127) * 16;
+        const uint32_t lbo_b = (uint32_t)BN * 16;
+        const uint32_t vdst = T * a_tile_bytes + (uint32_t)pc * lbo_b + (uint32_t)(8 * grp) * 16;
+        const uint32_t stage_s = smem_u32(stage_base);
+        const __half* Zh = reinterpret_cast<const __half*>(p.Z);
+
+        auto issue_chunk = [&](int64_t chunk) {
+            if (chunk < nchunks && pt == 0) {
+                const int slot = (int)(chunk % TC_RAW_SLOTS);
+                const uint32_t bar = smem_u32(&raw_full[slot]);
+                const uint32_t plane_bytes = z_rows * 16;
+                const uint32_t dst0 = raw_s + (uint32_t)slot * raw_bytes;
+                const __half* src0 = Zh + ((k_begin / H_KC + chunk) * H_NP) * (int64_t)z_rows * 8;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(H_NP * plane_bytes) : "memory");
+#pragma unroll
+                for (int part = 0; part < H_NP; ++part)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst0 + (uint32_t)part * plane_stride), "l"(src0 + (int64_t)part * z_rows * 8), "r"(plane_bytes), "r"(bar)
+                                 : "memory");
+            }
+        };
+        issue_chunk(0);
+        issue_chunk(1);
+
+        auto u_prefix = [&](uint32_t rbp, uint32_t key) -> uint4 {
+            const uint4 a = lds128u(rbp + (key & 1023u) * 16u);
+            const uint4 b = lds128u(rbp + ((key >> 10) & 1023u) * 16u);
+            const uint4 c = lds128u(rbp + (key >> 20) * 16u);
+            return hmul8(hmul8(a, b), c);
+        };
+
+        uint32_t acc_phase = 0;
+        int s = 0, rs = 0;
+        uint32_t ph = 0;
+        int64_t in_window = 0;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");
+            issue_chunk(c + 2);
+            mbar_wait(&raw_full[rs], (uint32_t)((c / TC_RAW_SLOTS) & 1));
+            if (lane == 0) mbar_wait(&empty[s], ph ^ 1);
+            __syncwarp();
+            const uint32_t rbp = raw_s + (uint32_t)rs * raw_bytes + (uint32_t)pc * plane_stride;     // this warp's plane of the slot
+            const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
+            {   // ---- U: prefixes, then eight rows
+                const uint4 preA = u_prefix(rbp, ur.keyA);
+                const uint4 preB = u_prefix(rbp, ur.keyB);
+                uint4 x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = lds128u(rbp + ur.last[i]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint4 pre = sel8((ur.selB >> i) & 1u, preB, preA);
+                    if ((ur.slow >> i) & 1u) pre = u_prefix(rbp, ur.key[i]);
+                    sts128u(sb + udst + (uint32_t)((i + rot) & 7) * 16u, hmul8(pre, x[i]));
+                }
+            }
+            if (v_active) {   // ---- V
+                const uint4 preA = lds128u(rbp + vr.keyA * 16u);
+                const uint4 preB = lds128u(rbp + vr.keyB * 16u);
+                uint4 y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] = lds128u(rbp + vr.last[i]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint4 pre = sel8((vr.selB >> i) & 1u, preB, preA);
+                    if ((vr.slow >> i) & 1u) pre = lds128u(rbp + vr.key[i] * 16u);
+                    sts128u(sb + vdst + (uint32_t)((i + rot) & 7) * 16u, hmul8(pre, y[i]));
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+            if (++s == NS) { s = 0; ph ^= 1; }
+            if (++rs == TC_RAW_SLOTS) rs = 0;
+            const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+            if (last_of_window) {
+                in_window = 0;
+                mbar_wait(acc_full, acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, reinterpret_cast<float*>(stage_base), unscale, TC_M, (c + 1) == nchunks);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
 static size_t tc16_smem_bytes(int mA, int mB, int mC, int BN, int T, int NS, int kc) {
     const size_t stage = (size_t)T * TC_M * kc * 2 + (size_t)BN * kc * 2;
     const size_t plane = (((size_t)(2 * mA + mB + mC + 1) * 16 + 95) / 128) * 128 + 32;
@@ -1012,6 +1279,245 @@ gram_tc_pair_kernel(TcParams p) {
     }
 }
 
+// ---- CTA-pair variant of the FP16 kernel (cta_group::2, kind::f16, M = 256 x N = 256 per MMA).  The fp16 kernel is bound by what
+// its producers and the tensor core move through shared memory, not by the tensor pipe (it runs at about half of the 16-bit MMA
+// rate), so -- unlike in 3xTF32, where the pair kernel above lost 5 % -- sharing every MMA between the two SMs of a TPC pays:
+// per SM and stage the producers synthesise 256 U rows + 128 V rows instead of 256 + 256, and the tensor core fetches 8 KB
+// instead of 12 KB of operands per K = 16 step.  Raw factors arrive as in gram_tc16_kernel (planes of eight fp16 samples, bulk
+// copies on an mbarrier, each CTA fills its own ring); the V rows are split over all eight producer warps (row = thread % 128,
+// half of the stage's pieces each) so that no warp idles.  Barriers as in gram_tc_pair_kernel.
+__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+template <int H_KC>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
+gram_tc16_pair_kernel(TcParams p) {
+    constexpr int H_NP = H_KC / 8;      // 16-byte pieces (8 samples) of a row per stage
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int NS = p.nstages;
+    const int mA = p.mA, mB = p.mB, mC = p.mC;
+    const uint32_t rank = cluster_rank();
+
+    constexpr uint32_t a_tile_bytes = TC_M * H_KC * 2;         // this CTA's 128 rows of one M = 256 U tile, one stage
+    constexpr uint32_t b_tile_bytes = TP_BH * H_KC * 2;        // this CTA's half of the V tile
+    constexpr uint32_t stage_bytes = TP_T * a_tile_bytes + b_tile_bytes;
+    const uint32_t z_rows = (uint32_t)(2 * mA + mB + mC);
+    const uint32_t raw_rows = z_rows + 1;
+    const uint32_t plane_stride = ((raw_rows * 16 + 95) / 128) * 128 + 32;
+    const uint32_t raw_bytes = H_NP * plane_stride;
+    uint8_t* stage_base = smem_raw;
+    uint8_t* raw_base = smem_raw + (size_t)NS * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)TC_RAW_SLOTS * raw_bytes);
+    uint64_t* full = bars;              // [NS]  used in the leader: producers of both CTAs -> MMA
+    uint64_t* empty = bars + NS;        // [NS]  per CTA: multicast tcgen05.commit -> producers
+    uint64_t* acc_full = bars + 2 * NS;     // per CTA (multicast commit)
+    uint64_t* acc_empty = bars + 2 * NS + 1;   // used in the leader: drainers of both CTAs -> MMA
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
+    uint64_t* raw_full = bars + 2 * NS + 3;      // [TC_RAW_SLOTS] per CTA
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], 2 * TC_PROD_WARPS);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, 2 * TC_PROD_WARPS);
+        for (int i = 0; i < TC_RAW_SLOTS; ++i) mbar_init(&raw_full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < TC_RAW_SLOTS * H_NP * 4; i += TC_THREADS) {      // the zero row of every plane of every slot (16 B each)
+        const int slot = i / (H_NP * 4), e = i % (H_NP * 4);
+        reinterpret_cast<uint32_t*>(raw_base + (size_t)slot * raw_bytes + (size_t)(e >> 2) * plane_stride + (size_t)z_rows * 16)[e & 3] = 0u;
+    }
+    cluster_sync_all();                  // barrier inits visible to the peer before anything arrives remotely
+    if (warp == 0) tmem_alloc2(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t k_begin = (int64_t)blockIdx.z * p.rows_per_split;
+    const int64_t k_end = min(p.zpitch, k_begin + p.rows_per_split);
+    const int64_t nchunks = (k_end > k_begin) ? (k_end - k_begin) / H_KC : 0;
+    const int64_t chunks_per_flush = p.flush_rows / H_KC;
+    const int64_t nU = (int64_t)p.nA * p.nB;
+    const int64_t u0_pair = (int64_t)(blockIdx.x >> 1) * (2 * TC_M * TP_T);     // 512 U rows per pair
+    const int v0 = blockIdx.y * TP_BN;
+
+    if (warp == 0) {
+        // =============================== MMA issuer (leader CTA only) ===============================
+        if (rank == 0 && lane == 0 && nchunks > 0) {
+            const uint32_t idesc = make_idesc_f16(2 * TC_M, TP_BN);
+            constexpr uint32_t lbo_a = TC_M * 16, lbo_b = TP_BH * 16, sbo = 128;
+            uint32_t acc_phase = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            int64_t in_window = 0;
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const bool first_of_window = in_window == 0;
+                if (first_of_window && c > 0) {
+                    mbar_wait_cluster(acc_empty, acc_phase);
+                    acc_phase ^= 1;
+                    tc_fence_after();
+                }
+                mbar_wait_cluster(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(stage_base + (size_t)s * stage_bytes);
+                const uint32_t b_base = sb + TP_T * a_tile_bytes;
+#pragma unroll
+                for (int t = 0; t < TP_T; ++t) {
+                    const uint32_t a_base = sb + (uint32_t)t * a_tile_bytes;
+                    const uint32_t d = tmem_base + (uint32_t)(t * TP_BN);
+#pragma unroll
+                    for (int j = 0; j < H_KC / 16; ++j) {          // one MMA = 16 samples = two 16-byte pieces
+                        const uint32_t ao = (uint32_t)(2 * j) * lbo_a, bo = (uint32_t)(2 * j) * lbo_b;
+                        const uint32_t acc0 = (first_of_window && j == 0) ? 0u : 1u;
+                        umma2_f16(d, make_desc(a_base + ao, lbo_a, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
+                    }
+                }
+                umma_commit2(&empty[s]);
+                const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+                if (last_of_window) {
+                    umma_commit2(acc_full);
+                    in_window = 0;
+                }
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // =============================== producers / epilogue (both CTAs) ===============================
+        const int pt = tid - 32;
+        const double unscale = ldexp(1.0, 2 * (tc_exponent(p.amax[0]) + tc_exponent(p.amax[1]) + tc_exponent(p.amax[2])) +
+                                              tc_exponent(p.amax[3]));
+        const uint32_t raw_s = smem_u32(raw_base);
+        const uint32_t zero_row = z_rows * 16;
+        uint32_t usrc[4] = {zero_row, zero_row, zero_row, zero_row};
+        const int u_tile = pt >> 7, u_row = pt & 127;
+        const int64_t u0_cta = u0_pair + (int64_t)rank * TC_M;        // tile t of this CTA covers rows u0_cta + t*256 + [0, 128)
+        {
+            const int64_t gu = u0_cta + (int64_t)u_tile * (2 * TC_M) + u_row;
+            if (gu < nU) {
+                const int qa = (int)(gu / p.nB), qb = (int)(gu - (int64_t)qa * p.nB);
+                int ia, ja, ib, jb;
+                pair_decode(qa, mA, ia, ja);
+                pair_decode(qb, mB, ib, jb);
+                usrc[0] = (uint32_t)ia * 16;
+                usrc[1] = (uint32_t)(mA + ja) * 16;
+                usrc[2] = (uint32_t)(2 * mA + ib) * 16;
+                usrc[3] = (uint32_t)(2 * mA + jb) * 16;
+            }
+        }
+        // V: row pt % 128 of this CTA's half of the tile, half of the stage's pieces per thread
+        constexpr int V_NC = H_NP / 2;
+        const int v_row = pt & 127, v_c0 = (pt >> 7) * V_NC;
+        uint32_t vsrc[2] = {zero_row, zero_row};
+        const int gv = v0 + (int)rank * TP_BH + v_row;
+        if (gv < p.nC) {
+            int ic, jc;
+            pair_decode(gv, mC, ic, jc);
+            vsrc[0] = (uint32_t)(2 * mA + mB + ic) * 16;
+            vsrc[1] = (uint32_t)(2 * mA + mB + jc) * 16;
+        }
+        const uint32_t udst = (uint32_t)u_tile * a_tile_bytes + (uint32_t)u_row * 16;
+        constexpr uint32_t lbo_b = TP_BH * 16;
+        const uint32_t vdst = TP_T * a_tile_bytes + (uint32_t)v_row * 16 + (uint32_t)v_c0 * lbo_b;
+        const uint32_t stage_s = smem_u32(stage_base);
+        const __half* Zh = reinterpret_cast<const __half*>(p.Z);
+
+        auto issue_chunk = [&](int64_t chunk) {
+            if (chunk < nchunks && pt == 0) {
+                const int slot = (int)(chunk % TC_RAW_SLOTS);
+                const uint32_t bar = smem_u32(&raw_full[slot]);
+                const uint32_t plane_bytes = z_rows * 16;
+                const uint32_t dst0 = raw_s + (uint32_t)slot * raw_bytes;
+                const __half* src0 = Zh + ((k_begin / H_KC + chunk) * H_NP) * (int64_t)z_rows * 8;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(H_NP * plane_bytes) : "memory");
+#pragma unroll
+                for (int part = 0; part < H_NP; ++part)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst0 + (uint32_t)part * plane_stride), "l"(src0 + (int64_t)part * z_rows * 8), "r"(plane_bytes), "r"(bar)
+                                 : "memory");
+            }
+        };
+        issue_chunk(0);
+        issue_chunk(1);
+
+        uint32_t acc_phase = 0;
+        int s = 0, rs = 0;
+        uint32_t ph = 0;
+        int64_t in_window = 0;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");  // chunk c-1 is fully consumed by every producer of this CTA
+            issue_chunk(c + 2);
+            mbar_wait(&raw_full[rs], (uint32_t)((c / TC_RAW_SLOTS) & 1));
+            if (lane == 0) mbar_wait(&empty[s], ph ^ 1);
+            __syncwarp();
+            const uint32_t rb = raw_s + (uint32_t)rs * raw_bytes;
+            const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
+#pragma unroll
+            for (int g0 = 0; g0 < H_NP; g0 += 4) {     // ---- U rows, four pieces at a time: all loads, then the products, then the stores
+                uint4 x0[4], x1[4], x2[4], x3[4];
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) {
+                    const uint32_t o = (uint32_t)(g0 + cc) * plane_stride;
+                    x0[cc] = lds128u(rb + usrc[0] + o);
+                    x1[cc] = lds128u(rb + usrc[1] + o);
+                    x2[cc] = lds128u(rb + usrc[2] + o);
+                    x3[cc] = lds128u(rb + usrc[3] + o);
+                }
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc)
+                    sts128u(sb + udst + (uint32_t)(g0 + cc) * (TC_M * 16), hmul8(hmul8(x0[cc], x1[cc]), hmul8(x2[cc], x3[cc])));
+            }
+            {   // ---- V rows
+                uint4 y0[V_NC], y1[V_NC];
+#pragma unroll
+                for (int cc = 0; cc < V_NC; ++cc) {
+                    y0[cc] = lds128u(rb + vsrc[0] + (uint32_t)(v_c0 + cc) * plane_stride);
+                    y1[cc] = lds128u(rb + vsrc[1] + (uint32_t)(v_c0 + cc) * plane_stride);
+                }
+#pragma unroll
+                for (int cc = 0; cc < V_NC; ++cc) sts128u(sb + vdst + (uint32_t)cc * lbo_b, hmul8(y0[cc], y1[cc]));
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(&full[s], 0);           // on the leader's barrier
+            if (++s == NS) { s = 0; ph ^= 1; }
+            if (++rs == TC_RAW_SLOTS) rs = 0;
+            const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+            if (last_of_window) {
+                in_window = 0;
+                mbar_wait(acc_full, acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                drain_accumulator(tmem_base, TP_T * TP_BN, TP_BN, warp, lane, u0_cta, nU, v0, p.nC, p.M,
+                                  reinterpret_cast<float*>(stage_base), unscale, 2 * TC_M, (c + 1) == nchunks);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty, 0);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncwarp();
+    cluster_sync_all();                  // the peer may still be reading this CTA's shared / tensor memory until here
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc2(tmem_base, 512);
+    }
+}
+
+static size_t tc16_pair_smem_bytes(int mA, int mB, int mC, int NS, int kc) {
+    const size_t stage = (size_t)TP_T * TC_M * kc * 2 + (size_t)TP_BH * kc * 2;
+    const size_t plane = (((size_t)(2 * mA + mB + mC + 1) * 16 + 95) / 128) * 128 + 32;
+    return NS * stage + TC_RAW_SLOTS * (kc / 8) * plane + (2 * NS + 2) * 8 + 16 + 32;
+}
+
 static size_t tc_pair_smem_bytes(int mA, int mB, int mC, int NS) {
     const size_t stage = 2 * (size_t)TP_T * TC_M * TC_KC * 4 + 2 * (size_t)TP_BH * TC_KC * 4;
     const size_t raw = (size_t)(2 * mA + mB + mC + 1) * TC_KCP * 4;
@@ -1166,8 +1672,39 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     if (ks > 65535) ks = 65535;
     p.rows_per_split = ceil_div64(ceil_div64(p.zpitch, ks), KC) * KC;
     ks = ceil_div64(p.zpitch, p.rows_per_split);
+    // CTA-pair fp16 kernel for the large sites (opt-in until measured: TN_TC16_PAIR=1)
+    if (f16 && kc16 == 64 && p.T == 2 && p.BN == TP_BN && nU >= 8LL * 512 && getenv("TN_TC16_PAIR") && atoi(getenv("TN_TC16_PAIR")) != 0) {
+        int NSP = 4;
+        while (NSP >= 2 && tc16_pair_smem_bytes(A.m, B.m, C.m, NSP, 64) > 226 * 1024) --NSP;
+        if (NSP >= 2) {
+            p.nstages = NSP;
+            const size_t psmem = tc16_pair_smem_bytes(A.m, B.m, C.m, NSP, 64);
+            const int64_t gxp = 2 * ceil_div64(nU, 2LL * TC_M * TP_T), gyp = ceil_div64(p.nC, TP_BN);
+            int64_t ksp = ceil_div64((int64_t)sm_count(), gxp * gyp);
+            const int64_t max_ksp = ceil_div64(p.zpitch, 4 * 64);
+            if (ksp > max_ksp) ksp = max_ksp;
+            if (ksp < 1) ksp = 1;
+            if (ksp > 65535) ksp = 65535;
+            p.rows_per_split = ceil_div64(ceil_div64(p.zpitch, ksp), 64) * 64;
+            ksp = ceil_div64(p.zpitch, p.rows_per_split);
+            TN_SMEM(gram_tc16_pair_kernel<64>, psmem);
+            dim3 pgrid((unsigned)gxp, (unsigned)gyp, (unsigned)ksp);
+            gram_tc16_pair_kernel<64><<<pgrid, TC_THREADS, psmem, st>>>(p);
+            TN_LAUNCH_CHECK();
+            TN_CUDA(cudaFreeAsync(Z, st));
+            return TN_OK;
+        }
+    }
     if (f16) {
         using Kern16 = void (*)(TcParams);
+        if (kc16 == 64 && p.T == 2 && z_rows < 1023 && getenv("TN_TC16_RUN") && atoi(getenv("TN_TC16_RUN")) != 0) {
+            TN_SMEM(gram_tc16_run_kernel, smem);
+            dim3 gridr((unsigned)gx, (unsigned)gy, (unsigned)ks);
+            gram_tc16_run_kernel<<<gridr, TC_THREADS, smem, st>>>(p);
+            TN_LAUNCH_CHECK();
+            TN_CUDA(cudaFreeAsync(Z, st));
+            return TN_OK;
+        }
         Kern16 k16 = (kc16 == 64) ? ((p.T == 2) ? gram_tc16_kernel<2, 64> : gram_tc16_kernel<1, 64>)
                                   : ((p.T == 2) ? gram_tc16_kernel<2, 32> : gram_tc16_kernel<1, 32>);
         TN_SMEM(k16, smem);

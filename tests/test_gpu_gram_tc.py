@@ -171,3 +171,50 @@ def test_f16_gram_special_cases():
     full = ops.gram(ops.GRAM_F16, Factor(Fa, m=ma), Factor(Fb, m=mb), Factor(Fc, m=mc), w, S)
     ref = ops.gram(ops.GRAM_FP64, Factor(Fa, m=ma), Factor(Fb, m=mb), Factor(Fc, m=mc), w, S)
     assert float((full - ref).norm() / ref.norm()) < 5e-3
+
+
+@pytest.mark.parametrize("shape", [(4096 + 70, 38, 29, 38), (20000, 38, 6, 38), (700, 24, 12, 38)])
+def test_f16_pair_kernel_same_bits_as_one_cta(shape, monkeypatch):
+    """CTA-pair fp16 kernel (gram_tc.cu::gram_tc16_pair_kernel: cta_group::2, each CTA synthesises its 128 rows of the two M = 256
+    U tiles and half of the V tile) against the 1-CTA fp16 kernel: same products, same accumulation order along the rows, same
+    flush windows, so M must agree to the bit; both against fp64 within the fp16 tolerance.  Ragged row counts, a flush boundary,
+    a V tile with padding columns (741 = 2 x 256 + 229)."""
+    S, ma, mb, mc = shape
+    g = torch.Generator(device=DEV).manual_seed(S + ma)
+    Fa = torch.randn((S, ma), device=DEV, generator=g)
+    Fb = torch.rand((S, mb), device=DEV, generator=g) * 2 - 1
+    Fc = torch.randn((S, mc), device=DEV, generator=g)
+    w = torch.rand((S,), device=DEV, generator=g) + 0.5
+    args = (Factor(Fa, m=ma), Factor(Fb, m=mb), Factor(Fc, m=mc), w, S)
+    monkeypatch.setenv("TN_TC16_PAIR", "0")
+    one = ops.gram(ops.GRAM_F16, *args, flush_rows=2048)
+    monkeypatch.setenv("TN_TC16_PAIR", "1")
+    two = ops.gram(ops.GRAM_F16, *args, flush_rows=2048)
+    torch.cuda.synchronize()
+    ref = ops.gram(ops.GRAM_FP64, *args)
+    assert gu.relerr(two.cpu().numpy(), ref.cpu().numpy()) < 5e-3
+    assert torch.equal(one, two)
+
+
+@pytest.mark.parametrize("shape", [(4096 + 70, 38, 29, 38), (6000, 24, 2, 24), (3000, 38, 6, 38), (2500, 38, 29, 1), (9000, 100, 9, 1),
+                                   (1500, 7, 3, 5), (2000, 3, 40, 9)])
+def test_f16_run_ordered_producers(shape, monkeypatch):
+    """fp16 Gram kernel with run-ordered producers (gram_tc.cu::gram_tc16_run_kernel: a thread owns one 8-sample piece of eight
+    consecutive tile rows and reuses the run prefix w fa[ia] fa[ja] fb[ib] / fc[ic]) against fp64 and against the row-per-thread
+    kernel: same operands up to the order of the fp16 multiplications.  Shapes: the config-5a / 3 / 5b middle sites, a last site
+    (one V column), the CPD factor, short runs (mB = 2, 3: more than two prefixes per eight rows -> the reloading path), long runs."""
+    S, ma, mb, mc = shape
+    g = torch.Generator(device=DEV).manual_seed(S + ma)
+    Fa = torch.randn((S, ma), device=DEV, generator=g)
+    Fb = torch.rand((S, mb), device=DEV, generator=g) * 2 - 1
+    Fc = torch.randn((S, mc), device=DEV, generator=g)
+    w = torch.rand((S,), device=DEV, generator=g) + 0.5
+    args = (Factor(Fa, m=ma), Factor(Fb, m=mb), Factor(Fc, m=mc), w, S)
+    monkeypatch.setenv("TN_TC16_RUN", "0")
+    one = ops.gram(ops.GRAM_F16, *args, flush_rows=2048)
+    monkeypatch.setenv("TN_TC16_RUN", "1")
+    two = ops.gram(ops.GRAM_F16, *args, flush_rows=2048)
+    torch.cuda.synchronize()
+    ref = ops.gram(ops.GRAM_FP64, *args)
+    assert gu.relerr(two.cpu().numpy(), ref.cpu().numpy()) < 5e-3
+    assert gu.relerr(two.cpu().numpy(), one.cpu().numpy()) < 2e-3

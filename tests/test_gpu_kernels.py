@@ -222,3 +222,40 @@ def test_env_update_full_size_linearity():
     phi = orc.fbasis(X[idx].cpu().numpy())[17]
     want = np.einsum("sa,sp,apb->sb", e1[idx].cpu().numpy(), phi, core.cpu().numpy())
     assert gu.relerr(o1[idx].cpu().numpy(), want) < 1e-13
+
+
+@pytest.mark.parametrize("S,C,rin,f,rout,fmap", [(200003, 1, 24, 2, 24, "sincos"), (160000, 1, 38, 2, 38, "sincos"), (40000, 5, 16, 2, 12, "sincos"),
+                                                 (170000, 1, 1, 4, 20, None), (180000, 1, 12, 3, 10, None), (150016, 1, 8, 4, 6, "poly")])
+def test_env_update_warp_per_tile_bulk_copy_path(S, C, rin, f, rout, fmap):
+    """Rows enough for the warp-per-tile kernel (env.cu::env_warp_kernel: every warp owns 16-row tiles, environment rows fetched
+    and results stored with bulk copies, no block barrier in the loop): dense environments, feature maps, a ragged last tile, the
+    prediction epilogue, class rows sharing a site input (cdiv), a strided output; against numpy on a sample of rows."""
+    rng = np.random.default_rng(S % 1000 + rin)
+    rows = S * C
+    env = rng.normal(size=(rows, rin))
+    X = rng.uniform(-1, 1, size=(S, 6))
+    core = rng.normal(size=(rin, f, rout))
+    if fmap is None:
+        fx = Factor(T(X[:, :f].copy()), m=f)
+        phi = X[:, :f]
+    else:
+        mk = ops.MAP_SINCOS if fmap == "sincos" else ops.MAP_POLY
+        fx = Factor(T(X), m=f, map_kind=mk, col=2)
+        phi = np.stack([np.cos(0.5 * np.pi * X[:, 2]), np.sin(0.5 * np.pi * X[:, 2])], 1) if fmap == "sincos" else np.stack([X[:, 2] ** d for d in range(f)], 1)
+    e = None if rin == 1 else T(env)
+    got = ops.env_update(e, fx, T(core), rows, cdiv=C).cpu().numpy()
+    idx = np.unique(np.concatenate([np.arange(0, rows, 997), np.arange(rows - 40, rows), np.arange(0, 40)]))
+    ein = np.ones((len(idx), 1)) if rin == 1 else env[idx]
+    want = np.einsum("sa,sp,apb->sb", ein, phi[idx // C], core)
+    assert gu.relerr(got[idx], want) < 1e-13
+    dot = rng.normal(size=(S, rout))
+    yh = ops.predict(e, fx, T(core), T(dot), rows, cdiv=C, dot_div=C).cpu().numpy()
+    assert gu.relerr(yh[idx], (want * dot[idx // C]).sum(1)) < 1e-13
+    wide = torch.zeros((rows, rout + 3), dtype=torch.float64, device="cuda")      # a column block of a wider tensor: row stride != r_out
+    ops.env_update(e, fx, T(core), rows, cdiv=C, out=wide[:, 1:1 + rout])
+    assert gu.relerr(wide[:, 1:1 + rout].cpu().numpy()[idx], want) < 1e-13 and float(wide[:, 0].abs().max()) == 0.0 and float(wide[:, 1 + rout:].abs().max()) == 0.0
+    if e is not None:       # environment rows as a column block of a wider tensor (row stride != r_in, still 16-byte aligned rows)
+        big = torch.zeros((rows, rin + 4), dtype=torch.float64, device="cuda")
+        big[:, 2:2 + rin] = e
+        got2 = ops.env_update(big[:, 2:2 + rin], fx, T(core), rows, cdiv=C)
+        assert torch.equal(got2, torch.as_tensor(got, device="cuda"))

@@ -1,0 +1,13 @@
+#!/bin/bash
+# round 2, GPU call 11 (1 GPU): run-ordered producers of the fp16 Gram kernel: test, A/B timing, flush windows, ncu
+mkdir -p gpurun_out/r2c11; O=gpurun_out/r2c11
+timeout 600 python -m pytest tests/test_gpu_gram_tc.py -q -rA -x -k "f16" -p no:cacheprovider > $O/pytest_f16.log 2>&1; echo "f16 tests rc=$?" > $O/rc.txt
+timeout 600 python tools/tc16_probe.py 262144 - TN_TC16_RUN=1 TN_TC16_RUN=1,TN_TC_FLUSH_ROWS=32768 TN_TC_FLUSH_ROWS=32768 > $O/tc16_run.log 2>&1; echo "run probe rc=$?" >> $O/rc.txt
+TC16_SHAPE=38,6,38 timeout 600 python tools/tc16_probe.py 524288 - TN_TC16_RUN=1 > $O/tc16_run_5b.log 2>&1
+TC16_SHAPE=24,2,24 timeout 600 python tools/tc16_probe.py 1048576 - TN_TC16_RUN=1 > $O/tc16_run_3.log 2>&1
+TN_TC16_RUN=1 timeout 300 python tools/tc_one.py 65536 f16 > $O/tc16_one_plain.log 2>&1 && \
+  TN_TC16_RUN=1 timeout 900 ncu --set full --clock-control none --import-source on -k regex:gram_tc16 -c 1 -o $O/ncu_tc16run python tools/tc_one.py 65536 f16 > $O/ncu_tc16run.log 2>&1
+ncu -i $O/ncu_tc16run.ncu-rep --page raw --csv > $O/ncu_tc16run_raw.csv 2>/dev/null
+python tools/ncu_hotspots.py $O/ncu_tc16run.ncu-rep 40 > $O/ncu_tc16run_hotspots.txt 2>&1
+rm -f $O/ncu_tc16run.ncu-rep
+echo done >> $O/rc.txt
