@@ -202,7 +202,8 @@ int tn_lanczos(const tn_operator *op, const double *b, const double *x0, double 
                int poll_every, double *work, double *stats, void *stream);
 
 /* Factorisation alone (the preconditioner of tn_cg): lower triangle of A <- L, work (tn_cholesky_work_elems(P)) <- the
- * inverted 64 x 64 diagonal blocks.  tensor_core != 0: trailing updates as 3xTF32 tcgen05 GEMMs (factor accurate to ~1e-5).
+ * inverted 64 x 64 diagonal blocks.  tensor_core == 1: trailing updates as 3xTF32 tcgen05 GEMMs (factor accurate to ~1e-5);
+ * tensor_core == 2: one TF32 pass per K step (~1e-3: a factor that only preconditions tn_cg).
  * tn_cholesky_apply: x <- L^-T L^-1 x.                                                                               */
 int tn_cholesky_factor(double *A, int64_t lda, int64_t P, int tensor_core, double *work, int *info, void *stream);
 int tn_cholesky_apply(const double *L, int64_t lda, int64_t P, double *x, const double *work, const int *info, void *stream);

@@ -70,6 +70,7 @@ cudaError_t ensure_dyn_smem(const void* func, size_t bytes);
 #define TN_SMEM(kernel, bytes) TN_CUDA(tn::ensure_dyn_smem(reinterpret_cast<const void*>(kernel), (size_t)(bytes)))
 // tensor-core trailing update of the blocked Cholesky (syrk_tc.cu)
 int64_t syrk_tc_work_floats(int64_t n, int kb);
+void syrk_tc_set_passes(int passes);   // 3 (default): 3xTF32; 1: one TF32 pass (calling thread's later syrk_tc_update calls)
 int syrk_tc_update(double* A, int64_t lda, int64_t P, int64_t c0, int64_t k0, int kb, float* X, const int* info, cudaStream_t st,
                    int64_t col_limit = 0);
 void count_launch(int n = 1);   // bookkeeping for tn_launch_count()

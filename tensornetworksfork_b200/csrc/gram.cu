@@ -312,6 +312,145 @@ rhs_small_vec_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __r
     }
 }
 
+// Right-hand side / J^T u for LARGE cores whose outer factors are at most 40 wide (config 5a: 38 x 29 x 38, P = 41 876).
+//   out[a, p, b] = sum_rows w * fa[a] * fb[p] * fc[b]  =  for every p:  (fa (.) (w fb[p]))^T fc   -- an (mA x rows) x (rows x mC) product
+// The GEMM-shaped kr3 kernel synthesises a 128-wide operand tile w*fa*fb per 32-row chunk in shared memory and pads mC = 38 to
+// a 64-wide tile; it runs at 4.5 TF/s on this shape (profiles/r2_launches_cfg5a_1M_summary.txt: 18.5 ms per call, and the exact
+// refinement calls it once per conjugate-gradient iteration).  Here nothing is synthesised in memory: a warp owns ONE p and the whole
+// (8 MT) x (8 NT) output block of that p in registers; per 4-row DMMA step it loads MT fragments of fa, scales them by the per-row
+// scalar w * fb[p] in registers (one multiply per fragment), loads NT fragments of fc and issues MT x NT DMMAs.  A CTA = 8 warps =
+// 8 consecutive p; rows are split over blockIdx.y.  Chunks of 32 rows are prefetched into registers while the previous chunk is
+// multiplied (one block barrier per chunk, two shared buffers).
+constexpr int RB_KC = 32;          // rows per chunk
+constexpr int RB_PW = 8;           // p values per CTA = warps
+constexpr int RB_MAXPRE = 14;      // prefetch registers per thread (>= 32 * (40 + 40 + 8) / 256)
+
+template <int MT, int NT>
+__global__ void __launch_bounds__(256, 1)
+rhs_big_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restrict__ w, int64_t rows, double* __restrict__ out,
+               int64_t rows_per_split) {
+    constexpr int stA = 8 * MT + 4, stC = 8 * NT + 4;      // == 4 (mod 8) doubles: conflict-free fragment loads
+    constexpr int BUF = RB_KC * (stA + stC + RB_PW);
+    __shared__ __align__(16) double sm[2 * BUF];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int fr = lane >> 2, fk = lane & 3;
+    const int p0 = blockIdx.x * RB_PW;
+    const int p = p0 + warp;
+    const int64_t k_begin = (int64_t)blockIdx.y * rows_per_split;
+    const int64_t k_end = min(rows, k_begin + rows_per_split);
+    for (int i = tid; i < 2 * BUF; i += 256) sm[i] = 0.0;           // the padding columns stay zero
+
+    // chunk elements owned by this thread: [32 x mA of fa | 32 x mC of fc | 32 x 8 of w * fb[p0 + q]]
+    const int nA = RB_KC * fa.m, nC = RB_KC * fc.m, nB = RB_KC * RB_PW;
+    const int total = nA + nC + nB;
+    int desc[RB_MAXPRE];            // (kind << 16) | (k << 8) | column
+    double pre[RB_MAXPRE];
+#pragma unroll
+    for (int q = 0; q < RB_MAXPRE; ++q) {
+        const int e = tid + 256 * q;
+        int d = -1;
+        if (e < nA) { const int k = e / fa.m; d = (0 << 16) | (k << 8) | (e - k * fa.m); }
+        else if (e < nA + nC) { const int e2 = e - nA; const int k = e2 / fc.m; d = (1 << 16) | (k << 8) | (e2 - k * fc.m); }
+        else if (e < total) { const int e2 = e - nA - nC; d = (2 << 16) | ((e2 >> 3) << 8) | (e2 & 7); }
+        desc[q] = d;
+    }
+    auto prefetch = [&](int64_t kb) {
+#pragma unroll
+        for (int q = 0; q < RB_MAXPRE; ++q) {
+            const int d = desc[q];
+            double v = 0.0;
+            if (d >= 0) {
+                const int kind = d >> 16, k = (d >> 8) & 255, c = d & 255;
+                const int64_t row = kb + k;
+                if (row < k_end) {
+                    if (kind == 0) v = map_eval(fa.map_kind, fa.ptr + (fa.div == 1 ? row : row / fa.div) * fa.ld, c);
+                    else if (kind == 1) v = map_eval(fc.map_kind, fc.ptr + (fc.div == 1 ? row : row / fc.div) * fc.ld, c);
+                    else if (p0 + c < fb.m) v = (w ? w[row] : 1.0) * map_eval(fb.map_kind, fb.ptr + (fb.div == 1 ? row : row / fb.div) * fb.ld, p0 + c);
+                }
+            }
+            pre[q] = v;
+        }
+    };
+    auto commit = [&](int buf) {
+        double* sA = sm + buf * BUF;
+        double* sC = sA + RB_KC * stA;
+        double* sB = sC + RB_KC * stC;
+#pragma unroll
+        for (int q = 0; q < RB_MAXPRE; ++q) {
+            const int d = desc[q];
+            if (d >= 0) {
+                const int kind = d >> 16, k = (d >> 8) & 255, c = d & 255;
+                if (kind == 0) sA[k * stA + c] = pre[q];
+                else if (kind == 1) sC[k * stC + c] = pre[q];
+                else sB[k * RB_PW + c] = pre[q];
+            }
+        }
+    };
+
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    __syncthreads();                 // zero fill done before the first commit
+    if (k_begin < k_end) prefetch(k_begin);
+    int buf = 0;
+    for (int64_t kb = k_begin; kb < k_end; kb += RB_KC, buf ^= 1) {
+        commit(buf);
+        __syncthreads();
+        if (kb + RB_KC < k_end) prefetch(kb + RB_KC);
+        if (p < fb.m) {
+            const double* sA = sm + buf * BUF;
+            const double* sC = sA + RB_KC * stA;
+            const double* sB = sC + RB_KC * stC;
+#pragma unroll 2
+            for (int k4 = 0; k4 < RB_KC; k4 += 4) {
+                const double sc = sB[(k4 + fk) * RB_PW + warp];
+                double af[MT], bf[NT];
+                const double* ap = sA + (k4 + fk) * stA + fr;
+                const double* cp = sC + (k4 + fk) * stC + fr;
+#pragma unroll
+                for (int i = 0; i < MT; ++i) af[i] = ap[i * 8] * sc;
+#pragma unroll
+                for (int j = 0; j < NT; ++j) bf[j] = cp[j * 8];
+#pragma unroll
+                for (int i = 0; i < MT; ++i)
+#pragma unroll
+                    for (int j = 0; j < NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+        }
+    }
+    if (p < fb.m) {
+        double* o = out + (int64_t)blockIdx.y * ((int64_t)fa.m * fb.m * fc.m);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+            const int a = i * 8 + fr;
+            if (a >= fa.m) continue;
+#pragma unroll
+            for (int j = 0; j < NT; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int b = j * 8 + 2 * fk + e;
+                    if (b < fc.m) o[((int64_t)a * fb.m + p) * fc.m + b] = acc[i][j][e];
+                }
+        }
+    }
+}
+
+template <int MT>
+static int launch_rhs_big_nt(int NT, dim3 grid, const FactorDev& a, const FactorDev& b, const FactorDev& c, const double* w, int64_t rows,
+                             double* dst, int64_t rps, cudaStream_t st) {
+    switch (NT) {
+        case 1: rhs_big_kernel<MT, 1><<<grid, 256, 0, st>>>(a, b, c, w, rows, dst, rps); break;
+        case 2: rhs_big_kernel<MT, 2><<<grid, 256, 0, st>>>(a, b, c, w, rows, dst, rps); break;
+        case 3: rhs_big_kernel<MT, 3><<<grid, 256, 0, st>>>(a, b, c, w, rows, dst, rps); break;
+        case 4: rhs_big_kernel<MT, 4><<<grid, 256, 0, st>>>(a, b, c, w, rows, dst, rps); break;
+        default: rhs_big_kernel<MT, 5><<<grid, 256, 0, st>>>(a, b, c, w, rows, dst, rps); break;
+    }
+    return TN_OK;
+}
+
 __global__ void reduce_splits_kernel(const double* __restrict__ work, double* __restrict__ dst, int64_t n, int ksplit,
                                      int accumulate) {
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -582,6 +721,33 @@ extern "C" int tn_rhs_kr3(const tn_factor* fa, const tn_factor* fb, const tn_fac
         TN_LAUNCH_CHECK();
         int64_t blocks = ceil_div64(P, 256);
         reduce_splits_kernel<<<(unsigned)blocks, 256, 0, as_stream(stream)>>>(work, b, P, ctas, accumulate);
+        TN_LAUNCH_CHECK();
+        return TN_OK;
+    }
+    if (fa->m <= 40 && fc->m <= 40 && fa->m * fc->m >= 64 && work != nullptr && ksplit >= 1 && !getenv("TN_RHS_NO_BIG")) {
+        // register-blocked kernel: one wave of CTAs, rows split so that (p blocks) x (row splits) fills the SMs
+        const FactorDev a = to_dev(fa), bb = to_dev(fb), c = to_dev(fc);
+        const int pblocks = (bb.m + RB_PW - 1) / RB_PW;
+        int64_t ks = sm_count() / pblocks;
+        if (ks > ksplit) ks = ksplit;
+        const int64_t max_by_rows = ceil_div64(rows, 4 * RB_KC);
+        if (ks > max_by_rows) ks = max_by_rows;
+        if (ks < 1) ks = 1;
+        const int64_t rps = ceil_div64(ceil_div64(rows, ks), RB_KC) * RB_KC;
+        ks = ceil_div64(rows, rps);
+        const int MT = (a.m + 7) / 8, NT = (c.m + 7) / 8;
+        dim3 grid((unsigned)pblocks, (unsigned)ks);
+        cudaStream_t st = as_stream(stream);
+        switch (MT) {
+            case 1: launch_rhs_big_nt<1>(NT, grid, a, bb, c, w, rows, work, rps, st); break;
+            case 2: launch_rhs_big_nt<2>(NT, grid, a, bb, c, w, rows, work, rps, st); break;
+            case 3: launch_rhs_big_nt<3>(NT, grid, a, bb, c, w, rows, work, rps, st); break;
+            case 4: launch_rhs_big_nt<4>(NT, grid, a, bb, c, w, rows, work, rps, st); break;
+            default: launch_rhs_big_nt<5>(NT, grid, a, bb, c, w, rows, work, rps, st); break;
+        }
+        TN_LAUNCH_CHECK();
+        int64_t blocks = ceil_div64(P, 256);
+        reduce_splits_kernel<<<(unsigned)blocks, 256, 0, st>>>(work, b, P, (int)ks, accumulate);
         TN_LAUNCH_CHECK();
         return TN_OK;
     }

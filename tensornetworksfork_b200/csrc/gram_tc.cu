@@ -175,12 +175,13 @@ __device__ __forceinline__ void red_add_f64_keep(double* addr, double v, uint64_
 
 __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_total, int BN, int warp, int lane, int64_t u0,
                                                int64_t nU, int v0, int nC, double* __restrict__ M, float* __restrict__ scratch,
-                                               double unscale, int tile_stride = TC_M, bool final_flush = false) {
+                                               double unscale, int tile_stride = TC_M, bool final_flush = false, int nparts = 2) {
     const int q = warp & 3;
-    const int half = (warp - 1) >> 2;
+    const int half = (warp - 1) >> 2;                  // which part of the columns (two warps per lane quarter by default, four with 16 producer warps)
     const int ngroups = (cols_total + 31) / 32;
-    const int g_lo = half * ((ngroups + 1) / 2);
-    const int g_hi = min(ngroups, g_lo + (ngroups + 1) / 2);
+    const int per_part = (ngroups + nparts - 1) / nparts;
+    const int g_lo = half * per_part;
+    const int g_hi = min(ngroups, g_lo + per_part);
     float* sc = scratch + (size_t)(warp - 1) * (32 * 33);
     const uint64_t l2_keep = final_flush ? l2_evict_first_policy() : l2_evict_last_policy();
     for (int g = g_lo; g < g_hi; ++g) {
@@ -742,12 +743,14 @@ gram_tc16_kernel(TcParams p) {
 // thread owns ONE 16-byte piece (8 samples) of EIGHT consecutive tile rows (= one 8-row core matrix of the UMMA layout) instead
 // of all pieces of one row: it builds the (at most two, else a slow path reloads per row) run prefixes of its rows once per stage
 // and then spends one LDS.128, four HMUL2 and one STS.128 per tile piece -- 24 loads per thread and stage instead of 48.
-// Bank conflicts: the 8 lanes of a quarter warp own 8 different core matrices (128 B apart, i.e. the same banks), so lane l walks
-// its rows in the rotated order (i + l) % 8: the eight 16-byte stores of an instruction then fall into eight different bank
-// groups, and so do the eight fb[jb] / fc[jc] loads inside a run (row indices 8 l + (i + l) % 8 are distinct modulo 8).
-struct RunRows {            // per thread: its eight rows in processing order
+// Bank conflicts (first version, profiles/r2_ncu_gram_tc16_run_v1.txt: lane = core matrix with rotated row order; the loads of a
+// quarter warp crossed run boundaries and collided, 1281 load wavefronts instead of 768): the eight lanes of a quarter warp now
+// own the EIGHT PIECES of the same rows, so every load instruction reads one raw-factor row in eight planes and every store one
+// tile row in eight piece slabs; with the plane stride and the piece stride (the descriptors' LBO) both == 16 (mod 128) bytes
+// the eight 16-byte accesses fall into eight different bank groups whatever the row pattern.
+struct RunRows {            // per thread: its eight rows
     uint32_t key[8];        // the three prefix rows of a U row (10 bits each) / the fc[ic] row of a V row
-    uint32_t last[8];       // the row of the last factor (fb[jb] / fc[jc])
+    uint32_t last[8];       // byte offset of the row of the last factor (fb[jb] / fc[jc]) in a plane
     uint32_t keyA, keyB;    // the (at most) two distinct prefixes handled without reloading
     uint32_t selB;          // bit i: row i uses prefix B
     uint32_t slow;          // bit i: row i has a third prefix: reload it in the loop
@@ -768,6 +771,10 @@ __device__ __forceinline__ void run_rows_finish(RunRows& r) {
 }
 __device__ __forceinline__ uint4 sel8(bool b, uint4 x, uint4 y) { return b ? x : y; }
 
+__host__ __device__ __forceinline__ uint32_t run_plane_stride(uint32_t raw_rows) { return ((raw_rows * 16 + 127) / 128) * 128 + 16; }
+constexpr uint32_t RUN_LBO_A = TC_M * 16 + 16;                   // bytes between two pieces of a U tile
+constexpr uint32_t RUN_A_TILE = 8 * RUN_LBO_A;                   // one U tile of one stage
+
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gram_tc16_run_kernel(TcParams p) {
     constexpr int T = 2, H_KC = 64, H_NP = 8;
@@ -777,12 +784,12 @@ gram_tc16_run_kernel(TcParams p) {
     const int BN = p.BN, NS = p.nstages;
     const int mA = p.mA, mB = p.mB, mC = p.mC;
 
-    constexpr uint32_t a_tile_bytes = TC_M * H_KC * 2;
-    const uint32_t b_tile_bytes = (uint32_t)BN * H_KC * 2;
-    const uint32_t stage_bytes = T * a_tile_bytes + b_tile_bytes;
+    const uint32_t lbo_b = (uint32_t)BN * 16 + 16;
+    const uint32_t b_tile_bytes = 8 * lbo_b;
+    const uint32_t stage_bytes = T * RUN_A_TILE + b_tile_bytes;
     const uint32_t z_rows = (uint32_t)(2 * mA + mB + mC);
     const uint32_t raw_rows = z_rows + 1;
-    const uint32_t plane_stride = ((raw_rows * 16 + 95) / 128) * 128 + 32;
+    const uint32_t plane_stride = run_plane_stride(raw_rows);
     const uint32_t raw_bytes = H_NP * plane_stride;
     uint8_t* stage_base = smem_raw;
     uint8_t* raw_base = smem_raw + (size_t)NS * stage_bytes;
@@ -827,10 +834,10 @@ gram_tc16_run_kernel(TcParams p) {
     const int v0 = blockIdx.y * BN;
 
     if (warp == 0) {
-        // =============================== MMA issuer (as in gram_tc16_kernel) ===============================
+        // =============================== MMA issuer ===============================
         if (lane == 0 && nchunks > 0) {
             const uint32_t idesc = make_idesc_f16(TC_M, BN);
-            const uint32_t lbo_a = TC_M * 16, lbo_b = (uint32_t)BN * 16, sbo = 128;
+            const uint32_t sbo = 128;
             uint32_t acc_phase = 0;
             int s = 0;
             uint32_t ph = 0;
@@ -845,16 +852,16 @@ gram_tc16_run_kernel(TcParams p) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t sb = smem_u32(stage_base + (size_t)s * stage_bytes);
-                const uint32_t b_base = sb + T * a_tile_bytes;
+                const uint32_t b_base = sb + T * RUN_A_TILE;
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
-                    const uint32_t a_base = sb + (uint32_t)t * a_tile_bytes;
+                    const uint32_t a_base = sb + (uint32_t)t * RUN_A_TILE;
                     const uint32_t d = tmem_base + (uint32_t)(t * BN);
 #pragma unroll
                     for (int j = 0; j < H_KC / 16; ++j) {
-                        const uint32_t ao = (uint32_t)(2 * j) * lbo_a, bo = (uint32_t)(2 * j) * lbo_b;
+                        const uint32_t ao = (uint32_t)(2 * j) * RUN_LBO_A, bo = (uint32_t)(2 * j) * lbo_b;
                         const uint32_t acc0 = (first_of_window && j == 0) ? 0u : 1u;
-                        umma_f16(d, make_desc(a_base + ao, lbo_a, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
+                        umma_f16(d, make_desc(a_base + ao, RUN_LBO_A, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
                     }
                 }
                 umma_commit(&empty[s]);
@@ -869,9 +876,8 @@ gram_tc16_run_kernel(TcParams p) {
     } else {
         // =============================== producers / epilogue ===============================
         const int pt = tid - 32;              // 0..255
-        const int pc = pt >> 5;               // this warp's piece of the stage (8 samples)
-        const int grp = lane;                 // this lane's 8-row core matrix: U rows 8 grp .. 8 grp + 7 of the CTA's 256, V rows likewise
-        const int rot = lane & 7;
+        const int pc = lane & 7;              // this lane's piece of the stage (8 samples): the 8 lanes of a quarter warp = the 8 pieces of one row
+        const int grp = (pt >> 5) * 4 + (lane >> 3);     // 8-row core matrix: U rows 8 grp .. 8 grp + 7 of the CTA's 256, V rows likewise
         const double unscale = ldexp(1.0, 2 * (tc_exponent(p.amax[0]) + tc_exponent(p.amax[1]) + tc_exponent(p.amax[2])) +
                                               tc_exponent(p.amax[3]));
         const uint32_t raw_s = smem_u32(raw_base);
@@ -879,8 +885,7 @@ gram_tc16_run_kernel(TcParams p) {
         const bool v_active = 8 * grp < BN;
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-            const int j = (i + rot) & 7;
-            const int64_t gu = u0 + 8 * grp + j;
+            const int64_t gu = u0 + 8 * grp + i;
             uint32_t key = z_rows | (z_rows << 10) | (z_rows << 20), last = z_rows;      // the zero row
             if (gu < nU) {
                 const int qa = (int)(gu / p.nB), qb = (int)(gu - (int64_t)qa * p.nB);
@@ -892,7 +897,7 @@ gram_tc16_run_kernel(TcParams p) {
             }
             ur.key[i] = key;
             ur.last[i] = last * 16u;
-            const int gv = v0 + 8 * grp + j;
+            const int gv = v0 + 8 * grp + i;
             uint32_t vkey = z_rows, vlast = z_rows;
             if (v_active && gv < p.nC) {
                 int ic, jc;
@@ -905,10 +910,9 @@ gram_tc16_run_kernel(TcParams p) {
         }
         run_rows_finish(ur);
         run_rows_finish(vr);
-        // destinations: tile (8 grp) / 128, row (8 grp) % 128 + j; piece pc
-        const uint32_t udst = (uint32_t)(grp >> 4) * a_tile_bytes + (uint32_t)pc * (TC_M * 16) + (uint32_t)((8 * grp) & 127) * 16;
-        const uint32_t lbo_b = (uint32_t)BN * 16;
-        const uint32_t vdst = T * a_tile_bytes + (uint32_t)pc * lbo_b + (uint32_t)(8 * grp) * 16;
+        // destinations: tile (8 grp) / 128, row (8 grp) % 128 + i; piece pc
+        const uint32_t udst = (uint32_t)(grp >> 4) * RUN_A_TILE + (uint32_t)pc * RUN_LBO_A + (uint32_t)((8 * grp) & 127) * 16;
+        const uint32_t vdst = T * RUN_A_TILE + (uint32_t)pc * lbo_b + (uint32_t)(8 * grp) * 16;
         const uint32_t stage_s = smem_u32(stage_base);
         const __half* Zh = reinterpret_cast<const __half*>(p.Z);
 
@@ -947,7 +951,7 @@ gram_tc16_run_kernel(TcParams p) {
             mbar_wait(&raw_full[rs], (uint32_t)((c / TC_RAW_SLOTS) & 1));
             if (lane == 0) mbar_wait(&empty[s], ph ^ 1);
             __syncwarp();
-            const uint32_t rbp = raw_s + (uint32_t)rs * raw_bytes + (uint32_t)pc * plane_stride;     // this warp's plane of the slot
+            const uint32_t rbp = raw_s + (uint32_t)rs * raw_bytes + (uint32_t)pc * plane_stride;     // this lane's plane of the slot
             const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
             {   // ---- U: prefixes, then eight rows
                 const uint4 preA = u_prefix(rbp, ur.keyA);
@@ -959,7 +963,7 @@ gram_tc16_run_kernel(TcParams p) {
                 for (int i = 0; i < 8; ++i) {
                     uint4 pre = sel8((ur.selB >> i) & 1u, preB, preA);
                     if ((ur.slow >> i) & 1u) pre = u_prefix(rbp, ur.key[i]);
-                    sts128u(sb + udst + (uint32_t)((i + rot) & 7) * 16u, hmul8(pre, x[i]));
+                    sts128u(sb + udst + (uint32_t)i * 16u, hmul8(pre, x[i]));
                 }
             }
             if (v_active) {   // ---- V
@@ -972,7 +976,7 @@ gram_tc16_run_kernel(TcParams p) {
                 for (int i = 0; i < 8; ++i) {
                     uint4 pre = sel8((vr.selB >> i) & 1u, preB, preA);
                     if ((vr.slow >> i) & 1u) pre = lds128u(rbp + vr.key[i] * 16u);
-                    sts128u(sb + vdst + (uint32_t)((i + rot) & 7) * 16u, hmul8(pre, y[i]));
+                    sts128u(sb + vdst + (uint32_t)i * 16u, hmul8(pre, y[i]));
                 }
             }
             fence_proxy_async();
@@ -999,6 +1003,495 @@ gram_tc16_run_kernel(TcParams p) {
         tc_fence_after();
         tmem_dealloc(tmem_base, tmem_cols);
     }
+}
+
+constexpr int RUN2_PROD_WARPS = 16;          // warps 1..8 synthesise U, warps 9..16 synthesise V: half the dependent work per warp, twice the warps to hide latency
+constexpr int RUN2_THREADS = 32 + RUN2_PROD_WARPS * 32;
+__global__ void __launch_bounds__(RUN2_THREADS, 1)
+gram_tc16_run2_kernel(TcParams p) {
+    constexpr int T = 2, H_KC = 64, H_NP = 8;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int BN = p.BN, NS = p.nstages;
+    const int mA = p.mA, mB = p.mB, mC = p.mC;
+
+    const uint32_t lbo_b = (uint32_t)BN * 16 + 16;
+    const uint32_t b_tile_bytes = 8 * lbo_b;
+    const uint32_t stage_bytes = T * RUN_A_TILE + b_tile_bytes;
+    const uint32_t z_rows = (uint32_t)(2 * mA + mB + mC);
+    const uint32_t raw_rows = z_rows + 1;
+    const uint32_t plane_stride = run_plane_stride(raw_rows);
+    const uint32_t raw_bytes = H_NP * plane_stride;
+    uint8_t* stage_base = smem_raw;
+    uint8_t* raw_base = smem_raw + (size_t)NS * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)TC_RAW_SLOTS * raw_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NS;
+    uint64_t* acc_full = bars + 2 * NS;
+    uint64_t* acc_empty = bars + 2 * NS + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
+    uint64_t* raw_full = bars + 2 * NS + 3;
+
+    const uint32_t tmem_cols_needed = (uint32_t)(T * BN);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], RUN2_PROD_WARPS);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, RUN2_PROD_WARPS);
+        for (int i = 0; i < TC_RAW_SLOTS; ++i) mbar_init(&raw_full[i], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < TC_RAW_SLOTS * H_NP * 4; i += RUN2_THREADS) {
+        const int slot = i / (H_NP * 4), e = i % (H_NP * 4);
+        reinterpret_cast<uint32_t*>(raw_base + (size_t)slot * raw_bytes + (size_t)(e >> 2) * plane_stride + (size_t)z_rows * 16)[e & 3] = 0u;
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t k_begin = (int64_t)blockIdx.z * p.rows_per_split;
+    const int64_t k_end = min(p.zpitch, k_begin + p.rows_per_split);
+    const int64_t nchunks = (k_end > k_begin) ? (k_end - k_begin) / H_KC : 0;
+    const int64_t chunks_per_flush = p.flush_rows / H_KC;
+    const int64_t nU = (int64_t)p.nA * p.nB;
+    const int64_t u0 = (int64_t)blockIdx.x * (TC_M * T);
+    const int v0 = blockIdx.y * BN;
+
+    if (warp == 0) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0 && nchunks > 0) {
+            const uint32_t idesc = make_idesc_f16(TC_M, BN);
+            const uint32_t sbo = 128;
+            uint32_t acc_phase = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            int64_t in_window = 0;
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const bool first_of_window = in_window == 0;
+                if (first_of_window && c > 0) {
+                    mbar_wait(acc_empty, acc_phase);
+                    acc_phase ^= 1;
+                    tc_fence_after();
+                }
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(stage_base + (size_t)s * stage_bytes);
+                const uint32_t b_base = sb + T * RUN_A_TILE;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    const uint32_t a_base = sb + (uint32_t)t * RUN_A_TILE;
+                    const uint32_t d = tmem_base + (uint32_t)(t * BN);
+#pragma unroll
+                    for (int j = 0; j < H_KC / 16; ++j) {
+                        const uint32_t ao = (uint32_t)(2 * j) * RUN_LBO_A, bo = (uint32_t)(2 * j) * lbo_b;
+                        const uint32_t acc0 = (first_of_window && j == 0) ? 0u : 1u;
+                        umma_f16(d, make_desc(a_base + ao, RUN_LBO_A, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
+                    }
+                }
+                umma_commit(&empty[s]);
+                const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+                if (last_of_window) {
+                    umma_commit(acc_full);
+                    in_window = 0;
+                }
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+        }
+    } else {
+        // =============================== producers / epilogue ===============================
+        const int pt = tid - 32;              // 0..511: warps 1..8 synthesise U, warps 9..16 synthesise V
+        const bool is_v = pt >= 256;
+        const int ptl = pt & 255;
+        const int pc = lane & 7;              // this lane's piece of the stage (8 samples): the 8 lanes of a quarter warp = the 8 pieces of one row
+        const int grp = (ptl >> 5) * 4 + (lane >> 3);     // 8-row core matrix: rows 8 grp .. 8 grp + 7 of the CTA's 256 U rows / of the V tile
+        const double unscale = ldexp(1.0, 2 * (tc_exponent(p.amax[0]) + tc_exponent(p.amax[1]) + tc_exponent(p.amax[2])) +
+                                              tc_exponent(p.amax[3]));
+        const uint32_t raw_s = smem_u32(raw_base);
+        RunRows rr;
+        const bool v_active = 8 * grp < BN;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            uint32_t key, last = z_rows;
+            if (!is_v) {
+                const int64_t gu = u0 + 8 * grp + i;
+                key = z_rows | (z_rows << 10) | (z_rows << 20);      // the zero row
+                if (gu < nU) {
+                    const int qa = (int)(gu / p.nB), qb = (int)(gu - (int64_t)qa * p.nB);
+                    int ia, ja, ib, jb;
+                    pair_decode(qa, mA, ia, ja);
+                    pair_decode(qb, mB, ib, jb);
+                    key = (uint32_t)ia | ((uint32_t)(mA + ja) << 10) | ((uint32_t)(2 * mA + ib) << 20);
+                    last = (uint32_t)(2 * mA + jb);
+                }
+            } else {
+                const int gv = v0 + 8 * grp + i;
+                key = z_rows;
+                if (v_active && gv < p.nC) {
+                    int ic, jc;
+                    pair_decode(gv, mC, ic, jc);
+                    key = (uint32_t)(2 * mA + mB + ic);
+                    last = (uint32_t)(2 * mA + mB + jc);
+                }
+            }
+            rr.key[i] = key;
+            rr.last[i] = last * 16u;
+        }
+        run_rows_finish(rr);
+        // destinations: U: tile (8 grp) / 128, row (8 grp) % 128 + i; V: row 8 grp + i; piece pc
+        const uint32_t udst = (uint32_t)(grp >> 4) * RUN_A_TILE + (uint32_t)pc * RUN_LBO_A + (uint32_t)((8 * grp) & 127) * 16;
+        const uint32_t vdst = T * RUN_A_TILE + (uint32_t)pc * lbo_b + (uint32_t)(8 * grp) * 16;
+        const uint32_t dst = is_v ? vdst : udst;
+        const uint32_t stage_s = smem_u32(stage_base);
+        const __half* Zh = reinterpret_cast<const __half*>(p.Z);
+
+        auto issue_chunk = [&](int64_t chunk) {
+            if (chunk < nchunks && pt == 0) {
+                const int slot = (int)(chunk % TC_RAW_SLOTS);
+                const uint32_t bar = smem_u32(&raw_full[slot]);
+                const uint32_t plane_bytes = z_rows * 16;
+                const uint32_t dst0 = raw_s + (uint32_t)slot * raw_bytes;
+                const __half* src0 = Zh + ((k_begin / H_KC + chunk) * H_NP) * (int64_t)z_rows * 8;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(H_NP * plane_bytes) : "memory");
+#pragma unroll
+                for (int part = 0; part < H_NP; ++part)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst0 + (uint32_t)part * plane_stride), "l"(src0 + (int64_t)part * z_rows * 8), "r"(plane_bytes), "r"(bar)
+                                 : "memory");
+            }
+        };
+        issue_chunk(0);
+        issue_chunk(1);
+
+        auto u_prefix = [&](uint32_t rbp, uint32_t key) -> uint4 {
+            const uint4 a = lds128u(rbp + (key & 1023u) * 16u);
+            const uint4 b = lds128u(rbp + ((key >> 10) & 1023u) * 16u);
+            const uint4 c = lds128u(rbp + (key >> 20) * 16u);
+            return hmul8(hmul8(a, b), c);
+        };
+
+        uint32_t acc_phase = 0;
+        int s = 0, rs = 0;
+        uint32_t ph = 0;
+        int64_t in_window = 0;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            asm volatile("bar.sync 1, %0;" ::"n"(RUN2_PROD_WARPS * 32) : "memory");
+            issue_chunk(c + 2);
+            mbar_wait(&raw_full[rs], (uint32_t)((c / TC_RAW_SLOTS) & 1));
+            if (lane == 0) mbar_wait(&empty[s], ph ^ 1);
+            __syncwarp();
+            const uint32_t rbp = raw_s + (uint32_t)rs * raw_bytes + (uint32_t)pc * plane_stride;     // this lane's plane of the slot
+            const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
+            if (!is_v) {   // ---- U: prefixes, then two groups of four rows
+                const uint4 preA = u_prefix(rbp, rr.keyA);
+                const uint4 preB = u_prefix(rbp, rr.keyB);
+#pragma unroll
+                for (int h = 0; h < 8; h += 4) {
+                    uint4 x[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) x[i] = lds128u(rbp + rr.last[h + i]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 pre = sel8((rr.selB >> (h + i)) & 1u, preB, preA);
+                        if ((rr.slow >> (h + i)) & 1u) pre = u_prefix(rbp, rr.key[h + i]);
+                        sts128u(sb + dst + (uint32_t)(h + i) * 16u, hmul8(pre, x[i]));
+                    }
+                }
+            } else if (v_active) {   // ---- V
+                const uint4 preA = lds128u(rbp + rr.keyA * 16u);
+                const uint4 preB = lds128u(rbp + rr.keyB * 16u);
+#pragma unroll
+                for (int h = 0; h < 8; h += 4) {
+                    uint4 y[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) y[i] = lds128u(rbp + rr.last[h + i]);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint4 pre = sel8((rr.selB >> (h + i)) & 1u, preB, preA);
+                        if ((rr.slow >> (h + i)) & 1u) pre = lds128u(rbp + rr.key[h + i] * 16u);
+                        sts128u(sb + dst + (uint32_t)(h + i) * 16u, hmul8(pre, y[i]));
+                    }
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&full[s]);
+            if (++s == NS) { s = 0; ph ^= 1; }
+            if (++rs == TC_RAW_SLOTS) rs = 0;
+            const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+            if (last_of_window) {
+                in_window = 0;
+                mbar_wait(acc_full, acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, reinterpret_cast<float*>(stage_base), unscale, TC_M, (c + 1) == nchunks, 4);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+constexpr int RUN3_THREADS = 32 * (2 + TC_PROD_WARPS);      // MMA issuer, eight producer warps, one loader warp
+__global__ void __launch_bounds__(RUN3_THREADS, 1)
+gram_tc16_run3_kernel(TcParams p) {
+    constexpr int T = 2, H_KC = 64, H_NP = 8;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int BN = p.BN, NS = p.nstages;
+    const int mA = p.mA, mB = p.mB, mC = p.mC;
+
+    const uint32_t lbo_b = (uint32_t)BN * 16 + 16;
+    const uint32_t b_tile_bytes = 8 * lbo_b;
+    const uint32_t stage_bytes = T * RUN_A_TILE + b_tile_bytes;
+    const uint32_t z_rows = (uint32_t)(2 * mA + mB + mC);
+    const uint32_t raw_rows = z_rows + 1;
+    const uint32_t plane_stride = run_plane_stride(raw_rows);
+    const uint32_t raw_bytes = H_NP * plane_stride;
+    uint8_t* stage_base = smem_raw;
+    uint8_t* raw_base = smem_raw + (size_t)NS * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)TC_RAW_SLOTS * raw_bytes);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + NS;
+    uint64_t* acc_full = bars + 2 * NS;
+    uint64_t* acc_empty = bars + 2 * NS + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
+    uint64_t* raw_full = bars + 2 * NS + 3;
+    uint64_t* raw_empty = raw_full + TC_RAW_SLOTS;      // producers -> loader warp: the slot has been read by all eight warps
+
+    const uint32_t tmem_cols_needed = (uint32_t)(T * BN);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], TC_PROD_WARPS);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, TC_PROD_WARPS);
+        for (int i = 0; i < TC_RAW_SLOTS; ++i) {
+            mbar_init(&raw_full[i], 1);
+            mbar_init(&raw_empty[i], TC_PROD_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    for (int i = tid; i < TC_RAW_SLOTS * H_NP * 4; i += RUN3_THREADS) {
+        const int slot = i / (H_NP * 4), e = i % (H_NP * 4);
+        reinterpret_cast<uint32_t*>(raw_base + (size_t)slot * raw_bytes + (size_t)(e >> 2) * plane_stride + (size_t)z_rows * 16)[e & 3] = 0u;
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t k_begin = (int64_t)blockIdx.z * p.rows_per_split;
+    const int64_t k_end = min(p.zpitch, k_begin + p.rows_per_split);
+    const int64_t nchunks = (k_end > k_begin) ? (k_end - k_begin) / H_KC : 0;
+    const int64_t chunks_per_flush = p.flush_rows / H_KC;
+    const int64_t nU = (int64_t)p.nA * p.nB;
+    const int64_t u0 = (int64_t)blockIdx.x * (TC_M * T);
+    const int v0 = blockIdx.y * BN;
+
+    if (warp == 0) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0 && nchunks > 0) {
+            const uint32_t idesc = make_idesc_f16(TC_M, BN);
+            const uint32_t sbo = 128;
+            uint32_t acc_phase = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            int64_t in_window = 0;
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const bool first_of_window = in_window == 0;
+                if (first_of_window && c > 0) {
+                    mbar_wait(acc_empty, acc_phase);
+                    acc_phase ^= 1;
+                    tc_fence_after();
+                }
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(stage_base + (size_t)s * stage_bytes);
+                const uint32_t b_base = sb + T * RUN_A_TILE;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    const uint32_t a_base = sb + (uint32_t)t * RUN_A_TILE;
+                    const uint32_t d = tmem_base + (uint32_t)(t * BN);
+#pragma unroll
+                    for (int j = 0; j < H_KC / 16; ++j) {
+                        const uint32_t ao = (uint32_t)(2 * j) * RUN_LBO_A, bo = (uint32_t)(2 * j) * lbo_b;
+                        const uint32_t acc0 = (first_of_window && j == 0) ? 0u : 1u;
+                        umma_f16(d, make_desc(a_base + ao, RUN_LBO_A, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
+                    }
+                }
+                umma_commit(&empty[s]);
+                const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+                if (last_of_window) {
+                    umma_commit(acc_full);
+                    in_window = 0;
+                }
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1 + TC_PROD_WARPS) {
+        // =============================== loader: keeps the raw-factor ring full (no block barrier among the producers) ===============================
+        if (lane == 0) {
+            const uint32_t raw_s = smem_u32(raw_base);
+            const __half* Zh = reinterpret_cast<const __half*>(p.Z);
+            const uint32_t plane_bytes = z_rows * 16;
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const int slot = (int)(c % TC_RAW_SLOTS);
+                if (c >= TC_RAW_SLOTS) mbar_wait(&raw_empty[slot], (uint32_t)((c / TC_RAW_SLOTS - 1) & 1));
+                const uint32_t bar = smem_u32(&raw_full[slot]);
+                const uint32_t dst0 = raw_s + (uint32_t)slot * raw_bytes;
+                const __half* src0 = Zh + ((k_begin / H_KC + c) * H_NP) * (int64_t)z_rows * 8;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(H_NP * plane_bytes) : "memory");
+#pragma unroll
+                for (int part = 0; part < H_NP; ++part)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(dst0 + (uint32_t)part * plane_stride), "l"(src0 + (int64_t)part * z_rows * 8), "r"(plane_bytes), "r"(bar)
+                                 : "memory");
+            }
+        }
+    } else {
+        // =============================== producers / epilogue ===============================
+        const int pt = tid - 32;              // 0..255
+        const int pc = lane & 7;              // this lane's piece of the stage (8 samples): the 8 lanes of a quarter warp = the 8 pieces of one row
+        const int grp = (pt >> 5) * 4 + (lane >> 3);     // 8-row core matrix: U rows 8 grp .. 8 grp + 7 of the CTA's 256, V rows likewise
+        const double unscale = ldexp(1.0, 2 * (tc_exponent(p.amax[0]) + tc_exponent(p.amax[1]) + tc_exponent(p.amax[2])) +
+                                              tc_exponent(p.amax[3]));
+        const uint32_t raw_s = smem_u32(raw_base);
+        RunRows ur, vr;
+        const bool v_active = 8 * grp < BN;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t gu = u0 + 8 * grp + i;
+            uint32_t key = z_rows | (z_rows << 10) | (z_rows << 20), last = z_rows;      // the zero row
+            if (gu < nU) {
+                const int qa = (int)(gu / p.nB), qb = (int)(gu - (int64_t)qa * p.nB);
+                int ia, ja, ib, jb;
+                pair_decode(qa, mA, ia, ja);
+                pair_decode(qb, mB, ib, jb);
+                key = (uint32_t)ia | ((uint32_t)(mA + ja) << 10) | ((uint32_t)(2 * mA + ib) << 20);
+                last = (uint32_t)(2 * mA + jb);
+            }
+            ur.key[i] = key;
+            ur.last[i] = last * 16u;
+            const int gv = v0 + 8 * grp + i;
+            uint32_t vkey = z_rows, vlast = z_rows;
+            if (v_active && gv < p.nC) {
+                int ic, jc;
+                pair_decode(gv, mC, ic, jc);
+                vkey = (uint32_t)(2 * mA + mB + ic);
+                vlast = (uint32_t)(2 * mA + mB + jc);
+            }
+            vr.key[i] = vkey;
+            vr.last[i] = vlast * 16u;
+        }
+        run_rows_finish(ur);
+        run_rows_finish(vr);
+        // destinations: tile (8 grp) / 128, row (8 grp) % 128 + i; piece pc
+        const uint32_t udst = (uint32_t)(grp >> 4) * RUN_A_TILE + (uint32_t)pc * RUN_LBO_A + (uint32_t)((8 * grp) & 127) * 16;
+        const uint32_t vdst = T * RUN_A_TILE + (uint32_t)pc * lbo_b + (uint32_t)(8 * grp) * 16;
+        const uint32_t stage_s = smem_u32(stage_base);
+        const __half* Zh = reinterpret_cast<const __half*>(p.Z);
+
+        auto u_prefix = [&](uint32_t rbp, uint32_t key) -> uint4 {
+            const uint4 a = lds128u(rbp + (key & 1023u) * 16u);
+            const uint4 b = lds128u(rbp + ((key >> 10) & 1023u) * 16u);
+            const uint4 c = lds128u(rbp + (key >> 20) * 16u);
+            return hmul8(hmul8(a, b), c);
+        };
+
+        uint32_t acc_phase = 0;
+        int s = 0, rs = 0;
+        uint32_t ph = 0;
+        int64_t in_window = 0;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            mbar_wait(&raw_full[rs], (uint32_t)((c / TC_RAW_SLOTS) & 1));
+            if (lane == 0) mbar_wait(&empty[s], ph ^ 1);
+            __syncwarp();
+            const uint32_t rbp = raw_s + (uint32_t)rs * raw_bytes + (uint32_t)pc * plane_stride;     // this lane's plane of the slot
+            const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
+            {   // ---- every load of the stage first (24 LDS.128 in flight per thread), then the products and the stores
+                uint4 x[8], y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = lds128u(rbp + ur.last[i]);
+                const uint4 preA = u_prefix(rbp, ur.keyA);
+                const uint4 preB = u_prefix(rbp, ur.keyB);
+                uint4 vpreA = make_uint4(0u, 0u, 0u, 0u), vpreB = vpreA;
+                if (v_active) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] = lds128u(rbp + vr.last[i]);
+                    vpreA = lds128u(rbp + vr.keyA * 16u);
+                    vpreB = lds128u(rbp + vr.keyB * 16u);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint4 pre = sel8((ur.selB >> i) & 1u, preB, preA);
+                    if ((ur.slow >> i) & 1u) pre = u_prefix(rbp, ur.key[i]);
+                    sts128u(sb + udst + (uint32_t)i * 16u, hmul8(pre, x[i]));
+                }
+                if (v_active) {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        uint4 pre = sel8((vr.selB >> i) & 1u, vpreB, vpreA);
+                        if ((vr.slow >> i) & 1u) pre = lds128u(rbp + vr.key[i] * 16u);
+                        sts128u(sb + vdst + (uint32_t)i * 16u, hmul8(pre, y[i]));
+                    }
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&full[s]);
+                mbar_arrive(&raw_empty[rs]);        // every load of this warp from the slot has returned (the stores above used them)
+            }
+            if (++s == NS) { s = 0; ph ^= 1; }
+            if (++rs == TC_RAW_SLOTS) rs = 0;
+            const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+            if (last_of_window) {
+                in_window = 0;
+                mbar_wait(acc_full, acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, reinterpret_cast<float*>(stage_base), unscale, TC_M, (c + 1) == nchunks);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);
+                // the drain's transpose scratch aliases the operand stages: nobody writes the next stage before everybody has drained
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+static size_t tc16_run_smem_bytes(int mA, int mB, int mC, int BN, int NS) {
+    const size_t stage = 2 * (size_t)RUN_A_TILE + 8 * ((size_t)BN * 16 + 16);
+    const size_t plane = run_plane_stride((uint32_t)(2 * mA + mB + mC + 1));
+    return NS * stage + TC_RAW_SLOTS * 8 * plane + (2 * NS + 2) * 8 + 16 + 32 + 32;      // + the raw_empty barriers of the loader-warp variant
 }
 
 static size_t tc16_smem_bytes(int mA, int mB, int mC, int BN, int T, int NS, int kc) {
@@ -1698,12 +2191,26 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     if (f16) {
         using Kern16 = void (*)(TcParams);
         if (kc16 == 64 && p.T == 2 && z_rows < 1023 && getenv("TN_TC16_RUN") && atoi(getenv("TN_TC16_RUN")) != 0) {
-            TN_SMEM(gram_tc16_run_kernel, smem);
-            dim3 gridr((unsigned)gx, (unsigned)gy, (unsigned)ks);
-            gram_tc16_run_kernel<<<gridr, TC_THREADS, smem, st>>>(p);
-            TN_LAUNCH_CHECK();
-            TN_CUDA(cudaFreeAsync(Z, st));
-            return TN_OK;
+            int NSR = 4;
+            while (NSR >= 2 && tc16_run_smem_bytes(A.m, B.m, C.m, p.BN, NSR) > 226 * 1024) --NSR;
+            if (NSR >= 2) {
+                p.nstages = NSR;
+                const size_t rsmem = tc16_run_smem_bytes(A.m, B.m, C.m, p.BN, NSR);
+                dim3 gridr((unsigned)gx, (unsigned)gy, (unsigned)ks);
+                if (atoi(getenv("TN_TC16_RUN")) == 3) {
+                    TN_SMEM(gram_tc16_run3_kernel, rsmem);
+                    gram_tc16_run3_kernel<<<gridr, RUN3_THREADS, rsmem, st>>>(p);
+                } else if (atoi(getenv("TN_TC16_RUN")) == 2) {
+                    TN_SMEM(gram_tc16_run2_kernel, rsmem);
+                    gram_tc16_run2_kernel<<<gridr, RUN2_THREADS, rsmem, st>>>(p);
+                } else {
+                    TN_SMEM(gram_tc16_run_kernel, rsmem);
+                    gram_tc16_run_kernel<<<gridr, TC_THREADS, rsmem, st>>>(p);
+                }
+                TN_LAUNCH_CHECK();
+                TN_CUDA(cudaFreeAsync(Z, st));
+                return TN_OK;
+            }
         }
         Kern16 k16 = (kc16 == 64) ? ((p.T == 2) ? gram_tc16_kernel<2, 64> : gram_tc16_kernel<1, 64>)
                                   : ((p.T == 2) ? gram_tc16_kernel<2, 32> : gram_tc16_kernel<1, 32>);

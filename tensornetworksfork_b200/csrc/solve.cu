@@ -1081,7 +1081,9 @@ extern "C" int tn_cholesky_factor(double* A, int64_t lda, int64_t P, int tensor_
     }
     float* X = nullptr;
     TN_CUDA(cudaMallocAsync(&X, (size_t)syrk_tc_work_floats(P, (int)NBO) * sizeof(float), st));
+    syrk_tc_set_passes(tensor_core == 2 ? 1 : 3);        // 2: one TF32 pass per K step (preconditioner-grade factor)
     const int rc = cholesky_factorize(A, lda, P, work, info, st, X, NBO);
+    syrk_tc_set_passes(3);
     cudaFreeAsync(X, st);
     return rc;
 }

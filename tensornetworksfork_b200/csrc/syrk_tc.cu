@@ -60,6 +60,9 @@ syrk_tc_convert_kernel(const double* __restrict__ A, int64_t lda, int64_t c0, in
     }
 }
 
+// SPLIT = true: 3xTF32 (hi/lo split, three MMAs per K step).  SPLIT = false: one TF32 MMA per K step on the fp32 panel as it
+// lands (the tensor core ignores the low 13 mantissa bits) -- the producers only copy; for factors that merely precondition.
+template <bool SPLIT>
 __global__ void __launch_bounds__(ST_THREADS, 1)
 syrk_tc_kernel(SyrkTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -127,8 +130,10 @@ syrk_tc_kernel(SyrkTcParams p) {
                     for (int j = 0; j < ST_KC / 8; ++j) {
                         const uint32_t ao = (uint32_t)(2 * j) * lbo_a, bo = (uint32_t)(2 * j) * lbo_b;
                         umma_tf32(d, make_desc(a_hi + ao, lbo_a, sbo), make_desc(b_hi + bo, lbo_b, sbo), idesc, (c == 0 && j == 0) ? 0u : 1u);
-                        umma_tf32(d, make_desc(a_hi + ao, lbo_a, sbo), make_desc(b_lo + bo, lbo_b, sbo), idesc, 1u);
-                        umma_tf32(d, make_desc(a_lo + ao, lbo_a, sbo), make_desc(b_hi + bo, lbo_b, sbo), idesc, 1u);
+                        if (SPLIT) {
+                            umma_tf32(d, make_desc(a_hi + ao, lbo_a, sbo), make_desc(b_lo + bo, lbo_b, sbo), idesc, 1u);
+                            umma_tf32(d, make_desc(a_lo + ao, lbo_a, sbo), make_desc(b_hi + bo, lbo_b, sbo), idesc, 1u);
+                        }
                     }
                 }
                 umma_commit(&empty[s]);
@@ -172,15 +177,17 @@ syrk_tc_kernel(SyrkTcParams p) {
         for (int c = 0; c < nchunks; ++c) {
             asm volatile("cp.async.wait_group 1;" ::: "memory");        // this thread's pieces of chunk c have landed
             const uint32_t sb = stage_s + (uint32_t)(c % ST_NS) * ST_STAGE + off0;
-            float4 v[8];
+            if (SPLIT) {
+                float4 v[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) v[u] = lds128(sb + (uint32_t)(u >> 1) * 256 + (uint32_t)(u & 1) * 2 * lbo);
+                for (int u = 0; u < 8; ++u) v[u] = lds128(sb + (uint32_t)(u >> 1) * 256 + (uint32_t)(u & 1) * 2 * lbo);
 #pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t a = sb + (uint32_t)(u >> 1) * 256 + (uint32_t)(u & 1) * 2 * lbo;
-                const float4 h = make_float4(tf32_rn(v[u].x), tf32_rn(v[u].y), tf32_rn(v[u].z), tf32_rn(v[u].w));
-                sts128(a, h);
-                sts128(a + lo_off, make_float4(v[u].x - h.x, v[u].y - h.y, v[u].z - h.z, v[u].w - h.w));
+                for (int u = 0; u < 8; ++u) {
+                    const uint32_t a = sb + (uint32_t)(u >> 1) * 256 + (uint32_t)(u & 1) * 2 * lbo;
+                    const float4 h = make_float4(tf32_rn(v[u].x), tf32_rn(v[u].y), tf32_rn(v[u].z), tf32_rn(v[u].w));
+                    sts128(a, h);
+                    sts128(a + lo_off, make_float4(v[u].x - h.x, v[u].y - h.y, v[u].z - h.z, v[u].w - h.w));
+                }
             }
             fence_proxy_async();
             __syncwarp();
@@ -247,11 +254,15 @@ int64_t syrk_tc_work_floats(int64_t n, int kb) {
 
 // C = A[c0:, c0:] -= A[c0:, k0:k0+kb] * A[c0:, k0:k0+kb]^T on the lower 256 x 256 tiles.  X: syrk_tc_work_floats(P - c0, kb).
 // col_limit > 0 restricts the update to the first col_limit columns of C (a multiple of 256, or everything up to P).
+static thread_local int g_syrk_passes = 3;
+void syrk_tc_set_passes(int passes) { g_syrk_passes = (passes == 1) ? 1 : 3; }
+
 int syrk_tc_update(double* A, int64_t lda, int64_t P, int64_t c0, int64_t k0, int kb, float* X, const int* info, cudaStream_t st,
                    int64_t col_limit) {
     const int64_t n = P - c0;
     if (n <= 0 || kb <= 0) return TN_OK;
-    TN_SMEM(syrk_tc_kernel, ST_SMEM);
+    TN_SMEM(syrk_tc_kernel<true>, ST_SMEM);
+    TN_SMEM(syrk_tc_kernel<false>, ST_SMEM);
     SyrkTcParams p;
     p.pitch = ceil_div64(kb, ST_KC) * ST_KC;
     const int64_t nt = ceil_div64(n, ST_TILE);
@@ -275,7 +286,8 @@ int syrk_tc_update(double* A, int64_t lda, int64_t P, int64_t c0, int64_t k0, in
     p.nct = (int)nct;
     const int64_t ntiles = nct * nt - nct * (nct - 1) / 2;
     TN_CHECK_ARG(ntiles <= 0x7fffffff, "syrk_tc_update: grid too large");
-    syrk_tc_kernel<<<(unsigned)ntiles, ST_THREADS, ST_SMEM, st>>>(p);
+    if (g_syrk_passes == 1) syrk_tc_kernel<false><<<(unsigned)ntiles, ST_THREADS, ST_SMEM, st>>>(p);
+    else syrk_tc_kernel<true><<<(unsigned)ntiles, ST_THREADS, ST_SMEM, st>>>(p);
     TN_LAUNCH_CHECK();
     return TN_OK;
 }

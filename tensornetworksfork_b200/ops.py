@@ -561,7 +561,8 @@ def _poll(op, poll_every):
 
 @_op
 def cholesky_factor(A, tensor_core=False):
-    """In place: lower triangle of A (P x lda) <- its Cholesky factor.  Returns (work, info) for cholesky_apply / cg."""
+    """In place: lower triangle of A (P x lda) <- its Cholesky factor.  Returns (work, info) for cholesky_apply / cg.
+    tensor_core: False / 0 = fp64, True / 1 = 3xTF32 trailing updates, 2 = one TF32 pass (a factor that only preconditions)."""
     lib = _lib.load()
     P = A.shape[0]
     _need_cuda(A)
@@ -569,7 +570,7 @@ def cholesky_factor(A, tensor_core=False):
         raise _lib.TnError(f"system matrix must be ({P}, >= {P}) with unit inner stride, got {tuple(A.shape)} / {A.stride()}")
     work = torch.empty((lib.tn_cholesky_work_elems(P),), dtype=torch.float64, device=A.device)
     info = torch.zeros((1,), dtype=torch.int32, device=A.device)
-    _lib.check(lib.tn_cholesky_factor(_p(A), A.stride(0), P, 1 if tensor_core else 0, _p(work), ctypes.c_void_p(info.data_ptr()),
+    _lib.check(lib.tn_cholesky_factor(_p(A), A.stride(0), P, int(tensor_core), _p(work), ctypes.c_void_p(info.data_ptr()),
                                       _stream()), "tn_cholesky_factor")
     return work, info
 

@@ -13,6 +13,7 @@ so ``node_states()/load_node_states()`` snapshots and EarlyStopping keep working
 change of a core is noticed through tensor identity/version and drops the cached environments,
 the way ``set_input``/``reset_stacks`` do in the reference (network.py:78-81, 329-345).
 """
+import os
 import time
 
 import torch
@@ -156,6 +157,8 @@ class TensorNetwork:
         self.refine_rtol = 1e-11        # stopping test of the refinement: estimated relative forward error of the step ...
         self.refine_accept = 1e-9       # ... and what it must reach for the step to be used, else the site is redone with an fp64 Gram
         self.refine_max_iter = 30
+        # tensor-core factorisation of the preconditioner: 1 = 3xTF32 trailing updates, 2 = one TF32 pass (TN_FACTOR_ONE_PASS=1)
+        self.factor_passes_code = 2 if os.environ.get("TN_FACTOR_ONE_PASS", "0") not in ("", "0") else 1
         self._refine_floor = -1.0       # ridge values at or below this needed the fp64 Gram; go there directly
         # fp32 accumulation window (rows) of the tensor-core Gram when it only preconditions the exact refinement: longer = faster,
         # coarser (None = the library default of 2048, the window the stand-alone accuracy figures of the Gram are quoted for)
@@ -689,7 +692,7 @@ class TensorNetwork:
         A = ops.gram_expand(M, m_pos, role_of_pos, sigma, ridge)
         rhs = ops.rhs_prepare(b, theta, sigma, ridge)
         tensor_core = self.solve_mode != "fp64" and P >= self.mixed_min_P
-        work, info = ops.cholesky_factor(A, tensor_core=tensor_core)
+        work, info = ops.cholesky_factor(A, tensor_core=(self.factor_passes_code if tensor_core else 0))
         op = ops.Operator(P, factors=prob["gram"], w=prob["gw"], rows=prob["grows"], group=self.process_group, sigma=sigma, ridge=ridge)
         x, stats = ops.cg(op, rhs, precond=(A, work, info), max_iter=self.refine_max_iter, rtol=self.refine_rtol)
         bad = int(info.item())

@@ -259,3 +259,36 @@ def test_env_update_warp_per_tile_bulk_copy_path(S, C, rin, f, rout, fmap):
         big[:, 2:2 + rin] = e
         got2 = ops.env_update(big[:, 2:2 + rin], fx, T(core), rows, cdiv=C)
         assert torch.equal(got2, torch.as_tensor(got, device="cuda"))
+
+
+@pytest.mark.parametrize("S,ma,mb,mc,V,fmap", [(20011, 38, 29, 38, 1, None), (9000, 38, 6, 38, 1, "poly"), (4100, 24, 12, 17, 1, None),
+                                              (3000, 40, 3, 40, 1, None), (2500, 9, 60, 8, 1, None), (1300, 38, 4, 38, 3, "poly"), (37, 33, 5, 33, 1, None)])
+def test_rhs_large_core_register_blocked(S, ma, mb, mc, V, fmap, monkeypatch):
+    """Right-hand side / J^T u for cores with P > 4096 and outer factors <= 40 wide (gram.cu::rhs_big_kernel: a warp owns one
+    middle index and its whole output block in registers, the middle factor enters as a per-row scalar): against numpy and
+    against the GEMM-shaped kernel it replaces; ragged row counts, a mapped middle factor, class rows sharing a site input,
+    accumulation into an existing vector, fewer rows than one split."""
+    rng = np.random.default_rng(S + ma)
+    rows = S * V
+    Fa = rng.normal(size=(rows, ma))
+    X = rng.uniform(-1, 1, size=(S, max(mb, 4)))
+    Fc = rng.normal(size=(S, mc))
+    w = rng.normal(size=rows)
+    if fmap is None:
+        fb = Factor(T(X[:, :mb].copy()), m=mb, div=V)
+        phi = X[:, :mb]
+    elif fmap == "poly":
+        fb = Factor(T(X), m=mb, map_kind=ops.MAP_POLY, col=1, div=V)
+        phi = np.stack([X[:, 1] ** d for d in range(mb)], 1)
+    else:
+        fb = Factor(T(X), m=mb, map_kind=ops.MAP_SINCOS, col=2, div=V)
+        phi = np.stack([np.cos(0.5 * np.pi * X[:, 2]), np.sin(0.5 * np.pi * X[:, 2])], 1)
+    fa, fc = Factor(T(Fa), m=ma), Factor(T(Fc), m=mc, div=V)
+    want = np.einsum("r,ra,rp,rb->apb", w, Fa, np.repeat(phi, V, axis=0), np.repeat(Fc, V, axis=0)).reshape(-1)
+    got = ops.rhs(fa, fb, fc, T(w), rows)
+    assert gu.relerr(got.cpu().numpy(), want) < 1e-12
+    twice = ops.rhs(fa, fb, fc, T(w), rows, b=got.clone(), accumulate=True)
+    assert gu.relerr(twice.cpu().numpy(), 2 * want) < 1e-12
+    monkeypatch.setenv("TN_RHS_NO_BIG", "1")
+    old = ops.rhs(fa, fb, fc, T(w), rows)
+    assert gu.relerr(old.cpu().numpy(), want) < 1e-12
