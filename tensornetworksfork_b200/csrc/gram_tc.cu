@@ -58,6 +58,8 @@ struct TcParams {
     int nstages;
     int split;        // 1 = 3xTF32, 0 = TF32
     int flush_rows;   // rows accumulated in fp32 before a drain to fp64 (multiple of TC_KC)
+    int dbg;          // TN_TC16_DBG (measurement only, wrong results): bit 0 = producers skip the synthesis, bit 1 = no MMAs are issued,
+                      // bit 2 = no fence.proxy.async, bit 3 = no raw-factor ring, bit 4 = no producer barrier, bit 5 = no drain
     int planar;       // 1: Z is staged piece-planar, Z[((s/16)*4 + (s%16)/4) * z_rows + row][s%4] (see gram_tc_kernel<.., PLANAR>)
 };
 
@@ -102,8 +104,10 @@ __device__ __forceinline__ int tc_exponent(unsigned long long bits) {
 // ---- pre-pass: factors (fp64, sample-major, possibly mapped / shared by V rows) -> Z (fp32, feature-major)
 __global__ void __launch_bounds__(256)
 tc_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict__ w, int64_t rows, float* __restrict__ Z,
-                int64_t zpitch, const unsigned long long* __restrict__ amax, int planar = 0) {
-    // planar: 0 = row-major fp32, 1 = planes of 4 fp32 samples (16 B per Z row), 2 = planes of 8 fp16 samples (16 B per Z row)
+                int64_t zpitch, const unsigned long long* __restrict__ amax, int planar = 0, int64_t plane_halves = 0) {
+    // planar: 0 = row-major fp32, 1 = planes of 4 fp32 samples (16 B per Z row), 2 = planes of 8 fp16 samples (16 B per Z row),
+    // 3 = as 2 with every plane padded to plane_halves fp16 (the shared-memory plane stride of gram_tc16_run_kernel): a 64-sample
+    //     chunk is one contiguous image of a raw-factor slot (8 planes; the zero row and the padding come from a memset of Z)
     __half* Zh = reinterpret_cast<__half*>(Z);
     __shared__ float tile[32][33];
     const double sa = ldexp(1.0, -tc_exponent(amax[0])), sb = ldexp(1.0, -tc_exponent(amax[1]));
@@ -136,11 +140,12 @@ tc_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict_
             const int64_t zr = 2 * mA + mB + mC;                         // Z rows
             // row-major: Z[row][s];  piece-planar: the 16 bytes (4 samples) of every row of one piece are contiguous
             auto at = [&](int64_t row) -> int64_t {
+                if (planar == 3) return (s >> 3) * plane_halves + row * 8 + (s & 7);
                 if (planar == 2) return (((s >> 5) * 4 + ((s >> 3) & 3)) * zr + row) * 8 + (s & 7);
                 return planar ? ((((s >> 4) * 4 + ((s >> 2) & 3)) * zr + row) * 4 + (s & 3)) : (row * zpitch + s);
             };
             const float vw = (i < mA && s < rows) ? v * (float)((w ? w[s] : 1.0) * sw) : 0.f;
-            if (planar == 2) {
+            if (planar >= 2) {
                 Zh[at(mA + i)] = __float2half_rn(v);
                 if (i < mA) Zh[at(i)] = __float2half_rn(vw);
             } else {
@@ -861,7 +866,7 @@ gram_tc16_run_kernel(TcParams p) {
                     for (int j = 0; j < H_KC / 16; ++j) {
                         const uint32_t ao = (uint32_t)(2 * j) * RUN_LBO_A, bo = (uint32_t)(2 * j) * lbo_b;
                         const uint32_t acc0 = (first_of_window && j == 0) ? 0u : 1u;
-                        umma_f16(d, make_desc(a_base + ao, RUN_LBO_A, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
+                        if (!(p.dbg & 2)) umma_f16(d, make_desc(a_base + ao, RUN_LBO_A, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
                     }
                 }
                 umma_commit(&empty[s]);
@@ -917,22 +922,21 @@ gram_tc16_run_kernel(TcParams p) {
         const __half* Zh = reinterpret_cast<const __half*>(p.Z);
 
         auto issue_chunk = [&](int64_t chunk) {
+            // one thread, ONE bulk copy: the pre-pass stores a chunk as the image of a slot (planes padded to the slot's plane stride)
             if (chunk < nchunks && pt == 0) {
                 const int slot = (int)(chunk % TC_RAW_SLOTS);
                 const uint32_t bar = smem_u32(&raw_full[slot]);
-                const uint32_t plane_bytes = z_rows * 16;
                 const uint32_t dst0 = raw_s + (uint32_t)slot * raw_bytes;
-                const __half* src0 = Zh + ((k_begin / H_KC + chunk) * H_NP) * (int64_t)z_rows * 8;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(H_NP * plane_bytes) : "memory");
-#pragma unroll
-                for (int part = 0; part < H_NP; ++part)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dst0 + (uint32_t)part * plane_stride), "l"(src0 + (int64_t)part * z_rows * 8), "r"(plane_bytes), "r"(bar)
-                                 : "memory");
+                const __half* src0 = Zh + (k_begin / H_KC + chunk) * (int64_t)(raw_bytes / 2);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(raw_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst0), "l"(src0), "r"(raw_bytes), "r"(bar) : "memory");
             }
         };
-        issue_chunk(0);
-        issue_chunk(1);
+        if (!(p.dbg & 8)) {
+            issue_chunk(0);
+            issue_chunk(1);
+        }
 
         auto u_prefix = [&](uint32_t rbp, uint32_t key) -> uint4 {
             const uint4 a = lds128u(rbp + (key & 1023u) * 16u);
@@ -946,13 +950,16 @@ gram_tc16_run_kernel(TcParams p) {
         uint32_t ph = 0;
         int64_t in_window = 0;
         for (int64_t c = 0; c < nchunks; ++c) {
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");
-            issue_chunk(c + 2);
-            mbar_wait(&raw_full[rs], (uint32_t)((c / TC_RAW_SLOTS) & 1));
+            if (!(p.dbg & 16)) asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");
+            if (!(p.dbg & 8)) {
+                issue_chunk(c + 2);
+                mbar_wait(&raw_full[rs], (uint32_t)((c / TC_RAW_SLOTS) & 1));
+            }
             if (lane == 0) mbar_wait(&empty[s], ph ^ 1);
             __syncwarp();
             const uint32_t rbp = raw_s + (uint32_t)rs * raw_bytes + (uint32_t)pc * plane_stride;     // this lane's plane of the slot
             const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
+            if (!(p.dbg & 1)) {
             {   // ---- U: prefixes, then eight rows
                 const uint4 preA = u_prefix(rbp, ur.keyA);
                 const uint4 preB = u_prefix(rbp, ur.keyB);
@@ -979,7 +986,8 @@ gram_tc16_run_kernel(TcParams p) {
                     sts128u(sb + vdst + (uint32_t)i * 16u, hmul8(pre, y[i]));
                 }
             }
-            fence_proxy_async();
+            }
+            if (!(p.dbg & 4)) fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(&full[s]);
             if (++s == NS) { s = 0; ph ^= 1; }
@@ -990,493 +998,10 @@ gram_tc16_run_kernel(TcParams p) {
                 mbar_wait(acc_full, acc_phase);
                 acc_phase ^= 1;
                 tc_fence_after();
-                drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, reinterpret_cast<float*>(stage_base), unscale, TC_M, (c + 1) == nchunks);
+                if (!(p.dbg & 32)) drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, reinterpret_cast<float*>(stage_base), unscale, TC_M, (c + 1) == nchunks);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, tmem_cols);
-    }
-}
-
-constexpr int RUN2_PROD_WARPS = 16;          // warps 1..8 synthesise U, warps 9..16 synthesise V: half the dependent work per warp, twice the warps to hide latency
-constexpr int RUN2_THREADS = 32 + RUN2_PROD_WARPS * 32;
-__global__ void __launch_bounds__(RUN2_THREADS, 1)
-gram_tc16_run2_kernel(TcParams p) {
-    constexpr int T = 2, H_KC = 64, H_NP = 8;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int BN = p.BN, NS = p.nstages;
-    const int mA = p.mA, mB = p.mB, mC = p.mC;
-
-    const uint32_t lbo_b = (uint32_t)BN * 16 + 16;
-    const uint32_t b_tile_bytes = 8 * lbo_b;
-    const uint32_t stage_bytes = T * RUN_A_TILE + b_tile_bytes;
-    const uint32_t z_rows = (uint32_t)(2 * mA + mB + mC);
-    const uint32_t raw_rows = z_rows + 1;
-    const uint32_t plane_stride = run_plane_stride(raw_rows);
-    const uint32_t raw_bytes = H_NP * plane_stride;
-    uint8_t* stage_base = smem_raw;
-    uint8_t* raw_base = smem_raw + (size_t)NS * stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)TC_RAW_SLOTS * raw_bytes);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + NS;
-    uint64_t* acc_full = bars + 2 * NS;
-    uint64_t* acc_empty = bars + 2 * NS + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
-    uint64_t* raw_full = bars + 2 * NS + 3;
-
-    const uint32_t tmem_cols_needed = (uint32_t)(T * BN);
-    uint32_t tmem_cols = 32;
-    while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
-
-    if (tid == 0) {
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(&full[s], RUN2_PROD_WARPS);
-            mbar_init(&empty[s], 1);
-        }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, RUN2_PROD_WARPS);
-        for (int i = 0; i < TC_RAW_SLOTS; ++i) mbar_init(&raw_full[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < TC_RAW_SLOTS * H_NP * 4; i += RUN2_THREADS) {
-        const int slot = i / (H_NP * 4), e = i % (H_NP * 4);
-        reinterpret_cast<uint32_t*>(raw_base + (size_t)slot * raw_bytes + (size_t)(e >> 2) * plane_stride + (size_t)z_rows * 16)[e & 3] = 0u;
-    }
-    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int64_t k_begin = (int64_t)blockIdx.z * p.rows_per_split;
-    const int64_t k_end = min(p.zpitch, k_begin + p.rows_per_split);
-    const int64_t nchunks = (k_end > k_begin) ? (k_end - k_begin) / H_KC : 0;
-    const int64_t chunks_per_flush = p.flush_rows / H_KC;
-    const int64_t nU = (int64_t)p.nA * p.nB;
-    const int64_t u0 = (int64_t)blockIdx.x * (TC_M * T);
-    const int v0 = blockIdx.y * BN;
-
-    if (warp == 0) {
-        // =============================== MMA issuer ===============================
-        if (lane == 0 && nchunks > 0) {
-            const uint32_t idesc = make_idesc_f16(TC_M, BN);
-            const uint32_t sbo = 128;
-            uint32_t acc_phase = 0;
-            int s = 0;
-            uint32_t ph = 0;
-            int64_t in_window = 0;
-            for (int64_t c = 0; c < nchunks; ++c) {
-                const bool first_of_window = in_window == 0;
-                if (first_of_window && c > 0) {
-                    mbar_wait(acc_empty, acc_phase);
-                    acc_phase ^= 1;
-                    tc_fence_after();
-                }
-                mbar_wait(&full[s], ph);
-                tc_fence_after();
-                const uint32_t sb = smem_u32(stage_base + (size_t)s * stage_bytes);
-                const uint32_t b_base = sb + T * RUN_A_TILE;
-#pragma unroll
-                for (int t = 0; t < T; ++t) {
-                    const uint32_t a_base = sb + (uint32_t)t * RUN_A_TILE;
-                    const uint32_t d = tmem_base + (uint32_t)(t * BN);
-#pragma unroll
-                    for (int j = 0; j < H_KC / 16; ++j) {
-                        const uint32_t ao = (uint32_t)(2 * j) * RUN_LBO_A, bo = (uint32_t)(2 * j) * lbo_b;
-                        const uint32_t acc0 = (first_of_window && j == 0) ? 0u : 1u;
-                        umma_f16(d, make_desc(a_base + ao, RUN_LBO_A, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
-                    }
-                }
-                umma_commit(&empty[s]);
-                const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
-                if (last_of_window) {
-                    umma_commit(acc_full);
-                    in_window = 0;
-                }
-                if (++s == NS) { s = 0; ph ^= 1; }
-            }
-        }
-    } else {
-        // =============================== producers / epilogue ===============================
-        const int pt = tid - 32;              // 0..511: warps 1..8 synthesise U, warps 9..16 synthesise V
-        const bool is_v = pt >= 256;
-        const int ptl = pt & 255;
-        const int pc = lane & 7;              // this lane's piece of the stage (8 samples): the 8 lanes of a quarter warp = the 8 pieces of one row
-        const int grp = (ptl >> 5) * 4 + (lane >> 3);     // 8-row core matrix: rows 8 grp .. 8 grp + 7 of the CTA's 256 U rows / of the V tile
-        const double unscale = ldexp(1.0, 2 * (tc_exponent(p.amax[0]) + tc_exponent(p.amax[1]) + tc_exponent(p.amax[2])) +
-                                              tc_exponent(p.amax[3]));
-        const uint32_t raw_s = smem_u32(raw_base);
-        RunRows rr;
-        const bool v_active = 8 * grp < BN;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            uint32_t key, last = z_rows;
-            if (!is_v) {
-                const int64_t gu = u0 + 8 * grp + i;
-                key = z_rows | (z_rows << 10) | (z_rows << 20);      // the zero row
-                if (gu < nU) {
-                    const int qa = (int)(gu / p.nB), qb = (int)(gu - (int64_t)qa * p.nB);
-                    int ia, ja, ib, jb;
-                    pair_decode(qa, mA, ia, ja);
-                    pair_decode(qb, mB, ib, jb);
-                    key = (uint32_t)ia | ((uint32_t)(mA + ja) << 10) | ((uint32_t)(2 * mA + ib) << 20);
-                    last = (uint32_t)(2 * mA + jb);
-                }
-            } else {
-                const int gv = v0 + 8 * grp + i;
-                key = z_rows;
-                if (v_active && gv < p.nC) {
-                    int ic, jc;
-                    pair_decode(gv, mC, ic, jc);
-                    key = (uint32_t)(2 * mA + mB + ic);
-                    last = (uint32_t)(2 * mA + mB + jc);
-                }
-            }
-            rr.key[i] = key;
-            rr.last[i] = last * 16u;
-        }
-        run_rows_finish(rr);
-        // destinations: U: tile (8 grp) / 128, row (8 grp) % 128 + i; V: row 8 grp + i; piece pc
-        const uint32_t udst = (uint32_t)(grp >> 4) * RUN_A_TILE + (uint32_t)pc * RUN_LBO_A + (uint32_t)((8 * grp) & 127) * 16;
-        const uint32_t vdst = T * RUN_A_TILE + (uint32_t)pc * lbo_b + (uint32_t)(8 * grp) * 16;
-        const uint32_t dst = is_v ? vdst : udst;
-        const uint32_t stage_s = smem_u32(stage_base);
-        const __half* Zh = reinterpret_cast<const __half*>(p.Z);
-
-        auto issue_chunk = [&](int64_t chunk) {
-            if (chunk < nchunks && pt == 0) {
-                const int slot = (int)(chunk % TC_RAW_SLOTS);
-                const uint32_t bar = smem_u32(&raw_full[slot]);
-                const uint32_t plane_bytes = z_rows * 16;
-                const uint32_t dst0 = raw_s + (uint32_t)slot * raw_bytes;
-                const __half* src0 = Zh + ((k_begin / H_KC + chunk) * H_NP) * (int64_t)z_rows * 8;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(H_NP * plane_bytes) : "memory");
-#pragma unroll
-                for (int part = 0; part < H_NP; ++part)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dst0 + (uint32_t)part * plane_stride), "l"(src0 + (int64_t)part * z_rows * 8), "r"(plane_bytes), "r"(bar)
-                                 : "memory");
-            }
-        };
-        issue_chunk(0);
-        issue_chunk(1);
-
-        auto u_prefix = [&](uint32_t rbp, uint32_t key) -> uint4 {
-            const uint4 a = lds128u(rbp + (key & 1023u) * 16u);
-            const uint4 b = lds128u(rbp + ((key >> 10) & 1023u) * 16u);
-            const uint4 c = lds128u(rbp + (key >> 20) * 16u);
-            return hmul8(hmul8(a, b), c);
-        };
-
-        uint32_t acc_phase = 0;
-        int s = 0, rs = 0;
-        uint32_t ph = 0;
-        int64_t in_window = 0;
-        for (int64_t c = 0; c < nchunks; ++c) {
-            asm volatile("bar.sync 1, %0;" ::"n"(RUN2_PROD_WARPS * 32) : "memory");
-            issue_chunk(c + 2);
-            mbar_wait(&raw_full[rs], (uint32_t)((c / TC_RAW_SLOTS) & 1));
-            if (lane == 0) mbar_wait(&empty[s], ph ^ 1);
-            __syncwarp();
-            const uint32_t rbp = raw_s + (uint32_t)rs * raw_bytes + (uint32_t)pc * plane_stride;     // this lane's plane of the slot
-            const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
-            if (!is_v) {   // ---- U: prefixes, then two groups of four rows
-                const uint4 preA = u_prefix(rbp, rr.keyA);
-                const uint4 preB = u_prefix(rbp, rr.keyB);
-#pragma unroll
-                for (int h = 0; h < 8; h += 4) {
-                    uint4 x[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) x[i] = lds128u(rbp + rr.last[h + i]);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 pre = sel8((rr.selB >> (h + i)) & 1u, preB, preA);
-                        if ((rr.slow >> (h + i)) & 1u) pre = u_prefix(rbp, rr.key[h + i]);
-                        sts128u(sb + dst + (uint32_t)(h + i) * 16u, hmul8(pre, x[i]));
-                    }
-                }
-            } else if (v_active) {   // ---- V
-                const uint4 preA = lds128u(rbp + rr.keyA * 16u);
-                const uint4 preB = lds128u(rbp + rr.keyB * 16u);
-#pragma unroll
-                for (int h = 0; h < 8; h += 4) {
-                    uint4 y[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) y[i] = lds128u(rbp + rr.last[h + i]);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        uint4 pre = sel8((rr.selB >> (h + i)) & 1u, preB, preA);
-                        if ((rr.slow >> (h + i)) & 1u) pre = lds128u(rbp + rr.key[h + i] * 16u);
-                        sts128u(sb + dst + (uint32_t)(h + i) * 16u, hmul8(pre, y[i]));
-                    }
-                }
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&full[s]);
-            if (++s == NS) { s = 0; ph ^= 1; }
-            if (++rs == TC_RAW_SLOTS) rs = 0;
-            const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
-            if (last_of_window) {
-                in_window = 0;
-                mbar_wait(acc_full, acc_phase);
-                acc_phase ^= 1;
-                tc_fence_after();
-                drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, reinterpret_cast<float*>(stage_base), unscale, TC_M, (c + 1) == nchunks, 4);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 0) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, tmem_cols);
-    }
-}
-
-constexpr int RUN3_THREADS = 32 * (2 + TC_PROD_WARPS);      // MMA issuer, eight producer warps, one loader warp
-__global__ void __launch_bounds__(RUN3_THREADS, 1)
-gram_tc16_run3_kernel(TcParams p) {
-    constexpr int T = 2, H_KC = 64, H_NP = 8;
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int BN = p.BN, NS = p.nstages;
-    const int mA = p.mA, mB = p.mB, mC = p.mC;
-
-    const uint32_t lbo_b = (uint32_t)BN * 16 + 16;
-    const uint32_t b_tile_bytes = 8 * lbo_b;
-    const uint32_t stage_bytes = T * RUN_A_TILE + b_tile_bytes;
-    const uint32_t z_rows = (uint32_t)(2 * mA + mB + mC);
-    const uint32_t raw_rows = z_rows + 1;
-    const uint32_t plane_stride = run_plane_stride(raw_rows);
-    const uint32_t raw_bytes = H_NP * plane_stride;
-    uint8_t* stage_base = smem_raw;
-    uint8_t* raw_base = smem_raw + (size_t)NS * stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)TC_RAW_SLOTS * raw_bytes);
-    uint64_t* full = bars;
-    uint64_t* empty = bars + NS;
-    uint64_t* acc_full = bars + 2 * NS;
-    uint64_t* acc_empty = bars + 2 * NS + 1;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
-    uint64_t* raw_full = bars + 2 * NS + 3;
-    uint64_t* raw_empty = raw_full + TC_RAW_SLOTS;      // producers -> loader warp: the slot has been read by all eight warps
-
-    const uint32_t tmem_cols_needed = (uint32_t)(T * BN);
-    uint32_t tmem_cols = 32;
-    while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
-
-    if (tid == 0) {
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(&full[s], TC_PROD_WARPS);
-            mbar_init(&empty[s], 1);
-        }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, TC_PROD_WARPS);
-        for (int i = 0; i < TC_RAW_SLOTS; ++i) {
-            mbar_init(&raw_full[i], 1);
-            mbar_init(&raw_empty[i], TC_PROD_WARPS);
-        }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < TC_RAW_SLOTS * H_NP * 4; i += RUN3_THREADS) {
-        const int slot = i / (H_NP * 4), e = i % (H_NP * 4);
-        reinterpret_cast<uint32_t*>(raw_base + (size_t)slot * raw_bytes + (size_t)(e >> 2) * plane_stride + (size_t)z_rows * 16)[e & 3] = 0u;
-    }
-    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int64_t k_begin = (int64_t)blockIdx.z * p.rows_per_split;
-    const int64_t k_end = min(p.zpitch, k_begin + p.rows_per_split);
-    const int64_t nchunks = (k_end > k_begin) ? (k_end - k_begin) / H_KC : 0;
-    const int64_t chunks_per_flush = p.flush_rows / H_KC;
-    const int64_t nU = (int64_t)p.nA * p.nB;
-    const int64_t u0 = (int64_t)blockIdx.x * (TC_M * T);
-    const int v0 = blockIdx.y * BN;
-
-    if (warp == 0) {
-        // =============================== MMA issuer ===============================
-        if (lane == 0 && nchunks > 0) {
-            const uint32_t idesc = make_idesc_f16(TC_M, BN);
-            const uint32_t sbo = 128;
-            uint32_t acc_phase = 0;
-            int s = 0;
-            uint32_t ph = 0;
-            int64_t in_window = 0;
-            for (int64_t c = 0; c < nchunks; ++c) {
-                const bool first_of_window = in_window == 0;
-                if (first_of_window && c > 0) {
-                    mbar_wait(acc_empty, acc_phase);
-                    acc_phase ^= 1;
-                    tc_fence_after();
-                }
-                mbar_wait(&full[s], ph);
-                tc_fence_after();
-                const uint32_t sb = smem_u32(stage_base + (size_t)s * stage_bytes);
-                const uint32_t b_base = sb + T * RUN_A_TILE;
-#pragma unroll
-                for (int t = 0; t < T; ++t) {
-                    const uint32_t a_base = sb + (uint32_t)t * RUN_A_TILE;
-                    const uint32_t d = tmem_base + (uint32_t)(t * BN);
-#pragma unroll
-                    for (int j = 0; j < H_KC / 16; ++j) {
-                        const uint32_t ao = (uint32_t)(2 * j) * RUN_LBO_A, bo = (uint32_t)(2 * j) * lbo_b;
-                        const uint32_t acc0 = (first_of_window && j == 0) ? 0u : 1u;
-                        umma_f16(d, make_desc(a_base + ao, RUN_LBO_A, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
-                    }
-                }
-                umma_commit(&empty[s]);
-                const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
-                if (last_of_window) {
-                    umma_commit(acc_full);
-                    in_window = 0;
-                }
-                if (++s == NS) { s = 0; ph ^= 1; }
-            }
-        }
-    } else if (warp == 1 + TC_PROD_WARPS) {
-        // =============================== loader: keeps the raw-factor ring full (no block barrier among the producers) ===============================
-        if (lane == 0) {
-            const uint32_t raw_s = smem_u32(raw_base);
-            const __half* Zh = reinterpret_cast<const __half*>(p.Z);
-            const uint32_t plane_bytes = z_rows * 16;
-            for (int64_t c = 0; c < nchunks; ++c) {
-                const int slot = (int)(c % TC_RAW_SLOTS);
-                if (c >= TC_RAW_SLOTS) mbar_wait(&raw_empty[slot], (uint32_t)((c / TC_RAW_SLOTS - 1) & 1));
-                const uint32_t bar = smem_u32(&raw_full[slot]);
-                const uint32_t dst0 = raw_s + (uint32_t)slot * raw_bytes;
-                const __half* src0 = Zh + ((k_begin / H_KC + c) * H_NP) * (int64_t)z_rows * 8;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(H_NP * plane_bytes) : "memory");
-#pragma unroll
-                for (int part = 0; part < H_NP; ++part)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dst0 + (uint32_t)part * plane_stride), "l"(src0 + (int64_t)part * z_rows * 8), "r"(plane_bytes), "r"(bar)
-                                 : "memory");
-            }
-        }
-    } else {
-        // =============================== producers / epilogue ===============================
-        const int pt = tid - 32;              // 0..255
-        const int pc = lane & 7;              // this lane's piece of the stage (8 samples): the 8 lanes of a quarter warp = the 8 pieces of one row
-        const int grp = (pt >> 5) * 4 + (lane >> 3);     // 8-row core matrix: U rows 8 grp .. 8 grp + 7 of the CTA's 256, V rows likewise
-        const double unscale = ldexp(1.0, 2 * (tc_exponent(p.amax[0]) + tc_exponent(p.amax[1]) + tc_exponent(p.amax[2])) +
-                                              tc_exponent(p.amax[3]));
-        const uint32_t raw_s = smem_u32(raw_base);
-        RunRows ur, vr;
-        const bool v_active = 8 * grp < BN;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int64_t gu = u0 + 8 * grp + i;
-            uint32_t key = z_rows | (z_rows << 10) | (z_rows << 20), last = z_rows;      // the zero row
-            if (gu < nU) {
-                const int qa = (int)(gu / p.nB), qb = (int)(gu - (int64_t)qa * p.nB);
-                int ia, ja, ib, jb;
-                pair_decode(qa, mA, ia, ja);
-                pair_decode(qb, mB, ib, jb);
-                key = (uint32_t)ia | ((uint32_t)(mA + ja) << 10) | ((uint32_t)(2 * mA + ib) << 20);
-                last = (uint32_t)(2 * mA + jb);
-            }
-            ur.key[i] = key;
-            ur.last[i] = last * 16u;
-            const int gv = v0 + 8 * grp + i;
-            uint32_t vkey = z_rows, vlast = z_rows;
-            if (v_active && gv < p.nC) {
-                int ic, jc;
-                pair_decode(gv, mC, ic, jc);
-                vkey = (uint32_t)(2 * mA + mB + ic);
-                vlast = (uint32_t)(2 * mA + mB + jc);
-            }
-            vr.key[i] = vkey;
-            vr.last[i] = vlast * 16u;
-        }
-        run_rows_finish(ur);
-        run_rows_finish(vr);
-        // destinations: tile (8 grp) / 128, row (8 grp) % 128 + i; piece pc
-        const uint32_t udst = (uint32_t)(grp >> 4) * RUN_A_TILE + (uint32_t)pc * RUN_LBO_A + (uint32_t)((8 * grp) & 127) * 16;
-        const uint32_t vdst = T * RUN_A_TILE + (uint32_t)pc * lbo_b + (uint32_t)(8 * grp) * 16;
-        const uint32_t stage_s = smem_u32(stage_base);
-        const __half* Zh = reinterpret_cast<const __half*>(p.Z);
-
-        auto u_prefix = [&](uint32_t rbp, uint32_t key) -> uint4 {
-            const uint4 a = lds128u(rbp + (key & 1023u) * 16u);
-            const uint4 b = lds128u(rbp + ((key >> 10) & 1023u) * 16u);
-            const uint4 c = lds128u(rbp + (key >> 20) * 16u);
-            return hmul8(hmul8(a, b), c);
-        };
-
-        uint32_t acc_phase = 0;
-        int s = 0, rs = 0;
-        uint32_t ph = 0;
-        int64_t in_window = 0;
-        for (int64_t c = 0; c < nchunks; ++c) {
-            mbar_wait(&raw_full[rs], (uint32_t)((c / TC_RAW_SLOTS) & 1));
-            if (lane == 0) mbar_wait(&empty[s], ph ^ 1);
-            __syncwarp();
-            const uint32_t rbp = raw_s + (uint32_t)rs * raw_bytes + (uint32_t)pc * plane_stride;     // this lane's plane of the slot
-            const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
-            {   // ---- every load of the stage first (24 LDS.128 in flight per thread), then the products and the stores
-                uint4 x[8], y[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i) x[i] = lds128u(rbp + ur.last[i]);
-                const uint4 preA = u_prefix(rbp, ur.keyA);
-                const uint4 preB = u_prefix(rbp, ur.keyB);
-                uint4 vpreA = make_uint4(0u, 0u, 0u, 0u), vpreB = vpreA;
-                if (v_active) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) y[i] = lds128u(rbp + vr.last[i]);
-                    vpreA = lds128u(rbp + vr.keyA * 16u);
-                    vpreB = lds128u(rbp + vr.keyB * 16u);
-                }
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    uint4 pre = sel8((ur.selB >> i) & 1u, preB, preA);
-                    if ((ur.slow >> i) & 1u) pre = u_prefix(rbp, ur.key[i]);
-                    sts128u(sb + udst + (uint32_t)i * 16u, hmul8(pre, x[i]));
-                }
-                if (v_active) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        uint4 pre = sel8((vr.selB >> i) & 1u, vpreB, vpreA);
-                        if ((vr.slow >> i) & 1u) pre = lds128u(rbp + vr.key[i] * 16u);
-                        sts128u(sb + vdst + (uint32_t)i * 16u, hmul8(pre, y[i]));
-                    }
-                }
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                mbar_arrive(&full[s]);
-                mbar_arrive(&raw_empty[rs]);        // every load of this warp from the slot has returned (the stores above used them)
-            }
-            if (++s == NS) { s = 0; ph ^= 1; }
-            if (++rs == TC_RAW_SLOTS) rs = 0;
-            const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
-            if (last_of_window) {
-                in_window = 0;
-                mbar_wait(acc_full, acc_phase);
-                acc_phase ^= 1;
-                tc_fence_after();
-                drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, reinterpret_cast<float*>(stage_base), unscale, TC_M, (c + 1) == nchunks);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(acc_empty);
-                // the drain's transpose scratch aliases the operand stages: nobody writes the next stage before everybody has drained
-                asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");
             }
         }
     }
@@ -1491,7 +1016,341 @@ gram_tc16_run3_kernel(TcParams p) {
 static size_t tc16_run_smem_bytes(int mA, int mB, int mC, int BN, int NS) {
     const size_t stage = 2 * (size_t)RUN_A_TILE + 8 * ((size_t)BN * 16 + 16);
     const size_t plane = run_plane_stride((uint32_t)(2 * mA + mB + mC + 1));
-    return NS * stage + TC_RAW_SLOTS * 8 * plane + (2 * NS + 2) * 8 + 16 + 32 + 32;      // + the raw_empty barriers of the loader-warp variant
+    return NS * stage + TC_RAW_SLOTS * 8 * plane + (2 * NS + 2) * 8 + 16 + 32;
+}
+
+// ---- fp16 kernel with a PRE-SYNTHESISED V operand and pair products of the left factor (T = 2 U tiles, 64-sample stages).
+// Measured on gram_tc16_run_kernel (tools/tc16_probe.py with TN_TC16_DBG, profiles/r2_gram_tc16_where_the_time_goes.txt): the
+// producers' synthesis alone takes 86 % of the kernel's time, and it is bound by shared-memory wavefronts (845 load + 600 store
+// per stage at 90 % of the pipe); the MMAs cost 15 % on top (their operand fetch shares the pipe), the barriers 18 %.  40 % of the
+// synthesis is the V tile pair(fc) -- which is THE SAME for all 1260 CTAs of a tile column.  So:
+//  * a pre-pass writes pair(fc) once, in fp16, as ready images of the V region of a stage (K-major core matrices, piece slabs
+//    padded like the shared-memory layout), and a loader warp drops a stage's image into place with ONE bulk copy that completes
+//    on the stage's `full` barrier (arrive.expect_tx): no producer instruction and no LSU wavefront is spent on V;
+//  * the same pre-pass writes pa[qa] = w fa[ia] fa[ja] per sample (fp32 product, one rounding), so the raw-factor ring of a CTA
+//    holds only the fb rows and the (at most 256 / nB + 2) pa rows of its own tile rows: 4.5 KB per stage instead of 18.5 KB,
+//    which frees the shared memory for a third operand stage (the V image needs about a microsecond from L2);
+//  * a U entry is pa[qa] fb[ib] * fb[jb]: the run prefix is two loads and one product.
+// Warp roles (352 threads): 0 = MMA issuer, 1..8 = U producers / drain, 9 = raw-ring loader, 10 = V-image loader.
+struct VimgParams {
+    const unsigned long long* amax;
+    const __half* Zc;        // [chunk][8 planes][psc / 2]: rows fb[0..mB) and the zero row, 8 samples per row and plane
+    const __half* Zpa;       // [chunk][nA][64]
+    const __half* Vimg;      // [tile column][chunk][8 pieces][lbo_b / 2]
+    int64_t zchunks;         // chunks of 64 samples in the staged data
+    int64_t rows_per_split;  // multiple of 64
+    double* M;
+    int mA, mB, mC;
+    int nA, nB, nC;
+    int BN, nstages, flush_rows, nq_max;
+    int dbg;                 // TN_TC16_DBG (measurement only, wrong results): 1 = no U synthesis, 2 = no MMAs, 8 = no raw ring, 32 = no drain, 64 = no V copies
+};
+constexpr int VI_THREADS = 32 * 11;
+
+// one block = one 64-sample chunk
+__global__ void __launch_bounds__(256)
+tc16_vimg_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict__ w, int64_t rows, const unsigned long long* __restrict__ amax,
+                       __half* __restrict__ Zc, __half* __restrict__ Zpa, __half* __restrict__ Vimg, int nA, int nC, int BN, int ytiles,
+                       int64_t zchunks, uint32_t psc, uint32_t lbo_b) {
+    extern __shared__ float vs[];
+    const int mA = fa.m, mB = fb.m, mC = fc.m;
+    constexpr int LD = 65;
+    float* sWA = vs;                       // [mA][LD]  w * fa (scaled)
+    float* sA = sWA + mA * LD;             // [mA][LD]
+    float* sB = sA + mA * LD;              // [mB][LD]
+    float* sC = sB + mB * LD;              // [mC][LD]
+    short* tA = reinterpret_cast<short*>(sC + mC * LD);      // [nA][2]
+    short* tC = tA + 2 * nA;                                  // [nC][2]
+    const double sa = ldexp(1.0, -tc_exponent(amax[0])), sb = ldexp(1.0, -tc_exponent(amax[1]));
+    const double sc = ldexp(1.0, -tc_exponent(amax[2])), sw = ldexp(1.0, -tc_exponent(amax[3]));
+    const int tid = threadIdx.x;
+    const int64_t chunk = blockIdx.x;
+    const int64_t s0 = chunk * 64;
+    const int msum = mA + mB + mC;
+    for (int idx = tid; idx < 64 * msum; idx += 256) {        // lane = feature: coalesced along a sample's row
+        const int s = idx / msum, i = idx - s * msum;
+        const int64_t row = s0 + s;
+        if (i < mA) {
+            float v = 0.f, vw = 0.f;
+            if (row < rows) {
+                const double x = map_eval(fa.map_kind, fa.ptr + (fa.div == 1 ? row : row / fa.div) * fa.ld, i) * sa;
+                v = (float)x;
+                vw = (float)(x * ((w ? w[row] : 1.0) * sw));
+            }
+            sA[i * LD + s] = v;
+            sWA[i * LD + s] = vw;
+        } else if (i < mA + mB) {
+            const int il = i - mA;
+            sB[il * LD + s] = (row < rows) ? (float)(map_eval(fb.map_kind, fb.ptr + (fb.div == 1 ? row : row / fb.div) * fb.ld, il) * sb) : 0.f;
+        } else {
+            const int il = i - mA - mB;
+            sC[il * LD + s] = (row < rows) ? (float)(map_eval(fc.map_kind, fc.ptr + (fc.div == 1 ? row : row / fc.div) * fc.ld, il) * sc) : 0.f;
+        }
+    }
+    for (int q = tid; q < nA + nC; q += 256) {
+        int i, j;
+        if (q < nA) { pair_decode(q, mA, i, j); tA[2 * q] = (short)i; tA[2 * q + 1] = (short)j; }
+        else { pair_decode(q - nA, mC, i, j); tC[2 * (q - nA)] = (short)i; tC[2 * (q - nA) + 1] = (short)j; }
+    }
+    __syncthreads();
+    auto pack8 = [](const float* x, const float* y) -> uint4 {       // eight products, one rounding each
+        uint4 o;
+        __half2 h0 = __floats2half2_rn(x[0] * y[0], x[1] * y[1]), h1 = __floats2half2_rn(x[2] * y[2], x[3] * y[3]);
+        __half2 h2 = __floats2half2_rn(x[4] * y[4], x[5] * y[5]), h3 = __floats2half2_rn(x[6] * y[6], x[7] * y[7]);
+        o.x = *reinterpret_cast<uint32_t*>(&h0); o.y = *reinterpret_cast<uint32_t*>(&h1);
+        o.z = *reinterpret_cast<uint32_t*>(&h2); o.w = *reinterpret_cast<uint32_t*>(&h3);
+        return o;
+    };
+    // common rows: fb as fp16, 8 samples per plane
+    for (int it = tid; it < mB * 8; it += 256) {
+        const int r = it >> 3, pc = it & 7;
+        const float* x = sB + r * LD + pc * 8;
+        const float one[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+        *reinterpret_cast<uint4*>(Zc + (chunk * 8 + pc) * (int64_t)(psc / 2) + r * 8) = pack8(x, one);
+    }
+    // pa[qa] = (w fa[ia]) fa[ja]
+    for (int it = tid; it < nA * 8; it += 256) {
+        const int qa = it >> 3, pc = it & 7;
+        *reinterpret_cast<uint4*>(Zpa + (chunk * nA + qa) * 64 + pc * 8) = pack8(sWA + tA[2 * qa] * LD + pc * 8, sA + tA[2 * qa + 1] * LD + pc * 8);
+    }
+    // V images: pair(fc) in the layout of a stage's V region
+    for (int it = tid; it < ytiles * BN * 8; it += 256) {
+        const int pc = it & 7, rr = it >> 3;
+        const int y = rr / BN, r = rr - y * BN;
+        const int gv = y * BN + r;
+        uint4 o = make_uint4(0u, 0u, 0u, 0u);
+        if (gv < nC) o = pack8(sC + tC[2 * gv] * LD + pc * 8, sC + tC[2 * gv + 1] * LD + pc * 8);
+        *reinterpret_cast<uint4*>(Vimg + (((int64_t)y * zchunks + chunk) * 8 + pc) * (int64_t)(lbo_b / 2) + r * 8) = o;
+    }
+}
+
+__global__ void __launch_bounds__(VI_THREADS, 1)
+gram_tc16_vimg_kernel(VimgParams p) {
+    constexpr int T = 2, H_KC = 64;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int BN = p.BN, NS = p.nstages;
+    const int mB = p.mB;
+
+    const uint32_t lbo_b = (uint32_t)BN * 16 + 16;
+    const uint32_t v_bytes = 8 * lbo_b;
+    const uint32_t stage_bytes = T * RUN_A_TILE + v_bytes;
+    const uint32_t psc = run_plane_stride((uint32_t)mB + 1);       // plane of the common rows (fb + the zero row)
+    const uint32_t common_bytes = 8 * psc;
+    const uint32_t slot_bytes = common_bytes + (uint32_t)p.nq_max * 128;
+    uint8_t* stage_base = smem_raw;
+    uint8_t* raw_base = smem_raw + (size_t)NS * stage_bytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)TC_RAW_SLOTS * slot_bytes);
+    uint64_t* full = bars;              // [NS]  8 producer warps + the V loader's expect_tx
+    uint64_t* empty = bars + NS;        // [NS]
+    uint64_t* acc_full = bars + 2 * NS;
+    uint64_t* acc_empty = bars + 2 * NS + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
+    uint64_t* raw_full = bars + 2 * NS + 3;            // [TC_RAW_SLOTS]
+    uint64_t* raw_empty = raw_full + TC_RAW_SLOTS;     // [TC_RAW_SLOTS]
+
+    const uint32_t tmem_cols_needed = (uint32_t)(T * BN);
+    uint32_t tmem_cols = 32;
+    while (tmem_cols < tmem_cols_needed) tmem_cols <<= 1;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; ++s) {
+            mbar_init(&full[s], TC_PROD_WARPS + 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, TC_PROD_WARPS);
+        for (int i = 0; i < TC_RAW_SLOTS; ++i) {
+            mbar_init(&raw_full[i], 1);
+            mbar_init(&raw_empty[i], TC_PROD_WARPS);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) tmem_alloc(tmem_slot, tmem_cols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int64_t k_begin = (int64_t)blockIdx.z * p.rows_per_split;
+    const int64_t k_end = min(p.zchunks * H_KC, k_begin + p.rows_per_split);
+    const int64_t nchunks = (k_end > k_begin) ? (k_end - k_begin) / H_KC : 0;
+    const int64_t chunk0 = k_begin / H_KC;
+    const int64_t chunks_per_flush = p.flush_rows / H_KC;
+    const int64_t nU = (int64_t)p.nA * p.nB;
+    const int64_t u0 = (int64_t)blockIdx.x * (TC_M * T);
+    const int v0 = blockIdx.y * BN;
+    const int qa_lo = (int)(u0 / p.nB);
+    const int64_t u_last = min(u0 + TC_M * T, nU) - 1;
+    const int nq = (int)(u_last / p.nB) - qa_lo + 1;               // pa rows this CTA needs (<= nq_max)
+
+    if (warp == 0) {
+        // =============================== MMA issuer ===============================
+        if (lane == 0 && nchunks > 0) {
+            const uint32_t idesc = make_idesc_f16(TC_M, BN);
+            const uint32_t sbo = 128;
+            uint32_t acc_phase = 0;
+            int s = 0;
+            uint32_t ph = 0;
+            int64_t in_window = 0;
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const bool first_of_window = in_window == 0;
+                if (first_of_window && c > 0) {
+                    mbar_wait(acc_empty, acc_phase);
+                    acc_phase ^= 1;
+                    tc_fence_after();
+                }
+                mbar_wait(&full[s], ph);
+                tc_fence_after();
+                const uint32_t sb = smem_u32(stage_base + (size_t)s * stage_bytes);
+                const uint32_t b_base = sb + T * RUN_A_TILE;
+#pragma unroll
+                for (int t = 0; t < T; ++t) {
+                    const uint32_t a_base = sb + (uint32_t)t * RUN_A_TILE;
+                    const uint32_t d = tmem_base + (uint32_t)(t * BN);
+#pragma unroll
+                    for (int j = 0; j < H_KC / 16; ++j) {
+                        const uint32_t ao = (uint32_t)(2 * j) * RUN_LBO_A, bo = (uint32_t)(2 * j) * lbo_b;
+                        const uint32_t acc0 = (first_of_window && j == 0) ? 0u : 1u;
+                        if (!(p.dbg & 2)) umma_f16(d, make_desc(a_base + ao, RUN_LBO_A, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
+                    }
+                }
+                umma_commit(&empty[s]);
+                const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+                if (last_of_window) {
+                    umma_commit(acc_full);
+                    in_window = 0;
+                }
+                if (++s == NS) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1 + TC_PROD_WARPS) {
+        // =============================== raw-ring loader: fb rows + this CTA's pa rows of every chunk ===============================
+        if (lane == 0 && !(p.dbg & 8)) {
+            const uint32_t raw_s = smem_u32(raw_base);
+            const uint32_t pa_bytes = (uint32_t)nq * 128;
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const int slot = (int)(c % TC_RAW_SLOTS);
+                if (c >= TC_RAW_SLOTS) mbar_wait(&raw_empty[slot], (uint32_t)((c / TC_RAW_SLOTS - 1) & 1));
+                const uint32_t bar = smem_u32(&raw_full[slot]);
+                const uint32_t dst0 = raw_s + (uint32_t)slot * slot_bytes;
+                const __half* srcc = p.Zc + (chunk0 + c) * (int64_t)(common_bytes / 2);
+                const __half* srcp = p.Zpa + ((chunk0 + c) * p.nA + qa_lo) * 64;
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(common_bytes + pa_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst0), "l"(srcc), "r"(common_bytes), "r"(bar) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst0 + common_bytes), "l"(srcp), "r"(pa_bytes), "r"(bar) : "memory");
+            }
+        }
+    } else if (warp == 2 + TC_PROD_WARPS) {
+        // =============================== V loader: the ready image of pair(fc) for every chunk, straight into the stage ===============================
+        if (lane == 0) {
+            const uint32_t stage_s = smem_u32(stage_base);
+            for (int64_t c = 0; c < nchunks; ++c) {
+                const int s = (int)(c % NS);
+                if (c >= NS) mbar_wait(&empty[s], (uint32_t)((c / NS - 1) & 1));      // the MMAs of chunk c - NS have read the stage
+                const uint32_t bar = smem_u32(&full[s]);
+                const __half* src = p.Vimg + ((int64_t)blockIdx.y * p.zchunks + chunk0 + c) * (int64_t)(v_bytes / 2);
+                if (p.dbg & 64) { mbar_arrive(&full[s]); continue; }
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(v_bytes) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(stage_s + (uint32_t)s * stage_bytes + T * RUN_A_TILE), "l"(src), "r"(v_bytes), "r"(bar) : "memory");
+            }
+        }
+    } else {
+        // =============================== U producers / epilogue ===============================
+        const int pt = tid - 32;              // 0..255
+        const int pc = lane & 7;              // this lane's piece of the stage (8 samples)
+        const int grp = (pt >> 5) * 4 + (lane >> 3);     // 8-row core matrix: U rows 8 grp .. 8 grp + 7 of the CTA's 256
+        const double unscale = ldexp(1.0, 2 * (tc_exponent(p.amax[0]) + tc_exponent(p.amax[1]) + tc_exponent(p.amax[2])) +
+                                              tc_exponent(p.amax[3]));
+        const uint32_t raw_s = smem_u32(raw_base);
+        RunRows ur;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t gu = u0 + 8 * grp + i;
+            uint32_t key = (uint32_t)mB, last = (uint32_t)mB;      // padding row: pa row 0 times the zero row
+            if (gu < nU) {
+                const int qa = (int)(gu / p.nB), qb = (int)(gu - (int64_t)qa * p.nB);
+                int ib, jb;
+                pair_decode(qb, mB, ib, jb);
+                key = ((uint32_t)(qa - qa_lo) << 10) | (uint32_t)ib;
+                last = (uint32_t)jb;
+            }
+            ur.key[i] = key;
+            ur.last[i] = last * 16u;
+        }
+        run_rows_finish(ur);
+        const uint32_t udst = (uint32_t)(grp >> 4) * RUN_A_TILE + (uint32_t)pc * RUN_LBO_A + (uint32_t)((8 * grp) & 127) * 16;
+        const uint32_t stage_s = smem_u32(stage_base);
+        auto u_prefix = [&](uint32_t slot, uint32_t key) -> uint4 {
+            const uint4 a = lds128u(slot + common_bytes + (key >> 10) * 128u + (uint32_t)pc * 16u);      // pa[qa]
+            const uint4 b = lds128u(slot + (uint32_t)pc * psc + (key & 1023u) * 16u);                    // fb[ib]
+            return hmul8(a, b);
+        };
+
+        uint32_t acc_phase = 0;
+        int s = 0, rs = 0;
+        uint32_t ph = 0;
+        int64_t in_window = 0;
+        for (int64_t c = 0; c < nchunks; ++c) {
+            if (!(p.dbg & 8)) mbar_wait(&raw_full[rs], (uint32_t)((c / TC_RAW_SLOTS) & 1));
+            if (lane == 0) mbar_wait(&empty[s], ph ^ 1);                 // first pass over the ring returns immediately
+            __syncwarp();
+            const uint32_t slot = raw_s + (uint32_t)rs * slot_bytes;
+            const uint32_t rbp = slot + (uint32_t)pc * psc;              // this lane's plane of the common rows
+            const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
+            if (!(p.dbg & 1)) {
+                uint4 x[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) x[i] = lds128u(rbp + ur.last[i]);
+                const uint4 preA = u_prefix(slot, ur.keyA);
+                const uint4 preB = u_prefix(slot, ur.keyB);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    uint4 pre = sel8((ur.selB >> i) & 1u, preB, preA);
+                    if ((ur.slow >> i) & 1u) pre = u_prefix(slot, ur.key[i]);
+                    sts128u(sb + udst + (uint32_t)i * 16u, hmul8(pre, x[i]));
+                }
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&full[s]);
+                mbar_arrive(&raw_empty[rs]);
+            }
+            if (++s == NS) { s = 0; ph ^= 1; }
+            if (++rs == TC_RAW_SLOTS) rs = 0;
+            const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
+            if (last_of_window) {
+                in_window = 0;
+                mbar_wait(acc_full, acc_phase);
+                acc_phase ^= 1;
+                tc_fence_after();
+                // transpose scratch: the U regions of stages 0 and 1 (the V regions belong to the loader, which may already be filling them)
+                float* scratch = reinterpret_cast<float*>(stage_base + (size_t)((warp - 1) >> 2) * stage_bytes) - (size_t)(((warp - 1) >> 2) * 4) * (32 * 33);
+                if (!(p.dbg & 32)) drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, scratch, unscale, TC_M, (c + 1) == nchunks);
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(acc_empty);
+                asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");      // nobody writes the next U tiles over a scratch still in use
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, tmem_cols);
+    }
+}
+
+static size_t tc16_vimg_smem_bytes(int mB, int BN, int nq_max, int NS) {
+    const size_t stage = 2 * (size_t)RUN_A_TILE + 8 * ((size_t)BN * 16 + 16);
+    const size_t slot = 8 * (size_t)run_plane_stride((uint32_t)mB + 1) + (size_t)nq_max * 128;
+    return NS * stage + TC_RAW_SLOTS * slot + (2 * NS + 2) * 8 + 16 + 2 * TC_RAW_SLOTS * 8 + 16;
 }
 
 static size_t tc16_smem_bytes(int mA, int mB, int mC, int BN, int T, int NS, int kc) {
@@ -1772,245 +1631,6 @@ gram_tc_pair_kernel(TcParams p) {
     }
 }
 
-// ---- CTA-pair variant of the FP16 kernel (cta_group::2, kind::f16, M = 256 x N = 256 per MMA).  The fp16 kernel is bound by what
-// its producers and the tensor core move through shared memory, not by the tensor pipe (it runs at about half of the 16-bit MMA
-// rate), so -- unlike in 3xTF32, where the pair kernel above lost 5 % -- sharing every MMA between the two SMs of a TPC pays:
-// per SM and stage the producers synthesise 256 U rows + 128 V rows instead of 256 + 256, and the tensor core fetches 8 KB
-// instead of 12 KB of operands per K = 16 step.  Raw factors arrive as in gram_tc16_kernel (planes of eight fp16 samples, bulk
-// copies on an mbarrier, each CTA fills its own ring); the V rows are split over all eight producer warps (row = thread % 128,
-// half of the stage's pieces each) so that no warp idles.  Barriers as in gram_tc_pair_kernel.
-__device__ __forceinline__ void umma2_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
-}
-
-template <int H_KC>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(TC_THREADS, 1)
-gram_tc16_pair_kernel(TcParams p) {
-    constexpr int H_NP = H_KC / 8;      // 16-byte pieces (8 samples) of a row per stage
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
-    const int NS = p.nstages;
-    const int mA = p.mA, mB = p.mB, mC = p.mC;
-    const uint32_t rank = cluster_rank();
-
-    constexpr uint32_t a_tile_bytes = TC_M * H_KC * 2;         // this CTA's 128 rows of one M = 256 U tile, one stage
-    constexpr uint32_t b_tile_bytes = TP_BH * H_KC * 2;        // this CTA's half of the V tile
-    constexpr uint32_t stage_bytes = TP_T * a_tile_bytes + b_tile_bytes;
-    const uint32_t z_rows = (uint32_t)(2 * mA + mB + mC);
-    const uint32_t raw_rows = z_rows + 1;
-    const uint32_t plane_stride = ((raw_rows * 16 + 95) / 128) * 128 + 32;
-    const uint32_t raw_bytes = H_NP * plane_stride;
-    uint8_t* stage_base = smem_raw;
-    uint8_t* raw_base = smem_raw + (size_t)NS * stage_bytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(raw_base + (size_t)TC_RAW_SLOTS * raw_bytes);
-    uint64_t* full = bars;              // [NS]  used in the leader: producers of both CTAs -> MMA
-    uint64_t* empty = bars + NS;        // [NS]  per CTA: multicast tcgen05.commit -> producers
-    uint64_t* acc_full = bars + 2 * NS;     // per CTA (multicast commit)
-    uint64_t* acc_empty = bars + 2 * NS + 1;   // used in the leader: drainers of both CTAs -> MMA
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NS + 2);
-    uint64_t* raw_full = bars + 2 * NS + 3;      // [TC_RAW_SLOTS] per CTA
-
-    if (tid == 0) {
-        for (int s = 0; s < NS; ++s) {
-            mbar_init(&full[s], 2 * TC_PROD_WARPS);
-            mbar_init(&empty[s], 1);
-        }
-        mbar_init(acc_full, 1);
-        mbar_init(acc_empty, 2 * TC_PROD_WARPS);
-        for (int i = 0; i < TC_RAW_SLOTS; ++i) mbar_init(&raw_full[i], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    for (int i = tid; i < TC_RAW_SLOTS * H_NP * 4; i += TC_THREADS) {      // the zero row of every plane of every slot (16 B each)
-        const int slot = i / (H_NP * 4), e = i % (H_NP * 4);
-        reinterpret_cast<uint32_t*>(raw_base + (size_t)slot * raw_bytes + (size_t)(e >> 2) * plane_stride + (size_t)z_rows * 16)[e & 3] = 0u;
-    }
-    cluster_sync_all();                  // barrier inits visible to the peer before anything arrives remotely
-    if (warp == 0) tmem_alloc2(tmem_slot, 512);
-    tc_fence_before();
-    cluster_sync_all();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    const int64_t k_begin = (int64_t)blockIdx.z * p.rows_per_split;
-    const int64_t k_end = min(p.zpitch, k_begin + p.rows_per_split);
-    const int64_t nchunks = (k_end > k_begin) ? (k_end - k_begin) / H_KC : 0;
-    const int64_t chunks_per_flush = p.flush_rows / H_KC;
-    const int64_t nU = (int64_t)p.nA * p.nB;
-    const int64_t u0_pair = (int64_t)(blockIdx.x >> 1) * (2 * TC_M * TP_T);     // 512 U rows per pair
-    const int v0 = blockIdx.y * TP_BN;
-
-    if (warp == 0) {
-        // =============================== MMA issuer (leader CTA only) ===============================
-        if (rank == 0 && lane == 0 && nchunks > 0) {
-            const uint32_t idesc = make_idesc_f16(2 * TC_M, TP_BN);
-            constexpr uint32_t lbo_a = TC_M * 16, lbo_b = TP_BH * 16, sbo = 128;
-            uint32_t acc_phase = 0;
-            int s = 0;
-            uint32_t ph = 0;
-            int64_t in_window = 0;
-            for (int64_t c = 0; c < nchunks; ++c) {
-                const bool first_of_window = in_window == 0;
-                if (first_of_window && c > 0) {
-                    mbar_wait_cluster(acc_empty, acc_phase);
-                    acc_phase ^= 1;
-                    tc_fence_after();
-                }
-                mbar_wait_cluster(&full[s], ph);
-                tc_fence_after();
-                const uint32_t sb = smem_u32(stage_base + (size_t)s * stage_bytes);
-                const uint32_t b_base = sb + TP_T * a_tile_bytes;
-#pragma unroll
-                for (int t = 0; t < TP_T; ++t) {
-                    const uint32_t a_base = sb + (uint32_t)t * a_tile_bytes;
-                    const uint32_t d = tmem_base + (uint32_t)(t * TP_BN);
-#pragma unroll
-                    for (int j = 0; j < H_KC / 16; ++j) {          // one MMA = 16 samples = two 16-byte pieces
-                        const uint32_t ao = (uint32_t)(2 * j) * lbo_a, bo = (uint32_t)(2 * j) * lbo_b;
-                        const uint32_t acc0 = (first_of_window && j == 0) ? 0u : 1u;
-                        umma2_f16(d, make_desc(a_base + ao, lbo_a, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
-                    }
-                }
-                umma_commit2(&empty[s]);
-                const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
-                if (last_of_window) {
-                    umma_commit2(acc_full);
-                    in_window = 0;
-                }
-                if (++s == NS) { s = 0; ph ^= 1; }
-            }
-        }
-    } else {
-        // =============================== producers / epilogue (both CTAs) ===============================
-        const int pt = tid - 32;
-        const double unscale = ldexp(1.0, 2 * (tc_exponent(p.amax[0]) + tc_exponent(p.amax[1]) + tc_exponent(p.amax[2])) +
-                                              tc_exponent(p.amax[3]));
-        const uint32_t raw_s = smem_u32(raw_base);
-        const uint32_t zero_row = z_rows * 16;
-        uint32_t usrc[4] = {zero_row, zero_row, zero_row, zero_row};
-        const int u_tile = pt >> 7, u_row = pt & 127;
-        const int64_t u0_cta = u0_pair + (int64_t)rank * TC_M;        // tile t of this CTA covers rows u0_cta + t*256 + [0, 128)
-        {
-            const int64_t gu = u0_cta + (int64_t)u_tile * (2 * TC_M) + u_row;
-            if (gu < nU) {
-                const int qa = (int)(gu / p.nB), qb = (int)(gu - (int64_t)qa * p.nB);
-                int ia, ja, ib, jb;
-                pair_decode(qa, mA, ia, ja);
-                pair_decode(qb, mB, ib, jb);
-                usrc[0] = (uint32_t)ia * 16;
-                usrc[1] = (uint32_t)(mA + ja) * 16;
-                usrc[2] = (uint32_t)(2 * mA + ib) * 16;
-                usrc[3] = (uint32_t)(2 * mA + jb) * 16;
-            }
-        }
-        // V: row pt % 128 of this CTA's half of the tile, half of the stage's pieces per thread
-        constexpr int V_NC = H_NP / 2;
-        const int v_row = pt & 127, v_c0 = (pt >> 7) * V_NC;
-        uint32_t vsrc[2] = {zero_row, zero_row};
-        const int gv = v0 + (int)rank * TP_BH + v_row;
-        if (gv < p.nC) {
-            int ic, jc;
-            pair_decode(gv, mC, ic, jc);
-            vsrc[0] = (uint32_t)(2 * mA + mB + ic) * 16;
-            vsrc[1] = (uint32_t)(2 * mA + mB + jc) * 16;
-        }
-        const uint32_t udst = (uint32_t)u_tile * a_tile_bytes + (uint32_t)u_row * 16;
-        constexpr uint32_t lbo_b = TP_BH * 16;
-        const uint32_t vdst = TP_T * a_tile_bytes + (uint32_t)v_row * 16 + (uint32_t)v_c0 * lbo_b;
-        const uint32_t stage_s = smem_u32(stage_base);
-        const __half* Zh = reinterpret_cast<const __half*>(p.Z);
-
-        auto issue_chunk = [&](int64_t chunk) {
-            if (chunk < nchunks && pt == 0) {
-                const int slot = (int)(chunk % TC_RAW_SLOTS);
-                const uint32_t bar = smem_u32(&raw_full[slot]);
-                const uint32_t plane_bytes = z_rows * 16;
-                const uint32_t dst0 = raw_s + (uint32_t)slot * raw_bytes;
-                const __half* src0 = Zh + ((k_begin / H_KC + chunk) * H_NP) * (int64_t)z_rows * 8;
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(H_NP * plane_bytes) : "memory");
-#pragma unroll
-                for (int part = 0; part < H_NP; ++part)
-                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                                 ::"r"(dst0 + (uint32_t)part * plane_stride), "l"(src0 + (int64_t)part * z_rows * 8), "r"(plane_bytes), "r"(bar)
-                                 : "memory");
-            }
-        };
-        issue_chunk(0);
-        issue_chunk(1);
-
-        uint32_t acc_phase = 0;
-        int s = 0, rs = 0;
-        uint32_t ph = 0;
-        int64_t in_window = 0;
-        for (int64_t c = 0; c < nchunks; ++c) {
-            asm volatile("bar.sync 1, %0;" ::"n"(TC_PROD) : "memory");  // chunk c-1 is fully consumed by every producer of this CTA
-            issue_chunk(c + 2);
-            mbar_wait(&raw_full[rs], (uint32_t)((c / TC_RAW_SLOTS) & 1));
-            if (lane == 0) mbar_wait(&empty[s], ph ^ 1);
-            __syncwarp();
-            const uint32_t rb = raw_s + (uint32_t)rs * raw_bytes;
-            const uint32_t sb = stage_s + (uint32_t)s * stage_bytes;
-#pragma unroll
-            for (int g0 = 0; g0 < H_NP; g0 += 4) {     // ---- U rows, four pieces at a time: all loads, then the products, then the stores
-                uint4 x0[4], x1[4], x2[4], x3[4];
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc) {
-                    const uint32_t o = (uint32_t)(g0 + cc) * plane_stride;
-                    x0[cc] = lds128u(rb + usrc[0] + o);
-                    x1[cc] = lds128u(rb + usrc[1] + o);
-                    x2[cc] = lds128u(rb + usrc[2] + o);
-                    x3[cc] = lds128u(rb + usrc[3] + o);
-                }
-#pragma unroll
-                for (int cc = 0; cc < 4; ++cc)
-                    sts128u(sb + udst + (uint32_t)(g0 + cc) * (TC_M * 16), hmul8(hmul8(x0[cc], x1[cc]), hmul8(x2[cc], x3[cc])));
-            }
-            {   // ---- V rows
-                uint4 y0[V_NC], y1[V_NC];
-#pragma unroll
-                for (int cc = 0; cc < V_NC; ++cc) {
-                    y0[cc] = lds128u(rb + vsrc[0] + (uint32_t)(v_c0 + cc) * plane_stride);
-                    y1[cc] = lds128u(rb + vsrc[1] + (uint32_t)(v_c0 + cc) * plane_stride);
-                }
-#pragma unroll
-                for (int cc = 0; cc < V_NC; ++cc) sts128u(sb + vdst + (uint32_t)cc * lbo_b, hmul8(y0[cc], y1[cc]));
-            }
-            fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(&full[s], 0);           // on the leader's barrier
-            if (++s == NS) { s = 0; ph ^= 1; }
-            if (++rs == TC_RAW_SLOTS) rs = 0;
-            const bool last_of_window = (++in_window == chunks_per_flush) || (c + 1) == nchunks;
-            if (last_of_window) {
-                in_window = 0;
-                mbar_wait(acc_full, acc_phase);
-                acc_phase ^= 1;
-                tc_fence_after();
-                drain_accumulator(tmem_base, TP_T * TP_BN, TP_BN, warp, lane, u0_cta, nU, v0, p.nC, p.M,
-                                  reinterpret_cast<float*>(stage_base), unscale, 2 * TC_M, (c + 1) == nchunks);
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(acc_empty, 0);
-            }
-        }
-    }
-    tc_fence_before();
-    __syncwarp();
-    cluster_sync_all();                  // the peer may still be reading this CTA's shared / tensor memory until here
-    if (warp == 0) {
-        tc_fence_after();
-        tmem_dealloc2(tmem_base, 512);
-    }
-}
-
-static size_t tc16_pair_smem_bytes(int mA, int mB, int mC, int NS, int kc) {
-    const size_t stage = (size_t)TP_T * TC_M * kc * 2 + (size_t)TP_BH * kc * 2;
-    const size_t plane = (((size_t)(2 * mA + mB + mC + 1) * 16 + 95) / 128) * 128 + 32;
-    return NS * stage + TC_RAW_SLOTS * (kc / 8) * plane + (2 * NS + 2) * 8 + 16 + 32;
-}
-
 static size_t tc_pair_smem_bytes(int mA, int mB, int mC, int NS) {
     const size_t stage = 2 * (size_t)TP_T * TC_M * TC_KC * 4 + 2 * (size_t)TP_BH * TC_KC * 4;
     const size_t raw = (size_t)(2 * mA + mB + mC + 1) * TC_KCP * 4;
@@ -2055,6 +1675,7 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     if (const char* e = getenv("TN_TC16_KC")) kc16 = (atoi(e) == 32) ? 32 : 64;
     const int KC = f16 ? kc16 : TC_KC;             // samples per pipeline stage
     p.split = (mode == 2) ? 1 : 0;
+    p.dbg = getenv("TN_TC16_DBG") ? atoi(getenv("TN_TC16_DBG")) : 0;
     p.planar = 0;
     p.flush_rows = (tn::g_tc_flush_rows > 0) ? tn::g_tc_flush_rows : TC_FLUSH_ROWS_DEFAULT;
     if (const char* e = getenv("TN_TC_FLUSH_ROWS")) {
@@ -2100,9 +1721,73 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
             pool_ready.fetch_or(1ull << (dev & 63), std::memory_order_relaxed);
         }
     }
+    // fp16, two U tiles, 64-sample stages: pre-synthesised V images + pa rows (gram_tc16_vimg_kernel; TN_TC16_VIMG=0 selects the older kernels)
+    if (f16 && kc16 == 64 && p.T == 2 && B.m + 1 < 1023 && !(getenv("TN_TC16_VIMG") && atoi(getenv("TN_TC16_VIMG")) == 0)) {
+        const int nq_max = 255 / p.nB + 2;
+        int NSV = 4;
+        while (NSV >= 2 && tc16_vimg_smem_bytes(B.m, p.BN, nq_max, NSV) > 226 * 1024) --NSV;
+        if (NSV >= 2) {
+            const int64_t zchunks = p.zpitch / 64;
+            const int ytiles = (int)ceil_div64(p.nC, p.BN);
+            const uint32_t psc = run_plane_stride((uint32_t)B.m + 1);
+            const uint32_t lbo_b = (uint32_t)p.BN * 16 + 16;
+            const size_t zc_bytes = (size_t)zchunks * 8 * psc;
+            const size_t zpa_bytes = (size_t)zchunks * p.nA * 128;
+            const size_t vimg_bytes = (size_t)ytiles * zchunks * 8 * lbo_b;
+            char* buf = nullptr;
+            TN_CUDA(cudaMallocAsync(&buf, zc_bytes + zpa_bytes + vimg_bytes + 64, st));
+            TN_CUDA(cudaMemsetAsync(buf, 0, zc_bytes, st));
+            unsigned long long* amaxv = reinterpret_cast<unsigned long long*>(buf + zc_bytes + zpa_bytes + vimg_bytes);
+            TN_CUDA(cudaMemsetAsync(amaxv, 0, 4 * sizeof(unsigned long long), st));
+            int64_t blocks = ceil_div64(rows * (A.m + B.m + C.m + 1), 256 * 8);
+            if (blocks > 8LL * sm_count()) blocks = 8LL * sm_count();
+            if (blocks < 1) blocks = 1;
+            tc_absmax_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, B, C, w, rows, amaxv);
+            TN_LAUNCH_CHECK();
+            VimgParams v;
+            v.amax = amaxv;
+            v.Zc = reinterpret_cast<const __half*>(buf);
+            v.Zpa = reinterpret_cast<const __half*>(buf + zc_bytes);
+            v.Vimg = reinterpret_cast<const __half*>(buf + zc_bytes + zpa_bytes);
+            v.zchunks = zchunks;
+            v.M = M;
+            v.mA = A.m; v.mB = B.m; v.mC = C.m;
+            v.nA = p.nA; v.nB = p.nB; v.nC = p.nC;
+            v.BN = p.BN; v.nstages = NSV; v.flush_rows = p.flush_rows; v.nq_max = nq_max; v.dbg = p.dbg;
+            const size_t ssmem = (size_t)(2 * A.m + B.m + C.m) * 65 * sizeof(float) + (size_t)(p.nA + p.nC) * 2 * sizeof(short);
+            TN_CHECK_ARG(ssmem <= 200 * 1024, "tn_gram_kr3 (fp16): factors %d+%d+%d too wide for the staging pass", A.m, B.m, C.m);
+            TN_SMEM(tc16_vimg_stage_kernel, ssmem);
+            tc16_vimg_stage_kernel<<<(unsigned)zchunks, 256, ssmem, st>>>(A, B, C, w, rows, amaxv, reinterpret_cast<__half*>(buf),
+                                                                       reinterpret_cast<__half*>(buf + zc_bytes), reinterpret_cast<__half*>(buf + zc_bytes + zpa_bytes),
+                                                                       p.nA, p.nC, p.BN, ytiles, zchunks, psc, lbo_b);
+            TN_LAUNCH_CHECK();
+            const int64_t gxv = ceil_div64(nU, (int64_t)TC_M * 2), gyv = ytiles;
+            int64_t ksv = ceil_div64((int64_t)sm_count(), gxv * gyv);
+            const int64_t max_ksv = ceil_div64(p.zpitch, 4 * 64);
+            if (ksv > max_ksv) ksv = max_ksv;
+            if (ksv < 1) ksv = 1;
+            if (ksv > 65535) ksv = 65535;
+            v.rows_per_split = ceil_div64(ceil_div64(p.zpitch, ksv), 64) * 64;
+            ksv = ceil_div64(p.zpitch, v.rows_per_split);
+            TN_CHECK_ARG(gyv <= 65535 && gxv <= 0x7fffffff, "tn_gram_kr3: grid too large");
+            const size_t vsmem = tc16_vimg_smem_bytes(B.m, p.BN, nq_max, NSV);
+            TN_SMEM(gram_tc16_vimg_kernel, vsmem);
+            dim3 gridv((unsigned)gxv, (unsigned)gyv, (unsigned)ksv);
+            gram_tc16_vimg_kernel<<<gridv, VI_THREADS, vsmem, st>>>(v);
+            TN_LAUNCH_CHECK();
+            TN_CUDA(cudaFreeAsync(buf, st));
+            return TN_OK;
+        }
+    }
+    // fp16, two U tiles, 64-sample stages: the run-ordered kernel (TN_TC16_RUN=0 keeps the row-per-thread kernel)
+    int NSR = 4;
+    while (NSR >= 2 && tc16_run_smem_bytes(A.m, B.m, C.m, p.BN, NSR) > 226 * 1024) --NSR;
+    const bool use_run = f16 && kc16 == 64 && p.T == 2 && z_rows < 1023 && NSR >= 2 && getenv("TN_TC16_RUN") && atoi(getenv("TN_TC16_RUN")) != 0;
+    const size_t run_plane = run_plane_stride((uint32_t)(z_rows + 1));
     float* Z = nullptr;
-    const size_t z_bytes = (size_t)z_rows * p.zpitch * (f16 ? sizeof(__half) : sizeof(float));
+    const size_t z_bytes = use_run ? (size_t)(p.zpitch / 8) * run_plane : (size_t)z_rows * p.zpitch * (f16 ? sizeof(__half) : sizeof(float));
     TN_CUDA(cudaMallocAsync(&Z, z_bytes + 64, st));
+    if (use_run) TN_CUDA(cudaMemsetAsync(Z, 0, z_bytes, st));
     unsigned long long* amax = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(Z) + z_bytes);
     TN_CUDA(cudaMemsetAsync(amax, 0, 4 * sizeof(unsigned long long), st));
     p.Z = Z;
@@ -2121,8 +1806,8 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
         p.planar = (!getenv("TN_TC_RAW_ROWMAJOR") && !getenv("TN_TC_PAIR") &&
                     4 * ((((size_t)(z_rows + 1) * 16 + 95) / 128) * 128 + 32) <= (size_t)(z_rows + 1) * TC_KCP * 4 &&
                     smem + 32 <= 227 * 1024) ? 1 : 0;
-        if (f16) p.planar = 2;                     // planes of eight fp16 samples
-        tc_stage_kernel<<<grid, 256, 0, st>>>(A, B, C, w, rows, Z, p.zpitch, amax, p.planar);
+        if (f16) p.planar = use_run ? 3 : 2;       // planes of eight fp16 samples (3: padded to the run kernel's slot image)
+        tc_stage_kernel<<<grid, 256, 0, st>>>(A, B, C, w, rows, Z, p.zpitch, amax, p.planar, (int64_t)(run_plane / 2));
         TN_LAUNCH_CHECK();
     }
     // CTA-pair kernel (opt-in, TN_TC_PAIR=1).  Measured on the config-5a middle site (131 072 rows, tools/tc_pair_probe.py):
@@ -2165,52 +1850,17 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     if (ks > 65535) ks = 65535;
     p.rows_per_split = ceil_div64(ceil_div64(p.zpitch, ks), KC) * KC;
     ks = ceil_div64(p.zpitch, p.rows_per_split);
-    // CTA-pair fp16 kernel for the large sites (opt-in until measured: TN_TC16_PAIR=1)
-    if (f16 && kc16 == 64 && p.T == 2 && p.BN == TP_BN && nU >= 8LL * 512 && getenv("TN_TC16_PAIR") && atoi(getenv("TN_TC16_PAIR")) != 0) {
-        int NSP = 4;
-        while (NSP >= 2 && tc16_pair_smem_bytes(A.m, B.m, C.m, NSP, 64) > 226 * 1024) --NSP;
-        if (NSP >= 2) {
-            p.nstages = NSP;
-            const size_t psmem = tc16_pair_smem_bytes(A.m, B.m, C.m, NSP, 64);
-            const int64_t gxp = 2 * ceil_div64(nU, 2LL * TC_M * TP_T), gyp = ceil_div64(p.nC, TP_BN);
-            int64_t ksp = ceil_div64((int64_t)sm_count(), gxp * gyp);
-            const int64_t max_ksp = ceil_div64(p.zpitch, 4 * 64);
-            if (ksp > max_ksp) ksp = max_ksp;
-            if (ksp < 1) ksp = 1;
-            if (ksp > 65535) ksp = 65535;
-            p.rows_per_split = ceil_div64(ceil_div64(p.zpitch, ksp), 64) * 64;
-            ksp = ceil_div64(p.zpitch, p.rows_per_split);
-            TN_SMEM(gram_tc16_pair_kernel<64>, psmem);
-            dim3 pgrid((unsigned)gxp, (unsigned)gyp, (unsigned)ksp);
-            gram_tc16_pair_kernel<64><<<pgrid, TC_THREADS, psmem, st>>>(p);
+    if (f16) {
+        using Kern16 = void (*)(TcParams);
+        if (use_run) {
+            p.nstages = NSR;
+            const size_t rsmem = tc16_run_smem_bytes(A.m, B.m, C.m, p.BN, NSR);
+            dim3 gridr((unsigned)gx, (unsigned)gy, (unsigned)ks);
+            TN_SMEM(gram_tc16_run_kernel, rsmem);
+            gram_tc16_run_kernel<<<gridr, TC_THREADS, rsmem, st>>>(p);
             TN_LAUNCH_CHECK();
             TN_CUDA(cudaFreeAsync(Z, st));
             return TN_OK;
-        }
-    }
-    if (f16) {
-        using Kern16 = void (*)(TcParams);
-        if (kc16 == 64 && p.T == 2 && z_rows < 1023 && getenv("TN_TC16_RUN") && atoi(getenv("TN_TC16_RUN")) != 0) {
-            int NSR = 4;
-            while (NSR >= 2 && tc16_run_smem_bytes(A.m, B.m, C.m, p.BN, NSR) > 226 * 1024) --NSR;
-            if (NSR >= 2) {
-                p.nstages = NSR;
-                const size_t rsmem = tc16_run_smem_bytes(A.m, B.m, C.m, p.BN, NSR);
-                dim3 gridr((unsigned)gx, (unsigned)gy, (unsigned)ks);
-                if (atoi(getenv("TN_TC16_RUN")) == 3) {
-                    TN_SMEM(gram_tc16_run3_kernel, rsmem);
-                    gram_tc16_run3_kernel<<<gridr, RUN3_THREADS, rsmem, st>>>(p);
-                } else if (atoi(getenv("TN_TC16_RUN")) == 2) {
-                    TN_SMEM(gram_tc16_run2_kernel, rsmem);
-                    gram_tc16_run2_kernel<<<gridr, RUN2_THREADS, rsmem, st>>>(p);
-                } else {
-                    TN_SMEM(gram_tc16_run_kernel, rsmem);
-                    gram_tc16_run_kernel<<<gridr, TC_THREADS, rsmem, st>>>(p);
-                }
-                TN_LAUNCH_CHECK();
-                TN_CUDA(cudaFreeAsync(Z, st));
-                return TN_OK;
-            }
         }
         Kern16 k16 = (kc16 == 64) ? ((p.T == 2) ? gram_tc16_kernel<2, 64> : gram_tc16_kernel<1, 64>)
                                   : ((p.T == 2) ? gram_tc16_kernel<2, 32> : gram_tc16_kernel<1, 32>);

@@ -162,7 +162,7 @@ class TensorNetwork:
         self._refine_floor = -1.0       # ridge values at or below this needed the fp64 Gram; go there directly
         # fp32 accumulation window (rows) of the tensor-core Gram when it only preconditions the exact refinement: longer = faster,
         # coarser (None = the library default of 2048, the window the stand-alone accuracy figures of the Gram are quoted for)
-        self.tc_flush_rows = 8192
+        self.tc_flush_rows = 16384
         self.small_site_fp64 = 2.0e9    # rows x unique Gram entries below which a site is built in fp64 outright (~0.5 ms of DMMA)
         self.process_group = None       # torch.distributed group: x, y are then this rank's row shard
         self.shard_offset = 0           # global index of this rank's first row

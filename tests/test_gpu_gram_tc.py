@@ -173,29 +173,6 @@ def test_f16_gram_special_cases():
     assert float((full - ref).norm() / ref.norm()) < 5e-3
 
 
-@pytest.mark.parametrize("shape", [(4096 + 70, 38, 29, 38), (20000, 38, 6, 38), (700, 24, 12, 38)])
-def test_f16_pair_kernel_same_bits_as_one_cta(shape, monkeypatch):
-    """CTA-pair fp16 kernel (gram_tc.cu::gram_tc16_pair_kernel: cta_group::2, each CTA synthesises its 128 rows of the two M = 256
-    U tiles and half of the V tile) against the 1-CTA fp16 kernel: same products, same accumulation order along the rows, same
-    flush windows, so M must agree to the bit; both against fp64 within the fp16 tolerance.  Ragged row counts, a flush boundary,
-    a V tile with padding columns (741 = 2 x 256 + 229)."""
-    S, ma, mb, mc = shape
-    g = torch.Generator(device=DEV).manual_seed(S + ma)
-    Fa = torch.randn((S, ma), device=DEV, generator=g)
-    Fb = torch.rand((S, mb), device=DEV, generator=g) * 2 - 1
-    Fc = torch.randn((S, mc), device=DEV, generator=g)
-    w = torch.rand((S,), device=DEV, generator=g) + 0.5
-    args = (Factor(Fa, m=ma), Factor(Fb, m=mb), Factor(Fc, m=mc), w, S)
-    monkeypatch.setenv("TN_TC16_PAIR", "0")
-    one = ops.gram(ops.GRAM_F16, *args, flush_rows=2048)
-    monkeypatch.setenv("TN_TC16_PAIR", "1")
-    two = ops.gram(ops.GRAM_F16, *args, flush_rows=2048)
-    torch.cuda.synchronize()
-    ref = ops.gram(ops.GRAM_FP64, *args)
-    assert gu.relerr(two.cpu().numpy(), ref.cpu().numpy()) < 5e-3
-    assert torch.equal(one, two)
-
-
 @pytest.mark.parametrize("shape", [(4096 + 70, 38, 29, 38), (6000, 24, 2, 24), (3000, 38, 6, 38), (2500, 38, 29, 1), (9000, 100, 9, 1),
                                    (1500, 7, 3, 5), (2000, 3, 40, 9)])
 def test_f16_run_ordered_producers(shape, monkeypatch):
@@ -210,15 +187,23 @@ def test_f16_run_ordered_producers(shape, monkeypatch):
     Fc = torch.randn((S, mc), device=DEV, generator=g)
     w = torch.rand((S,), device=DEV, generator=g) + 0.5
     args = (Factor(Fa, m=ma), Factor(Fb, m=mb), Factor(Fc, m=mc), w, S)
+    monkeypatch.setenv("TN_TC16_VIMG", "0")
     monkeypatch.setenv("TN_TC16_RUN", "0")
     one = ops.gram(ops.GRAM_F16, *args, flush_rows=2048)
     ref = ops.gram(ops.GRAM_FP64, *args)
-    outs = []
-    for variant in ("1", "2", "3"):      # 2 = 16 producer warps (U and V rows by different warps); 3 = loader warp instead of the producers' block barrier
-        monkeypatch.setenv("TN_TC16_RUN", variant)
-        two = ops.gram(ops.GRAM_F16, *args, flush_rows=2048)
-        torch.cuda.synchronize()
-        assert gu.relerr(two.cpu().numpy(), ref.cpu().numpy()) < 5e-3
-        assert gu.relerr(two.cpu().numpy(), one.cpu().numpy()) < 2e-3
-        outs.append(two)
-    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])       # same products in the same order, only the warp that forms them differs
+    monkeypatch.setenv("TN_TC16_RUN", "1")
+    two = ops.gram(ops.GRAM_F16, *args, flush_rows=2048)
+    torch.cuda.synchronize()
+    assert gu.relerr(two.cpu().numpy(), ref.cpu().numpy()) < 5e-3
+    assert gu.relerr(two.cpu().numpy(), one.cpu().numpy()) < 2e-3
+    again = ops.gram(ops.GRAM_F16, *args, flush_rows=2048)
+    assert torch.equal(two, again)          # deterministic: every tile of M has one owner
+    # pre-synthesised V images + pair products of the left factor (gram_tc16_vimg_kernel): operands rounded once from fp32 products
+    monkeypatch.setenv("TN_TC16_VIMG", "1")
+    three = ops.gram(ops.GRAM_F16, *args, flush_rows=2048)
+    torch.cuda.synchronize()
+    assert gu.relerr(three.cpu().numpy(), ref.cpu().numpy()) < 5e-3
+    assert gu.relerr(three.cpu().numpy(), one.cpu().numpy()) < 2e-3
+    assert torch.equal(three, ops.gram(ops.GRAM_F16, *args, flush_rows=2048))
+    acc = ops.gram(ops.GRAM_F16, *args, flush_rows=2048, M=three.clone(), accumulate=True)
+    assert gu.relerr(acc.cpu().numpy(), 2 * three.cpu().numpy()) < 1e-12
