@@ -62,6 +62,21 @@ __device__ __forceinline__ double map_eval(int map_kind, const double* __restric
     return v;
 }
 
+// The two halves of map_eval for software-pipelined kernels: the address to fetch now, the function to apply to the fetched value later.
+__device__ __forceinline__ const double* map_raw_ptr(int map_kind, const double* __restrict__ xrow, int p) {
+    return (map_kind == TN_MAP_IDENTITY) ? xrow + p : xrow;
+}
+__device__ __forceinline__ double map_apply(int map_kind, double raw, int p) {
+    if (map_kind == TN_MAP_IDENTITY) return raw;
+    if (map_kind == TN_MAP_SINCOS) {
+        const double a = (0.5 * 3.14159265358979323846) * raw;
+        return p == 0 ? cos(a) : sin(a);
+    }
+    double v = 1.0;
+    for (int d = 0; d < p; ++d) v *= raw;
+    return v;
+}
+
 int sm_count();   // of the calling thread's current device (cached per device)
 // Raise a kernel's dynamic shared-memory limit to at least `bytes` on the CURRENT device.  The attribute is per device and per
 // function; what has been set is remembered per (device, function) under a mutex, so a process that drives several GPUs (or

@@ -330,7 +330,7 @@ __global__ void __launch_bounds__(256, 1)
 rhs_big_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restrict__ w, int64_t rows, double* __restrict__ out,
                int64_t rows_per_split) {
     constexpr int stA = 8 * MT + 4, stC = 8 * NT + 4;      // == 4 (mod 8) doubles: conflict-free fragment loads
-    constexpr int BUF = RB_KC * (stA + stC + RB_PW);
+    constexpr int BUF = RB_KC * (stA + stC + RB_PW);       // the weights live in a padding column of the fc tile
     __shared__ __align__(16) double sm[2 * BUF];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fr = lane >> 2, fk = lane & 3;
@@ -340,9 +340,10 @@ rhs_big_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
     const int64_t k_end = min(rows, k_begin + rows_per_split);
     for (int i = tid; i < 2 * BUF; i += 256) sm[i] = 0.0;           // the padding columns stay zero
 
-    // chunk elements owned by this thread: [32 x mA of fa | 32 x mC of fc | 32 x 8 of w * fb[p0 + q]]
+    // chunk elements owned by this thread: [32 x mA of fa | 32 x mC of fc | 32 x 8 of fb[p0 + q] | 32 of w].  The prefetch only
+    // LOADS (raw values, nothing depends on them until the commit one chunk later); feature maps are applied at the commit.
     const int nA = RB_KC * fa.m, nC = RB_KC * fc.m, nB = RB_KC * RB_PW;
-    const int total = nA + nC + nB;
+    const int total = nA + nC + nB + RB_KC;
     int desc[RB_MAXPRE];            // (kind << 16) | (k << 8) | column
     double pre[RB_MAXPRE];
 #pragma unroll
@@ -351,7 +352,8 @@ rhs_big_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
         int d = -1;
         if (e < nA) { const int k = e / fa.m; d = (0 << 16) | (k << 8) | (e - k * fa.m); }
         else if (e < nA + nC) { const int e2 = e - nA; const int k = e2 / fc.m; d = (1 << 16) | (k << 8) | (e2 - k * fc.m); }
-        else if (e < total) { const int e2 = e - nA - nC; d = (2 << 16) | ((e2 >> 3) << 8) | (e2 & 7); }
+        else if (e < nA + nC + nB) { const int e2 = e - nA - nC; d = ((p0 + (e2 & 7) < fb.m ? 2 : 4) << 16) | ((e2 >> 3) << 8) | (e2 & 7); }
+        else if (e < total) { d = (3 << 16) | ((e - nA - nC - nB) << 8); }
         desc[q] = d;
     }
     auto prefetch = [&](int64_t kb) {
@@ -362,10 +364,15 @@ rhs_big_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
             if (d >= 0) {
                 const int kind = d >> 16, k = (d >> 8) & 255, c = d & 255;
                 const int64_t row = kb + k;
-                if (row < k_end) {
-                    if (kind == 0) v = map_eval(fa.map_kind, fa.ptr + (fa.div == 1 ? row : row / fa.div) * fa.ld, c);
-                    else if (kind == 1) v = map_eval(fc.map_kind, fc.ptr + (fc.div == 1 ? row : row / fc.div) * fc.ld, c);
-                    else if (p0 + c < fb.m) v = (w ? w[row] : 1.0) * map_eval(fb.map_kind, fb.ptr + (fb.div == 1 ? row : row / fb.div) * fb.ld, p0 + c);
+                if (row < k_end && kind != 4) {
+                    const double* src;
+                    if (kind == 0) src = map_raw_ptr(fa.map_kind, fa.ptr + (fa.div == 1 ? row : row / fa.div) * fa.ld, c);
+                    else if (kind == 1) src = map_raw_ptr(fc.map_kind, fc.ptr + (fc.div == 1 ? row : row / fc.div) * fc.ld, c);
+                    else if (kind == 2) src = map_raw_ptr(fb.map_kind, fb.ptr + (fb.div == 1 ? row : row / fb.div) * fb.ld, p0 + c);
+                    else src = w ? w + row : nullptr;
+                    v = src ? *src : 1.0;
+                } else if (kind != 3 && kind != 4 && row >= k_end) {
+                    v = __longlong_as_double(0x7ff8000000000001ll);      // marks "row past the end": the commit stores 0
                 }
             }
             pre[q] = v;
@@ -380,9 +387,12 @@ rhs_big_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
             const int d = desc[q];
             if (d >= 0) {
                 const int kind = d >> 16, k = (d >> 8) & 255, c = d & 255;
-                if (kind == 0) sA[k * stA + c] = pre[q];
-                else if (kind == 1) sC[k * stC + c] = pre[q];
-                else sB[k * RB_PW + c] = pre[q];
+                const double raw = pre[q];
+                const bool past = (__double_as_longlong(raw) == 0x7ff8000000000001ll);
+                if (kind == 0) sA[k * stA + c] = past ? 0.0 : map_apply(fa.map_kind, raw, c);
+                else if (kind == 1) sC[k * stC + c] = past ? 0.0 : map_apply(fc.map_kind, raw, c);
+                else if (kind == 2) sB[k * RB_PW + c] = past ? 0.0 : map_apply(fb.map_kind, raw, p0 + c);
+                else if (kind == 3) sC[k * stC + 8 * NT] = raw;      // 0 past the end (never loaded): the row contributes nothing
             }
         }
     };
@@ -406,7 +416,7 @@ rhs_big_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
             const double* sB = sC + RB_KC * stC;
 #pragma unroll 2
             for (int k4 = 0; k4 < RB_KC; k4 += 4) {
-                const double sc = sB[(k4 + fk) * RB_PW + warp];
+                const double sc = sB[(k4 + fk) * RB_PW + warp] * sC[(k4 + fk) * stC + 8 * NT];
                 double af[MT], bf[NT];
                 const double* ap = sA + (k4 + fk) * stA + fr;
                 const double* cp = sC + (k4 + fk) * stC + fr;

@@ -174,17 +174,6 @@ syrk_tc_kernel(SyrkTcParams p) {
         };
         issue_chunk(0);
         issue_chunk(1);
-        {   // pull this CTA's fp64 tile of C towards the L2 while the MMAs run: the epilogue's read-modify-write then waits on L2, not
-            // on HBM (the capture of round 1 has 17 % of the kernel's stall samples on those loads; 148 tiles x 512 KB fit the L2)
-            const int pr = tid - 32;                                    // row of the tile
-            const int64_t grow = r0 + pr;
-            if (grow < p.n) {
-                const double* rowp = p.C + grow * p.lda + q0;
-                const int64_t ncol = min((int64_t)ST_TILE, min(p.n - q0, grow - q0 + 1));      // lower triangle only
-                for (int64_t cc = 0; cc < ncol; cc += 16)
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(rowp + cc));
-            }
-        }
         for (int c = 0; c < nchunks; ++c) {
             asm volatile("cp.async.wait_group 1;" ::: "memory");        // this thread's pieces of chunk c have landed
             const uint32_t sb = stage_s + (uint32_t)(c % ST_NS) * ST_STAGE + off0;
@@ -233,7 +222,9 @@ syrk_tc_kernel(SyrkTcParams p) {
             double* dst = p.C + grow0 * p.lda + gcol;
             if (gcol < p.n) {
 #pragma unroll
-                for (int rr0 = 0; rr0 < 32; rr0 += 16) {           // 16 rows of 256 B in flight per warp
+                // 16 rows of 256 B in flight per warp.  (An L2 prefetch of the whole 512 KB tile at kernel start was measured and removed:
+                // it evicts the panel the MMAs stream from L2 -- P = 41 876 mixed solve 337 -> 650-900 ms, profiles/r2_chol_prefetch.txt.)
+                for (int rr0 = 0; rr0 < 32; rr0 += 16) {
                     double cv[16];
 #pragma unroll
                     for (int e = 0; e < 16; ++e) {
