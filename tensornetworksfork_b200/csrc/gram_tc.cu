@@ -1726,6 +1726,8 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
         const int nq_max = 255 / p.nB + 2;
         int NSV = 4;
         while (NSV >= 2 && tc16_vimg_smem_bytes(B.m, p.BN, nq_max, NSV) > 226 * 1024) --NSV;
+        // (A CTA-pair variant of this kernel -- cta_group::2, half of the V image per CTA, four stages -- produced bit-identical M and
+        // was 10 % slower on the config-5a site, 23 % on config 5b: profiles/r2_gram_tc16_vimg_probe.jsonl; removed.)
         if (NSV >= 2) {
             const int64_t zchunks = p.zpitch / 64;
             const int ytiles = (int)ceil_div64(p.nC, p.BN);
@@ -1770,10 +1772,12 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
             v.rows_per_split = ceil_div64(ceil_div64(p.zpitch, ksv), 64) * 64;
             ksv = ceil_div64(p.zpitch, v.rows_per_split);
             TN_CHECK_ARG(gyv <= 65535 && gxv <= 0x7fffffff, "tn_gram_kr3: grid too large");
-            const size_t vsmem = tc16_vimg_smem_bytes(B.m, p.BN, nq_max, NSV);
-            TN_SMEM(gram_tc16_vimg_kernel, vsmem);
-            dim3 gridv((unsigned)gxv, (unsigned)gyv, (unsigned)ksv);
-            gram_tc16_vimg_kernel<<<gridv, VI_THREADS, vsmem, st>>>(v);
+            {
+                const size_t vsmem = tc16_vimg_smem_bytes(B.m, p.BN, nq_max, NSV);
+                TN_SMEM(gram_tc16_vimg_kernel, vsmem);
+                dim3 gridv((unsigned)gxv, (unsigned)gyv, (unsigned)ksv);
+                gram_tc16_vimg_kernel<<<gridv, VI_THREADS, vsmem, st>>>(v);
+            }
             TN_LAUNCH_CHECK();
             TN_CUDA(cudaFreeAsync(buf, st));
             return TN_OK;
