@@ -1032,6 +1032,18 @@ static size_t tc16_run_smem_bytes(int mA, int mB, int mC, int BN, int NS) {
 //    which frees the shared memory for a third operand stage (the V image needs about a microsecond from L2);
 //  * a U entry is pa[qa] fb[ib] * fb[jb]: the run prefix is two loads and one product.
 // Warp roles (352 threads): 0 = MMA issuer, 1..8 = U producers / drain, 9 = raw-ring loader, 10 = V-image loader.
+// Shared-memory matrix descriptor, K-major, SWIZZLE_128B: rows of 128 bytes, 8-row groups 1024 bytes apart (SBO), the 16-byte chunk index of
+// a row XORed with row % 8 by the hardware; LBO is not used by this mode (encoded as 1).  Tile bases are 1024-byte aligned.
+__device__ __forceinline__ uint64_t make_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
 struct VimgParams {
     const unsigned long long* amax;
     const __half* Zc;        // [chunk][8 planes][psc / 2]: rows fb[0..mB) and the zero row, 8 samples per row and plane
@@ -1043,6 +1055,7 @@ struct VimgParams {
     int mA, mB, mC;
     int nA, nB, nC;
     int BN, nstages, flush_rows, nq_max;
+    int sw128;               // 1: operand tiles in the 128-byte-swizzled K-major layout (rows of 128 B = the 64 samples of a stage, 16-byte chunk index XOR row % 8)
     int dbg;                 // TN_TC16_DBG (measurement only, wrong results): 1 = no U synthesis, 2 = no MMAs, 8 = no raw ring, 32 = no drain, 64 = no V copies
 };
 constexpr int VI_THREADS = 32 * 11;
@@ -1051,7 +1064,7 @@ constexpr int VI_THREADS = 32 * 11;
 __global__ void __launch_bounds__(256)
 tc16_vimg_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __restrict__ w, int64_t rows, const unsigned long long* __restrict__ amax,
                        __half* __restrict__ Zc, __half* __restrict__ Zpa, __half* __restrict__ Vimg, int nA, int nC, int BN, int ytiles,
-                       int64_t zchunks, uint32_t psc, uint32_t lbo_b) {
+                       int64_t zchunks, uint32_t psc, uint32_t lbo_b, int sw128) {
     extern __shared__ float vs[];
     const int mA = fa.m, mB = fb.m, mC = fc.m;
     constexpr int LD = 65;
@@ -1120,7 +1133,10 @@ tc16_vimg_stage_kernel(TcFactor fa, TcFactor fb, TcFactor fc, const double* __re
         const int gv = y * BN + r;
         uint4 o = make_uint4(0u, 0u, 0u, 0u);
         if (gv < nC) o = pack8(sC + tC[2 * gv] * LD + pc * 8, sC + tC[2 * gv + 1] * LD + pc * 8);
-        *reinterpret_cast<uint4*>(Vimg + (((int64_t)y * zchunks + chunk) * 8 + pc) * (int64_t)(lbo_b / 2) + r * 8) = o;
+        if (sw128)      // image of BN rows x 128 B, 8-row groups of 1024 B, chunk ^= row % 8
+            *reinterpret_cast<uint4*>(Vimg + ((int64_t)y * zchunks + chunk) * (int64_t)(BN * 64) + (r >> 3) * 512 + (r & 7) * 64 + ((pc ^ (r & 7)) * 8)) = o;
+        else
+            *reinterpret_cast<uint4*>(Vimg + (((int64_t)y * zchunks + chunk) * 8 + pc) * (int64_t)(lbo_b / 2) + r * 8) = o;
     }
 }
 
@@ -1133,9 +1149,11 @@ gram_tc16_vimg_kernel(VimgParams p) {
     const int BN = p.BN, NS = p.nstages;
     const int mB = p.mB;
 
+    const bool sw = p.sw128 != 0;
     const uint32_t lbo_b = (uint32_t)BN * 16 + 16;
-    const uint32_t v_bytes = 8 * lbo_b;
-    const uint32_t stage_bytes = T * RUN_A_TILE + v_bytes;
+    const uint32_t v_bytes = sw ? (uint32_t)BN * 128 : 8 * lbo_b;
+    const uint32_t a_tile = sw ? (uint32_t)TC_M * 128 : RUN_A_TILE;
+    const uint32_t stage_bytes = T * a_tile + v_bytes;
     const uint32_t psc = run_plane_stride((uint32_t)mB + 1);       // plane of the common rows (fb + the zero row)
     const uint32_t common_bytes = 8 * psc;
     const uint32_t slot_bytes = common_bytes + (uint32_t)p.nq_max * 128;
@@ -1204,16 +1222,21 @@ gram_tc16_vimg_kernel(VimgParams p) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t sb = smem_u32(stage_base + (size_t)s * stage_bytes);
-                const uint32_t b_base = sb + T * RUN_A_TILE;
+                const uint32_t b_base = sb + T * a_tile;
 #pragma unroll
                 for (int t = 0; t < T; ++t) {
-                    const uint32_t a_base = sb + (uint32_t)t * RUN_A_TILE;
+                    const uint32_t a_base = sb + (uint32_t)t * a_tile;
                     const uint32_t d = tmem_base + (uint32_t)(t * BN);
 #pragma unroll
                     for (int j = 0; j < H_KC / 16; ++j) {
-                        const uint32_t ao = (uint32_t)(2 * j) * RUN_LBO_A, bo = (uint32_t)(2 * j) * lbo_b;
                         const uint32_t acc0 = (first_of_window && j == 0) ? 0u : 1u;
-                        if (!(p.dbg & 2)) umma_f16(d, make_desc(a_base + ao, RUN_LBO_A, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
+                        if (p.dbg & 2) continue;
+                        if (sw) {       // K step j = 32 bytes further inside the 128-byte rows
+                            umma_f16(d, make_desc_sw128(a_base + 32u * j), make_desc_sw128(b_base + 32u * j), idesc, acc0);
+                        } else {
+                            const uint32_t ao = (uint32_t)(2 * j) * RUN_LBO_A, bo = (uint32_t)(2 * j) * lbo_b;
+                            umma_f16(d, make_desc(a_base + ao, RUN_LBO_A, sbo), make_desc(b_base + bo, lbo_b, sbo), idesc, acc0);
+                        }
                     }
                 }
                 umma_commit(&empty[s]);
@@ -1256,7 +1279,7 @@ gram_tc16_vimg_kernel(VimgParams p) {
                 if (p.dbg & 64) { mbar_arrive(&full[s]); continue; }
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(v_bytes) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(stage_s + (uint32_t)s * stage_bytes + T * RUN_A_TILE), "l"(src), "r"(v_bytes), "r"(bar) : "memory");
+                             ::"r"(stage_s + (uint32_t)s * stage_bytes + T * a_tile), "l"(src), "r"(v_bytes), "r"(bar) : "memory");
             }
         }
     } else {
@@ -1283,7 +1306,9 @@ gram_tc16_vimg_kernel(VimgParams p) {
             ur.last[i] = last * 16u;
         }
         run_rows_finish(ur);
-        const uint32_t udst = (uint32_t)(grp >> 4) * RUN_A_TILE + (uint32_t)pc * RUN_LBO_A + (uint32_t)((8 * grp) & 127) * 16;
+        // padded slabs: tile, piece slab, row;  swizzled: tile, 8-row group of 1024 B (row i of it at i * 128, chunk pc ^ i)
+        const uint32_t udst = sw ? (uint32_t)(grp >> 4) * a_tile + (uint32_t)(grp & 15) * 1024
+                                 : (uint32_t)(grp >> 4) * RUN_A_TILE + (uint32_t)pc * RUN_LBO_A + (uint32_t)((8 * grp) & 127) * 16;
         const uint32_t stage_s = smem_u32(stage_base);
         auto u_prefix = [&](uint32_t slot, uint32_t key) -> uint4 {
             const uint4 a = lds128u(slot + common_bytes + (key >> 10) * 128u + (uint32_t)pc * 16u);      // pa[qa]
@@ -1312,7 +1337,8 @@ gram_tc16_vimg_kernel(VimgParams p) {
                 for (int i = 0; i < 8; ++i) {
                     uint4 pre = sel8((ur.selB >> i) & 1u, preB, preA);
                     if ((ur.slow >> i) & 1u) pre = u_prefix(slot, ur.key[i]);
-                    sts128u(sb + udst + (uint32_t)i * 16u, hmul8(pre, x[i]));
+                    const uint32_t off = sw ? (uint32_t)i * 128u + (uint32_t)((pc ^ i) * 16) : (uint32_t)i * 16u;
+                    sts128u(sb + udst + off, hmul8(pre, x[i]));
                 }
             }
             fence_proxy_async();
@@ -1756,12 +1782,13 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
             v.mA = A.m; v.mB = B.m; v.mC = C.m;
             v.nA = p.nA; v.nB = p.nB; v.nC = p.nC;
             v.BN = p.BN; v.nstages = NSV; v.flush_rows = p.flush_rows; v.nq_max = nq_max; v.dbg = p.dbg;
+            v.sw128 = (getenv("TN_TC16_SW128") && atoi(getenv("TN_TC16_SW128")) != 0) ? 1 : 0;
             const size_t ssmem = (size_t)(2 * A.m + B.m + C.m) * 65 * sizeof(float) + (size_t)(p.nA + p.nC) * 2 * sizeof(short);
             TN_CHECK_ARG(ssmem <= 200 * 1024, "tn_gram_kr3 (fp16): factors %d+%d+%d too wide for the staging pass", A.m, B.m, C.m);
             TN_SMEM(tc16_vimg_stage_kernel, ssmem);
             tc16_vimg_stage_kernel<<<(unsigned)zchunks, 256, ssmem, st>>>(A, B, C, w, rows, amaxv, reinterpret_cast<__half*>(buf),
                                                                        reinterpret_cast<__half*>(buf + zc_bytes), reinterpret_cast<__half*>(buf + zc_bytes + zpa_bytes),
-                                                                       p.nA, p.nC, p.BN, ytiles, zchunks, psc, lbo_b);
+                                                                       p.nA, p.nC, p.BN, ytiles, zchunks, psc, lbo_b, v.sw128);
             TN_LAUNCH_CHECK();
             const int64_t gxv = ceil_div64(nU, (int64_t)TC_M * 2), gyv = ytiles;
             int64_t ksv = ceil_div64((int64_t)sm_count(), gxv * gyv);

@@ -207,3 +207,8 @@ def test_f16_run_ordered_producers(shape, monkeypatch):
     assert torch.equal(three, ops.gram(ops.GRAM_F16, *args, flush_rows=2048))
     acc = ops.gram(ops.GRAM_F16, *args, flush_rows=2048, M=three.clone(), accumulate=True)
     assert gu.relerr(acc.cpu().numpy(), 2 * three.cpu().numpy()) < 1e-12
+    # operand tiles in the 128-byte-swizzled K-major layout: the same operands in another arrangement -> the same bits
+    monkeypatch.setenv("TN_TC16_SW128", "1")
+    four = ops.gram(ops.GRAM_F16, *args, flush_rows=2048)
+    torch.cuda.synchronize()
+    assert torch.equal(three, four)

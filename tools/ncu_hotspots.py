@@ -36,6 +36,21 @@ def main():
     for s, f, ln, src, r in sorted(out, key=lambda o: -o[0])[:top]:
         st = sorted(((int(r[i]), h) for i, h in stalls), reverse=True)[:2]
         print(f"{100 * s / tot:5.1f}%  {f}:{ln:<4d} {src[:88]:88s} {st[0][1]}={st[0][0]} {st[1][1]}={st[1][0]}")
+    # shared-memory wavefronts per source line (the data pipe the tensor-core kernels are bound by): total, ideal, excessive
+    cols = {h: i for i, h in enumerate(hdr)}
+    wf = next((h for h in hdr if h.startswith("L1 Wavefronts Shared") and "Excessive" not in h and "Ideal" not in h), None)
+    ex = next((h for h in hdr if h.startswith("L1 Wavefronts Shared Excessive")), None)
+    if wf and ex:
+        def num(r, h):
+            try:
+                return int(float(r[cols[h]].replace(",", "")))
+            except ValueError:
+                return 0
+        rows_wf = sorted(((num(r, wf), num(r, ex), f, ln, src) for _, f, ln, src, r in out), reverse=True)
+        twf = sum(x[0] for x in rows_wf) or 1
+        print(f"# shared-memory wavefronts by source line ({twf} in total, {sum(x[1] for x in rows_wf)} excessive)")
+        for w_, e_, f, ln, src in rows_wf[:20]:
+            print(f"{100 * w_ / twf:5.1f}%  {f}:{ln:<4d} wavefronts={w_} excessive={e_}  {src[:80]}")
 
 
 if __name__ == "__main__":
