@@ -182,183 +182,6 @@ kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
     }
 }
 
-// ---- fp64 Gram, software-pipelined (MODE 1 of the kernel above, same tiles, same DMMA fragments, same results up to the order of
-// the row sum inside a 16-row chunk).  The capture of kr3_f64_kernel<1> (profiles/r2_ncu_kr3_f64.txt) has the FP64 tensor pipe 42 % active:
-// three block barriers per 32-row chunk, the raw factors fetched from global memory (with an integer division per element) between two
-// of them, nothing overlapped.  Here (a) the raw factors of chunk c+1 are prefetched into registers while chunk c is synthesised and
-// multiplied -- load-only, per-thread element descriptors computed once, the feature map applied at the commit --, (b) the synthesised
-// operand tiles are double buffered, so the synthesis of chunk c+1 by fast warps overlaps the DMMAs of chunk c of slow ones, and
-// (c) two barriers per 16-row chunk remain (raw factors visible / tiles visible).  Two CTAs per SM as before.
-constexpr int G2_KC = 16;
-constexpr int G2_MAXPRE = 12;        // raw elements per thread and chunk: 16 * (mA + mB + mC + 1) / 256 <= 12  ->  mA + mB + mC <= 191
-
-__global__ void __launch_bounds__(GR_THREADS, 2)
-gram_f64_pipe_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restrict__ w, int64_t rows, double* __restrict__ out,
-                     int nA, int nB, int nC, int64_t rows_per_split) {
-    extern __shared__ double sm[];
-    const int stA = fa.m | 1, stB = fb.m | 1, stC = fc.m | 1;
-    double* sFA = sm;                              // [G2_KC][stA]
-    double* sFB = sFA + G2_KC * stA;
-    double* sFC = sFB + G2_KC * stB;
-    double* sW = sFC + G2_KC * stC;                // [G2_KC]
-    double* sU = sW + G2_KC;                       // [2][G2_KC][GR_SU]
-    double* sV = sU + 2 * G2_KC * GR_SU;           // [2][G2_KC][GR_SV]
-    short* tIA = reinterpret_cast<short*>(sV + 2 * G2_KC * GR_SV);
-    short* tJA = tIA + GR_TU;
-    short* tIB = tJA + GR_TU;
-    short* tJB = tIB + GR_TU;
-    short* tIC = tJB + GR_TU;
-    short* tJC = tIC + GR_TV;
-
-    const int tid = threadIdx.x;
-    const int64_t nU = (int64_t)nA * nB;
-    const int64_t u0 = (int64_t)blockIdx.x * GR_TU;
-    const int v0 = blockIdx.y * GR_TV;
-    const int64_t k_begin = (int64_t)blockIdx.z * rows_per_split;
-    const int64_t k_end = min(rows, k_begin + rows_per_split);
-
-    if (tid < GR_TU) {
-        const int64_t gu = u0 + tid;
-        int ia = -1, ja = 0, ib = 0, jb = 0;
-        if (gu < nU) {
-            const int qa = (int)(gu / nB), qb = (int)(gu - (int64_t)qa * nB);
-            pair_decode(qa, fa.m, ia, ja);
-            pair_decode(qb, fb.m, ib, jb);
-        }
-        tIA[tid] = (short)ia; tJA[tid] = (short)ja; tIB[tid] = (short)ib; tJB[tid] = (short)jb;
-    } else if (tid < GR_TU + GR_TV) {
-        const int t = tid - GR_TU;
-        const int gv = v0 + t;
-        int ic = -1, jc = 0;
-        if (gv < nC) pair_decode(gv, fc.m, ic, jc);
-        tIC[t] = (short)ic; tJC[t] = (short)jc;
-    }
-
-    // raw elements of a chunk owned by this thread: [KC x mA | KC x mB | KC x mC | KC weights]
-    const int eA = G2_KC * fa.m, eB = G2_KC * fb.m, eC = G2_KC * fc.m;
-    const int total = eA + eB + eC + G2_KC;
-    int desc[G2_MAXPRE];            // (kind << 16) | (k << 8) | column
-    double pre[G2_MAXPRE];
-#pragma unroll
-    for (int q = 0; q < G2_MAXPRE; ++q) {
-        const int e = tid + GR_THREADS * q;
-        int d = -1;
-        if (e < eA) { const int k = e / fa.m; d = (0 << 16) | (k << 8) | (e - k * fa.m); }
-        else if (e < eA + eB) { const int e2 = e - eA; const int k = e2 / fb.m; d = (1 << 16) | (k << 8) | (e2 - k * fb.m); }
-        else if (e < eA + eB + eC) { const int e2 = e - eA - eB; const int k = e2 / fc.m; d = (2 << 16) | (k << 8) | (e2 - k * fc.m); }
-        else if (e < total) { d = (3 << 16) | ((e - eA - eB - eC) << 8); }
-        desc[q] = d;
-    }
-    auto prefetch = [&](int64_t kb) {
-#pragma unroll
-        for (int q = 0; q < G2_MAXPRE; ++q) {
-            const int d = desc[q];
-            double v = 0.0;
-            if (d >= 0) {
-                const int kind = d >> 16, k = (d >> 8) & 255, c = d & 255;
-                const int64_t row = kb + k;
-                if (row < k_end) {
-                    const double* src;
-                    if (kind == 0) src = map_raw_ptr(fa.map_kind, fa.ptr + (fa.div == 1 ? row : row / fa.div) * fa.ld, c);
-                    else if (kind == 1) src = map_raw_ptr(fb.map_kind, fb.ptr + (fb.div == 1 ? row : row / fb.div) * fb.ld, c);
-                    else if (kind == 2) src = map_raw_ptr(fc.map_kind, fc.ptr + (fc.div == 1 ? row : row / fc.div) * fc.ld, c);
-                    else src = w ? w + row : nullptr;
-                    v = src ? *src : 1.0;
-                } else if (kind != 3) {
-                    v = __longlong_as_double(0x7ff8000000000001ll);      // "row past the end": the commit stores 0
-                }
-            }
-            pre[q] = v;
-        }
-    };
-    auto commit = [&]() {
-#pragma unroll
-        for (int q = 0; q < G2_MAXPRE; ++q) {
-            const int d = desc[q];
-            if (d >= 0) {
-                const int kind = d >> 16, k = (d >> 8) & 255, c = d & 255;
-                const double raw = pre[q];
-                const bool past = (__double_as_longlong(raw) == 0x7ff8000000000001ll);
-                if (kind == 0) sFA[k * stA + c] = past ? 0.0 : map_apply(fa.map_kind, raw, c);
-                else if (kind == 1) sFB[k * stB + c] = past ? 0.0 : map_apply(fb.map_kind, raw, c);
-                else if (kind == 2) sFC[k * stC + c] = past ? 0.0 : map_apply(fc.map_kind, raw, c);
-                else sW[k] = raw;                  // 0 past the end (never loaded)
-            }
-        }
-    };
-
-    // 8 warps as 4 (u) x 2 (v): each warp owns a 32 x 32 block of the tile = 4 x 4 DMMA m8n8k4 accumulators
-    const int lane = tid & 31, warp = tid >> 5;
-    const int wu = (warp >> 1) * 32, wv = (warp & 1) * 32;
-    const int fr = lane >> 2, fk = lane & 3;
-    double acc[4][4][2];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-
-    if (k_begin < k_end) prefetch(k_begin);
-    int buf = 0;
-    for (int64_t kb = k_begin; kb < k_end; kb += G2_KC, buf ^= 1) {
-        commit();                      // the raw buffers are free: every warp finished synthesising the previous chunk before barrier (C) below
-        __syncthreads();               // (B) raw factors of this chunk (and, first pass, the tables) visible
-        if (kb + G2_KC < k_end) prefetch(kb + G2_KC);
-        double* cU = sU + buf * (G2_KC * GR_SU);
-        double* cV = sV + buf * (G2_KC * GR_SV);
-        for (int idx = tid; idx < G2_KC * GR_TU; idx += GR_THREADS) {
-            const int k = idx >> 7, u = idx & (GR_TU - 1);
-            const int ia = tIA[u];
-            double v = 0.0;
-            if (ia >= 0) {
-                const double* a = sFA + k * stA;
-                const double* b = sFB + k * stB;
-                v = sW[k] * a[ia] * a[tJA[u]] * b[tIB[u]] * b[tJB[u]];
-            }
-            cU[k * GR_SU + u] = v;
-        }
-        for (int idx = tid; idx < G2_KC * GR_TV; idx += GR_THREADS) {
-            const int k = idx >> 6, t = idx & (GR_TV - 1);
-            const int ic = tIC[t];
-            double v = 0.0;
-            if (ic >= 0) {
-                const double* c = sFC + k * stC;
-                v = c[ic] * c[tJC[t]];
-            }
-            cV[k * GR_SV + t] = v;
-        }
-        __syncthreads();               // (C) tiles of this chunk visible; the other buffer may still be read by slower warps
-#pragma unroll
-        for (int k4 = 0; k4 < G2_KC; k4 += 4) {
-            double af[4], bf[4];
-            const double* up = cU + (k4 + fk) * GR_SU + wu + fr;
-            const double* vp = cV + (k4 + fk) * GR_SV + wv + fr;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) af[i] = up[i * 8];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = vp[j * 8];
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-        }
-    }
-
-    double* o = out + (int64_t)blockIdx.z * nU * nC;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const int64_t gu = u0 + wu + i * 8 + fr;
-        if (gu >= nU) continue;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                const int gv = v0 + wv + j * 8 + 2 * fk + e;
-                if (gv < nC) o[gu * nC + gv] = acc[i][j][e];
-            }
-        }
-    }
-}
-
 // Right-hand side for small cores (P <= 4096): up to four entries of b per thread, rows streamed through shared memory in tiles.
 // The GEMM-shaped kernel above wastes most of its 128 x 64 tile when P is a few hundred.
 constexpr int RS_ROWS = 64;
@@ -682,16 +505,10 @@ static int launch_kr3(const tn_factor* fa, const tn_factor* fb, const tn_factor*
     const int64_t gx = ceil_div64(nU, GR_TU), gy = ceil_div64(nC, GR_TV);
     TN_CHECK_ARG(gy <= 65535 && ksplit <= 65535 && gx <= 0x7fffffff, "kr3: grid too large");
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)ksplit);
-    if (MODE == 1 && a.m + b.m + c.m <= 191 && a.m < 256 && b.m < 256 && c.m < 256 && !getenv("TN_GRAM_F64_NO_PIPE")) {
-        // software-pipelined kernel (register prefetch of the raw factors, double-buffered operand tiles)
-        const size_t psmem = (size_t)(G2_KC * ((a.m | 1) + (b.m | 1) + (c.m | 1)) + G2_KC + 2 * G2_KC * GR_SU + 2 * G2_KC * GR_SV) * sizeof(double) +
-                             (size_t)(4 * GR_TU + 2 * GR_TV) * sizeof(short);
-        TN_SMEM(gram_f64_pipe_kernel, psmem);
-        gram_f64_pipe_kernel<<<grid, GR_THREADS, psmem, st>>>(a, b, c, w, rows, direct ? dst : work, nA, nB, nC, rps);
-    } else {
-        TN_SMEM(kr3_f64_kernel<MODE>, smem);
-        kr3_f64_kernel<MODE><<<grid, GR_THREADS, smem, st>>>(a, b, c, w, rows, direct ? dst : work, nA, nB, nC, rps, t1, t2, t3);
-    }
+    // (A software-pipelined variant -- register prefetch of the raw factors, double-buffered operand tiles, two barriers per 16-row chunk --
+    // gave the same bits and was 10-20 % SLOWER than this three-barrier kernel: profiles/r2_gram_f64_probe.jsonl; removed.)
+    TN_SMEM(kr3_f64_kernel<MODE>, smem);
+    kr3_f64_kernel<MODE><<<grid, GR_THREADS, smem, st>>>(a, b, c, w, rows, direct ? dst : work, nA, nB, nC, rps, t1, t2, t3);
     TN_LAUNCH_CHECK();
     if (!direct) {
         int64_t blocks = ceil_div64(n, 256);
