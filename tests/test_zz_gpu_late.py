@@ -1,13 +1,13 @@
 """GPU parity tests of the host flows added late in round 1 (needs a B200).
 
 They drive the same kernels, at the same kinds of shapes, as the files before them -- only the host flow is new -- and each has a
-twin on the CPU stand-in kernels (named in its docstring).  They ran on a B200 once, in the last seconds of the round's GPU budget
-(``profiles/r1_pytest_gpu_late.log``, ``-rxX`` summary only): ten passed; ``test_conv_growing_flow_gpu`` did not.  The cause was found
-afterwards on the CPU: after ``grow_cart`` the old last cores are stride-0 broadcasts, and a pixel-core Jacobian handed such a
-core to ``tn_rows_dot``, whose wrapper asserts unit row stride -- the CPU stand-ins did not enforce the kernels' layout contracts
-and let it through.  The stand-ins now assert the same contracts (``tests/fake_ops.py``), the twin reproduced the failure, and
-``conv._to_canon`` densifies broadcast cores.  The fix has not run on hardware (no GPU minutes left), so that one test keeps a
-non-strict ``xfail`` until it has.  The file sorts last so that it cannot hide other results under ``pytest -x``.
+twin on the CPU stand-in kernels (named in its docstring).  History: in round 1 they ran once behind non-strict markers and
+``test_conv_growing_flow_gpu`` failed (after ``grow_cart`` the old last cores are stride-0 broadcasts, and a pixel-core Jacobian
+handed such a core to ``tn_rows_dot``, whose wrapper asserts unit row stride); the CPU stand-ins now assert the kernels' layout
+contracts (``tests/fake_ops.py``), ``conv._to_canon`` densifies broadcast cores, and since round 2 every test of this file runs
+WITHOUT markers and passes on hardware (``profiles/r2_pytest_gpu_call24.log``), including the tensor-core twins of the BASELINE
+configurations, which follow the reference recordings through the exact refinement.  The file sorts last so that it cannot hide
+other results under ``pytest -x``.
 """
 import os
 
