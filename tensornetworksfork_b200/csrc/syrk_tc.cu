@@ -23,10 +23,10 @@ constexpr int ST_KC = 16;                                   // k per pipeline st
 constexpr int ST_NS = 3;                                    // stages
 constexpr int ST_PROD_WARPS = 8;
 constexpr int ST_THREADS = 32 + 32 * ST_PROD_WARPS;
-constexpr uint32_t ST_A_TILE = ST_M * ST_KC * 4;            // bytes of one 128-row operand tile (hi or lo)
-constexpr uint32_t ST_B_TILE = ST_BN * ST_KC * 4;
-constexpr uint32_t ST_STAGE = 2 * ST_T * ST_A_TILE + 2 * ST_B_TILE;   // [t0 hi][t0 lo][t1 hi][t1 lo][b hi][b lo]
-constexpr size_t ST_SMEM = (size_t)ST_NS * ST_STAGE + (2 * ST_NS + 1) * 8 + 16;
+constexpr uint32_t ST_BLK = ST_TILE * ST_KC * 4;            // bytes of one 256-row x 16-k operand block: [piece of 4 k][256 rows][16 B]
+constexpr uint32_t ST_LBO = ST_TILE * 16;                   // bytes between two 4-k pieces of a block
+constexpr uint32_t ST_STAGE = 4 * ST_BLK;                   // [row block hi][column block hi][row block lo][column block lo]
+constexpr size_t ST_SMEM = (size_t)ST_NS * ST_STAGE + (3 * ST_NS + 1) * 8 + 16;
 
 struct SyrkTcParams {
     const float* X;     // n_pad x pitch, X[r][k] = (float)A[c0 + r][k0 + k], zero for r >= n
@@ -40,11 +40,16 @@ struct SyrkTcParams {
     int nct;            // tile columns to update (== nt: the whole lower triangle; smaller: only the leading column tiles)
 };
 
+// X = (float) of the panel, stored as the IMAGES the update kernel's stages are made of: for every block of 256 rows and every chunk
+// of 16 k one contiguous 16 KB block [piece of 4 k][256 rows][4 floats] (the UMMA K-major core-matrix layout, LBO = 4096 B), so that a
+// stage operand is ONE bulk copy.  (Round 1 filled the stages with 16-byte cp.async: its capture attributes 67 % of the kernel's
+// shared-memory wavefronts to LDGSTS replays -- about one wavefront per 32-byte sector whatever the bank pattern.)
 __global__ void __launch_bounds__(256)
 syrk_tc_convert_kernel(const double* __restrict__ A, int64_t lda, int64_t c0, int64_t k0, int64_t n, int kb, float* __restrict__ X,
                        int64_t pitch, int64_t n_pad) {
     const int64_t q4 = pitch / 4;
     const int64_t total = n_pad * q4;
+    const int64_t nchunks = pitch / ST_KC;
     for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
         const int64_t r = idx / q4;
         const int k = (int)(idx - r * q4) * 4;
@@ -56,7 +61,9 @@ syrk_tc_convert_kernel(const double* __restrict__ A, int64_t lda, int64_t c0, in
             if (k + 2 < kb) v.z = (float)src[2];
             if (k + 3 < kb) v.w = (float)src[3];
         }
-        reinterpret_cast<float4*>(X)[idx] = v;
+        const int64_t rb = r / ST_TILE, rr = r - rb * ST_TILE;
+        const int64_t chunk = k / ST_KC, piece = (k % ST_KC) / 4;
+        reinterpret_cast<float4*>(X)[((rb * nchunks + chunk) * 4 + piece) * ST_TILE + rr] = v;
     }
 }
 
@@ -90,13 +97,15 @@ syrk_tc_kernel(SyrkTcParams p) {
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + (size_t)ST_NS * ST_STAGE);
     uint64_t* full = bars;               // [NS]  producers -> MMA
     uint64_t* empty = bars + ST_NS;      // [NS]  tcgen05.commit -> producers
-    uint64_t* acc_full = bars + 2 * ST_NS;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * ST_NS + 1);
+    uint64_t* raw_full = bars + 2 * ST_NS;   // [NS]  the two bulk copies of a stage have landed
+    uint64_t* acc_full = bars + 3 * ST_NS;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * ST_NS + 1);
 
     if (tid == 0) {
         for (int s = 0; s < ST_NS; ++s) {
             mbar_init(&full[s], ST_PROD_WARPS);
             mbar_init(&empty[s], 1);
+            mbar_init(&raw_full[s], 1);
         }
         mbar_init(acc_full, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -112,27 +121,26 @@ syrk_tc_kernel(SyrkTcParams p) {
         // =============================== MMA issuer ===============================
         if (lane == 0) {
             const uint32_t idesc = make_idesc(ST_M, ST_BN);
-            constexpr uint32_t lbo_a = ST_M * 16, lbo_b = ST_BN * 16, sbo = 128;
+            constexpr uint32_t sbo = 128;
             int s = 0;
             uint32_t ph = 0;
             for (int c = 0; c < nchunks; ++c) {
                 mbar_wait(&full[s], ph);
                 tc_fence_after();
                 const uint32_t sb = smem_u32(stage_base + (size_t)s * ST_STAGE);
-                const uint32_t b_hi = sb + 2 * ST_T * ST_A_TILE;
-                const uint32_t b_lo = b_hi + ST_B_TILE;
+                const uint32_t b_hi = sb + ST_BLK, b_lo = sb + 3 * ST_BLK;
 #pragma unroll
                 for (int t = 0; t < ST_T; ++t) {
-                    const uint32_t a_hi = sb + (uint32_t)t * 2 * ST_A_TILE;
-                    const uint32_t a_lo = a_hi + ST_A_TILE;
+                    const uint32_t a_hi = sb + (uint32_t)t * (ST_M * 16);          // rows t * 128 .. of the 256-row block
+                    const uint32_t a_lo = a_hi + 2 * ST_BLK;
                     const uint32_t d = tmem_base + (uint32_t)(t * ST_BN);
 #pragma unroll
                     for (int j = 0; j < ST_KC / 8; ++j) {
-                        const uint32_t ao = (uint32_t)(2 * j) * lbo_a, bo = (uint32_t)(2 * j) * lbo_b;
-                        umma_tf32(d, make_desc(a_hi + ao, lbo_a, sbo), make_desc(b_hi + bo, lbo_b, sbo), idesc, (c == 0 && j == 0) ? 0u : 1u);
+                        const uint32_t ko = (uint32_t)(2 * j) * ST_LBO;
+                        umma_tf32(d, make_desc(a_hi + ko, ST_LBO, sbo), make_desc(b_hi + ko, ST_LBO, sbo), idesc, (c == 0 && j == 0) ? 0u : 1u);
                         if (SPLIT) {
-                            umma_tf32(d, make_desc(a_hi + ao, lbo_a, sbo), make_desc(b_lo + bo, lbo_b, sbo), idesc, 1u);
-                            umma_tf32(d, make_desc(a_lo + ao, lbo_a, sbo), make_desc(b_hi + bo, lbo_b, sbo), idesc, 1u);
+                            umma_tf32(d, make_desc(a_hi + ko, ST_LBO, sbo), make_desc(b_lo + ko, ST_LBO, sbo), idesc, 1u);
+                            umma_tf32(d, make_desc(a_lo + ko, ST_LBO, sbo), make_desc(b_hi + ko, ST_LBO, sbo), idesc, 1u);
                         }
                     }
                 }
@@ -143,64 +151,54 @@ syrk_tc_kernel(SyrkTcParams p) {
         }
     } else {
         // =============================== producers / epilogue ===============================
-        const int pw = warp - 1;                       // 0..7; warps 0-3 stage the 256 "row" panel rows, 4-7 the "column" rows
-        const bool is_a = pw < 4;
-        // piece u of this thread: tile row = row_base + 16 * (u >> 1), 16-byte part = part_base + 2 * (u & 1).
-        // A warp instruction covers 16 rows x 2 adjacent parts: full 32-byte sectors from global memory, and the 8 lanes of
-        // every shared-memory phase hit 8 different rows (conflict free in the canonical layout).
-        const int row_base = 64 * (pw & 3) + (lane & 7) + 8 * (lane >> 4);    // within the 256-row block
-        const int part_base = (lane >> 3) & 1;
-        const uint32_t lbo = is_a ? ST_M * 16 : ST_BN * 16;
-        const uint32_t lo_off = is_a ? ST_A_TILE : ST_B_TILE;
-        uint32_t off0;
-        if (is_a) off0 = (uint32_t)(row_base >> 7) * 2 * ST_A_TILE + (uint32_t)(row_base & 127) * 16;
-        else off0 = 2 * ST_T * ST_A_TILE + (uint32_t)row_base * 16;
-        off0 += (uint32_t)part_base * lbo;
-        const float* src0 = p.X + ((is_a ? r0 : q0) + row_base) * p.pitch + part_base * 4;
-        const int64_t src_step = 16 * p.pitch;
+        // One thread keeps the ring full: two bulk copies per stage (row block and column block of the panel, 16 KB each) completing on
+        // raw_full[s].  All producer threads then split THEIR 16-byte pieces of the hi images in place (hi = tf32(x), lo = x - hi into
+        // the lo images; consecutive lanes = consecutive pieces: conflict free) and hand the stage to the MMA warp.
+        const int pt = tid - 32;                       // 0..255
         const uint32_t stage_s = smem_u32(stage_base);
-
+        const int64_t rb_a = r0 / ST_TILE, rb_b = q0 / ST_TILE;
         auto issue_chunk = [&](int chunk) {
-            if (chunk < nchunks) {
-                const uint32_t sb = stage_s + (uint32_t)(chunk % ST_NS) * ST_STAGE + off0;
-                const float* src = src0 + (int64_t)chunk * ST_KC;
-#pragma unroll
-                for (int u = 0; u < 8; ++u) {
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sb + (uint32_t)(u >> 1) * 256 + (uint32_t)(u & 1) * 2 * lbo),
-                                 "l"(src + (int64_t)(u >> 1) * src_step + (u & 1) * 8) : "memory");
-                }
+            if (chunk < nchunks && pt == 0) {
+                const int s = chunk % ST_NS;
+                const uint32_t bar = smem_u32(&raw_full[s]);
+                const uint32_t dst = stage_s + (uint32_t)s * ST_STAGE;
+                const float* srca = p.X + (rb_a * nchunks + chunk) * (int64_t)(ST_BLK / 4);
+                const float* srcb = p.X + (rb_b * nchunks + chunk) * (int64_t)(ST_BLK / 4);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(2 * ST_BLK) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(srca), "r"(ST_BLK), "r"(bar) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst + ST_BLK), "l"(srcb), "r"(ST_BLK), "r"(bar) : "memory");
             }
-            asm volatile("cp.async.commit_group;" ::: "memory");
         };
         issue_chunk(0);
         issue_chunk(1);
         for (int c = 0; c < nchunks; ++c) {
-            asm volatile("cp.async.wait_group 1;" ::: "memory");        // this thread's pieces of chunk c have landed
-            const uint32_t sb = stage_s + (uint32_t)(c % ST_NS) * ST_STAGE + off0;
+            const int s = c % ST_NS;
+            mbar_wait(&raw_full[s], (uint32_t)((c / ST_NS) & 1));       // this stage's two blocks have landed
             if (SPLIT) {
+                const uint32_t sb = stage_s + (uint32_t)s * ST_STAGE + (uint32_t)pt * 16;
                 float4 v[8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) v[u] = lds128(sb + (uint32_t)(u >> 1) * 256 + (uint32_t)(u & 1) * 2 * lbo);
+                for (int u = 0; u < 8; ++u) v[u] = lds128(sb + (uint32_t)u * 4096);
 #pragma unroll
                 for (int u = 0; u < 8; ++u) {
-                    const uint32_t a = sb + (uint32_t)(u >> 1) * 256 + (uint32_t)(u & 1) * 2 * lbo;
+                    const uint32_t a = sb + (uint32_t)u * 4096;
                     const float4 h = make_float4(tf32_rn(v[u].x), tf32_rn(v[u].y), tf32_rn(v[u].z), tf32_rn(v[u].w));
                     sts128(a, h);
-                    sts128(a + lo_off, make_float4(v[u].x - h.x, v[u].y - h.y, v[u].z - h.z, v[u].w - h.w));
+                    sts128(a + 2 * ST_BLK, make_float4(v[u].x - h.x, v[u].y - h.y, v[u].z - h.z, v[u].w - h.w));
                 }
+                fence_proxy_async();
             }
-            fence_proxy_async();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&full[c % ST_NS]);
+            if (lane == 0) mbar_arrive(&full[s]);
             // refill: chunk c+2 goes where chunk c-1 was; wait until its MMAs have read it
             const int m = c + 2;
-            if (m < nchunks && m >= ST_NS) {
-                if (lane == 0) mbar_wait(&empty[m % ST_NS], (uint32_t)((m / ST_NS - 1) & 1));
-                __syncwarp();
+            if (pt == 0 && m < nchunks) {
+                if (m >= ST_NS) mbar_wait(&empty[m % ST_NS], (uint32_t)((m / ST_NS - 1) & 1));
+                issue_chunk(m);
             }
-            issue_chunk(m);
         }
-        asm volatile("cp.async.wait_group 0;" ::: "memory");
 
         // ---- epilogue: C tile -= accumulator (fp64 read-modify-write; the tile belongs to this CTA alone)
         mbar_wait(acc_full, 0);
