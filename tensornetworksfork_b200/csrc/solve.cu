@@ -481,9 +481,10 @@ trsv_small_kernel(const double* __restrict__ A, int64_t lda, int P, double* __re
 
 }  // namespace tn
 
-extern "C" int64_t tn_cholesky_work_elems(int64_t P) {
-    return tn::ceil_div64(P, tn::CH_NB) * tn::CH_NB * tn::CH_NB;
-}
+// work = [inverted 64 x 64 diagonal blocks][for P > 8192: inverted 512 x 512 diagonal blocks (the substitutions' block solves as GEMVs)]
+static int64_t chol_linv_elems(int64_t P) { return tn::ceil_div64(P, tn::CH_NB) * tn::CH_NB * tn::CH_NB; }
+static int64_t chol_x512_elems(int64_t P) { return (P > 8192) ? tn::ceil_div64(P, 512) * 512 * 512 : 0; }
+extern "C" int64_t tn_cholesky_work_elems(int64_t P) { return chol_linv_elems(P) + chol_x512_elems(P); }
 
 namespace tn {
 
@@ -581,10 +582,15 @@ trsv_block_kernel(const double* __restrict__ A, int64_t lda, int64_t j0, int nbw
 // forward panel: rhs[i] -= sum_t A[i][j0+t] * y[t], i >= j0+nbw.  One warp per row, the row piece (<= 512 doubles) coalesced.
 __global__ void __launch_bounds__(256)
 trsv_fwd_panel_kernel(const double* __restrict__ A, int64_t lda, int64_t P, int64_t j0, int nbw, double* __restrict__ rhs,
-                      const int* __restrict__ stop) {
+                      const int* __restrict__ stop, const double* __restrict__ ysrc = nullptr) {
     __shared__ double y[TB_W];
     if (*stop != 0) return;
-    for (int i = threadIdx.x; i < TB_W; i += 256) y[i] = (i < nbw) ? rhs[j0 + i] : 0.0;
+    // ysrc: the window's solution comes from the block-inverse product (trsv_gemv512_kernel); CTA 0 also stores it into rhs
+    for (int i = threadIdx.x; i < TB_W; i += 256) {
+        const double v = (i < nbw) ? (ysrc ? ysrc[i] : rhs[j0 + i]) : 0.0;
+        y[i] = v;
+        if (ysrc && blockIdx.x == 0 && i < nbw) rhs[j0 + i] = v;
+    }
     __syncthreads();
     const int lane = threadIdx.x & 31, wp = threadIdx.x >> 5;
     for (int64_t i = j0 + nbw + (int64_t)blockIdx.x * 8 + wp; i < P; i += (int64_t)gridDim.x * 8) {
@@ -606,13 +612,17 @@ trsv_fwd_panel_kernel(const double* __restrict__ A, int64_t lda, int64_t P, int6
 // nbw rows into groups of 64 whose partial sums are added atomically.
 __global__ void __launch_bounds__(256)
 trsv_bwd_panel_kernel(const double* __restrict__ A, int64_t lda, int64_t j0, int nbw, double* __restrict__ rhs,
-                      const int* __restrict__ stop) {
+                      const int* __restrict__ stop, const double* __restrict__ ysrc = nullptr) {
     __shared__ double x[CH_NB];
     if (*stop != 0) return;
     const int t0 = blockIdx.y * CH_NB;
     if (t0 >= nbw) return;
     const int nt = min(CH_NB, nbw - t0);
-    if (threadIdx.x < CH_NB) x[threadIdx.x] = (threadIdx.x < nt) ? rhs[j0 + t0 + threadIdx.x] : 0.0;
+    if (threadIdx.x < CH_NB) {
+        const double v = (threadIdx.x < nt) ? (ysrc ? ysrc[t0 + threadIdx.x] : rhs[j0 + t0 + threadIdx.x]) : 0.0;
+        x[threadIdx.x] = v;
+        if (ysrc && blockIdx.x == 0 && threadIdx.x < nt) rhs[j0 + t0 + threadIdx.x] = v;     // the window's solution, stored once
+    }
     __syncthreads();
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= j0) return;
@@ -627,6 +637,138 @@ trsv_bwd_panel_kernel(const double* __restrict__ A, int64_t lda, int64_t j0, int
     }
     for (; t < nt; ++t) s0 = fma(col[(int64_t)t * lda], x[t], s0);
     atomicAdd(rhs + c, -((s0 + s1) + (s2 + s3)));
+}
+
+// ---- inverses of the 512 x 512 diagonal blocks (P > 8192).  The block solve of a substitution step was one CTA walking eight
+//      64-column steps of the triangle (trsv_block_kernel: 60 us, 655 x 2 launches per application on the critical path of every
+//      conjugate-gradient iteration of the refinement).  With X = L_BB^-1 stored, it is a 512 x 512 triangular matrix-vector product
+//      spread over 64 CTAs.  X is built once per factorisation from the inverted 64 x 64 diagonal blocks: for sub-block column j,
+//      X_jj = Linv_j and X_ij = -Linv_i * sum_{k=j..i-1} L_ik X_kj (i > j).  One CTA per (block, j); 64 x 64 x 64 products through
+//      two padded shared tiles, 4 x 4 outputs per thread.
+constexpr int TB_NS = TB_W / CH_NB;     // 8 sub-blocks of 64
+
+__device__ __forceinline__ void mm64_acc(double (*a)[CH_NB + 1], double (*b)[CH_NB + 1], int ty, int tx, double acc[4][4]) {
+    // acc[i][q] += sum_t a[ty*4+i][t] * b[t][tx + 16 q]
+    for (int t = 0; t < CH_NB; ++t) {
+        double x[4], y[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[i] = a[ty * 4 + i][t];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) y[q] = b[t][tx + 16 * q];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[i][q] = fma(x[i], y[q], acc[i][q]);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+blkinv512_kernel(const double* __restrict__ A, int64_t lda, int64_t P, const double* __restrict__ Linv_all, double* __restrict__ X512,
+                 const int* __restrict__ info) {
+    extern __shared__ double dsm[];
+    double (*ta)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(dsm);
+    double (*tb)[CH_NB + 1] = reinterpret_cast<double (*)[CH_NB + 1]>(dsm + CH_NB * (CH_NB + 1));
+    if (*info != 0) return;
+    const int64_t B = blockIdx.x / TB_NS;
+    const int j = blockIdx.x % TB_NS;
+    const int64_t j0 = B * TB_W;
+    double* X = X512 + B * (int64_t)TB_W * TB_W;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    if (j0 + (int64_t)j * CH_NB >= P) return;          // sub-block column past the end of the matrix
+    // X_jj = Linv_j
+    {
+        const double* Lj = Linv_all + ((j0 / CH_NB) + j) * (int64_t)CH_NB * CH_NB;
+        for (int idx = tid; idx < CH_NB * CH_NB; idx += 256) {
+            const int r = idx >> 6, c = idx & 63;
+            X[(int64_t)(j * CH_NB + r) * TB_W + j * CH_NB + c] = (c <= r) ? Lj[idx] : 0.0;
+        }
+    }
+    for (int i = j + 1; i < TB_NS; ++i) {
+        if (j0 + (int64_t)i * CH_NB >= P) break;
+        __syncthreads();                                 // X_kj of the previous rows (written by this CTA) visible; tiles free
+        double acc[4][4];
+#pragma unroll
+        for (int a = 0; a < 4; ++a)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+        for (int k = j; k < i; ++k) {
+            for (int idx = tid; idx < CH_NB * CH_NB; idx += 256) {
+                const int r = idx >> 6, c = idx & 63;
+                const int64_t gr = j0 + (int64_t)i * CH_NB + r, gc = j0 + (int64_t)k * CH_NB + c;
+                ta[r][c] = (gr < P && gc < P) ? A[gr * lda + gc] : 0.0;                                   // L_ik
+                tb[r][c] = X[(int64_t)(k * CH_NB + r) * TB_W + j * CH_NB + c];                             // X_kj
+            }
+            __syncthreads();
+            mm64_acc(ta, tb, ty, tx, acc);
+            __syncthreads();
+        }
+        // X_ij = -Linv_i * S
+        {
+            const double* Li = Linv_all + ((j0 / CH_NB) + i) * (int64_t)CH_NB * CH_NB;
+            for (int idx = tid; idx < CH_NB * CH_NB; idx += 256) {
+                const int r = idx >> 6, c = idx & 63;
+                ta[r][c] = (c <= r) ? Li[idx] : 0.0;
+            }
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) tb[ty * 4 + a][tx + 16 * b] = acc[a][b];
+            __syncthreads();
+            double out[4][4];
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) out[a][b] = 0.0;
+            mm64_acc(ta, tb, ty, tx, out);
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int b = 0; b < 4; ++b) X[(int64_t)(i * CH_NB + ty * 4 + a) * TB_W + j * CH_NB + tx + 16 * b] = -out[a][b];
+        }
+    }
+}
+
+// y = X x (forward, lower triangle: row r uses columns 0..r) or y = X^T x (backward: column c uses rows c..nbw-1) for the window
+// [j0, j0 + nbw).  Forward: one warp per row, the row read coalesced.  Backward: 64 columns per CTA, 4 row phases per column
+// (coalesced 512-byte row segments), reduced through shared memory.  y goes to ytmp; the panel kernel that follows (or the copy
+// kernel for the last window) stores it into the right-hand side.
+__global__ void __launch_bounds__(256)
+trsv_gemv512_kernel(const double* __restrict__ X, int nbw, const double* __restrict__ x, double* __restrict__ ytmp, int transpose,
+                    const int* __restrict__ stop) {
+    __shared__ double sx[TB_W];
+    __shared__ double red[4][CH_NB];
+    if (*stop != 0) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < TB_W; i += 256) sx[i] = (i < nbw) ? x[i] : 0.0;
+    __syncthreads();
+    if (!transpose) {
+        const int r = blockIdx.x * 8 + warp;
+        if (r < nbw) {
+            const double* row = X + (int64_t)r * TB_W;
+            double s0 = 0.0, s1 = 0.0;
+            for (int c = lane * 2; c <= r; c += 64) {
+                const double2 v = *reinterpret_cast<const double2*>(row + c);
+                s0 = fma(v.x, sx[c], s0);
+                if (c + 1 <= r) s1 = fma(v.y, sx[c + 1], s1);
+            }
+            double sd = s0 + s1;
+            for (int o = 16; o > 0; o >>= 1) sd += __shfl_xor_sync(0xffffffffu, sd, o);
+            if (lane == 0) ytmp[r] = sd;
+        }
+    } else {
+        const int c = blockIdx.x * CH_NB + (tid & 63), ph = tid >> 6;
+        double s = 0.0;
+        if (c < nbw)
+            for (int r = c + ph; r < nbw; r += 4) s = fma(X[(int64_t)r * TB_W + c], sx[r], s);
+        red[ph][tid & 63] = s;
+        __syncthreads();
+        if (tid < CH_NB && c < nbw) ytmp[c] = (red[0][tid] + red[1][tid]) + (red[2][tid] + red[3][tid]);
+    }
+}
+
+__global__ void trsv_copy_kernel(const double* __restrict__ ytmp, double* __restrict__ dst, int n, const int* __restrict__ stop) {
+    if (*stop != 0) return;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = ytmp[i];
 }
 
 static int cholesky_configure() {
@@ -730,6 +872,11 @@ int cholesky_factorize(double* A, int64_t lda, int64_t P, double* work, int* inf
         }
         TN_LAUNCH_CHECK();
     }
+    if (chol_x512_elems(P) > 0) {      // inverses of the 512 x 512 diagonal blocks for the substitutions
+        TN_SMEM(blkinv512_kernel, kBlkSmem);
+        blkinv512_kernel<<<(unsigned)(ceil_div64(P, TB_W) * TB_NS), 256, kBlkSmem, st>>>(A, lda, P, work, work + chol_linv_elems(P), info);
+        TN_LAUNCH_CHECK();
+    }
     return TN_OK;
 }
 
@@ -774,29 +921,43 @@ int cholesky_substitute(const double* A, int64_t lda, int64_t P, double* rhs, co
         TN_LAUNCH_CHECK();
         return TN_OK;
     }
+    // block solves as products with the inverted 512 x 512 diagonal blocks (TN_TRSV_NO_BLKINV=1: the serial block kernel)
+    const bool blkinv = !getenv("TN_TRSV_NO_BLKINV");
+    const double* X512 = work + chol_linv_elems(P);
+    double* ytmp = nullptr;
+    if (blkinv) TN_CUDA(cudaMallocAsync(&ytmp, TB_W * sizeof(double), st));
     for (int64_t j0 = 0; j0 < P; j0 += TB_W) {
         const int nbw = (int)((P - j0 < TB_W) ? P - j0 : TB_W);
-        trsv_block_kernel<<<1, 1024, 0, st>>>(A, lda, j0, nbw, rhs, work, 0, stop);
+        if (blkinv) trsv_gemv512_kernel<<<(unsigned)ceil_div64(nbw, 8), 256, 0, st>>>(X512 + (j0 / TB_W) * (int64_t)TB_W * TB_W, nbw, rhs + j0, ytmp, 0, stop);
+        else trsv_block_kernel<<<1, 1024, 0, st>>>(A, lda, j0, nbw, rhs, work, 0, stop);
         count_launch();
         const int64_t below = P - (j0 + nbw);
         if (below > 0) {
             int64_t blocks = ceil_div64(below, 8);
             if (blocks > 8LL * sms) blocks = 8LL * sms;
-            trsv_fwd_panel_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, lda, P, j0, nbw, rhs, stop);
+            trsv_fwd_panel_kernel<<<(unsigned)blocks, 256, 0, st>>>(A, lda, P, j0, nbw, rhs, stop, ytmp);
+            count_launch();
+        } else if (blkinv) {
+            trsv_copy_kernel<<<1, 256, 0, st>>>(ytmp, rhs + j0, nbw, stop);
             count_launch();
         }
     }
     for (int64_t j0 = ((P - 1) / TB_W) * TB_W; j0 >= 0; j0 -= TB_W) {
         const int nbw = (int)((P - j0 < TB_W) ? P - j0 : TB_W);
-        trsv_block_kernel<<<1, 1024, 0, st>>>(A, lda, j0, nbw, rhs, work, 1, stop);
+        if (blkinv) trsv_gemv512_kernel<<<(unsigned)ceil_div64(nbw, CH_NB), 256, 0, st>>>(X512 + (j0 / TB_W) * (int64_t)TB_W * TB_W, nbw, rhs + j0, ytmp, 1, stop);
+        else trsv_block_kernel<<<1, 1024, 0, st>>>(A, lda, j0, nbw, rhs, work, 1, stop);
         count_launch();
         if (j0 > 0) {
             dim3 grid((unsigned)ceil_div64(j0, 256), (unsigned)ceil_div64(nbw, CH_NB));
-            trsv_bwd_panel_kernel<<<grid, 256, 0, st>>>(A, lda, j0, nbw, rhs, stop);
+            trsv_bwd_panel_kernel<<<grid, 256, 0, st>>>(A, lda, j0, nbw, rhs, stop, ytmp);
+            count_launch();
+        } else if (blkinv) {
+            trsv_copy_kernel<<<1, 256, 0, st>>>(ytmp, rhs + j0, nbw, stop);
             count_launch();
         }
     }
     TN_LAUNCH_CHECK();
+    if (ytmp) TN_CUDA(cudaFreeAsync(ytmp, st));
     return TN_OK;
 }
 
@@ -982,7 +1143,7 @@ extern "C" int tn_cholesky_solve(double* A, int64_t lda, int64_t P, double* rhs,
 
 extern "C" int64_t tn_cholesky_mixed_work_elems(int64_t P) {
     const int64_t Pp = tn::ceil_div64(P, 64) * 64;
-    return tn::ceil_div64(P, tn::CH_NB) * tn::CH_NB * tn::CH_NB + 7 * Pp + 16;
+    return tn_cholesky_work_elems(P) + 7 * Pp + 16;
 }
 
 extern "C" int tn_cholesky_solve_mixed(double* A, int64_t lda, int64_t P, double* rhs, double* work, int* info, double rtol,
@@ -991,7 +1152,7 @@ extern "C" int tn_cholesky_solve_mixed(double* A, int64_t lda, int64_t P, double
     TN_CHECK_ARG(A && rhs && work && info && P >= 1 && lda >= P && max_iter >= 0 && rtol > 0.0, "tn_cholesky_solve_mixed: bad arguments");
     cudaStream_t st = as_stream(stream);
     const int64_t Pp = ceil_div64(P, 64) * 64;
-    double* vec = work + ceil_div64(P, CH_NB) * CH_NB * CH_NB;
+    double* vec = work + tn_cholesky_work_elems(P);
     double *d = vec, *b = vec + Pp, *x = vec + 2 * Pp, *r = vec + 3 * Pp, *z = vec + 4 * Pp, *p = vec + 5 * Pp, *q = vec + 6 * Pp;
     double* scal = vec + 7 * Pp;                                   // 8 doubles + the stop flag
     int* stop = reinterpret_cast<int*>(scal + 8);

@@ -97,6 +97,24 @@ def test_cholesky_large_substitution(P):
     assert res < 1e-11, res
 
 
+@pytest.mark.parametrize("P", [8200, 9001, 12345])
+def test_block_inverse_substitution_matches_serial_block_solve(P, monkeypatch):
+    """The substitutions' 512 x 512 block solves as products with the inverted diagonal blocks (solve.cu::blkinv512_kernel,
+    trsv_gemv512_kernel) against the serial block kernel (TN_TRSV_NO_BLKINV=1) and against the residual of the system; window
+    counts that are not multiples of 512 / 64, repeated applications of one factor (the preconditioner of tn_cg)."""
+    A, Ap, rhs = spd_device(P, P + 3)
+    L = Ap.clone()
+    work, info = ops.cholesky_factor(L, tensor_core=False)
+    assert int(info.item()) == 0
+    x = ops.cholesky_apply(L, work, info, rhs.clone())
+    assert float(torch.norm(A @ x - rhs) / torch.norm(rhs)) < 1e-11
+    x2 = ops.cholesky_apply(L, work, info, rhs.clone())
+    assert torch.equal(x, x2)
+    monkeypatch.setenv("TN_TRSV_NO_BLKINV", "1")
+    y = ops.cholesky_apply(L, work, info, rhs.clone())
+    assert float(torch.norm(x - y) / torch.norm(y)) < 1e-12
+
+
 def test_sweep_with_mixed_solve_tracks_fp64_solve():
     """A TT sweep whose local solves go through the mixed path lands on the same model as the fp64 solve."""
     import tensornetworksfork_b200 as tnb
