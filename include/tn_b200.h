@@ -118,8 +118,10 @@ int tn_gram_expand(const double *M, const int *m_pos, const int *role_of_pos, co
 int tn_rhs_prepare(const double *b, const double *theta, const double *sigma, double ridge, double *rhs, int64_t P,
                    void *stream);
 /* In-place blocked Cholesky of the lower triangle of A, then the two triangular solves on rhs.
- * work: tn_cholesky_work_elems(P) doubles.  info[0] = 0, or k>0 if the leading minor of order
- * k is not positive definite (caller raises LinAlgError as torch.linalg.cholesky does).         */
+ * work: tn_cholesky_work_elems(P) doubles (the inverted 64 x 64 diagonal blocks and, for P > 8192, the
+ * inverted 512 x 512 diagonal blocks that turn the substitutions' block solves into matrix-vector
+ * products).  info[0] = 0, or k>0 if the leading minor of order k is not positive definite (caller
+ * raises LinAlgError as torch.linalg.cholesky does).                                              */
 int64_t tn_cholesky_work_elems(int64_t P);
 int tn_cholesky_solve(double *A, int64_t lda, int64_t P, double *rhs, double *work, int *info, void *stream);
 

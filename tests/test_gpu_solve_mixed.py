@@ -109,7 +109,7 @@ def test_block_inverse_substitution_matches_serial_block_solve(P, monkeypatch):
     x = ops.cholesky_apply(L, work, info, rhs.clone())
     assert float(torch.norm(A @ x - rhs) / torch.norm(rhs)) < 1e-11
     x2 = ops.cholesky_apply(L, work, info, rhs.clone())
-    assert torch.equal(x, x2)
+    assert float(torch.norm(x - x2) / torch.norm(x)) < 1e-13          # the backward panels combine row groups with fp64 atomics: equal to rounding
     monkeypatch.setenv("TN_TRSV_NO_BLKINV", "1")
     y = ops.cholesky_apply(L, work, info, rhs.clone())
     assert float(torch.norm(x - y) / torch.norm(y)) < 1e-12
