@@ -132,7 +132,9 @@ int tn_cholesky_solve(double *A, int64_t lda, int64_t P, double *rhs, double *wo
  * plus the saved diagonal, until ||A x - b|| <= rtol ||b|| or max_iter iterations.
  * stats[0] = relative residual reached, stats[1] = refinement iterations used (device doubles; may be NULL).
  * info as above; when info[0] != 0, or the residual stays above rtol, rhs does not hold a usable solution and the caller
- * re-expands A and calls tn_cholesky_solve.  work: tn_cholesky_mixed_work_elems(P) doubles.                      */
+ * re-expands A and calls tn_cholesky_solve.  work: tn_cholesky_mixed_work_elems(P) doubles.
+ * Unlike tn_cholesky_solve this call SYNCHRONISES the stream once per refinement iteration (the host reads the stop flag),
+ * so it cannot be captured into a CUDA graph.                                                                      */
 int64_t tn_cholesky_mixed_work_elems(int64_t P);
 int tn_cholesky_solve_mixed(double *A, int64_t lda, int64_t P, double *rhs, double *work, int *info, double rtol,
                             int max_iter, double *stats, void *stream);

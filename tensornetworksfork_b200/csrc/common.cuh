@@ -77,6 +77,22 @@ __device__ __forceinline__ double map_apply(int map_kind, double raw, int p) {
     return v;
 }
 
+// Stream-ordered scratch that is returned on EVERY path out of a launcher (error returns included).
+struct AsyncScratch {
+    void* ptr = nullptr;
+    cudaStream_t st = nullptr;
+    AsyncScratch() = default;
+    AsyncScratch(const AsyncScratch&) = delete;
+    AsyncScratch& operator=(const AsyncScratch&) = delete;
+    cudaError_t alloc(size_t bytes, cudaStream_t s) {
+        st = s;
+        return cudaMallocAsync(&ptr, bytes, s);
+    }
+    ~AsyncScratch() {
+        if (ptr) cudaFreeAsync(ptr, st);
+    }
+};
+
 int sm_count();   // of the calling thread's current device (cached per device)
 // Raise a kernel's dynamic shared-memory limit to at least `bytes` on the CURRENT device.  The attribute is per device and per
 // function; what has been set is remembered per (device, function) under a mutex, so a process that drives several GPUs (or

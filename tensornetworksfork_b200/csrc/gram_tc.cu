@@ -180,7 +180,8 @@ __device__ __forceinline__ void red_add_f64_keep(double* addr, double v, uint64_
 
 __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_total, int BN, int warp, int lane, int64_t u0,
                                                int64_t nU, int v0, int nC, double* __restrict__ M, float* __restrict__ scratch,
-                                               double unscale, int tile_stride = TC_M, bool final_flush = false, int nparts = 2) {
+                                               double unscale, int tile_stride = TC_M, bool final_flush = false, int nparts = 2,
+                                               int red_policy = 1) {
     const int q = warp & 3;
     const int half = (warp - 1) >> 2;                  // which part of the columns (two warps per lane quarter by default, four with 16 producer warps)
     const int ngroups = (cols_total + 31) / 32;
@@ -188,7 +189,9 @@ __device__ __noinline__ void drain_accumulator(uint32_t tmem_base, int cols_tota
     const int g_lo = half * per_part;
     const int g_hi = min(ngroups, g_lo + per_part);
     float* sc = scratch + (size_t)(warp - 1) * (32 * 33);
-    const uint64_t l2_keep = final_flush ? l2_evict_first_policy() : l2_evict_last_policy();
+    // red_policy 1: keep the tile in L2 between flushes (short windows); 0: let it leave first (long windows: the tile is not touched
+    // again for hundreds of stages, and the L2 is better spent on the operand streams all CTAs of a wave share)
+    const uint64_t l2_keep = (final_flush || red_policy == 0) ? l2_evict_first_policy() : l2_evict_last_policy();
     for (int g = g_lo; g < g_hi; ++g) {
         uint32_t r[32];
         tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(g * 32), r);
@@ -1055,6 +1058,8 @@ struct VimgParams {
     int mA, mB, mC;
     int nA, nB, nC;
     int BN, nstages, flush_rows, nq_max;
+    int red_policy;          // L2 policy of the flush's reductions: 1 = evict_last, 0 = evict_first
+    int stream_keep;         // 1: L2 evict_last hint on the V-image copies
     int sw128;               // 1: operand tiles in the 128-byte-swizzled K-major layout (rows of 128 B = the 64 samples of a stage, 16-byte chunk index XOR row % 8)
     int dbg;                 // TN_TC16_DBG (measurement only, wrong results): 1 = no U synthesis, 2 = no MMAs, 8 = no raw ring, 32 = no drain, 64 = no V copies
 };
@@ -1271,6 +1276,7 @@ gram_tc16_vimg_kernel(VimgParams p) {
         // =============================== V loader: the ready image of pair(fc) for every chunk, straight into the stage ===============================
         if (lane == 0) {
             const uint32_t stage_s = smem_u32(stage_base);
+            const uint64_t keep_pol = l2_evict_last_policy();
             for (int64_t c = 0; c < nchunks; ++c) {
                 const int s = (int)(c % NS);
                 if (c >= NS) mbar_wait(&empty[s], (uint32_t)((c / NS - 1) & 1));      // the MMAs of chunk c - NS have read the stage
@@ -1278,8 +1284,12 @@ gram_tc16_vimg_kernel(VimgParams p) {
                 const __half* src = p.Vimg + ((int64_t)blockIdx.y * p.zchunks + chunk0 + c) * (int64_t)(v_bytes / 2);
                 if (p.dbg & 64) { mbar_arrive(&full[s]); continue; }
                 asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(v_bytes) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             ::"r"(stage_s + (uint32_t)s * stage_bytes + T * a_tile), "l"(src), "r"(v_bytes), "r"(bar) : "memory");
+                if (p.stream_keep)      // the image is read by every CTA of the tile column: ask the L2 to keep it
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;"
+                                 ::"r"(stage_s + (uint32_t)s * stage_bytes + T * a_tile), "l"(src), "r"(v_bytes), "r"(bar), "l"(keep_pol) : "memory");
+                else
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(stage_s + (uint32_t)s * stage_bytes + T * a_tile), "l"(src), "r"(v_bytes), "r"(bar) : "memory");
             }
         }
     } else {
@@ -1357,7 +1367,7 @@ gram_tc16_vimg_kernel(VimgParams p) {
                 tc_fence_after();
                 // transpose scratch: the U regions of stages 0 and 1 (the V regions belong to the loader, which may already be filling them)
                 float* scratch = reinterpret_cast<float*>(stage_base + (size_t)((warp - 1) >> 2) * stage_bytes) - (size_t)(((warp - 1) >> 2) * 4) * (32 * 33);
-                if (!(p.dbg & 32)) drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, scratch, unscale, TC_M, (c + 1) == nchunks);
+                if (!(p.dbg & 32)) drain_accumulator(tmem_base, T * BN, BN, warp, lane, u0, nU, v0, p.nC, p.M, scratch, unscale, TC_M, (c + 1) == nchunks, 2, p.red_policy);
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(acc_empty);
@@ -1762,8 +1772,9 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
             const size_t zc_bytes = (size_t)zchunks * 8 * psc;
             const size_t zpa_bytes = (size_t)zchunks * p.nA * 128;
             const size_t vimg_bytes = (size_t)ytiles * zchunks * 8 * lbo_b;
-            char* buf = nullptr;
-            TN_CUDA(cudaMallocAsync(&buf, zc_bytes + zpa_bytes + vimg_bytes + 64, st));
+            AsyncScratch scratch;
+            TN_CUDA(scratch.alloc(zc_bytes + zpa_bytes + vimg_bytes + 64, st));
+            char* buf = static_cast<char*>(scratch.ptr);
             TN_CUDA(cudaMemsetAsync(buf, 0, zc_bytes, st));
             unsigned long long* amaxv = reinterpret_cast<unsigned long long*>(buf + zc_bytes + zpa_bytes + vimg_bytes);
             TN_CUDA(cudaMemsetAsync(amaxv, 0, 4 * sizeof(unsigned long long), st));
@@ -1783,6 +1794,8 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
             v.nA = p.nA; v.nB = p.nB; v.nC = p.nC;
             v.BN = p.BN; v.nstages = NSV; v.flush_rows = p.flush_rows; v.nq_max = nq_max; v.dbg = p.dbg;
             v.sw128 = (getenv("TN_TC16_SW128") && atoi(getenv("TN_TC16_SW128")) != 0) ? 1 : 0;
+            v.red_policy = getenv("TN_TC16_RED_POLICY") ? atoi(getenv("TN_TC16_RED_POLICY")) : 1;
+            v.stream_keep = getenv("TN_TC16_STREAM_KEEP") ? atoi(getenv("TN_TC16_STREAM_KEEP")) : 1;      // measured: DRAM reads 53.7 -> 39.2 GB per 131 072 rows (profiles/r2_traffic.json)
             const size_t ssmem = (size_t)(2 * A.m + B.m + C.m) * 65 * sizeof(float) + (size_t)(p.nA + p.nC) * 2 * sizeof(short);
             TN_CHECK_ARG(ssmem <= 200 * 1024, "tn_gram_kr3 (fp16): factors %d+%d+%d too wide for the staging pass", A.m, B.m, C.m);
             TN_SMEM(tc16_vimg_stage_kernel, ssmem);
@@ -1806,7 +1819,6 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
                 gram_tc16_vimg_kernel<<<gridv, VI_THREADS, vsmem, st>>>(v);
             }
             TN_LAUNCH_CHECK();
-            TN_CUDA(cudaFreeAsync(buf, st));
             return TN_OK;
         }
     }
@@ -1815,9 +1827,11 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     while (NSR >= 2 && tc16_run_smem_bytes(A.m, B.m, C.m, p.BN, NSR) > 226 * 1024) --NSR;
     const bool use_run = f16 && kc16 == 64 && p.T == 2 && z_rows < 1023 && NSR >= 2 && getenv("TN_TC16_RUN") && atoi(getenv("TN_TC16_RUN")) != 0;
     const size_t run_plane = run_plane_stride((uint32_t)(z_rows + 1));
+    AsyncScratch zscratch;
     float* Z = nullptr;
     const size_t z_bytes = use_run ? (size_t)(p.zpitch / 8) * run_plane : (size_t)z_rows * p.zpitch * (f16 ? sizeof(__half) : sizeof(float));
-    TN_CUDA(cudaMallocAsync(&Z, z_bytes + 64, st));
+    TN_CUDA(zscratch.alloc(z_bytes + 64, st));
+    Z = static_cast<float*>(zscratch.ptr);
     if (use_run) TN_CUDA(cudaMemsetAsync(Z, 0, z_bytes, st));
     unsigned long long* amax = reinterpret_cast<unsigned long long*>(reinterpret_cast<char*>(Z) + z_bytes);
     TN_CUDA(cudaMemsetAsync(amax, 0, 4 * sizeof(unsigned long long), st));
@@ -1868,7 +1882,6 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
         dim3 pgrid((unsigned)gxp, (unsigned)gyp, (unsigned)ksp);
         pk[p.split]<<<pgrid, TC_THREADS, psmem, st>>>(p);
         TN_LAUNCH_CHECK();
-        TN_CUDA(cudaFreeAsync(Z, st));
         return TN_OK;
     }
     const int64_t gx = ceil_div64(nU, (int64_t)TC_M * p.T), gy = ceil_div64(p.nC, p.BN);
@@ -1890,7 +1903,6 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
             TN_SMEM(gram_tc16_run_kernel, rsmem);
             gram_tc16_run_kernel<<<gridr, TC_THREADS, rsmem, st>>>(p);
             TN_LAUNCH_CHECK();
-            TN_CUDA(cudaFreeAsync(Z, st));
             return TN_OK;
         }
         Kern16 k16 = (kc16 == 64) ? ((p.T == 2) ? gram_tc16_kernel<2, 64> : gram_tc16_kernel<1, 64>)
@@ -1899,7 +1911,6 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
         dim3 grid16((unsigned)gx, (unsigned)gy, (unsigned)ks);
         k16<<<grid16, TC_THREADS, smem, st>>>(p);
         TN_LAUNCH_CHECK();
-        TN_CUDA(cudaFreeAsync(Z, st));
         return TN_OK;
     }
     using Kern = void (*)(TcParams);
@@ -1914,6 +1925,5 @@ int tn_gram_kr3_tc(int mode, const tn_factor* fa, const tn_factor* fb, const tn_
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)ks);
     k<<<grid, TC_THREADS, smem_k, st>>>(p);
     TN_LAUNCH_CHECK();
-    TN_CUDA(cudaFreeAsync(Z, st));
     return TN_OK;
 }

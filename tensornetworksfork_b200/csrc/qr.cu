@@ -97,12 +97,12 @@ extern "C" int tn_qr(double* a, int m, int n, double* r, void* stream) {
     TN_CHECK_ARG(a && r && m >= n && n >= 1 && n <= 128, "tn_qr: need m >= n, 1 <= n <= 128 (got %d x %d)", m, n);
     const size_t bytes = 2 * (size_t)m * n * sizeof(double);
     const int use_smem = bytes <= 200 * 1024;
-    double* q_g = nullptr;
     cudaStream_t st = as_stream(stream);
-    if (!use_smem) TN_CUDA(cudaMallocAsync(&q_g, (size_t)m * n * sizeof(double), st));
+    AsyncScratch qscratch;
+    if (!use_smem) TN_CUDA(qscratch.alloc((size_t)m * n * sizeof(double), st));
+    double* q_g = static_cast<double*>(qscratch.ptr);
     if (use_smem) TN_SMEM(qr_kernel, bytes);
     qr_kernel<<<1, QR_THREADS, use_smem ? bytes : 0, st>>>(a, m, n, r, q_g, use_smem);
     TN_LAUNCH_CHECK();
-    if (q_g) TN_CUDA(cudaFreeAsync(q_g, st));
     return TN_OK;
 }

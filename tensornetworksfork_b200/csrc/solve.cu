@@ -924,8 +924,9 @@ int cholesky_substitute(const double* A, int64_t lda, int64_t P, double* rhs, co
     // block solves as products with the inverted 512 x 512 diagonal blocks (TN_TRSV_NO_BLKINV=1: the serial block kernel)
     const bool blkinv = !getenv("TN_TRSV_NO_BLKINV");
     const double* X512 = work + chol_linv_elems(P);
-    double* ytmp = nullptr;
-    if (blkinv) TN_CUDA(cudaMallocAsync(&ytmp, TB_W * sizeof(double), st));
+    AsyncScratch yscratch;
+    if (blkinv) TN_CUDA(yscratch.alloc(TB_W * sizeof(double), st));
+    double* ytmp = static_cast<double*>(yscratch.ptr);
     for (int64_t j0 = 0; j0 < P; j0 += TB_W) {
         const int nbw = (int)((P - j0 < TB_W) ? P - j0 : TB_W);
         if (blkinv) trsv_gemv512_kernel<<<(unsigned)ceil_div64(nbw, 8), 256, 0, st>>>(X512 + (j0 / TB_W) * (int64_t)TB_W * TB_W, nbw, rhs + j0, ytmp, 0, stop);
@@ -957,7 +958,6 @@ int cholesky_substitute(const double* A, int64_t lda, int64_t P, double* rhs, co
         }
     }
     TN_LAUNCH_CHECK();
-    if (ytmp) TN_CUDA(cudaFreeAsync(ytmp, st));
     return TN_OK;
 }
 
@@ -1172,10 +1172,10 @@ extern "C" int tn_cholesky_solve_mixed(double* A, int64_t lda, int64_t P, double
         const int v = atoi(e);
         if (v >= CH_NB && v % CH_NB == 0) NBO = v;
     }
-    float* X = nullptr;
-    TN_CUDA(cudaMallocAsync(&X, (size_t)syrk_tc_work_floats(P, (int)NBO) * sizeof(float), st));
+    AsyncScratch xscratch;
+    TN_CUDA(xscratch.alloc((size_t)syrk_tc_work_floats(P, (int)NBO) * sizeof(float), st));
+    float* X = static_cast<float*>(xscratch.ptr);
     int rc = cholesky_factorize(A, lda, P, work, info, st, X, NBO);
-    cudaFreeAsync(X, st);
     if (rc != TN_OK) return rc;
 
     auto symv = [&](const double* v, double* out) -> int {
@@ -1240,12 +1240,12 @@ extern "C" int tn_cholesky_factor(double* A, int64_t lda, int64_t P, int tensor_
         const int v = atoi(e);
         if (v >= CH_NB && v % CH_NB == 0) NBO = v;
     }
-    float* X = nullptr;
-    TN_CUDA(cudaMallocAsync(&X, (size_t)syrk_tc_work_floats(P, (int)NBO) * sizeof(float), st));
+    AsyncScratch xscratch;
+    TN_CUDA(xscratch.alloc((size_t)syrk_tc_work_floats(P, (int)NBO) * sizeof(float), st));
+    float* X = static_cast<float*>(xscratch.ptr);
     syrk_tc_set_passes(tensor_core == 2 ? 1 : 3);        // 2: one TF32 pass per K step (preconditioner-grade factor)
     const int rc = cholesky_factorize(A, lda, P, work, info, st, X, NBO);
     syrk_tc_set_passes(3);
-    cudaFreeAsync(X, st);
     return rc;
 }
 
