@@ -65,6 +65,21 @@ WORKLOADS = {
 }
 
 
+
+def site_updates_per_step(wl):
+    """Site updates of one step (one sweep / one pass pair) of a workload: what both arms divide by."""
+    if wl.get("solver") or wl["kind"] == "conv":
+        return 2 * wl["sites"]          # matrix-free passes visit every node in both directions
+    return 2 * wl["sites"] - 1          # dense sweep: the turning site is updated once
+
+
+def workload_config(args, wl, rows_per_gpu, world, updates_per_step=None):
+    """`config` of the JSON line: identical for the b200 arm and the reference arm run with the same arguments."""
+    return {"workload": f"{args.workload}: {wl['desc']}", "rows_per_gpu": rows_per_gpu, "rows_total": rows_per_gpu * world,
+            "site_updates_per_step": updates_per_step if updates_per_step is not None else site_updates_per_step(wl),
+            "gram_mode": args.gram_mode, "eps": args.eps,
+            "l2": "inputs larger than L2 (per-site streams of rows*(r_l+f+r_r)*8 B)", "parallelism": f"sample-shard x{world}"}
+
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -576,9 +591,7 @@ def bench_b200(args):
            "dtype_note": None if args.gram_mode == "fp64" else
            f"everything fp64 except the Gram build ({args.gram_mode} on tcgen05), which only preconditions the fp64 conjugate-gradient "
            f"refinement of every site's system: steps, cores and losses are those of the fp64 path (see `accuracy`, `solve.refinement`)",
-           "config": {"workload": f"{args.workload}: {wl['desc']}", "rows_per_gpu": n, "rows_total": n * world,
-                      "site_updates_per_step": updates // max(args.steps, 1), "gram_mode": args.gram_mode, "eps": args.eps,
-                      "l2": "inputs larger than L2 (per-site streams of rows*(r_l+f+r_r)*8 B)", "parallelism": f"sample-shard x{world}"},
+           "config": workload_config(args, wl, n, world, updates // max(args.steps, 1)),
            "roofline": roofline, "solve": solve_info, "kernel_time_share": shares,
            "gpu_launches": launches,
            "clocks": clk, "e2e": e2e, "accuracy": accuracy}
@@ -932,8 +945,7 @@ def bench_reference(args):
            "site_updates_per_s": value / n, "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": step_s * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-           "config": {"workload": f"{args.workload}: {wl['desc']}", "rows_per_gpu": n // world, "rows_total": n, "eps": args.eps,
-                      "parallelism": f"host cores ({os.cpu_count()})"},
+           "config": workload_config(args, wl, n // world, world),      # the b200 arm's config, key for key (the host side is in cpu_baseline)
            "cpu_baseline": base,
            "e2e": {"value": value, "unit": "sample-site-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(out))
