@@ -9,6 +9,7 @@
 //   M = U^T V,  U[row,(qa,qb)] = w*pair(fa)*pair(fb),  V[row,qc] = pair(fc)
 // whose operand tiles are synthesised in shared memory from the raw factors; nothing of
 // size rows x P ever exists.  tn_gram_expand scatters M to the dense scaled system.
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace tn {
@@ -170,6 +171,267 @@ kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int64_t gu = u0 + wu + i * 8 + fr;
+        if (gu >= nU) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gv = v0 + wv + j * 8 + 2 * fk + e;
+                if (gv < nC) o[gu * nC + gv] = acc[i][j][e];
+            }
+        }
+    }
+}
+
+// ---- fp64 Gram of a Kronecker Jacobian with a FACTORED left operand (MODE 1 of the kernel above: same 128 x 64 tile, same warp
+// layout, same DMMA fragments; results differ from it by the rounding of the operand products only).
+// The capture of kr3_f64_kernel<1> (profiles/r2_ncu_kr3_f64.txt, hot lines by tools/ncu_hotspots.py) has the FP64 tensor pipe 42 %
+// active and almost no stall samples in the DMMA loop: 45 % of them sit in the staging loop (one exposed global load and two integer
+// divisions per element), 25 % in the synthesis of the 32 x 128 U tile (four gathers and four multiplies per element), 9 % in the
+// three block barriers of a chunk.  Here
+//  (a) U = (w * pair(fa)) (x) pair(fb) is never formed: the tile keeps the two factors' pair columns ([PA | PB | V], TAW + TBW + 64
+//      columns per row instead of 128 + 64) and a DMMA A-fragment element is one product PA[k][la] * PB[k][lb] made in registers.  The
+//      128 U columns of a CTA are a 16 x 8 box of (qa, qb) when the middle factor has many pairs (BOX: 24 operand columns), else
+//      128 consecutive (qa, qb) indices (all pairs of the middle factor, <= 129 of the left one);
+//  (b) the raw factors of chunk c+2 arrive by cp.async (8 bytes per element, zero fill past the end of the split, no divisions,
+//      a warp per row) while chunk c+1 is synthesised and chunk c multiplied; a feature-mapped factor (one raw value per row) is
+//      loaded into a register at the top of the iteration and expanded at its end by one warp;
+//  (c) one block barrier per 32-row chunk: raw buffers and operand tiles are double buffered, so the synthesis of the next chunk by
+//      fast warps overlaps the DMMAs of slow ones.
+__device__ __forceinline__ void cp_async8(double* dst, const double* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+// identity factor: the m values of one row, a lane per column (zero fill when the row is past the end)
+__device__ __forceinline__ void gf_fill_row(const FactorDev& f, double* dst, int64_t row, bool ok, int lane) {
+    if (f.map_kind != TN_MAP_IDENTITY) return;
+    const double* src = f.ptr + (f.div == 1 ? row : row / f.div) * f.ld;
+    for (int i = lane; i < f.m; i += 32) cp_async8(dst + i, src + i, ok);
+}
+// feature-mapped factor: lane k of the owning warp holds the raw value of row k and writes its m features
+__device__ __forceinline__ double gf_load_raw(const FactorDev& f, int64_t row) {
+    return f.ptr[(f.div == 1 ? row : row / f.div) * f.ld];
+}
+__device__ __forceinline__ void gf_store_mapped(const FactorDev& f, double* dst, double raw, bool ok) {
+    for (int i = 0; i < f.m; ++i) dst[i] = ok ? map_apply(f.map_kind, raw, i) : 0.0;
+}
+
+template <bool BOX>
+__global__ void __launch_bounds__(GR_THREADS, 2)
+gram_f64_fact_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restrict__ w, int64_t rows, double* __restrict__ out,
+                     int nA, int nB, int nC, int64_t rows_per_split, int TAW, int TBW, int stT, int nTB) {
+    extern __shared__ double sm[];
+    const int stA = fa.m | 1, stB = fb.m | 1, stC = fc.m | 1;
+    const int rawsz = GR_KC * (stA + stB + stC + 1);                      // one raw buffer: [FA | FB | FC | W]
+    double* sRaw = sm;                                                    // [2][rawsz]
+    double* sT = sRaw + 2 * rawsz;                                        // [2][GR_KC][stT]: rows of [PA | PB | V]
+    unsigned* tCol = reinterpret_cast<unsigned*>(sT + 2 * GR_KC * stT);   // [NCOL]: i | j << 16 of the column's index pair
+    const int NCOL = TAW + TBW + GR_TV;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t nU = (int64_t)nA * nB;
+    const int v0 = blockIdx.y * GR_TV;
+    const int64_t k_begin = (int64_t)blockIdx.z * rows_per_split;
+    const int64_t k_end = min(rows, k_begin + rows_per_split);
+    int64_t u0 = 0;
+    int a0, b0 = 0;
+    if (BOX) {
+        const int ta = blockIdx.x / nTB;
+        a0 = ta * 16;
+        b0 = (blockIdx.x - ta * nTB) * 8;
+    } else {
+        u0 = (int64_t)blockIdx.x * GR_TU;
+        a0 = (int)(u0 / nB);
+    }
+
+    for (int col = tid; col < NCOL; col += GR_THREADS) {
+        int i = 0, j = 0;
+        bool valid;
+        if (col < TAW) {
+            const int q = a0 + col;
+            valid = q < nA;
+            if (valid) pair_decode(q, fa.m, i, j);
+        } else if (col < TAW + TBW) {
+            const int q = b0 + col - TAW;
+            valid = q < nB;
+            if (valid) pair_decode(q, fb.m, i, j);
+        } else {
+            const int q = v0 + col - TAW - TBW;
+            valid = q < nC;
+            if (valid) pair_decode(q, fc.m, i, j);
+        }
+        tCol[col] = valid ? ((unsigned)i | ((unsigned)j << 16)) : 0xFFFFFFFFu;
+    }
+
+    // 8 warps as 4 (u) x 2 (v): each warp owns a 32 x 32 block of the tile = 4 x 4 DMMA m8n8k4 accumulators
+    const int wu = (warp >> 1) * 32, wv = (warp & 1) * 32;
+    const int fr = lane >> 2, fk = lane & 3;
+    int offA[4], offB[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int jc = wu + i * 8 + fr;
+        int la = 0, lb = 0;
+        if (BOX) {
+            la = jc >> 3;
+            lb = jc & 7;
+        } else {
+            const int64_t gu = u0 + jc;
+            if (gu < nU) {
+                const int qa = (int)(gu / nB);
+                la = qa - a0;
+                lb = (int)(gu - (int64_t)qa * nB);
+            }
+        }
+        offA[i] = la;
+        offB[i] = TAW + lb;
+    }
+    double acc[4][4][2];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+    const int nch = (k_end > k_begin) ? (int)((k_end - k_begin + GR_KC - 1) / GR_KC) : 0;
+    const int64_t last_row = rows - 1;
+    // warps 1, 2, 3 expand a feature-mapped fa, fb, fc (lane = row of the chunk)
+    FactorDev fm;
+    fm.ptr = (warp == 1) ? fa.ptr : (warp == 2) ? fb.ptr : fc.ptr;
+    fm.ld = (warp == 1) ? fa.ld : (warp == 2) ? fb.ld : fc.ld;
+    fm.m = (warp == 1) ? fa.m : (warp == 2) ? fb.m : fc.m;
+    fm.div = (warp == 1) ? fa.div : (warp == 2) ? fb.div : fc.div;
+    fm.map_kind = (warp == 1) ? fa.map_kind : (warp == 2) ? fb.map_kind : fc.map_kind;
+    const bool mapper = (warp >= 1 && warp <= 3) && fm.map_kind != TN_MAP_IDENTITY;
+    const int m_off = (warp == 1) ? 0 : (warp == 2) ? GR_KC * stA : GR_KC * (stA + stB);
+    const int m_st = (warp == 1) ? stA : (warp == 2) ? stB : stC;
+
+    auto fill = [&](int c, double* raw) {          // asynchronous part of the raw factors of chunk c
+        const int64_t kb = k_begin + (int64_t)c * GR_KC;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int k = warp + 8 * r;
+            const int64_t row = kb + k;
+            const bool ok = row < k_end;
+            const int64_t rc = ok ? row : last_row;
+            gf_fill_row(fa, raw + k * stA, rc, ok, lane);
+            gf_fill_row(fb, raw + GR_KC * stA + k * stB, rc, ok, lane);
+            gf_fill_row(fc, raw + GR_KC * (stA + stB) + k * stC, rc, ok, lane);
+        }
+        if (warp == 0) {
+            const int64_t row = kb + lane;
+            const bool ok = row < k_end;
+            double* dw = raw + GR_KC * (stA + stB + stC) + lane;
+            if (w) cp_async8(dw, w + (ok ? row : last_row), ok);
+            else *dw = ok ? 1.0 : 0.0;
+        }
+    };
+    auto load_mapped = [&](int c) -> double {
+        const int64_t row = k_begin + (int64_t)c * GR_KC + lane;
+        return (mapper && row < k_end) ? gf_load_raw(fm, row) : 0.0;
+    };
+    auto store_mapped = [&](int c, double* raw, double x) {
+        if (!mapper) return;
+        const int64_t row = k_begin + (int64_t)c * GR_KC + lane;
+        gf_store_mapped(fm, raw + m_off + lane * m_st, x, row < k_end);
+    };
+    auto synth = [&](const double* raw, double* tile) {       // operand columns of 4 rows per warp, a lane per column
+        const double* rW = raw + GR_KC * (stA + stB + stC);
+        for (int col = lane; col < NCOL; col += 32) {
+            const unsigned pk = tCol[col];
+            const int i = pk & 0xFFFF, j = pk >> 16;
+            const bool isA = col < TAW;
+            const double* src = raw;
+            int st = stA;
+            if (!isA) {
+                if (col < TAW + TBW) { src = raw + GR_KC * stA; st = stB; }
+                else { src = raw + GR_KC * (stA + stB); st = stC; }
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r) {
+                const int k = warp + 8 * r;
+                double v = 0.0;
+                if (pk != 0xFFFFFFFFu) {
+                    v = src[k * st + i] * src[k * st + j];
+                    if (isA) v *= rW[k];
+                }
+                tile[k * stT + col] = v;
+            }
+        }
+    };
+    auto mma_chunk = [&](const double* tile) {
+        const double* rowp = tile + fk * stT;
+#pragma unroll
+        for (int k4 = 0; k4 < GR_KC; k4 += 4, rowp += 4 * stT) {
+            double af[4], bf[4];
+            if (BOX) {
+                const double vb = rowp[offB[0]];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) af[i] = rowp[offA[i]] * vb;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) af[i] = rowp[offA[i]] * rowp[offB[i]];
+            }
+            const double* vp = rowp + TAW + TBW + wv + fr;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) bf[j] = vp[j * 8];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        }
+    };
+
+    double* raw0 = sRaw;
+    double* raw1 = sRaw + rawsz;
+    double* tile0 = sT;
+    double* tile1 = sT + GR_KC * stT;
+    if (nch > 0) {
+        fill(0, raw0);
+        store_mapped(0, raw0, load_mapped(0));
+    }
+    cp_async_wait_all();
+    __syncthreads();              // raw factors of chunk 0 and the column table visible
+    {
+        double xpre = 0.0;
+        if (nch > 1) {
+            fill(1, raw1);
+            xpre = load_mapped(1);
+        }
+        if (nch > 0) synth(raw0, tile0);
+        if (nch > 1) store_mapped(1, raw1, xpre);
+    }
+    cp_async_wait_all();
+    __syncthreads();
+    for (int c = 0; c < nch; ++c) {
+        double* rawc = (c & 1) ? raw1 : raw0;          // holds chunk c (already synthesised): refilled with chunk c + 2
+        double* rawn = (c & 1) ? raw0 : raw1;          // chunk c + 1
+        double* tilec = (c & 1) ? tile1 : tile0;
+        double* tilen = (c & 1) ? tile0 : tile1;
+        double xpre = 0.0;
+        if (c + 2 < nch) {
+            fill(c + 2, rawc);
+            xpre = load_mapped(c + 2);
+        }
+        if (c + 1 < nch) synth(rawn, tilen);
+        mma_chunk(tilec);
+        if (c + 2 < nch) store_mapped(c + 2, rawc, xpre);
+        cp_async_wait_all();
+        __syncthreads();          // the one barrier of a chunk: tiles of c + 1 and raw factors of c + 2 visible, buffers of c free
+    }
+
+    double* o = out + (int64_t)blockIdx.z * nU * nC;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int jc = wu + i * 8 + fr;
+        int64_t gu;
+        if (BOX) {
+            const int qa = a0 + (jc >> 3), qb = b0 + (jc & 7);
+            gu = (qa < nA && qb < nB) ? (int64_t)qa * nB + qb : nU;
+        } else {
+            gu = u0 + jc;
+        }
         if (gu >= nU) continue;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -505,10 +767,35 @@ static int launch_kr3(const tn_factor* fa, const tn_factor* fb, const tn_factor*
     const int64_t gx = ceil_div64(nU, GR_TU), gy = ceil_div64(nC, GR_TV);
     TN_CHECK_ARG(gy <= 65535 && ksplit <= 65535 && gx <= 0x7fffffff, "kr3: grid too large");
     dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)ksplit);
-    // (A software-pipelined variant -- register prefetch of the raw factors, double-buffered operand tiles, two barriers per 16-row chunk --
-    // gave the same bits and was 10-20 % SLOWER than this three-barrier kernel: profiles/r2_gram_f64_probe.jsonl; removed.)
-    TN_SMEM(kr3_f64_kernel<MODE>, smem);
-    kr3_f64_kernel<MODE><<<grid, GR_THREADS, smem, st>>>(a, b, c, w, rows, direct ? dst : work, nA, nB, nC, rps, t1, t2, t3);
+    // (A software-pipelined variant of the kernel below -- register prefetch of the raw factors, double-buffered 128-wide operand tiles,
+    // two barriers per 16-row chunk -- gave the same bits and was 10-20 % SLOWER: profiles/r2_gram_f64_probe.jsonl; removed.)
+    bool launched = false;
+    if (MODE == 1 && !getenv("TN_GRAM_F64_UNFACTORED")) {
+        // factored-operand kernel: a 16 x 8 box of (qa, qb) per CTA when the middle factor has >= 64 pairs, else 128 consecutive indices
+        const bool box = nB >= 64;
+        const int TAW = box ? 16 : (GR_TU - 1) / nB + 2, TBW = box ? 8 : nB;
+        int stT = TAW + TBW + GR_TV;
+        stT += (4 - (stT & 7) + 8) & 7;           // = 4 (mod 8): conflict-free DMMA fragment reads (row offset 8 banks per k)
+        const int nTB = (nB + 7) / 8;
+        const size_t fsmem = (size_t)(2 * GR_KC * ((a.m | 1) + (b.m | 1) + (c.m | 1) + 1) + 2 * GR_KC * stT) * sizeof(double) +
+                             (size_t)(TAW + TBW + GR_TV) * sizeof(unsigned);
+        const int64_t fgx = box ? (int64_t)((nA + 15) / 16) * nTB : gx;
+        if (fsmem <= 227 * 1024 && fgx <= 0x7fffffff) {
+            dim3 fgrid((unsigned)fgx, (unsigned)gy, (unsigned)ksplit);
+            if (box) {
+                TN_SMEM(gram_f64_fact_kernel<true>, fsmem);
+                gram_f64_fact_kernel<true><<<fgrid, GR_THREADS, fsmem, st>>>(a, b, c, w, rows, direct ? dst : work, nA, nB, nC, rps, TAW, TBW, stT, nTB);
+            } else {
+                TN_SMEM(gram_f64_fact_kernel<false>, fsmem);
+                gram_f64_fact_kernel<false><<<fgrid, GR_THREADS, fsmem, st>>>(a, b, c, w, rows, direct ? dst : work, nA, nB, nC, rps, TAW, TBW, stT, nTB);
+            }
+            launched = true;
+        }
+    }
+    if (!launched) {
+        TN_SMEM(kr3_f64_kernel<MODE>, smem);
+        kr3_f64_kernel<MODE><<<grid, GR_THREADS, smem, st>>>(a, b, c, w, rows, direct ? dst : work, nA, nB, nC, rps, t1, t2, t3);
+    }
     TN_LAUNCH_CHECK();
     if (!direct) {
         int64_t blocks = ceil_div64(n, 256);
