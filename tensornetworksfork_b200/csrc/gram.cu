@@ -211,18 +211,18 @@ __device__ __forceinline__ void gf_fill_row(const FactorDev& f, double* dst, int
     const double* src = f.ptr + (f.div == 1 ? row : row / f.div) * f.ld;
     for (int i = lane; i < f.m; i += 32) cp_async8(dst + i, src + i, ok);
 }
-// feature-mapped factor: lane k of the owning warp holds the raw value of row k and writes its m features
+// feature-mapped factor: lane k of an owning warp holds the raw value of row k and writes every second of its m features
 __device__ __forceinline__ double gf_load_raw(const FactorDev& f, int64_t row) {
     return f.ptr[(f.div == 1 ? row : row / f.div) * f.ld];
 }
-__device__ __forceinline__ void gf_store_mapped(const FactorDev& f, double* dst, double raw, bool ok) {
-    for (int i = 0; i < f.m; ++i) dst[i] = ok ? map_apply(f.map_kind, raw, i) : 0.0;
+__device__ __forceinline__ void gf_store_mapped(const FactorDev& f, double* dst, double raw, bool ok, int first) {
+    for (int i = first; i < f.m; i += 2) dst[i] = ok ? map_apply(f.map_kind, raw, i) : 0.0;
 }
 
 template <bool BOX>
 __global__ void __launch_bounds__(GR_THREADS, 2)
 gram_f64_fact_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restrict__ w, int64_t rows, double* __restrict__ out,
-                     int nA, int nB, int nC, int64_t rows_per_split, int TAW, int TBW, int stT, int nTB) {
+                     int nA, int nB, int nC, int64_t rows_per_split, int TAW, int TBW, int stT, int nTB, int swapU) {
     extern __shared__ double sm[];
     const int stA = fa.m | 1, stB = fb.m | 1, stC = fc.m | 1;
     const int rawsz = GR_KC * (stA + stB + stC + 1);                      // one raw buffer: [FA | FB | FC | W]
@@ -296,16 +296,17 @@ gram_f64_fact_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __r
 
     const int nch = (k_end > k_begin) ? (int)((k_end - k_begin + GR_KC - 1) / GR_KC) : 0;
     const int64_t last_row = rows - 1;
-    // warps 1, 2, 3 expand a feature-mapped fa, fb, fc (lane = row of the chunk)
+    // warps 1 / 4, 2 / 5, 3 / 6 expand the even / odd features of a feature-mapped fa, fb, fc (lane = row of the chunk)
+    const int mw = (warp >= 1 && warp <= 6) ? (warp - 1) % 3 : -1, m_par = (warp >= 4) ? 1 : 0;
     FactorDev fm;
-    fm.ptr = (warp == 1) ? fa.ptr : (warp == 2) ? fb.ptr : fc.ptr;
-    fm.ld = (warp == 1) ? fa.ld : (warp == 2) ? fb.ld : fc.ld;
-    fm.m = (warp == 1) ? fa.m : (warp == 2) ? fb.m : fc.m;
-    fm.div = (warp == 1) ? fa.div : (warp == 2) ? fb.div : fc.div;
-    fm.map_kind = (warp == 1) ? fa.map_kind : (warp == 2) ? fb.map_kind : fc.map_kind;
-    const bool mapper = (warp >= 1 && warp <= 3) && fm.map_kind != TN_MAP_IDENTITY;
-    const int m_off = (warp == 1) ? 0 : (warp == 2) ? GR_KC * stA : GR_KC * (stA + stB);
-    const int m_st = (warp == 1) ? stA : (warp == 2) ? stB : stC;
+    fm.ptr = (mw == 0) ? fa.ptr : (mw == 1) ? fb.ptr : fc.ptr;
+    fm.ld = (mw == 0) ? fa.ld : (mw == 1) ? fb.ld : fc.ld;
+    fm.m = (mw == 0) ? fa.m : (mw == 1) ? fb.m : fc.m;
+    fm.div = (mw == 0) ? fa.div : (mw == 1) ? fb.div : fc.div;
+    fm.map_kind = (mw == 0) ? fa.map_kind : (mw == 1) ? fb.map_kind : fc.map_kind;
+    const bool mapper = mw >= 0 && fm.map_kind != TN_MAP_IDENTITY;
+    const int m_off = (mw == 0) ? 0 : (mw == 1) ? GR_KC * stA : GR_KC * (stA + stB);
+    const int m_st = (mw == 0) ? stA : (mw == 1) ? stB : stC;
 
     auto fill = [&](int c, double* raw) {          // asynchronous part of the raw factors of chunk c
         const int64_t kb = k_begin + (int64_t)c * GR_KC;
@@ -334,7 +335,7 @@ gram_f64_fact_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __r
     auto store_mapped = [&](int c, double* raw, double x) {
         if (!mapper) return;
         const int64_t row = k_begin + (int64_t)c * GR_KC + lane;
-        gf_store_mapped(fm, raw + m_off + lane * m_st, x, row < k_end);
+        gf_store_mapped(fm, raw + m_off + lane * m_st, x, row < k_end, m_par);
     };
     auto synth = [&](const double* raw, double* tile) {       // operand columns of 4 rows per warp, a lane per column
         const double* rW = raw + GR_KC * (stA + stB + stC);
@@ -425,12 +426,16 @@ gram_f64_fact_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __r
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         const int jc = wu + i * 8 + fr;
-        int64_t gu;
+        int64_t gu;        // output row: (qa, qb) in the caller's order (swapU: the launcher exchanged the first two factors)
         if (BOX) {
             const int qa = a0 + (jc >> 3), qb = b0 + (jc & 7);
-            gu = (qa < nA && qb < nB) ? (int64_t)qa * nB + qb : nU;
+            gu = (qa < nA && qb < nB) ? (swapU ? (int64_t)qb * nA + qa : (int64_t)qa * nB + qb) : nU;
         } else {
             gu = u0 + jc;
+            if (swapU && gu < nU) {
+                const int qa = (int)(gu / nB), qb = (int)(gu - (int64_t)qa * nB);
+                gu = (int64_t)qb * nA + qa;
+            }
         }
         if (gu >= nU) continue;
 #pragma unroll
@@ -732,17 +737,26 @@ __global__ void reduce_splits_kernel(const double* __restrict__ work, double* __
     }
 }
 
+// Row splits of the Gram / right-hand-side GEMM.  Two CTAs are resident per SM and every CTA of a launch does the same work, so the
+// launch takes ceil(tiles * ks / slots) rounds of rows / ks rows each: 600 CTAs on 296 slots (config 3's middle site with the former
+// "4 CTAs per SM" rule) ran three rounds for two rounds' worth of work.  ks minimises rounds * (rows per split + a per-CTA overhead).
 static int choose_ksplit(int64_t rows, int64_t nU, int64_t nV) {
     const int64_t tiles = ceil_div64(nU, GR_TU) * ceil_div64(nV, GR_TV);
-    const int64_t want = 4LL * sm_count();
-    int64_t ks = ceil_div64(want, tiles);
-    const int64_t max_by_rows = ceil_div64(rows, 8 * GR_KC);
-    if (ks > max_by_rows) ks = max_by_rows;
+    const int64_t slots = 2LL * sm_count();
+    int64_t ks_max = ceil_div64(rows, 8 * GR_KC);
     const int64_t max_by_mem = (int64_t)(64LL << 20) / (nU * nV > 0 ? nU * nV : 1);  // <= 512 MB of partials
-    if (ks > max_by_mem) ks = max_by_mem;
-    if (ks < 1) ks = 1;
-    if (ks > 1024) ks = 1024;
-    return (int)ks;
+    if (ks_max > max_by_mem) ks_max = max_by_mem;
+    if (ks_max > 1024) ks_max = 1024;
+    if (ks_max < 1) ks_max = 1;
+    if (tiles >= 4 * slots) return 1;
+    const int64_t overhead = 2 * GR_KC;            // prologue + partial-tile store + its share of the reduction, in rows of work
+    int64_t best = 1;
+    double best_t = (double)ceil_div64(tiles, slots) * (double)(rows + overhead);
+    for (int64_t ks = 2; ks <= ks_max && tiles * ks <= 8 * slots; ++ks) {
+        const double t = (double)ceil_div64(tiles * ks, slots) * (double)(ceil_div64(rows, ks) + overhead);
+        if (t < 0.98 * best_t) { best_t = t; best = ks; }
+    }
+    return (int)best;
 }
 
 template <int MODE>
@@ -771,25 +785,51 @@ static int launch_kr3(const tn_factor* fa, const tn_factor* fb, const tn_factor*
     // two barriers per 16-row chunk -- gave the same bits and was 10-20 % SLOWER: profiles/r2_gram_f64_probe.jsonl; removed.)
     bool launched = false;
     if (MODE == 1 && !getenv("TN_GRAM_F64_UNFACTORED")) {
-        // factored-operand kernel: a 16 x 8 box of (qa, qb) per CTA when the middle factor has >= 64 pairs, else 128 consecutive indices
-        const bool box = nB >= 64;
-        const int TAW = box ? 16 : (GR_TU - 1) / nB + 2, TBW = box ? 8 : nB;
-        int stT = TAW + TBW + GR_TV;
-        stT += (4 - (stT & 7) + 8) & 7;           // = 4 (mod 8): conflict-free DMMA fragment reads (row offset 8 banks per k)
-        const int nTB = (nB + 7) / 8;
-        const size_t fsmem = (size_t)(2 * GR_KC * ((a.m | 1) + (b.m | 1) + (c.m | 1) + 1) + 2 * GR_KC * stT) * sizeof(double) +
-                             (size_t)(TAW + TBW + GR_TV) * sizeof(unsigned);
-        const int64_t fgx = box ? (int64_t)((nA + 15) / 16) * nTB : gx;
-        if (fsmem <= 227 * 1024 && fgx <= 0x7fffffff) {
-            dim3 fgrid((unsigned)fgx, (unsigned)gy, (unsigned)ksplit);
-            if (box) {
-                TN_SMEM(gram_f64_fact_kernel<true>, fsmem);
-                gram_f64_fact_kernel<true><<<fgrid, GR_THREADS, fsmem, st>>>(a, b, c, w, rows, direct ? dst : work, nA, nB, nC, rps, TAW, TBW, stT, nTB);
-            } else {
-                TN_SMEM(gram_f64_fact_kernel<false>, fsmem);
-                gram_f64_fact_kernel<false><<<fgrid, GR_THREADS, fsmem, st>>>(a, b, c, w, rows, direct ? dst : work, nA, nB, nC, rps, TAW, TBW, stT, nTB);
+        // factored-operand kernel.  Tiling of the 128 U columns of a CTA: a 16 x 8 box of (qa, qb) (24 operand columns), or 128 consecutive
+        // (qa, qb) indices (needs the second factor's pairs to fit: nB < 64; 127 / nB + 2 + nB operand columns); the first two factors may
+        // be exchanged (the kernel writes row qb * nA + qa then).  The choice minimises the padded tile area; a site where no choice
+        // comes within 25 % of the plain 128-column tiling, or whose operand columns are no fewer than U's, keeps the kernel above.
+        const int64_t lin_pad = ceil_div64(nU, GR_TU) * GR_TU;
+        int best_swap = 0, best_box = 0;
+        int64_t best_pad = -1;
+        int best_cols = 0;
+        for (int sw = 0; sw < 2; ++sw) {
+            const int xA = sw ? nB : nA, xB = sw ? nA : nB;
+            for (int bx = 0; bx < 2; ++bx) {
+                if (!bx && xB >= 64) continue;
+                const int64_t pad = bx ? ceil_div64(xA, 16) * 16 * (ceil_div64(xB, 8) * 8) : lin_pad;
+                const int cols = bx ? 24 : (GR_TU - 1) / xB + 2 + xB;
+                if (cols > 64) continue;
+                if (best_pad < 0 || pad < best_pad || (pad == best_pad && cols < best_cols)) {
+                    best_pad = pad; best_cols = cols; best_swap = sw; best_box = bx;
+                }
             }
-            launched = true;
+        }
+        if (best_pad >= 0 && 4 * best_pad <= 5 * lin_pad) {
+            const FactorDev& xa = best_swap ? b : a;
+            const FactorDev& xb = best_swap ? a : b;
+            const int xA = best_swap ? nB : nA, xB = best_swap ? nA : nB;
+            const bool box = best_box != 0;
+            const int TAW = box ? 16 : (GR_TU - 1) / xB + 2, TBW = box ? 8 : xB;
+            int stT = TAW + TBW + GR_TV;
+            stT += (4 - (stT & 7) + 8) & 7;           // = 4 (mod 8): conflict-free DMMA fragment reads (row offset 8 banks per k)
+            const int nTB = (xB + 7) / 8;
+            const size_t fsmem = (size_t)(2 * GR_KC * ((a.m | 1) + (b.m | 1) + (c.m | 1) + 1) + 2 * GR_KC * stT) * sizeof(double) +
+                                 (size_t)(TAW + TBW + GR_TV) * sizeof(unsigned);
+            const int64_t fgx = box ? (int64_t)((xA + 15) / 16) * nTB : gx;
+            if (fsmem <= 227 * 1024 && fgx <= 0x7fffffff) {
+                dim3 fgrid((unsigned)fgx, (unsigned)gy, (unsigned)ksplit);
+                if (box) {
+                    TN_SMEM(gram_f64_fact_kernel<true>, fsmem);
+                    gram_f64_fact_kernel<true><<<fgrid, GR_THREADS, fsmem, st>>>(xa, xb, c, w, rows, direct ? dst : work, xA, xB, nC, rps, TAW, TBW, stT,
+                                                                                 nTB, best_swap);
+                } else {
+                    TN_SMEM(gram_f64_fact_kernel<false>, fsmem);
+                    gram_f64_fact_kernel<false><<<fgrid, GR_THREADS, fsmem, st>>>(xa, xb, c, w, rows, direct ? dst : work, xA, xB, nC, rps, TAW, TBW, stT,
+                                                                                  nTB, best_swap);
+                }
+                launched = true;
+            }
         }
     }
     if (!launched) {

@@ -38,7 +38,10 @@ cases = [("tiny", 37, 3, 2, 4, {}), ("ragged_box", 1000, 5, 12, 7, {}), ("no_w",
          ("sincos_mid", 2051, 10, 2, 9, {"map_b": ops.MAP_SINCOS}), ("poly_mid", 777, 8, 4, 8, {"map_b": ops.MAP_POLY}),
          ("poly_box", 4100, 4, 11, 5, {"map_b": ops.MAP_POLY}), ("div_a", 640, 5, 3, 6, {"div_a": 4}), ("one_c", 500, 20, 9, 1, {}),
          ("one_b", 900, 17, 1, 13, {}), ("acc", 70000, 7, 2, 7, {"accumulate": True}), ("wide", 300, 40, 12, 38, {}),
-         ("sincos_a", 1500, 2, 5, 6, {"map_a": ops.MAP_SINCOS})]
+         ("sincos_a", 1500, 2, 5, 6, {"map_a": ops.MAP_SINCOS}),
+         # the engine's own role orders (network.py::_roles puts the input factor first): the launcher exchanges the first two factors
+         ("swap_lin_cfg3", 3000, 2, 24, 24, {"map_a": ops.MAP_SINCOS}), ("swap_lin_cfg5b", 1200, 6, 38, 38, {}), ("swap_box", 800, 11, 12, 3, {}),
+         ("swap_lin_acc", 9000, 3, 20, 5, {"accumulate": True})]
 worst = 0.0
 for name, S, ma, mb, mc, o in cases:
     w = None if "w" in o else torch.rand((S,), device="cuda", generator=g) + 0.5
@@ -75,14 +78,22 @@ for name, S, ma, mb, mc, o in cases:
 print(json.dumps({"worst_rel_err_fact": worst, "ok": worst < 1e-13}), flush=True)
 
 # ---- timing on the BASELINE sites
-sites = (("cfg3_mid", 515345, 24, 2, 24), ("cfg5a_mid", 32768, 38, 29, 38), ("cfg5b_mid", 131072, 38, 6, 38), ("cfg2", 20640, 100, 9, 1),
-         ("cfg1", 4177, 6, 9, 6))
+sites = (("cfg3_mid", 515345, 24, 2, 24, 0), ("cfg3_mid_sincos", 515345, 24, 2, 24, ops.MAP_SINCOS), ("cfg3_engine_order", 515345, 2, 24, 24, 0),
+         ("cfg5a_mid", 32768, 38, 29, 38, 0), ("cfg5a_engine_order", 32768, 38, 38, 29, 0),
+         ("cfg5b_mid", 131072, 38, 6, 38, 0), ("cfg5b_mid_poly", 131072, 38, 6, 38, ops.MAP_POLY), ("cfg5b_engine_order", 131072, 6, 38, 38, 0),
+         ("cfg2_site", 20640, 100, 1, 9, 0), ("cfg1", 4177, 6, 9, 6, 0))
 if QUICK:
-    sites = (("cfg3_mid", 131072, 24, 2, 24), ("cfg5a_mid", 8192, 38, 29, 38), ("cfg5b_mid", 32768, 38, 6, 38))
-for name, S, ma, mb, mc in sites:
-    Fa = torch.randn((S, ma), device="cuda", generator=g); Fb = torch.rand((S, mb), device="cuda", generator=g); Fc = torch.randn((S, mc), device="cuda", generator=g)
+    sites = (("cfg3_engine_order", 515345, 2, 24, 24, 0), ("cfg5a_engine_order", 8192, 38, 38, 29, 0), ("cfg5b_engine_order", 65536, 6, 38, 38, 0),
+             ("cfg2_site", 20640, 100, 1, 9, 0))
+for name, S, ma, mb, mc, kind in sites:
+    Fa = torch.randn((S, ma), device="cuda", generator=g); Fc = torch.randn((S, mc), device="cuda", generator=g)
+    if kind:
+        X = torch.rand((S, 4), device="cuda", generator=g) * 2 - 1
+        fb = Factor(X, m=mb, map_kind=kind, col=2)
+    else:
+        fb = Factor(torch.rand((S, mb), device="cuda", generator=g), m=mb)
     w = torch.rand((S,), device="cuda", generator=g) + 0.5
-    args = (ops.GRAM_FP64, Factor(Fa, m=ma), Factor(Fb, m=mb), Factor(Fc, m=mc), w, S)
+    args = (ops.GRAM_FP64, Factor(Fa, m=ma), fb, Factor(Fc, m=mc), w, S)
     fl = 2.0 * S * npair(ma) * npair(mb) * npair(mc)
     outs = {}
     for var in ("fact", "old"):
@@ -94,5 +105,6 @@ for name, S, ma, mb, mc in sites:
         e1.record(); torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 3
         outs[var] = M.clone()
-        print(json.dumps({"site": name, "rows": S, "kernel": var, "ms": ms, "tflops_fp64": fl / ms / 1e9}), flush=True)
+        print(json.dumps({"site": name, "rows": S, "kernel": var, "ms": ms, "tflops_fp64": fl / ms / 1e9,
+                          "ksplit": int(ops._lib.load().tn_gram_ksplit(S, ma, mb, mc, 0))}), flush=True)
     print(json.dumps({"site": name, "rel_diff": float((outs["fact"] - outs["old"]).norm() / outs["old"].norm())}), flush=True)
