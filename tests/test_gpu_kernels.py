@@ -292,3 +292,64 @@ def test_rhs_large_core_register_blocked(S, ma, mb, mc, V, fmap, monkeypatch):
     monkeypatch.setenv("TN_RHS_NO_BIG", "1")
     old = ops.rhs(fa, fb, fc, T(w), rows)
     assert gu.relerr(old.cpu().numpy(), want) < 1e-12
+
+
+@pytest.mark.parametrize("S,ma,mb,mc,opts", [
+    (37, 3, 2, 4, {}),                                  # fewer rows than two chunks
+    (1000, 5, 12, 7, {}),                               # 16 x 8 box tiling, ragged boxes on both sides
+    (333, 6, 3, 6, {"no_w": True}),                     # consecutive-index tiling, unit weights
+    (2051, 10, 2, 9, {"map_b": "sincos"}),              # mapped middle factor expanded by the two mapper warps
+    (4100, 4, 11, 5, {"map_b": "poly"}),                # mapped factor on the box tiling
+    (640, 5, 3, 6, {"div_a": 4}),                       # rows of the first factor shared by 4 samples
+    (900, 17, 1, 13, {}),                               # one pair in the middle: the unfactored kernel keeps the site
+    (3000, 2, 24, 24, {"map_a": "sincos"}),             # the engine's role order of config 3: first two factors exchanged
+    (1200, 6, 38, 38, {}),                              # ... of config 5b
+    (800, 11, 12, 3, {}),                               # exchanged factors on the box tiling
+    (70000, 7, 2, 7, {"accumulate": True}),             # several row splits reduced into an existing M
+    (300, 40, 12, 38, {}),                              # wide factors (two cp.async rounds per row)
+])
+def test_gram_fp64_factored_operand_kernel(S, ma, mb, mc, opts, monkeypatch):
+    """fp64 Gram with the factored left operand (gram.cu::gram_f64_fact_kernel: the tile holds [w pair(fa) | pair(fb) | pair(fc)] and
+    an A-fragment element is one product made in registers; cp.async ring of raw factors; one barrier per 32-row chunk) on every
+    tiling the launcher can choose, against numpy and against the unfactored kernel (TN_GRAM_F64_UNFACTORED=1)."""
+    rng = np.random.default_rng(S + 7 * ma + mb)
+    da = opts.get("div_a", 1)
+
+    def feat(raw, kind, m):
+        if kind == "sincos":
+            return np.stack([np.cos(0.5 * np.pi * raw), np.sin(0.5 * np.pi * raw)], 1)
+        return np.stack([raw ** d for d in range(m)], 1)
+
+    kinds = {"sincos": ops.MAP_SINCOS, "poly": ops.MAP_POLY}
+    if "map_a" in opts:
+        Xa = rng.uniform(-1, 1, size=(S, 3))
+        fa, Fa = Factor(T(Xa), m=ma, map_kind=kinds[opts["map_a"]], col=2), feat(Xa[:, 2], opts["map_a"], ma)
+    else:
+        Ta = rng.normal(size=(S // da, ma))
+        fa, Fa = Factor(T(Ta), m=ma, div=da), np.repeat(Ta, da, axis=0)
+    if "map_b" in opts:
+        Xb = rng.uniform(-1, 1, size=(S, 4))
+        fb, Fb = Factor(T(Xb), m=mb, map_kind=kinds[opts["map_b"]], col=1), feat(Xb[:, 1], opts["map_b"], mb)
+    else:
+        Fb = rng.uniform(-1, 1, size=(S, mb))
+        fb = Factor(T(Fb), m=mb)
+    Fc_wide = rng.normal(size=(S, mc + 3))
+    Fc = Fc_wide[:, :mc]
+    fc = Factor(T(Fc_wide)[:, :mc], m=mc)              # row stride != m
+    w = None if opts.get("no_w") else rng.uniform(0.5, 1.5, size=S)
+    want = np.einsum("s,sa,sb,sc->abc", np.ones(S) if w is None else w, pairs(Fa), pairs(Fb), pairs(Fc)).reshape(-1)
+    wt = None if w is None else T(w)
+
+    def run():
+        if opts.get("accumulate"):
+            M0 = torch.full((want.size,), 0.25, device=DEV)
+            return (ops.gram(ops.GRAM_FP64, fa, fb, fc, wt, S, M=M0, accumulate=True) - 0.25).cpu().numpy()
+        return ops.gram(ops.GRAM_FP64, fa, fb, fc, wt, S).cpu().numpy()
+
+    got = run()
+    assert np.isfinite(got).all()
+    assert gu.relerr(got, want) < 1e-13
+    monkeypatch.setenv("TN_GRAM_F64_UNFACTORED", "1")
+    old = run()
+    assert gu.relerr(old, want) < 1e-13
+    assert gu.relerr(got, old) < 1e-14
