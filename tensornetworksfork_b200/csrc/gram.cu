@@ -205,11 +205,22 @@ __device__ __forceinline__ void cp_async8(double* dst, const double* src, bool v
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-// identity factor: the m values of one row, a lane per column (zero fill when the row is past the end)
-__device__ __forceinline__ void gf_fill_row(const FactorDev& f, double* dst, int64_t row, bool ok, int lane) {
+__device__ __forceinline__ void cp_async16(double* dst, const double* src, bool valid) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+// identity factor: the m values of one row (zero fill when the row is past the end); a lane per column pair when the factor's rows are
+// 16-byte aligned in global memory (vec: base aligned, even row stride -- the environments of even bond dimension), else a lane per column
+__device__ __forceinline__ void gf_fill_row(const FactorDev& f, double* dst, int64_t row, bool ok, int lane, bool vec) {
     if (f.map_kind != TN_MAP_IDENTITY) return;
     const double* src = f.ptr + (f.div == 1 ? row : row / f.div) * f.ld;
-    for (int i = lane; i < f.m; i += 32) cp_async8(dst + i, src + i, ok);
+    if (vec) {
+        for (int i = 2 * lane; i + 1 < f.m; i += 64) cp_async16(dst + i, src + i, ok);
+        if ((f.m & 1) && lane == 31) cp_async8(dst + f.m - 1, src + f.m - 1, ok);
+    } else {
+        for (int i = lane; i < f.m; i += 32) cp_async8(dst + i, src + i, ok);
+    }
 }
 // feature-mapped factor: lane k of an owning warp holds the raw value of row k and writes every second of its m features
 __device__ __forceinline__ double gf_load_raw(const FactorDev& f, int64_t row) {
@@ -222,11 +233,13 @@ __device__ __forceinline__ void gf_store_mapped(const FactorDev& f, double* dst,
 template <bool BOX>
 __global__ void __launch_bounds__(GR_THREADS, 2)
 gram_f64_fact_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restrict__ w, int64_t rows, double* __restrict__ out,
-                     int nA, int nB, int nC, int64_t rows_per_split, int TAW, int TBW, int stT, int nTB, int swapU) {
-    extern __shared__ double sm[];
-    const int stA = fa.m | 1, stB = fb.m | 1, stC = fc.m | 1;
+                     int nA, int nB, int nC, int64_t rows_per_split, int TAW, int TBW, int stT, int nTB, int swapU, int vecmask) {
+    extern __shared__ __align__(16) double smf[];
+    // even row strides: every row of a raw factor starts on a 16-byte boundary (16-byte cp.async); the synthesis gathers columns of ONE row
+    // per instruction, so the stride does not enter its bank pattern
+    const int stA = (fa.m + 1) & ~1, stB = (fb.m + 1) & ~1, stC = (fc.m + 1) & ~1;
     const int rawsz = GR_KC * (stA + stB + stC + 1);                      // one raw buffer: [FA | FB | FC | W]
-    double* sRaw = sm;                                                    // [2][rawsz]
+    double* sRaw = smf;                                                    // [2][rawsz]
     double* sT = sRaw + 2 * rawsz;                                        // [2][GR_KC][stT]: rows of [PA | PB | V]
     unsigned* tCol = reinterpret_cast<unsigned*>(sT + 2 * GR_KC * stT);   // [NCOL]: i | j << 16 of the column's index pair
     const int NCOL = TAW + TBW + GR_TV;
@@ -316,9 +329,9 @@ gram_f64_fact_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __r
             const int64_t row = kb + k;
             const bool ok = row < k_end;
             const int64_t rc = ok ? row : last_row;
-            gf_fill_row(fa, raw + k * stA, rc, ok, lane);
-            gf_fill_row(fb, raw + GR_KC * stA + k * stB, rc, ok, lane);
-            gf_fill_row(fc, raw + GR_KC * (stA + stB) + k * stC, rc, ok, lane);
+            gf_fill_row(fa, raw + k * stA, rc, ok, lane, vecmask & 1);
+            gf_fill_row(fb, raw + GR_KC * stA + k * stB, rc, ok, lane, vecmask & 2);
+            gf_fill_row(fc, raw + GR_KC * (stA + stB) + k * stC, rc, ok, lane, vecmask & 4);
         }
         if (warp == 0) {
             const int64_t row = kb + lane;
@@ -814,19 +827,23 @@ static int launch_kr3(const tn_factor* fa, const tn_factor* fb, const tn_factor*
             int stT = TAW + TBW + GR_TV;
             stT += (4 - (stT & 7) + 8) & 7;           // = 4 (mod 8): conflict-free DMMA fragment reads (row offset 8 banks per k)
             const int nTB = (xB + 7) / 8;
-            const size_t fsmem = (size_t)(2 * GR_KC * ((a.m | 1) + (b.m | 1) + (c.m | 1) + 1) + 2 * GR_KC * stT) * sizeof(double) +
+            const size_t fsmem = (size_t)(2 * GR_KC * (((a.m + 1) & ~1) + ((b.m + 1) & ~1) + ((c.m + 1) & ~1) + 1) + 2 * GR_KC * stT) * sizeof(double) +
                                  (size_t)(TAW + TBW + GR_TV) * sizeof(unsigned);
             const int64_t fgx = box ? (int64_t)((xA + 15) / 16) * nTB : gx;
+            auto vec_ok = [](const FactorDev& f) {
+                return f.map_kind == TN_MAP_IDENTITY && f.m >= 2 && (reinterpret_cast<uintptr_t>(f.ptr) & 15) == 0 && (f.ld & 1) == 0;
+            };
+            const int vecmask = getenv("TN_GRAM_F64_CP8") ? 0 : (vec_ok(xa) ? 1 : 0) | (vec_ok(xb) ? 2 : 0) | (vec_ok(c) ? 4 : 0);
             if (fsmem <= 227 * 1024 && fgx <= 0x7fffffff) {
                 dim3 fgrid((unsigned)fgx, (unsigned)gy, (unsigned)ksplit);
                 if (box) {
                     TN_SMEM(gram_f64_fact_kernel<true>, fsmem);
                     gram_f64_fact_kernel<true><<<fgrid, GR_THREADS, fsmem, st>>>(xa, xb, c, w, rows, direct ? dst : work, xA, xB, nC, rps, TAW, TBW, stT,
-                                                                                 nTB, best_swap);
+                                                                                 nTB, best_swap, vecmask);
                 } else {
                     TN_SMEM(gram_f64_fact_kernel<false>, fsmem);
                     gram_f64_fact_kernel<false><<<fgrid, GR_THREADS, fsmem, st>>>(xa, xb, c, w, rows, direct ? dst : work, xA, xB, nC, rps, TAW, TBW, stT,
-                                                                                  nTB, best_swap);
+                                                                                  nTB, best_swap, vecmask);
                 }
                 launched = true;
             }
