@@ -104,6 +104,30 @@ def test_library_exports_every_declared_symbol():
     assert lib.tn_version() >= 100
 
 
+@pytest.mark.parametrize("rows,m", [(515345, (24, 2, 24)), (4177, (6, 9, 6)), (20640, (100, 1, 9)), (1000000, (38, 29, 38)), (131072, (38, 6, 38)),
+                                    (60000, (10, 2, 10)), (300, (3, 3, 3))])
+def test_gram_row_split_fills_whole_rounds(rows, m):
+    """tn_gram_ksplit (fp64 Gram / right-hand side): every CTA of a launch does the same work and two are resident per SM, so a launch takes
+    ceil(tiles * ks / slots) rounds -- the split must not leave the last round nearly empty (config 3's site once ran 600 CTAs on 296 slots),
+    keeps at least 8 chunks of 32 rows per split, and needs no GPU to be asked (148 SMs assumed off-device)."""
+    lib = _lib.load()
+    ks = lib.tn_gram_ksplit(rows, m[0], m[1], m[2], 0)
+    npair = lambda k: k * (k + 1) // 2
+    nU, nV = npair(m[0]) * npair(m[1]), npair(m[2])
+    tiles = -(-nU // 128) * -(-nV // 64)
+    slots = 2 * 148
+    assert 1 <= ks <= 1024
+    assert ks == 1 or ks <= -(-rows // 256)
+    assert lib.tn_gram_ksplit(rows, m[0], m[1], m[2], 3) == 1          # the tensor-core modes flush into M themselves
+    if ks > 1:
+        rounds = -(-tiles * ks // slots)
+        if ks < -(-rows // 256):                      # not limited by the rows: the last round is (almost) full
+            assert tiles * ks / (rounds * slots) > 0.85, (ks, tiles, rounds)
+        # no split with fewer rounds per row of work is left on the table (2 % hysteresis, 64 rows of per-CTA overhead)
+        cost = lambda k: -(-tiles * k // slots) * (-(-rows // k) + 64)
+        assert cost(ks) <= min(cost(k) for k in range(1, min(1024, -(-rows // 256)) + 1) if tiles * k <= 8 * slots) * 1.021
+
+
 def test_no_cpu_fallback():
     """On a CPU tensor the product path raises instead of computing."""
     layer = tnb.TensorTrainLayer(3, 2, 3, output_shape=1, seed=0)
