@@ -193,8 +193,8 @@ kr3_f64_kernel(FactorDev fa, FactorDev fb, FactorDev fc, const double* __restric
 //      columns per row instead of 128 + 64) and a DMMA A-fragment element is one product PA[k][la] * PB[k][lb] made in registers.  The
 //      128 U columns of a CTA are a 16 x 8 box of (qa, qb) when the middle factor has many pairs (BOX: 24 operand columns), else
 //      128 consecutive (qa, qb) indices (all pairs of the middle factor, <= 129 of the left one);
-//  (b) the raw factors of chunk c+2 arrive by cp.async (8 bytes per element, zero fill past the end of the split, no divisions,
-//      a warp per row) while chunk c+1 is synthesised and chunk c multiplied; a feature-mapped factor (one raw value per row) is
+//  (b) the raw factors of chunk c+2 arrive by cp.async (8 bytes per element, 16 where the factor's rows are 16-byte aligned -- measured
+//      equal --, zero fill past the end of the split, no divisions, a warp per row) while chunk c+1 is synthesised and chunk c multiplied; a feature-mapped factor (one raw value per row) is
 //      loaded into a register at the top of the iteration and expanded at its end by one warp;
 //  (c) one block barrier per 32-row chunk: raw buffers and operand tiles are double buffered, so the synthesis of the next chunk by
 //      fast warps overlaps the DMMAs of slow ones.
