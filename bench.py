@@ -747,7 +747,7 @@ def cpu_baseline_leg(args, wl, rows_total):
         if args.ref_rows:
             cmd += ["--ref-rows", str(args.ref_rows)]
         try:
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env, cwd=ROOT)   # bounded: the whole N = 1 line must stay far inside the driver's per-run limit
             line = [l for l in r.stdout.splitlines() if l.startswith("{")][-1]
             return json.loads(line)["cpu_baseline"]
         except Exception as e:      # fall through to the port, and say why
