@@ -296,7 +296,10 @@ class TensorNetwork:
         s = self._plan()[k]
         node = s.node
         order = self._order(s)
-        t = t4.reshape([node.dim_size(l) for l in order])
+        # bond and class sizes come from t4 (a QR re-gauge of a wide core shrinks a bond, reference network.py:644-657), the
+        # physical legs keep the node's
+        size = {s.left: t4.shape[0], s.cls: t4.shape[1], s.right: t4.shape[3]}
+        t = t4.reshape([size[l] if l in size else node.dim_size(l) for l in order])
         return t.permute(*[order.index(l) for l in node.dim_labels]).contiguous()
 
     # ------------------------------------------------------------------ data binding / caches
@@ -839,8 +842,24 @@ class TensorNetwork:
         for n in self.main_nodes:
             self.node_orthonormalize_right(n)
 
+    @staticmethod
+    def _qr_reduced(a):
+        """Reduced QR of ``a`` (m x n, contiguous; overwritten when tall): (Q (m x k), R (k x n)), k = min(m, n), in LAPACK's sign
+        convention like ``torch.linalg.qr(mode='reduced')`` (reference network.py:644,686).  A wide matrix -- a core with fewer rows
+        than columns, e.g. the first core of an unconstricted train with r > f -- has Householder vectors that only involve its first
+        m columns: Q is the Q of that square block, R = [R1 | Q^T A2]."""
+        m, n = a.shape
+        if m >= n:
+            R = ops.qr(a)
+            return a, R
+        q = a[:, :m].contiguous()
+        R1 = ops.qr(q)
+        rest = a[:, m:].contiguous()
+        R2 = ops.env_update(None, Factor(q.t().contiguous(), m=m), rest.reshape(1, m, n - m), m)
+        return q, torch.cat([R1, R2.reshape(m, n - m)], dim=1).contiguous()
+
     def node_orthonormalize_left(self, node):
-        """core_k <- Q, core_{k+1} <- R core_{k+1} (reference network.py:625-660)."""
+        """core_k <- Q, core_{k+1} <- R core_{k+1} (reference network.py:625-660); the bond shrinks to the row count of a wide core."""
         k = self.main_nodes.index(node)
         if k >= len(self.main_nodes) - 1:
             return
@@ -848,14 +867,13 @@ class TensorNetwork:
         G = self._canon(k)
         rl, c, f, rr = G.shape
         a = G.reshape(rl * c * f, rr).contiguous().clone()
-        if a.shape[0] < a.shape[1]:
-            raise NotImplementedError("QR re-gauge of a core with fewer rows than columns")
-        Rm = ops.qr(a)
-        node.tensor = self._from_canon(k, a.reshape(rl, c, f, rr))
+        Q, Rm = self._qr_reduced(a)                                   # (rows, kk), (kk, rr)
+        kk = Q.shape[1]
+        node.tensor = self._from_canon(k, Q.reshape(rl, c, f, kk))
         Gn = self._canon(k + 1)
         nl, nc, nf, nr = Gn.shape
-        newn = ops.env_update(None, Factor(Rm, m=rr), Gn.reshape(1, nl, nc * nf * nr), rr)
-        self.main_nodes[k + 1].tensor = self._from_canon(k + 1, newn.reshape(nl, nc, nf, nr))
+        newn = ops.env_update(None, Factor(Rm, m=rr), Gn.reshape(1, nl, nc * nf * nr), kk)
+        self.main_nodes[k + 1].tensor = self._from_canon(k + 1, newn.reshape(kk, nc, nf, nr))
         self._core_changed(k)
         self._core_changed(k + 1)
 
@@ -868,18 +886,17 @@ class TensorNetwork:
         G = self._canon(k)
         rl, c, f, rr = G.shape
         a = G.permute(1, 2, 3, 0).reshape(c * f * rr, rl)
-        if a.shape[0] < a.shape[1]:
-            raise NotImplementedError("QR re-gauge of a core with fewer rows than columns")
         a = torch.flip(a, dims=[0, 1]).contiguous()
-        Rrev = ops.qr(a)
-        Q = torch.flip(a, dims=[0, 1]).reshape(c, f, rr, rl).permute(3, 0, 1, 2)
+        Qrev, Rrev = self._qr_reduced(a)                              # (rows, kk), (kk, rl)
+        kk = Qrev.shape[1]
+        Q = torch.flip(Qrev, dims=[0, 1]).reshape(c, f, rr, kk).permute(3, 0, 1, 2)
         Rm = torch.flip(Rrev.t(), dims=[0, 1]).contiguous()          # (rl_old, rl_new)
-        node.tensor = self._from_canon(k, Q.reshape(rl, c, f, rr))
+        node.tensor = self._from_canon(k, Q.reshape(kk, c, f, rr))
         Gp = self._canon(k - 1)
         pl, pc, pf, pr = Gp.shape
         rows = pl * pc * pf
-        newp = ops.env_update(None, Factor(Gp.reshape(rows, pr).contiguous(), m=pr), Rm.reshape(1, pr, rl), rows)
-        self.main_nodes[k - 1].tensor = self._from_canon(k - 1, newp.reshape(pl, pc, pf, rl))
+        newp = ops.env_update(None, Factor(Gp.reshape(rows, pr).contiguous(), m=pr), Rm.reshape(1, pr, kk), rows)
+        self.main_nodes[k - 1].tensor = self._from_canon(k - 1, newp.reshape(pl, pc, pf, kk))
         self._core_changed(k)
         self._core_changed(k - 1)
 

@@ -188,3 +188,17 @@ def test_kl_divergence_uses_the_soft_target_in_its_gradient():
         spec.loader.exec_module(mod)
         rl, rg, rH = mod.KLDivBregman(w=0.7).forward(x, y)
         assert torch.allclose(rl, loss, atol=1e-13) and torch.allclose(rg, g, atol=1e-13) and torch.allclose(rH, H, atol=1e-13)
+
+
+def test_qr_regauge_of_wide_cores_cpu(monkeypatch):
+    """CPU twin of test_zz_gpu_late.py::test_qr_regauge_of_wide_cores_shrinks_the_bond_gpu on the stand-in kernels: the bonds of wide
+    cores shrink exactly as the reference's reduced QR makes them (found by running the fuzz suite on 700 more seeds)."""
+    import fake_ops
+    import qr_wide_case as qw
+    fake_ops.install(monkeypatch)
+    mid, final, worst, drift = qw.run("cpu")
+    assert mid == [(1, 2, 2), (2, 2, 4), (4, 2, 5), (5, 2)], mid
+    assert final == [(1, 2, 2), (2, 2, 4), (4, 2, 2), (2, 2)], final
+    assert worst < 1e-12 and drift < 1e-12, (worst, drift)
+    mid, final, worst, drift = qw.run("cpu", sites=5, r=7, f=3, seed=11)
+    assert worst < 1e-12 and drift < 1e-12, (worst, drift)

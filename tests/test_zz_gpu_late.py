@@ -151,3 +151,14 @@ def test_tc_gram_planar_raw_slots_match_the_row_major_layout(shape, monkeypatch)
     torch.cuda.synchronize()
     # fp64 atomics of different CTAs land in a different order from run to run: compare to rounding, not bit for bit
     assert float((got - ref).norm() / ref.norm()) < 1e-12
+
+
+def test_qr_regauge_of_wide_cores_shrinks_the_bond_gpu():
+    """An unconstricted 4-site train with r = 5 > f = 2: the first cores are wide (2 x 5, 4 x 5), the reference's reduced QR shrinks
+    their bonds (network.py:644-657, 686-704).  The engine builds Q from the square leading block (tn_qr) and R = [R1 | Q^T A2]
+    (tn_env_update); cores against the numpy oracle after a left and a right sweep of re-gauges, predictions unchanged
+    (first run on a B200: profiles/r2_qr_wide_check.log; CPU twin: test_host_logic.py::test_qr_regauge_of_wide_cores_cpu)."""
+    import qr_wide_case as qw
+    mid, final, worst, drift = qw.run("cuda")
+    assert mid[0] == (1, 2, 2) and mid[1] == (2, 2, 4), mid
+    assert worst < 1e-11 and drift < 1e-11, (worst, drift)
