@@ -78,17 +78,29 @@ def sweep_schedule(first_cols, second_cols, num_swipes, eps, eps_decay=None, ski
     last_first = None
     last_second = None
 
+    def pick(idx):
+        # A list that is too short is an IndexError in the reference at the moment the sweep gets there -- and never, when a
+        # convergence criterion ends the sweep first (TensorTrainRegressorEarlyStopping passes one epsilon per CORE while a
+        # linear-projection train has two trained nodes per core, tensor/module.py:573-582): the error object takes the place of the
+        # value and accumulating_swipe raises it when it reaches the entry.
+        if not isinstance(eps, list):
+            return eps
+        try:
+            return eps[idx]
+        except IndexError as err:
+            return err
+
     def eps_at(ns):
-        e = eps[ns] if isinstance(eps, list) else eps
-        if eps_decay is not None:
+        e = pick(ns)
+        if eps_decay is not None and not isinstance(e, Exception):
             e = e * eps_decay ** ns
         return e
 
     for _ in range(num_swipes):
         e = eps_at(NS)
         for i, col in enumerate(first_cols):
-            if eps_per_node:
-                e = eps[i if direction == "l2r" else len(first_cols) - 1 - i] if isinstance(eps, list) else eps
+            if eps_per_node and not isinstance(e, Exception):
+                e = pick(i if direction == "l2r" else len(first_cols) - 1 - i)
             last_first = col
             if last_second is not None and col == last_second:
                 continue
@@ -98,8 +110,8 @@ def sweep_schedule(first_cols, second_cols, num_swipes, eps, eps_decay=None, ski
             continue
         e = eps_at(NS)
         for i, col in enumerate(second_cols):
-            if eps_per_node:
-                e = eps[i if direction == "r2l" else len(second_cols) - 1 - i] if isinstance(eps, list) else eps
+            if eps_per_node and not isinstance(e, Exception):
+                e = pick(i if direction == "r2l" else len(second_cols) - 1 - i)
             last_second = col
             if last_first is not None and col == last_first:
                 continue
@@ -1149,6 +1161,8 @@ class TensorNetwork:
         need_loss = loss_callback is not None or (verbose and verbose > 1)
         for NS, half, pos, eps_ in sched:
             node = halves[half][pos]
+            if isinstance(eps_, Exception):
+                raise eps_                  # an epsilon list too short for this entry: the reference's IndexError, at the same point
             if timeout is not None and (time.time() - start) > timeout:
                 print(f"Timeout reached ({timeout} seconds). Stopping accumulating_swipe.")
                 return False

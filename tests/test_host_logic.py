@@ -83,6 +83,39 @@ def test_schedule_eps_list_and_skip_second():
     assert [(ns, i) for ns, _, i, _ in s2] == [(0, 0), (0, 1), (1, 0), (1, 1)]
 
 
+def test_schedule_short_eps_list_fails_where_the_reference_does():
+    """An epsilon list shorter than the sweep is an IndexError in the reference only when the sweep gets to the missing entry
+    (network.py:412,431): the schedule carries the error in place of the value, so a convergence criterion that ends the sweep
+    earlier never sees it (TensorTrainRegressorEarlyStopping on a linear-projection train: N epsilons, 2N trained nodes)."""
+    s = sweep_schedule([0, 1, 2, 3], [3, 2, 1, 0], 1, [4.0, 3.0], skip_second=True, eps_per_node=True)
+    assert [e for *_, e in s][:2] == [4.0, 3.0]
+    assert all(isinstance(e, IndexError) for *_, e in s[2:])
+    s = sweep_schedule([0, 1], [1, 0], 2, [4.0, 3.0, 2.0])          # the fourth half-sweep has no epsilon
+    assert [e for *_, e in s][:4] == [4.0, 4.0, 3.0, 2.0] and isinstance(s[-1][3], IndexError)
+
+
+def test_early_stopping_regressor_on_a_linear_projection_train(monkeypatch):
+    """tensor/module.py:573-582 passes one epsilon per core with eps_per_node=True; with linear_dim the train has two trained nodes per
+    core, and the fit only works because early stopping ends the pass before the list runs out (found by a fuzz of the module.py
+    classes against the reference: 750 configurations, this the only disagreement)."""
+    import fake_ops
+    import numpy as np
+    from tensornetworksfork_b200.tensor.module import TensorTrainRegressorEarlyStopping
+    fake_ops.install(monkeypatch)
+    rng = np.random.default_rng(103)
+    X = rng.uniform(-1, 1, size=(314, 5))
+    y = np.tanh(X @ rng.normal(size=(5, 1))) + 0.3 * X[:, :1] * X[:, 1:2] + 0.05 * rng.normal(size=(314, 1))
+    est = TensorTrainRegressorEarlyStopping(device="cpu", N=4, r=4, seed=22, constrict_bond=True, perturb=False, eps_start=0.1, eps_end=1.0,
+                                            batch_size=500, method="ridge_cholesky", linear_dim=2, early_stopping=2)
+    est.fit(X[:235], y[:235], X_val=X[235:], y_val=y[235:])
+    assert np.isfinite(est.predict(X[235:])).all()
+    # without a criterion the same call runs out of epsilons at the fifth trained node, as the reference does
+    tn = est._model.tensor_network
+    with pytest.raises(IndexError):
+        tn.accumulating_swipe(torch.tensor(np.concatenate([X, np.ones((314, 1))], 1)), torch.tensor(y), est.bf, eps=[1.0] * 4, eps_per_node=True,
+                              num_swipes=1, skip_second=True, method="ridge_cholesky", batch_size=500)
+
+
 def test_batch_mean_of_means_overweights_short_batch():
     loss = torch.arange(10.0)
     got = batch_mean_of_means(loss, 4)
