@@ -76,8 +76,10 @@ def test_module_fuzz(seed, monkeypatch):
         except Exception as e:
             out.append(("exc", type(e).__name__, str(e)[:300]))
     r, m = out
-    if r[0] == "exc":          # a constricted train the reference itself cannot contract
-        assert r[1] == "RuntimeError" and "einsum" in r[2], (name, kw, r)
+    if r[0] == "exc":
+        if r[1] == "RuntimeError" and "einsum" in r[2]:       # a constricted train the reference itself cannot contract
+            return
+        assert m[0] == "exc" and m[1] == r[1], (name, kw, r, m)  # e.g. the IndexError of an epsilon list that runs out mid-pass
         return
     assert m[0] == "ok", (name, kw, m)
     err = np.linalg.norm(np.asarray(m[1]) - np.asarray(r[1])) / max(np.linalg.norm(np.asarray(r[1])), 1e-12)
