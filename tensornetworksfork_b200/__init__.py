@@ -6,6 +6,7 @@ kernels behind a C ABI (include/tn_b200.h).  See DESIGN.md and INTEGRATION.md.
 """
 from . import ops  # noqa: F401
 from .tensor import (TensorNode, TensorNetwork, SumOfNetworks, CPDNetwork, MappedInput, TensorNetworkLayer, TensorTrainLayer,  # noqa: F401
-                     CPDLayer, TensorTrainDMRGInfiLayer, CumSumLayer, TensorConvolutionTrainLayer, TensorTrainLinearLayer, ConvTrainNetwork, SquareBregFunction, AutogradLoss, XEAutogradBregman, KLDivBregman)
+                     CPDLayer, TensorTrainDMRGInfiLayer, CumSumLayer, TensorConvolutionTrainLayer, TensorTrainLinearLayer, ConvTrainNetwork, BregFunction, SquareBregFunction, AutogradLoss, XEAutogradBregman, KLDivBregman, SoftmaxSquaredLoss,
+                     BinaryKLDivBregman, AutogradBregman, UncertaintyAutogradLoss)
 
 __version__ = "0.1.0"

@@ -5,4 +5,5 @@ from .layers import (TensorNetworkLayer, TensorTrainLayer, CPDLayer, MainNodeLay
                      TensorTrainDMRGInfiLayer, CumSumLayer, TensorConvolutionTrainLayer, TensorTrainLinearLayer)
 from .conv import ConvTrainNetwork  # noqa: F401
 from .cumsum import CumSumNetwork  # noqa: F401
-from .bregman import SquareBregFunction, AutogradLoss, XEAutogradBregman, KLDivBregman  # noqa: F401
+from .bregman import (BregFunction, SquareBregFunction, AutogradLoss, XEAutogradBregman, KLDivBregman, SoftmaxSquaredLoss,  # noqa: F401
+                      BinaryKLDivBregman, AutogradBregman, UncertaintyAutogradLoss)

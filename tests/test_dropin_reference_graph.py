@@ -155,8 +155,9 @@ def test_singular_system_returns_false_like_reference(monkeypatch):
 @pytest.mark.parametrize("loss_name", ["KLDivBregman", "SoftmaxSquaredLoss", "BinaryKLDivBregman", "UncertaintyAutogradLoss", "AutogradLoss"])
 def test_reference_loss_objects_drive_the_engine(loss_name, monkeypatch):
     """Any object with the reference's ``forward(y_pred, y) -> (loss, d_loss, sqd_loss)`` contract (tensor/bregman.py) can be handed
-    to the B200 engine unchanged: the per-sample Hessian is taken apart into rank-one terms on the host.  Side by side with the
-    reference's own engine, same loss object class, same seed."""
+    to the B200 engine: the per-sample Hessian is taken apart into rank-one terms on the host.  Side by side with the reference's own
+    engine under the reference's class, the B200 engine under the mirrored class of tensor/bregman.py (values of the mirrored classes
+    against the reference's: test_losses_vs_reference.py), same seed."""
     import fake_ops
     fake_ops.install(monkeypatch)
     ref_layers, ref_breg = _import_reference()
@@ -167,30 +168,30 @@ def test_reference_loss_objects_drive_the_engine(loss_name, monkeypatch):
     if loss_name == "KLDivBregman":
         C = 2                                       # C logits + an appended zero logit against C + 1 class probabilities
         y = torch.tensor(np.eye(C + 1)[rng.integers(0, C + 1, N)])
-        make = lambda: ref_breg.KLDivBregman(w=1.0)
+        make = lambda b: b.KLDivBregman(w=1.0)
     elif loss_name == "SoftmaxSquaredLoss":
         C = 3
         y = torch.tensor(np.eye(C)[rng.integers(0, C, N)] * 0.9 + 0.1 / C)
-        make = lambda: ref_breg.SoftmaxSquaredLoss(w=1.0)
+        make = lambda b: b.SoftmaxSquaredLoss(w=1.0)
     elif loss_name == "BinaryKLDivBregman":
         C = 1
         y = torch.tensor(rng.integers(0, 2, size=(N, 1)).astype(np.float64))
-        make = lambda: ref_breg.BinaryKLDivBregman(w=1.0)
+        make = lambda b: b.BinaryKLDivBregman(w=1.0)
     elif loss_name == "UncertaintyAutogradLoss":
         C = 2                                       # (mean, pre-softplus std), default_train_uncertainty.py
         y = torch.tensor(np.tanh(X[:, 0].numpy()) + 0.1 * rng.normal(size=N))
-        make = lambda: ref_breg.UncertaintyAutogradLoss()
+        make = lambda b: b.UncertaintyAutogradLoss()
     else:
         C = 2
         y = torch.tensor(np.tanh(X[:, :2].numpy()) + 0.1 * rng.normal(size=(N, 2)))
-        make = lambda: ref_breg.AutogradLoss(torch.nn.HuberLoss(reduction="none", delta=0.5))
+        make = lambda b: b.AutogradLoss(torch.nn.HuberLoss(reduction="none", delta=0.5))
     kw = dict(batch_size=64, num_swipes=1, lr=0.5, method="ridge_cholesky", eps=2.0)
     out = []
-    for mod in (ref_layers, tnb):
+    for mod, breg in ((ref_layers, ref_breg), (tnb, tnb)):       # the reference's loss class on its engine, the mirrored class on ours
         layer = mod.TensorTrainLayer(3, 3, F + 1, output_shape=C, constrict_bond=False, seed=11)
         tn = layer.tensor_network
         losses = []
-        ok = tn.accumulating_swipe(X, y, make(), loss_callback=lambda NS, nd, l: losses.append(float(l)), **kw)
+        ok = tn.accumulating_swipe(X, y, make(breg), loss_callback=lambda NS, nd, l: losses.append(float(l)), **kw)
         out.append((ok, losses, tn.forward(X, to_tensor=True).detach()))
     (r_ok, r_l, r_p), (m_ok, m_l, m_p) = out
     assert m_ok == r_ok
