@@ -809,6 +809,24 @@ class TensorNetwork:
         A = A.permute(*(perm + [len(dims) + p for p in perm])).contiguous()
         return A, self._from_canon(k, b.reshape(tuple(self._canon(k).shape)))
 
+    def get_b(self, node, grad):
+        """b = J^T grad of one node, in the node's own shape (reference network.py:259-291: the right-hand side the matrix-free
+        sweeps start from), built from the currently bound data by the right-hand-side kernel; J is not formed.  As for ``get_A_b``
+        the data is what ``set_input`` bound last (the engine's ``forward`` does not rebind, so that predicting on validation rows
+        inside a sweep leaves the cached environments of the training rows alone)."""
+        if self._data is None:
+            raise RuntimeError("get_b: no data bound -- call set_input(x) first")
+        k = self.main_nodes.index(node)
+        S = grad.shape[0]
+        g = grad.reshape(S, -1)
+        prob = self._site_problem(k, None, _FixedTerms(g, torch.zeros((S, g.shape[1], 1), dtype=g.dtype, device=g.device)))
+        rf = prob["rhs"]
+        b = ops.rhs(rf[0], rf[1], rf[2], prob["rw"], prob["rrows"])
+        if self.process_group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(b, group=self.process_group)
+        return self._from_canon(k, b.reshape(tuple(self._canon(k).shape)))
+
     def _layout(self, k):
         """(sizes of the node's legs in canonical order, permutation canonical -> node label order)."""
         s = self._plan()[k]

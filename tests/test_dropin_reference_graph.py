@@ -202,6 +202,31 @@ def test_reference_loss_objects_drive_the_engine(loss_name, monkeypatch):
         assert float((m_p - r_p).norm() / r_p.norm()) < 1e-7
 
 
+@pytest.mark.parametrize("C,n,r,F", [(1, 3, 3, 3), (2, 4, 3, 2), (3, 2, 4, 4)])
+def test_get_b_matches_the_reference(C, n, r, F, monkeypatch):
+    """``get_b(node, grad)`` -- the right-hand side J^T grad the reference's matrix-free sweeps start from (network.py:259-291) --
+    for every core of a train, from the right-hand-side kernel (stand-in here) against the reference's materialised-Jacobian einsum."""
+    import fake_ops
+    fake_ops.install(monkeypatch)
+    ref_layers, _ = _import_reference()
+    import tensornetworksfork_b200 as tnb
+    rng = np.random.default_rng(C + 10 * n)
+    N = 70
+    X = torch.tensor(np.concatenate([rng.uniform(-1, 1, size=(N, F)), np.ones((N, 1))], 1))
+    grad = torch.tensor(rng.normal(size=(N, C)))
+    outs = []
+    for mod in (ref_layers, tnb):
+        tn = mod.TensorTrainLayer(n, r, F + 1, output_shape=C, constrict_bond=False, seed=4).tensor_network
+        tn.forward(X, to_tensor=True)
+        tn.set_input(X)
+        outs.append([tn.get_b(nd, grad) for nd in tn.train_nodes])
+    for a, b in zip(*outs):
+        assert a.shape == b.shape
+        assert float((a - b).norm() / a.norm()) < 1e-13
+    with pytest.raises(RuntimeError):
+        tnb.TensorTrainLayer(n, r, F + 1, output_shape=C, seed=4).tensor_network.get_b(None, grad)
+
+
 def test_cpd_engine_runs_reference_built_graph(monkeypatch):
     """INTEGRATION.md route 1 for CPD: the reference's CPDLayer builds the graph, the B200 CPDNetwork runs it."""
     import fake_ops
