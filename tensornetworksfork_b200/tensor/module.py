@@ -24,6 +24,14 @@ def root_mean_squared_error_torch(y_true, y_pred):
     return root_mean_squared_error(y_true.cpu().numpy(), y_pred.cpu().numpy())
 
 
+def unexplained_variance(y_true, y_pred):
+    """Mean over samples of the residual sum of squares across outputs over the total one about the column means (reference
+    tensor/module.py:16-20)."""
+    total = ((y_true - y_true.mean(dim=0, keepdim=True)) ** 2).sum(dim=1, keepdim=True)
+    resid = ((y_true - y_pred) ** 2).sum(dim=1, keepdim=True)
+    return (resid / total).mean().item()
+
+
 class EarlyStopping:
     """Validation after every core of the one-pass sweep, indexed by the degree reached (reference tensor/module.py:22-101)."""
 
