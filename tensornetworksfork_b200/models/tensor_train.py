@@ -14,6 +14,7 @@ from sklearn.metrics import accuracy_score, r2_score, root_mean_squared_error
 
 from ..tensor.bregman import SquareBregFunction
 from ..tensor.layers import CPDLayer, CumSumLayer, TensorNetworkLayer, TensorTrainLayer, TensorTrainLinearLayer
+from ..tensor.module import unexplained_variance  # noqa: F401  (reference models/tensor_train.py:20-24, models/tnml.py:30-34)
 from ..tensor.network import SumOfNetworks
 
 

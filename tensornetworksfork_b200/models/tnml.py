@@ -16,7 +16,7 @@ from sklearn.metrics import accuracy_score, r2_score
 from ..tensor.bregman import SquareBregFunction
 from ..tensor.layers import TensorTrainLayer
 from ..tensor.network import MappedInput
-from .tensor_train import EarlyStopping, error_rate_torch, root_mean_squared_error_torch, split_validation
+from .tensor_train import EarlyStopping, error_rate_torch, root_mean_squared_error_torch, split_validation, unexplained_variance  # noqa: F401
 
 
 def fbasis(X):
