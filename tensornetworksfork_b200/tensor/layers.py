@@ -217,6 +217,20 @@ class TensorTrainLinearLayer(TensorNetworkLayer):
                                               output_labels=self.main_node_layer.labels))
 
 
+def get_cum_sum_operator(n, num_carriages, input_features, dtype=None):
+    """Operator node of site ``n`` of the reference's cum-sum train as a dense tensor (left, p_in, p_core, right), reference
+    tensor/layers.py:408-423: entry (i, k, k, m) is one where i <= k (a single all-ones row on the first site) and m = k (m = 0 on the
+    last site).  ``CumSumLayer`` here never builds it -- ``tensor/cumsum.py`` uses the closed form of the contracted train -- it is kept
+    for callers that assemble the operator train themselves."""
+    f = input_features
+    left = 1 if n == 0 else f
+    right = 1 if n == num_carriages - 1 else f
+    op = torch.zeros((left, f, f, right), dtype=dtype)
+    for k in range(f):
+        op[: (1 if left == 1 else k + 1), k, k, 0 if right == 1 else k] = 1
+    return op
+
+
 class CumSumLayer(TensorNetworkLayer):
     """Tensor train over ordered feature tuples (reference layers.py:425-477).  Same cores and draws as
     ``TensorTrainLayer``; the reference's dense cum-sum operator nodes are replaced by the closed form in
