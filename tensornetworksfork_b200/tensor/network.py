@@ -399,6 +399,22 @@ class TensorNetwork:
         self.left_stacks = None
         self.right_stacks = None
 
+    # The reference keeps its environments as dictionaries of contracted nodes and exposes their maintenance (network.py:73-99,152-172);
+    # callers outside the class only ever ask for them to be brought up to date (symmetric_operator.py:52, cum_sum_operator.py:67).
+    # Here the environments are cached device tensors rebuilt on demand, so "recompute" and "update" mean: forget what the change
+    # invalidated.
+    def recompute_all_stacks(self, exclude_nodes=None):
+        self.reset_stacks()
+
+    def left_update_stacks(self, node):
+        """The node changed: environments that contain it are dropped (reference network.py:152-161 recontracts the left one)."""
+        if type(self) is TensorNetwork and any(node is n for n in self.main_nodes):
+            self._core_changed(self.main_nodes.index(node))
+        else:
+            self.reset_stacks()          # subclasses keep further caches: drop everything
+
+    right_update_stacks = left_update_stacks
+
     def _stamp(self):
         return [(id(s.node.tensor), s.node.tensor._version) + ((id(s.linear.tensor), s.linear.tensor._version) if s.linear is not None else ())
                 for s in self._plan()]

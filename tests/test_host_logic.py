@@ -235,3 +235,29 @@ def test_qr_regauge_of_wide_cores_cpu(monkeypatch):
     assert worst < 1e-12 and drift < 1e-12, (worst, drift)
     mid, final, worst, drift = qw.run("cpu", sites=5, r=7, f=3, seed=11)
     assert worst < 1e-12 and drift < 1e-12, (worst, drift)
+
+
+def test_stack_maintenance_calls_of_the_reference_are_accepted(monkeypatch):
+    """recompute_all_stacks / left_update_stacks / right_update_stacks (reference network.py:73-77,152-172; called from outside the
+    class by symmetric_operator.py:52 and cum_sum_operator.py:67): here they only forget cached environments, and a prediction after
+    a core was changed in place is the one of the new cores either way."""
+    import fake_ops
+    import numpy as np
+    import tensornetworksfork_b200 as tnb
+    fake_ops.install(monkeypatch)
+    rng = np.random.default_rng(2)
+    X = torch.tensor(np.concatenate([rng.uniform(-1, 1, size=(40, 3)), np.ones((40, 1))], 1))
+    y = torch.tensor(rng.normal(size=(40, 1)))
+    tn = tnb.TensorTrainLayer(4, 3, 4, output_shape=1, constrict_bond=False, seed=1).tensor_network
+    tn.accumulating_swipe(X, y, tnb.SquareBregFunction(), method="ridge_cholesky", eps=1.0, num_swipes=1)
+    fresh = tnb.TensorTrainLayer(4, 3, 4, output_shape=1, constrict_bond=False, seed=1).tensor_network
+    node = tn.main_nodes[1]
+    node.tensor.mul_(1.25)
+    tn.left_update_stacks(node)
+    tn.right_update_stacks(node)
+    for a, b in zip(fresh.main_nodes, tn.main_nodes):
+        a.tensor = b.tensor.clone()
+    assert float((tn.forward(X, to_tensor=True) - fresh.forward(X, to_tensor=True)).abs().max()) < 1e-13
+    tn.recompute_all_stacks()
+    assert float((tn.forward(X, to_tensor=True) - fresh.forward(X, to_tensor=True)).abs().max()) < 1e-13
+    tnb.CPDLayer(3, 2, 4, output_shape=(1,), seed=1).tensor_network.recompute_all_stacks()
